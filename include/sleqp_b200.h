@@ -1,0 +1,179 @@
+/*
+ * sleqp_b200.h -- C-ABI of libsleqp_b200.so, the B200-native sparse KKT backend for SLEQP.
+ *
+ * Plain C types only (no C++/torch types): this header is what the C11 host glue
+ * `sleqp_b200/host/fact_b200.c` includes, exactly like fact_umfpack.c includes <umfpack.h>.
+ *
+ * Each entry point names the reference interface it stands behind (paths relative to the
+ * reference tree, chrhansk/sleqp v1.0.2):
+ *
+ *   SleqpFactCallbacks.set_matrix   src/main/fact/fact_types.h:9-10,  fact.c:59-75,
+ *                                   backend example fact_umfpack.c:119-183
+ *   SleqpFactCallbacks.solve        fact_types.h:12,  fact.c:83-89,   fact_umfpack.c:207-233
+ *   SleqpFactCallbacks.solution     fact_types.h:14-18, fact.c:91-102, fact_umfpack.c:245-262
+ *   SleqpFactCallbacks.condition    fact_types.h:20-21, fact.c:104-118, fact_cholmod.c:197-209
+ *   SleqpFactCallbacks.free         fact_types.h:23,  fact.c:128-141, fact_umfpack.c:264-284
+ *   sleqp_mat_mult_vec              src/main/sparse/mat.c:282-310
+ *   sleqp_mat_mult_vec_trans        src/main/sparse/mat.c:312-363
+ *
+ * There is NO CPU fallback: every function that computes returns B200_ERR_CUDA when no
+ * device is usable. Only the b200_symbolic_* entry points (host-side analysis, which the
+ * north-star keeps on the host) work without a GPU.
+ *
+ * All functions return 0 (B200_OK) on success, non-zero on failure; b200_last_error()
+ * returns a thread-local message for the last failing call on this thread (the glue turns
+ * it into sleqp_raise(SLEQP_INTERNAL_ERROR, ...), pub_error.h:38-48).
+ */
+#ifndef SLEQP_B200_H
+#define SLEQP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_VERSION_STRING "0.1.0"
+
+enum
+{
+  B200_OK              = 0,
+  B200_ERR_ARG         = 1, /* malformed input (dims, unsorted rows, ...) */
+  B200_ERR_CUDA        = 2, /* no device / CUDA runtime failure */
+  B200_ERR_SINGULAR    = 3, /* numerically singular KKT (Umfpack convention: error, fact_umfpack.c:66-82) */
+  B200_ERR_UNSUPPORTED = 4, /* structure outside the supported class (off-diagonal (1,1) block) */
+  B200_ERR_STATE       = 5  /* call protocol violated (solve before set_matrix, ...) */
+};
+
+typedef struct b200_fact b200_fact; /* opaque factorization handle (one per SleqpFact) */
+typedef struct b200_mat b200_mat;   /* opaque device CSC matrix (one per SleqpMat used for SpMV) */
+
+/* Statistics for parity checks and roofline arithmetic. */
+typedef struct b200_stats
+{
+  int32_t n;               /* order of K */
+  int32_t n_elim;          /* diagonal (variable) nodes eliminated in closed form */
+  int32_t n_reduced;       /* nodes of the Schur system S (constraints) */
+  int64_t nnz_K;           /* stored entries of tril(K) */
+  int64_t nnz_S;           /* entries of tril(S) */
+  int64_t nnz_L;           /* exact nnz(L_S) incl. diagonal = sum of column counts */
+  int64_t nnz_L_stored;    /* entries of the dense supernodal panels (>= nnz_L) */
+  int64_t n_row_idx;       /* sum over supernodes of update rows */
+  int32_t n_supernodes;
+  int32_t n_levels;        /* supernodal etree height (solve levels) */
+  int32_t n_stages;        /* numeric factorization stages */
+  int32_t max_front;       /* largest front order k+r */
+  double flops_factor;     /* sum_j cc_j^2 (exact structure) */
+  double flops_factor_stored; /* flops actually executed on the padded panels */
+  int64_t update_ws_doubles;  /* high-water mark of the update-matrix workspace */
+  uint64_t pattern_hash;
+  uint64_t perm_hash;      /* FNV-1a over the full permutation of K */
+  int32_t symbolic_cached; /* 1 if the last set_matrix reused a cached analysis */
+  int32_t n_perturbed;     /* pivots replaced by the static-pivot threshold */
+  int32_t refine_steps;    /* refinement steps each solve performs for this factor */
+  double probe_residual;   /* ||K x - b|| / ||b|| of the probe solve after refinement */
+  double ms_symbolic;      /* host wall time of the analysis (0 when cached) */
+  double ms_numeric;       /* device time of the last numeric factorization (CUDA events) */
+  double ms_solve;         /* device time of the last solve (CUDA events) */
+} b200_stats;
+
+/* ---- factorization plugin (SleqpFactCallbacks) --------------------------------------- */
+
+/* device = -1: use B200_DEVICE from the environment, else LOCAL_RANK, else 0. */
+int b200_fact_create(b200_fact** handle, int device);
+
+/* K given as CSC (colptr[n_cols+1], rowidx[nnz] strictly increasing per column, val[nnz]),
+ * lower triangle incl. diagonal when lower_only != 0 (SLEQP_FACT_FLAGS_LOWER), otherwise the
+ * full symmetric matrix (strictly upper entries are then ignored). Arrays are borrowed for the
+ * duration of the call only. Looks up / builds the cached symbolic analysis, uploads the
+ * values and runs the numeric LDL^T on the device. */
+int b200_fact_set_matrix(b200_fact* handle,
+                         int n_rows,
+                         int n_cols,
+                         int nnz,
+                         const int* colptr,
+                         const int* rowidx,
+                         const double* val,
+                         int lower_only);
+
+/* Solve K x = b for a sparse right-hand side (idx ascending, dim == n). The result stays in
+ * device memory inside the handle (like `umfpack->solution`). */
+int b200_fact_solve(b200_fact* handle, int nnz_rhs, const int* idx, const double* val, int dim);
+
+/* Copy x[begin:end) of the last solve into out_dense (host memory, end-begin doubles). */
+int b200_fact_solution(b200_fact* handle, int begin, int end, double* out_dense);
+
+/* Same, but returns a pointer into the handle's pinned staging buffer (valid until the next
+ * call on this handle) -- saves one host memcpy in the glue. */
+int b200_fact_solution_ptr(b200_fact* handle, int begin, int end, const double** out);
+
+/* Device-resident variants used by the benchmark's "inputs already in HBM" leg and by a
+ * device-resident CG: d_rhs and d_sol are device pointers to n doubles. */
+int b200_fact_solve_device(b200_fact* handle, const double* d_rhs, double* d_sol);
+
+/* rcond = min|d_i| / max|d_i| over the pivots of D (cf. cholmod_l_rcond, fact_cholmod.c:204). */
+int b200_fact_rcond(b200_fact* handle, double* rcond);
+
+int b200_fact_stats(b200_fact* handle, b200_stats* stats);
+
+/* Structural outputs of the cached analysis, for parity tests. Every array is optional (NULL
+ * = skip). perm[n]: position p of the factorization holds K index perm[p]; parent[n]:
+ * elimination tree of P K P^T (-1 = root); colcount[n]: column counts of L incl. diagonal;
+ * super_first[n_supernodes_total+1] over the full order (variables are 1x1 supernodes). */
+int b200_fact_structure(b200_fact* handle, int* perm, int* parent, int* colcount, int* n_super_total, int* super_first);
+
+/* Debug/parity: copy the dense pivots D (n doubles, factorization order) to the host. */
+int b200_fact_pivots(b200_fact* handle, double* d_out);
+
+/* CUDA stream the handle launches on (cudaStream_t as void*), for event timing by callers. */
+void* b200_fact_stream(b200_fact* handle);
+
+int b200_fact_free(b200_fact** handle);
+
+const char* b200_last_error(void);
+
+/* ---- host-only symbolic analysis (no GPU needed) -------------------------------------- */
+
+typedef struct b200_symbolic b200_symbolic;
+
+int b200_symbolic_analyze(b200_symbolic** out,
+                          int n,
+                          int nnz,
+                          const int* colptr,
+                          const int* rowidx,
+                          const double* val,
+                          int lower_only);
+int b200_symbolic_stats(const b200_symbolic* s, b200_stats* stats);
+int b200_symbolic_structure(const b200_symbolic* s, int* perm, int* parent, int* colcount, int* n_super_total, int* super_first);
+/* Export of the numeric plan (reduced system) for the CPU emulation used in tests:
+ * query sizes with all pointers NULL first. See sleqp_b200/fact.py for the field list. */
+int b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64_t* count);
+int b200_symbolic_free(b200_symbolic** s);
+
+/* ---- CSC SpMV / SpMV^T (sleqp_mat_mult_vec / sleqp_mat_mult_vec_trans) ---------------- */
+
+int b200_mat_create(b200_mat** handle, int device);
+/* Upload a CSC matrix (same layout as SleqpMat: cols[num_cols+1], rows[nnz], data[nnz]). A
+ * CSR mirror for the gather-form y = A x is built on the host when the pattern changes. */
+int b200_mat_set(b200_mat* handle, int num_rows, int num_cols, int nnz, const int* cols, const int* rows, const double* data);
+/* result[num_rows] = A * x, x sparse (mat.c:282-310). */
+int b200_mat_mult_vec(b200_mat* handle, int nnz_x, const int* idx, const double* val, double* result_dense);
+/* result[num_cols] = A^T * v, v sparse; dense result, the glue drops |s| <= eps (mat.c:312-363). */
+int b200_mat_mult_vec_trans(b200_mat* handle, int nnz_v, const int* idx, const double* val, double* result_dense);
+/* Device-resident forms: d_x/d_y dense device vectors. */
+int b200_mat_mult_vec_device(b200_mat* handle, const double* d_x, double* d_y);
+int b200_mat_mult_vec_trans_device(b200_mat* handle, const double* d_v, double* d_y);
+void* b200_mat_stream(b200_mat* handle);
+int b200_mat_free(b200_mat** handle);
+
+/* ---- misc ------------------------------------------------------------------------------ */
+int b200_device_count(void);
+/* Number of kernel launches issued by this library on this process so far (bench.py's
+ * "gpu_launches" claim; graph replays count their kernel nodes). */
+int64_t b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SLEQP_B200_H */

@@ -1,0 +1,263 @@
+// capi_symbolic.cpp -- host-only C-ABI entry points (symbolic analysis, plan cache, errors).
+#include "common.hpp"
+
+#include <cstring>
+#include <list>
+#include <mutex>
+
+namespace b200
+{
+
+thread_local std::string g_last_error;
+
+int
+set_error(int code, const std::string& msg)
+{
+  g_last_error = msg;
+  return code;
+}
+
+// Process-wide pattern-keyed cache of analyses (north-star: "done once per sparsity pattern and
+// cached across SQP iterations"). Plans are immutable, so handles on different threads/devices
+// share them read-only.
+namespace
+{
+std::mutex g_cache_mutex;
+std::list<std::shared_ptr<const Plan>> g_cache; // most recently used first
+constexpr size_t CACHE_CAPACITY = 16;
+} // namespace
+
+int
+get_plan(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only, std::shared_ptr<const Plan>& out, bool& cached)
+{
+  if (n < 0 || nnz < 0 || !colptr || colptr[0] != 0 || colptr[n] != nnz)
+  {
+    return set_error(B200_ERR_ARG, "malformed CSC header");
+  }
+  const uint64_t h = hash_pattern(n, nnz, colptr, rowidx, val, lower_only);
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
+    {
+      if ((*it)->pattern_hash == h && (*it)->N == n)
+      {
+        out = *it;
+        g_cache.splice(g_cache.begin(), g_cache, it);
+        cached = true;
+        return B200_OK;
+      }
+    }
+  }
+  auto plan = std::make_shared<Plan>();
+  std::string err;
+  int rc = analyze(n, nnz, colptr, rowidx, val, lower_only, *plan, err);
+  if (rc != B200_OK)
+  {
+    return set_error(rc, err);
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    g_cache.push_front(plan);
+    while (g_cache.size() > CACHE_CAPACITY)
+    {
+      g_cache.pop_back();
+    }
+  }
+  out    = plan;
+  cached = false;
+  return B200_OK;
+}
+
+void
+fill_stats_from_plan(const Plan& P, b200_stats* s)
+{
+  std::memset(s, 0, sizeof(*s));
+  s->n                   = P.N;
+  s->n_elim              = P.nE;
+  s->n_reduced           = P.m;
+  s->nnz_K               = P.nnzK;
+  s->nnz_S               = P.nnzS;
+  s->nnz_L               = P.nnzL;
+  s->nnz_L_stored        = P.nnzL_stored;
+  s->n_row_idx           = (int64_t)P.Ridx.size();
+  s->n_supernodes        = P.nsuper;
+  s->n_levels            = P.nlevels;
+  s->n_stages            = (int)P.stages.size();
+  s->max_front           = P.max_front;
+  s->flops_factor        = P.flops;
+  s->flops_factor_stored = P.flops_stored;
+  s->update_ws_doubles   = P.Utotal;
+  s->pattern_hash        = P.pattern_hash;
+  s->perm_hash           = P.perm_hash;
+  s->ms_symbolic         = P.ms_symbolic;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+struct b200_symbolic
+{
+  std::shared_ptr<const Plan> plan;
+  bool cached;
+};
+
+namespace
+{
+template <typename T>
+int
+export_vec(const std::vector<T>& v, void* out, int64_t* count)
+{
+  if (count)
+  {
+    *count = (int64_t)v.size();
+  }
+  if (out && !v.empty())
+  {
+    std::memcpy(out, v.data(), sizeof(T) * v.size());
+  }
+  return B200_OK;
+}
+} // namespace
+
+extern "C" {
+
+const char*
+b200_last_error(void)
+{
+  return g_last_error.c_str();
+}
+
+int
+b200_symbolic_analyze(b200_symbolic** out, int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only)
+{
+  if (!out)
+  {
+    return set_error(B200_ERR_ARG, "null output handle");
+  }
+  *out = nullptr;
+  // Always analyse afresh here (this entry point exists for tests and timing of the analysis);
+  // b200_fact_set_matrix goes through the cache.
+  auto plan = std::make_shared<Plan>();
+  std::string err;
+  int rc = analyze(n, nnz, colptr, rowidx, val, lower_only, *plan, err);
+  if (rc != B200_OK)
+  {
+    return set_error(rc, err);
+  }
+  *out = new b200_symbolic{plan, false};
+  return B200_OK;
+}
+
+int
+b200_symbolic_stats(const b200_symbolic* s, b200_stats* stats)
+{
+  if (!s || !stats)
+  {
+    return set_error(B200_ERR_ARG, "null argument");
+  }
+  fill_stats_from_plan(*s->plan, stats);
+  return B200_OK;
+}
+
+int
+b200_symbolic_structure(const b200_symbolic* s, int* perm, int* parent, int* colcount, int* n_super_total, int* super_first)
+{
+  if (!s)
+  {
+    return set_error(B200_ERR_ARG, "null argument");
+  }
+  full_structure(*s->plan, perm, parent, colcount, n_super_total, super_first);
+  return B200_OK;
+}
+
+
+// Field list (element type): see sleqp_b200/fact.py PLAN_FIELDS.
+int
+b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64_t* count)
+{
+  if (!s || !field)
+  {
+    return set_error(B200_ERR_ARG, "null argument");
+  }
+  const Plan& P = *s->plan;
+  const std::string f(field);
+#define FIELD(name)                                                                                                     \
+  if (f == #name)                                                                                                       \
+  {                                                                                                                     \
+    return export_vec(P.name, out, count);                                                                              \
+  }
+  FIELD(e_of_k)
+  FIELD(r_of_k)
+  FIELD(k_of_e)
+  FIELD(k_of_r)
+  FIELD(dE_src)
+  FIELD(Acsc_ptr)
+  FIELD(Acsc_row)
+  FIELD(Acsc_src)
+  FIELD(Acsr_ptr)
+  FIELD(Acsr_col)
+  FIELD(Acsr_src)
+  FIELD(Gsym_ptr)
+  FIELD(Gsym_col)
+  FIELD(Gsym_src)
+  FIELD(perm)
+  FIELD(pinv)
+  FIELD(parent)
+  FIELD(colcount)
+  FIELD(sn_first)
+  FIELD(sn_of_col)
+  FIELD(sn_parent)
+  FIELD(sn_level)
+  FIELD(Rptr)
+  FIELD(Ridx)
+  FIELD(rel)
+  FIELD(Lptr)
+  FIELD(Wptr)
+  FIELD(child_ptr)
+  FIELD(child_idx)
+  FIELD(Sdest)
+  FIELD(Sgsrc)
+  FIELD(Sterm_ptr)
+  FIELD(Sterm_a)
+  FIELD(Sterm_b)
+  FIELD(Sterm_d)
+  FIELD(Uoff)
+  FIELD(sn_base)
+  FIELD(sn_nt)
+  FIELD(zero_sn)
+  FIELD(lvl_ptr)
+  FIELD(lvl_sn)
+#undef FIELD
+  if (f == "stages")
+  {
+    static_assert(sizeof(Stage) == 8 * sizeof(int), "Stage layout");
+    return export_vec(P.stages, out, count);
+  }
+  if (f == "ea_tasks")
+  {
+    return export_vec(P.ea_tasks, out, count);
+  }
+  if (f == "pan_tasks")
+  {
+    return export_vec(P.pan_tasks, out, count);
+  }
+  if (f == "upd_tasks")
+  {
+    return export_vec(P.upd_tasks, out, count);
+  }
+  return set_error(B200_ERR_ARG, "unknown plan field: " + f);
+}
+
+int
+b200_symbolic_free(b200_symbolic** s)
+{
+  if (s && *s)
+  {
+    delete *s;
+    *s = nullptr;
+  }
+  return B200_OK;
+}
+
+} // extern "C"

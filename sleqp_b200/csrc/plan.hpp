@@ -1,0 +1,126 @@
+// plan.hpp -- the cached symbolic analysis ("plan") shared by the host analysis and the
+// device numeric/solve code. One Plan per sparsity pattern of tril(K); immutable once built.
+//
+// K = [D  A^T; A  G]  (reference: standard_aug_jac.c:135-237 builds it with D = I, G = 0)
+//   E-nodes: columns with a non-zero diagonal and no off-diagonal coupling to other E-nodes
+//            (the variables). They are eliminated in closed form (pivot d_e, L-column = A(:,e)/d_e).
+//   R-nodes: the rest (working-set rows). The Schur system S = G - A D^-1 A^T on them is
+//            factored by a supernodal multifrontal LDL^T.
+// Full factorization order of K: [E-nodes in natural order | R-nodes in fill-reducing order],
+// i.e. every constraint is eliminated after all variables it touches (SURVEY.md hard part 1).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace b200
+{
+
+typedef int64_t i64;
+
+constexpr int NB       = 32;  // panel width of the blocked dense LDL^T
+constexpr int RB       = 128; // rows per TRSM row-block CTA
+constexpr int TILE     = 64;  // output tile edge of the DMMA update kernel
+constexpr int EA_COLS  = 16;  // update-matrix columns per extend-add task
+constexpr int LEAF_MAX = 32;  // etree subtrees up to this many columns become one dense supernode
+
+// kinds of update tasks
+enum
+{
+  UPD_INPANEL  = 0, // trailing update inside the supernode's own panel
+  UPD_SCHUR    = 1, // U -= L21 D L21^T over the whole supernode width (last step only)
+  UPD_DIAGCOPY = 2  // copy the factored diagonal block back from scratch
+};
+
+struct Task5
+{
+  int sn, t, kind, i0, j0;
+};
+
+struct PanelTask
+{
+  int sn, t, rb, slot; // slot < 0: single row block, factor the diagonal block in place
+};
+
+struct EaTask
+{
+  int child, jb;
+};
+
+struct Stage
+{
+  int zero_begin, zero_end;
+  int ea_begin, ea_end;
+  int pan_begin, pan_end;
+  int upd_begin, upd_end;
+};
+
+struct Plan
+{
+  int N = 0, nE = 0, m = 0;
+  i64 nnzK = 0;
+  uint64_t pattern_hash = 0, perm_hash = 0;
+
+  // node classification / index maps
+  std::vector<int> e_of_k, r_of_k, k_of_e, k_of_r;
+  std::vector<int> dE_src;                       // K-value index of d_e
+  std::vector<int> Acsc_ptr, Acsc_row, Acsc_src; // by E column; rows = original R index
+  std::vector<int> Acsr_ptr, Acsr_col, Acsr_src; // by R row (original index); cols = E index
+  std::vector<int> Gsym_ptr, Gsym_col, Gsym_src; // symmetric R-R coupling by R row (original)
+
+  // ordering of the reduced system
+  std::vector<int> perm, pinv; // new -> old R index, old -> new
+  std::vector<int> parent, colcount;
+
+  // supernodes
+  int nsuper = 0;
+  std::vector<int> sn_first; // nsuper+1
+  std::vector<int> sn_of_col;
+  std::vector<int> sn_parent, sn_level;
+  std::vector<i64> Rptr; // nsuper+1, offsets into Ridx/rel
+  std::vector<int> Ridx; // update rows (new labels), ascending
+  std::vector<int> rel;  // position of each update row in the parent's front
+  std::vector<i64> Lptr; // nsuper+1, panel offsets (doubles); panel is h x k column-major
+  std::vector<i64> Wptr; // nsuper+1, prefix sum of front heights (solve front vectors)
+  std::vector<int> child_ptr, child_idx;
+
+  // assembly of S straight into the panels: S_e = val[gsrc] - sum_t val[a]*val[b]/val[d]
+  i64 nnzS = 0;
+  std::vector<i64> Sdest;
+  std::vector<int> Sgsrc;
+  std::vector<i64> Sterm_ptr;
+  std::vector<int> Sterm_a, Sterm_b, Sterm_d;
+
+  // update-matrix workspace (lifetime-packed)
+  std::vector<i64> Uoff;
+  i64 Utotal = 0;
+
+  // numeric schedule
+  std::vector<int> sn_base, sn_nt;
+  std::vector<Stage> stages;
+  std::vector<int> zero_sn;
+  std::vector<EaTask> ea_tasks;
+  std::vector<PanelTask> pan_tasks;
+  std::vector<Task5> upd_tasks;
+  int n_scratch_slots = 0;
+
+  // solve schedule (levels of the supernodal tree)
+  int nlevels = 0;
+  std::vector<int> lvl_ptr, lvl_sn;
+
+  // statistics
+  i64 nnzL = 0, nnzL_stored = 0;
+  double flops = 0, flops_stored = 0;
+  int max_front = 0;
+  double ms_symbolic = 0;
+};
+
+// Builds the plan. Returns 0 or a B200_ERR_* code with a message in err.
+int analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only, Plan& plan, std::string& err);
+
+uint64_t hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only);
+
+// Expands (perm, parent, colcount, supernodes) of the reduced system to the full order of K.
+void full_structure(const Plan& p, int* perm, int* parent, int* colcount, int* n_super_total, int* super_first);
+
+} // namespace b200

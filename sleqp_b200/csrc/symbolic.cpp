@@ -1,0 +1,1403 @@
+// symbolic.cpp -- host-side symbolic analysis, done once per sparsity pattern and cached
+// (north-star subsystem 1: ordering, elimination tree, supernode amalgamation).
+//
+// No reference backend has an equivalent: Umfpack/CHOLMOD redo their analysis inside the
+// vendor library on every set_matrix (fact_umfpack.c:139-160, fact_cholmod.c:133). The
+// algorithms here are the published ones: George's automatic nested dissection on level
+// structures, Liu's elimination tree with path compression, the Gilbert-Ng-Peyton column
+// counts, fundamental supernodes plus relaxed amalgamation.
+#include "plan.hpp"
+
+#include "../../include/sleqp_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <numeric>
+
+namespace b200
+{
+
+static inline uint64_t
+fnv1a(uint64_t h, const void* data, size_t bytes)
+{
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < bytes; ++i)
+  {
+    h ^= p[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+uint64_t
+hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only)
+{
+  uint64_t h = 14695981039346656037ull;
+  int hdr[3] = {n, nnz, lower_only ? 1 : 0};
+  h          = fnv1a(h, hdr, sizeof(hdr));
+  h          = fnv1a(h, colptr, sizeof(int) * (size_t)(n + 1));
+  h          = fnv1a(h, rowidx, sizeof(int) * (size_t)nnz);
+  // the E/R classification depends on which diagonals are non-zero: part of the key
+  std::vector<unsigned char> dz((size_t)n, 0);
+  for (int j = 0; j < n; ++j)
+  {
+    for (int p = colptr[j]; p < colptr[j + 1]; ++p)
+    {
+      if (rowidx[p] == j && val[p] != 0.)
+      {
+        dz[j] = 1;
+      }
+    }
+  }
+  h = fnv1a(h, dz.data(), dz.size());
+  return h;
+}
+
+// ---------------------------------------------------------------------------------------
+// Nested dissection on rooted level structures (George 1973; George & Liu 1978).
+// ---------------------------------------------------------------------------------------
+namespace
+{
+
+struct Graph
+{
+  int n;
+  const std::vector<int>& xadj;
+  const std::vector<int>& adj;
+};
+
+struct NDWork
+{
+  std::vector<int> tag;   // subproblem id a node currently belongs to
+  std::vector<int> level; // BFS level
+  std::vector<int> seen;  // BFS visit stamp
+  std::vector<int> queue;
+  int stamp = 0;
+};
+
+// BFS restricted to nodes with tag == id, starting from root. Returns number of levels; fills
+// w.queue with the visit order (first `count` entries) and w.level.
+static int
+bfs(const Graph& g, NDWork& w, int root, int id, int& count, std::vector<int>& level_ptr)
+{
+  ++w.stamp;
+  int head = 0, tail = 0;
+  w.queue[tail++] = root;
+  w.seen[root]    = w.stamp;
+  w.level[root]   = 0;
+  level_ptr.clear();
+  level_ptr.push_back(0);
+  int cur_level = 0;
+  while (head < tail)
+  {
+    int v = w.queue[head];
+    if (w.level[v] != cur_level)
+    {
+      cur_level = w.level[v];
+      level_ptr.push_back(head);
+    }
+    ++head;
+    for (int p = g.xadj[v]; p < g.xadj[v + 1]; ++p)
+    {
+      int u = g.adj[p];
+      if (w.tag[u] == id && w.seen[u] != w.stamp)
+      {
+        w.seen[u]       = w.stamp;
+        w.level[u]      = cur_level + 1;
+        w.queue[tail++] = u;
+      }
+    }
+  }
+  level_ptr.push_back(tail);
+  count = tail;
+  return (int)level_ptr.size() - 1;
+}
+
+struct Sub
+{
+  std::vector<int> nodes;
+  int lo; // nodes occupy perm[lo, lo + nodes.size())
+  bool connected;
+};
+
+} // namespace
+
+static void
+nested_dissection(int m, const std::vector<int>& xadj, const std::vector<int>& adj, int leaf_size, std::vector<int>& perm)
+{
+  Graph g{m, xadj, adj};
+  NDWork w;
+  w.tag.assign(m, 0);
+  w.level.assign(m, 0);
+  w.seen.assign(m, 0);
+  w.queue.assign(m, 0);
+  perm.assign(m, -1);
+
+  std::vector<Sub> stack;
+  {
+    Sub root;
+    root.nodes.resize(m);
+    std::iota(root.nodes.begin(), root.nodes.end(), 0);
+    root.lo        = 0;
+    root.connected = false;
+    stack.push_back(std::move(root));
+  }
+  int next_id = 1;
+  std::vector<int> level_ptr;
+
+  while (!stack.empty())
+  {
+    Sub sub = std::move(stack.back());
+    stack.pop_back();
+    const int ns = (int)sub.nodes.size();
+    if (ns == 0)
+    {
+      continue;
+    }
+    const int id = next_id++;
+    for (int v : sub.nodes)
+    {
+      w.tag[v] = id;
+    }
+
+    if (!sub.connected)
+    {
+      // split into connected components; each gets a consecutive range
+      int lo = sub.lo;
+      ++w.stamp;
+      const int comp_stamp = w.stamp;
+      std::vector<int> comp_mark; // reuse seen[] through separate BFS calls: need own marker
+      // We cannot use w.seen across bfs() calls (stamp changes), so keep a local flag array
+      // indexed by position in sub.nodes via tag trick: move processed nodes to tag = -id.
+      (void)comp_stamp;
+      std::vector<Sub> comps;
+      for (int v : sub.nodes)
+      {
+        if (w.tag[v] != id)
+        {
+          continue;
+        }
+        int cnt;
+        bfs(g, w, v, id, cnt, level_ptr);
+        Sub c;
+        c.nodes.assign(w.queue.begin(), w.queue.begin() + cnt);
+        c.connected = true;
+        c.lo        = lo;
+        lo += cnt;
+        for (int u : c.nodes)
+        {
+          w.tag[u] = -id; // taken
+        }
+        comps.push_back(std::move(c));
+      }
+      if (comps.size() == 1)
+      {
+        // re-tag and fall through to the connected case
+        sub = std::move(comps[0]);
+        for (int u : sub.nodes)
+        {
+          w.tag[u] = id;
+        }
+      }
+      else
+      {
+        for (auto& c : comps)
+        {
+          if ((int)c.nodes.size() <= leaf_size)
+          {
+            for (size_t i = 0; i < c.nodes.size(); ++i)
+            {
+              perm[c.lo + (int)i] = c.nodes[i]; // BFS order
+            }
+          }
+          else
+          {
+            stack.push_back(std::move(c));
+          }
+        }
+        continue;
+      }
+    }
+
+    // connected subgraph
+    if (ns <= leaf_size)
+    {
+      int cnt;
+      bfs(g, w, sub.nodes[0], id, cnt, level_ptr);
+      for (int i = 0; i < cnt; ++i)
+      {
+        perm[sub.lo + i] = w.queue[i];
+      }
+      continue;
+    }
+
+    // pseudo-peripheral root
+    int root = sub.nodes[0];
+    int cnt;
+    int nlev = bfs(g, w, root, id, cnt, level_ptr);
+    for (int iter = 0; iter < 6; ++iter)
+    {
+      // pick a minimum-degree node of the last level
+      int best = -1, bestdeg = 0x7fffffff;
+      for (int q = level_ptr[nlev - 1]; q < level_ptr[nlev]; ++q)
+      {
+        int v   = w.queue[q];
+        int deg = g.xadj[v + 1] - g.xadj[v];
+        if (deg < bestdeg)
+        {
+          bestdeg = deg;
+          best    = v;
+        }
+      }
+      std::vector<int> lp2;
+      int cnt2;
+      int nlev2 = bfs(g, w, best, id, cnt2, lp2);
+      if (nlev2 > nlev)
+      {
+        root      = best;
+        nlev      = nlev2;
+        level_ptr = lp2;
+        cnt       = cnt2;
+      }
+      else
+      {
+        // restore the level structure of `root`
+        nlev = bfs(g, w, root, id, cnt, level_ptr);
+        break;
+      }
+    }
+
+    if (nlev < 3)
+    {
+      // no interior level: cannot be separated by a level set; emit as one block
+      for (int i = 0; i < cnt; ++i)
+      {
+        perm[sub.lo + i] = w.queue[i];
+      }
+      continue;
+    }
+
+    // choose the separator level: smallest level among the balanced ones
+    int s = -1;
+    {
+      const double lo_frac = 0.3;
+      int best_size        = 0x7fffffff;
+      int median_level     = 1;
+      for (int l = 0; l < nlev; ++l)
+      {
+        if (level_ptr[l] <= ns / 2 && ns / 2 < level_ptr[l + 1])
+        {
+          median_level = l;
+        }
+      }
+      median_level = std::min(std::max(median_level, 1), nlev - 2);
+      for (int l = 1; l <= nlev - 2; ++l)
+      {
+        int below = level_ptr[l];
+        int above = ns - level_ptr[l + 1];
+        if (below >= lo_frac * ns && above >= lo_frac * ns)
+        {
+          int size = level_ptr[l + 1] - level_ptr[l];
+          if (size < best_size || (size == best_size && std::abs(l - median_level) < std::abs(s - median_level)))
+          {
+            best_size = size;
+            s         = l;
+          }
+        }
+      }
+      if (s < 0)
+      {
+        s = median_level;
+      }
+    }
+
+    // thin the separator: level-s nodes without a neighbour in level s+1 join part A
+    Sub A, B;
+    std::vector<int> sep;
+    for (int q = 0; q < level_ptr[s]; ++q)
+    {
+      A.nodes.push_back(w.queue[q]);
+    }
+    for (int q = level_ptr[s]; q < level_ptr[s + 1]; ++q)
+    {
+      int v         = w.queue[q];
+      bool touchesB = false;
+      for (int p = g.xadj[v]; p < g.xadj[v + 1] && !touchesB; ++p)
+      {
+        int u = g.adj[p];
+        if (w.tag[u] == id && w.level[u] == s + 1)
+        {
+          touchesB = true;
+        }
+      }
+      if (touchesB)
+      {
+        sep.push_back(v);
+      }
+      else
+      {
+        A.nodes.push_back(v);
+      }
+    }
+    for (int q = level_ptr[s + 1]; q < cnt; ++q)
+    {
+      B.nodes.push_back(w.queue[q]);
+    }
+    // separator last
+    const int hi = sub.lo + ns;
+    for (size_t i = 0; i < sep.size(); ++i)
+    {
+      perm[hi - (int)sep.size() + (int)i] = sep[i];
+    }
+    A.lo        = sub.lo;
+    A.connected = false;
+    B.lo        = sub.lo + (int)A.nodes.size();
+    B.connected = false;
+    stack.push_back(std::move(A));
+    stack.push_back(std::move(B));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+
+static int
+fail(std::string& err, int code, const std::string& msg)
+{
+  err = msg;
+  return code;
+}
+
+int
+analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only, Plan& P, std::string& err)
+{
+  auto t0 = std::chrono::steady_clock::now();
+  if (n < 0 || nnz < 0 || !colptr || (nnz > 0 && (!rowidx || !val)))
+  {
+    return fail(err, B200_ERR_ARG, "null or negative-sized input");
+  }
+  if (colptr[0] != 0 || colptr[n] != nnz)
+  {
+    return fail(err, B200_ERR_ARG, "colptr[0] must be 0 and colptr[n] == nnz");
+  }
+  P       = Plan();
+  P.N     = n;
+  P.nnzK  = 0;
+  P.pattern_hash = hash_pattern(n, nnz, colptr, rowidx, val, lower_only);
+
+  // ---- classification ----------------------------------------------------------------
+  std::vector<int> diag_src(n, -1);
+  for (int j = 0; j < n; ++j)
+  {
+    if (colptr[j + 1] < colptr[j])
+    {
+      return fail(err, B200_ERR_ARG, "colptr not monotone");
+    }
+    int prev = -1;
+    for (int p = colptr[j]; p < colptr[j + 1]; ++p)
+    {
+      int i = rowidx[p];
+      if (i < 0 || i >= n || i <= prev)
+      {
+        return fail(err, B200_ERR_ARG, "row indices must be in range and strictly increasing per column (mat.c:797-804)");
+      }
+      prev = i;
+      if (i < j)
+      {
+        if (lower_only)
+        {
+          return fail(err, B200_ERR_ARG, "entry above the diagonal in a matrix passed as lower-triangular");
+        }
+        continue;
+      }
+      ++P.nnzK;
+      if (i == j && val[p] != 0.)
+      {
+        diag_src[j] = p;
+      }
+    }
+  }
+  P.e_of_k.assign(n, -1);
+  P.r_of_k.assign(n, -1);
+  for (int j = 0; j < n; ++j)
+  {
+    if (diag_src[j] >= 0)
+    {
+      P.e_of_k[j] = P.nE++;
+      P.k_of_e.push_back(j);
+      P.dE_src.push_back(diag_src[j]);
+    }
+    else
+    {
+      P.r_of_k[j] = P.m++;
+      P.k_of_r.push_back(j);
+    }
+  }
+  const int nE = P.nE, m = P.m;
+
+  // ---- split tril(K) into A (R x E) and G (R x R) ---------------------------------------
+  struct Ent
+  {
+    int r, c, src;
+  };
+  std::vector<Ent> Aent, Gent;
+  for (int j = 0; j < n; ++j)
+  {
+    for (int p = colptr[j]; p < colptr[j + 1]; ++p)
+    {
+      int i = rowidx[p];
+      if (i < j)
+      {
+        continue;
+      }
+      if (i == j)
+      {
+        if (P.r_of_k[j] >= 0)
+        {
+          Gent.push_back({P.r_of_k[j], P.r_of_k[j], p}); // explicit zero diagonal
+        }
+        continue;
+      }
+      const bool jE = P.e_of_k[j] >= 0, iE = P.e_of_k[i] >= 0;
+      if (jE && iE)
+      {
+        return fail(err,
+                    B200_ERR_UNSUPPORTED,
+                    "off-diagonal entry inside the (1,1) block: the B200 backend factors K = [D A^T; A G] with diagonal D "
+                    "(what standard_aug_jac.c:160 builds)");
+      }
+      if (jE)
+      {
+        Aent.push_back({P.r_of_k[i], P.e_of_k[j], p});
+      }
+      else if (iE)
+      {
+        Aent.push_back({P.r_of_k[j], P.e_of_k[i], p});
+      }
+      else
+      {
+        int a = P.r_of_k[i], b = P.r_of_k[j];
+        Gent.push_back({std::max(a, b), std::min(a, b), p});
+      }
+    }
+  }
+  // A by column (E), rows ascending
+  std::sort(Aent.begin(), Aent.end(), [](const Ent& x, const Ent& y) { return x.c != y.c ? x.c < y.c : x.r < y.r; });
+  const int nnzA = (int)Aent.size();
+  P.Acsc_ptr.assign(nE + 1, 0);
+  P.Acsc_row.resize(nnzA);
+  P.Acsc_src.resize(nnzA);
+  for (const Ent& e : Aent)
+  {
+    ++P.Acsc_ptr[e.c + 1];
+  }
+  for (int e = 0; e < nE; ++e)
+  {
+    P.Acsc_ptr[e + 1] += P.Acsc_ptr[e];
+  }
+  for (int q = 0; q < nnzA; ++q)
+  {
+    P.Acsc_row[q] = Aent[q].r;
+    P.Acsc_src[q] = Aent[q].src;
+  }
+  // A by row (R)
+  P.Acsr_ptr.assign(m + 1, 0);
+  P.Acsr_col.resize(nnzA);
+  P.Acsr_src.resize(nnzA);
+  for (const Ent& e : Aent)
+  {
+    ++P.Acsr_ptr[e.r + 1];
+  }
+  for (int r = 0; r < m; ++r)
+  {
+    P.Acsr_ptr[r + 1] += P.Acsr_ptr[r];
+  }
+  {
+    std::vector<int> fill(P.Acsr_ptr.begin(), P.Acsr_ptr.end() - 1);
+    for (const Ent& e : Aent) // ascending (c, r) => columns ascending within each row
+    {
+      int q         = fill[e.r]++;
+      P.Acsr_col[q] = e.c;
+      P.Acsr_src[q] = e.src;
+    }
+  }
+  // G symmetric by row
+  {
+    P.Gsym_ptr.assign(m + 1, 0);
+    for (const Ent& e : Gent)
+    {
+      ++P.Gsym_ptr[e.r + 1];
+      if (e.r != e.c)
+      {
+        ++P.Gsym_ptr[e.c + 1];
+      }
+    }
+    for (int r = 0; r < m; ++r)
+    {
+      P.Gsym_ptr[r + 1] += P.Gsym_ptr[r];
+    }
+    P.Gsym_col.resize(P.Gsym_ptr[m]);
+    P.Gsym_src.resize(P.Gsym_ptr[m]);
+    std::vector<int> fill(P.Gsym_ptr.begin(), P.Gsym_ptr.end() - 1);
+    for (const Ent& e : Gent)
+    {
+      int q         = fill[e.r]++;
+      P.Gsym_col[q] = e.c;
+      P.Gsym_src[q] = e.src;
+      if (e.r != e.c)
+      {
+        q             = fill[e.c]++;
+        P.Gsym_col[q] = e.r;
+        P.Gsym_src[q] = e.src;
+      }
+    }
+  }
+
+  // ---- adjacency of S = G - A D^-1 A^T (original R labels) -----------------------------
+  {
+    double work = 0;
+    for (int e = 0; e < nE; ++e)
+    {
+      double q = P.Acsc_ptr[e + 1] - P.Acsc_ptr[e];
+      work += q * q;
+    }
+    if (work > 4e9)
+    {
+      return fail(err, B200_ERR_UNSUPPORTED, "a variable couples too many working-set rows: Schur pattern would exceed 4e9 entries");
+    }
+  }
+  std::vector<int> xadj(m + 1, 0), adj;
+  {
+    std::vector<int> mark(m, -1);
+    for (int r = 0; r < m; ++r)
+    {
+      mark[r] = r;
+      for (int q = P.Acsr_ptr[r]; q < P.Acsr_ptr[r + 1]; ++q)
+      {
+        int e = P.Acsr_col[q];
+        for (int s = P.Acsc_ptr[e]; s < P.Acsc_ptr[e + 1]; ++s)
+        {
+          int r2 = P.Acsc_row[s];
+          if (mark[r2] != r)
+          {
+            mark[r2] = r;
+            adj.push_back(r2);
+          }
+        }
+      }
+      for (int q = P.Gsym_ptr[r]; q < P.Gsym_ptr[r + 1]; ++q)
+      {
+        int r2 = P.Gsym_col[q];
+        if (mark[r2] != r)
+        {
+          mark[r2] = r;
+          adj.push_back(r2);
+        }
+      }
+      xadj[r + 1] = (int)adj.size();
+      if (adj.size() > (size_t)0x7ffffff0)
+      {
+        return fail(err, B200_ERR_UNSUPPORTED, "Schur pattern exceeds 2^31 entries");
+      }
+    }
+  }
+
+  // ---- fill-reducing ordering -----------------------------------------------------------
+  std::vector<int> perm0;
+  nested_dissection(m, xadj, adj, /*leaf_size=*/24, perm0);
+  std::vector<int> pinv0(m);
+  for (int k = 0; k < m; ++k)
+  {
+    pinv0[perm0[k]] = k;
+  }
+
+  // ---- elimination tree (Liu) -------------------------------------------------------------
+  std::vector<int> parent0(m, -1);
+  {
+    std::vector<int> anc(m, -1);
+    for (int k = 0; k < m; ++k)
+    {
+      int v = perm0[k];
+      for (int p = xadj[v]; p < xadj[v + 1]; ++p)
+      {
+        int i = pinv0[adj[p]];
+        while (i != -1 && i < k)
+        {
+          int inext = anc[i];
+          anc[i]    = k;
+          if (inext == -1)
+          {
+            parent0[i] = k;
+          }
+          i = inext;
+        }
+      }
+    }
+  }
+  // ---- postorder and relabel ------------------------------------------------------------------
+  std::vector<int> post(m);
+  {
+    std::vector<int> head(m, -1), next(m, -1), stk;
+    for (int j = m - 1; j >= 0; --j)
+    {
+      if (parent0[j] != -1)
+      {
+        next[j]          = head[parent0[j]];
+        head[parent0[j]] = j;
+      }
+    }
+    int k = 0;
+    for (int root = 0; root < m; ++root)
+    {
+      if (parent0[root] != -1)
+      {
+        continue;
+      }
+      stk.push_back(root);
+      while (!stk.empty())
+      {
+        int v = stk.back();
+        int c = head[v];
+        if (c == -1)
+        {
+          post[k++] = v;
+          stk.pop_back();
+        }
+        else
+        {
+          head[v] = next[c];
+          stk.push_back(c);
+        }
+      }
+    }
+  }
+  P.perm.resize(m);
+  P.pinv.resize(m);
+  P.parent.assign(m, -1);
+  {
+    std::vector<int> postinv(m);
+    for (int k = 0; k < m; ++k)
+    {
+      postinv[post[k]] = k;
+    }
+    for (int k = 0; k < m; ++k)
+    {
+      P.perm[k]         = perm0[post[k]];
+      P.pinv[P.perm[k]] = k;
+      int p0            = parent0[post[k]];
+      P.parent[k]       = p0 == -1 ? -1 : postinv[p0];
+    }
+  }
+  // adjacency in new labels
+  std::vector<int> xadj2(m + 1, 0), adj2(adj.size());
+  for (int k = 0; k < m; ++k)
+  {
+    int v        = P.perm[k];
+    xadj2[k + 1] = xadj2[k] + (xadj[v + 1] - xadj[v]);
+    int o        = xadj2[k];
+    for (int p = xadj[v]; p < xadj[v + 1]; ++p)
+    {
+      adj2[o++] = P.pinv[adj[p]];
+    }
+    std::sort(adj2.begin() + xadj2[k], adj2.begin() + xadj2[k + 1]);
+  }
+  std::vector<int>().swap(adj);
+
+  // ---- column counts (Gilbert, Ng, Peyton 1994) ------------------------------------------------
+  const std::vector<int>& parent = P.parent;
+  P.colcount.assign(m, 0);
+  {
+    std::vector<int> first(m, -1), maxfirst(m, -1), prevleaf(m, -1), ancestor(m);
+    std::vector<int>& delta = P.colcount;
+    for (int k = 0; k < m; ++k)
+    {
+      int j    = k;
+      delta[j] = (first[j] == -1) ? 1 : 0;
+      for (; j != -1 && first[j] == -1; j = parent[j])
+      {
+        first[j] = k;
+      }
+    }
+    std::iota(ancestor.begin(), ancestor.end(), 0);
+    for (int j = 0; j < m; ++j)
+    {
+      if (parent[j] != -1)
+      {
+        --delta[parent[j]];
+      }
+      for (int p = xadj2[j]; p < xadj2[j + 1]; ++p)
+      {
+        int i = adj2[p];
+        if (i <= j || first[j] <= maxfirst[i])
+        {
+          continue;
+        }
+        maxfirst[i] = first[j];
+        int jprev   = prevleaf[i];
+        prevleaf[i] = j;
+        if (jprev == -1)
+        {
+          ++delta[j];
+        }
+        else
+        {
+          int q = jprev;
+          while (q != ancestor[q])
+          {
+            q = ancestor[q];
+          }
+          for (int s = jprev; s != q;)
+          {
+            int sp      = ancestor[s];
+            ancestor[s] = q;
+            s           = sp;
+          }
+          ++delta[j];
+          --delta[q];
+        }
+      }
+      if (parent[j] != -1)
+      {
+        ancestor[j] = parent[j];
+      }
+    }
+    for (int j = 0; j < m; ++j)
+    {
+      if (parent[j] != -1)
+      {
+        delta[parent[j]] += delta[j];
+      }
+    }
+  }
+  const std::vector<int>& cc = P.colcount;
+
+  // ---- supernodes: dense leaf subtrees + fundamental + relaxed chains -----------------------------
+  std::vector<int> blk(m, -1);
+  {
+    std::vector<int> size(m, 1);
+    for (int j = 0; j < m; ++j)
+    {
+      if (parent[j] != -1)
+      {
+        size[parent[j]] += size[j];
+      }
+    }
+    for (int j = 0; j < m; ++j)
+    {
+      if (size[j] <= LEAF_MAX && size[j] > 1 && (parent[j] == -1 || size[parent[j]] > LEAF_MAX))
+      {
+        for (int c = j - size[j] + 1; c <= j; ++c)
+        {
+          blk[c] = j;
+        }
+      }
+    }
+  }
+  std::vector<char> join(std::max(m, 1), 0); // join[j]: j and j+1 share a supernode
+  if (m > 0)
+  {
+    int l         = m - 1;
+    i64 k         = 1;
+    i64 actual    = cc[l];
+    for (int j = m - 2; j >= 0; --j)
+    {
+      const bool forced = blk[j] != -1 && blk[j] == blk[j + 1];
+      const bool chain  = parent[j] == j + 1;
+      bool jn           = false;
+      if (forced || chain)
+      {
+        const i64 r       = cc[l] - 1;
+        const i64 kn      = k + 1;
+        const i64 stored  = kn * (kn + r) - kn * (kn - 1) / 2;
+        const i64 act     = actual + cc[j];
+        const bool fundam = chain && cc[j] == cc[j + 1] + 1;
+        jn                = forced || fundam || (chain && (kn <= 4 || (double)(stored - act) <= 0.2 * (double)stored));
+      }
+      if (jn)
+      {
+        join[j] = 1;
+        ++k;
+        actual += cc[j];
+      }
+      else
+      {
+        l      = j;
+        k      = 1;
+        actual = cc[j];
+      }
+    }
+  }
+  P.sn_of_col.assign(m, 0);
+  P.sn_first.clear();
+  for (int j = 0; j < m; ++j)
+  {
+    if (j == 0 || !join[j - 1])
+    {
+      P.sn_first.push_back(j);
+    }
+    P.sn_of_col[j] = (int)P.sn_first.size() - 1;
+  }
+  P.nsuper = (int)P.sn_first.size();
+  P.sn_first.push_back(m);
+  const int ns = P.nsuper;
+
+  // supernodal tree
+  P.sn_parent.assign(ns, -1);
+  for (int T = 0; T < ns; ++T)
+  {
+    int l = P.sn_first[T + 1] - 1;
+    if (parent[l] != -1)
+    {
+      P.sn_parent[T] = P.sn_of_col[parent[l]];
+    }
+  }
+  P.child_ptr.assign(ns + 1, 0);
+  for (int T = 0; T < ns; ++T)
+  {
+    if (P.sn_parent[T] >= 0)
+    {
+      ++P.child_ptr[P.sn_parent[T] + 1];
+    }
+  }
+  for (int T = 0; T < ns; ++T)
+  {
+    P.child_ptr[T + 1] += P.child_ptr[T];
+  }
+  P.child_idx.resize(P.child_ptr[ns]);
+  {
+    std::vector<int> fill(P.child_ptr.begin(), P.child_ptr.end() - 1);
+    for (int T = 0; T < ns; ++T)
+    {
+      if (P.sn_parent[T] >= 0)
+      {
+        P.child_idx[fill[P.sn_parent[T]]++] = T;
+      }
+    }
+  }
+
+  // ---- row structures ---------------------------------------------------------------------------------
+  P.Rptr.assign(ns + 1, 0);
+  P.Ridx.clear();
+  {
+    std::vector<int> mark(m, -1);
+    std::vector<int> rows;
+    for (int T = 0; T < ns; ++T)
+    {
+      const int f = P.sn_first[T], l = P.sn_first[T + 1] - 1;
+      rows.clear();
+      for (int j = f; j <= l; ++j)
+      {
+        for (int p = xadj2[j]; p < xadj2[j + 1]; ++p)
+        {
+          int i = adj2[p];
+          if (i > l && mark[i] != T)
+          {
+            mark[i] = T;
+            rows.push_back(i);
+          }
+        }
+      }
+      for (int q = P.child_ptr[T]; q < P.child_ptr[T + 1]; ++q)
+      {
+        int c = P.child_idx[q];
+        for (i64 p = P.Rptr[c]; p < P.Rptr[c + 1]; ++p)
+        {
+          int i = P.Ridx[p];
+          if (i > l && mark[i] != T)
+          {
+            mark[i] = T;
+            rows.push_back(i);
+          }
+        }
+      }
+      std::sort(rows.begin(), rows.end());
+      if ((int)rows.size() != cc[l] - 1)
+      {
+        return fail(err, B200_ERR_ARG, "internal: supernode row structure disagrees with the column count");
+      }
+      P.Ridx.insert(P.Ridx.end(), rows.begin(), rows.end());
+      P.Rptr[T + 1] = (i64)P.Ridx.size();
+    }
+  }
+  // relative indices into the parent's front
+  P.rel.assign(P.Ridx.size(), -1);
+  {
+    std::vector<int> pos(m, -1);
+    for (int T = 0; T < ns; ++T)
+    {
+      if (P.child_ptr[T] == P.child_ptr[T + 1])
+      {
+        continue;
+      }
+      const int f = P.sn_first[T], k = P.sn_first[T + 1] - f;
+      for (int c = 0; c < k; ++c)
+      {
+        pos[f + c] = c;
+      }
+      for (i64 p = P.Rptr[T]; p < P.Rptr[T + 1]; ++p)
+      {
+        pos[P.Ridx[p]] = k + (int)(p - P.Rptr[T]);
+      }
+      for (int q = P.child_ptr[T]; q < P.child_ptr[T + 1]; ++q)
+      {
+        int c = P.child_idx[q];
+        for (i64 p = P.Rptr[c]; p < P.Rptr[c + 1]; ++p)
+        {
+          P.rel[p] = pos[P.Ridx[p]];
+          if (P.rel[p] < 0)
+          {
+            return fail(err, B200_ERR_ARG, "internal: child update row missing from the parent front");
+          }
+        }
+      }
+      // pos entries are overwritten by later parents; stale values are never read because a
+      // child's rows are always a subset of its parent's front (checked above via rel >= 0 on a
+      // freshly reset map would be stricter; reset to be safe)
+      for (int c = 0; c < k; ++c)
+      {
+        pos[f + c] = -1;
+      }
+      for (i64 p = P.Rptr[T]; p < P.Rptr[T + 1]; ++p)
+      {
+        pos[P.Ridx[p]] = -1;
+      }
+    }
+  }
+
+  // ---- storage offsets, levels, statistics ---------------------------------------------------------
+  P.Lptr.assign(ns + 1, 0);
+  P.Wptr.assign(ns + 1, 0);
+  P.sn_level.assign(ns, 0);
+  P.max_front = 0;
+  for (int T = 0; T < ns; ++T)
+  {
+    const i64 k = P.sn_first[T + 1] - P.sn_first[T];
+    const i64 r = P.Rptr[T + 1] - P.Rptr[T];
+    const i64 h = k + r;
+    i64 sz      = h * k;
+    sz          = (sz + 3) & ~(i64)3;
+    P.Lptr[T + 1] = P.Lptr[T] + sz;
+    P.Wptr[T + 1] = P.Wptr[T] + h;
+    P.max_front   = std::max<i64>(P.max_front, h);
+    P.nnzL_stored += k * h - k * (k - 1) / 2;
+    for (i64 c = 0; c < k; ++c)
+    {
+      P.flops_stored += (double)(h - c) * (double)(h - c);
+    }
+  }
+  for (int j = 0; j < m; ++j)
+  {
+    P.nnzL += cc[j];
+    P.flops += (double)cc[j] * (double)cc[j];
+  }
+  for (int T = 0; T < ns; ++T)
+  {
+    if (P.sn_parent[T] >= 0)
+    {
+      P.sn_level[P.sn_parent[T]] = std::max(P.sn_level[P.sn_parent[T]], P.sn_level[T] + 1);
+    }
+  }
+  P.nlevels = 0;
+  for (int T = 0; T < ns; ++T)
+  {
+    P.nlevels = std::max(P.nlevels, P.sn_level[T] + 1);
+  }
+  P.lvl_ptr.assign(P.nlevels + 1, 0);
+  for (int T = 0; T < ns; ++T)
+  {
+    ++P.lvl_ptr[P.sn_level[T] + 1];
+  }
+  for (int l = 0; l < P.nlevels; ++l)
+  {
+    P.lvl_ptr[l + 1] += P.lvl_ptr[l];
+  }
+  P.lvl_sn.resize(ns);
+  {
+    std::vector<int> fill(P.lvl_ptr.begin(), P.lvl_ptr.end() - 1);
+    for (int T = 0; T < ns; ++T)
+    {
+      P.lvl_sn[fill[P.sn_level[T]]++] = T;
+    }
+  }
+
+  // ---- assembly map of S into the panels ------------------------------------------------------------------
+  {
+    // lower pattern of S by column (new labels), rows ascending incl. diagonal
+    std::vector<i64> Sptr(m + 1, 0);
+    for (int j = 0; j < m; ++j)
+    {
+      i64 cnt = 1;
+      for (int p = xadj2[j]; p < xadj2[j + 1]; ++p)
+      {
+        cnt += adj2[p] > j;
+      }
+      Sptr[j + 1] = Sptr[j] + cnt;
+    }
+    P.nnzS = Sptr[m];
+    std::vector<int> Srow((size_t)P.nnzS);
+    P.Sdest.resize((size_t)P.nnzS);
+    for (int j = 0; j < m; ++j)
+    {
+      i64 o     = Sptr[j];
+      Srow[o++] = j;
+      for (int p = xadj2[j]; p < xadj2[j + 1]; ++p)
+      {
+        if (adj2[p] > j)
+        {
+          Srow[o++] = adj2[p];
+        }
+      }
+      const int T = P.sn_of_col[j];
+      const int f = P.sn_first[T], l = P.sn_first[T + 1] - 1, k = l - f + 1;
+      const i64 h      = k + (P.Rptr[T + 1] - P.Rptr[T]);
+      const int* rows  = P.Ridx.data() + P.Rptr[T];
+      const int nrows  = (int)(P.Rptr[T + 1] - P.Rptr[T]);
+      for (i64 q = Sptr[j]; q < Sptr[j + 1]; ++q)
+      {
+        int i = Srow[q];
+        i64 rowpos;
+        if (i <= l)
+        {
+          rowpos = i - f;
+        }
+        else
+        {
+          const int* it = std::lower_bound(rows, rows + nrows, i);
+          if (it == rows + nrows || *it != i)
+          {
+            return fail(err, B200_ERR_ARG, "internal: S entry outside the supernode structure");
+          }
+          rowpos = k + (it - rows);
+        }
+        P.Sdest[q] = P.Lptr[T] + (i64)(j - f) * h + rowpos;
+      }
+    }
+    auto entry_id = [&](int row, int col) -> i64 {
+      const int* b  = Srow.data() + Sptr[col];
+      const int* e  = Srow.data() + Sptr[col + 1];
+      const int* it = std::lower_bound(b, e, row);
+      return (it != e && *it == row) ? (i64)(it - Srow.data()) : -1;
+    };
+    P.Sgsrc.assign((size_t)P.nnzS, -1);
+    for (const Ent& g : Gent)
+    {
+      int a = P.pinv[g.r], b = P.pinv[g.c];
+      i64 id = entry_id(std::max(a, b), std::min(a, b));
+      if (id < 0)
+      {
+        return fail(err, B200_ERR_ARG, "internal: G entry missing from the S pattern");
+      }
+      P.Sgsrc[id] = g.src;
+    }
+    // product terms, two passes
+    P.Sterm_ptr.assign((size_t)P.nnzS + 1, 0);
+    for (int pass = 0; pass < 2; ++pass)
+    {
+      std::vector<i64> fill;
+      if (pass == 1)
+      {
+        for (i64 q = 0; q < P.nnzS; ++q)
+        {
+          P.Sterm_ptr[q + 1] += P.Sterm_ptr[q];
+        }
+        const size_t nt = (size_t)P.Sterm_ptr[P.nnzS];
+        P.Sterm_a.resize(nt);
+        P.Sterm_b.resize(nt);
+        P.Sterm_d.resize(nt);
+        fill.assign(P.Sterm_ptr.begin(), P.Sterm_ptr.end() - 1);
+      }
+      for (int e = 0; e < nE; ++e)
+      {
+        for (int s = P.Acsc_ptr[e]; s < P.Acsc_ptr[e + 1]; ++s)
+        {
+          int a = P.pinv[P.Acsc_row[s]];
+          for (int t = P.Acsc_ptr[e]; t <= s; ++t)
+          {
+            int b  = P.pinv[P.Acsc_row[t]];
+            i64 id = entry_id(std::max(a, b), std::min(a, b));
+            if (id < 0)
+            {
+              return fail(err, B200_ERR_ARG, "internal: product term missing from the S pattern");
+            }
+            if (pass == 0)
+            {
+              ++P.Sterm_ptr[id + 1];
+            }
+            else
+            {
+              i64 o        = fill[id]++;
+              P.Sterm_a[o] = P.Acsc_src[s];
+              P.Sterm_b[o] = P.Acsc_src[t];
+              P.Sterm_d[o] = P.dE_src[e];
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- numeric schedule: stages of panel steps -------------------------------------------------------------
+  P.sn_base.assign(ns, 0);
+  P.sn_nt.assign(ns, 1);
+  int nstages = 0;
+  for (int T = 0; T < ns; ++T)
+  {
+    const int k = P.sn_first[T + 1] - P.sn_first[T];
+    P.sn_nt[T]  = (k + NB - 1) / NB;
+  }
+  for (int T = 0; T < ns; ++T) // children precede parents
+  {
+    nstages = std::max(nstages, P.sn_base[T] + P.sn_nt[T]);
+    int p   = P.sn_parent[T];
+    if (p >= 0)
+    {
+      P.sn_base[p] = std::max(P.sn_base[p], P.sn_base[T] + P.sn_nt[T]);
+    }
+  }
+  // update-matrix workspace: U_T lives from stage base[T] to stage base[parent] (inclusive)
+  P.Uoff.assign(ns, -1);
+  {
+    std::vector<std::vector<int>> alloc_at(nstages + 1), free_at(nstages + 2);
+    for (int T = 0; T < ns; ++T)
+    {
+      i64 r = P.Rptr[T + 1] - P.Rptr[T];
+      if (r == 0)
+      {
+        continue;
+      }
+      alloc_at[P.sn_base[T]].push_back(T);
+      int p = P.sn_parent[T];
+      free_at[(p >= 0 ? P.sn_base[p] : nstages - 1) + 1].push_back(T);
+    }
+    std::map<i64, i64> freelist; // offset -> size
+    i64 top = 0;
+    auto release = [&](i64 off, i64 sz) {
+      auto it = freelist.insert({off, sz}).first;
+      auto nx = std::next(it);
+      if (nx != freelist.end() && it->first + it->second == nx->first)
+      {
+        it->second += nx->second;
+        freelist.erase(nx);
+      }
+      if (it != freelist.begin())
+      {
+        auto pv = std::prev(it);
+        if (pv->first + pv->second == it->first)
+        {
+          pv->second += it->second;
+          freelist.erase(it);
+          it = pv;
+        }
+      }
+      if (it->first + it->second == top)
+      {
+        top = it->first;
+        freelist.erase(it);
+      }
+    };
+    std::vector<i64> usz(ns, 0);
+    for (int s = 0; s < nstages; ++s)
+    {
+      for (int T : free_at[s])
+      {
+        release(P.Uoff[T], usz[T]);
+      }
+      for (int T : alloc_at[s])
+      {
+        i64 r  = P.Rptr[T + 1] - P.Rptr[T];
+        i64 sz = (r * r + 3) & ~(i64)3;
+        usz[T] = sz;
+        i64 off = -1;
+        // first fit among the largest few: bounded scan keeps this O(n log n) in practice
+        int scanned = 0;
+        for (auto it = freelist.begin(); it != freelist.end() && scanned < 64; ++it, ++scanned)
+        {
+          if (it->second >= sz)
+          {
+            off = it->first;
+            i64 rem = it->second - sz;
+            i64 o2  = it->first + sz;
+            freelist.erase(it);
+            if (rem > 0)
+            {
+              freelist.insert({o2, rem});
+            }
+            break;
+          }
+        }
+        if (off < 0)
+        {
+          off = top;
+          top += sz;
+        }
+        P.Uoff[T]  = off;
+        P.Utotal   = std::max(P.Utotal, top);
+      }
+    }
+  }
+  // tasks
+  {
+    std::vector<std::vector<int>> starts(nstages), active(nstages);
+    for (int T = 0; T < ns; ++T)
+    {
+      starts[P.sn_base[T]].push_back(T);
+      for (int t = 0; t < P.sn_nt[T]; ++t)
+      {
+        active[P.sn_base[T] + t].push_back(T);
+      }
+    }
+    P.stages.resize(nstages);
+    P.n_scratch_slots = 0;
+    for (int s = 0; s < nstages; ++s)
+    {
+      Stage& st     = P.stages[s];
+      st.zero_begin = (int)P.zero_sn.size();
+      st.ea_begin   = (int)P.ea_tasks.size();
+      for (int T : starts[s])
+      {
+        if (P.child_ptr[T] == P.child_ptr[T + 1])
+        {
+          continue;
+        }
+        if (P.Rptr[T + 1] > P.Rptr[T])
+        {
+          P.zero_sn.push_back(T);
+        }
+        for (int q = P.child_ptr[T]; q < P.child_ptr[T + 1]; ++q)
+        {
+          int c  = P.child_idx[q];
+          int rc = (int)(P.Rptr[c + 1] - P.Rptr[c]);
+          for (int jb = 0; jb * EA_COLS < rc; ++jb)
+          {
+            P.ea_tasks.push_back({c, jb});
+          }
+        }
+      }
+      st.zero_end  = (int)P.zero_sn.size();
+      st.ea_end    = (int)P.ea_tasks.size();
+      st.pan_begin = (int)P.pan_tasks.size();
+      st.upd_begin = (int)P.upd_tasks.size();
+      int slots    = 0;
+      for (int T : active[s])
+      {
+        const int t  = s - P.sn_base[T];
+        const int k  = P.sn_first[T + 1] - P.sn_first[T];
+        const int r  = (int)(P.Rptr[T + 1] - P.Rptr[T]);
+        const int h  = k + r;
+        const int c0 = t * NB;
+        const int w  = std::min(NB, k - c0);
+        const int below = h - c0 - w;
+        const int nrb   = std::max(1, (below + RB - 1) / RB);
+        int slot        = -1;
+        if (nrb > 1)
+        {
+          slot = slots++;
+          P.upd_tasks.push_back({T, t, UPD_DIAGCOPY, slot, 0});
+        }
+        for (int rb = 0; rb < nrb; ++rb)
+        {
+          P.pan_tasks.push_back({T, t, rb, slot});
+        }
+        // trailing update inside the panel: front columns [c0+w, k), rows >= column
+        for (int j0 = c0 + w; j0 < k; j0 += TILE)
+        {
+          for (int i0 = j0; i0 < h; i0 += TILE)
+          {
+            P.upd_tasks.push_back({T, t, UPD_INPANEL, i0, j0});
+          }
+        }
+        if (t == P.sn_nt[T] - 1 && r > 0)
+        {
+          for (int j0 = 0; j0 < r; j0 += TILE)
+          {
+            for (int i0 = j0; i0 < r; i0 += TILE)
+            {
+              P.upd_tasks.push_back({T, t, UPD_SCHUR, i0, j0});
+            }
+          }
+        }
+      }
+      P.n_scratch_slots = std::max(P.n_scratch_slots, slots);
+      st.pan_end        = (int)P.pan_tasks.size();
+      st.upd_end        = (int)P.upd_tasks.size();
+    }
+  }
+
+  // ---- hash of the full permutation -----------------------------------------------------------------------------
+  {
+    std::vector<int> fp(n);
+    full_structure(P, fp.data(), nullptr, nullptr, nullptr, nullptr);
+    P.perm_hash = fnv1a(14695981039346656037ull, fp.data(), sizeof(int) * (size_t)n);
+  }
+  P.ms_symbolic = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return B200_OK;
+}
+
+void
+full_structure(const Plan& P, int* perm, int* parent, int* colcount, int* n_super_total, int* super_first)
+{
+  const int nE = P.nE, m = P.m;
+  if (perm)
+  {
+    for (int e = 0; e < nE; ++e)
+    {
+      perm[e] = P.k_of_e[e];
+    }
+    for (int j = 0; j < m; ++j)
+    {
+      perm[nE + j] = P.k_of_r[P.perm[j]];
+    }
+  }
+  if (parent || colcount)
+  {
+    for (int e = 0; e < nE; ++e)
+    {
+      int best = -1;
+      for (int q = P.Acsc_ptr[e]; q < P.Acsc_ptr[e + 1]; ++q)
+      {
+        int pos = nE + P.pinv[P.Acsc_row[q]];
+        if (best == -1 || pos < best)
+        {
+          best = pos;
+        }
+      }
+      if (parent)
+      {
+        parent[e] = best;
+      }
+      if (colcount)
+      {
+        colcount[e] = 1 + (P.Acsc_ptr[e + 1] - P.Acsc_ptr[e]);
+      }
+    }
+    for (int j = 0; j < m; ++j)
+    {
+      if (parent)
+      {
+        parent[nE + j] = P.parent[j] == -1 ? -1 : nE + P.parent[j];
+      }
+      if (colcount)
+      {
+        colcount[nE + j] = P.colcount[j];
+      }
+    }
+  }
+  if (n_super_total)
+  {
+    *n_super_total = nE + P.nsuper;
+  }
+  if (super_first)
+  {
+    for (int e = 0; e < nE; ++e)
+    {
+      super_first[e] = e;
+    }
+    for (int T = 0; T <= P.nsuper; ++T)
+    {
+      super_first[nE + T] = nE + P.sn_first[T];
+    }
+  }
+}
+
+} // namespace b200

@@ -1,0 +1,235 @@
+"""Host-side mirror of the reference's factorization plugin and sparse mat-vec interface.
+
+Names, argument meaning and error behaviour follow the reference (chrhansk/sleqp v1.0.2):
+
+  Fact.set_matrix / solve / solution / cond / release  <->  sleqp_fact_set_matrix / _solve / _solution /
+      _cond / _release (src/main/fact/fact.h:36-68); flags() returns SLEQP_FACT_FLAGS_LOWER only
+      (fact.h:9-14), so callers hand over the lower triangle and the indefinite standard form
+      (trial_point.c:94-109).
+  Mat.mult_vec / mult_vec_trans  <->  sleqp_mat_mult_vec / sleqp_mat_mult_vec_trans (sparse/mat.c:282-363)
+
+Every method goes through the C-ABI (include/sleqp_b200.h); there is no Python or CPU compute path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import Stats, check, lib
+
+SLEQP_FACT_FLAGS_NONE = 0
+SLEQP_FACT_FLAGS_PSD = 1 << 0
+SLEQP_FACT_FLAGS_LOWER = 1 << 1
+
+_ip = C.POINTER(C.c_int)
+_dp = C.POINTER(C.c_double)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _pi(a):
+    return a.ctypes.data_as(_ip)
+
+
+def _pd(a):
+    return a.ctypes.data_as(_dp)
+
+
+PLAN_FIELDS = {
+    # name: dtype
+    **{k: np.int32 for k in (
+        "e_of_k r_of_k k_of_e k_of_r dE_src Acsc_ptr Acsc_row Acsc_src Acsr_ptr Acsr_col Acsr_src "
+        "Gsym_ptr Gsym_col Gsym_src perm pinv parent colcount sn_first sn_of_col sn_parent sn_level "
+        "Ridx rel child_ptr child_idx Sgsrc Sterm_a Sterm_b Sterm_d sn_base sn_nt zero_sn lvl_ptr lvl_sn"
+    ).split()},
+    **{k: np.int64 for k in "Rptr Lptr Wptr Sdest Sterm_ptr Uoff".split()},
+}
+PLAN_STRUCTS = {"stages": 8, "ea_tasks": 2, "pan_tasks": 4, "upd_tasks": 5}  # int32 columns
+
+
+class Symbolic:
+    """Host-only symbolic analysis (no GPU): ordering, elimination tree, supernodes, schedule."""
+
+    def __init__(self, n, colptr, rowidx, val, lower_only=True):
+        self._h = C.c_void_p()
+        colptr, rowidx, val = _i32(colptr), _i32(rowidx), _f64(val)
+        check(lib().b200_symbolic_analyze(C.byref(self._h), int(n), int(len(rowidx)), _pi(colptr), _pi(rowidx), _pd(val), int(bool(lower_only))))
+        self.n = int(n)
+
+    def stats(self) -> dict:
+        s = Stats()
+        check(lib().b200_symbolic_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def structure(self):
+        """(perm, parent, colcount, super_first) over the full order of K."""
+        n = self.n
+        perm, parent, cc = (np.empty(n, dtype=np.int32) for _ in range(3))
+        ns = C.c_int()
+        sf = np.empty(n + 2, dtype=np.int32)
+        check(lib().b200_symbolic_structure(self._h, _pi(perm), _pi(parent), _pi(cc), C.byref(ns), _pi(sf)))
+        return perm, parent, cc, sf[: ns.value + 1].copy()
+
+    def export(self, field):
+        cnt = C.c_int64()
+        check(lib().b200_symbolic_export(self._h, field.encode(), None, C.byref(cnt)))
+        if field in PLAN_STRUCTS:
+            out = np.empty((cnt.value, PLAN_STRUCTS[field]), dtype=np.int32)
+        else:
+            out = np.empty(cnt.value, dtype=PLAN_FIELDS[field])
+        if cnt.value:
+            check(lib().b200_symbolic_export(self._h, field.encode(), out.ctypes.data_as(C.c_void_p), C.byref(cnt)))
+        return out
+
+    def plan(self) -> dict:
+        d = {k: self.export(k) for k in list(PLAN_FIELDS) + list(PLAN_STRUCTS)}
+        d.update(self.stats())
+        return d
+
+    def close(self):
+        if self._h:
+            lib().b200_symbolic_free(C.byref(self._h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Fact:
+    """The B200 factorization backend behind SleqpFactCallbacks (fact_types.h:25-32)."""
+
+    name = "B200"
+
+    def __init__(self, device: int = -1):
+        self._h = C.c_void_p()
+        check(lib().b200_fact_create(C.byref(self._h), int(device)))
+        self._n = 0
+
+    @staticmethod
+    def flags() -> int:
+        return SLEQP_FACT_FLAGS_LOWER
+
+    def set_matrix(self, n, colptr, rowidx, val, lower_only=True):
+        """sleqp_fact_set_matrix (fact.c:59-75): symbolic (cached per pattern) + numeric LDL^T."""
+        colptr, rowidx, val = _i32(colptr), _i32(rowidx), _f64(val)
+        check(lib().b200_fact_set_matrix(self._h, int(n), int(n), int(len(rowidx)), _pi(colptr), _pi(rowidx), _pd(val), int(bool(lower_only))))
+        self._n = int(n)
+
+    def solve(self, idx, val, dim=None):
+        """sleqp_fact_solve (fact.c:83-89) with a sparse right-hand side of dimension `dim`."""
+        idx, val = _i32(idx), _f64(val)
+        check(lib().b200_fact_solve(self._h, int(len(idx)), _pi(idx), _pd(val), int(self._n if dim is None else dim)))
+
+    def solution_dense(self, begin, end) -> np.ndarray:
+        out = np.empty(int(end - begin), dtype=np.float64)
+        check(lib().b200_fact_solution(self._h, int(begin), int(end), _pd(out)))
+        return out
+
+    def solution(self, begin, end, zero_eps=1e-20):
+        """sleqp_fact_solution (fact.c:91-102): sparse slice, entries with |v| <= zero_eps dropped
+        (sleqp_vec_set_from_raw, vec.c:72-104). Returns (indices, values)."""
+        p = _dp()
+        check(lib().b200_fact_solution_ptr(self._h, int(begin), int(end), C.byref(p)))
+        v = np.ctypeslib.as_array(p, shape=(int(end - begin),))
+        idx = np.nonzero(np.abs(v) > zero_eps)[0].astype(np.int32)
+        return idx, v[idx].copy()
+
+    def solve_device(self, d_rhs_ptr: int, d_sol_ptr: int):
+        check(lib().b200_fact_solve_device(self._h, C.c_void_p(d_rhs_ptr), C.c_void_p(d_sol_ptr)))
+
+    def cond(self) -> float:
+        """sleqp_fact_cond (fact.c:104-118): 1 / rcond."""
+        r = C.c_double()
+        check(lib().b200_fact_rcond(self._h, C.byref(r)))
+        return float("inf") if r.value == 0.0 else 1.0 / r.value
+
+    def stats(self) -> dict:
+        s = Stats()
+        check(lib().b200_fact_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def structure(self):
+        n = self._n
+        perm, parent, cc = (np.empty(n, dtype=np.int32) for _ in range(3))
+        ns = C.c_int()
+        sf = np.empty(n + 2, dtype=np.int32)
+        check(lib().b200_fact_structure(self._h, _pi(perm), _pi(parent), _pi(cc), C.byref(ns), _pi(sf)))
+        return perm, parent, cc, sf[: ns.value + 1].copy()
+
+    def pivots(self) -> np.ndarray:
+        d = np.empty(self._n, dtype=np.float64)
+        check(lib().b200_fact_pivots(self._h, _pd(d)))
+        return d
+
+    @property
+    def stream(self) -> int:
+        return int(lib().b200_fact_stream(self._h) or 0)
+
+    def release(self):
+        """sleqp_fact_release (fact.c:143-161) -> callbacks.free."""
+        if self._h:
+            check(lib().b200_fact_free(C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class Mat:
+    """Device-resident CSC matrix for the Jacobian/Hessian products of the EQP loop."""
+
+    def __init__(self, device: int = -1):
+        self._h = C.c_void_p()
+        check(lib().b200_mat_create(C.byref(self._h), int(device)))
+        self.num_rows = self.num_cols = 0
+
+    def set(self, num_rows, num_cols, cols, rows, data):
+        cols, rows, data = _i32(cols), _i32(rows), _f64(data)
+        check(lib().b200_mat_set(self._h, int(num_rows), int(num_cols), int(len(rows)), _pi(cols), _pi(rows), _pd(data)))
+        self.num_rows, self.num_cols = int(num_rows), int(num_cols)
+
+    def mult_vec(self, idx, val) -> np.ndarray:
+        """sleqp_mat_mult_vec (mat.c:282-310): dense result of length num_rows."""
+        idx, val = _i32(idx), _f64(val)
+        out = np.empty(self.num_rows, dtype=np.float64)
+        check(lib().b200_mat_mult_vec(self._h, int(len(idx)), _pi(idx), _pd(val), _pd(out)))
+        return out
+
+    def mult_vec_trans(self, idx, val, eps=0.0):
+        """sleqp_mat_mult_vec_trans (mat.c:312-363): sparse result, |s| <= eps dropped."""
+        idx, val = _i32(idx), _f64(val)
+        out = np.empty(self.num_cols, dtype=np.float64)
+        check(lib().b200_mat_mult_vec_trans(self._h, int(len(idx)), _pi(idx), _pd(val), _pd(out)))
+        keep = np.nonzero(np.abs(out) > eps)[0].astype(np.int32)
+        return keep, out[keep]
+
+    def mult_vec_device(self, d_x: int, d_y: int):
+        check(lib().b200_mat_mult_vec_device(self._h, C.c_void_p(d_x), C.c_void_p(d_y)))
+
+    def mult_vec_trans_device(self, d_v: int, d_y: int):
+        check(lib().b200_mat_mult_vec_trans_device(self._h, C.c_void_p(d_v), C.c_void_p(d_y)))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().b200_mat_stream(self._h) or 0)
+
+    def release(self):
+        if self._h:
+            check(lib().b200_mat_free(C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
