@@ -35,6 +35,12 @@ extern "C" {
 
 #define B200_VERSION_STRING "0.1.0"
 
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
 enum
 {
   B200_OK              = 0,
@@ -75,19 +81,21 @@ typedef struct b200_stats
   double ms_symbolic;      /* host wall time of the analysis (0 when cached) */
   double ms_numeric;       /* device time of the last numeric factorization (CUDA events) */
   double ms_solve;         /* device time of the last solve (CUDA events) */
+  int32_t n_scratch_slots; /* diagonal-block scratch slots of the numeric schedule */
+  int32_t reserved;
 } b200_stats;
 
 /* ---- factorization plugin (SleqpFactCallbacks) --------------------------------------- */
 
 /* device = -1: use B200_DEVICE from the environment, else LOCAL_RANK, else 0. */
-int b200_fact_create(b200_fact** handle, int device);
+B200_API int b200_fact_create(b200_fact** handle, int device);
 
 /* K given as CSC (colptr[n_cols+1], rowidx[nnz] strictly increasing per column, val[nnz]),
  * lower triangle incl. diagonal when lower_only != 0 (SLEQP_FACT_FLAGS_LOWER), otherwise the
  * full symmetric matrix (strictly upper entries are then ignored). Arrays are borrowed for the
  * duration of the call only. Looks up / builds the cached symbolic analysis, uploads the
  * values and runs the numeric LDL^T on the device. */
-int b200_fact_set_matrix(b200_fact* handle,
+B200_API int b200_fact_set_matrix(b200_fact* handle,
                          int n_rows,
                          int n_cols,
                          int nnz,
@@ -98,79 +106,79 @@ int b200_fact_set_matrix(b200_fact* handle,
 
 /* Solve K x = b for a sparse right-hand side (idx ascending, dim == n). The result stays in
  * device memory inside the handle (like `umfpack->solution`). */
-int b200_fact_solve(b200_fact* handle, int nnz_rhs, const int* idx, const double* val, int dim);
+B200_API int b200_fact_solve(b200_fact* handle, int nnz_rhs, const int* idx, const double* val, int dim);
 
 /* Copy x[begin:end) of the last solve into out_dense (host memory, end-begin doubles). */
-int b200_fact_solution(b200_fact* handle, int begin, int end, double* out_dense);
+B200_API int b200_fact_solution(b200_fact* handle, int begin, int end, double* out_dense);
 
 /* Same, but returns a pointer into the handle's pinned staging buffer (valid until the next
  * call on this handle) -- saves one host memcpy in the glue. */
-int b200_fact_solution_ptr(b200_fact* handle, int begin, int end, const double** out);
+B200_API int b200_fact_solution_ptr(b200_fact* handle, int begin, int end, const double** out);
 
 /* Device-resident variants used by the benchmark's "inputs already in HBM" leg and by a
  * device-resident CG: d_rhs and d_sol are device pointers to n doubles. */
-int b200_fact_solve_device(b200_fact* handle, const double* d_rhs, double* d_sol);
+B200_API int b200_fact_solve_device(b200_fact* handle, const double* d_rhs, double* d_sol);
 
 /* rcond = min|d_i| / max|d_i| over the pivots of D (cf. cholmod_l_rcond, fact_cholmod.c:204). */
-int b200_fact_rcond(b200_fact* handle, double* rcond);
+B200_API int b200_fact_rcond(b200_fact* handle, double* rcond);
 
-int b200_fact_stats(b200_fact* handle, b200_stats* stats);
+B200_API int b200_fact_stats(b200_fact* handle, b200_stats* stats);
 
 /* Structural outputs of the cached analysis, for parity tests. Every array is optional (NULL
  * = skip). perm[n]: position p of the factorization holds K index perm[p]; parent[n]:
  * elimination tree of P K P^T (-1 = root); colcount[n]: column counts of L incl. diagonal;
  * super_first[n_supernodes_total+1] over the full order (variables are 1x1 supernodes). */
-int b200_fact_structure(b200_fact* handle, int* perm, int* parent, int* colcount, int* n_super_total, int* super_first);
+B200_API int b200_fact_structure(b200_fact* handle, int* perm, int* parent, int* colcount, int* n_super_total, int* super_first);
 
 /* Debug/parity: copy the dense pivots D (n doubles, factorization order) to the host. */
-int b200_fact_pivots(b200_fact* handle, double* d_out);
+B200_API int b200_fact_pivots(b200_fact* handle, double* d_out);
 
 /* CUDA stream the handle launches on (cudaStream_t as void*), for event timing by callers. */
-void* b200_fact_stream(b200_fact* handle);
+B200_API void* b200_fact_stream(b200_fact* handle);
 
-int b200_fact_free(b200_fact** handle);
+B200_API int b200_fact_free(b200_fact** handle);
 
-const char* b200_last_error(void);
+B200_API const char* b200_last_error(void);
 
 /* ---- host-only symbolic analysis (no GPU needed) -------------------------------------- */
 
 typedef struct b200_symbolic b200_symbolic;
 
-int b200_symbolic_analyze(b200_symbolic** out,
+B200_API int b200_symbolic_analyze(b200_symbolic** out,
                           int n,
                           int nnz,
                           const int* colptr,
                           const int* rowidx,
                           const double* val,
                           int lower_only);
-int b200_symbolic_stats(const b200_symbolic* s, b200_stats* stats);
-int b200_symbolic_structure(const b200_symbolic* s, int* perm, int* parent, int* colcount, int* n_super_total, int* super_first);
+B200_API int b200_symbolic_stats(const b200_symbolic* s, b200_stats* stats);
+B200_API int b200_symbolic_structure(const b200_symbolic* s, int* perm, int* parent, int* colcount, int* n_super_total, int* super_first);
 /* Export of the numeric plan (reduced system) for the CPU emulation used in tests:
  * query sizes with all pointers NULL first. See sleqp_b200/fact.py for the field list. */
-int b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64_t* count);
-int b200_symbolic_free(b200_symbolic** s);
+B200_API int b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64_t* count);
+B200_API int b200_symbolic_free(b200_symbolic** s);
 
 /* ---- CSC SpMV / SpMV^T (sleqp_mat_mult_vec / sleqp_mat_mult_vec_trans) ---------------- */
 
-int b200_mat_create(b200_mat** handle, int device);
+B200_API int b200_mat_create(b200_mat** handle, int device);
 /* Upload a CSC matrix (same layout as SleqpMat: cols[num_cols+1], rows[nnz], data[nnz]). A
  * CSR mirror for the gather-form y = A x is built on the host when the pattern changes. */
-int b200_mat_set(b200_mat* handle, int num_rows, int num_cols, int nnz, const int* cols, const int* rows, const double* data);
+B200_API int b200_mat_set(b200_mat* handle, int num_rows, int num_cols, int nnz, const int* cols, const int* rows, const double* data);
 /* result[num_rows] = A * x, x sparse (mat.c:282-310). */
-int b200_mat_mult_vec(b200_mat* handle, int nnz_x, const int* idx, const double* val, double* result_dense);
+B200_API int b200_mat_mult_vec(b200_mat* handle, int nnz_x, const int* idx, const double* val, double* result_dense);
 /* result[num_cols] = A^T * v, v sparse; dense result, the glue drops |s| <= eps (mat.c:312-363). */
-int b200_mat_mult_vec_trans(b200_mat* handle, int nnz_v, const int* idx, const double* val, double* result_dense);
+B200_API int b200_mat_mult_vec_trans(b200_mat* handle, int nnz_v, const int* idx, const double* val, double* result_dense);
 /* Device-resident forms: d_x/d_y dense device vectors. */
-int b200_mat_mult_vec_device(b200_mat* handle, const double* d_x, double* d_y);
-int b200_mat_mult_vec_trans_device(b200_mat* handle, const double* d_v, double* d_y);
-void* b200_mat_stream(b200_mat* handle);
-int b200_mat_free(b200_mat** handle);
+B200_API int b200_mat_mult_vec_device(b200_mat* handle, const double* d_x, double* d_y);
+B200_API int b200_mat_mult_vec_trans_device(b200_mat* handle, const double* d_v, double* d_y);
+B200_API void* b200_mat_stream(b200_mat* handle);
+B200_API int b200_mat_free(b200_mat** handle);
 
 /* ---- misc ------------------------------------------------------------------------------ */
-int b200_device_count(void);
+B200_API int b200_device_count(void);
 /* Number of kernel launches issued by this library on this process so far (bench.py's
  * "gpu_launches" claim; graph replays count their kernel nodes). */
-int64_t b200_launch_count(void);
+B200_API int64_t b200_launch_count(void);
 
 #ifdef __cplusplus
 }

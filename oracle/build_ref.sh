@@ -95,7 +95,7 @@ echo "built $OUT/libsleqp_ref_lapack.so"
 
 # drop-in: same reference core, our host glue instead of fact_lapack.c
 if [ -f "$REPO/sleqp_b200/host/fact_b200.c" ] && [ -f "$REPO/sleqp_b200/libsleqp_b200.so" ]; then
-  gcc $CFLAGS -I"$REPO/include" -c "$REPO/sleqp_b200/host/fact_b200.c" -o "$OUT/obj/fact_b200.o"
+  gcc $CFLAGS -I"$REPO/include" -I"$REPO/sleqp_b200/host" -I"$SRC/fact" -c "$REPO/sleqp_b200/host/fact_b200.c" -o "$OUT/obj/fact_b200.o"
   gcc -shared -o "$OUT/libsleqp_ref_b200.so" $OBJS "$OUT/obj/fact_b200.o" \
       -L"$REPO/sleqp_b200" -lsleqp_b200 -Wl,-rpath,'$ORIGIN/../../sleqp_b200' -lm
   echo "built $OUT/libsleqp_ref_b200.so"

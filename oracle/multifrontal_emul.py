@@ -1,0 +1,264 @@
+"""Task-by-task numpy emulation of the device numeric factorization and solve -- TEST
+INFRASTRUCTURE ONLY (see oracle/sleqp_oracle.py header for the import rule).
+
+It executes the *same plan* (assembly map, stages, extend-add / panel / update tasks, solve
+levels) that the CUDA kernels in sleqp_b200/csrc/numeric.cu and solve.cu execute, one task at a
+time, so that schedule or index-map defects show up on the CPU before any GPU time is spent, and
+so that GPU intermediates (pivots D) can be compared against it. The update workspace is filled
+with NaN first: a missing zero-fill or a read of a dead region poisons the result.
+
+This is not a restatement of reference code (the reference delegates all of this to
+Umfpack/CHOLMOD); the parity anchor for numerics is oracle/sleqp_oracle.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+NB, RB, TILE, EA_COLS = 32, 128, 64, 16
+UPD_INPANEL, UPD_SCHUR, UPD_DIAGCOPY = 0, 1, 2
+
+
+class Emulated:
+    def __init__(self, plan: dict, kval: np.ndarray):
+        self.p = plan
+        self.kval = np.asarray(kval, dtype=np.float64)
+        self.m = int(plan["n_reduced"])
+        self.nE = int(plan["n_elim"])
+        self.N = int(plan["n"])
+        self.n_perturbed = 0
+        self._factor()
+
+    # ---------------------------------------------------------------- geometry helpers
+    def _geom(self, T):
+        p = self.p
+        f = int(p["sn_first"][T])
+        k = int(p["sn_first"][T + 1]) - f
+        r = int(p["Rptr"][T + 1] - p["Rptr"][T])
+        return f, k, r, k + r
+
+    def panel(self, T):
+        """h x k column-major view of supernode T's panel."""
+        f, k, r, h = self._geom(T)
+        o = int(self.p["Lptr"][T])
+        return self.L[o : o + h * k].reshape((k, h)).T
+
+    def umat(self, T):
+        f, k, r, h = self._geom(T)
+        o = int(self.p["Uoff"][T])
+        return self.U[o : o + r * r].reshape((r, r)).T
+
+    # ---------------------------------------------------------------- numeric
+    def _factor(self):
+        p, kv = self.p, self.kval
+        nS = len(p["Sdest"])
+        self.L = np.zeros(int(p["Lptr"][-1]))
+        self.U = np.full(int(p["update_ws_doubles"]), np.nan)
+        self.D = np.zeros(self.m)
+        # assembly of S = G - A D^-1 A^T into the panels
+        val = np.zeros(nS)
+        g = p["Sgsrc"]
+        val[g >= 0] = kv[g[g >= 0]]
+        nt = len(p["Sterm_a"])
+        if nt:
+            prod = kv[p["Sterm_a"]] * kv[p["Sterm_b"]] / kv[p["Sterm_d"]]
+            ent = np.repeat(np.arange(nS), np.diff(p["Sterm_ptr"]))
+            np.subtract.at(val, ent, prod)
+        self.L[p["Sdest"]] = val
+        # static pivot threshold from the largest |S_jj|
+        first_ent = np.zeros(self.m, dtype=np.int64)
+        # diagonal entry is the first entry of every column of S; recover via Sdest of (j,j)
+        smax = 0.0
+        for T in range(int(p["n_supernodes"])):
+            f, k, r, h = self._geom(T)
+            smax = max(smax, np.abs(np.diag(self.panel(T)[:k, :k])).max(initial=0.0))
+        self.tau = 64 * np.finfo(float).eps * smax
+        scratch = np.full(max(1, int(p["n_scratch_slots"]) if "n_scratch_slots" in p else 1) * NB * NB, np.nan)
+        has_children = np.diff(p["child_ptr"]) > 0
+        for st in p["stages"]:
+            zb, ze, eb, ee, pb, pe, ub, ue = (int(x) for x in st)
+            for T in p["zero_sn"][zb:ze]:
+                self.umat(T)[:, :] = 0.0
+            for c, jb in p["ea_tasks"][eb:ee]:
+                self._extend_add(int(c), int(jb))
+            # scratch slots needed this stage
+            slots = [int(t[3]) for t in p["pan_tasks"][pb:pe] if t[3] >= 0]
+            if slots and (max(slots) + 1) * NB * NB > len(scratch):
+                scratch = np.full((max(slots) + 1) * NB * NB, np.nan)
+            for T, t, rb, slot in p["pan_tasks"][pb:pe]:
+                self._panel(int(T), int(t), int(rb), int(slot), scratch)
+            for T, t, kind, i0, j0 in p["upd_tasks"][ub:ue]:
+                self._update(int(T), int(t), int(kind), int(i0), int(j0), scratch, bool(has_children[T]))
+
+    def _extend_add(self, c, jb):
+        p = self.p
+        par = int(p["sn_parent"][c])
+        fc, kc, rc, hc = self._geom(c)
+        fp, kp, rp, hp = self._geom(par)
+        rel = p["rel"][int(p["Rptr"][c]) : int(p["Rptr"][c + 1])]
+        Uc = self.umat(c)
+        Lp = self.panel(par)
+        Up = self.umat(par) if rp > 0 else None
+        for j in range(jb * EA_COLS, min(rc, (jb + 1) * EA_COLS)):
+            pj = int(rel[j])
+            for i in range(j, rc):
+                pi = int(rel[i])
+                if pj < kp:
+                    Lp[pi, pj] += Uc[i, j]
+                else:
+                    Up[pi - kp, pj - kp] += Uc[i, j]
+
+    def _factor_diag(self, A):
+        """LDL^T of a dense w x w block (lower part of A), returns (unit-lower L, d)."""
+        w = A.shape[0]
+        A = np.tril(A).copy()
+        d = np.zeros(w)
+        nper = 0
+        for j in range(w):
+            dj = A[j, j]
+            if abs(dj) < self.tau or not np.isfinite(dj):
+                dj = -self.tau if self.tau > 0 else -1e-300
+                nper += 1
+            d[j] = dj
+            A[j, j] = 1.0
+            A[j + 1 :, j] /= dj
+            for c in range(j + 1, w):
+                A[c:, c] -= A[c:, j] * dj * A[c, j]
+        return A, d, nper
+
+    def _panel(self, T, t, rb, slot, scratch):
+        f, k, r, h = self._geom(T)
+        P = self.panel(T)
+        c0 = t * NB
+        w = min(NB, k - c0)
+        L11, d, nper = self._factor_diag(P[c0 : c0 + w, c0 : c0 + w])
+        r0 = c0 + w + rb * RB
+        r1 = min(h, r0 + RB)
+        if r1 > r0:
+            X = P[r0:r1, c0 : c0 + w].copy()
+            # solve X_new * D * L11^T = X
+            for j in range(w):
+                X[:, j] = (X[:, j] - (X[:, :j] * d[:j]) @ L11[j, :j]) / d[j]
+            P[r0:r1, c0 : c0 + w] = X
+        if rb == 0:
+            self.n_perturbed += nper
+            self.D[f + c0 : f + c0 + w] = d
+            if slot < 0:
+                il = np.tril_indices(w)
+                blk = P[c0 : c0 + w, c0 : c0 + w]
+                blk[il] = L11[il]
+            else:
+                scratch[slot * NB * NB : slot * NB * NB + w * w] = L11.T.ravel()  # column-major w x w
+
+    def _update(self, T, t, kind, i0, j0, scratch, accumulate):
+        f, k, r, h = self._geom(T)
+        P = self.panel(T)
+        if kind == UPD_DIAGCOPY:
+            slot = i0
+            c0 = t * NB
+            w = min(NB, k - c0)
+            L11 = scratch[slot * NB * NB : slot * NB * NB + w * w].reshape((w, w)).T
+            il = np.tril_indices(w)
+            blk = P[c0 : c0 + w, c0 : c0 + w]
+            blk[il] = L11[il]
+            return
+        if kind == UPD_INPANEL:
+            c0 = t * NB
+            w = min(NB, k - c0)
+            d = self.D[f + c0 : f + c0 + w]
+            i1, j1 = min(h, i0 + TILE), min(k, j0 + TILE)
+            Li = P[i0:i1, c0 : c0 + w]
+            Lj = P[j0:j1, c0 : c0 + w]
+            upd = (Li * d) @ Lj.T
+            mask = (np.arange(i0, i1)[:, None] >= np.arange(j0, j1)[None, :])
+            blk = P[i0:i1, j0:j1]
+            blk[mask] -= upd[mask]
+            return
+        if kind == UPD_SCHUR:
+            d = self.D[f : f + k]
+            Um = self.umat(T)
+            i1, j1 = min(r, i0 + TILE), min(r, j0 + TILE)
+            Li = P[k + i0 : k + i1, :k]
+            Lj = P[k + j0 : k + j1, :k]
+            upd = (Li * d) @ Lj.T
+            mask = (np.arange(i0, i1)[:, None] >= np.arange(j0, j1)[None, :])
+            blk = Um[i0:i1, j0:j1]
+            if accumulate:
+                blk[mask] -= upd[mask]
+            else:
+                blk[mask] = -upd[mask]
+            return
+        raise ValueError(kind)
+
+    # ---------------------------------------------------------------- solve
+    def solve_reduced(self, b_new):
+        """Solve S x = b in the permuted (new) labels with the multifrontal front vectors."""
+        p = self.p
+        ns = int(p["n_supernodes"])
+        W = np.full(int(p["Wptr"][-1]), np.nan)
+        x = np.zeros(self.m)
+        for lv in range(int(p["n_levels"])):
+            for T in p["lvl_sn"][int(p["lvl_ptr"][lv]) : int(p["lvl_ptr"][lv + 1])]:
+                T = int(T)
+                f, k, r, h = self._geom(T)
+                w = W[int(p["Wptr"][T]) : int(p["Wptr"][T]) + h]
+                w[:k] = b_new[f : f + k]
+                w[k:] = 0.0
+                for c in p["child_idx"][int(p["child_ptr"][T]) : int(p["child_ptr"][T + 1])]:
+                    c = int(c)
+                    fc, kc, rc, hc = self._geom(c)
+                    rel = p["rel"][int(p["Rptr"][c]) : int(p["Rptr"][c + 1])]
+                    wc = W[int(p["Wptr"][c]) + kc : int(p["Wptr"][c]) + hc]
+                    np.add.at(w, rel, wc)
+                P = self.panel(T)
+                L11 = np.tril(P[:k, :k], -1) + np.eye(k)
+                y = np.linalg.solve(L11, w[:k])
+                w[:k] = y
+                w[k:] -= P[k:, :k] @ y
+                x[f : f + k] = y
+        x /= self.D
+        for lv in range(int(p["n_levels"]) - 1, -1, -1):
+            for T in p["lvl_sn"][int(p["lvl_ptr"][lv]) : int(p["lvl_ptr"][lv + 1])]:
+                T = int(T)
+                f, k, r, h = self._geom(T)
+                rows = p["Ridx"][int(p["Rptr"][T]) : int(p["Rptr"][T + 1])]
+                P = self.panel(T)
+                L11 = np.tril(P[:k, :k], -1) + np.eye(k)
+                t = x[f : f + k] - P[k:, :k].T @ x[rows]
+                x[f : f + k] = np.linalg.solve(L11.T, t)
+        return x
+
+    def solve(self, rhs, refine=1):
+        """Full K solve in original K indices, block elimination around the reduced system."""
+        p, kv = self.p, self.kval
+        ke, kr = p["k_of_e"], p["k_of_r"]
+        dE = kv[p["dE_src"]]
+        import scipy.sparse as sp
+
+        A = sp.csr_matrix((kv[p["Acsr_src"]], p["Acsr_col"], p["Acsr_ptr"]), shape=(self.m, self.nE))
+        G = sp.csr_matrix((kv[p["Gsym_src"]], p["Gsym_col"], p["Gsym_ptr"]), shape=(self.m, self.m))
+
+        def once(b):
+            t = b[ke] / dE
+            bR = b[kr] - A @ t
+            lam_new = self.solve_reduced(bR[p["perm"]])
+            lam = np.empty(self.m)
+            lam[p["perm"]] = lam_new
+            z = np.empty(self.N)
+            z[kr] = lam
+            z[ke] = t - (A.T @ lam) / dE
+            return z
+
+        def kmul(z):
+            out = np.empty(self.N)
+            out[ke] = dE * z[ke] + A.T @ z[kr]
+            out[kr] = A @ z[ke] + G @ z[kr]
+            return out
+
+        z = once(rhs)
+        for _ in range(refine):
+            z = z + once(rhs - kmul(z))
+        return z
+
+    def pivots_full(self):
+        """D in factorization order of K: [d_E | D_S]."""
+        return np.concatenate([self.kval[self.p["dE_src"]], self.D])

@@ -38,6 +38,8 @@ class Stats(C.Structure):
         ("ms_symbolic", C.c_double),
         ("ms_numeric", C.c_double),
         ("ms_solve", C.c_double),
+        ("n_scratch_slots", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
     def as_dict(self):

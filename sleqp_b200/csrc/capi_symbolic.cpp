@@ -90,6 +90,7 @@ fill_stats_from_plan(const Plan& P, b200_stats* s)
   s->pattern_hash        = P.pattern_hash;
   s->perm_hash           = P.perm_hash;
   s->ms_symbolic         = P.ms_symbolic;
+  s->n_scratch_slots     = P.n_scratch_slots;
 }
 
 } // namespace b200

@@ -1,0 +1,158 @@
+// device.cuh -- CUDA helpers shared by the kernels and the C-ABI layer.
+#pragma once
+#include "common.hpp"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <stdexcept>
+#include <vector>
+
+namespace b200
+{
+
+struct CudaError : std::runtime_error
+{
+  explicit CudaError(const std::string& s) : std::runtime_error(s) {}
+};
+
+#define B200_CUDA(expr)                                                                                                  \
+  do                                                                                                                     \
+  {                                                                                                                      \
+    cudaError_t e__ = (expr);                                                                                            \
+    if (e__ != cudaSuccess)                                                                                              \
+    {                                                                                                                    \
+      throw ::b200::CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" +              \
+                              std::to_string(__LINE__) + ")");                                                           \
+    }                                                                                                                    \
+  } while (0)
+
+extern std::atomic<int64_t> g_launches;
+
+// Counts kernel launches: directly when launched eagerly, into `captured` while a graph is being
+// recorded (each replay then adds the recorded count).
+struct LaunchCounter
+{
+  int64_t* captured = nullptr;
+  inline void tick()
+  {
+    if (captured)
+    {
+      ++*captured;
+    }
+    else
+    {
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+  }
+};
+
+template <typename T>
+struct DevBuf
+{
+  T* p       = nullptr;
+  size_t cap = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&)            = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release()
+  {
+    if (p)
+    {
+      cudaFree(p);
+      p   = nullptr;
+      cap = 0;
+    }
+  }
+  // grows (never shrinks); contents are NOT preserved
+  void reserve(size_t n)
+  {
+    if (n > cap)
+    {
+      release();
+      size_t want = n + n / 8 + 16;
+      B200_CUDA(cudaMalloc((void**)&p, want * sizeof(T)));
+      cap = want;
+    }
+  }
+  void upload(const std::vector<T>& v, cudaStream_t s)
+  {
+    reserve(v.size());
+    if (!v.empty())
+    {
+      B200_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+  }
+};
+
+template <typename T>
+struct PinnedBuf
+{
+  T* p       = nullptr;
+  size_t cap = 0;
+  PinnedBuf() {}
+  PinnedBuf(const PinnedBuf&)            = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  ~PinnedBuf()
+  {
+    if (p)
+    {
+      cudaFreeHost(p);
+    }
+  }
+  void reserve(size_t n)
+  {
+    if (n > cap)
+    {
+      if (p)
+      {
+        cudaFreeHost(p);
+        p = nullptr;
+      }
+      size_t want = n + n / 8 + 16;
+      B200_CUDA(cudaMallocHost((void**)&p, want * sizeof(T)));
+      cap = want;
+    }
+  }
+};
+
+// Per-supernode geometry on the device.
+struct SnMeta
+{
+  long long Lptr;
+  long long Uoff;
+  long long Rptr;
+  long long Wptr;
+  int first;
+  int k;
+  int r;
+  int parent;
+  int child_begin;
+  int child_end;
+  int pad0, pad1;
+};
+
+// Device copy of a Plan (per handle).
+struct DevPlan
+{
+  std::shared_ptr<const Plan> plan;
+  DevBuf<SnMeta> sn;
+  DevBuf<int> Ridx, rel, child_idx;
+  // assembly
+  DevBuf<long long> Sdest, Sterm_ptr, Sdiag;
+  DevBuf<int> Sgsrc, Sterm_a, Sterm_b, Sterm_d;
+  // tasks
+  DevBuf<int> zero_sn;
+  DevBuf<EaTask> ea_tasks;
+  DevBuf<PanelTask> pan_tasks;
+  DevBuf<Task5> upd_tasks;
+  DevBuf<int> lvl_sn;
+  // E-part / residual operators
+  DevBuf<int> k_of_e, k_of_r, pinv, perm, dE_src;
+  DevBuf<int> Acsc_ptr, Acsc_row, Acsc_src, Acsr_ptr, Acsr_col, Acsr_src, Gsym_ptr, Gsym_col, Gsym_src;
+  std::vector<int> lvl_maxh; // largest front height per solve level (shared-memory sizing)
+};
+
+} // namespace b200

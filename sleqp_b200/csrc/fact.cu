@@ -1,0 +1,703 @@
+// fact.cu -- the b200_fact_* C-ABI: one handle per SleqpFact, owning a CUDA stream, the device
+// copy of the cached plan, the factor, and the solve workspaces. Host glue: ../host/fact_b200.c.
+#include "numeric.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace b200
+{
+std::atomic<int64_t> g_launches{0};
+}
+
+using namespace b200;
+
+namespace
+{
+
+struct Graph
+{
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches     = 0;
+  void reset()
+  {
+    if (exec)
+    {
+      cudaGraphExecDestroy(exec);
+      exec = nullptr;
+    }
+    launches = 0;
+  }
+};
+
+constexpr int MAX_REFINE = 3;
+
+} // namespace
+
+struct b200_fact
+{
+  int device          = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+
+  DevPlan dp;
+  // factor
+  DevBuf<double> val, L, U, D, scratch, scal, dE, Acsc_val, Acsr_val, Gsym_val;
+  DevBuf<int> nper;
+  // solve
+  DevBuf<double> rhs, z, res, dz, bR, y, W;
+  DevBuf<int> rhs_idx;
+  DevBuf<double> rhs_val;
+  PinnedBuf<int> h_rhs_idx;
+  PinnedBuf<double> h_rhs_val, h_sol, h_scal;
+  PinnedBuf<int> h_nper;
+
+  Graph g_numeric;
+  Graph g_solve[MAX_REFINE + 1];
+
+  bool factored = false, solved = false;
+  bool timed_numeric = false, timed_solve = false;
+  int refine          = 0;
+  int n_perturbed     = 0;
+  double probe_res    = 0;
+  double rcond        = 0;
+  bool symbolic_cached = false;
+  double ms_symbolic  = 0;
+
+  NumericBuffers nbuf() const
+  {
+    NumericBuffers nb;
+    nb.val         = val.p;
+    nb.L           = L.p;
+    nb.U           = U.p;
+    nb.D           = D.p;
+    nb.scratch     = scratch.p;
+    nb.scal        = scal.p;
+    nb.n_perturbed = nper.p;
+    nb.dE          = dE.p;
+    nb.Acsc_val    = Acsc_val.p;
+    nb.Acsr_val    = Acsr_val.p;
+    nb.Gsym_val    = Gsym_val.p;
+    return nb;
+  }
+  SolveBuffers sbuf() const
+  {
+    SolveBuffers sb;
+    sb.rhs = rhs.p;
+    sb.z   = z.p;
+    sb.res = res.p;
+    sb.dz  = dz.p;
+    sb.bR  = bR.p;
+    sb.y   = y.p;
+    sb.W   = W.p;
+    return sb;
+  }
+  void drop_graphs()
+  {
+    g_numeric.reset();
+    for (auto& g : g_solve)
+    {
+      g.reset();
+    }
+  }
+};
+
+namespace
+{
+
+int
+pick_device(int device)
+{
+  if (device >= 0)
+  {
+    return device;
+  }
+  for (const char* name : {"B200_DEVICE", "LOCAL_RANK"})
+  {
+    const char* v = std::getenv(name);
+    if (v && *v)
+    {
+      return std::atoi(v);
+    }
+  }
+  return 0;
+}
+
+template <typename F>
+int
+guarded(F&& f)
+{
+  try
+  {
+    return f();
+  }
+  catch (const CudaError& e)
+  {
+    return set_error(B200_ERR_CUDA, e.what());
+  }
+  catch (const std::bad_alloc&)
+  {
+    return set_error(B200_ERR_CUDA, "host allocation failed");
+  }
+  catch (const std::exception& e)
+  {
+    return set_error(B200_ERR_CUDA, e.what());
+  }
+}
+
+void
+upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
+{
+  const Plan& P  = *plan;
+  DevPlan& dp    = F->dp;
+  cudaStream_t s = F->stream;
+  F->drop_graphs();
+  dp.plan = plan;
+  std::vector<SnMeta> meta((size_t)P.nsuper);
+  dp.lvl_maxh.assign((size_t)P.nlevels, 0);
+  for (int T = 0; T < P.nsuper; ++T)
+  {
+    SnMeta& m     = meta[T];
+    m.Lptr        = P.Lptr[T];
+    m.Uoff        = P.Uoff[T];
+    m.Rptr        = P.Rptr[T];
+    m.Wptr        = P.Wptr[T];
+    m.first       = P.sn_first[T];
+    m.k           = P.sn_first[T + 1] - P.sn_first[T];
+    m.r           = (int)(P.Rptr[T + 1] - P.Rptr[T]);
+    m.parent      = P.sn_parent[T];
+    m.child_begin = P.child_ptr[T];
+    m.child_end   = P.child_ptr[T + 1];
+    m.pad0 = m.pad1 = 0;
+    dp.lvl_maxh[P.sn_level[T]] = std::max(dp.lvl_maxh[P.sn_level[T]], m.k + m.r);
+  }
+  dp.sn.upload(meta, s);
+  dp.Ridx.upload(P.Ridx, s);
+  dp.rel.upload(P.rel, s);
+  dp.child_idx.upload(P.child_idx, s);
+  static_assert(sizeof(long long) == sizeof(i64), "i64");
+  auto up64 = [&](DevBuf<long long>& b, const std::vector<i64>& v) {
+    b.reserve(v.size());
+    if (!v.empty())
+    {
+      B200_CUDA(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(i64), cudaMemcpyHostToDevice, s));
+    }
+  };
+  up64(dp.Sdest, P.Sdest);
+  up64(dp.Sterm_ptr, P.Sterm_ptr);
+  up64(dp.Sdiag, P.Sdiag);
+  dp.Sgsrc.upload(P.Sgsrc, s);
+  dp.Sterm_a.upload(P.Sterm_a, s);
+  dp.Sterm_b.upload(P.Sterm_b, s);
+  dp.Sterm_d.upload(P.Sterm_d, s);
+  dp.zero_sn.upload(P.zero_sn, s);
+  dp.ea_tasks.upload(P.ea_tasks, s);
+  dp.pan_tasks.upload(P.pan_tasks, s);
+  dp.upd_tasks.upload(P.upd_tasks, s);
+  dp.lvl_sn.upload(P.lvl_sn, s);
+  dp.k_of_e.upload(P.k_of_e, s);
+  dp.k_of_r.upload(P.k_of_r, s);
+  dp.pinv.upload(P.pinv, s);
+  dp.perm.upload(P.perm, s);
+  dp.dE_src.upload(P.dE_src, s);
+  dp.Acsc_ptr.upload(P.Acsc_ptr, s);
+  dp.Acsc_row.upload(P.Acsc_row, s);
+  dp.Acsc_src.upload(P.Acsc_src, s);
+  dp.Acsr_ptr.upload(P.Acsr_ptr, s);
+  dp.Acsr_col.upload(P.Acsr_col, s);
+  dp.Acsr_src.upload(P.Acsr_src, s);
+  dp.Gsym_ptr.upload(P.Gsym_ptr, s);
+  dp.Gsym_col.upload(P.Gsym_col, s);
+  dp.Gsym_src.upload(P.Gsym_src, s);
+  // the uploads read pageable host vectors owned by the (shared, immutable) plan: safe, but
+  // finish them before anything else touches the stream
+  B200_CUDA(cudaStreamSynchronize(s));
+
+  const size_t N = (size_t)P.N, m = (size_t)P.m;
+  F->L.reserve((size_t)P.Lptr[P.nsuper] + 8);
+  F->U.reserve((size_t)P.Utotal + 8);
+  F->D.reserve(m + 8);
+  F->scratch.reserve((size_t)std::max(1, P.n_scratch_slots) * NB * NB);
+  F->scal.reserve(8);
+  F->nper.reserve(2);
+  F->dE.reserve((size_t)P.nE + 8);
+  F->Acsc_val.reserve(P.Acsc_src.size() + 8);
+  F->Acsr_val.reserve(P.Acsr_src.size() + 8);
+  F->Gsym_val.reserve(P.Gsym_src.size() + 8);
+  F->rhs.reserve(N + 8);
+  F->z.reserve(N + 8);
+  F->res.reserve(N + 8);
+  F->dz.reserve(N + 8);
+  F->bR.reserve(m + 8);
+  F->y.reserve(m + 8);
+  F->W.reserve((size_t)P.Wptr[P.nsuper] + 8);
+  F->h_sol.reserve(N + 8);
+  F->h_scal.reserve(8);
+  F->h_nper.reserve(2);
+}
+
+template <typename Enqueue>
+void
+run_graph(b200_fact* F, Graph& g, Enqueue&& enqueue)
+{
+  if (!g.exec)
+  {
+    LaunchCounter lc;
+    int64_t captured = 0;
+    lc.captured      = &captured;
+    cudaGraph_t graph = nullptr;
+    B200_CUDA(cudaStreamBeginCapture(F->stream, cudaStreamCaptureModeThreadLocal));
+    try
+    {
+      enqueue(lc);
+    }
+    catch (...)
+    {
+      cudaStreamEndCapture(F->stream, &graph);
+      if (graph)
+      {
+        cudaGraphDestroy(graph);
+      }
+      throw;
+    }
+    B200_CUDA(cudaStreamEndCapture(F->stream, &graph));
+    cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    B200_CUDA(e);
+    g.launches = captured;
+  }
+  B200_CUDA(cudaGraphLaunch(g.exec, F->stream));
+  g_launches.fetch_add(g.launches, std::memory_order_relaxed);
+}
+
+void
+launch_solve(b200_fact* F, int refine)
+{
+  const NumericBuffers nb = F->nbuf();
+  const SolveBuffers sb   = F->sbuf();
+  run_graph(F, F->g_solve[refine], [&](LaunchCounter& lc) { enqueue_solve(F->dp, nb, sb, refine, F->stream, lc); });
+}
+
+} // namespace
+
+extern "C" {
+
+int
+b200_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int64_t
+b200_launch_count(void)
+{
+  return g_launches.load();
+}
+
+int
+b200_fact_create(b200_fact** handle, int device)
+{
+  if (!handle)
+  {
+    return set_error(B200_ERR_ARG, "null handle pointer");
+  }
+  *handle = nullptr;
+  return guarded([&]() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+    {
+      cudaGetLastError();
+      return set_error(B200_ERR_CUDA, "no CUDA device available: the B200 backend has no CPU fallback");
+    }
+    const int dev = pick_device(device);
+    if (dev >= count)
+    {
+      return set_error(B200_ERR_CUDA, "requested device " + std::to_string(dev) + " but only " + std::to_string(count) + " visible");
+    }
+    B200_CUDA(cudaSetDevice(dev));
+    std::unique_ptr<b200_fact> F(new b200_fact());
+    F->device = dev;
+    B200_CUDA(cudaStreamCreateWithFlags(&F->stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaEventCreate(&F->ev_a));
+    B200_CUDA(cudaEventCreate(&F->ev_b));
+    B200_CUDA(cudaEventCreate(&F->ev_c));
+    B200_CUDA(cudaEventCreate(&F->ev_d));
+    configure_solve_kernels();
+    *handle = F.release();
+    return (int)B200_OK;
+  });
+}
+
+int
+b200_fact_set_matrix(b200_fact* F, int n_rows, int n_cols, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only)
+{
+  if (!F)
+  {
+    return set_error(B200_ERR_ARG, "null handle");
+  }
+  if (n_rows != n_cols)
+  {
+    return set_error(B200_ERR_ARG, "matrix must be square (fact_umfpack.c:127 asserts the same)");
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaSetDevice(F->device));
+    F->factored = F->solved = false;
+    std::shared_ptr<const Plan> plan;
+    bool cached = false;
+    int rc      = get_plan(n_rows, nnz, colptr, rowidx, val, lower_only, plan, cached);
+    if (rc != B200_OK)
+    {
+      return rc;
+    }
+    F->symbolic_cached = cached;
+    F->ms_symbolic     = cached ? 0.0 : plan->ms_symbolic;
+    if (F->dp.plan != plan)
+    {
+      upload_plan(F, plan);
+    }
+    const Plan& P = *plan;
+    if (P.N == 0)
+    {
+      F->factored = true;
+      F->refine   = 0;
+      F->rcond    = 1.0;
+      return (int)B200_OK;
+    }
+    F->val.reserve((size_t)nnz + 8);
+    B200_CUDA(cudaEventRecord(F->ev_a, F->stream));
+    if (nnz > 0)
+    {
+      B200_CUDA(cudaMemcpyAsync(F->val.p, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, F->stream));
+    }
+    {
+      const NumericBuffers nb = F->nbuf();
+      run_graph(F, F->g_numeric, [&](LaunchCounter& lc) {
+        enqueue_numeric(F->dp, nb, F->stream, lc);
+        enqueue_pivot_range(F->dp, nb, F->stream, lc);
+      });
+    }
+    B200_CUDA(cudaEventRecord(F->ev_b, F->stream));
+    F->timed_numeric = true;
+    // pivot range and perturbation count
+    B200_CUDA(cudaMemcpyAsync(F->h_scal.p, F->scal.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, F->stream));
+    B200_CUDA(cudaMemcpyAsync(F->h_nper.p, F->nper.p, sizeof(int), cudaMemcpyDeviceToHost, F->stream));
+    B200_CUDA(cudaStreamSynchronize(F->stream));
+    const double dmin = F->h_scal.p[2], dmax = F->h_scal.p[3];
+    F->rcond       = (dmax > 0.0 && std::isfinite(dmax) && std::isfinite(dmin)) ? dmin / dmax : 0.0;
+    F->n_perturbed = P.m > 0 ? F->h_nper.p[0] : 0;
+
+    // probe solve: choose the number of refinement steps every solve of this factor performs
+    const NumericBuffers nb = F->nbuf();
+    const SolveBuffers sb   = F->sbuf();
+    LaunchCounter eager;
+    double best = INFINITY, prev = INFINITY;
+    int refine  = 0;
+    for (int r = 0; r <= MAX_REFINE; ++r)
+    {
+      enqueue_probe_rhs(sb.rhs, P.N, F->stream, eager);
+      launch_solve(F, r);
+      enqueue_residual_norms(F->dp, nb, sb, F->stream, eager);
+      B200_CUDA(cudaMemcpyAsync(F->h_scal.p, F->scal.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, F->stream));
+      B200_CUDA(cudaStreamSynchronize(F->stream));
+      const double rr = std::sqrt(F->h_scal.p[2]) / std::sqrt(F->h_scal.p[3]);
+      if (std::isfinite(rr) && rr < best)
+      {
+        best   = rr;
+        refine = r;
+      }
+      // good enough, broken, or refinement stopped paying
+      if (!std::isfinite(rr) || rr <= 1e-13 || (r > 0 && rr > 0.25 * prev))
+      {
+        break;
+      }
+      prev = rr;
+    }
+    F->refine    = refine;
+    F->probe_res = best;
+    if (!(best <= 1e-6))
+    {
+      return set_error(B200_ERR_SINGULAR,
+                       "KKT matrix is numerically singular (probe residual " + std::to_string(best) + ", " + std::to_string(F->n_perturbed) +
+                         " perturbed pivots): the working set rows are not linearly independent");
+    }
+    F->factored = true;
+    return (int)B200_OK;
+  });
+}
+
+int
+b200_fact_solve(b200_fact* F, int nnz_rhs, const int* idx, const double* val, int dim)
+{
+  if (!F)
+  {
+    return set_error(B200_ERR_ARG, "null handle");
+  }
+  if (!F->factored)
+  {
+    return set_error(B200_ERR_STATE, "solve called before a successful set_matrix");
+  }
+  const Plan& P = *F->dp.plan;
+  if (dim != P.N)
+  {
+    return set_error(B200_ERR_ARG, "rhs dimension " + std::to_string(dim) + " != matrix order " + std::to_string(P.N));
+  }
+  if (nnz_rhs < 0 || nnz_rhs > dim || (nnz_rhs > 0 && (!idx || !val)))
+  {
+    return set_error(B200_ERR_ARG, "malformed sparse rhs");
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaSetDevice(F->device));
+    if (P.N == 0)
+    {
+      F->solved = true;
+      return (int)B200_OK;
+    }
+    // the previous solve may still be reading the staging buffers
+    B200_CUDA(cudaStreamSynchronize(F->stream));
+    LaunchCounter eager;
+    B200_CUDA(cudaEventRecord(F->ev_c, F->stream));
+    if (nnz_rhs > 0)
+    {
+      if (idx[0] < 0 || idx[nnz_rhs - 1] >= dim)
+      {
+        return set_error(B200_ERR_ARG, "rhs index out of range");
+      }
+      const bool contiguous = (idx[nnz_rhs - 1] - idx[0]) == nnz_rhs - 1; // ascending indices (pub_vec.h:13-14)
+      F->h_rhs_val.reserve((size_t)nnz_rhs);
+      F->rhs_val.reserve((size_t)nnz_rhs);
+      std::memcpy(F->h_rhs_val.p, val, sizeof(double) * (size_t)nnz_rhs);
+      B200_CUDA(cudaMemcpyAsync(F->rhs_val.p, F->h_rhs_val.p, sizeof(double) * (size_t)nnz_rhs, cudaMemcpyHostToDevice, F->stream));
+      const int* d_idx = nullptr;
+      if (!contiguous)
+      {
+        F->h_rhs_idx.reserve((size_t)nnz_rhs);
+        F->rhs_idx.reserve((size_t)nnz_rhs);
+        std::memcpy(F->h_rhs_idx.p, idx, sizeof(int) * (size_t)nnz_rhs);
+        B200_CUDA(cudaMemcpyAsync(F->rhs_idx.p, F->h_rhs_idx.p, sizeof(int) * (size_t)nnz_rhs, cudaMemcpyHostToDevice, F->stream));
+        d_idx = F->rhs_idx.p;
+      }
+      enqueue_scatter_rhs(F->rhs.p, P.N, nnz_rhs, d_idx, idx[0], F->rhs_val.p, F->stream, eager);
+    }
+    else
+    {
+      enqueue_scatter_rhs(F->rhs.p, P.N, 0, nullptr, 0, nullptr, F->stream, eager);
+    }
+    launch_solve(F, F->refine);
+    B200_CUDA(cudaEventRecord(F->ev_d, F->stream));
+    F->timed_solve = true;
+    F->solved      = true;
+    return (int)B200_OK;
+  });
+}
+
+int
+b200_fact_solution_ptr(b200_fact* F, int begin, int end, const double** out)
+{
+  if (!F || !out)
+  {
+    return set_error(B200_ERR_ARG, "null argument");
+  }
+  if (!F->solved)
+  {
+    return set_error(B200_ERR_STATE, "solution requested before solve");
+  }
+  const Plan& P = *F->dp.plan;
+  if (begin < 0 || end < begin || end > P.N)
+  {
+    return set_error(B200_ERR_ARG, "solution slice out of range");
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaSetDevice(F->device));
+    if (end > begin)
+    {
+      B200_CUDA(cudaMemcpyAsync(F->h_sol.p, F->z.p + begin, sizeof(double) * (size_t)(end - begin), cudaMemcpyDeviceToHost, F->stream));
+    }
+    B200_CUDA(cudaStreamSynchronize(F->stream));
+    *out = F->h_sol.p;
+    return (int)B200_OK;
+  });
+}
+
+int
+b200_fact_solution(b200_fact* F, int begin, int end, double* out_dense)
+{
+  const double* p = nullptr;
+  int rc          = b200_fact_solution_ptr(F, begin, end, &p);
+  if (rc != B200_OK)
+  {
+    return rc;
+  }
+  if (end > begin)
+  {
+    if (!out_dense)
+    {
+      return set_error(B200_ERR_ARG, "null output");
+    }
+    std::memcpy(out_dense, p, sizeof(double) * (size_t)(end - begin));
+  }
+  return B200_OK;
+}
+
+int
+b200_fact_solve_device(b200_fact* F, const double* d_rhs, double* d_sol)
+{
+  if (!F || !d_rhs || !d_sol)
+  {
+    return set_error(B200_ERR_ARG, "null argument");
+  }
+  if (!F->factored)
+  {
+    return set_error(B200_ERR_STATE, "solve called before a successful set_matrix");
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaSetDevice(F->device));
+    const Plan& P = *F->dp.plan;
+    if (P.N == 0)
+    {
+      return (int)B200_OK;
+    }
+    B200_CUDA(cudaEventRecord(F->ev_c, F->stream));
+    B200_CUDA(cudaMemcpyAsync(F->rhs.p, d_rhs, sizeof(double) * (size_t)P.N, cudaMemcpyDeviceToDevice, F->stream));
+    launch_solve(F, F->refine);
+    B200_CUDA(cudaMemcpyAsync(d_sol, F->z.p, sizeof(double) * (size_t)P.N, cudaMemcpyDeviceToDevice, F->stream));
+    B200_CUDA(cudaEventRecord(F->ev_d, F->stream));
+    F->timed_solve = true;
+    F->solved      = true;
+    return (int)B200_OK;
+  });
+}
+
+int
+b200_fact_rcond(b200_fact* F, double* rcond)
+{
+  if (!F || !rcond)
+  {
+    return set_error(B200_ERR_ARG, "null argument");
+  }
+  if (!F->factored)
+  {
+    return set_error(B200_ERR_STATE, "condition requested before a successful set_matrix");
+  }
+  *rcond = F->rcond;
+  return B200_OK;
+}
+
+int
+b200_fact_stats(b200_fact* F, b200_stats* stats)
+{
+  if (!F || !stats)
+  {
+    return set_error(B200_ERR_ARG, "null argument");
+  }
+  if (!F->dp.plan)
+  {
+    return set_error(B200_ERR_STATE, "no matrix set");
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaSetDevice(F->device));
+    fill_stats_from_plan(*F->dp.plan, stats);
+    stats->symbolic_cached = F->symbolic_cached;
+    stats->ms_symbolic     = F->ms_symbolic;
+    stats->n_perturbed     = F->n_perturbed;
+    stats->refine_steps    = F->refine;
+    stats->probe_residual  = F->probe_res;
+    B200_CUDA(cudaStreamSynchronize(F->stream));
+    float ms = 0.f;
+    if (F->timed_numeric)
+    {
+      B200_CUDA(cudaEventElapsedTime(&ms, F->ev_a, F->ev_b));
+      stats->ms_numeric = ms;
+    }
+    if (F->timed_solve)
+    {
+      B200_CUDA(cudaEventElapsedTime(&ms, F->ev_c, F->ev_d));
+      stats->ms_solve = ms;
+    }
+    return (int)B200_OK;
+  });
+}
+
+int
+b200_fact_structure(b200_fact* F, int* perm, int* parent, int* colcount, int* n_super_total, int* super_first)
+{
+  if (!F || !F->dp.plan)
+  {
+    return set_error(B200_ERR_STATE, "no matrix set");
+  }
+  full_structure(*F->dp.plan, perm, parent, colcount, n_super_total, super_first);
+  return B200_OK;
+}
+
+int
+b200_fact_pivots(b200_fact* F, double* d_out)
+{
+  if (!F || !d_out)
+  {
+    return set_error(B200_ERR_ARG, "null argument");
+  }
+  if (!F->factored)
+  {
+    return set_error(B200_ERR_STATE, "pivots requested before a successful set_matrix");
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaSetDevice(F->device));
+    const Plan& P = *F->dp.plan;
+    if (P.nE > 0)
+    {
+      B200_CUDA(cudaMemcpyAsync(d_out, F->dE.p, sizeof(double) * (size_t)P.nE, cudaMemcpyDeviceToHost, F->stream));
+    }
+    if (P.m > 0)
+    {
+      B200_CUDA(cudaMemcpyAsync(d_out + P.nE, F->D.p, sizeof(double) * (size_t)P.m, cudaMemcpyDeviceToHost, F->stream));
+    }
+    B200_CUDA(cudaStreamSynchronize(F->stream));
+    return (int)B200_OK;
+  });
+}
+
+void*
+b200_fact_stream(b200_fact* F)
+{
+  return F ? (void*)F->stream : nullptr;
+}
+
+int
+b200_fact_free(b200_fact** handle)
+{
+  if (!handle || !*handle)
+  {
+    return B200_OK;
+  }
+  b200_fact* F = *handle;
+  cudaSetDevice(F->device);
+  if (F->stream)
+  {
+    cudaStreamSynchronize(F->stream);
+  }
+  F->drop_graphs();
+  for (cudaEvent_t e : {F->ev_a, F->ev_b, F->ev_c, F->ev_d})
+  {
+    if (e)
+    {
+      cudaEventDestroy(e);
+    }
+  }
+  if (F->stream)
+  {
+    cudaStreamDestroy(F->stream);
+  }
+  delete F;
+  *handle = nullptr;
+  return B200_OK;
+}
+
+} // extern "C"

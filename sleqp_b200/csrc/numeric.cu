@@ -1,0 +1,491 @@
+// numeric.cu -- device numeric factorization: S = G - A D^-1 A^T assembled straight into the
+// supernodal panels, then a multifrontal LDL^T driven by the stage schedule of the plan.
+//
+// Replaces the vendor calls umfpack_di_numeric (fact_umfpack.c:154) / cholmod_l_factorize
+// (fact_cholmod.c:137). Kernels (all FP64):
+//   k_assemble      one thread per entry of tril(S): gathers its product terms      (HBM-bound)
+//   k_extend_add    child update matrix -> parent front (relative indices)         (HBM-bound)
+//   k_panel         NB-wide panel step: dense LDL^T of the diagonal block in shared memory,
+//                   then one thread per row solves its row of L21                   (latency/HBM)
+//   k_update        64x64 output tiles of C -= L_i D L_j^T on the FP64 tensor cores
+//                   (mma.sync m8n8k4.f64 = DMMA), operands staged through shared memory
+//                   (tcgen05 has no f64 kind, so DMMA is the FP64 tensor path on sm_100a)
+#include "numeric.cuh"
+
+namespace b200
+{
+
+// ---------------------------------------------------------------------------------------------
+__global__ void
+k_assemble(long long nnzS,
+           const long long* __restrict__ Sdest,
+           const int* __restrict__ Sgsrc,
+           const long long* __restrict__ Sterm_ptr,
+           const int* __restrict__ Sa,
+           const int* __restrict__ Sb,
+           const int* __restrict__ Sd,
+           const double* __restrict__ val,
+           double* __restrict__ L)
+{
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nnzS)
+  {
+    return;
+  }
+  const int g = Sgsrc[q];
+  double v    = g >= 0 ? val[g] : 0.0;
+  for (long long t = Sterm_ptr[q]; t < Sterm_ptr[q + 1]; ++t)
+  {
+    v -= val[Sa[t]] * val[Sb[t]] / val[Sd[t]];
+  }
+  L[Sdest[q]] = v;
+}
+
+// gathers contiguous value arrays used by the solve: dE, A (both layouts), G
+__global__ void
+k_gather(int n, const int* __restrict__ src, const double* __restrict__ val, double* __restrict__ out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+  {
+    out[i] = val[src[i]];
+  }
+}
+
+// scal[0] = max_j |S_jj|, scal[1] = 64 eps * that  (static pivot threshold)
+__global__ void
+k_diagmax(int m, const long long* __restrict__ Sdiag, const double* __restrict__ L, unsigned long long* __restrict__ scal_bits)
+{
+  double v = 0.0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x)
+  {
+    v = fmax(v, fabs(L[Sdiag[j]]));
+  }
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  }
+  if ((threadIdx.x & 31) == 0 && v > 0.0)
+  {
+    atomicMax(scal_bits, (unsigned long long)__double_as_longlong(v)); // non-negative doubles order like integers
+  }
+}
+
+__global__ void
+k_set_tau(double* scal)
+{
+  scal[1] = 64.0 * 2.220446049250313e-16 * scal[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void
+k_zero_updates(const int* __restrict__ zero_sn, const SnMeta* __restrict__ sn, double* __restrict__ U)
+{
+  const SnMeta s      = sn[zero_sn[blockIdx.x]];
+  const long long cnt = (long long)s.r * s.r;
+  double* u           = U + s.Uoff;
+  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.y * blockDim.x)
+  {
+    u[i] = 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Extend-add of EA_COLS columns of a child's update matrix into its parent's front. Children of
+// one parent run concurrently in the same launch, hence the (native FP64) atomics.
+__global__ void
+k_extend_add(const EaTask* __restrict__ tasks,
+             const SnMeta* __restrict__ sn,
+             const int* __restrict__ rel,
+             double* __restrict__ L,
+             double* __restrict__ U)
+{
+  const EaTask t   = tasks[blockIdx.x];
+  const SnMeta c   = sn[t.child];
+  const SnMeta p   = sn[c.parent];
+  const int* rl    = rel + c.Rptr;
+  const double* Uc = U + c.Uoff;
+  double* Lp       = L + p.Lptr;
+  double* Up       = U + p.Uoff;
+  const int hp     = p.k + p.r;
+  const int jend   = min(c.r, (t.jb + 1) * EA_COLS);
+  for (int j = t.jb * EA_COLS; j < jend; ++j)
+  {
+    const int pj = rl[j];
+    double* dst  = pj < p.k ? Lp + (long long)pj * hp : Up + (long long)(pj - p.k) * p.r - p.k;
+    for (int i = j + threadIdx.x; i < c.r; i += blockDim.x)
+    {
+      atomicAdd(dst + rl[i], Uc[(long long)j * c.r + i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One panel step of supernode T: columns [c0, c0+w) of the front, w <= NB.
+// Every CTA of the step factors the w x w diagonal block redundantly in shared memory (identical
+// arithmetic, so identical results) and then solves its RB rows of L21; row block 0 also publishes
+// the factored block and the pivots. With more than one row block the block goes to a scratch
+// slot (other CTAs are still reading the unfactored one) and k_update copies it back.
+__global__ void __launch_bounds__(RB)
+k_panel(const PanelTask* __restrict__ tasks,
+        const SnMeta* __restrict__ sn,
+        double* __restrict__ L,
+        double* __restrict__ D,
+        double* __restrict__ scratch,
+        const double* __restrict__ scal,
+        int* __restrict__ n_perturbed)
+{
+  __shared__ double A[NB][NB + 1];
+  __shared__ double dsh[NB];
+  const PanelTask t = tasks[blockIdx.x];
+  const SnMeta s    = sn[t.sn];
+  const int h       = s.k + s.r;
+  const int c0      = t.t * NB;
+  const int w       = min(NB, s.k - c0);
+  double* P         = L + s.Lptr;
+  const int tid     = threadIdx.x;
+  const double tau  = scal[1];
+
+  for (int idx = tid; idx < w * w; idx += RB)
+  {
+    const int i = idx % w, j = idx / w;
+    A[i][j] = P[(long long)(c0 + j) * h + c0 + i];
+  }
+  __syncthreads();
+  int nper = 0;
+  for (int j = 0; j < w; ++j)
+  {
+    if (tid == 0)
+    {
+      double dj = A[j][j];
+      if (!(fabs(dj) >= tau) || !isfinite(dj))
+      {
+        dj = tau > 0.0 ? -tau : -1e-300;
+        ++nper;
+      }
+      dsh[j] = dj;
+    }
+    __syncthreads();
+    const double dj = dsh[j];
+    if (tid > j && tid < w)
+    {
+      A[tid][j] = A[tid][j] / dj;
+    }
+    __syncthreads();
+    const int rem = w - j - 1;
+    for (int idx = tid; idx < rem * rem; idx += RB)
+    {
+      const int i = j + 1 + idx % rem, c = j + 1 + idx / rem;
+      if (i >= c)
+      {
+        A[i][c] -= A[i][j] * dj * A[c][j];
+      }
+    }
+    __syncthreads();
+  }
+
+  // rows of L21: x_j = (a_j - sum_{q<j} (x_q d_q) L11[j][q]) / d_j
+  const int row = c0 + w + t.rb * RB + tid;
+  if (row < h)
+  {
+    double x[NB], y[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+    {
+      x[j] = j < w ? P[(long long)(c0 + j) * h + row] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+    {
+      if (j < w)
+      {
+        double acc = x[j];
+#pragma unroll
+        for (int q = 0; q < j; ++q)
+        {
+          acc -= y[q] * A[j][q];
+        }
+        x[j] = acc / dsh[j];
+        y[j] = x[j] * dsh[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+    {
+      if (j < w)
+      {
+        P[(long long)(c0 + j) * h + row] = x[j];
+      }
+    }
+  }
+
+  if (t.rb == 0)
+  {
+    if (tid == 0 && nper)
+    {
+      atomicAdd(n_perturbed, nper);
+    }
+    if (tid < w)
+    {
+      D[s.first + c0 + tid] = dsh[tid];
+    }
+    if (t.slot < 0)
+    {
+      for (int idx = tid; idx < w * w; idx += RB)
+      {
+        const int i = idx % w, j = idx / w;
+        if (i >= j)
+        {
+          P[(long long)(c0 + j) * h + c0 + i] = i == j ? 1.0 : A[i][j];
+        }
+      }
+    }
+    else
+    {
+      double* sc = scratch + (long long)t.slot * NB * NB;
+      for (int idx = tid; idx < w * w; idx += RB)
+      {
+        const int i = idx % w, j = idx / w;
+        sc[idx] = i == j ? 1.0 : A[i][j];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DMMA: D(8x8) += A(8x4, row) * B(4x8, col). Lane l holds a = A[l/4][l%4], b = B[l%4][l/4],
+// c0/c1 = C[l/4][2*(l%4) + 0/1].
+__device__ __forceinline__ void
+dmma(double& c0, double& c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int KC   = 16;       // k-chunk staged per iteration
+constexpr int LDT  = TILE + 4; // padded leading dimension: (LDT mod 16) == 4 -> conflict-free fragments
+
+// C(tile) -= Lrow_i * diag(d) * Lrow_j^T over front columns [kb, ke). Operand rows come from the
+// panel (column-major, leading dimension h): A-rows start at ra0, B-rows at rb0, at most na / nb
+// valid. Output element (i, j) of the tile lives at C[i + j * ldc]; only gi >= gj are touched,
+// where gi/gj are the global row/column ordinals used for the lower-triangle mask.
+__device__ __forceinline__ void
+tile_update(const double* __restrict__ P,
+            int h,
+            int kb,
+            int ke,
+            const double* __restrict__ d,
+            int ra0,
+            int na,
+            int rb0,
+            int nb,
+            double* __restrict__ C,
+            long long ldc,
+            int gi0,
+            int gj0,
+            bool accumulate,
+            double (*As)[LDT],
+            double (*Bs)[LDT])
+{
+  const int tid  = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wy = warp >> 1, wx = warp & 1;
+  // a 32x32 warp tile strictly above the diagonal has nothing to do (diagonal tiles only)
+  const bool active = (gi0 + wy * 32 + 31) >= (gj0 + wx * 32);
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+    {
+      acc[a][b][0] = 0.0;
+      acc[a][b][1] = 0.0;
+    }
+
+  for (int kc = kb; kc < ke; kc += KC)
+  {
+    // stage KC x TILE of both operands; consecutive threads read consecutive rows (coalesced)
+    for (int idx = tid; idx < KC * TILE; idx += 128)
+    {
+      const int kk = idx / TILE, ii = idx % TILE;
+      const int col = kc + kk;
+      double av = 0.0, bv = 0.0;
+      if (col < ke)
+      {
+        const double* pc = P + (long long)col * h;
+        if (ii < na)
+        {
+          av = pc[ra0 + ii];
+        }
+        if (ii < nb)
+        {
+          bv = pc[rb0 + ii] * d[col];
+        }
+      }
+      As[kk][ii] = av;
+      Bs[kk][ii] = bv;
+    }
+    __syncthreads();
+    if (active)
+    {
+#pragma unroll
+      for (int k4 = 0; k4 < KC / 4; ++k4)
+      {
+        const int kr = k4 * 4 + (lane & 3);
+        double af[4], bf[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+        {
+          af[a] = As[kr][wy * 32 + a * 8 + (lane >> 2)];
+          bf[a] = Bs[kr][wx * 32 + a * 8 + (lane >> 2)];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+          {
+            dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+          }
+      }
+    }
+    __syncthreads();
+  }
+  if (!active)
+  {
+    return;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+      {
+        const int i = wy * 32 + a * 8 + (lane >> 2);
+        const int j = wx * 32 + b * 8 + 2 * (lane & 3) + e;
+        if (i < na && j < nb && gi0 + i >= gj0 + j)
+        {
+          double* c = C + i + (long long)j * ldc;
+          *c        = (accumulate ? *c : 0.0) - acc[a][b][e];
+        }
+      }
+}
+
+__global__ void __launch_bounds__(128)
+k_update(const Task5* __restrict__ tasks,
+         const SnMeta* __restrict__ sn,
+         double* __restrict__ L,
+         double* __restrict__ U,
+         const double* __restrict__ D,
+         const double* __restrict__ scratch)
+{
+  __shared__ double As[KC][LDT];
+  __shared__ double Bs[KC][LDT];
+  const Task5 t  = tasks[blockIdx.x];
+  const SnMeta s = sn[t.sn];
+  const int h    = s.k + s.r;
+  double* P      = L + s.Lptr;
+  const int c0   = t.t * NB;
+  const int w    = min(NB, s.k - c0);
+  if (t.kind == UPD_DIAGCOPY)
+  {
+    const double* sc = scratch + (long long)t.i0 * NB * NB;
+    for (int idx = threadIdx.x; idx < w * w; idx += 128)
+    {
+      const int i = idx % w, j = idx / w;
+      if (i >= j)
+      {
+        P[(long long)(c0 + j) * h + c0 + i] = sc[idx];
+      }
+    }
+    return;
+  }
+  if (t.kind == UPD_INPANEL)
+  {
+    // front rows [i0, i0+64) x front columns [j0, j0+64), columns < k, rows < h
+    const int na = min(TILE, h - t.i0), nb = min(TILE, s.k - t.j0);
+    tile_update(P, h, c0, c0 + w, D + s.first, t.i0, na, t.j0, nb, P + t.i0 + (long long)t.j0 * h, h, t.i0, t.j0, true, As, Bs);
+    return;
+  }
+  // UPD_SCHUR: update rows/cols [i0, i0+64) x [j0, j0+64) of U (r x r), operands are panel rows k + ...
+  {
+    const int na = min(TILE, s.r - t.i0), nb = min(TILE, s.r - t.j0);
+    double* Um   = U + s.Uoff;
+    const bool accumulate = s.child_end > s.child_begin;
+    tile_update(P, h, 0, s.k, D + s.first, s.k + t.i0, na, s.k + t.j0, nb, Um + t.i0 + (long long)t.j0 * s.r, s.r, t.i0, t.j0, accumulate, As, Bs);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+void
+enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc)
+{
+  const Plan& P = *dp.plan;
+  if (P.m == 0)
+  {
+    return;
+  }
+  B200_CUDA(cudaMemsetAsync(nb.L, 0, sizeof(double) * (size_t)P.Lptr[P.nsuper], stream));
+  B200_CUDA(cudaMemsetAsync(nb.scal, 0, sizeof(double) * 4, stream));
+  B200_CUDA(cudaMemsetAsync(nb.n_perturbed, 0, sizeof(int), stream));
+  {
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((P.nnzS + threads - 1) / threads);
+    k_assemble<<<blocks, threads, 0, stream>>>(P.nnzS, dp.Sdest.p, dp.Sgsrc.p, dp.Sterm_ptr.p, dp.Sterm_a.p, dp.Sterm_b.p, dp.Sterm_d.p, nb.val, nb.L);
+    lc.tick();
+    const unsigned rb = (unsigned)std::min<long long>((P.m + threads - 1) / threads, 1184);
+    k_diagmax<<<rb, threads, 0, stream>>>(P.m, dp.Sdiag.p, nb.L, (unsigned long long*)nb.scal);
+    lc.tick();
+    k_set_tau<<<1, 1, 0, stream>>>(nb.scal);
+    lc.tick();
+  }
+  for (const Stage& st : P.stages)
+  {
+    if (st.zero_end > st.zero_begin)
+    {
+      dim3 grid((unsigned)(st.zero_end - st.zero_begin), 16);
+      k_zero_updates<<<grid, 256, 0, stream>>>(dp.zero_sn.p + st.zero_begin, dp.sn.p, nb.U);
+      lc.tick();
+    }
+    if (st.ea_end > st.ea_begin)
+    {
+      k_extend_add<<<(unsigned)(st.ea_end - st.ea_begin), 128, 0, stream>>>(dp.ea_tasks.p + st.ea_begin, dp.sn.p, dp.rel.p, nb.L, nb.U);
+      lc.tick();
+    }
+    if (st.pan_end > st.pan_begin)
+    {
+      k_panel<<<(unsigned)(st.pan_end - st.pan_begin), RB, 0, stream>>>(dp.pan_tasks.p + st.pan_begin, dp.sn.p, nb.L, nb.D, nb.scratch, nb.scal, nb.n_perturbed);
+      lc.tick();
+    }
+    if (st.upd_end > st.upd_begin)
+    {
+      k_update<<<(unsigned)(st.upd_end - st.upd_begin), 128, 0, stream>>>(dp.upd_tasks.p + st.upd_begin, dp.sn.p, nb.L, nb.U, nb.D, nb.scratch);
+      lc.tick();
+    }
+  }
+  // contiguous operator values for the solve
+  const int threads = 256;
+  if (P.nE > 0)
+  {
+    k_gather<<<(P.nE + threads - 1) / threads, threads, 0, stream>>>(P.nE, dp.dE_src.p, nb.val, nb.dE);
+    lc.tick();
+  }
+  const int nnzA = (int)P.Acsc_src.size();
+  if (nnzA > 0)
+  {
+    k_gather<<<(nnzA + threads - 1) / threads, threads, 0, stream>>>(nnzA, dp.Acsc_src.p, nb.val, nb.Acsc_val);
+    lc.tick();
+    k_gather<<<(nnzA + threads - 1) / threads, threads, 0, stream>>>(nnzA, dp.Acsr_src.p, nb.val, nb.Acsr_val);
+    lc.tick();
+  }
+  const int nnzG = (int)P.Gsym_src.size();
+  if (nnzG > 0)
+  {
+    k_gather<<<(nnzG + threads - 1) / threads, threads, 0, stream>>>(nnzG, dp.Gsym_src.p, nb.val, nb.Gsym_val);
+    lc.tick();
+  }
+  B200_CUDA(cudaGetLastError());
+}
+
+} // namespace b200

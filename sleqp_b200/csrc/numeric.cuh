@@ -1,0 +1,59 @@
+// numeric.cuh -- interfaces between the C-ABI layer (fact.cu) and the kernel files.
+#pragma once
+#include "device.cuh"
+
+namespace b200
+{
+
+// Raw device pointers of one factorization (owned by the handle).
+struct NumericBuffers
+{
+  const double* val; // values of tril(K), same order as the caller's CSC
+  double* L;         // supernodal panels
+  double* U;         // update-matrix workspace
+  double* D;         // pivots of S (new labels)
+  double* scratch;   // diagonal-block scratch slots
+  double* scal;      // [0] max|S_jj|, [1] pivot threshold, [2..3] reduction results
+  int* n_perturbed;
+  double* dE;        // pivots of the E block
+  double* Acsc_val;
+  double* Acsr_val;
+  double* Gsym_val;
+};
+
+struct SolveBuffers
+{
+  double* rhs;  // N, original K indexing
+  double* z;    // N, solution
+  double* res;  // N, residual / correction right-hand side
+  double* dz;   // N, correction
+  double* bR;   // m, reduced right-hand side (new labels)
+  double* y;    // m, forward result / solution of the reduced system (new labels)
+  double* W;    // front vectors (sum of front heights)
+};
+
+// raise the dynamic shared-memory limit of the solve kernels (once per process, before capture)
+void configure_solve_kernels();
+
+void enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc);
+
+// One solve K z = rhs with `refine` refinement steps, everything on `stream`.
+void enqueue_solve(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, int refine, cudaStream_t stream, LaunchCounter& lc);
+
+// scal[2] = ||rhs - K z||_2^2, scal[3] = ||rhs||_2^2
+void enqueue_residual_norms(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc);
+
+// rhs[i] = 0 for all i, then rhs[idx[q]] = val[q]; idx == nullptr means the contiguous range
+// [first, first + nnz).
+void enqueue_scatter_rhs(double* rhs, int n, int nnz, const int* d_idx, int first, const double* d_val, cudaStream_t stream, LaunchCounter& lc);
+
+// deterministic pseudo-random probe right-hand side
+void enqueue_probe_rhs(double* rhs, int n, cudaStream_t stream, LaunchCounter& lc);
+
+// min/max |d| over both pivot sets -> scal[2], scal[3]
+void enqueue_pivot_range(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc);
+
+// out[i] = dE[i] for i < nE, D[i - nE] otherwise
+void enqueue_copy_pivots(const DevPlan& dp, const NumericBuffers& nb, double* out, cudaStream_t stream, LaunchCounter& lc);
+
+} // namespace b200

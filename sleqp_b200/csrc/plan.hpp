@@ -87,6 +87,7 @@ struct Plan
   // assembly of S straight into the panels: S_e = val[gsrc] - sum_t val[a]*val[b]/val[d]
   i64 nnzS = 0;
   std::vector<i64> Sdest;
+  std::vector<i64> Sdiag; // panel offset of S(j,j) for every column j
   std::vector<int> Sgsrc;
   std::vector<i64> Sterm_ptr;
   std::vector<int> Sterm_a, Sterm_b, Sterm_d;

@@ -1037,6 +1037,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     P.nnzS = Sptr[m];
     std::vector<int> Srow((size_t)P.nnzS);
     P.Sdest.resize((size_t)P.nnzS);
+    P.Sdiag.resize((size_t)m);
     for (int j = 0; j < m; ++j)
     {
       i64 o     = Sptr[j];
@@ -1072,6 +1073,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         }
         P.Sdest[q] = P.Lptr[T] + (i64)(j - f) * h + rowpos;
       }
+      P.Sdiag[j] = P.Sdest[Sptr[j]];
     }
     auto entry_id = [&](int row, int col) -> i64 {
       const int* b  = Srow.data() + Sptr[col];

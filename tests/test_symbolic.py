@@ -1,0 +1,118 @@
+"""Host symbolic analysis (sleqp_b200/csrc/symbolic.cpp) through the C-ABI, no GPU needed:
+structural outputs vs an independent symbolic factorization, and the numeric plan executed by a
+task-by-task numpy emulation vs a sparse LU of the same K."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from oracle import sleqp_oracle as orc
+from oracle.multifrontal_emul import Emulated
+from sleqp_b200 import B200Error, Symbolic, problems
+
+CASES = {
+    "config1": lambda: problems.config(0),
+    "poisson2d_g8": lambda: problems.poisson_control(8, 2),
+    "poisson2d_g24": lambda: problems.poisson_control(24, 2, seed=2),
+    "poisson3d_g6": lambda: problems.poisson_control(6, 3),
+    "chain_n2000": lambda: problems.chain_rosenbrock(2000, 0.1),
+    "chain_n33_noactive": lambda: problems.chain_rosenbrock(33, 0.0),
+    "no_constraints": lambda: _no_cons(),
+}
+
+
+def _no_cons():
+    p = problems.chain_rosenbrock(20, 0.0)
+    p.active_cons = p.active_cons[:0]
+    return p
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_structure_matches_independent_symbolic(name):
+    p = CASES[name]()
+    cp, ri, v = p.kkt_lower()
+    s = Symbolic(p.N, cp, ri, v)
+    perm, parent, cc, sf = s.structure()
+    assert sorted(perm.tolist()) == list(range(p.N))
+    par_ref, cc_ref = orc.symbolic_reference(p.N, cp, ri, perm)
+    assert np.array_equal(parent, par_ref)  # bit-exact: functions of pattern and permutation only
+    assert np.array_equal(cc, cc_ref)
+    st = s.stats()
+    assert st["nnz_L"] == int(cc[st["n_elim"]:].sum())
+    # every constraint is ordered after every variable it touches (SURVEY.md hard part 1)
+    pinv = np.empty(p.N, dtype=np.int64)
+    pinv[perm] = np.arange(p.N)
+    for j in range(p.n):
+        rows = ri[cp[j] + 1: cp[j + 1]]
+        assert np.all(pinv[rows] > pinv[j])
+    # supernodes partition the order, the etree is a forest with parent > child
+    assert sf[0] == 0 and sf[-1] == p.N and np.all(np.diff(sf) > 0)
+    nz = parent >= 0
+    assert np.all(parent[nz] > np.nonzero(nz)[0])
+
+
+@pytest.mark.parametrize("name", ["config1", "poisson2d_g24", "poisson3d_g6", "chain_n2000"])
+def test_plan_emulation_solves_kkt(name):
+    p = CASES[name]()
+    cp, ri, v = p.kkt_lower()
+    s = Symbolic(p.N, cp, ri, v)
+    em = Emulated(s.plan(), v)
+    assert em.n_perturbed == 0
+    K = p.kkt_full()
+    for kind in ("project_nullspace", "solve_min_norm", "solve_lsq"):
+        idx, val = p.rhs(kind, 3)
+        b = orc.vec_to_raw(idx, val, p.N)
+        z = em.solve(b, refine=0)
+        assert np.linalg.norm(K @ z - b) <= 1e-12 * np.linalg.norm(b)
+        zr = spla.spsolve(K.tocsc(), b)
+        assert np.linalg.norm(z - zr) <= 1e-10 * np.linalg.norm(zr)
+
+
+def test_same_pattern_same_structure_different_values():
+    a = problems.chain_rosenbrock(300, 0.2, seed=1)
+    b = problems.chain_rosenbrock(300, 0.2, seed=1)
+    b.J.data[:] = np.random.default_rng(9).uniform(0.5, 1.5, size=len(b.J.data))
+    sa = Symbolic(a.N, *a.kkt_lower())
+    sb = Symbolic(b.N, *b.kkt_lower())
+    assert sa.stats()["pattern_hash"] == sb.stats()["pattern_hash"]
+    assert sa.stats()["perm_hash"] == sb.stats()["perm_hash"]
+    c = problems.chain_rosenbrock(300, 0.2, seed=2)  # other active set => other pattern
+    assert Symbolic(c.N, *c.kkt_lower()).stats()["pattern_hash"] != sa.stats()["pattern_hash"]
+
+
+def test_full_matrix_input_equals_lower_input():
+    p = problems.poisson_control(6, 2)
+    cp, ri, v = p.kkt_lower()
+    K = p.kkt_full()
+    K.sort_indices()
+    a = Symbolic(p.N, cp, ri, v, lower_only=True).structure()
+    b = Symbolic(p.N, K.indptr, K.indices, K.data, lower_only=False).structure()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_malformed_input_is_rejected():
+    p = problems.config(0)
+    cp, ri, v = p.kkt_lower()
+    bad = ri.copy()
+    bad[1], bad[2] = bad[2], bad[1]  # rows not increasing in a column
+    with pytest.raises(B200Error):
+        Symbolic(p.N, cp, bad, v)
+    K = p.kkt_full()
+    K.sort_indices()
+    with pytest.raises(B200Error):  # upper entries in a matrix declared lower
+        Symbolic(p.N, K.indptr, K.indices, K.data, lower_only=True)
+    # off-diagonal coupling inside the (1,1) block is outside the supported class
+    import scipy.sparse as sp
+
+    K2 = sp.tril(K).tolil()
+    K2[1, 0] = 0.5
+    K2 = K2.tocsc()
+    K2.sort_indices()
+    with pytest.raises(B200Error) as e:
+        Symbolic(p.N, K2.indptr, K2.indices, K2.data)
+    assert e.value.code == 4
+
+
+def test_empty_matrix():
+    s = Symbolic(0, np.zeros(1, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0))
+    assert s.stats()["n"] == 0
