@@ -119,6 +119,16 @@ B200_API int b200_fact_solution_ptr(b200_fact* handle, int begin, int end, const
  * device-resident CG: d_rhs and d_sol are device pointers to n doubles. */
 B200_API int b200_fact_solve_device(b200_fact* handle, const double* d_rhs, double* d_sol);
 
+/* Numeric refactorization with new values already in device memory (same pattern and value order
+ * as the last set_matrix; no probe solve, no host synchronisation): the "inputs resident in HBM"
+ * leg of the benchmark and the building block for device-side KKT assembly. */
+B200_API int b200_fact_refactor_device(b200_fact* handle, const double* d_val);
+
+/* Device time (ms, CUDA events, mean of `reps` eager runs) of the four phases of one unrefined
+ * solve: ms_out[0] E-block elimination, [1] forward sweep, [2] backward sweep, [3] back-substitution.
+ * For roofline arithmetic in bench.py. */
+B200_API int b200_fact_profile_solve(b200_fact* handle, int reps, double* ms_out);
+
 /* rcond = min|d_i| / max|d_i| over the pivots of D (cf. cholmod_l_rcond, fact_cholmod.c:204). */
 B200_API int b200_fact_rcond(b200_fact* handle, double* rcond);
 
@@ -172,6 +182,9 @@ B200_API int b200_mat_mult_vec_trans(b200_mat* handle, int nnz_v, const int* idx
 B200_API int b200_mat_mult_vec_device(b200_mat* handle, const double* d_x, double* d_y);
 B200_API int b200_mat_mult_vec_trans_device(b200_mat* handle, const double* d_v, double* d_y);
 B200_API void* b200_mat_stream(b200_mat* handle);
+/* Launch this matrix's products on another CUDA stream (e.g. b200_fact_stream of the factorization the
+ * products alternate with in the projected-CG loop); the handle does not own that stream. */
+B200_API int b200_mat_set_stream(b200_mat* handle, void* stream);
 B200_API int b200_mat_free(b200_mat** handle);
 
 /* ---- misc ------------------------------------------------------------------------------ */

@@ -51,11 +51,11 @@ _lib = None
 # every symbol include/sleqp_b200.h declares (tests check they are all exported)
 SYMBOLS = [
     "b200_fact_create", "b200_fact_set_matrix", "b200_fact_solve", "b200_fact_solution",
-    "b200_fact_solution_ptr", "b200_fact_solve_device", "b200_fact_rcond", "b200_fact_stats",
+    "b200_fact_solution_ptr", "b200_fact_solve_device", "b200_fact_refactor_device", "b200_fact_profile_solve", "b200_fact_rcond", "b200_fact_stats",
     "b200_fact_structure", "b200_fact_pivots", "b200_fact_stream", "b200_fact_free", "b200_last_error",
     "b200_symbolic_analyze", "b200_symbolic_stats", "b200_symbolic_structure", "b200_symbolic_export",
     "b200_symbolic_free", "b200_mat_create", "b200_mat_set", "b200_mat_mult_vec", "b200_mat_mult_vec_trans",
-    "b200_mat_mult_vec_device", "b200_mat_mult_vec_trans_device", "b200_mat_stream", "b200_mat_free",
+    "b200_mat_mult_vec_device", "b200_mat_mult_vec_trans_device", "b200_mat_stream", "b200_mat_set_stream", "b200_mat_free",
     "b200_device_count", "b200_launch_count",
 ]
 
@@ -78,6 +78,8 @@ def lib():
     L.b200_fact_solution.argtypes = [vp, C.c_int, C.c_int, dp]
     L.b200_fact_solution_ptr.argtypes = [vp, C.c_int, C.c_int, C.POINTER(dp)]
     L.b200_fact_solve_device.argtypes = [vp, vp, vp]
+    L.b200_fact_refactor_device.argtypes = [vp, vp]
+    L.b200_fact_profile_solve.argtypes = [vp, C.c_int, dp]
     L.b200_fact_rcond.argtypes = [vp, dp]
     L.b200_fact_stats.argtypes = [vp, C.POINTER(Stats)]
     L.b200_fact_structure.argtypes = [vp, ip, ip, ip, ip, ip]
@@ -98,6 +100,7 @@ def lib():
     L.b200_mat_mult_vec_trans_device.argtypes = [vp, vp, vp]
     L.b200_mat_stream.argtypes = [vp]
     L.b200_mat_stream.restype = vp
+    L.b200_mat_set_stream.argtypes = [vp, vp]
     L.b200_mat_free.argtypes = [C.POINTER(vp)]
     L.b200_device_count.restype = C.c_int
     L.b200_launch_count.restype = C.c_int64

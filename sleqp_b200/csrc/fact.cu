@@ -435,6 +435,86 @@ b200_fact_set_matrix(b200_fact* F, int n_rows, int n_cols, int nnz, const int* c
 }
 
 int
+b200_fact_refactor_device(b200_fact* F, const double* d_val)
+{
+  if (!F || !d_val)
+  {
+    return set_error(B200_ERR_ARG, "null argument");
+  }
+  if (!F->factored)
+  {
+    return set_error(B200_ERR_STATE, "refactor needs a previous successful set_matrix with the same pattern");
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaSetDevice(F->device));
+    const Plan& P = *F->dp.plan;
+    if (P.N == 0)
+    {
+      return (int)B200_OK;
+    }
+    B200_CUDA(cudaEventRecord(F->ev_a, F->stream));
+    B200_CUDA(cudaMemcpyAsync(F->val.p, d_val, sizeof(double) * (size_t)P.nnzK_input, cudaMemcpyDeviceToDevice, F->stream));
+    const NumericBuffers nb = F->nbuf();
+    run_graph(F, F->g_numeric, [&](LaunchCounter& lc) {
+      enqueue_numeric(F->dp, nb, F->stream, lc);
+      enqueue_pivot_range(F->dp, nb, F->stream, lc);
+    });
+    B200_CUDA(cudaEventRecord(F->ev_b, F->stream));
+    F->timed_numeric = true;
+    return (int)B200_OK;
+  });
+}
+
+int
+b200_fact_profile_solve(b200_fact* F, int reps, double* ms_out)
+{
+  if (!F || !ms_out || reps <= 0)
+  {
+    return set_error(B200_ERR_ARG, "bad argument");
+  }
+  if (!F->factored)
+  {
+    return set_error(B200_ERR_STATE, "profile needs a factorization");
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaSetDevice(F->device));
+    const NumericBuffers nb = F->nbuf();
+    const SolveBuffers sb   = F->sbuf();
+    LaunchCounter eager;
+    double acc[4] = {0, 0, 0, 0};
+    cudaEvent_t ev[5];
+    for (auto& e : ev)
+    {
+      B200_CUDA(cudaEventCreate(&e));
+    }
+    for (int it = 0; it < reps + 1; ++it)
+    {
+      enqueue_solve_phases(F->dp, nb, sb, F->stream, eager, ev);
+      B200_CUDA(cudaStreamSynchronize(F->stream));
+      if (it == 0)
+      {
+        continue; // warm-up
+      }
+      for (int p = 0; p < 4; ++p)
+      {
+        float ms = 0.f;
+        B200_CUDA(cudaEventElapsedTime(&ms, ev[p], ev[p + 1]));
+        acc[p] += ms;
+      }
+    }
+    for (auto& e : ev)
+    {
+      cudaEventDestroy(e);
+    }
+    for (int p = 0; p < 4; ++p)
+    {
+      ms_out[p] = acc[p] / reps;
+    }
+    return (int)B200_OK;
+  });
+}
+
+int
 b200_fact_solve(b200_fact* F, int nnz_rhs, const int* idx, const double* val, int dim)
 {
   if (!F)

@@ -422,14 +422,11 @@ void
 enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc)
 {
   const Plan& P = *dp.plan;
-  if (P.m == 0)
-  {
-    return;
-  }
-  B200_CUDA(cudaMemsetAsync(nb.L, 0, sizeof(double) * (size_t)P.Lptr[P.nsuper], stream));
   B200_CUDA(cudaMemsetAsync(nb.scal, 0, sizeof(double) * 4, stream));
   B200_CUDA(cudaMemsetAsync(nb.n_perturbed, 0, sizeof(int), stream));
+  if (P.m > 0)
   {
+    B200_CUDA(cudaMemsetAsync(nb.L, 0, sizeof(double) * (size_t)P.Lptr[P.nsuper], stream));
     const int threads = 256;
     const unsigned blocks = (unsigned)((P.nnzS + threads - 1) / threads);
     k_assemble<<<blocks, threads, 0, stream>>>(P.nnzS, dp.Sdest.p, dp.Sgsrc.p, dp.Sterm_ptr.p, dp.Sterm_a.p, dp.Sterm_b.p, dp.Sterm_d.p, nb.val, nb.L);

@@ -40,6 +40,10 @@ void enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t s
 // One solve K z = rhs with `refine` refinement steps, everything on `stream`.
 void enqueue_solve(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, int refine, cudaStream_t stream, LaunchCounter& lc);
 
+// one unrefined solve launched eagerly with events around its four phases:
+// ev[0] pre ev[1] forward sweep ev[2] backward sweep ev[3] post ev[4]
+void enqueue_solve_phases(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc, cudaEvent_t* ev);
+
 // scal[2] = ||rhs - K z||_2^2, scal[3] = ||rhs||_2^2
 void enqueue_residual_norms(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc);
 

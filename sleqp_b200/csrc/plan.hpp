@@ -59,6 +59,7 @@ struct Plan
 {
   int N = 0, nE = 0, m = 0;
   i64 nnzK = 0;
+  i64 nnzK_input = 0; // entries of the caller's CSC (== nnzK for lower-triangular input)
   uint64_t pattern_hash = 0, perm_hash = 0;
 
   // node classification / index maps

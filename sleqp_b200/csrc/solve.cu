@@ -414,14 +414,22 @@ nblocks(long long n, int threads)
 constexpr size_t SOLVE_SMEM_LIMIT = 160 * 1024;
 
 static void
-solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, const double* in, double* out, cudaStream_t stream, LaunchCounter& lc)
+solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, const double* in, double* out, cudaStream_t stream, LaunchCounter& lc, cudaEvent_t* ev = nullptr)
 {
+  auto mark = [&](int i) {
+    if (ev)
+    {
+      B200_CUDA(cudaEventRecord(ev[i], stream));
+    }
+  };
+  mark(0);
   const Plan& P = *dp.plan;
   const int T   = 256;
   if (P.m > 0)
   {
     k_pre<<<nblocks(P.m, T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.k_of_e.p, dp.pinv.p, dp.Acsr_ptr.p, dp.Acsr_col.p, nb.Acsr_val, nb.dE, in, sb.bR);
     lc.tick();
+    mark(1);
     for (int l = 0; l < P.nlevels; ++l)
     {
       const int cnt          = P.lvl_ptr[l + 1] - P.lvl_ptr[l];
@@ -431,6 +439,7 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
       k_fwd_level<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.lvl_sn.p + P.lvl_ptr[l], dp.sn.p, dp.child_idx.p, dp.rel.p, nb.L, sb.bR, sb.y, sb.W, use_smem);
       lc.tick();
     }
+    mark(2);
     for (int l = P.nlevels - 1; l >= 0; --l)
     {
       const int cnt          = P.lvl_ptr[l + 1] - P.lvl_ptr[l];
@@ -440,6 +449,7 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
       k_bwd_level<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.lvl_sn.p + P.lvl_ptr[l], dp.sn.p, dp.Ridx.p, nb.L, nb.D, sb.y, sb.W, use_smem);
       lc.tick();
     }
+    mark(3);
     k_post_r<<<nblocks(P.m, T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.pinv.p, sb.y, out);
     lc.tick();
   }
@@ -448,6 +458,7 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
     k_post_e<<<nblocks(P.nE, T), T, 0, stream>>>(P.nE, dp.k_of_e.p, dp.pinv.p, dp.Acsc_ptr.p, dp.Acsc_row.p, nb.Acsc_val, nb.dE, in, sb.y, out);
     lc.tick();
   }
+  mark(4);
 }
 
 static void
@@ -477,6 +488,13 @@ configure_solve_kernels()
     B200_CUDA(cudaFuncSetAttribute(k_bwd_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
     done = true;
   }
+}
+
+void
+enqueue_solve_phases(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc, cudaEvent_t* ev)
+{
+  solve_once(dp, nb, sb, sb.rhs, sb.z, stream, lc, ev);
+  B200_CUDA(cudaGetLastError());
 }
 
 void

@@ -118,6 +118,7 @@ struct b200_mat
 {
   int device          = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
   int num_rows = 0, num_cols = 0, nnz = 0;
   bool have = false;
   std::vector<int> h_cols, h_rows; // cached pattern
@@ -232,7 +233,8 @@ b200_mat_create(b200_mat** handle, int device)
     B200_CUDA(cudaSetDevice(dev));
     std::unique_ptr<b200_mat> M(new b200_mat());
     M->device = dev;
-    B200_CUDA(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaStreamCreateWithFlags(&M->own_stream, cudaStreamNonBlocking));
+    M->stream = M->own_stream;
     *handle = M.release();
     return (int)B200_OK;
   });
@@ -407,6 +409,19 @@ b200_mat_mult_vec_trans(b200_mat* M, int nnz_v, const int* idx, const double* va
   });
 }
 
+int
+b200_mat_set_stream(b200_mat* M, void* stream)
+{
+  if (!M)
+  {
+    return set_error(B200_ERR_ARG, "null handle");
+  }
+  cudaSetDevice(M->device);
+  cudaStreamSynchronize(M->stream);
+  M->stream = stream ? (cudaStream_t)stream : M->own_stream;
+  return B200_OK;
+}
+
 void*
 b200_mat_stream(b200_mat* M)
 {
@@ -425,7 +440,10 @@ b200_mat_free(b200_mat** handle)
   if (M->stream)
   {
     cudaStreamSynchronize(M->stream);
-    cudaStreamDestroy(M->stream);
+  }
+  if (M->own_stream)
+  {
+    cudaStreamDestroy(M->own_stream);
   }
   delete M;
   *handle = nullptr;

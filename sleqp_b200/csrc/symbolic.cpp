@@ -384,6 +384,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   P       = Plan();
   P.N     = n;
   P.nnzK  = 0;
+  P.nnzK_input = nnz;
   P.pattern_hash = hash_pattern(n, nnz, colptr, rowidx, val, lower_only);
 
   // ---- classification ----------------------------------------------------------------

@@ -146,6 +146,16 @@ class Fact:
     def solve_device(self, d_rhs_ptr: int, d_sol_ptr: int):
         check(lib().b200_fact_solve_device(self._h, C.c_void_p(d_rhs_ptr), C.c_void_p(d_sol_ptr)))
 
+    def refactor_device(self, d_val_ptr: int):
+        """Numeric refactorization from values resident in device memory (same pattern)."""
+        check(lib().b200_fact_refactor_device(self._h, C.c_void_p(d_val_ptr)))
+
+    def profile_solve(self, reps=20):
+        """Mean device ms of (E-elimination, forward sweep, backward sweep, back-substitution)."""
+        out = np.zeros(4, dtype=np.float64)
+        check(lib().b200_fact_profile_solve(self._h, int(reps), _pd(out)))
+        return out
+
     def cond(self) -> float:
         """sleqp_fact_cond (fact.c:104-118): 1 / rcond."""
         r = C.c_double()
@@ -213,6 +223,9 @@ class Mat:
         check(lib().b200_mat_mult_vec_trans(self._h, int(len(idx)), _pi(idx), _pd(val), _pd(out)))
         keep = np.nonzero(np.abs(out) > eps)[0].astype(np.int32)
         return keep, out[keep]
+
+    def set_stream(self, stream_ptr: int):
+        check(lib().b200_mat_set_stream(self._h, C.c_void_p(stream_ptr)))
 
     def mult_vec_device(self, d_x: int, d_y: int):
         check(lib().b200_mat_mult_vec_device(self._h, C.c_void_p(d_x), C.c_void_p(d_y)))
