@@ -366,6 +366,12 @@ def run_ours(args, rank, world, local_rank):
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+    # release the native handles while the CUDA context is certainly alive
+    torch.cuda.synchronize()
+    mJ.set_stream(0)
+    mH.set_stream(0)
+    for obj in (mJ, mH, fact):
+        obj.release()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

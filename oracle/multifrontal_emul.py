@@ -27,6 +27,7 @@ class Emulated:
         self.N = int(plan["n"])
         self.n_perturbed = 0
         self._factor()
+        self._invert()
 
     # ---------------------------------------------------------------- geometry helpers
     def _geom(self, T):
@@ -88,6 +89,84 @@ class Emulated:
                 self._panel(int(T), int(t), int(rb), int(slot), scratch)
             for T, t, kind, i0, j0 in p["upd_tasks"][ub:ue]:
                 self._update(int(T), int(t), int(kind), int(i0), int(j0), scratch, bool(has_children[T]))
+
+    # ---------------------------------------------------------------- selective inversion
+    def mpanel(self, T):
+        f, k, r, h = self._geom(T)
+        o = int(self.p["Lptr"][T])
+        return self.Mt[o : o + h * k].reshape((k, h)).T
+
+    def _invert(self):
+        """Minv = [L11^-1; -L21 L11^-1] per supernode, executed tile task by tile task."""
+        p = self.p
+        self.Mt = np.zeros_like(self.L)
+        tmp = np.full(max(1, int(p["Tptr"][-1])), np.nan)
+        ns = int(p["n_supernodes"])
+        for T in range(ns):  # what k_panel publishes: inverse of every NB x NB diagonal block
+            f, k, r, h = self._geom(T)
+            P, M = self.panel(T), self.mpanel(T)
+            for c0 in range(0, k, NB):
+                w = min(NB, k - c0)
+                L11 = np.tril(P[c0 : c0 + w, c0 : c0 + w], -1) + np.eye(w)
+                M[c0 : c0 + w, c0 : c0 + w] = np.tril(np.linalg.inv(L11))
+        ph = p["inv_phase_ptr"]
+        for q in range(len(ph) - 1):
+            for T, kind, i0, j0, kb, ke in p["inv_tasks"][int(ph[q]) : int(ph[q + 1])]:
+                T, kind, i0, j0, kb, ke = int(T), int(kind), int(i0), int(j0), int(kb), int(ke)
+                f, k, r, h = self._geom(T)
+                P, M = self.panel(T), self.mpanel(T)
+                Tm = tmp[int(p["Tptr"][T]) : int(p["Tptr"][T]) + k * k].reshape((k, k)).T if k > NB else None
+                if kind == 0:  # T1: Tmp = L11[C, A] * Ainv ; A columns end at ke
+                    i1, j1 = min(i0 + TILE, k), min(j0 + TILE, ke)
+                    Tm[i0:i1, j0:j1] = P[i0:i1, kb:ke] @ M[kb:ke, j0:j1]
+                elif kind == 1:  # T2: Minv[C, A] = -Cinv * Tmp ; C starts at kb (= end of the A columns)
+                    i1, j1 = min(i0 + TILE, k), min(j0 + TILE, kb)
+                    M[i0:i1, j0:j1] = -(M[i0:i1, kb:ke] @ Tm[kb:ke, j0:j1])
+                else:  # Z: Minv[k + i, j] = -sum_q L21[i, q] Linv[q, j]
+                    i1, j1 = min(i0 + TILE, r), min(j0 + TILE, k)
+                    M[k + i0 : k + i1, j0:j1] = -(P[k + i0 : k + i1, kb:ke] @ M[kb:ke, j0:j1])
+
+    def solve_reduced_minv(self, b_new):
+        """The v2 device solve: per supernode y = Minv b (forward), x = Minv^T [z; x_rows] (backward),
+        executed chunk task by chunk task."""
+        p = self.p
+        W = np.full(int(p["Wptr"][-1]), np.nan)
+        y = np.full(self.m, np.nan)
+        x = np.full(self.m, np.nan)
+        for lv in range(int(p["n_levels"])):
+            for T, row0, nrows in p["fwd_tasks"][int(p["fwd_ptr"][lv]) : int(p["fwd_ptr"][lv + 1])]:
+                T, row0, nrows = int(T), int(row0), int(nrows)
+                f, k, r, h = self._geom(T)
+                M = self.mpanel(T)
+                bT = b_new[f : f + k].copy()
+                out = np.zeros(nrows)
+                for c in p["child_idx"][int(p["child_ptr"][T]) : int(p["child_ptr"][T + 1])]:
+                    c = int(c)
+                    fc, kc, rc, hc = self._geom(c)
+                    rel = p["rel"][int(p["Rptr"][c]) : int(p["Rptr"][c + 1])]
+                    wc = W[int(p["Wptr"][c]) + kc : int(p["Wptr"][c]) + hc]
+                    nc = int(p["sn_ncol"][c])
+                    assert np.all(rel[:nc] < k) and np.all(rel[nc:] >= k)
+                    np.add.at(bT, rel[:nc], wc[:nc])
+                    lo, hi = np.searchsorted(rel, [max(row0, k), row0 + nrows])
+                    np.add.at(out, rel[lo:hi] - row0, wc[lo:hi])
+                rows = np.arange(row0, row0 + nrows)
+                Mc = M[rows, :k].copy()
+                top = rows < k
+                Mc[top] = np.tril(M[:k, :k])[rows[top]]
+                out += Mc @ bT
+                y[f + rows[top]] = out[top]
+                W[int(p["Wptr"][T]) + rows[~top]] = out[~top]
+        for lv in range(int(p["n_levels"]) - 1, -1, -1):
+            for T, col0, ncols in p["bwd_tasks"][int(p["bwd_ptr"][lv]) : int(p["bwd_ptr"][lv + 1])]:
+                T, col0, ncols = int(T), int(col0), int(ncols)
+                f, k, r, h = self._geom(T)
+                rows = p["Ridx"][int(p["Rptr"][T]) : int(p["Rptr"][T + 1])]
+                M = self.mpanel(T)
+                v = np.concatenate([y[f : f + k] / self.D[f : f + k], x[rows]])
+                Mfull = np.vstack([np.tril(M[:k, :k]), M[k:, :k]])
+                x[f + col0 : f + col0 + ncols] = Mfull[:, col0 : col0 + ncols].T @ v
+        return x
 
     def _extend_add(self, c, jb):
         p = self.p
@@ -227,7 +306,7 @@ class Emulated:
                 x[f : f + k] = np.linalg.solve(L11.T, t)
         return x
 
-    def solve(self, rhs, refine=1):
+    def solve(self, rhs, refine=1, minv=True):
         """Full K solve in original K indices, block elimination around the reduced system."""
         p, kv = self.p, self.kval
         ke, kr = p["k_of_e"], p["k_of_r"]
@@ -240,7 +319,7 @@ class Emulated:
         def once(b):
             t = b[ke] / dE
             bR = b[kr] - A @ t
-            lam_new = self.solve_reduced(bR[p["perm"]])
+            lam_new = (self.solve_reduced_minv if minv else self.solve_reduced)(bR[p["perm"]])
             lam = np.empty(self.m)
             lam[p["perm"]] = lam_new
             z = np.empty(self.N)

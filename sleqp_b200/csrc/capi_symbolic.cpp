@@ -229,6 +229,14 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
   FIELD(zero_sn)
   FIELD(lvl_ptr)
   FIELD(lvl_sn)
+  FIELD(inv_phase_ptr)
+  FIELD(Tptr)
+  FIELD(sn_ncol)
+  FIELD(cptr)
+  FIELD(cidx)
+  FIELD(fwd_ptr)
+  FIELD(bwd_ptr)
+  FIELD(lvl_maxh)
 #undef FIELD
   if (f == "stages")
   {
@@ -242,6 +250,18 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
   if (f == "pan_tasks")
   {
     return export_vec(P.pan_tasks, out, count);
+  }
+  if (f == "inv_tasks")
+  {
+    return export_vec(P.inv_tasks, out, count);
+  }
+  if (f == "fwd_tasks")
+  {
+    return export_vec(P.fwd_tasks, out, count);
+  }
+  if (f == "bwd_tasks")
+  {
+    return export_vec(P.bwd_tasks, out, count);
   }
   if (f == "upd_tasks")
   {

@@ -125,13 +125,15 @@ struct SnMeta
   long long Uoff;
   long long Rptr;
   long long Wptr;
+  long long Tptr;
   int first;
   int k;
   int r;
   int parent;
   int child_begin;
   int child_end;
-  int pad0, pad1;
+  int ncol; // update rows that are columns of the parent (a prefix of the row list)
+  int pad0, pad1, pad2;
 };
 
 // Device copy of a Plan (per handle).
@@ -139,7 +141,7 @@ struct DevPlan
 {
   std::shared_ptr<const Plan> plan;
   DevBuf<SnMeta> sn;
-  DevBuf<int> Ridx, rel, child_idx;
+  DevBuf<int> Ridx, rel, child_idx, cptr, cidx;
   // assembly
   DevBuf<long long> Sdest, Sterm_ptr, Sdiag;
   DevBuf<int> Sgsrc, Sterm_a, Sterm_b, Sterm_d;
@@ -149,10 +151,13 @@ struct DevPlan
   DevBuf<PanelTask> pan_tasks;
   DevBuf<Task5> upd_tasks;
   DevBuf<int> lvl_sn;
+  DevBuf<InvTask> inv_tasks;
+  DevBuf<TrTask> tr_tasks;
+  DevBuf<FwdTask> fwd_tasks;
+  DevBuf<BwdTask> bwd_tasks;
   // E-part / residual operators
   DevBuf<int> k_of_e, k_of_r, pinv, perm, dE_src;
   DevBuf<int> Acsc_ptr, Acsc_row, Acsc_src, Acsr_ptr, Acsr_col, Acsr_src, Gsym_ptr, Gsym_col, Gsym_src;
-  std::vector<int> lvl_maxh; // largest front height per solve level (shared-memory sizing)
 };
 
 } // namespace b200

@@ -44,10 +44,10 @@ struct b200_fact
 
   DevPlan dp;
   // factor
-  DevBuf<double> val, L, U, D, scratch, scal, dE, Acsc_val, Acsr_val, Gsym_val;
+  DevBuf<double> val, L, Mt, Mr, tmp, U, D, scratch, scal, dE, Acsc_val, Acsr_val, Gsym_val;
   DevBuf<int> nper;
   // solve
-  DevBuf<double> rhs, z, res, dz, bR, y, W;
+  DevBuf<double> rhs, z, res, dz, bR, y, x, W;
   DevBuf<int> rhs_idx;
   DevBuf<double> rhs_val;
   PinnedBuf<int> h_rhs_idx;
@@ -71,6 +71,9 @@ struct b200_fact
     NumericBuffers nb;
     nb.val         = val.p;
     nb.L           = L.p;
+    nb.Mt          = Mt.p;
+    nb.tmp         = tmp.p;
+    nb.Mr          = Mr.p;
     nb.U           = U.p;
     nb.D           = D.p;
     nb.scratch     = scratch.p;
@@ -91,6 +94,7 @@ struct b200_fact
     sb.dz  = dz.p;
     sb.bR  = bR.p;
     sb.y   = y.p;
+    sb.x   = x.p;
     sb.W   = W.p;
     return sb;
   }
@@ -156,7 +160,6 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   F->drop_graphs();
   dp.plan = plan;
   std::vector<SnMeta> meta((size_t)P.nsuper);
-  dp.lvl_maxh.assign((size_t)P.nlevels, 0);
   for (int T = 0; T < P.nsuper; ++T)
   {
     SnMeta& m     = meta[T];
@@ -164,19 +167,22 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
     m.Uoff        = P.Uoff[T];
     m.Rptr        = P.Rptr[T];
     m.Wptr        = P.Wptr[T];
+    m.Tptr        = P.Tptr[T];
+    m.ncol        = P.sn_ncol[T];
     m.first       = P.sn_first[T];
     m.k           = P.sn_first[T + 1] - P.sn_first[T];
     m.r           = (int)(P.Rptr[T + 1] - P.Rptr[T]);
     m.parent      = P.sn_parent[T];
     m.child_begin = P.child_ptr[T];
     m.child_end   = P.child_ptr[T + 1];
-    m.pad0 = m.pad1 = 0;
-    dp.lvl_maxh[P.sn_level[T]] = std::max(dp.lvl_maxh[P.sn_level[T]], m.k + m.r);
+    m.pad0 = m.pad1 = m.pad2 = 0;
   }
   dp.sn.upload(meta, s);
   dp.Ridx.upload(P.Ridx, s);
   dp.rel.upload(P.rel, s);
   dp.child_idx.upload(P.child_idx, s);
+  dp.cptr.upload(P.cptr, s);
+  dp.cidx.upload(P.cidx, s);
   static_assert(sizeof(long long) == sizeof(i64), "i64");
   auto up64 = [&](DevBuf<long long>& b, const std::vector<i64>& v) {
     b.reserve(v.size());
@@ -197,6 +203,10 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   dp.pan_tasks.upload(P.pan_tasks, s);
   dp.upd_tasks.upload(P.upd_tasks, s);
   dp.lvl_sn.upload(P.lvl_sn, s);
+  dp.inv_tasks.upload(P.inv_tasks, s);
+  dp.tr_tasks.upload(P.tr_tasks, s);
+  dp.fwd_tasks.upload(P.fwd_tasks, s);
+  dp.bwd_tasks.upload(P.bwd_tasks, s);
   dp.k_of_e.upload(P.k_of_e, s);
   dp.k_of_r.upload(P.k_of_r, s);
   dp.pinv.upload(P.pinv, s);
@@ -217,6 +227,9 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
 
   const size_t N = (size_t)P.N, m = (size_t)P.m;
   F->L.reserve((size_t)P.Lptr[P.nsuper] + 8);
+  F->Mt.reserve((size_t)P.Lptr[P.nsuper] + 8);
+  F->tmp.reserve((size_t)P.Tptr[P.nsuper] + 8);
+  F->Mr.reserve((size_t)P.Lptr[P.nsuper] + 8);
   F->U.reserve((size_t)P.Utotal + 8);
   F->D.reserve(m + 8);
   F->scratch.reserve((size_t)std::max(1, P.n_scratch_slots) * NB * NB);
@@ -232,6 +245,7 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   F->dz.reserve(N + 8);
   F->bR.reserve(m + 8);
   F->y.reserve(m + 8);
+  F->x.reserve(m + 8);
   F->W.reserve((size_t)P.Wptr[P.nsuper] + 8);
   F->h_sol.reserve(N + 8);
   F->h_scal.reserve(8);

@@ -1,15 +1,17 @@
 // numeric.cu -- device numeric factorization: S = G - A D^-1 A^T assembled straight into the
-// supernodal panels, then a multifrontal LDL^T driven by the stage schedule of the plan.
+// supernodal panels, a multifrontal LDL^T driven by the stage schedule of the plan, then the
+// selective inversion that turns every panel into Minv = [L11^-1; -L21 L11^-1] for the solves.
 //
 // Replaces the vendor calls umfpack_di_numeric (fact_umfpack.c:154) / cholmod_l_factorize
 // (fact_cholmod.c:137). Kernels (all FP64):
 //   k_assemble      one thread per entry of tril(S): gathers its product terms      (HBM-bound)
 //   k_extend_add    child update matrix -> parent front (relative indices)         (HBM-bound)
 //   k_panel         NB-wide panel step: dense LDL^T of the diagonal block in shared memory,
-//                   then one thread per row solves its row of L21                   (latency/HBM)
+//                   one thread per row solves its row of L21; also inverts the block   (latency/HBM)
 //   k_update        64x64 output tiles of C -= L_i D L_j^T on the FP64 tensor cores
 //                   (mma.sync m8n8k4.f64 = DMMA), operands staged through shared memory
 //                   (tcgen05 has no f64 kind, so DMMA is the FP64 tensor path on sm_100a)
+//   k_inv_gemm      64x64 DMMA tiles of the triangular products of the selective inversion
 #include "numeric.cuh"
 
 namespace b200
@@ -124,18 +126,21 @@ k_extend_add(const EaTask* __restrict__ tasks,
 // One panel step of supernode T: columns [c0, c0+w) of the front, w <= NB.
 // Every CTA of the step factors the w x w diagonal block redundantly in shared memory (identical
 // arithmetic, so identical results) and then solves its RB rows of L21; row block 0 also publishes
-// the factored block and the pivots. With more than one row block the block goes to a scratch
-// slot (other CTAs are still reading the unfactored one) and k_update copies it back.
+// the factored block, the pivots and the inverse of the (unit lower) block into the inverse panel.
+// With more than one row block the factored block goes to a scratch slot (other CTAs are still
+// reading the unfactored one) and k_update copies it back.
 __global__ void __launch_bounds__(RB)
 k_panel(const PanelTask* __restrict__ tasks,
         const SnMeta* __restrict__ sn,
         double* __restrict__ L,
+        double* __restrict__ Mt,
         double* __restrict__ D,
         double* __restrict__ scratch,
         const double* __restrict__ scal,
         int* __restrict__ n_perturbed)
 {
   __shared__ double A[NB][NB + 1];
+  __shared__ double Ainv[NB][NB + 1];
   __shared__ double dsh[NB];
   const PanelTask t = tasks[blockIdx.x];
   const SnMeta s    = sn[t.sn];
@@ -228,6 +233,28 @@ k_panel(const PanelTask* __restrict__ tasks,
     if (tid < w)
     {
       D[s.first + c0 + tid] = dsh[tid];
+      // column tid of the inverse of the unit lower block by forward substitution
+      const int c = tid;
+      Ainv[c][c]  = 1.0;
+      for (int i = c + 1; i < w; ++i)
+      {
+        double acc = 0.0;
+        for (int q = c; q < i; ++q)
+        {
+          acc -= A[i][q] * Ainv[q][c];
+        }
+        Ainv[i][c] = acc;
+      }
+    }
+    __syncthreads();
+    double* M = Mt + s.Lptr;
+    for (int idx = tid; idx < w * w; idx += RB)
+    {
+      const int i = idx % w, j = idx / w;
+      if (i >= j)
+      {
+        M[(long long)(c0 + j) * h + c0 + i] = Ainv[i][j];
+      }
     }
     if (t.slot < 0)
     {
@@ -263,8 +290,33 @@ dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-constexpr int KC   = 16;       // k-chunk staged per iteration
-constexpr int LDT  = TILE + 4; // padded leading dimension: (LDT mod 16) == 4 -> conflict-free fragments
+constexpr int KC  = 16;       // k-chunk staged per iteration
+constexpr int LDT = TILE + 4; // padded leading dimension: (LDT mod 16) == 4 -> conflict-free fragments
+
+// acc += As^T * Bs for one staged chunk: As[kk][i], Bs[kk][j]; warp (wy, wx) owns a 32x32 quadrant
+__device__ __forceinline__ void
+mma_chunk(const double (*As)[LDT], const double (*Bs)[LDT], double (&acc)[4][4][2], int wy, int wx, int lane)
+{
+#pragma unroll
+  for (int k4 = 0; k4 < KC / 4; ++k4)
+  {
+    const int kr = k4 * 4 + (lane & 3);
+    double af[4], bf[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+    {
+      af[a] = As[kr][wy * 32 + a * 8 + (lane >> 2)];
+      bf[a] = Bs[kr][wx * 32 + a * 8 + (lane >> 2)];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+      {
+        dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+      }
+  }
+}
 
 // C(tile) -= Lrow_i * diag(d) * Lrow_j^T over front columns [kb, ke). Operand rows come from the
 // panel (column-major, leading dimension h): A-rows start at ra0, B-rows at rb0, at most na / nb
@@ -329,25 +381,7 @@ tile_update(const double* __restrict__ P,
     __syncthreads();
     if (active)
     {
-#pragma unroll
-      for (int k4 = 0; k4 < KC / 4; ++k4)
-      {
-        const int kr = k4 * 4 + (lane & 3);
-        double af[4], bf[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-        {
-          af[a] = As[kr][wy * 32 + a * 8 + (lane >> 2)];
-          bf[a] = Bs[kr][wx * 32 + a * 8 + (lane >> 2)];
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-          {
-            dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-          }
-      }
+      mma_chunk(As, Bs, acc, wy, wx, lane);
     }
     __syncthreads();
   }
@@ -418,6 +452,133 @@ k_update(const Task5* __restrict__ tasks,
 }
 
 // ---------------------------------------------------------------------------------------------
+// out(tile) = sign * X[:, kb:ke] * Y[kb:ke, :], both operands column-major, non-transposed:
+//   X element (i, q) at X[i + q * ldx] (na valid rows), Y element (q, j) at Y[q + j * ldy] (nb valid columns).
+__global__ void __launch_bounds__(128)
+k_inv_gemm(const InvTask* __restrict__ tasks,
+           const SnMeta* __restrict__ sn,
+           const double* __restrict__ L,
+           double* __restrict__ Mt,
+           double* __restrict__ tmp)
+{
+  __shared__ double As[KC][LDT];
+  __shared__ double Bs[KC][LDT];
+  const InvTask t = tasks[blockIdx.x];
+  const SnMeta s  = sn[t.sn];
+  const int k = s.k, h = s.k + s.r;
+  const double* P = L + s.Lptr;
+  double* M       = Mt + s.Lptr;
+  double* Tm      = tmp + s.Tptr;
+
+  const double *X, *Y;
+  double* out;
+  long long ldx, ldy, ldo;
+  int na, nb;
+  double sign;
+  if (t.kind == INV_T1)
+  {
+    // Tmp[i, j] = sum_q L11[i, q] Ainv[q, j]; A columns end at ke
+    X = P + t.i0, ldx = h;
+    Y = M + (long long)t.j0 * h, ldy = h;
+    out = Tm + t.i0 + (long long)t.j0 * k, ldo = k;
+    na = min(TILE, k - t.i0), nb = min(TILE, t.ke - t.j0);
+    sign = 1.0;
+  }
+  else if (t.kind == INV_T2)
+  {
+    // Minv[i, j] = -sum_q Cinv[i, q] Tmp[q, j]; C rows [kb, ...), A columns end at kb
+    X = M + t.i0, ldx = h;
+    Y = Tm + (long long)t.j0 * k, ldy = k;
+    out = M + t.i0 + (long long)t.j0 * h, ldo = h;
+    na = min(TILE, t.ke - t.i0), nb = min(TILE, t.kb - t.j0);
+    sign = -1.0;
+  }
+  else
+  {
+    // Minv[k + i, j] = -sum_q L21[i, q] Linv[q, j]
+    X = P + k + t.i0, ldx = h;
+    Y = M + (long long)t.j0 * h, ldy = h;
+    out = M + k + t.i0 + (long long)t.j0 * h, ldo = h;
+    na = min(TILE, s.r - t.i0), nb = min(TILE, k - t.j0);
+    sign = -1.0;
+  }
+
+  const int tid  = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wy = warp >> 1, wx = warp & 1;
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+    {
+      acc[a][b][0] = 0.0;
+      acc[a][b][1] = 0.0;
+    }
+  for (int kc = t.kb; kc < t.ke; kc += KC)
+  {
+    for (int idx = tid; idx < KC * TILE; idx += 128)
+    {
+      {
+        const int kk = idx / TILE, ii = idx % TILE; // consecutive threads -> consecutive rows of X
+        const int q = kc + kk;
+        As[kk][ii]  = (q < t.ke && ii < na) ? X[ii + (long long)q * ldx] : 0.0;
+      }
+      {
+        const int jj = idx / KC, kk = idx % KC; // consecutive threads -> consecutive rows of Y
+        const int q = kc + kk;
+        Bs[kk][jj]  = (q < t.ke && jj < nb) ? Y[q + (long long)jj * ldy] : 0.0;
+      }
+    }
+    __syncthreads();
+    mma_chunk(As, Bs, acc, wy, wx, lane);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+      {
+        const int i = wy * 32 + a * 8 + (lane >> 2);
+        const int j = wx * 32 + b * 8 + 2 * (lane & 3) + e;
+        if (i < na && j < nb)
+        {
+          out[i + (long long)j * ldo] = sign * acc[a][b][e];
+        }
+      }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-major copy of the inverse panels: Mr[r * k + j] = Mt[j * h + r], 32x32 tiles through shared memory.
+__global__ void __launch_bounds__(256)
+k_transpose(const TrTask* __restrict__ tasks, const SnMeta* __restrict__ sn, const double* __restrict__ Mt, double* __restrict__ Mr)
+{
+  __shared__ double tile[32][33];
+  const TrTask t = tasks[blockIdx.x];
+  const SnMeta s = sn[t.sn];
+  const int k = s.k, h = s.k + s.r;
+  const double* src = Mt + s.Lptr;
+  double* dst       = Mr + s.Lptr;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int jj = ty; jj < 32; jj += 8)
+  {
+    const int i = t.i0 + tx, j = t.j0 + jj;
+    tile[jj][tx] = (i < h && j < k) ? src[(long long)j * h + i] : 0.0;
+  }
+  __syncthreads();
+  for (int ii = ty; ii < 32; ii += 8)
+  {
+    const int i = t.i0 + ii, j = t.j0 + tx;
+    if (i < h && j < k)
+    {
+      dst[(long long)i * k + j] = tile[tx][ii];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 void
 enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc)
 {
@@ -427,6 +588,7 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
   if (P.m > 0)
   {
     B200_CUDA(cudaMemsetAsync(nb.L, 0, sizeof(double) * (size_t)P.Lptr[P.nsuper], stream));
+    B200_CUDA(cudaMemsetAsync(nb.Mt, 0, sizeof(double) * (size_t)P.Lptr[P.nsuper], stream));
     const int threads = 256;
     const unsigned blocks = (unsigned)((P.nnzS + threads - 1) / threads);
     k_assemble<<<blocks, threads, 0, stream>>>(P.nnzS, dp.Sdest.p, dp.Sgsrc.p, dp.Sterm_ptr.p, dp.Sterm_a.p, dp.Sterm_b.p, dp.Sterm_d.p, nb.val, nb.L);
@@ -452,7 +614,7 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
     }
     if (st.pan_end > st.pan_begin)
     {
-      k_panel<<<(unsigned)(st.pan_end - st.pan_begin), RB, 0, stream>>>(dp.pan_tasks.p + st.pan_begin, dp.sn.p, nb.L, nb.D, nb.scratch, nb.scal, nb.n_perturbed);
+      k_panel<<<(unsigned)(st.pan_end - st.pan_begin), RB, 0, stream>>>(dp.pan_tasks.p + st.pan_begin, dp.sn.p, nb.L, nb.Mt, nb.D, nb.scratch, nb.scal, nb.n_perturbed);
       lc.tick();
     }
     if (st.upd_end > st.upd_begin)
@@ -460,6 +622,21 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
       k_update<<<(unsigned)(st.upd_end - st.upd_begin), 128, 0, stream>>>(dp.upd_tasks.p + st.upd_begin, dp.sn.p, nb.L, nb.U, nb.D, nb.scratch);
       lc.tick();
     }
+  }
+  // selective inversion
+  for (size_t ph = 0; ph + 1 < P.inv_phase_ptr.size(); ++ph)
+  {
+    const int b = P.inv_phase_ptr[ph], e = P.inv_phase_ptr[ph + 1];
+    if (e > b)
+    {
+      k_inv_gemm<<<(unsigned)(e - b), 128, 0, stream>>>(dp.inv_tasks.p + b, dp.sn.p, nb.L, nb.Mt, nb.tmp);
+      lc.tick();
+    }
+  }
+  if (!P.tr_tasks.empty())
+  {
+    k_transpose<<<(unsigned)P.tr_tasks.size(), 256, 0, stream>>>(dp.tr_tasks.p, dp.sn.p, nb.Mt, nb.Mr);
+    lc.tick();
   }
   // contiguous operator values for the solve
   const int threads = 256;

@@ -9,7 +9,10 @@ namespace b200
 struct NumericBuffers
 {
   const double* val; // values of tril(K), same order as the caller's CSC
-  double* L;         // supernodal panels
+  double* L;         // supernodal panels [L11; L21]
+  double* Mt;        // inverse panels [L11^-1; -L21 L11^-1] (what the solves read)
+  double* Mr;        // row-major copy of the inverse panels (forward sweep reads rows)
+  double* tmp;       // k x k scratch of the selective inversion
   double* U;         // update-matrix workspace
   double* D;         // pivots of S (new labels)
   double* scratch;   // diagonal-block scratch slots
@@ -28,7 +31,8 @@ struct SolveBuffers
   double* res;  // N, residual / correction right-hand side
   double* dz;   // N, correction
   double* bR;   // m, reduced right-hand side (new labels)
-  double* y;    // m, forward result / solution of the reduced system (new labels)
+  double* y;    // m, forward result (new labels)
+  double* x;    // m, solution of the reduced system (new labels)
   double* W;    // front vectors (sum of front heights)
 };
 

@@ -47,6 +47,38 @@ struct EaTask
   int child, jb;
 };
 
+// Tile task of the selective-inversion phases (after the factorization proper):
+//   INV_T1: Tmp[C x A]  =  L11[C, A] * Ainv            (Ainv lower triangular, from the inverse panel)
+//   INV_T2: Minv[C x A] = -Cinv * Tmp[C x A]           (Cinv lower triangular)
+//   INV_Z : Minv[tail, :] = -L21 * L11^-1
+// i0/j0: first row / column of the 64x64 output tile in front coordinates, [kb, ke): inner range.
+enum
+{
+  INV_T1 = 0,
+  INV_T2 = 1,
+  INV_Z  = 2
+};
+
+struct InvTask
+{
+  int sn, kind, i0, j0, kb, ke;
+};
+
+struct TrTask
+{
+  int sn, i0, j0; // 32x32 tile of a panel to transpose into the row-major copy
+};
+
+struct FwdTask
+{
+  int sn, row0, nrows;
+};
+
+struct BwdTask
+{
+  int sn, col0, ncols;
+};
+
 struct Stage
 {
   int zero_begin, zero_end;
@@ -106,9 +138,23 @@ struct Plan
   std::vector<Task5> upd_tasks;
   int n_scratch_slots = 0;
 
+  // selective inversion: phases of tile tasks; phase p covers inv_tasks[inv_phase_ptr[p], inv_phase_ptr[p+1])
+  std::vector<InvTask> inv_tasks;
+  std::vector<int> inv_phase_ptr;
+  std::vector<TrTask> tr_tasks;
+  std::vector<i64> Tptr; // nsuper+1, k x k scratch of the inversion (only supernodes wider than NB)
+
   // solve schedule (levels of the supernodal tree)
   int nlevels = 0;
   std::vector<int> lvl_ptr, lvl_sn;
+  // contributor lists (inverse of rel): front row i of supernode T (global index Wptr[T] + i) receives
+  // W[cidx[e]] for e in [cptr[Wptr[T] + i], cptr[Wptr[T] + i + 1]), children in ascending order
+  std::vector<int> cptr, cidx;
+  std::vector<int> sn_ncol; // number of a supernode's update rows that are columns of its parent
+  std::vector<FwdTask> fwd_tasks;
+  std::vector<BwdTask> bwd_tasks;
+  std::vector<int> fwd_ptr, bwd_ptr; // per level ranges into the task arrays
+  std::vector<int> lvl_maxh;
 
   // statistics
   i64 nnzL = 0, nnzL_stored = 0;

@@ -145,190 +145,268 @@ k_axpy1(int n, const double* __restrict__ x, double* __restrict__ y)
   }
 }
 
-// ---- forward sweep: one CTA per supernode of the level -----------------------------------------------
-__global__ void __launch_bounds__(SOLVE_THREADS)
-k_fwd_level(const int* __restrict__ lvl_sn,
-            const SnMeta* __restrict__ sn,
-            const int* __restrict__ child_idx,
-            const int* __restrict__ rel,
-            const double* __restrict__ L,
-            const double* __restrict__ b,
-            double* __restrict__ y,
-            double* __restrict__ W,
-            int use_smem)
+// ---- forward sweep ---------------------------------------------------------------------------------
+// One CTA per (supernode, row chunk). With the inverse panel Minv = [L11^-1; -L21 L11^-1] the whole
+// supernode step is one matrix-vector product  [y_T; dW_tail] = Minv * b_T,  b_T = b[cols] + the
+// children's tail contributions that land on T's columns (contributor lists, fixed order: the sum is
+// deterministic). Every CTA of a supernode rebuilds b_T itself, so nothing depends on anything inside a
+// level. Tail rows also receive the children's pass-through contributions.
+// Reads the row-major copy Mr of the inverse panel: a warp owns RG rows at a time, lanes stride the
+// (contiguous) columns with 8 independent loads in flight. Dynamic shared memory: bT[k].
+template <int RG>
+__device__ __forceinline__ void
+fwd_rows(const double* __restrict__ P, int k, const double* __restrict__ bT, int r0, int nvalid, int lane, double (&res)[RG])
 {
-  extern __shared__ double smem[];
-  const SnMeta s  = sn[lvl_sn[blockIdx.x]];
-  const int k = s.k, h = s.k + s.r;
-  const double* P = L + s.Lptr;
-  double* Wg      = W + s.Wptr;
-  double* w       = use_smem ? smem : Wg;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  for (int i = tid; i < h; i += SOLVE_THREADS)
-  {
-    w[i] = i < k ? b[s.first + i] : 0.0;
-  }
-  __syncthreads();
-  for (int q = s.child_begin; q < s.child_end; ++q)
-  {
-    const SnMeta c   = sn[child_idx[q]];
-    const int* rl    = rel + c.Rptr;
-    const double* wc = W + c.Wptr + c.k;
-    for (int i = tid; i < c.r; i += SOLVE_THREADS)
+  constexpr int U = 8 / RG;
+  double acc[RG][U];
+#pragma unroll
+  for (int a = 0; a < RG; ++a)
+#pragma unroll
+    for (int u = 0; u < U; ++u)
     {
-      w[rl[i]] += wc[i];
+      acc[a][u] = 0.0;
     }
-    __syncthreads();
-  }
-  for (int jb = 0; jb < k; jb += 32)
+  // the top block is lower triangular: row r only needs columns <= r; rows of one group share the
+  // bound of the last row (entries beyond a row's diagonal are zeros of the memset / transpose)
+  const int rlast = r0 + nvalid - 1;
+  const int jend  = rlast < k ? rlast + 1 : k;
+  int j           = lane;
+  for (; j + 32 * (U - 1) < jend; j += 32 * U)
   {
-    const int wb = min(32, k - jb);
-    if (warp == 0)
+#pragma unroll
+    for (int u = 0; u < U; ++u)
     {
-      double a[32];
+      const double bj = bT[j + 32 * u];
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj)
+      for (int a = 0; a < RG; ++a)
       {
-        a[jj] = (jj < lane && lane < wb) ? P[(long long)(jb + jj) * h + jb + lane] : 0.0;
-      }
-      double v = lane < wb ? w[jb + lane] : 0.0;
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj)
-      {
-        const double yj = __shfl_sync(0xffffffffu, v, jj);
-        if (lane > jj)
+        if (a < nvalid)
         {
-          v -= a[jj] * yj;
+          acc[a][u] += P[(long long)(r0 + a) * k + j + 32 * u] * bj;
         }
       }
-      if (lane < wb)
-      {
-        w[jb + lane] = v;
-      }
     }
-    __syncthreads();
-    for (int i = jb + wb + tid; i < h; i += SOLVE_THREADS)
-    {
-      double acc = w[i];
-      for (int jj = 0; jj < wb; ++jj)
-      {
-        acc -= P[(long long)(jb + jj) * h + i] * w[jb + jj];
-      }
-      w[i] = acc;
-    }
-    __syncthreads();
   }
-  for (int i = tid; i < h; i += SOLVE_THREADS)
+  for (; j < jend; j += 32)
   {
-    if (i < k)
+    const double bj = bT[j];
+#pragma unroll
+    for (int a = 0; a < RG; ++a)
     {
-      y[s.first + i] = w[i];
+      if (a < nvalid)
+      {
+        acc[a][0] += P[(long long)(r0 + a) * k + j] * bj;
+      }
     }
-    else if (use_smem)
+  }
+#pragma unroll
+  for (int a = 0; a < RG; ++a)
+  {
+    double v = 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
     {
-      Wg[i] = w[i];
+      v += acc[a][u];
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    res[a] = v;
+  }
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_fwd_chunk(const FwdTask* __restrict__ tasks,
+            const SnMeta* __restrict__ sn,
+            const int* __restrict__ cptr,
+            const int* __restrict__ cidx,
+            const double* __restrict__ Mr,
+            const double* __restrict__ b,
+            double* __restrict__ y,
+            double* __restrict__ W)
+{
+  extern __shared__ double bT[];
+  const FwdTask t = tasks[blockIdx.x];
+  const SnMeta s  = sn[t.sn];
+  const int k     = s.k;
+  const double* P = Mr + s.Lptr;
+  const int* cp   = cptr + s.Wptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int j = tid; j < k; j += SOLVE_THREADS)
+  {
+    double acc = b[s.first + j];
+    for (int e = cp[j]; e < cp[j + 1]; ++e)
+    {
+      acc += W[cidx[e]];
+    }
+    bT[j] = acc;
+  }
+  __syncthreads();
+  constexpr int NW = SOLVE_THREADS / 32;
+  const int rg     = (t.nrows + NW - 1) / NW; // rows per warp: 1..4
+  const int g0     = warp * rg;
+  if (g0 >= t.nrows)
+  {
+    return;
+  }
+  const int nvalid = min(rg, t.nrows - g0);
+  const int r0     = t.row0 + g0;
+  double res[4];
+  if (rg == 1)
+  {
+    double r1[1];
+    fwd_rows<1>(P, k, bT, r0, nvalid, lane, r1);
+    res[0] = r1[0];
+  }
+  else if (rg == 2)
+  {
+    double r2[2];
+    fwd_rows<2>(P, k, bT, r0, nvalid, lane, r2);
+    res[0] = r2[0];
+    res[1] = r2[1];
+  }
+  else
+  {
+    fwd_rows<4>(P, k, bT, r0, nvalid, lane, res);
+  }
+  if (lane < nvalid)
+  {
+    const int r = r0 + lane;
+    double v    = lane == 0 ? res[0] : lane == 1 ? res[1] : lane == 2 ? res[2] : res[3];
+    if (r < k)
+    {
+      y[s.first + r] = v;
+    }
+    else
+    {
+      for (int e = cp[r]; e < cp[r + 1]; ++e) // pass-through from the children
+      {
+        v += W[cidx[e]];
+      }
+      W[s.Wptr + r] = v;
     }
   }
 }
 
 // ---- diagonal + backward sweep -----------------------------------------------------------------------
+// One CTA per (supernode, column chunk):  x_T = Minv^T [D^-1 y_T; x_rows].  A warp owns CG columns at a
+// time (rows are contiguous in the column-major panel), lanes stride the rows with 8 independent loads
+// in flight, shuffle reduction. Dynamic shared memory: v[h].
+template <int CG>
+__device__ __forceinline__ void
+bwd_cols(const double* __restrict__ P, int h, const double* __restrict__ v, int j0, int nvalid, int lane, double (&res)[CG])
+{
+  constexpr int U = 8 / CG;
+  double acc[CG][U];
+#pragma unroll
+  for (int c = 0; c < CG; ++c)
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      acc[c][u] = 0.0;
+    }
+  // column j needs rows >= j; the columns of a group start at the first one's diagonal (the entries
+  // above a diagonal are zeros)
+  int i = j0 + lane;
+  for (; i + 32 * (U - 1) < h; i += 32 * U)
+  {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const double vi = v[i + 32 * u];
+#pragma unroll
+      for (int c = 0; c < CG; ++c)
+      {
+        if (c < nvalid)
+        {
+          acc[c][u] += P[(long long)(j0 + c) * h + i + 32 * u] * vi;
+        }
+      }
+    }
+  }
+  for (; i < h; i += 32)
+  {
+    const double vi = v[i];
+#pragma unroll
+    for (int c = 0; c < CG; ++c)
+    {
+      if (c < nvalid)
+      {
+        acc[c][0] += P[(long long)(j0 + c) * h + i] * vi;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CG; ++c)
+  {
+    double a = 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      a += acc[c][u];
+    }
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+    }
+    res[c] = a;
+  }
+}
+
 __global__ void __launch_bounds__(SOLVE_THREADS)
-k_bwd_level(const int* __restrict__ lvl_sn,
+k_bwd_chunk(const BwdTask* __restrict__ tasks,
             const SnMeta* __restrict__ sn,
             const int* __restrict__ Ridx,
-            const double* __restrict__ L,
+            const double* __restrict__ Mt,
             const double* __restrict__ D,
-            double* __restrict__ y,
-            double* __restrict__ W,
-            int use_smem)
+            const double* __restrict__ y,
+            double* __restrict__ x)
 {
-  extern __shared__ double smem[];
-  const SnMeta s  = sn[lvl_sn[blockIdx.x]];
+  extern __shared__ double v[];
+  const BwdTask t = tasks[blockIdx.x];
+  const SnMeta s  = sn[t.sn];
   const int k = s.k, h = s.k + s.r;
-  const double* P = L + s.Lptr;
-  double* w       = use_smem ? smem : W + s.Wptr;
+  const double* P = Mt + s.Lptr;
   const int* rows = Ridx + s.Rptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW  = SOLVE_THREADS / 32;
-  constexpr int CPW = 32 / NW; // columns per warp inside a 32-column block
 
-  for (int i = tid; i < h; i += SOLVE_THREADS)
+  for (int i = t.col0 + tid; i < h; i += SOLVE_THREADS)
   {
-    w[i] = i < k ? y[s.first + i] / D[s.first + i] : y[rows[i - k]];
+    v[i] = i < k ? y[s.first + i] / D[s.first + i] : x[rows[i - k]];
   }
   __syncthreads();
-  const int nblk = (k + 31) / 32;
-  for (int blk = nblk - 1; blk >= 0; --blk)
+  constexpr int NW = SOLVE_THREADS / 32;
+  const int cg     = (t.ncols + NW - 1) / NW; // columns per warp: 1..4
+  const int g0     = warp * cg;
+  if (g0 >= t.ncols)
   {
-    const int jb = blk * 32;
-    const int wb = min(32, k - jb);
-    // w[c] -= sum_{i >= jb+wb} L[i][c] * w[i] for the block's columns
-    {
-      double acc[CPW];
-#pragma unroll
-      for (int cc = 0; cc < CPW; ++cc)
-      {
-        acc[cc] = 0.0;
-      }
-      for (int i = jb + wb + lane; i < h; i += 32)
-      {
-        const double wi = w[i];
-#pragma unroll
-        for (int cc = 0; cc < CPW; ++cc)
-        {
-          const int c = jb + warp * CPW + cc;
-          if (c < jb + wb)
-          {
-            acc[cc] += P[(long long)c * h + i] * wi;
-          }
-        }
-      }
-#pragma unroll
-      for (int cc = 0; cc < CPW; ++cc)
-      {
-        double v = acc[cc];
-        for (int o = 16; o > 0; o >>= 1)
-        {
-          v += __shfl_xor_sync(0xffffffffu, v, o);
-        }
-        const int c = jb + warp * CPW + cc;
-        if (lane == 0 && c < jb + wb)
-        {
-          w[c] -= v;
-        }
-      }
-    }
-    __syncthreads();
-    if (warp == 0)
-    {
-      // L11^T x = t on the block: lane j owns column j of the block
-      double col[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-      {
-        col[i] = (i > lane && i < wb) ? P[(long long)(jb + lane) * h + jb + i] : 0.0;
-      }
-      double v = lane < wb ? w[jb + lane] : 0.0;
-#pragma unroll
-      for (int jj = 31; jj >= 0; --jj)
-      {
-        const double xj = __shfl_sync(0xffffffffu, v, jj);
-        if (lane < jj)
-        {
-          v -= col[jj] * xj;
-        }
-      }
-      if (lane < wb)
-      {
-        w[jb + lane] = v;
-      }
-    }
-    __syncthreads();
+    return;
   }
-  for (int i = tid; i < k; i += SOLVE_THREADS)
+  const int nvalid = min(cg, t.ncols - g0);
+  const int j0     = t.col0 + g0;
+  double res[4];
+  if (cg == 1)
   {
-    y[s.first + i] = w[i];
+    double r1[1];
+    bwd_cols<1>(P, h, v, j0, nvalid, lane, r1);
+    res[0] = r1[0];
+  }
+  else if (cg == 2)
+  {
+    double r2[2];
+    bwd_cols<2>(P, h, v, j0, nvalid, lane, r2);
+    res[0] = r2[0];
+    res[1] = r2[1];
+  }
+  else
+  {
+    bwd_cols<4>(P, h, v, j0, nvalid, lane, res);
+  }
+  if (lane < nvalid)
+  {
+    x[s.first + j0 + lane] = lane == 0 ? res[0] : lane == 1 ? res[1] : lane == 2 ? res[2] : res[3];
   }
 }
 
@@ -432,30 +510,26 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
     mark(1);
     for (int l = 0; l < P.nlevels; ++l)
     {
-      const int cnt          = P.lvl_ptr[l + 1] - P.lvl_ptr[l];
-      const size_t smem_need = sizeof(double) * (size_t)dp.lvl_maxh[l];
-      const int use_smem     = smem_need <= SOLVE_SMEM_LIMIT;
-      const size_t smem      = use_smem ? smem_need : 0;
-      k_fwd_level<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.lvl_sn.p + P.lvl_ptr[l], dp.sn.p, dp.child_idx.p, dp.rel.p, nb.L, sb.bR, sb.y, sb.W, use_smem);
+      const int cnt     = P.fwd_ptr[l + 1] - P.fwd_ptr[l];
+      const size_t smem = sizeof(double) * (size_t)P.lvl_maxh[l];
+      k_fwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.fwd_tasks.p + P.fwd_ptr[l], dp.sn.p, dp.cptr.p, dp.cidx.p, nb.Mr, sb.bR, sb.y, sb.W);
       lc.tick();
     }
     mark(2);
     for (int l = P.nlevels - 1; l >= 0; --l)
     {
-      const int cnt          = P.lvl_ptr[l + 1] - P.lvl_ptr[l];
-      const size_t smem_need = sizeof(double) * (size_t)dp.lvl_maxh[l];
-      const int use_smem     = smem_need <= SOLVE_SMEM_LIMIT;
-      const size_t smem      = use_smem ? smem_need : 0;
-      k_bwd_level<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.lvl_sn.p + P.lvl_ptr[l], dp.sn.p, dp.Ridx.p, nb.L, nb.D, sb.y, sb.W, use_smem);
+      const int cnt = P.bwd_ptr[l + 1] - P.bwd_ptr[l];
+      const size_t smem = sizeof(double) * (size_t)P.lvl_maxh[l];
+      k_bwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.bwd_tasks.p + P.bwd_ptr[l], dp.sn.p, dp.Ridx.p, nb.Mt, nb.D, sb.y, sb.x);
       lc.tick();
     }
     mark(3);
-    k_post_r<<<nblocks(P.m, T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.pinv.p, sb.y, out);
+    k_post_r<<<nblocks(P.m, T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.pinv.p, sb.x, out);
     lc.tick();
   }
   if (P.nE > 0)
   {
-    k_post_e<<<nblocks(P.nE, T), T, 0, stream>>>(P.nE, dp.k_of_e.p, dp.pinv.p, dp.Acsc_ptr.p, dp.Acsc_row.p, nb.Acsc_val, nb.dE, in, sb.y, out);
+    k_post_e<<<nblocks(P.nE, T), T, 0, stream>>>(P.nE, dp.k_of_e.p, dp.pinv.p, dp.Acsc_ptr.p, dp.Acsc_row.p, nb.Acsc_val, nb.dE, in, sb.x, out);
     lc.tick();
   }
   mark(4);
@@ -484,8 +558,8 @@ configure_solve_kernels()
   static bool done = false;
   if (!done)
   {
-    B200_CUDA(cudaFuncSetAttribute(k_fwd_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
-    B200_CUDA(cudaFuncSetAttribute(k_bwd_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
+    B200_CUDA(cudaFuncSetAttribute(k_fwd_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
+    B200_CUDA(cudaFuncSetAttribute(k_bwd_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
     done = true;
   }
 }

@@ -1327,6 +1327,202 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
 
+  // ---- selective inversion schedule ------------------------------------------------------------------------------
+  // After the factorization every panel [L11; L21] is turned into Minv = [L11^-1; -L21 L11^-1], so that both
+  // sweeps of a solve are plain matrix-vector products per supernode (Raghavan's selective inversion). L11^-1
+  // is built by recursive halving over NB-blocks: inv([A 0; B C]) = [Ainv 0; -Cinv B Ainv, Cinv]; the NB x NB
+  // diagonal blocks are inverted by k_panel itself. Nodes of equal height (over all supernodes) share a launch.
+  {
+    P.Tptr.assign(ns + 1, 0);
+    struct Node
+    {
+      int sn, a, b, c, ht;
+    };
+    std::vector<Node> nodes;
+    int hmax = 0;
+    // iterative-recursive split; returns the height of block range [a, c)
+    struct Rec
+    {
+      std::vector<Node>& nodes;
+      int sn;
+      int run(int a, int c)
+      {
+        if (c - a <= 1)
+        {
+          return 0;
+        }
+        int half = 1;
+        while (half * 2 < c - a)
+        {
+          half *= 2;
+        }
+        const int b  = a + half;
+        const int hl = run(a, b), hr = run(b, c);
+        const int ht = 1 + std::max(hl, hr);
+        nodes.push_back({sn, a, b, c, ht});
+        return ht;
+      }
+    };
+    for (int T = 0; T < ns; ++T)
+    {
+      const i64 k  = P.sn_first[T + 1] - P.sn_first[T];
+      const int nb = (int)((k + NB - 1) / NB);
+      P.Tptr[T + 1] = P.Tptr[T] + (nb > 1 ? ((k * k + 3) & ~(i64)3) : 0);
+      if (nb > 1)
+      {
+        Rec rec{nodes, T};
+        hmax = std::max(hmax, rec.run(0, nb));
+      }
+    }
+    P.inv_phase_ptr.assign(1, 0);
+    for (int ht = 1; ht <= hmax; ++ht)
+    {
+      for (int kind = INV_T1; kind <= INV_T2; ++kind)
+      {
+        for (const Node& nd : nodes)
+        {
+          if (nd.ht != ht)
+          {
+            continue;
+          }
+          const int k    = P.sn_first[nd.sn + 1] - P.sn_first[nd.sn];
+          const int ca   = nd.a * NB, cb = nd.b * NB;       // A columns [ca, cb)
+          const int rend = std::min(nd.c * NB, k);            // C rows [cb, rend)
+          for (int j0 = ca; j0 < cb; j0 += TILE)
+          {
+            for (int i0 = cb; i0 < rend; i0 += TILE)
+            {
+              if (kind == INV_T1)
+              {
+                P.inv_tasks.push_back({nd.sn, INV_T1, i0, j0, j0, cb}); // Ainv[q, j] = 0 for q < j
+              }
+              else
+              {
+                P.inv_tasks.push_back({nd.sn, INV_T2, i0, j0, cb, std::min(i0 + TILE, rend)}); // Cinv[i, q] = 0 for q > i
+              }
+            }
+          }
+        }
+        P.inv_phase_ptr.push_back((int)P.inv_tasks.size());
+      }
+    }
+    for (int T = 0; T < ns; ++T)
+    {
+      const int k = P.sn_first[T + 1] - P.sn_first[T];
+      const int r = (int)(P.Rptr[T + 1] - P.Rptr[T]);
+      for (int j0 = 0; j0 < k; j0 += TILE)
+      {
+        for (int i0 = 0; i0 < r; i0 += TILE)
+        {
+          P.inv_tasks.push_back({T, INV_Z, i0, j0, j0, k});
+        }
+      }
+    }
+    P.inv_phase_ptr.push_back((int)P.inv_tasks.size());
+    // row-major copy of every inverse panel for the forward sweep
+    for (int T = 0; T < ns; ++T)
+    {
+      const int k = P.sn_first[T + 1] - P.sn_first[T];
+      const int h = k + (int)(P.Rptr[T + 1] - P.Rptr[T]);
+      for (int j0 = 0; j0 < k; j0 += 32)
+      {
+        // one tile band above the diagonal is copied too (zeros): a warp's row group may straddle a tile edge
+        for (int i0 = std::max(0, j0 - 32); i0 < h; i0 += 32)
+        {
+          P.tr_tasks.push_back({T, i0, j0});
+        }
+      }
+    }
+  }
+
+  // ---- solve tasks: row chunks (forward) / column chunks (backward) of every supernode, per level ---------------
+  {
+    P.sn_ncol.assign(ns, 0);
+    for (int T = 0; T < ns; ++T)
+    {
+      const int p = P.sn_parent[T];
+      if (p < 0)
+      {
+        continue;
+      }
+      const int kp = P.sn_first[p + 1] - P.sn_first[p];
+      int cnt      = 0;
+      for (i64 q = P.Rptr[T]; q < P.Rptr[T + 1] && P.rel[q] < kp; ++q)
+      {
+        ++cnt;
+      }
+      P.sn_ncol[T] = cnt;
+    }
+    {
+      const i64 totalh = P.Wptr[ns];
+      if (totalh > 0x7ffffff0 || (i64)P.Ridx.size() > 0x7ffffff0)
+      {
+        return fail(err, B200_ERR_UNSUPPORTED, "front-vector workspace exceeds 2^31 entries");
+      }
+      P.cptr.assign((size_t)totalh + 1, 0);
+      for (int c = 0; c < ns; ++c)
+      {
+        const int p = P.sn_parent[c];
+        if (p < 0)
+        {
+          continue;
+        }
+        for (i64 q = P.Rptr[c]; q < P.Rptr[c + 1]; ++q)
+        {
+          ++P.cptr[(size_t)(P.Wptr[p] + P.rel[q]) + 1];
+        }
+      }
+      for (i64 i = 0; i < totalh; ++i)
+      {
+        P.cptr[i + 1] += P.cptr[i];
+      }
+      P.cidx.resize((size_t)P.cptr[totalh]);
+      std::vector<int> fill(P.cptr.begin(), P.cptr.end() - 1);
+      for (int c = 0; c < ns; ++c) // ascending child index => deterministic summation order
+      {
+        const int p = P.sn_parent[c];
+        if (p < 0)
+        {
+          continue;
+        }
+        const int kc = P.sn_first[c + 1] - P.sn_first[c];
+        for (i64 q = P.Rptr[c]; q < P.Rptr[c + 1]; ++q)
+        {
+          P.cidx[fill[(size_t)(P.Wptr[p] + P.rel[q])]++] = (int)(P.Wptr[c] + kc + (q - P.Rptr[c]));
+        }
+      }
+    }
+    P.fwd_ptr.assign(P.nlevels + 1, 0);
+    P.bwd_ptr.assign(P.nlevels + 1, 0);
+    P.lvl_maxh.assign(P.nlevels, 0);
+    for (int l = 0; l < P.nlevels; ++l)
+    {
+      // big supernodes first: their CTAs are the long ones
+      std::vector<int> order(P.lvl_sn.begin() + P.lvl_ptr[l], P.lvl_sn.begin() + P.lvl_ptr[l + 1]);
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return (P.Wptr[x + 1] - P.Wptr[x]) > (P.Wptr[y + 1] - P.Wptr[y]); });
+      for (int T : order)
+      {
+        const int k = P.sn_first[T + 1] - P.sn_first[T];
+        const int h = (int)(P.Wptr[T + 1] - P.Wptr[T]);
+        P.lvl_maxh[l] = std::max(P.lvl_maxh[l], h);
+        int nrows = std::min(16, std::max(4, (4096 + k - 1) / k)); // a warp works on up to 4 rows at once
+        nrows     = (nrows + 3) & ~3;
+        for (int row0 = 0; row0 < h; row0 += nrows)
+        {
+          P.fwd_tasks.push_back({T, row0, std::min(nrows, h - row0)});
+        }
+        int ncols = std::min(16, std::max(4, (4096 + h - 1) / h)); // a warp works on up to 4 columns at once
+        ncols     = (ncols + 3) & ~3;
+        for (int col0 = 0; col0 < k; col0 += ncols)
+        {
+          P.bwd_tasks.push_back({T, col0, std::min(ncols, k - col0)});
+        }
+      }
+      P.fwd_ptr[l + 1] = (int)P.fwd_tasks.size();
+      P.bwd_ptr[l + 1] = (int)P.bwd_tasks.size();
+    }
+  }
+
   // ---- hash of the full permutation -----------------------------------------------------------------------------
   {
     std::vector<int> fp(n);

@@ -47,11 +47,12 @@ PLAN_FIELDS = {
     **{k: np.int32 for k in (
         "e_of_k r_of_k k_of_e k_of_r dE_src Acsc_ptr Acsc_row Acsc_src Acsr_ptr Acsr_col Acsr_src "
         "Gsym_ptr Gsym_col Gsym_src perm pinv parent colcount sn_first sn_of_col sn_parent sn_level "
-        "Ridx rel child_ptr child_idx Sgsrc Sterm_a Sterm_b Sterm_d sn_base sn_nt zero_sn lvl_ptr lvl_sn"
+        "Ridx rel child_ptr child_idx Sgsrc Sterm_a Sterm_b Sterm_d sn_base sn_nt zero_sn lvl_ptr lvl_sn "
+        "inv_phase_ptr sn_ncol fwd_ptr bwd_ptr lvl_maxh cptr cidx"
     ).split()},
-    **{k: np.int64 for k in "Rptr Lptr Wptr Sdest Sterm_ptr Uoff".split()},
+    **{k: np.int64 for k in "Rptr Lptr Wptr Sdest Sterm_ptr Uoff Tptr".split()},
 }
-PLAN_STRUCTS = {"stages": 8, "ea_tasks": 2, "pan_tasks": 4, "upd_tasks": 5}  # int32 columns
+PLAN_STRUCTS = {"stages": 8, "ea_tasks": 2, "pan_tasks": 4, "upd_tasks": 5, "inv_tasks": 6, "fwd_tasks": 3, "bwd_tasks": 3}  # int32 columns
 
 
 class Symbolic:
@@ -188,6 +189,7 @@ class Fact:
         """sleqp_fact_release (fact.c:143-161) -> callbacks.free."""
         if self._h:
             check(lib().b200_fact_free(C.byref(self._h)))
+            self._h = C.c_void_p()
 
     def __del__(self):
         try:

@@ -67,6 +67,23 @@ def test_plan_emulation_solves_kkt(name):
         assert np.linalg.norm(z - zr) <= 1e-10 * np.linalg.norm(zr)
 
 
+def test_contributor_lists_invert_the_relative_indices():
+    p = problems.poisson_control(24, 2, seed=2)
+    pl = Symbolic(p.N, *p.kkt_lower()).plan()
+    ns = int(pl["n_supernodes"])
+    k = np.diff(pl["sn_first"])
+    want = [[] for _ in range(int(pl["Wptr"][-1]))]
+    for c in range(ns):
+        par = int(pl["sn_parent"][c])
+        if par < 0:
+            continue
+        rel = pl["rel"][int(pl["Rptr"][c]): int(pl["Rptr"][c + 1])]
+        for t, r in enumerate(rel):
+            want[int(pl["Wptr"][par]) + int(r)].append(int(pl["Wptr"][c]) + int(k[c]) + t)
+    got = [list(pl["cidx"][pl["cptr"][i]: pl["cptr"][i + 1]]) for i in range(len(want))]
+    assert got == want
+
+
 def test_same_pattern_same_structure_different_values():
     a = problems.chain_rosenbrock(300, 0.2, seed=1)
     b = problems.chain_rosenbrock(300, 0.2, seed=1)
