@@ -115,6 +115,10 @@ B200_API int b200_fact_solution(b200_fact* handle, int begin, int end, double* o
  * call on this handle) -- saves one host memcpy in the glue. */
 B200_API int b200_fact_solution_ptr(b200_fact* handle, int begin, int end, const double** out);
 
+/* The slice as a sparse vector, exactly what sleqp_vec_set_from_raw (sparse/vec.c:72-104) would build from it:
+ * entries with |v| > zero_eps, ascending. idx_out / val_out must hold end-begin entries. */
+B200_API int b200_fact_solution_sparse(b200_fact* handle, int begin, int end, double zero_eps, int* idx_out, double* val_out, int* nnz_out);
+
 /* Device-resident variants used by the benchmark's "inputs already in HBM" leg and by a
  * device-resident CG: d_rhs and d_sol are device pointers to n doubles. */
 B200_API int b200_fact_solve_device(b200_fact* handle, const double* d_rhs, double* d_sol);
@@ -128,6 +132,10 @@ B200_API int b200_fact_refactor_device(b200_fact* handle, const double* d_val);
  * solve: ms_out[0] E-block elimination, [1] forward sweep, [2] backward sweep, [3] back-substitution.
  * For roofline arithmetic in bench.py. */
 B200_API int b200_fact_profile_solve(b200_fact* handle, int reps, double* ms_out);
+
+/* Device time (ms, CUDA events, one eager run) of the numeric factorization by kernel class:
+ * ms_out[0] assemble, [1] zero, [2] extend_add, [3] panel, [4] update, [5] inv_gemm, [6] transpose, [7] rest. */
+B200_API int b200_fact_profile_numeric(b200_fact* handle, double* ms_out);
 
 /* rcond = min|d_i| / max|d_i| over the pivots of D (cf. cholmod_l_rcond, fact_cholmod.c:204). */
 B200_API int b200_fact_rcond(b200_fact* handle, double* rcond);

@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import numpy as np
 
-NB, RB, TILE, EA_COLS = 32, 128, 64, 16
+NB, RB, TILE, EA_COLS = 32, 128, 64, 4
 UPD_INPANEL, UPD_SCHUR, UPD_DIAGCOPY = 0, 1, 2
 
 
@@ -134,7 +134,7 @@ class Emulated:
         y = np.full(self.m, np.nan)
         x = np.full(self.m, np.nan)
         for lv in range(int(p["n_levels"])):
-            for T, row0, nrows in p["fwd_tasks"][int(p["fwd_ptr"][lv]) : int(p["fwd_ptr"][lv + 1])]:
+            for T, row0, nrows in p["fwd_tasks"][int(p["fwd_ptr"][lv]) : int(p["fwd_ptr"][lv + 1]), :3]:
                 T, row0, nrows = int(T), int(row0), int(nrows)
                 f, k, r, h = self._geom(T)
                 M = self.mpanel(T)
@@ -158,7 +158,7 @@ class Emulated:
                 y[f + rows[top]] = out[top]
                 W[int(p["Wptr"][T]) + rows[~top]] = out[~top]
         for lv in range(int(p["n_levels"]) - 1, -1, -1):
-            for T, col0, ncols in p["bwd_tasks"][int(p["bwd_ptr"][lv]) : int(p["bwd_ptr"][lv + 1])]:
+            for T, col0, ncols in p["bwd_tasks"][int(p["bwd_ptr"][lv]) : int(p["bwd_ptr"][lv + 1]), :3]:
                 T, col0, ncols = int(T), int(col0), int(ncols)
                 f, k, r, h = self._geom(T)
                 rows = p["Ridx"][int(p["Rptr"][T]) : int(p["Rptr"][T + 1])]

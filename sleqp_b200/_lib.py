@@ -51,7 +51,7 @@ _lib = None
 # every symbol include/sleqp_b200.h declares (tests check they are all exported)
 SYMBOLS = [
     "b200_fact_create", "b200_fact_set_matrix", "b200_fact_solve", "b200_fact_solution",
-    "b200_fact_solution_ptr", "b200_fact_solve_device", "b200_fact_refactor_device", "b200_fact_profile_solve", "b200_fact_rcond", "b200_fact_stats",
+    "b200_fact_solution_ptr", "b200_fact_solution_sparse", "b200_fact_solve_device", "b200_fact_refactor_device", "b200_fact_profile_solve", "b200_fact_profile_numeric", "b200_fact_rcond", "b200_fact_stats",
     "b200_fact_structure", "b200_fact_pivots", "b200_fact_stream", "b200_fact_free", "b200_last_error",
     "b200_symbolic_analyze", "b200_symbolic_stats", "b200_symbolic_structure", "b200_symbolic_export",
     "b200_symbolic_free", "b200_mat_create", "b200_mat_set", "b200_mat_mult_vec", "b200_mat_mult_vec_trans",
@@ -77,9 +77,11 @@ def lib():
     L.b200_fact_solve.argtypes = [vp, C.c_int, ip, dp, C.c_int]
     L.b200_fact_solution.argtypes = [vp, C.c_int, C.c_int, dp]
     L.b200_fact_solution_ptr.argtypes = [vp, C.c_int, C.c_int, C.POINTER(dp)]
+    L.b200_fact_solution_sparse.argtypes = [vp, C.c_int, C.c_int, C.c_double, ip, dp, ip]
     L.b200_fact_solve_device.argtypes = [vp, vp, vp]
     L.b200_fact_refactor_device.argtypes = [vp, vp]
     L.b200_fact_profile_solve.argtypes = [vp, C.c_int, dp]
+    L.b200_fact_profile_numeric.argtypes = [vp, dp]
     L.b200_fact_rcond.argtypes = [vp, dp]
     L.b200_fact_stats.argtypes = [vp, C.POINTER(Stats)]
     L.b200_fact_structure.argtypes = [vp, ip, ip, ip, ip, ip]

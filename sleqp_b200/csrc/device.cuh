@@ -35,8 +35,15 @@ extern std::atomic<int64_t> g_launches;
 struct LaunchCounter
 {
   int64_t* captured = nullptr;
-  inline void tick()
+  // optional tracer (profiling entry points): called after each launch with a kernel-class tag
+  void (*trace)(void* ctx, const char* tag) = nullptr;
+  void* trace_ctx                           = nullptr;
+  inline void tick(const char* tag = nullptr)
   {
+    if (trace && tag)
+    {
+      trace(trace_ctx, tag);
+    }
     if (captured)
     {
       ++*captured;

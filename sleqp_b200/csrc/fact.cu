@@ -480,6 +480,68 @@ b200_fact_refactor_device(b200_fact* F, const double* d_val)
 }
 
 int
+b200_fact_profile_numeric(b200_fact* F, double* ms_out)
+{
+  if (!F || !ms_out)
+  {
+    return set_error(B200_ERR_ARG, "bad argument");
+  }
+  if (!F->factored)
+  {
+    return set_error(B200_ERR_STATE, "profile needs a factorization");
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaSetDevice(F->device));
+    struct Ctx
+    {
+      cudaStream_t stream;
+      std::vector<cudaEvent_t> ev;
+      std::vector<const char*> tag;
+    } ctx;
+    ctx.stream = F->stream;
+    auto mark  = [](void* c, const char* tag) {
+      Ctx* x = (Ctx*)c;
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, x->stream);
+      x->ev.push_back(e);
+      x->tag.push_back(tag);
+    };
+    const NumericBuffers nb = F->nbuf();
+    LaunchCounter lc;
+    lc.trace     = mark;
+    lc.trace_ctx = &ctx;
+    B200_CUDA(cudaStreamSynchronize(F->stream));
+    mark(&ctx, "start");
+    enqueue_numeric(F->dp, nb, F->stream, lc);
+    mark(&ctx, "rest");
+    B200_CUDA(cudaStreamSynchronize(F->stream));
+    const char* names[8] = {"assemble", "zero", "extend_add", "panel", "update", "inv_gemm", "transpose", "rest"};
+    for (int i = 0; i < 8; ++i)
+    {
+      ms_out[i] = 0.0;
+    }
+    for (size_t i = 1; i < ctx.ev.size(); ++i)
+    {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx.ev[i - 1], ctx.ev[i]);
+      for (int n = 0; n < 8; ++n)
+      {
+        if (std::strcmp(ctx.tag[i], names[n]) == 0)
+        {
+          ms_out[n] += ms;
+        }
+      }
+    }
+    for (cudaEvent_t e : ctx.ev)
+    {
+      cudaEventDestroy(e);
+    }
+    return (int)B200_OK;
+  });
+}
+
+int
 b200_fact_profile_solve(b200_fact* F, int reps, double* ms_out)
 {
   if (!F || !ms_out || reps <= 0)
@@ -638,6 +700,31 @@ b200_fact_solution(b200_fact* F, int begin, int end, double* out_dense)
     }
     std::memcpy(out_dense, p, sizeof(double) * (size_t)(end - begin));
   }
+  return B200_OK;
+}
+
+int
+b200_fact_solution_sparse(b200_fact* F, int begin, int end, double zero_eps, int* idx_out, double* val_out, int* nnz_out)
+{
+  const double* p = nullptr;
+  int rc          = b200_fact_solution_ptr(F, begin, end, &p);
+  if (rc != B200_OK)
+  {
+    return rc;
+  }
+  if (!nnz_out || (end > begin && (!idx_out || !val_out)))
+  {
+    return set_error(B200_ERR_ARG, "null output");
+  }
+  int nnz = 0;
+  for (int i = 0; i < end - begin; ++i)
+  {
+    const double v = p[i];
+    idx_out[nnz]   = i;
+    val_out[nnz]   = v;
+    nnz += std::fabs(v) > zero_eps; // branch-free compaction
+  }
+  *nnz_out = nnz;
   return B200_OK;
 }
 

@@ -93,9 +93,10 @@ k_zero_updates(const int* __restrict__ zero_sn, const SnMeta* __restrict__ sn, d
 }
 
 // ---------------------------------------------------------------------------------------------
-// Extend-add of EA_COLS columns of a child's update matrix into its parent's front. Children of
-// one parent run concurrently in the same launch, hence the (native FP64) atomics.
-__global__ void
+// Extend-add of EA_COLS columns of a child's update matrix into its parent's front: one warp per
+// column, lanes stride the rows with 8 independent loads in flight. Children of one parent run
+// concurrently in the same launch, hence the (native FP64) atomics.
+__global__ void __launch_bounds__(32 * EA_COLS)
 k_extend_add(const EaTask* __restrict__ tasks,
              const SnMeta* __restrict__ sn,
              const int* __restrict__ rel,
@@ -107,175 +108,36 @@ k_extend_add(const EaTask* __restrict__ tasks,
   const SnMeta p   = sn[c.parent];
   const int* rl    = rel + c.Rptr;
   const double* Uc = U + c.Uoff;
-  double* Lp       = L + p.Lptr;
-  double* Up       = U + p.Uoff;
   const int hp     = p.k + p.r;
-  const int jend   = min(c.r, (t.jb + 1) * EA_COLS);
-  for (int j = t.jb * EA_COLS; j < jend; ++j)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = t.jb * EA_COLS + warp;
+  if (j >= c.r)
   {
-    const int pj = rl[j];
-    double* dst  = pj < p.k ? Lp + (long long)pj * hp : Up + (long long)(pj - p.k) * p.r - p.k;
-    for (int i = j + threadIdx.x; i < c.r; i += blockDim.x)
-    {
-      atomicAdd(dst + rl[i], Uc[(long long)j * c.r + i]);
-    }
+    return;
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// One panel step of supernode T: columns [c0, c0+w) of the front, w <= NB.
-// Every CTA of the step factors the w x w diagonal block redundantly in shared memory (identical
-// arithmetic, so identical results) and then solves its RB rows of L21; row block 0 also publishes
-// the factored block, the pivots and the inverse of the (unit lower) block into the inverse panel.
-// With more than one row block the factored block goes to a scratch slot (other CTAs are still
-// reading the unfactored one) and k_update copies it back.
-__global__ void __launch_bounds__(RB)
-k_panel(const PanelTask* __restrict__ tasks,
-        const SnMeta* __restrict__ sn,
-        double* __restrict__ L,
-        double* __restrict__ Mt,
-        double* __restrict__ D,
-        double* __restrict__ scratch,
-        const double* __restrict__ scal,
-        int* __restrict__ n_perturbed)
-{
-  __shared__ double A[NB][NB + 1];
-  __shared__ double Ainv[NB][NB + 1];
-  __shared__ double dsh[NB];
-  const PanelTask t = tasks[blockIdx.x];
-  const SnMeta s    = sn[t.sn];
-  const int h       = s.k + s.r;
-  const int c0      = t.t * NB;
-  const int w       = min(NB, s.k - c0);
-  double* P         = L + s.Lptr;
-  const int tid     = threadIdx.x;
-  const double tau  = scal[1];
-
-  for (int idx = tid; idx < w * w; idx += RB)
+  const int pj      = rl[j];
+  double* dst       = pj < p.k ? L + p.Lptr + (long long)pj * hp : U + p.Uoff + (long long)(pj - p.k) * p.r - p.k;
+  const double* src = Uc + (long long)j * c.r;
+  int i             = j + lane;
+  for (; i + 32 * 7 < c.r; i += 32 * 8)
   {
-    const int i = idx % w, j = idx / w;
-    A[i][j] = P[(long long)(c0 + j) * h + c0 + i];
-  }
-  __syncthreads();
-  int nper = 0;
-  for (int j = 0; j < w; ++j)
-  {
-    if (tid == 0)
-    {
-      double dj = A[j][j];
-      if (!(fabs(dj) >= tau) || !isfinite(dj))
-      {
-        dj = tau > 0.0 ? -tau : -1e-300;
-        ++nper;
-      }
-      dsh[j] = dj;
-    }
-    __syncthreads();
-    const double dj = dsh[j];
-    if (tid > j && tid < w)
-    {
-      A[tid][j] = A[tid][j] / dj;
-    }
-    __syncthreads();
-    const int rem = w - j - 1;
-    for (int idx = tid; idx < rem * rem; idx += RB)
-    {
-      const int i = j + 1 + idx % rem, c = j + 1 + idx / rem;
-      if (i >= c)
-      {
-        A[i][c] -= A[i][j] * dj * A[c][j];
-      }
-    }
-    __syncthreads();
-  }
-
-  // rows of L21: x_j = (a_j - sum_{q<j} (x_q d_q) L11[j][q]) / d_j
-  const int row = c0 + w + t.rb * RB + tid;
-  if (row < h)
-  {
-    double x[NB], y[NB];
+    int ri[8];
+    double uv[8];
 #pragma unroll
-    for (int j = 0; j < NB; ++j)
+    for (int u = 0; u < 8; ++u)
     {
-      x[j] = j < w ? P[(long long)(c0 + j) * h + row] : 0.0;
+      ri[u] = rl[i + 32 * u];
+      uv[u] = src[i + 32 * u];
     }
 #pragma unroll
-    for (int j = 0; j < NB; ++j)
+    for (int u = 0; u < 8; ++u)
     {
-      if (j < w)
-      {
-        double acc = x[j];
-#pragma unroll
-        for (int q = 0; q < j; ++q)
-        {
-          acc -= y[q] * A[j][q];
-        }
-        x[j] = acc / dsh[j];
-        y[j] = x[j] * dsh[j];
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < NB; ++j)
-    {
-      if (j < w)
-      {
-        P[(long long)(c0 + j) * h + row] = x[j];
-      }
+      atomicAdd(dst + ri[u], uv[u]);
     }
   }
-
-  if (t.rb == 0)
+  for (; i < c.r; i += 32)
   {
-    if (tid == 0 && nper)
-    {
-      atomicAdd(n_perturbed, nper);
-    }
-    if (tid < w)
-    {
-      D[s.first + c0 + tid] = dsh[tid];
-      // column tid of the inverse of the unit lower block by forward substitution
-      const int c = tid;
-      Ainv[c][c]  = 1.0;
-      for (int i = c + 1; i < w; ++i)
-      {
-        double acc = 0.0;
-        for (int q = c; q < i; ++q)
-        {
-          acc -= A[i][q] * Ainv[q][c];
-        }
-        Ainv[i][c] = acc;
-      }
-    }
-    __syncthreads();
-    double* M = Mt + s.Lptr;
-    for (int idx = tid; idx < w * w; idx += RB)
-    {
-      const int i = idx % w, j = idx / w;
-      if (i >= j)
-      {
-        M[(long long)(c0 + j) * h + c0 + i] = Ainv[i][j];
-      }
-    }
-    if (t.slot < 0)
-    {
-      for (int idx = tid; idx < w * w; idx += RB)
-      {
-        const int i = idx % w, j = idx / w;
-        if (i >= j)
-        {
-          P[(long long)(c0 + j) * h + c0 + i] = i == j ? 1.0 : A[i][j];
-        }
-      }
-    }
-    else
-    {
-      double* sc = scratch + (long long)t.slot * NB * NB;
-      for (int idx = tid; idx < w * w; idx += RB)
-      {
-        const int i = idx % w, j = idx / w;
-        sc[idx] = i == j ? 1.0 : A[i][j];
-      }
-    }
+    atomicAdd(dst + rl[i], src[i]);
   }
 }
 
@@ -290,6 +152,208 @@ dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
+// ---------------------------------------------------------------------------------------------
+// One panel step of supernode T: columns [c0, c0+w) of the front, w <= NB.
+//   1. warp 0 factors the w x w diagonal block (LDL^T, static pivoting) in shared memory: lane i owns row i;
+//   2. warp 1 inverts the unit lower factor column by column (lane c owns column c);
+//   3. every warp applies  L21 = F21 * L11^-T D^-1  to its 32 rows as a DMMA product with the inverted
+//      block -- the triangular solve becomes a 32x32x32 tensor-core GEMM with operands straight from
+//      global memory (A fragments) and shared memory (B fragments).
+// Every CTA of a step (one per RB rows) repeats 1-2 redundantly (identical arithmetic, identical results), so
+// there is no inter-CTA dependency; row block 0 publishes the factored block, the pivots and the inverse.
+// With more than one row block the factored block goes to a scratch slot (the other CTAs still read the
+// unfactored one) and k_update copies it back. Loops are kept rolled on purpose: a fully unrolled version was
+// instruction-fetch bound (ncu: stall_no_instruction ~7 cycles/issue, 42 us per CTA).
+constexpr int LDP = 36; // leading dimension of the B-fragment operand: (4 k + n) mod 16 is conflict-free
+
+__global__ void __launch_bounds__(RB)
+k_panel(const PanelTask* __restrict__ tasks,
+        const SnMeta* __restrict__ sn,
+        double* __restrict__ L,
+        double* __restrict__ Mt,
+        double* __restrict__ D,
+        double* __restrict__ scratch,
+        const double* __restrict__ scal,
+        int* __restrict__ n_perturbed)
+{
+  __shared__ double A[NB][NB + 1];    // unit lower factor of the diagonal block (strict lower part)
+  __shared__ double Ainv[NB][NB + 1]; // its inverse
+  __shared__ double Wm[NB][LDP];      // Wm[k][n] = Ainv[n][k] / d_n
+  __shared__ double dsh[NB], dinv[NB];
+  const PanelTask t = tasks[blockIdx.x];
+  const SnMeta s    = sn[t.sn];
+  const int h       = s.k + s.r;
+  const int c0      = t.t * NB;
+  const int w       = min(NB, s.k - c0);
+  double* P         = L + s.Lptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // A fragments of this warp's 32 rows: issued first, they do not depend on the factorization
+  const int r0 = c0 + w + t.rb * RB + warp * 32;
+  double af[4][8];
+  if (r0 < h)
+  {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4)
+      {
+        const int row = r0 + mi * 8 + (lane >> 2), col = k4 * 4 + (lane & 3);
+        af[mi][k4]    = (row < h && col < w) ? P[(long long)(c0 + col) * h + row] : 0.0;
+      }
+  }
+  for (int idx = tid; idx < NB * NB; idx += RB)
+  {
+    const int i = idx % NB, j = idx / NB;
+    A[i][j]    = (i < w && j <= i) ? P[(long long)(c0 + j) * h + c0 + i] : 0.0;
+    Ainv[i][j] = i == j ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  {
+    // Right-looking LDL^T and, in the same sweep, the inverse of the unit lower factor (the elimination
+    // steps applied to the identity). Thread (lane = row i, warp = column class c mod 4) owns 8 entries
+    // of the 32 x 32 work per step; one barrier per step. Column j is left unscaled (f_ij) during the
+    // loop: l_ij d_j l_cj = f_ij f_cj / d_j.
+    const double tau = scal[1];
+    int nper         = 0;
+    for (int j = 0; j < w; ++j)
+    {
+      double dj = A[j][j];
+      if (!(fabs(dj) >= tau) || !isfinite(dj))
+      {
+        dj = tau > 0.0 ? -tau : -1e-300;
+        ++nper;
+      }
+      const double rdj = 1.0 / dj;
+      if (tid == 0)
+      {
+        dsh[j]  = dj;
+        dinv[j] = rdj;
+      }
+      if (lane > j && lane < w)
+      {
+        const double lij = A[lane][j] * rdj;
+        // all loads, then all stores: shared-memory read-modify-writes would otherwise serialise
+        double cur[NB / 4], oth[NB / 4];
+#pragma unroll
+        for (int u = 0; u < NB / 4; ++u)
+        {
+          const int c = warp + 4 * u;
+          cur[u]      = c > j ? A[lane][c] : Ainv[lane][c];
+          oth[u]      = c > j ? A[c][j] : Ainv[j][c];
+        }
+#pragma unroll
+        for (int u = 0; u < NB / 4; ++u)
+        {
+          const int c = warp + 4 * u;
+          if (c > j)
+          {
+            if (c <= lane)
+            {
+              A[lane][c] = cur[u] - lij * oth[u];
+            }
+          }
+          else
+          {
+            Ainv[lane][c] = cur[u] - lij * oth[u];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (t.rb == 0 && tid == 0 && nper)
+    {
+      atomicAdd(n_perturbed, nper);
+    }
+    // scale the columns: l_ij = f_ij / d_j, unit diagonal
+    for (int idx = tid; idx < NB * NB; idx += RB)
+    {
+      const int i = idx % NB, j = idx / NB;
+      if (j < w)
+      {
+        A[i][j] = i == j ? 1.0 : (i > j ? A[i][j] * dinv[j] : 0.0);
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NB * NB; idx += RB)
+  {
+    const int kk = idx / NB, n = idx % NB;
+    Wm[kk][n] = (n < w && kk <= n) ? Ainv[n][kk] * dinv[n] : 0.0;
+  }
+  __syncthreads();
+
+  if (r0 < h)
+  {
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj)
+      {
+        acc[mi][nj][0] = 0.0;
+        acc[mi][nj][1] = 0.0;
+      }
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4)
+    {
+      double bf[4];
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj)
+      {
+        bf[nj] = Wm[k4 * 4 + (lane & 3)][nj * 8 + (lane >> 2)];
+      }
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj)
+        {
+          dmma(acc[mi][nj][0], acc[mi][nj][1], af[mi][k4], bf[nj]);
+        }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+        {
+          const int row = r0 + mi * 8 + (lane >> 2), col = nj * 8 + 2 * (lane & 3) + e;
+          if (row < h && col < w)
+          {
+            P[(long long)(c0 + col) * h + row] = acc[mi][nj][e];
+          }
+        }
+  }
+
+  if (t.rb == 0)
+  {
+    if (tid < w)
+    {
+      D[s.first + c0 + tid] = dsh[tid];
+    }
+    double* M  = Mt + s.Lptr;
+    double* sc = scratch + (long long)max(t.slot, 0) * NB * NB;
+    for (int idx = tid; idx < w * w; idx += RB)
+    {
+      const int i = idx % w, j = idx / w;
+      if (i >= j)
+      {
+        M[(long long)(c0 + j) * h + c0 + i] = Ainv[i][j];
+        if (t.slot < 0)
+        {
+          P[(long long)(c0 + j) * h + c0 + i] = A[i][j];
+        }
+      }
+      if (t.slot >= 0)
+      {
+        sc[idx] = A[i][j];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 constexpr int KC  = 16;       // k-chunk staged per iteration
 constexpr int LDT = TILE + 4; // padded leading dimension: (LDT mod 16) == 4 -> conflict-free fragments
 
@@ -355,11 +419,15 @@ tile_update(const double* __restrict__ P,
       acc[a][b][1] = 0.0;
     }
 
-  for (int kc = kb; kc < ke; kc += KC)
-  {
-    // stage KC x TILE of both operands; consecutive threads read consecutive rows (coalesced)
-    for (int idx = tid; idx < KC * TILE; idx += 128)
+  // software pipeline: the next chunk's global loads are in flight while this chunk's DMMAs run.
+  // Element u of a thread: idx = tid + 128 u -> (kk = idx / TILE, ii = idx % TILE): consecutive threads
+  // read consecutive rows (coalesced).
+  double pa[8], pb[8];
+  auto gload = [&](int kc) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
     {
+      const int idx = tid + 128 * u;
       const int kk = idx / TILE, ii = idx % TILE;
       const int col = kc + kk;
       double av = 0.0, bv = 0.0;
@@ -375,10 +443,25 @@ tile_update(const double* __restrict__ P,
           bv = pc[rb0 + ii] * d[col];
         }
       }
-      As[kk][ii] = av;
-      Bs[kk][ii] = bv;
+      pa[u] = av;
+      pb[u] = bv;
+    }
+  };
+  gload(kb);
+  for (int kc = kb; kc < ke; kc += KC)
+  {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+    {
+      const int idx = tid + 128 * u;
+      As[idx / TILE][idx % TILE] = pa[u];
+      Bs[idx / TILE][idx % TILE] = pb[u];
     }
     __syncthreads();
+    if (kc + KC < ke)
+    {
+      gload(kc + KC);
+    }
     if (active)
     {
       mma_chunk(As, Bs, acc, wy, wx, lane);
@@ -389,6 +472,21 @@ tile_update(const double* __restrict__ P,
   {
     return;
   }
+  // epilogue in two phases (all loads, then all stores): interleaving them serialises 32 dependent
+  // load -> store round trips per thread (ncu: 25 us for a single 64x64 tile with K = 32)
+  double cv[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+      {
+        const int i = wy * 32 + a * 8 + (lane >> 2);
+        const int j = wx * 32 + b * 8 + 2 * (lane & 3) + e;
+        const bool ok = i < na && j < nb && gi0 + i >= gj0 + j;
+        cv[a][b][e]   = (ok && accumulate) ? C[i + (long long)j * ldc] : 0.0;
+      }
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -400,8 +498,7 @@ tile_update(const double* __restrict__ P,
         const int j = wx * 32 + b * 8 + 2 * (lane & 3) + e;
         if (i < na && j < nb && gi0 + i >= gj0 + j)
         {
-          double* c = C + i + (long long)j * ldc;
-          *c        = (accumulate ? *c : 0.0) - acc[a][b][e];
+          C[i + (long long)j * ldc] = cv[a][b][e] - acc[a][b][e];
         }
       }
 }
@@ -515,22 +612,39 @@ k_inv_gemm(const InvTask* __restrict__ tasks,
       acc[a][b][0] = 0.0;
       acc[a][b][1] = 0.0;
     }
-  for (int kc = t.kb; kc < t.ke; kc += KC)
-  {
-    for (int idx = tid; idx < KC * TILE; idx += 128)
+  double pa[8], pb[8];
+  auto gload = [&](int kc) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
     {
+      const int idx = tid + 128 * u;
       {
         const int kk = idx / TILE, ii = idx % TILE; // consecutive threads -> consecutive rows of X
         const int q = kc + kk;
-        As[kk][ii]  = (q < t.ke && ii < na) ? X[ii + (long long)q * ldx] : 0.0;
+        pa[u]       = (q < t.ke && ii < na) ? X[ii + (long long)q * ldx] : 0.0;
       }
       {
         const int jj = idx / KC, kk = idx % KC; // consecutive threads -> consecutive rows of Y
         const int q = kc + kk;
-        Bs[kk][jj]  = (q < t.ke && jj < nb) ? Y[q + (long long)jj * ldy] : 0.0;
+        pb[u]       = (q < t.ke && jj < nb) ? Y[q + (long long)jj * ldy] : 0.0;
       }
     }
+  };
+  gload(t.kb);
+  for (int kc = t.kb; kc < t.ke; kc += KC)
+  {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+    {
+      const int idx = tid + 128 * u;
+      As[idx / TILE][idx % TILE] = pa[u];
+      Bs[idx % KC][idx / KC]     = pb[u];
+    }
     __syncthreads();
+    if (kc + KC < t.ke)
+    {
+      gload(kc + KC);
+    }
     mma_chunk(As, Bs, acc, wy, wx, lane);
     __syncthreads();
   }
@@ -592,7 +706,7 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
     const int threads = 256;
     const unsigned blocks = (unsigned)((P.nnzS + threads - 1) / threads);
     k_assemble<<<blocks, threads, 0, stream>>>(P.nnzS, dp.Sdest.p, dp.Sgsrc.p, dp.Sterm_ptr.p, dp.Sterm_a.p, dp.Sterm_b.p, dp.Sterm_d.p, nb.val, nb.L);
-    lc.tick();
+    lc.tick("assemble");
     const unsigned rb = (unsigned)std::min<long long>((P.m + threads - 1) / threads, 1184);
     k_diagmax<<<rb, threads, 0, stream>>>(P.m, dp.Sdiag.p, nb.L, (unsigned long long*)nb.scal);
     lc.tick();
@@ -605,22 +719,22 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
     {
       dim3 grid((unsigned)(st.zero_end - st.zero_begin), 16);
       k_zero_updates<<<grid, 256, 0, stream>>>(dp.zero_sn.p + st.zero_begin, dp.sn.p, nb.U);
-      lc.tick();
+      lc.tick("zero");
     }
     if (st.ea_end > st.ea_begin)
     {
-      k_extend_add<<<(unsigned)(st.ea_end - st.ea_begin), 128, 0, stream>>>(dp.ea_tasks.p + st.ea_begin, dp.sn.p, dp.rel.p, nb.L, nb.U);
-      lc.tick();
+      k_extend_add<<<(unsigned)(st.ea_end - st.ea_begin), 32 * EA_COLS, 0, stream>>>(dp.ea_tasks.p + st.ea_begin, dp.sn.p, dp.rel.p, nb.L, nb.U);
+      lc.tick("extend_add");
     }
     if (st.pan_end > st.pan_begin)
     {
       k_panel<<<(unsigned)(st.pan_end - st.pan_begin), RB, 0, stream>>>(dp.pan_tasks.p + st.pan_begin, dp.sn.p, nb.L, nb.Mt, nb.D, nb.scratch, nb.scal, nb.n_perturbed);
-      lc.tick();
+      lc.tick("panel");
     }
     if (st.upd_end > st.upd_begin)
     {
       k_update<<<(unsigned)(st.upd_end - st.upd_begin), 128, 0, stream>>>(dp.upd_tasks.p + st.upd_begin, dp.sn.p, nb.L, nb.U, nb.D, nb.scratch);
-      lc.tick();
+      lc.tick("update");
     }
   }
   // selective inversion
@@ -630,13 +744,13 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
     if (e > b)
     {
       k_inv_gemm<<<(unsigned)(e - b), 128, 0, stream>>>(dp.inv_tasks.p + b, dp.sn.p, nb.L, nb.Mt, nb.tmp);
-      lc.tick();
+      lc.tick("inv_gemm");
     }
   }
   if (!P.tr_tasks.empty())
   {
     k_transpose<<<(unsigned)P.tr_tasks.size(), 256, 0, stream>>>(dp.tr_tasks.p, dp.sn.p, nb.Mt, nb.Mr);
-    lc.tick();
+    lc.tick("transpose");
   }
   // contiguous operator values for the solve
   const int threads = 256;

@@ -21,7 +21,7 @@ typedef int64_t i64;
 constexpr int NB       = 32;  // panel width of the blocked dense LDL^T
 constexpr int RB       = 128; // rows per TRSM row-block CTA
 constexpr int TILE     = 64;  // output tile edge of the DMMA update kernel
-constexpr int EA_COLS  = 16;  // update-matrix columns per extend-add task
+constexpr int EA_COLS  = 4;   // update-matrix columns per extend-add task (one warp each)
 constexpr int LEAF_MAX = 32;  // etree subtrees up to this many columns become one dense supernode
 
 // kinds of update tasks
@@ -69,14 +69,18 @@ struct TrTask
   int sn, i0, j0; // 32x32 tile of a panel to transpose into the row-major copy
 };
 
+// The sweep tasks carry the geometry they need, so a CTA starts loading panel data after ONE dependent
+// load (the task) instead of two (task -> supernode record).
 struct FwdTask
 {
-  int sn, row0, nrows;
+  int sn, row0, nrows, first, k, pad;
+  long long Lptr, Wptr;
 };
 
 struct BwdTask
 {
-  int sn, col0, ncols;
+  int sn, col0, ncols, first, k, h;
+  long long Lptr, Rptr;
 };
 
 struct Stage

@@ -152,25 +152,67 @@ k_axpy1(int n, const double* __restrict__ x, double* __restrict__ y)
 // deterministic). Every CTA of a supernode rebuilds b_T itself, so nothing depends on anything inside a
 // level. Tail rows also receive the children's pass-through contributions.
 // Reads the row-major copy Mr of the inverse panel: a warp owns RG rows at a time, lanes stride the
-// (contiguous) columns with 8 independent loads in flight. Dynamic shared memory: bT[k].
+// (contiguous) columns with 8 independent loads in flight; the first round of panel loads is issued
+// before b_T is assembled (it does not depend on it). Dynamic shared memory: bT[k].
 template <int RG>
 __device__ __forceinline__ void
-fwd_rows(const double* __restrict__ P, int k, const double* __restrict__ bT, int r0, int nvalid, int lane, double (&res)[RG])
+fwd_body(const FwdTask& t,
+         const int* __restrict__ cptr,
+         const int* __restrict__ cidx,
+         const double* __restrict__ Mr,
+         const double* __restrict__ b,
+         double* __restrict__ y,
+         double* __restrict__ W,
+         double* bT)
 {
-  constexpr int U = 8 / RG;
+  constexpr int U  = 8 / RG;
+  constexpr int NW = SOLVE_THREADS / 32;
+  const int k      = t.k;
+  const double* P  = Mr + t.Lptr;
+  const int* cp    = cptr + t.Wptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g0     = warp * RG;
+  const int nvalid = min(RG, t.nrows - g0); // <= 0: this warp has no rows
+  const int r0     = t.row0 + g0;
+  // the top block is lower triangular: row r only needs columns <= r; rows of one group share the bound
+  // of the last row (entries beyond a row's diagonal are zeros)
+  const int rlast = r0 + nvalid - 1;
+  const int jend  = nvalid <= 0 ? 0 : (rlast < k ? rlast + 1 : k);
+
+  double pre[RG][U];
+#pragma unroll
+  for (int a = 0; a < RG; ++a)
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const int j = lane + 32 * u;
+      pre[a][u]   = (a < nvalid && j < jend) ? P[(long long)(r0 + a) * k + j] : 0.0;
+    }
+
+  for (int j = tid; j < k; j += SOLVE_THREADS)
+  {
+    double acc = b[t.first + j];
+    for (int e = cp[j]; e < cp[j + 1]; ++e)
+    {
+      acc += W[cidx[e]];
+    }
+    bT[j] = acc;
+  }
+  __syncthreads();
+  if (nvalid <= 0)
+  {
+    return;
+  }
   double acc[RG][U];
 #pragma unroll
   for (int a = 0; a < RG; ++a)
 #pragma unroll
     for (int u = 0; u < U; ++u)
     {
-      acc[a][u] = 0.0;
+      const int j = lane + 32 * u;
+      acc[a][u]   = j < jend ? pre[a][u] * bT[j] : 0.0;
     }
-  // the top block is lower triangular: row r only needs columns <= r; rows of one group share the
-  // bound of the last row (entries beyond a row's diagonal are zeros of the memset / transpose)
-  const int rlast = r0 + nvalid - 1;
-  const int jend  = rlast < k ? rlast + 1 : k;
-  int j           = lane;
+  int j = lane + 32 * U;
   for (; j + 32 * (U - 1) < jend; j += 32 * U)
   {
 #pragma unroll
@@ -199,6 +241,7 @@ fwd_rows(const double* __restrict__ P, int k, const double* __restrict__ bT, int
       }
     }
   }
+  double mine = 0.0;
 #pragma unroll
   for (int a = 0; a < RG; ++a)
   {
@@ -212,13 +255,31 @@ fwd_rows(const double* __restrict__ P, int k, const double* __restrict__ bT, int
     {
       v += __shfl_xor_sync(0xffffffffu, v, o);
     }
-    res[a] = v;
+    if (lane == a)
+    {
+      mine = v;
+    }
+  }
+  if (lane < nvalid)
+  {
+    const int r = r0 + lane;
+    if (r < k)
+    {
+      y[t.first + r] = mine;
+    }
+    else
+    {
+      for (int e = cp[r]; e < cp[r + 1]; ++e) // pass-through from the children
+      {
+        mine += W[cidx[e]];
+      }
+      W[t.Wptr + r] = mine;
+    }
   }
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS)
 k_fwd_chunk(const FwdTask* __restrict__ tasks,
-            const SnMeta* __restrict__ sn,
             const int* __restrict__ cptr,
             const int* __restrict__ cidx,
             const double* __restrict__ Mr,
@@ -227,89 +288,75 @@ k_fwd_chunk(const FwdTask* __restrict__ tasks,
             double* __restrict__ W)
 {
   extern __shared__ double bT[];
-  const FwdTask t = tasks[blockIdx.x];
-  const SnMeta s  = sn[t.sn];
-  const int k     = s.k;
-  const double* P = Mr + s.Lptr;
-  const int* cp   = cptr + s.Wptr;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  for (int j = tid; j < k; j += SOLVE_THREADS)
-  {
-    double acc = b[s.first + j];
-    for (int e = cp[j]; e < cp[j + 1]; ++e)
-    {
-      acc += W[cidx[e]];
-    }
-    bT[j] = acc;
-  }
-  __syncthreads();
+  const FwdTask t  = tasks[blockIdx.x];
   constexpr int NW = SOLVE_THREADS / 32;
   const int rg     = (t.nrows + NW - 1) / NW; // rows per warp: 1..4
-  const int g0     = warp * rg;
-  if (g0 >= t.nrows)
-  {
-    return;
-  }
-  const int nvalid = min(rg, t.nrows - g0);
-  const int r0     = t.row0 + g0;
-  double res[4];
   if (rg == 1)
   {
-    double r1[1];
-    fwd_rows<1>(P, k, bT, r0, nvalid, lane, r1);
-    res[0] = r1[0];
+    fwd_body<1>(t, cptr, cidx, Mr, b, y, W, bT);
   }
   else if (rg == 2)
   {
-    double r2[2];
-    fwd_rows<2>(P, k, bT, r0, nvalid, lane, r2);
-    res[0] = r2[0];
-    res[1] = r2[1];
+    fwd_body<2>(t, cptr, cidx, Mr, b, y, W, bT);
   }
   else
   {
-    fwd_rows<4>(P, k, bT, r0, nvalid, lane, res);
-  }
-  if (lane < nvalid)
-  {
-    const int r = r0 + lane;
-    double v    = lane == 0 ? res[0] : lane == 1 ? res[1] : lane == 2 ? res[2] : res[3];
-    if (r < k)
-    {
-      y[s.first + r] = v;
-    }
-    else
-    {
-      for (int e = cp[r]; e < cp[r + 1]; ++e) // pass-through from the children
-      {
-        v += W[cidx[e]];
-      }
-      W[s.Wptr + r] = v;
-    }
+    fwd_body<4>(t, cptr, cidx, Mr, b, y, W, bT);
   }
 }
 
 // ---- diagonal + backward sweep -----------------------------------------------------------------------
 // One CTA per (supernode, column chunk):  x_T = Minv^T [D^-1 y_T; x_rows].  A warp owns CG columns at a
 // time (rows are contiguous in the column-major panel), lanes stride the rows with 8 independent loads
-// in flight, shuffle reduction. Dynamic shared memory: v[h].
+// in flight (first round issued before the vector is gathered), shuffle reduction. Dynamic shared memory: v[h].
 template <int CG>
 __device__ __forceinline__ void
-bwd_cols(const double* __restrict__ P, int h, const double* __restrict__ v, int j0, int nvalid, int lane, double (&res)[CG])
+bwd_body(const BwdTask& t,
+         const int* __restrict__ Ridx,
+         const double* __restrict__ Mt,
+         const double* __restrict__ D,
+         const double* __restrict__ y,
+         double* __restrict__ x,
+         double* v)
 {
   constexpr int U = 8 / CG;
+  const int k = t.k, h = t.h;
+  const double* P = Mt + t.Lptr;
+  const int* rows = Ridx + t.Rptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g0     = warp * CG;
+  const int nvalid = min(CG, t.ncols - g0);
+  const int j0     = t.col0 + g0;
+  // column j needs rows >= j; the columns of a group start at the first one's diagonal (the entries above a
+  // diagonal are zeros)
+  double pre[CG][U];
+#pragma unroll
+  for (int c = 0; c < CG; ++c)
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const int i = j0 + lane + 32 * u;
+      pre[c][u]   = (c < nvalid && i < h) ? P[(long long)(j0 + c) * h + i] : 0.0;
+    }
+  for (int i = t.col0 + tid; i < h; i += SOLVE_THREADS)
+  {
+    v[i] = i < k ? y[t.first + i] / D[t.first + i] : x[rows[i - k]];
+  }
+  __syncthreads();
+  if (nvalid <= 0)
+  {
+    return;
+  }
   double acc[CG][U];
 #pragma unroll
   for (int c = 0; c < CG; ++c)
 #pragma unroll
     for (int u = 0; u < U; ++u)
     {
-      acc[c][u] = 0.0;
+      const int i = j0 + lane + 32 * u;
+      acc[c][u]   = i < h ? pre[c][u] * v[i] : 0.0;
     }
-  // column j needs rows >= j; the columns of a group start at the first one's diagonal (the entries
-  // above a diagonal are zeros)
-  int i = j0 + lane;
+  int i = j0 + lane + 32 * U;
   for (; i + 32 * (U - 1) < h; i += 32 * U)
   {
 #pragma unroll
@@ -338,6 +385,7 @@ bwd_cols(const double* __restrict__ P, int h, const double* __restrict__ v, int 
       }
     }
   }
+  double mine = 0.0;
 #pragma unroll
   for (int c = 0; c < CG; ++c)
   {
@@ -351,13 +399,19 @@ bwd_cols(const double* __restrict__ P, int h, const double* __restrict__ v, int 
     {
       a += __shfl_xor_sync(0xffffffffu, a, o);
     }
-    res[c] = a;
+    if (lane == c)
+    {
+      mine = a;
+    }
+  }
+  if (lane < nvalid)
+  {
+    x[t.first + j0 + lane] = mine;
   }
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS)
 k_bwd_chunk(const BwdTask* __restrict__ tasks,
-            const SnMeta* __restrict__ sn,
             const int* __restrict__ Ridx,
             const double* __restrict__ Mt,
             const double* __restrict__ D,
@@ -365,48 +419,20 @@ k_bwd_chunk(const BwdTask* __restrict__ tasks,
             double* __restrict__ x)
 {
   extern __shared__ double v[];
-  const BwdTask t = tasks[blockIdx.x];
-  const SnMeta s  = sn[t.sn];
-  const int k = s.k, h = s.k + s.r;
-  const double* P = Mt + s.Lptr;
-  const int* rows = Ridx + s.Rptr;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  for (int i = t.col0 + tid; i < h; i += SOLVE_THREADS)
-  {
-    v[i] = i < k ? y[s.first + i] / D[s.first + i] : x[rows[i - k]];
-  }
-  __syncthreads();
+  const BwdTask t  = tasks[blockIdx.x];
   constexpr int NW = SOLVE_THREADS / 32;
   const int cg     = (t.ncols + NW - 1) / NW; // columns per warp: 1..4
-  const int g0     = warp * cg;
-  if (g0 >= t.ncols)
-  {
-    return;
-  }
-  const int nvalid = min(cg, t.ncols - g0);
-  const int j0     = t.col0 + g0;
-  double res[4];
   if (cg == 1)
   {
-    double r1[1];
-    bwd_cols<1>(P, h, v, j0, nvalid, lane, r1);
-    res[0] = r1[0];
+    bwd_body<1>(t, Ridx, Mt, D, y, x, v);
   }
   else if (cg == 2)
   {
-    double r2[2];
-    bwd_cols<2>(P, h, v, j0, nvalid, lane, r2);
-    res[0] = r2[0];
-    res[1] = r2[1];
+    bwd_body<2>(t, Ridx, Mt, D, y, x, v);
   }
   else
   {
-    bwd_cols<4>(P, h, v, j0, nvalid, lane, res);
-  }
-  if (lane < nvalid)
-  {
-    x[s.first + j0 + lane] = lane == 0 ? res[0] : lane == 1 ? res[1] : lane == 2 ? res[2] : res[3];
+    bwd_body<4>(t, Ridx, Mt, D, y, x, v);
   }
 }
 
@@ -512,7 +538,7 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
     {
       const int cnt     = P.fwd_ptr[l + 1] - P.fwd_ptr[l];
       const size_t smem = sizeof(double) * (size_t)P.lvl_maxh[l];
-      k_fwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.fwd_tasks.p + P.fwd_ptr[l], dp.sn.p, dp.cptr.p, dp.cidx.p, nb.Mr, sb.bR, sb.y, sb.W);
+      k_fwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.fwd_tasks.p + P.fwd_ptr[l], dp.cptr.p, dp.cidx.p, nb.Mr, sb.bR, sb.y, sb.W);
       lc.tick();
     }
     mark(2);
@@ -520,7 +546,7 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
     {
       const int cnt = P.bwd_ptr[l + 1] - P.bwd_ptr[l];
       const size_t smem = sizeof(double) * (size_t)P.lvl_maxh[l];
-      k_bwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.bwd_tasks.p + P.bwd_ptr[l], dp.sn.p, dp.Ridx.p, nb.Mt, nb.D, sb.y, sb.x);
+      k_bwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.bwd_tasks.p + P.bwd_ptr[l], dp.Ridx.p, nb.Mt, nb.D, sb.y, sb.x);
       lc.tick();
     }
     mark(3);

@@ -31,28 +31,70 @@ fnv1a(uint64_t h, const void* data, size_t bytes)
   return h;
 }
 
+// Fast 64-bit hash over 8-byte words, four independent lanes (this runs on every set_matrix, over
+// the whole pattern: ~16 MB for config 3, so a byte-wise FNV would cost more than the GPU factorization).
+static inline uint64_t
+mix64(uint64_t h, uint64_t v)
+{
+  h ^= v;
+  h *= 0x9E3779B97F4A7C15ull;
+  h ^= h >> 29;
+  return h;
+}
+
+static uint64_t
+hash_words(uint64_t seed, const void* data, size_t bytes)
+{
+  const unsigned char* p = (const unsigned char*)data;
+  uint64_t h0 = seed ^ 0x243F6A8885A308D3ull, h1 = seed ^ 0x13198A2E03707344ull, h2 = seed ^ 0xA4093822299F31D0ull, h3 = seed ^ 0x082EFA98EC4E6C89ull;
+  size_t i = 0;
+  for (; i + 32 <= bytes; i += 32)
+  {
+    uint64_t w[4];
+    std::memcpy(w, p + i, 32);
+    h0 = mix64(h0, w[0]);
+    h1 = mix64(h1, w[1]);
+    h2 = mix64(h2, w[2]);
+    h3 = mix64(h3, w[3]);
+  }
+  uint64_t tail[4] = {0, 0, 0, 0};
+  std::memcpy(tail, p + i, bytes - i);
+  h0 = mix64(h0, tail[0]);
+  h1 = mix64(h1, tail[1]);
+  h2 = mix64(h2, tail[2]);
+  h3 = mix64(h3, tail[3] ^ (uint64_t)bytes);
+  return mix64(mix64(mix64(h0, h1), h2), h3);
+}
+
 uint64_t
 hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only)
 {
-  uint64_t h = 14695981039346656037ull;
-  int hdr[3] = {n, nnz, lower_only ? 1 : 0};
-  h          = fnv1a(h, hdr, sizeof(hdr));
-  h          = fnv1a(h, colptr, sizeof(int) * (size_t)(n + 1));
-  h          = fnv1a(h, rowidx, sizeof(int) * (size_t)nnz);
+  int hdr[4] = {n, nnz, lower_only ? 1 : 0, 0};
+  uint64_t h = hash_words(0x5EED, hdr, sizeof(hdr));
+  h          = hash_words(h, colptr, sizeof(int) * (size_t)(n + 1));
+  h          = hash_words(h, rowidx, sizeof(int) * (size_t)nnz);
   // the E/R classification depends on which diagonals are non-zero: part of the key
-  std::vector<unsigned char> dz((size_t)n, 0);
+  uint64_t bits = 0, hb = h;
   for (int j = 0; j < n; ++j)
   {
-    for (int p = colptr[j]; p < colptr[j + 1]; ++p)
+    int p         = colptr[j];
+    const int end = colptr[j + 1];
+    if (!lower_only)
     {
-      if (rowidx[p] == j && val[p] != 0.)
+      while (p < end && rowidx[p] < j)
       {
-        dz[j] = 1;
+        ++p;
       }
     }
+    const uint64_t nz = (p < end && rowidx[p] == j && val[p] != 0.) ? 1u : 0u;
+    bits              = (bits << 1) | nz;
+    if ((j & 63) == 63)
+    {
+      hb   = mix64(hb, bits);
+      bits = 0;
+    }
   }
-  h = fnv1a(h, dz.data(), dz.size());
-  return h;
+  return mix64(hb, bits ^ 0xD1A6);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1509,13 +1551,13 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         nrows     = (nrows + 3) & ~3;
         for (int row0 = 0; row0 < h; row0 += nrows)
         {
-          P.fwd_tasks.push_back({T, row0, std::min(nrows, h - row0)});
+          P.fwd_tasks.push_back({T, row0, std::min(nrows, h - row0), P.sn_first[T], k, 0, P.Lptr[T], P.Wptr[T]});
         }
         int ncols = std::min(16, std::max(4, (4096 + h - 1) / h)); // a warp works on up to 4 columns at once
         ncols     = (ncols + 3) & ~3;
         for (int col0 = 0; col0 < k; col0 += ncols)
         {
-          P.bwd_tasks.push_back({T, col0, std::min(ncols, k - col0)});
+          P.bwd_tasks.push_back({T, col0, std::min(ncols, k - col0), P.sn_first[T], k, h, P.Lptr[T], P.Rptr[T]});
         }
       }
       P.fwd_ptr[l + 1] = (int)P.fwd_tasks.size();

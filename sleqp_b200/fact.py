@@ -52,7 +52,7 @@ PLAN_FIELDS = {
     ).split()},
     **{k: np.int64 for k in "Rptr Lptr Wptr Sdest Sterm_ptr Uoff Tptr".split()},
 }
-PLAN_STRUCTS = {"stages": 8, "ea_tasks": 2, "pan_tasks": 4, "upd_tasks": 5, "inv_tasks": 6, "fwd_tasks": 3, "bwd_tasks": 3}  # int32 columns
+PLAN_STRUCTS = {"stages": 8, "ea_tasks": 2, "pan_tasks": 4, "upd_tasks": 5, "inv_tasks": 6, "fwd_tasks": 10, "bwd_tasks": 10}  # int32 columns
 
 
 class Symbolic:
@@ -138,11 +138,12 @@ class Fact:
     def solution(self, begin, end, zero_eps=1e-20):
         """sleqp_fact_solution (fact.c:91-102): sparse slice, entries with |v| <= zero_eps dropped
         (sleqp_vec_set_from_raw, vec.c:72-104). Returns (indices, values)."""
-        p = _dp()
-        check(lib().b200_fact_solution_ptr(self._h, int(begin), int(end), C.byref(p)))
-        v = np.ctypeslib.as_array(p, shape=(int(end - begin),))
-        idx = np.nonzero(np.abs(v) > zero_eps)[0].astype(np.int32)
-        return idx, v[idx].copy()
+        n = int(end - begin)
+        idx = np.empty(max(n, 1), dtype=np.int32)
+        val = np.empty(max(n, 1), dtype=np.float64)
+        nnz = C.c_int()
+        check(lib().b200_fact_solution_sparse(self._h, int(begin), int(end), float(zero_eps), _pi(idx), _pd(val), C.byref(nnz)))
+        return idx[: nnz.value], val[: nnz.value]
 
     def solve_device(self, d_rhs_ptr: int, d_sol_ptr: int):
         check(lib().b200_fact_solve_device(self._h, C.c_void_p(d_rhs_ptr), C.c_void_p(d_sol_ptr)))
@@ -156,6 +157,12 @@ class Fact:
         out = np.zeros(4, dtype=np.float64)
         check(lib().b200_fact_profile_solve(self._h, int(reps), _pd(out)))
         return out
+
+    def profile_numeric(self) -> dict:
+        """Device ms of one eager numeric factorization by kernel class."""
+        out = np.zeros(8, dtype=np.float64)
+        check(lib().b200_fact_profile_numeric(self._h, _pd(out)))
+        return dict(zip(("assemble", "zero", "extend_add", "panel", "update", "inv_gemm", "transpose", "rest"), out.tolist()))
 
     def cond(self) -> float:
         """sleqp_fact_cond (fact.c:104-118): 1 / rcond."""
