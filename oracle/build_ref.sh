@@ -92,6 +92,9 @@ gcc $CFLAGS -c "$SRC/fact/fact_lapack.c" -o "$OUT/obj/fact_lapack.o"
 gcc -shared -o "$OUT/libsleqp_ref_lapack.so" $OBJS "$OUT/obj/fact_lapack.o" "$OUT/obj/lapack_shim.o" \
     "$OPENBLAS" -Wl,-rpath,"$(dirname "$OPENBLAS")" -lm
 echo "built $OUT/libsleqp_ref_lapack.so"
+# EQP harness over the reference LAPACK backend (expected values of the SLEQP-iterate proxy)
+gcc $CFLAGS -I"$SRC/fact" -I"$SRC/aug_jac" -I"$SRC/tr" "$HERE/eqp_harness.c" -o "$OUT/eqp_harness_lapack" \
+    -L"$OUT" -lsleqp_ref_lapack -Wl,-rpath,'$ORIGIN' -lm
 
 # drop-in: same reference core, our host glue instead of fact_lapack.c
 if [ -f "$REPO/sleqp_b200/host/fact_b200.c" ] && [ -f "$REPO/sleqp_b200/libsleqp_b200.so" ]; then
@@ -99,4 +102,6 @@ if [ -f "$REPO/sleqp_b200/host/fact_b200.c" ] && [ -f "$REPO/sleqp_b200/libsleqp
   gcc -shared -o "$OUT/libsleqp_ref_b200.so" $OBJS "$OUT/obj/fact_b200.o" \
       -L"$REPO/sleqp_b200" -lsleqp_b200 -Wl,-rpath,'$ORIGIN/../../sleqp_b200' -lm
   echo "built $OUT/libsleqp_ref_b200.so"
+  gcc $CFLAGS -I"$SRC/fact" -I"$SRC/aug_jac" -I"$SRC/tr" "$HERE/eqp_harness.c" -o "$OUT/eqp_harness_b200" \
+      -L"$OUT" -lsleqp_ref_b200 -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../sleqp_b200' -L"$REPO/sleqp_b200" -lsleqp_b200 -lm
 fi

@@ -103,3 +103,21 @@ if __name__ == "__main__":
     spmv_cases(ref)
     fact_cases(ref)
     vec_cases(ref)
+
+
+def eqp_harness_case(n=400, radii=12):
+    """Output of the reference EQP harness (oracle/eqp_harness.c over the reference LAPACK backend)."""
+    import subprocess
+
+    exe = os.path.join(ROOT, "oracle", "_ref", "eqp_harness_lapack")
+    out = subprocess.run([exe, str(n), str(radii)], check=True, capture_output=True, text=True).stdout
+    data = {}
+    for line in out.splitlines():
+        parts = line.split()
+        data[parts[0]] = np.array(parts[2:], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, f"eqp_harness_lapack_n{n}.npz"), **data)
+    print("eqp harness:", list(data))
+
+
+if __name__ == "__main__":
+    eqp_harness_case()
