@@ -272,11 +272,9 @@ def run_ours(args, rank, world, local_rank):
     launches = lib.b200_launch_count() - launches0
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     clocks = sampler.stop()
-    ms_dev = float(step_ms.mean())
-    if dist is not None:
-        t = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev = float(t.item())
+    from sleqp_b200 import shard
+
+    ms_dev = shard.max_over_ranks(float(step_ms.mean()), dist, dev)
     value = world * 1e3 / ms_dev
 
     # ---- break-down and roofline of the dominant kernel (live, CUDA events) ----------------------------
@@ -329,11 +327,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(e2e_steps):
         host_step()
     torch.cuda.synchronize()
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
-    if dist is not None:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = shard.max_over_ranks(1e3 * (time.perf_counter() - t0) / e2e_steps, dist, dev)
     # factor / solve through the boundary, separately (absolute times the north-star asks for)
     t0 = time.perf_counter()
     fact.set_matrix(p.N, w["cp"], w["ri"], w["v"])
