@@ -86,6 +86,28 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic_per_launch(kernel, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of the same workload (profiles/, one sweep = one launch per tree level); None if
+    there is no capture for this workload."""
+    import csv
+
+    if "config2" not in workload:
+        return None
+    path = os.path.join(ROOT, "profiles", f"ncu_full_{kernel}_config2.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            tot += sum(float(r[i]) for r in rows[2:]) * scale[units[i]]
+        return tot / len(rows[2:])
+    except Exception:
+        return None
+
+
 def make_workload(cfg_idx, seed=0):
     from sleqp_b200 import problems
 
@@ -285,17 +307,17 @@ def run_ours(args, rank, world, local_rank):
     solve_ms = float(phases.sum())
     peaks, peak_src = load_peaks()
     n_solves = len(rhs)
-    share = {"numeric_factor(graph)": factor_ms, "k_fwd_level": phases[1] * n_solves, "k_bwd_level": phases[2] * n_solves,
+    share = {"numeric_factor(graph)": factor_ms, "k_fwd_chunk": phases[1] * n_solves, "k_bwd_chunk": phases[2] * n_solves,
              "k_pre+k_post": (phases[0] + phases[3]) * n_solves}
-    dom = max(("k_fwd_level", "k_bwd_level"), key=lambda x: share[x])
+    dom = max(("k_fwd_chunk", "k_bwd_chunk"), key=lambda x: share[x])
     nlev = st["n_levels"]
     # algorithmic bytes of one sweep: the factor once (exact nnz(L), 8 B), the row indices of
     # every supernode (4 B), the right-hand side in and out (8 B each), plus the pivots for the backward sweep
-    sweep_bytes = 8 * st["nnz_L"] + 4 * st["n_row_idx"] + 16 * st["n_reduced"] + (8 * st["n_reduced"] if dom == "k_bwd_level" else 0)
-    sweep_ms = float(phases[1] if dom == "k_fwd_level" else phases[2])
+    sweep_bytes = 8 * st["nnz_L"] + 4 * st["n_row_idx"] + 16 * st["n_reduced"] + (8 * st["n_reduced"] if dom == "k_bwd_chunk" else 0)
+    sweep_ms = float(phases[1] if dom == "k_fwd_chunk" else phases[2])
     achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": None, "peak_source": peak_src, "launches_per_sweep": nlev,
+                "traffic": ncu_traffic_per_launch(dom, p.name), "peak_source": peak_src, "launches_per_sweep": nlev,
                 "bytes_per_launch": sweep_bytes / nlev, "ms_per_launch": sweep_ms / nlev,
                 "step_share_ms": {k_: float(v_) for k_, v_ in share.items()}}
 
@@ -305,17 +327,19 @@ def run_ours(args, rank, world, local_rank):
     vh_idx = np.arange(p.m, dtype=np.int32)
     vh = w["rng"].standard_normal(p.m)
 
+    buf_n, buf_m = np.empty(p.n), np.empty(p.m)
+
     def host_step():
         fact.set_matrix(p.N, w["cp"], w["ri"], w["v"])
         out = None
         for i, (kind, idx, val, b, e) in enumerate(rhs):
             if i == 2:
-                mJ.mult_vec_trans(vh_idx, vh, 0.0)
+                mJ.mult_vec_trans(vh_idx, vh, 0.0, out=buf_n)
             if i >= 2:
-                mH.mult_vec(xh_idx, xh)
+                mH.mult_vec(xh_idx, xh, out=buf_n)
             fact.solve(idx, val, p.N)
             out = fact.solution(b, e, 1e-20)
-        mJ.mult_vec(xh_idx, xh)
+        mJ.mult_vec(xh_idx, xh, out=buf_m)
         return out
 
     h2d = 8 * len(w["v"]) + sum(8 * len(val) for _, _, val, _, _ in rhs) + 8 * p.m + 8 * p.n * (k + 1)
@@ -371,6 +395,88 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_batch(args, rank, world, local_rank):
+    """Config 5: `--batch B` independent instances (same pattern family, different seeds) sharded over the ranks
+    (instance i -> rank i mod world); on each GPU every instance has its own handle and CUDA stream, so the small
+    latency-bound systems overlap. One step = one EQP inner loop of every instance. Strong scaling in B."""
+    import torch
+
+    from sleqp_b200 import Fact, _lib, shard
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    mine = shard.assign_instances(args.batch, world, rank)
+    k = args.cg_iters
+    inst = []
+    for i in mine:
+        w = make_workload(args.config, seed=i)
+        p = w["p"]
+        f = Fact(device=local_rank)
+        f.set_matrix(p.N, w["cp"], w["ri"], w["v"])
+        rhs = step_rhs(w, k)
+        d_val = torch.from_numpy(w["v"]).to(dev)
+        d_rhs = []
+        for kind, idx, val, b, e in rhs[:4]:  # 4 distinct right-hand sides are cycled
+            full = np.zeros(p.N)
+            full[idx] = val
+            d_rhs.append(torch.from_numpy(full).to(dev))
+        inst.append(dict(f=f, d_val=d_val, d_rhs=d_rhs, d_sol=torch.empty(p.N, dtype=torch.float64, device=dev), p=p))
+    n_solves = 2 + k
+    torch.cuda.synchronize()
+
+    def step():
+        for it in inst:
+            it["f"].refactor_device(it["d_val"].data_ptr())
+        for s_ in range(n_solves):
+            for it in inst:
+                it["f"].solve_device(it["d_rhs"][s_ % 4].data_ptr(), it["d_sol"].data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    lib = _lib.lib()
+    l0 = lib.b200_launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    launches = lib.b200_launch_count() - l0
+    ms = shard.max_over_ranks(ms, dist, dev)
+    if rank == 0:
+        p0 = inst[0]["p"]
+        st = inst[0]["f"].stats()
+        print(json.dumps({
+            "metric": "sleqp_eqp_instance_iterations_per_s", "value": args.batch * 1e3 / ms, "unit": "instance-iter/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": p0.name + f"_x{args.batch}", "N": p0.N, "instances": args.batch, "instances_on_rank0": len(inst),
+                       "cg_iters": k, "solves_per_step": n_solves, "timing": "wall clock between device synchronisations (all streams)",
+                       "symbolic_cached": st["symbolic_cached"]},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }), flush=True)
+    for it in inst:
+        it["f"].release()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def cpu_baseline_sample(w, rhs, k):
     """Bounded CPU sample of the same step (oracle / reference code; never the thing shipped)."""
     from oracle import ref_lib
@@ -419,12 +525,15 @@ def main():
     ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (default 1: 2D Poisson control, n~2.5e5)")
     ap.add_argument("--cg-iters", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="config 5 mode: this many independent instances sharded over the ranks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.batch > 0:
+        run_batch(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

@@ -139,8 +139,11 @@ class Fact:
         """sleqp_fact_solution (fact.c:91-102): sparse slice, entries with |v| <= zero_eps dropped
         (sleqp_vec_set_from_raw, vec.c:72-104). Returns (indices, values)."""
         n = int(end - begin)
-        idx = np.empty(max(n, 1), dtype=np.int32)
-        val = np.empty(max(n, 1), dtype=np.float64)
+        if getattr(self, "_sol_cap", 0) < n:  # grown on demand and reused, like the caller-owned SleqpVec
+            self._sol_cap = max(n, 1)
+            self._sol_idx = np.empty(self._sol_cap, dtype=np.int32)
+            self._sol_val = np.empty(self._sol_cap, dtype=np.float64)
+        idx, val = self._sol_idx, self._sol_val
         nnz = C.c_int()
         check(lib().b200_fact_solution_sparse(self._h, int(begin), int(end), float(zero_eps), _pi(idx), _pd(val), C.byref(nnz)))
         return idx[: nnz.value], val[: nnz.value]
@@ -218,17 +221,17 @@ class Mat:
         check(lib().b200_mat_set(self._h, int(num_rows), int(num_cols), int(len(rows)), _pi(cols), _pi(rows), _pd(data)))
         self.num_rows, self.num_cols = int(num_rows), int(num_cols)
 
-    def mult_vec(self, idx, val) -> np.ndarray:
+    def mult_vec(self, idx, val, out=None) -> np.ndarray:
         """sleqp_mat_mult_vec (mat.c:282-310): dense result of length num_rows."""
         idx, val = _i32(idx), _f64(val)
-        out = np.empty(self.num_rows, dtype=np.float64)
+        out = np.empty(self.num_rows, dtype=np.float64) if out is None else out
         check(lib().b200_mat_mult_vec(self._h, int(len(idx)), _pi(idx), _pd(val), _pd(out)))
         return out
 
-    def mult_vec_trans(self, idx, val, eps=0.0):
+    def mult_vec_trans(self, idx, val, eps=0.0, out=None):
         """sleqp_mat_mult_vec_trans (mat.c:312-363): sparse result, |s| <= eps dropped."""
         idx, val = _i32(idx), _f64(val)
-        out = np.empty(self.num_cols, dtype=np.float64)
+        out = np.empty(self.num_cols, dtype=np.float64) if out is None else out
         check(lib().b200_mat_mult_vec_trans(self._h, int(len(idx)), _pi(idx), _pd(val), _pd(out)))
         keep = np.nonzero(np.abs(out) > eps)[0].astype(np.int32)
         return keep, out[keep]
