@@ -76,17 +76,15 @@ class Emulated:
         scratch = np.full(max(1, int(p["n_scratch_slots"]) if "n_scratch_slots" in p else 1) * NB * NB, np.nan)
         has_children = np.diff(p["child_ptr"]) > 0
         for st in p["stages"]:
-            zb, ze, eb, ee, pb, pe, ub, ue = (int(x) for x in st)
+            zb, ze, eb, ee, db, de, pb, pe, ub, ue = (int(x) for x in st)
             for T in p["zero_sn"][zb:ze]:
                 self.umat(T)[:, :] = 0.0
             for c, jb in p["ea_tasks"][eb:ee]:
                 self._extend_add(int(c), int(jb))
-            # scratch slots needed this stage
-            slots = [int(t[3]) for t in p["pan_tasks"][pb:pe] if t[3] >= 0]
-            if slots and (max(slots) + 1) * NB * NB > len(scratch):
-                scratch = np.full((max(slots) + 1) * NB * NB, np.nan)
-            for T, t, rb, slot in p["pan_tasks"][pb:pe]:
-                self._panel(int(T), int(t), int(rb), int(slot), scratch)
+            for T, t in p["diag_tasks"][db:de]:
+                self._panel(int(T), int(t), 0, -1, scratch, diag_only=True)
+            for T, t, rb, _pad in p["pan_tasks"][pb:pe]:
+                self._panel(int(T), int(t), int(rb), -1, scratch, trsm_only=True)
             for T, t, kind, i0, j0 in p["upd_tasks"][ub:ue]:
                 self._update(int(T), int(t), int(kind), int(i0), int(j0), scratch, bool(has_children[T]))
 
@@ -204,21 +202,26 @@ class Emulated:
                 A[c:, c] -= A[c:, j] * dj * A[c, j]
         return A, d, nper
 
-    def _panel(self, T, t, rb, slot, scratch):
+    def _panel(self, T, t, rb, slot, scratch, diag_only=False, trsm_only=False):
         f, k, r, h = self._geom(T)
         P = self.panel(T)
         c0 = t * NB
         w = min(NB, k - c0)
-        L11, d, nper = self._factor_diag(P[c0 : c0 + w, c0 : c0 + w])
+        if trsm_only:
+            # k_trsm reads the factored block published by k_diag
+            L11 = np.tril(P[c0 : c0 + w, c0 : c0 + w], -1) + np.eye(w)
+            d, nper = self.D[f + c0 : f + c0 + w].copy(), 0
+        else:
+            L11, d, nper = self._factor_diag(P[c0 : c0 + w, c0 : c0 + w])
         r0 = c0 + w + rb * RB
         r1 = min(h, r0 + RB)
-        if r1 > r0:
+        if r1 > r0 and not diag_only:
             X = P[r0:r1, c0 : c0 + w].copy()
             # solve X_new * D * L11^T = X
             for j in range(w):
                 X[:, j] = (X[:, j] - (X[:, :j] * d[:j]) @ L11[j, :j]) / d[j]
             P[r0:r1, c0 : c0 + w] = X
-        if rb == 0:
+        if rb == 0 and not trsm_only:
             self.n_perturbed += nper
             self.D[f + c0 : f + c0 + w] = d
             if slot < 0:

@@ -155,12 +155,14 @@ struct DevPlan
   // tasks
   DevBuf<int> zero_sn;
   DevBuf<EaTask> ea_tasks;
+  DevBuf<DiagTask> diag_tasks;
   DevBuf<PanelTask> pan_tasks;
   DevBuf<Task5> upd_tasks;
   DevBuf<int> lvl_sn;
   DevBuf<InvTask> inv_tasks;
   DevBuf<TrTask> tr_tasks;
   DevBuf<FwdTask> fwd_tasks;
+  DevBuf<int> fwd_ptr, bwd_ptr; // per-level task offsets (for the fused top-of-tree kernels)
   DevBuf<BwdTask> bwd_tasks;
   // E-part / residual operators
   DevBuf<int> k_of_e, k_of_r, pinv, perm, dE_src;

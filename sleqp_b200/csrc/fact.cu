@@ -47,7 +47,7 @@ struct b200_fact
   DevBuf<double> val, L, Mt, Mr, tmp, U, D, scratch, scal, dE, Acsc_val, Acsr_val, Gsym_val;
   DevBuf<int> nper;
   // solve
-  DevBuf<double> rhs, z, res, dz, bR, y, x, W;
+  DevBuf<double> rhs, z, res, dz, bR, y, yf, x, W;
   DevBuf<int> rhs_idx;
   DevBuf<double> rhs_val;
   PinnedBuf<int> h_rhs_idx;
@@ -94,6 +94,7 @@ struct b200_fact
     sb.dz  = dz.p;
     sb.bR  = bR.p;
     sb.y   = y.p;
+    sb.yf  = yf.p;
     sb.x   = x.p;
     sb.W   = W.p;
     return sb;
@@ -181,8 +182,6 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   dp.Ridx.upload(P.Ridx, s);
   dp.rel.upload(P.rel, s);
   dp.child_idx.upload(P.child_idx, s);
-  dp.cptr.upload(P.cptr, s);
-  dp.cidx.upload(P.cidx, s);
   static_assert(sizeof(long long) == sizeof(i64), "i64");
   auto up64 = [&](DevBuf<long long>& b, const std::vector<i64>& v) {
     b.reserve(v.size());
@@ -200,12 +199,15 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   dp.Sterm_d.upload(P.Sterm_d, s);
   dp.zero_sn.upload(P.zero_sn, s);
   dp.ea_tasks.upload(P.ea_tasks, s);
+  dp.diag_tasks.upload(P.diag_tasks, s);
   dp.pan_tasks.upload(P.pan_tasks, s);
   dp.upd_tasks.upload(P.upd_tasks, s);
   dp.lvl_sn.upload(P.lvl_sn, s);
   dp.inv_tasks.upload(P.inv_tasks, s);
   dp.tr_tasks.upload(P.tr_tasks, s);
   dp.fwd_tasks.upload(P.fwd_tasks, s);
+  dp.fwd_ptr.upload(P.fwd_ptr, s);
+  dp.bwd_ptr.upload(P.bwd_ptr, s);
   dp.bwd_tasks.upload(P.bwd_tasks, s);
   dp.k_of_e.upload(P.k_of_e, s);
   dp.k_of_r.upload(P.k_of_r, s);
@@ -245,8 +247,8 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   F->dz.reserve(N + 8);
   F->bR.reserve(m + 8);
   F->y.reserve(m + 8);
+  F->yf.reserve(m + 8);
   F->x.reserve(m + 8);
-  F->W.reserve((size_t)P.Wptr[P.nsuper] + 8);
   F->h_sol.reserve(N + 8);
   F->h_scal.reserve(8);
   F->h_nper.reserve(2);

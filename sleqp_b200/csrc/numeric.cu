@@ -6,8 +6,8 @@
 // (fact_cholmod.c:137). Kernels (all FP64):
 //   k_assemble      one thread per entry of tril(S): gathers its product terms      (HBM-bound)
 //   k_extend_add    child update matrix -> parent front (relative indices)         (HBM-bound)
-//   k_panel         NB-wide panel step: dense LDL^T of the diagonal block in shared memory,
-//                   one thread per row solves its row of L21; also inverts the block   (latency/HBM)
+//   k_diag/k_trsm   NB-wide panel step: LDL^T + inverse of the diagonal block in shared memory, then
+//                   L21 = F21 L11^-T D^-1 as a DMMA product with the inverted block       (latency/HBM)
 //   k_update        64x64 output tiles of C -= L_i D L_j^T on the FP64 tensor cores
 //                   (mma.sync m8n8k4.f64 = DMMA), operands staged through shared memory
 //                   (tcgen05 has no f64 kind, so DMMA is the FP64 tensor path on sm_100a)
@@ -153,42 +153,136 @@ dmma(double& c0, double& c1, double a, double b)
 }
 
 // ---------------------------------------------------------------------------------------------
-// One panel step of supernode T: columns [c0, c0+w) of the front, w <= NB.
-//   1. warp 0 factors the w x w diagonal block (LDL^T, static pivoting) in shared memory: lane i owns row i;
-//   2. warp 1 inverts the unit lower factor column by column (lane c owns column c);
-//   3. every warp applies  L21 = F21 * L11^-T D^-1  to its 32 rows as a DMMA product with the inverted
-//      block -- the triangular solve becomes a 32x32x32 tensor-core GEMM with operands straight from
-//      global memory (A fragments) and shared memory (B fragments).
-// Every CTA of a step (one per RB rows) repeats 1-2 redundantly (identical arithmetic, identical results), so
-// there is no inter-CTA dependency; row block 0 publishes the factored block, the pivots and the inverse.
-// With more than one row block the factored block goes to a scratch slot (the other CTAs still read the
-// unfactored one) and k_update copies it back. Loops are kept rolled on purpose: a fully unrolled version was
-// instruction-fetch bound (ncu: stall_no_instruction ~7 cycles/issue, 42 us per CTA).
-constexpr int LDP = 36; // leading dimension of the B-fragment operand: (4 k + n) mod 16 is conflict-free
+// Panel step t of supernode T, columns [c0, c0+w) of the front (w <= NB), in two kernels:
+//
+// k_diag  (one CTA of 256 threads per step): right-looking LDL^T of the w x w diagonal block with static
+//   pivoting and, in the same sweep, the inverse of its unit lower factor (the elimination steps applied
+//   to the identity). Thread (lane = row i, warp = column class c mod 8) owns 4 entries of the 32 x 32
+//   work per pivot; one barrier per pivot; shared-memory read-modify-writes are batched (all loads, then
+//   all stores). Column j stays unscaled (f_ij) inside the loop: l_ij d_j l_cj = f_ij f_cj / d_j.
+//   Publishes L11 (in place), the pivots and L11^-1 (into the inverse panel).
+// k_trsm  (one CTA of 128 threads per RB rows): L21 = F21 * L11^-T D^-1 as a 32x32x32 DMMA product per
+//   warp with the inverted block: A fragments straight from global memory, B fragments
+//   Wm[k][n] = L11^-1[n][k] / d_n from shared memory. The triangular solve is a tensor-core GEMM.
+//
+// History (ncu, profiles/): a single fused kernel with the factorization unrolled on one warp was
+// instruction-fetch bound (42 us per CTA), a 128-thread rolled version issue-bound (~200 SASS instructions
+// per pivot on one warp per scheduler, 27 us); this split is ~3x faster per stage.
+constexpr int LDP      = 36; // leading dimension of the B-fragment operand: (4 k + n) mod 16 is conflict-free
+constexpr int DIAG_THR = 256;
+
+__global__ void __launch_bounds__(DIAG_THR)
+k_diag(const DiagTask* __restrict__ tasks,
+       const SnMeta* __restrict__ sn,
+       double* __restrict__ L,
+       double* __restrict__ Mt,
+       double* __restrict__ D,
+       const double* __restrict__ scal,
+       int* __restrict__ n_perturbed)
+{
+  __shared__ double A[NB][NB + 1];    // becomes the unit lower factor (strict lower part)
+  __shared__ double Ainv[NB][NB + 1]; // becomes its inverse
+  __shared__ double dsh[NB], dinv[NB];
+  const DiagTask t = tasks[blockIdx.x];
+  const SnMeta s   = sn[t.sn];
+  const int h      = s.k + s.r;
+  const int c0     = t.t * NB;
+  const int w      = min(NB, s.k - c0);
+  double* P        = L + s.Lptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWD = DIAG_THR / 32, EPT = NB / NWD; // entries per thread and pivot
+
+#pragma unroll
+  for (int u = 0; u < EPT; ++u)
+  {
+    const int c    = warp + NWD * u;
+    A[lane][c]     = (lane < w && c <= lane) ? P[(long long)(c0 + c) * h + c0 + lane] : 0.0;
+    Ainv[lane][c]  = lane == c ? 1.0 : 0.0;
+  }
+  const double tau = scal[1];
+  int nper         = 0;
+  __syncthreads();
+  for (int j = 0; j < w; ++j)
+  {
+    double dj = A[j][j];
+    if (!(fabs(dj) >= tau) || !isfinite(dj))
+    {
+      dj = tau > 0.0 ? -tau : -1e-300;
+      ++nper;
+    }
+    const double rdj = 1.0 / dj;
+    if (tid == 0)
+    {
+      dsh[j]  = dj;
+      dinv[j] = rdj;
+    }
+    if (lane > j && lane < w)
+    {
+      const double lij = A[lane][j] * rdj;
+      double cur[EPT], oth[EPT];
+#pragma unroll
+      for (int u = 0; u < EPT; ++u)
+      {
+        const int c = warp + NWD * u;
+        cur[u]      = c > j ? A[lane][c] : Ainv[lane][c];
+        oth[u]      = c > j ? A[c][j] : Ainv[j][c];
+      }
+#pragma unroll
+      for (int u = 0; u < EPT; ++u)
+      {
+        const int c = warp + NWD * u;
+        if (c > j)
+        {
+          if (c <= lane)
+          {
+            A[lane][c] = cur[u] - lij * oth[u];
+          }
+        }
+        else
+        {
+          Ainv[lane][c] = cur[u] - lij * oth[u];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && nper)
+  {
+    atomicAdd(n_perturbed, nper);
+  }
+  if (tid < w)
+  {
+    D[s.first + c0 + tid] = dsh[tid];
+  }
+  double* M = Mt + s.Lptr;
+#pragma unroll
+  for (int u = 0; u < EPT; ++u)
+  {
+    const int c = warp + NWD * u;
+    if (lane < w && c <= lane)
+    {
+      P[(long long)(c0 + c) * h + c0 + lane] = lane == c ? 1.0 : A[lane][c] * dinv[c];
+      M[(long long)(c0 + c) * h + c0 + lane] = Ainv[lane][c];
+    }
+  }
+}
 
 __global__ void __launch_bounds__(RB)
-k_panel(const PanelTask* __restrict__ tasks,
-        const SnMeta* __restrict__ sn,
-        double* __restrict__ L,
-        double* __restrict__ Mt,
-        double* __restrict__ D,
-        double* __restrict__ scratch,
-        const double* __restrict__ scal,
-        int* __restrict__ n_perturbed)
+k_trsm(const PanelTask* __restrict__ tasks,
+       const SnMeta* __restrict__ sn,
+       double* __restrict__ L,
+       const double* __restrict__ Mt,
+       const double* __restrict__ D)
 {
-  __shared__ double A[NB][NB + 1];    // unit lower factor of the diagonal block (strict lower part)
-  __shared__ double Ainv[NB][NB + 1]; // its inverse
-  __shared__ double Wm[NB][LDP];      // Wm[k][n] = Ainv[n][k] / d_n
-  __shared__ double dsh[NB], dinv[NB];
+  __shared__ double Wm[NB][LDP]; // Wm[k][n] = L11^-1[n][k] / d_n
   const PanelTask t = tasks[blockIdx.x];
   const SnMeta s    = sn[t.sn];
   const int h       = s.k + s.r;
   const int c0      = t.t * NB;
   const int w       = min(NB, s.k - c0);
   double* P         = L + s.Lptr;
+  const double* M   = Mt + s.Lptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  // A fragments of this warp's 32 rows: issued first, they do not depend on the factorization
   const int r0 = c0 + w + t.rb * RB + warp * 32;
   double af[4][8];
   if (r0 < h)
@@ -204,153 +298,53 @@ k_panel(const PanelTask* __restrict__ tasks,
   }
   for (int idx = tid; idx < NB * NB; idx += RB)
   {
-    const int i = idx % NB, j = idx / NB;
-    A[i][j]    = (i < w && j <= i) ? P[(long long)(c0 + j) * h + c0 + i] : 0.0;
-    Ainv[i][j] = i == j ? 1.0 : 0.0;
+    const int n = idx % NB, kk = idx / NB; // consecutive threads -> consecutive rows n of column kk
+    Wm[kk][n]   = (n < w && kk <= n) ? M[(long long)(c0 + kk) * h + c0 + n] / D[s.first + c0 + n] : 0.0;
   }
   __syncthreads();
+  if (r0 >= h)
   {
-    // Right-looking LDL^T and, in the same sweep, the inverse of the unit lower factor (the elimination
-    // steps applied to the identity). Thread (lane = row i, warp = column class c mod 4) owns 8 entries
-    // of the 32 x 32 work per step; one barrier per step. Column j is left unscaled (f_ij) during the
-    // loop: l_ij d_j l_cj = f_ij f_cj / d_j.
-    const double tau = scal[1];
-    int nper         = 0;
-    for (int j = 0; j < w; ++j)
-    {
-      double dj = A[j][j];
-      if (!(fabs(dj) >= tau) || !isfinite(dj))
-      {
-        dj = tau > 0.0 ? -tau : -1e-300;
-        ++nper;
-      }
-      const double rdj = 1.0 / dj;
-      if (tid == 0)
-      {
-        dsh[j]  = dj;
-        dinv[j] = rdj;
-      }
-      if (lane > j && lane < w)
-      {
-        const double lij = A[lane][j] * rdj;
-        // all loads, then all stores: shared-memory read-modify-writes would otherwise serialise
-        double cur[NB / 4], oth[NB / 4];
+    return;
+  }
+  double acc[4][4][2];
 #pragma unroll
-        for (int u = 0; u < NB / 4; ++u)
-        {
-          const int c = warp + 4 * u;
-          cur[u]      = c > j ? A[lane][c] : Ainv[lane][c];
-          oth[u]      = c > j ? A[c][j] : Ainv[j][c];
-        }
+  for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int u = 0; u < NB / 4; ++u)
-        {
-          const int c = warp + 4 * u;
-          if (c > j)
-          {
-            if (c <= lane)
-            {
-              A[lane][c] = cur[u] - lij * oth[u];
-            }
-          }
-          else
-          {
-            Ainv[lane][c] = cur[u] - lij * oth[u];
-          }
-        }
-      }
-      __syncthreads();
-    }
-    if (t.rb == 0 && tid == 0 && nper)
+    for (int nj = 0; nj < 4; ++nj)
     {
-      atomicAdd(n_perturbed, nper);
+      acc[mi][nj][0] = 0.0;
+      acc[mi][nj][1] = 0.0;
     }
-    // scale the columns: l_ij = f_ij / d_j, unit diagonal
-    for (int idx = tid; idx < NB * NB; idx += RB)
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4)
+  {
+    double bf[4];
+#pragma unroll
+    for (int nj = 0; nj < 4; ++nj)
     {
-      const int i = idx % NB, j = idx / NB;
-      if (j < w)
-      {
-        A[i][j] = i == j ? 1.0 : (i > j ? A[i][j] * dinv[j] : 0.0);
-      }
+      bf[nj] = Wm[k4 * 4 + (lane & 3)][nj * 8 + (lane >> 2)];
     }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < NB * NB; idx += RB)
-  {
-    const int kk = idx / NB, n = idx % NB;
-    Wm[kk][n] = (n < w && kk <= n) ? Ainv[n][kk] * dinv[n] : 0.0;
-  }
-  __syncthreads();
-
-  if (r0 < h)
-  {
-    double acc[4][4][2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
       for (int nj = 0; nj < 4; ++nj)
       {
-        acc[mi][nj][0] = 0.0;
-        acc[mi][nj][1] = 0.0;
+        dmma(acc[mi][nj][0], acc[mi][nj][1], af[mi][k4], bf[nj]);
       }
-#pragma unroll
-    for (int k4 = 0; k4 < 8; ++k4)
-    {
-      double bf[4];
-#pragma unroll
-      for (int nj = 0; nj < 4; ++nj)
-      {
-        bf[nj] = Wm[k4 * 4 + (lane & 3)][nj * 8 + (lane >> 2)];
-      }
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int nj = 0; nj < 4; ++nj)
-        {
-          dmma(acc[mi][nj][0], acc[mi][nj][1], af[mi][k4], bf[nj]);
-        }
-    }
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-      for (int nj = 0; nj < 4; ++nj)
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-        {
-          const int row = r0 + mi * 8 + (lane >> 2), col = nj * 8 + 2 * (lane & 3) + e;
-          if (row < h && col < w)
-          {
-            P[(long long)(c0 + col) * h + row] = acc[mi][nj][e];
-          }
-        }
   }
-
-  if (t.rb == 0)
-  {
-    if (tid < w)
-    {
-      D[s.first + c0 + tid] = dsh[tid];
-    }
-    double* M  = Mt + s.Lptr;
-    double* sc = scratch + (long long)max(t.slot, 0) * NB * NB;
-    for (int idx = tid; idx < w * w; idx += RB)
-    {
-      const int i = idx % w, j = idx / w;
-      if (i >= j)
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int nj = 0; nj < 4; ++nj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
       {
-        M[(long long)(c0 + j) * h + c0 + i] = Ainv[i][j];
-        if (t.slot < 0)
+        const int row = r0 + mi * 8 + (lane >> 2), col = nj * 8 + 2 * (lane & 3) + e;
+        if (row < h && col < w)
         {
-          P[(long long)(c0 + j) * h + c0 + i] = A[i][j];
+          P[(long long)(c0 + col) * h + row] = acc[mi][nj][e];
         }
       }
-      if (t.slot >= 0)
-      {
-        sc[idx] = A[i][j];
-      }
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -519,19 +513,6 @@ k_update(const Task5* __restrict__ tasks,
   double* P      = L + s.Lptr;
   const int c0   = t.t * NB;
   const int w    = min(NB, s.k - c0);
-  if (t.kind == UPD_DIAGCOPY)
-  {
-    const double* sc = scratch + (long long)t.i0 * NB * NB;
-    for (int idx = threadIdx.x; idx < w * w; idx += 128)
-    {
-      const int i = idx % w, j = idx / w;
-      if (i >= j)
-      {
-        P[(long long)(c0 + j) * h + c0 + i] = sc[idx];
-      }
-    }
-    return;
-  }
   if (t.kind == UPD_INPANEL)
   {
     // front rows [i0, i0+64) x front columns [j0, j0+64), columns < k, rows < h
@@ -726,9 +707,14 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
       k_extend_add<<<(unsigned)(st.ea_end - st.ea_begin), 32 * EA_COLS, 0, stream>>>(dp.ea_tasks.p + st.ea_begin, dp.sn.p, dp.rel.p, nb.L, nb.U);
       lc.tick("extend_add");
     }
+    if (st.diag_end > st.diag_begin)
+    {
+      k_diag<<<(unsigned)(st.diag_end - st.diag_begin), DIAG_THR, 0, stream>>>(dp.diag_tasks.p + st.diag_begin, dp.sn.p, nb.L, nb.Mt, nb.D, nb.scal, nb.n_perturbed);
+      lc.tick("panel");
+    }
     if (st.pan_end > st.pan_begin)
     {
-      k_panel<<<(unsigned)(st.pan_end - st.pan_begin), RB, 0, stream>>>(dp.pan_tasks.p + st.pan_begin, dp.sn.p, nb.L, nb.Mt, nb.D, nb.scratch, nb.scal, nb.n_perturbed);
+      k_trsm<<<(unsigned)(st.pan_end - st.pan_begin), RB, 0, stream>>>(dp.pan_tasks.p + st.pan_begin, dp.sn.p, nb.L, nb.Mt, nb.D);
       lc.tick("panel");
     }
     if (st.upd_end > st.upd_begin)

@@ -31,7 +31,8 @@ struct SolveBuffers
   double* res;  // N, residual / correction right-hand side
   double* dz;   // N, correction
   double* bR;   // m, reduced right-hand side (new labels)
-  double* y;    // m, forward result (new labels)
+  double* y;    // m, right-hand side of the reduced system, accumulates the updates of the forward sweep
+  double* yf;   // m, forward result (new labels)
   double* x;    // m, solution of the reduced system (new labels)
   double* W;    // front vectors (sum of front heights)
 };

@@ -29,7 +29,7 @@ enum
 {
   UPD_INPANEL  = 0, // trailing update inside the supernode's own panel
   UPD_SCHUR    = 1, // U -= L21 D L21^T over the whole supernode width (last step only)
-  UPD_DIAGCOPY = 2  // copy the factored diagonal block back from scratch
+  UPD_DIAGCOPY = 2  // (unused since the diagonal block has its own kernel)
 };
 
 struct Task5
@@ -37,9 +37,14 @@ struct Task5
   int sn, t, kind, i0, j0;
 };
 
+struct DiagTask
+{
+  int sn, t; // factor + invert the NB x NB diagonal block of panel step t
+};
+
 struct PanelTask
 {
-  int sn, t, rb, slot; // slot < 0: single row block, factor the diagonal block in place
+  int sn, t, rb, pad; // RB rows of L21 below the diagonal block
 };
 
 struct EaTask
@@ -74,7 +79,7 @@ struct TrTask
 struct FwdTask
 {
   int sn, row0, nrows, first, k, pad;
-  long long Lptr, Wptr;
+  long long Lptr, Rptr;
 };
 
 struct BwdTask
@@ -87,6 +92,7 @@ struct Stage
 {
   int zero_begin, zero_end;
   int ea_begin, ea_end;
+  int diag_begin, diag_end;
   int pan_begin, pan_end;
   int upd_begin, upd_end;
 };
@@ -138,6 +144,7 @@ struct Plan
   std::vector<Stage> stages;
   std::vector<int> zero_sn;
   std::vector<EaTask> ea_tasks;
+  std::vector<DiagTask> diag_tasks;
   std::vector<PanelTask> pan_tasks;
   std::vector<Task5> upd_tasks;
   int n_scratch_slots = 0;

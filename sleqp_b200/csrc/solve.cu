@@ -3,10 +3,16 @@
 //
 //   K = [D A^T; A G]:  t = b_E / d,  b_R' = b_R - A t,  S y = b_R',  z_R = y,  z_E = (b_E - A^T y) / d
 // The reduced system is solved with level-scheduled supernodal forward / diagonal / backward
-// sweeps over the multifrontal front vectors (children are pulled by their parent, one CTA per
-// supernode, so the summation order is fixed and the solve is deterministic).
+// sweeps over the inverse panels (selective inversion): every supernode step is a matrix-vector product.
 // Iterative refinement runs against the unperturbed K (SURVEY.md hard part 1).
 #include "numeric.cuh"
+
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace cg = cooperative_groups;
 
 namespace b200
 {
@@ -147,29 +153,21 @@ k_axpy1(int n, const double* __restrict__ x, double* __restrict__ y)
 
 // ---- forward sweep ---------------------------------------------------------------------------------
 // One CTA per (supernode, row chunk). With the inverse panel Minv = [L11^-1; -L21 L11^-1] the whole
-// supernode step is one matrix-vector product  [y_T; dW_tail] = Minv * b_T,  b_T = b[cols] + the
-// children's tail contributions that land on T's columns (contributor lists, fixed order: the sum is
-// deterministic). Every CTA of a supernode rebuilds b_T itself, so nothing depends on anything inside a
-// level. Tail rows also receive the children's pass-through contributions.
+// supernode step is one matrix-vector product  [y_T; delta_tail] = Minv * b_T. The right-hand side lives in
+// one global accumulator `yacc`: b_T = yacc[cols of T] already holds every update from T's descendants
+// (they ran in earlier launches); tail results are pushed straight to their final rows with native FP64
+// atomics (yacc[row] += delta), so there is no per-supernode front vector, no pass-through copying and the
+// dependent-load chain of a CTA is task -> yacc -> panel. Rows of the top block go to `yf`.
 // Reads the row-major copy Mr of the inverse panel: a warp owns RG rows at a time, lanes stride the
 // (contiguous) columns with 8 independent loads in flight; the first round of panel loads is issued
-// before b_T is assembled (it does not depend on it). Dynamic shared memory: bT[k].
+// before b_T is staged. Dynamic shared memory: bT[k].
 template <int RG>
 __device__ __forceinline__ void
-fwd_body(const FwdTask& t,
-         const int* __restrict__ cptr,
-         const int* __restrict__ cidx,
-         const double* __restrict__ Mr,
-         const double* __restrict__ b,
-         double* __restrict__ y,
-         double* __restrict__ W,
-         double* bT)
+fwd_body(const FwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mr, double* __restrict__ yacc, double* __restrict__ yf, double* bT)
 {
-  constexpr int U  = 8 / RG;
-  constexpr int NW = SOLVE_THREADS / 32;
-  const int k      = t.k;
-  const double* P  = Mr + t.Lptr;
-  const int* cp    = cptr + t.Wptr;
+  constexpr int U = 8 / RG;
+  const int k     = t.k;
+  const double* P = Mr + t.Lptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g0     = warp * RG;
   const int nvalid = min(RG, t.nrows - g0); // <= 0: this warp has no rows
@@ -188,20 +186,14 @@ fwd_body(const FwdTask& t,
       const int j = lane + 32 * u;
       pre[a][u]   = (a < nvalid && j < jend) ? P[(long long)(r0 + a) * k + j] : 0.0;
     }
-
   for (int j = tid; j < k; j += SOLVE_THREADS)
   {
-    double acc = b[t.first + j];
-    for (int e = cp[j]; e < cp[j + 1]; ++e)
-    {
-      acc += W[cidx[e]];
-    }
-    bT[j] = acc;
+    bT[j] = yacc[t.first + j];
   }
   __syncthreads();
   if (nvalid <= 0)
   {
-    return;
+    return; // no barrier follows inside this body
   }
   double acc[RG][U];
 #pragma unroll
@@ -265,27 +257,17 @@ fwd_body(const FwdTask& t,
     const int r = r0 + lane;
     if (r < k)
     {
-      y[t.first + r] = mine;
+      yf[t.first + r] = mine;
     }
     else
     {
-      for (int e = cp[r]; e < cp[r + 1]; ++e) // pass-through from the children
-      {
-        mine += W[cidx[e]];
-      }
-      W[t.Wptr + r] = mine;
+      atomicAdd(yacc + Ridx[t.Rptr + r - k], mine);
     }
   }
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS)
-k_fwd_chunk(const FwdTask* __restrict__ tasks,
-            const int* __restrict__ cptr,
-            const int* __restrict__ cidx,
-            const double* __restrict__ Mr,
-            const double* __restrict__ b,
-            double* __restrict__ y,
-            double* __restrict__ W)
+k_fwd_chunk(const FwdTask* __restrict__ tasks, const int* __restrict__ Ridx, const double* __restrict__ Mr, double* __restrict__ yacc, double* __restrict__ yf)
 {
   extern __shared__ double bT[];
   const FwdTask t  = tasks[blockIdx.x];
@@ -293,15 +275,15 @@ k_fwd_chunk(const FwdTask* __restrict__ tasks,
   const int rg     = (t.nrows + NW - 1) / NW; // rows per warp: 1..4
   if (rg == 1)
   {
-    fwd_body<1>(t, cptr, cidx, Mr, b, y, W, bT);
+    fwd_body<1>(t, Ridx, Mr, yacc, yf, bT);
   }
   else if (rg == 2)
   {
-    fwd_body<2>(t, cptr, cidx, Mr, b, y, W, bT);
+    fwd_body<2>(t, Ridx, Mr, yacc, yf, bT);
   }
   else
   {
-    fwd_body<4>(t, cptr, cidx, Mr, b, y, W, bT);
+    fwd_body<4>(t, Ridx, Mr, yacc, yf, bT);
   }
 }
 
@@ -436,6 +418,92 @@ k_bwd_chunk(const BwdTask* __restrict__ tasks,
   }
 }
 
+// ---- fused top of the tree ---------------------------------------------------------------------------
+// The upper levels of the supernodal tree have few chunks each (tens to a few hundred CTAs) and cost a full
+// kernel launch + drain (~13 us) per level. These cooperative kernels walk all of them in one launch with a
+// grid barrier between levels; every CTA strides over the level's tasks.
+__device__ __forceinline__ void
+fwd_dispatch(const FwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mr, double* __restrict__ yacc, double* __restrict__ yf, double* bT)
+{
+  constexpr int NW = SOLVE_THREADS / 32;
+  const int rg     = (t.nrows + NW - 1) / NW;
+  if (rg == 1)
+  {
+    fwd_body<1>(t, Ridx, Mr, yacc, yf, bT);
+  }
+  else if (rg == 2)
+  {
+    fwd_body<2>(t, Ridx, Mr, yacc, yf, bT);
+  }
+  else
+  {
+    fwd_body<4>(t, Ridx, Mr, yacc, yf, bT);
+  }
+}
+
+__device__ __forceinline__ void
+bwd_dispatch(const BwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ D, const double* __restrict__ y, double* __restrict__ x, double* v)
+{
+  constexpr int NW = SOLVE_THREADS / 32;
+  const int cg_    = (t.ncols + NW - 1) / NW;
+  if (cg_ == 1)
+  {
+    bwd_body<1>(t, Ridx, Mt, D, y, x, v);
+  }
+  else if (cg_ == 2)
+  {
+    bwd_body<2>(t, Ridx, Mt, D, y, x, v);
+  }
+  else
+  {
+    bwd_body<4>(t, Ridx, Mt, D, y, x, v);
+  }
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_fwd_top(const FwdTask* __restrict__ tasks, const int* __restrict__ lvl_ptr, int l0, int l1, const int* __restrict__ Ridx, const double* __restrict__ Mr, double* __restrict__ yacc, double* __restrict__ yf)
+{
+  extern __shared__ double smem_top[];
+  cg::grid_group grid = cg::this_grid();
+  for (int l = l0; l < l1; ++l)
+  {
+    for (int q = lvl_ptr[l] + blockIdx.x; q < lvl_ptr[l + 1]; q += gridDim.x)
+    {
+      const FwdTask t = tasks[q];
+      fwd_dispatch(t, Ridx, Mr, yacc, yf, smem_top);
+      __syncthreads(); // the staging buffer is reused by the next task
+    }
+    grid.sync();
+  }
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS)
+k_bwd_top(const BwdTask* __restrict__ tasks, const int* __restrict__ lvl_ptr, int l0, int l1, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ D, const double* __restrict__ y, double* __restrict__ x)
+{
+  extern __shared__ double smem_top[];
+  cg::grid_group grid = cg::this_grid();
+  for (int l = l1 - 1; l >= l0; --l)
+  {
+    for (int q = lvl_ptr[l] + blockIdx.x; q < lvl_ptr[l + 1]; q += gridDim.x)
+    {
+      const BwdTask t = tasks[q];
+      bwd_dispatch(t, Ridx, Mt, D, y, x, smem_top);
+      __syncthreads();
+    }
+    grid.sync();
+  }
+}
+
+__global__ void
+k_coop_probe(int* out)
+{
+  cg::this_grid().sync();
+  if (out && blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    *out = 1;
+  }
+}
+
 // ---- small utilities -----------------------------------------------------------------------------------
 __global__ void
 k_scatter(int nnz, const int* __restrict__ idx, int first, const double* __restrict__ val, double* __restrict__ out)
@@ -517,6 +585,129 @@ nblocks(long long n, int threads)
 
 constexpr size_t SOLVE_SMEM_LIMIT = 160 * 1024;
 
+// ---- which levels go into the fused cooperative kernels ----------------------------------------------------
+namespace
+{
+struct TopFusion
+{
+  int split;    // levels [split, nlevels) are fused; split == nlevels disables the fusion
+  int grid_fwd; // cooperative grid sizes
+  int grid_bwd;
+  size_t smem;
+};
+
+int g_coop_ok   = -1; // -1 unknown, 0 unusable, 1 usable (process-wide)
+int g_coop_ctas = 0;  // co-resident CTAs of the fused kernels with the worst-case shared memory
+
+// Cooperative launches must be capturable into a CUDA graph and the device must support them; probed once,
+// outside of any capture (configure_solve_kernels).
+void
+probe_cooperative()
+{
+  if (g_coop_ok >= 0)
+  {
+    return;
+  }
+  g_coop_ok = 0;
+  if (const char* e = std::getenv("B200_NO_TOP_FUSION"))
+  {
+    if (*e && *e != '0')
+    {
+      return;
+    }
+  }
+  int dev = 0, coop = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop)
+  {
+    cudaGetLastError();
+    return;
+  }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaStream_t s = nullptr;
+  cudaGraph_t g  = nullptr;
+  cudaGraphExec_t ge = nullptr;
+  bool ok = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
+  if (ok)
+  {
+    int* out     = nullptr;
+    void* args[] = {&out};
+    ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok)
+    {
+      const bool launched = cudaLaunchCooperativeKernel((void*)k_coop_probe, dim3(2), dim3(32), args, 0, s) == cudaSuccess;
+      const bool ended    = cudaStreamEndCapture(s, &g) == cudaSuccess;
+      ok                  = launched && ended && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess;
+      if (ok)
+      {
+        ok = cudaGraphLaunch(ge, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess;
+      }
+    }
+  }
+  if (ge)
+  {
+    cudaGraphExecDestroy(ge);
+  }
+  if (g)
+  {
+    cudaGraphDestroy(g);
+  }
+  if (s)
+  {
+    cudaStreamDestroy(s);
+  }
+  cudaGetLastError();
+  if (!ok)
+  {
+    return;
+  }
+  // worst-case shared memory of the fused kernels: 32 KB (fronts up to 4096 rows); larger levels stay unfused
+  int per_sm_f = 0, per_sm_b = 0;
+  const size_t smem = 32 * 1024;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, k_fwd_top, SOLVE_THREADS, smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_bwd_top, SOLVE_THREADS, smem) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return;
+  }
+  g_coop_ctas = sms * std::max(1, std::min(std::min(per_sm_f, per_sm_b), 4));
+  g_coop_ok   = g_coop_ctas > 0;
+}
+
+TopFusion
+plan_top_fusion(const Plan& P)
+{
+  TopFusion tf{P.nlevels, 0, 0, 0};
+  if (g_coop_ok != 1 || P.nlevels < 3)
+  {
+    return tf;
+  }
+  // fuse the maximal run of top levels whose task counts fit the co-resident grid and whose fronts fit 32 KB
+  int split = P.nlevels;
+  int maxf = 0, maxb = 0, maxh = 0;
+  for (int l = P.nlevels - 1; l >= 1; --l)
+  {
+    const int nf = P.fwd_ptr[l + 1] - P.fwd_ptr[l], nb = P.bwd_ptr[l + 1] - P.bwd_ptr[l];
+    if (nf > 2 * g_coop_ctas || nb > 2 * g_coop_ctas || P.lvl_maxh[l] > 4096)
+    {
+      break;
+    }
+    split = l;
+    maxf  = std::max(maxf, nf);
+    maxb  = std::max(maxb, nb);
+    maxh  = std::max(maxh, P.lvl_maxh[l]);
+  }
+  if (P.nlevels - split < 2)
+  {
+    return tf;
+  }
+  tf.split    = split;
+  tf.grid_fwd = std::max(1, std::min(g_coop_ctas, maxf));
+  tf.grid_bwd = std::max(1, std::min(g_coop_ctas, maxb));
+  tf.smem     = sizeof(double) * (size_t)maxh;
+  return tf;
+}
+} // namespace
+
 static void
 solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, const double* in, double* out, cudaStream_t stream, LaunchCounter& lc, cudaEvent_t* ev = nullptr)
 {
@@ -531,22 +722,47 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
   const int T   = 256;
   if (P.m > 0)
   {
-    k_pre<<<nblocks(P.m, T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.k_of_e.p, dp.pinv.p, dp.Acsr_ptr.p, dp.Acsr_col.p, nb.Acsr_val, nb.dE, in, sb.bR);
+    k_pre<<<nblocks(P.m, T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.k_of_e.p, dp.pinv.p, dp.Acsr_ptr.p, dp.Acsr_col.p, nb.Acsr_val, nb.dE, in, sb.y);
     lc.tick();
     mark(1);
-    for (int l = 0; l < P.nlevels; ++l)
+    const TopFusion tf = plan_top_fusion(P);
+    for (int l = 0; l < tf.split; ++l)
     {
       const int cnt     = P.fwd_ptr[l + 1] - P.fwd_ptr[l];
       const size_t smem = sizeof(double) * (size_t)P.lvl_maxh[l];
-      k_fwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.fwd_tasks.p + P.fwd_ptr[l], dp.cptr.p, dp.cidx.p, nb.Mr, sb.bR, sb.y, sb.W);
+      k_fwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.fwd_tasks.p + P.fwd_ptr[l], dp.Ridx.p, nb.Mr, sb.y, sb.yf);
+      lc.tick();
+    }
+    if (tf.split < P.nlevels)
+    {
+      const FwdTask* tasks = dp.fwd_tasks.p;
+      const int* lp        = dp.fwd_ptr.p;
+      int l0 = tf.split, l1 = P.nlevels;
+      const int* ridx  = dp.Ridx.p;
+      const double* mr = nb.Mr;
+      double *ya = sb.y, *yf = sb.yf;
+      void* args[] = {&tasks, &lp, &l0, &l1, &ridx, &mr, &ya, &yf};
+      B200_CUDA(cudaLaunchCooperativeKernel((void*)k_fwd_top, dim3(tf.grid_fwd), dim3(SOLVE_THREADS), args, tf.smem, stream));
       lc.tick();
     }
     mark(2);
-    for (int l = P.nlevels - 1; l >= 0; --l)
+    if (tf.split < P.nlevels)
     {
-      const int cnt = P.bwd_ptr[l + 1] - P.bwd_ptr[l];
+      const BwdTask* tasks = dp.bwd_tasks.p;
+      const int* lp        = dp.bwd_ptr.p;
+      int l0 = tf.split, l1 = P.nlevels;
+      const int* ridx  = dp.Ridx.p;
+      const double *mt = nb.Mt, *dd = nb.D, *yf = sb.yf;
+      double* xx       = sb.x;
+      void* args[] = {&tasks, &lp, &l0, &l1, &ridx, &mt, &dd, &yf, &xx};
+      B200_CUDA(cudaLaunchCooperativeKernel((void*)k_bwd_top, dim3(tf.grid_bwd), dim3(SOLVE_THREADS), args, tf.smem, stream));
+      lc.tick();
+    }
+    for (int l = tf.split - 1; l >= 0; --l)
+    {
+      const int cnt     = P.bwd_ptr[l + 1] - P.bwd_ptr[l];
       const size_t smem = sizeof(double) * (size_t)P.lvl_maxh[l];
-      k_bwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.bwd_tasks.p + P.bwd_ptr[l], dp.Ridx.p, nb.Mt, nb.D, sb.y, sb.x);
+      k_bwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.bwd_tasks.p + P.bwd_ptr[l], dp.Ridx.p, nb.Mt, nb.D, sb.yf, sb.x);
       lc.tick();
     }
     mark(3);
@@ -586,6 +802,7 @@ configure_solve_kernels()
   {
     B200_CUDA(cudaFuncSetAttribute(k_fwd_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
     B200_CUDA(cudaFuncSetAttribute(k_bwd_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
+    probe_cooperative();
     done = true;
   }
 }

@@ -1321,9 +1321,9 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       }
       st.zero_end  = (int)P.zero_sn.size();
       st.ea_end    = (int)P.ea_tasks.size();
-      st.pan_begin = (int)P.pan_tasks.size();
-      st.upd_begin = (int)P.upd_tasks.size();
-      int slots    = 0;
+      st.diag_begin = (int)P.diag_tasks.size();
+      st.pan_begin  = (int)P.pan_tasks.size();
+      st.upd_begin  = (int)P.upd_tasks.size();
       for (int T : active[s])
       {
         const int t  = s - P.sn_base[T];
@@ -1333,16 +1333,10 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         const int c0 = t * NB;
         const int w  = std::min(NB, k - c0);
         const int below = h - c0 - w;
-        const int nrb   = std::max(1, (below + RB - 1) / RB);
-        int slot        = -1;
-        if (nrb > 1)
+        P.diag_tasks.push_back({T, t});
+        for (int rb = 0; rb * RB < below; ++rb)
         {
-          slot = slots++;
-          P.upd_tasks.push_back({T, t, UPD_DIAGCOPY, slot, 0});
-        }
-        for (int rb = 0; rb < nrb; ++rb)
-        {
-          P.pan_tasks.push_back({T, t, rb, slot});
+          P.pan_tasks.push_back({T, t, rb, 0});
         }
         // trailing update inside the panel: front columns [c0+w, k), rows >= column
         for (int j0 = c0 + w; j0 < k; j0 += TILE)
@@ -1363,7 +1357,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
           }
         }
       }
-      P.n_scratch_slots = std::max(P.n_scratch_slots, slots);
+      st.diag_end       = (int)P.diag_tasks.size();
       st.pan_end        = (int)P.pan_tasks.size();
       st.upd_end        = (int)P.upd_tasks.size();
     }
@@ -1547,11 +1541,11 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         const int k = P.sn_first[T + 1] - P.sn_first[T];
         const int h = (int)(P.Wptr[T + 1] - P.Wptr[T]);
         P.lvl_maxh[l] = std::max(P.lvl_maxh[l], h);
-        int nrows = std::min(16, std::max(4, (4096 + k - 1) / k)); // a warp works on up to 4 rows at once
+        int nrows = k > 1024 ? 16 : std::min(16, std::max(4, (4096 + k - 1) / k)); // a warp works on up to 4 rows at once
         nrows     = (nrows + 3) & ~3;
         for (int row0 = 0; row0 < h; row0 += nrows)
         {
-          P.fwd_tasks.push_back({T, row0, std::min(nrows, h - row0), P.sn_first[T], k, 0, P.Lptr[T], P.Wptr[T]});
+          P.fwd_tasks.push_back({T, row0, std::min(nrows, h - row0), P.sn_first[T], k, 0, P.Lptr[T], P.Rptr[T]});
         }
         int ncols = std::min(16, std::max(4, (4096 + h - 1) / h)); // a warp works on up to 4 columns at once
         ncols     = (ncols + 3) & ~3;
