@@ -85,8 +85,8 @@ class Emulated:
                 self._panel(int(T), int(t), 0, -1, scratch, diag_only=True)
             for T, t, rb, _pad in p["pan_tasks"][pb:pe]:
                 self._panel(int(T), int(t), int(rb), -1, scratch, trsm_only=True)
-            for T, t, kind, i0, j0 in p["upd_tasks"][ub:ue]:
-                self._update(int(T), int(t), int(kind), int(i0), int(j0), scratch, bool(has_children[T]))
+            for T, t, kind, i0, j0, kb, ke in p["upd_tasks"][ub:ue]:
+                self._update(int(T), int(t), int(kind), int(i0), int(j0), scratch, bool(has_children[T]), int(kb), int(ke))
 
     # ---------------------------------------------------------------- selective inversion
     def mpanel(self, T):
@@ -231,7 +231,7 @@ class Emulated:
             else:
                 scratch[slot * NB * NB : slot * NB * NB + w * w] = L11.T.ravel()  # column-major w x w
 
-    def _update(self, T, t, kind, i0, j0, scratch, accumulate):
+    def _update(self, T, t, kind, i0, j0, scratch, accumulate, kb=None, ke=None):
         f, k, r, h = self._geom(T)
         P = self.panel(T)
         if kind == UPD_DIAGCOPY:
@@ -244,12 +244,10 @@ class Emulated:
             blk[il] = L11[il]
             return
         if kind == UPD_INPANEL:
-            c0 = t * NB
-            w = min(NB, k - c0)
-            d = self.D[f + c0 : f + c0 + w]
-            i1, j1 = min(h, i0 + TILE), min(k, j0 + TILE)
-            Li = P[i0:i1, c0 : c0 + w]
-            Lj = P[j0:j1, c0 : c0 + w]
+            d = self.D[f + kb : f + ke]
+            i1, j1 = min(h, i0 + TILE), min(t, j0 + TILE)  # t carries the tile's column limit
+            Li = P[i0:i1, kb:ke]
+            Lj = P[j0:j1, kb:ke]
             upd = (Li * d) @ Lj.T
             mask = (np.arange(i0, i1)[:, None] >= np.arange(j0, j1)[None, :])
             blk = P[i0:i1, j0:j1]

@@ -44,7 +44,7 @@ struct b200_fact
 
   DevPlan dp;
   // factor
-  DevBuf<double> val, L, Mt, Mr, tmp, U, D, scratch, scal, dE, Acsc_val, Acsr_val, Gsym_val;
+  DevBuf<double> val, L, Mt, Mr, tmp, U, D, Dinv, scratch, scal, dE, Acsc_val, Acsr_val, Gsym_val;
   DevBuf<int> nper;
   // solve
   DevBuf<double> rhs, z, res, dz, bR, y, yf, x, W;
@@ -76,6 +76,7 @@ struct b200_fact
     nb.Mr          = Mr.p;
     nb.U           = U.p;
     nb.D           = D.p;
+    nb.Dinv        = Dinv.p;
     nb.scratch     = scratch.p;
     nb.scal        = scal.p;
     nb.n_perturbed = nper.p;
@@ -234,6 +235,7 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   F->Mr.reserve((size_t)P.Lptr[P.nsuper] + 8);
   F->U.reserve((size_t)P.Utotal + 8);
   F->D.reserve(m + 8);
+  F->Dinv.reserve(m + 8);
   F->scratch.reserve((size_t)std::max(1, P.n_scratch_slots) * NB * NB);
   F->scal.reserve(8);
   F->nper.reserve(2);
@@ -348,6 +350,7 @@ b200_fact_create(b200_fact** handle, int device)
     B200_CUDA(cudaEventCreate(&F->ev_c));
     B200_CUDA(cudaEventCreate(&F->ev_d));
     configure_solve_kernels();
+    configure_numeric_kernels();
     *handle = F.release();
     return (int)B200_OK;
   });
@@ -718,13 +721,37 @@ b200_fact_solution_sparse(b200_fact* F, int begin, int end, double zero_eps, int
   {
     return set_error(B200_ERR_ARG, "null output");
   }
-  int nnz = 0;
-  for (int i = 0; i < end - begin; ++i)
+  // compaction in blocks of 64: solutions are mostly dense, so a block without dropped entries (the common
+  // case) is a straight copy; only mixed blocks take the entry-by-entry path
+  const int n = end - begin;
+  int nnz     = 0;
+  for (int i0 = 0; i0 < n; i0 += 64)
   {
-    const double v = p[i];
-    idx_out[nnz]   = i;
-    val_out[nnz]   = v;
-    nnz += std::fabs(v) > zero_eps; // branch-free compaction
+    const int len = std::min(64, n - i0);
+    int keep      = 0;
+    for (int i = 0; i < len; ++i)
+    {
+      keep += std::fabs(p[i0 + i]) > zero_eps;
+    }
+    if (keep == len)
+    {
+      std::memcpy(val_out + nnz, p + i0, sizeof(double) * (size_t)len);
+      for (int i = 0; i < len; ++i)
+      {
+        idx_out[nnz + i] = i0 + i;
+      }
+      nnz += len;
+    }
+    else if (keep > 0)
+    {
+      for (int i = 0; i < len; ++i)
+      {
+        const double v = p[i0 + i];
+        idx_out[nnz]   = i0 + i;
+        val_out[nnz]   = v;
+        nnz += std::fabs(v) > zero_eps;
+      }
+    }
   }
   *nnz_out = nnz;
   return B200_OK;

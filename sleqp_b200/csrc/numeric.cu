@@ -177,6 +177,7 @@ k_diag(const DiagTask* __restrict__ tasks,
        double* __restrict__ L,
        double* __restrict__ Mt,
        double* __restrict__ D,
+       double* __restrict__ Dinv,
        const double* __restrict__ scal,
        int* __restrict__ n_perturbed)
 {
@@ -252,7 +253,8 @@ k_diag(const DiagTask* __restrict__ tasks,
   }
   if (tid < w)
   {
-    D[s.first + c0 + tid] = dsh[tid];
+    D[s.first + c0 + tid]    = dsh[tid];
+    Dinv[s.first + c0 + tid] = dinv[tid];
   }
   double* M = Mt + s.Lptr;
 #pragma unroll
@@ -348,23 +350,67 @@ k_trsm(const PanelTask* __restrict__ tasks,
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int KC  = 16;       // k-chunk staged per iteration
-constexpr int LDT = TILE + 4; // padded leading dimension: (LDT mod 16) == 4 -> conflict-free fragments
+// 64x64 output tiles on the FP64 tensor cores. Operands are staged through a 4-stage cp.async (LDGSTS)
+// pipeline in shared memory: chunk c+3 is in flight while chunk c is multiplied, one barrier per chunk.
+// (A 1-deep register prefetch left the DMMA pipe 22 % active with long-scoreboard stalls dominating:
+// profiles/README.md.)
+constexpr int KC     = 16;       // k-chunk per stage
+constexpr int LDT    = TILE + 4; // padded leading dimension: (LDT mod 16) == 4 -> conflict-free fragments
+constexpr int STAGES = 4;
+constexpr size_t TILE_SMEM = sizeof(double) * (size_t)(STAGES * (2 * KC * LDT + KC));
 
-// acc += As^T * Bs for one staged chunk: As[kk][i], Bs[kk][j]; warp (wy, wx) owns a 32x32 quadrant
 __device__ __forceinline__ void
-mma_chunk(const double (*As)[LDT], const double (*Bs)[LDT], double (&acc)[4][4][2], int wy, int wx, int lane)
+cp_async8(double* smem_dst, const double* gsrc, bool valid)
+{
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz     = valid ? 8 : 0; // src-size 0: nothing is read, the destination is zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void
+cp_async_commit()
+{
+  asm volatile("cp.async.commit_group;\n" ::);
+}
+template <int N>
+__device__ __forceinline__ void
+cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+struct TileSmem
+{
+  double (*As)[KC][LDT];
+  double (*Bs)[KC][LDT];
+  double (*ds)[KC];
+  __device__ explicit TileSmem(double* base)
+  {
+    As = reinterpret_cast<double(*)[KC][LDT]>(base);
+    Bs = reinterpret_cast<double(*)[KC][LDT]>(base + STAGES * KC * LDT);
+    ds = reinterpret_cast<double(*)[KC]>(base + 2 * STAGES * KC * LDT);
+  }
+};
+
+// acc += As^T * (Bs .* scale) for one staged chunk: As[kk][i], Bs[kk][j]; warp (wy, wx) owns a 32x32 quadrant
+template <bool SCALE>
+__device__ __forceinline__ void
+mma_chunk(const double (*As)[LDT], const double (*Bs)[LDT], const double* dsc, double (&acc)[4][4][2], int wy, int wx, int lane)
 {
 #pragma unroll
   for (int k4 = 0; k4 < KC / 4; ++k4)
   {
-    const int kr = k4 * 4 + (lane & 3);
+    const int kr   = k4 * 4 + (lane & 3);
+    const double d = SCALE ? dsc[kr] : 1.0;
     double af[4], bf[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
     {
       af[a] = As[kr][wy * 32 + a * 8 + (lane >> 2)];
       bf[a] = Bs[kr][wx * 32 + a * 8 + (lane >> 2)];
+      if (SCALE)
+      {
+        bf[a] *= d;
+      }
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -395,8 +441,7 @@ tile_update(const double* __restrict__ P,
             int gi0,
             int gj0,
             bool accumulate,
-            double (*As)[LDT],
-            double (*Bs)[LDT])
+            TileSmem sm)
 {
   const int tid  = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -412,55 +457,51 @@ tile_update(const double* __restrict__ P,
       acc[a][b][0] = 0.0;
       acc[a][b][1] = 0.0;
     }
-
-  // software pipeline: the next chunk's global loads are in flight while this chunk's DMMAs run.
-  // Element u of a thread: idx = tid + 128 u -> (kk = idx / TILE, ii = idx % TILE): consecutive threads
-  // read consecutive rows (coalesced).
-  double pa[8], pb[8];
-  auto gload = [&](int kc) {
+  const int nchunks = (ke - kb + KC - 1) / KC;
+  // element u of a thread: idx = tid + 128 u -> (kk = idx / TILE, ii = idx % TILE): consecutive threads copy
+  // consecutive rows (coalesced 8-byte cp.async)
+  auto issue = [&](int c, int st) {
+    const int kc = kb + c * KC;
 #pragma unroll
     for (int u = 0; u < 8; ++u)
     {
       const int idx = tid + 128 * u;
       const int kk = idx / TILE, ii = idx % TILE;
-      const int col = kc + kk;
-      double av = 0.0, bv = 0.0;
-      if (col < ke)
-      {
-        const double* pc = P + (long long)col * h;
-        if (ii < na)
-        {
-          av = pc[ra0 + ii];
-        }
-        if (ii < nb)
-        {
-          bv = pc[rb0 + ii] * d[col];
-        }
-      }
-      pa[u] = av;
-      pb[u] = bv;
+      const int col    = kc + kk;
+      const bool okc   = col < ke;
+      const double* pc = P + (long long)(okc ? col : kb) * h;
+      cp_async8(&sm.As[st][kk][ii], pc + ra0 + (ii < na ? ii : 0), okc && ii < na);
+      cp_async8(&sm.Bs[st][kk][ii], pc + rb0 + (ii < nb ? ii : 0), okc && ii < nb);
+    }
+    if (tid < KC)
+    {
+      const int col = kc + tid;
+      cp_async8(&sm.ds[st][tid], d + (col < ke ? col : kb), col < ke);
     }
   };
-  gload(kb);
-  for (int kc = kb; kc < ke; kc += KC)
-  {
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
+  for (int c = 0; c < STAGES - 1; ++c)
+  {
+    if (c < nchunks)
     {
-      const int idx = tid + 128 * u;
-      As[idx / TILE][idx % TILE] = pa[u];
-      Bs[idx / TILE][idx % TILE] = pb[u];
+      issue(c, c);
     }
-    __syncthreads();
-    if (kc + KC < ke)
+    cp_async_commit();
+  }
+  for (int c = 0; c < nchunks; ++c)
+  {
+    cp_async_wait<STAGES - 2>(); // chunk c has landed (for this thread's copies)
+    __syncthreads();             // ... for everybody's, and stage (c-1) % STAGES is free again
+    if (c + STAGES - 1 < nchunks)
     {
-      gload(kc + KC);
+      issue(c + STAGES - 1, (c + STAGES - 1) % STAGES);
     }
+    cp_async_commit();
     if (active)
     {
-      mma_chunk(As, Bs, acc, wy, wx, lane);
+      const int st = c % STAGES;
+      mma_chunk<true>(sm.As[st], sm.Bs[st], sm.ds[st], acc, wy, wx, lane);
     }
-    __syncthreads();
   }
   if (!active)
   {
@@ -502,22 +543,19 @@ k_update(const Task5* __restrict__ tasks,
          const SnMeta* __restrict__ sn,
          double* __restrict__ L,
          double* __restrict__ U,
-         const double* __restrict__ D,
-         const double* __restrict__ scratch)
+         const double* __restrict__ D)
 {
-  __shared__ double As[KC][LDT];
-  __shared__ double Bs[KC][LDT];
+  extern __shared__ double tile_smem[];
+  TileSmem sm(tile_smem);
   const Task5 t  = tasks[blockIdx.x];
   const SnMeta s = sn[t.sn];
   const int h    = s.k + s.r;
   double* P      = L + s.Lptr;
-  const int c0   = t.t * NB;
-  const int w    = min(NB, s.k - c0);
   if (t.kind == UPD_INPANEL)
   {
     // front rows [i0, i0+64) x front columns [j0, j0+64), columns < k, rows < h
-    const int na = min(TILE, h - t.i0), nb = min(TILE, s.k - t.j0);
-    tile_update(P, h, c0, c0 + w, D + s.first, t.i0, na, t.j0, nb, P + t.i0 + (long long)t.j0 * h, h, t.i0, t.j0, true, As, Bs);
+    const int na = min(TILE, h - t.i0), nb = min(TILE, t.jend - t.j0);
+    tile_update(P, h, t.kb, t.ke, D + s.first, t.i0, na, t.j0, nb, P + t.i0 + (long long)t.j0 * h, h, t.i0, t.j0, true, sm);
     return;
   }
   // UPD_SCHUR: update rows/cols [i0, i0+64) x [j0, j0+64) of U (r x r), operands are panel rows k + ...
@@ -525,7 +563,7 @@ k_update(const Task5* __restrict__ tasks,
     const int na = min(TILE, s.r - t.i0), nb = min(TILE, s.r - t.j0);
     double* Um   = U + s.Uoff;
     const bool accumulate = s.child_end > s.child_begin;
-    tile_update(P, h, 0, s.k, D + s.first, s.k + t.i0, na, s.k + t.j0, nb, Um + t.i0 + (long long)t.j0 * s.r, s.r, t.i0, t.j0, accumulate, As, Bs);
+    tile_update(P, h, 0, s.k, D + s.first, s.k + t.i0, na, s.k + t.j0, nb, Um + t.i0 + (long long)t.j0 * s.r, s.r, t.i0, t.j0, accumulate, sm);
   }
 }
 
@@ -539,8 +577,8 @@ k_inv_gemm(const InvTask* __restrict__ tasks,
            double* __restrict__ Mt,
            double* __restrict__ tmp)
 {
-  __shared__ double As[KC][LDT];
-  __shared__ double Bs[KC][LDT];
+  extern __shared__ double tile_smem[];
+  TileSmem sm(tile_smem);
   const InvTask t = tasks[blockIdx.x];
   const SnMeta s  = sn[t.sn];
   const int k = s.k, h = s.k + s.r;
@@ -593,41 +631,47 @@ k_inv_gemm(const InvTask* __restrict__ tasks,
       acc[a][b][0] = 0.0;
       acc[a][b][1] = 0.0;
     }
-  double pa[8], pb[8];
-  auto gload = [&](int kc) {
+  const int nchunks = (t.ke - t.kb + KC - 1) / KC;
+  auto issue = [&](int c, int st) {
+    const int kc = t.kb + c * KC;
 #pragma unroll
     for (int u = 0; u < 8; ++u)
     {
       const int idx = tid + 128 * u;
       {
         const int kk = idx / TILE, ii = idx % TILE; // consecutive threads -> consecutive rows of X
-        const int q = kc + kk;
-        pa[u]       = (q < t.ke && ii < na) ? X[ii + (long long)q * ldx] : 0.0;
+        const int q   = kc + kk;
+        const bool ok = q < t.ke && ii < na;
+        cp_async8(&sm.As[st][kk][ii], X + (ok ? ii + (long long)q * ldx : 0), ok);
       }
       {
         const int jj = idx / KC, kk = idx % KC; // consecutive threads -> consecutive rows of Y
-        const int q = kc + kk;
-        pb[u]       = (q < t.ke && jj < nb) ? Y[q + (long long)jj * ldy] : 0.0;
+        const int q   = kc + kk;
+        const bool ok = q < t.ke && jj < nb;
+        cp_async8(&sm.Bs[st][kk][jj], Y + (ok ? q + (long long)jj * ldy : 0), ok);
       }
     }
   };
-  gload(t.kb);
-  for (int kc = t.kb; kc < t.ke; kc += KC)
-  {
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
+  for (int c = 0; c < STAGES - 1; ++c)
+  {
+    if (c < nchunks)
     {
-      const int idx = tid + 128 * u;
-      As[idx / TILE][idx % TILE] = pa[u];
-      Bs[idx % KC][idx / KC]     = pb[u];
+      issue(c, c);
     }
+    cp_async_commit();
+  }
+  for (int c = 0; c < nchunks; ++c)
+  {
+    cp_async_wait<STAGES - 2>();
     __syncthreads();
-    if (kc + KC < t.ke)
+    if (c + STAGES - 1 < nchunks)
     {
-      gload(kc + KC);
+      issue(c + STAGES - 1, (c + STAGES - 1) % STAGES);
     }
-    mma_chunk(As, Bs, acc, wy, wx, lane);
-    __syncthreads();
+    cp_async_commit();
+    const int st = c % STAGES;
+    mma_chunk<false>(sm.As[st], sm.Bs[st], nullptr, acc, wy, wx, lane);
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -675,6 +719,18 @@ k_transpose(const TrTask* __restrict__ tasks, const SnMeta* __restrict__ sn, con
 
 // ---------------------------------------------------------------------------------------------
 void
+configure_numeric_kernels()
+{
+  static bool done = false;
+  if (!done)
+  {
+    B200_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_inv_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+    done = true;
+  }
+}
+
+void
 enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc)
 {
   const Plan& P = *dp.plan;
@@ -709,7 +765,7 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
     }
     if (st.diag_end > st.diag_begin)
     {
-      k_diag<<<(unsigned)(st.diag_end - st.diag_begin), DIAG_THR, 0, stream>>>(dp.diag_tasks.p + st.diag_begin, dp.sn.p, nb.L, nb.Mt, nb.D, nb.scal, nb.n_perturbed);
+      k_diag<<<(unsigned)(st.diag_end - st.diag_begin), DIAG_THR, 0, stream>>>(dp.diag_tasks.p + st.diag_begin, dp.sn.p, nb.L, nb.Mt, nb.D, nb.Dinv, nb.scal, nb.n_perturbed);
       lc.tick("panel");
     }
     if (st.pan_end > st.pan_begin)
@@ -719,7 +775,7 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
     }
     if (st.upd_end > st.upd_begin)
     {
-      k_update<<<(unsigned)(st.upd_end - st.upd_begin), 128, 0, stream>>>(dp.upd_tasks.p + st.upd_begin, dp.sn.p, nb.L, nb.U, nb.D, nb.scratch);
+      k_update<<<(unsigned)(st.upd_end - st.upd_begin), 128, TILE_SMEM, stream>>>(dp.upd_tasks.p + st.upd_begin, dp.sn.p, nb.L, nb.U, nb.D);
       lc.tick("update");
     }
   }
@@ -729,7 +785,7 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
     const int b = P.inv_phase_ptr[ph], e = P.inv_phase_ptr[ph + 1];
     if (e > b)
     {
-      k_inv_gemm<<<(unsigned)(e - b), 128, 0, stream>>>(dp.inv_tasks.p + b, dp.sn.p, nb.L, nb.Mt, nb.tmp);
+      k_inv_gemm<<<(unsigned)(e - b), 128, TILE_SMEM, stream>>>(dp.inv_tasks.p + b, dp.sn.p, nb.L, nb.Mt, nb.tmp);
       lc.tick("inv_gemm");
     }
   }

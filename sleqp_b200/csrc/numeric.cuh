@@ -15,6 +15,7 @@ struct NumericBuffers
   double* tmp;       // k x k scratch of the selective inversion
   double* U;         // update-matrix workspace
   double* D;         // pivots of S (new labels)
+  double* Dinv;      // their reciprocals (the diagonal solve is a multiply in the forward sweep)
   double* scratch;   // diagonal-block scratch slots
   double* scal;      // [0] max|S_jj|, [1] pivot threshold, [2..3] reduction results
   int* n_perturbed;
@@ -39,6 +40,7 @@ struct SolveBuffers
 
 // raise the dynamic shared-memory limit of the solve kernels (once per process, before capture)
 void configure_solve_kernels();
+void configure_numeric_kernels();
 
 void enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc);
 

@@ -21,6 +21,7 @@ typedef int64_t i64;
 constexpr int NB       = 32;  // panel width of the blocked dense LDL^T
 constexpr int RB       = 128; // rows per TRSM row-block CTA
 constexpr int TILE     = 64;  // output tile edge of the DMMA update kernel
+constexpr int NBO      = 128; // outer block: columns beyond it are updated once per outer block with K = NBO
 constexpr int EA_COLS  = 4;   // update-matrix columns per extend-add task (one warp each)
 constexpr int LEAF_MAX = 32;  // etree subtrees up to this many columns become one dense supernode
 
@@ -34,7 +35,8 @@ enum
 
 struct Task5
 {
-  int sn, t, kind, i0, j0;
+  int sn, jend, kind, i0, j0; // jend: first column the tile must not touch
+  int kb, ke;                 // inner (front column) range
 };
 
 struct DiagTask

@@ -163,7 +163,7 @@ k_axpy1(int n, const double* __restrict__ x, double* __restrict__ y)
 // before b_T is staged. Dynamic shared memory: bT[k].
 template <int RG>
 __device__ __forceinline__ void
-fwd_body(const FwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mr, double* __restrict__ yacc, double* __restrict__ yf, double* bT)
+fwd_body(const FwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mr, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf, double* bT)
 {
   constexpr int U = 8 / RG;
   const int k     = t.k;
@@ -186,9 +186,25 @@ fwd_body(const FwdTask& t, const int* __restrict__ Ridx, const double* __restric
       const int j = lane + 32 * u;
       pre[a][u]   = (a < nvalid && j < jend) ? P[(long long)(r0 + a) * k + j] : 0.0;
     }
-  for (int j = tid; j < k; j += SOLVE_THREADS)
+  // staged in batches of 4 independent loads per thread
+  for (int j = tid; j < k; j += 4 * SOLVE_THREADS)
   {
-    bT[j] = yacc[t.first + j];
+    double tmp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      const int jj = j + u * SOLVE_THREADS;
+      tmp[u]       = jj < k ? yacc[t.first + jj] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      const int jj = j + u * SOLVE_THREADS;
+      if (jj < k)
+      {
+        bT[jj] = tmp[u];
+      }
+    }
   }
   __syncthreads();
   if (nvalid <= 0)
@@ -257,7 +273,7 @@ fwd_body(const FwdTask& t, const int* __restrict__ Ridx, const double* __restric
     const int r = r0 + lane;
     if (r < k)
     {
-      yf[t.first + r] = mine;
+      yf[t.first + r] = mine * Dinv[t.first + r]; // D^-1 y: the diagonal solve is folded into the forward sweep
     }
     else
     {
@@ -267,7 +283,7 @@ fwd_body(const FwdTask& t, const int* __restrict__ Ridx, const double* __restric
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS)
-k_fwd_chunk(const FwdTask* __restrict__ tasks, const int* __restrict__ Ridx, const double* __restrict__ Mr, double* __restrict__ yacc, double* __restrict__ yf)
+k_fwd_chunk(const FwdTask* __restrict__ tasks, const int* __restrict__ Ridx, const double* __restrict__ Mr, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf)
 {
   extern __shared__ double bT[];
   const FwdTask t  = tasks[blockIdx.x];
@@ -275,15 +291,15 @@ k_fwd_chunk(const FwdTask* __restrict__ tasks, const int* __restrict__ Ridx, con
   const int rg     = (t.nrows + NW - 1) / NW; // rows per warp: 1..4
   if (rg == 1)
   {
-    fwd_body<1>(t, Ridx, Mr, yacc, yf, bT);
+    fwd_body<1>(t, Ridx, Mr, Dinv, yacc, yf, bT);
   }
   else if (rg == 2)
   {
-    fwd_body<2>(t, Ridx, Mr, yacc, yf, bT);
+    fwd_body<2>(t, Ridx, Mr, Dinv, yacc, yf, bT);
   }
   else
   {
-    fwd_body<4>(t, Ridx, Mr, yacc, yf, bT);
+    fwd_body<4>(t, Ridx, Mr, Dinv, yacc, yf, bT);
   }
 }
 
@@ -320,9 +336,32 @@ bwd_body(const BwdTask& t,
       const int i = j0 + lane + 32 * u;
       pre[c][u]   = (c < nvalid && i < h) ? P[(long long)(j0 + c) * h + i] : 0.0;
     }
-  for (int i = t.col0 + tid; i < h; i += SOLVE_THREADS)
+  // v = [D^-1 y_T; x_rows], staged in batches of 4 independent (two-hop) loads per thread
+  for (int i = t.col0 + tid; i < h; i += 4 * SOLVE_THREADS)
   {
-    v[i] = i < k ? y[t.first + i] / D[t.first + i] : x[rows[i - k]];
+    int src[4];
+    double tmp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      const int ii = i + u * SOLVE_THREADS;
+      src[u]       = ii < k ? t.first + ii : (ii < h ? rows[ii - k] : 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      const int ii = i + u * SOLVE_THREADS;
+      tmp[u]       = ii < k ? y[src[u]] : (ii < h ? x[src[u]] : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      const int ii = i + u * SOLVE_THREADS;
+      if (ii < h)
+      {
+        v[ii] = tmp[u];
+      }
+    }
   }
   __syncthreads();
   if (nvalid <= 0)
@@ -423,21 +462,21 @@ k_bwd_chunk(const BwdTask* __restrict__ tasks,
 // kernel launch + drain (~13 us) per level. These cooperative kernels walk all of them in one launch with a
 // grid barrier between levels; every CTA strides over the level's tasks.
 __device__ __forceinline__ void
-fwd_dispatch(const FwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mr, double* __restrict__ yacc, double* __restrict__ yf, double* bT)
+fwd_dispatch(const FwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mr, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf, double* bT)
 {
   constexpr int NW = SOLVE_THREADS / 32;
   const int rg     = (t.nrows + NW - 1) / NW;
   if (rg == 1)
   {
-    fwd_body<1>(t, Ridx, Mr, yacc, yf, bT);
+    fwd_body<1>(t, Ridx, Mr, Dinv, yacc, yf, bT);
   }
   else if (rg == 2)
   {
-    fwd_body<2>(t, Ridx, Mr, yacc, yf, bT);
+    fwd_body<2>(t, Ridx, Mr, Dinv, yacc, yf, bT);
   }
   else
   {
-    fwd_body<4>(t, Ridx, Mr, yacc, yf, bT);
+    fwd_body<4>(t, Ridx, Mr, Dinv, yacc, yf, bT);
   }
 }
 
@@ -461,7 +500,7 @@ bwd_dispatch(const BwdTask& t, const int* __restrict__ Ridx, const double* __res
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS)
-k_fwd_top(const FwdTask* __restrict__ tasks, const int* __restrict__ lvl_ptr, int l0, int l1, const int* __restrict__ Ridx, const double* __restrict__ Mr, double* __restrict__ yacc, double* __restrict__ yf)
+k_fwd_top(const FwdTask* __restrict__ tasks, const int* __restrict__ lvl_ptr, int l0, int l1, const int* __restrict__ Ridx, const double* __restrict__ Mr, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf)
 {
   extern __shared__ double smem_top[];
   cg::grid_group grid = cg::this_grid();
@@ -470,7 +509,7 @@ k_fwd_top(const FwdTask* __restrict__ tasks, const int* __restrict__ lvl_ptr, in
     for (int q = lvl_ptr[l] + blockIdx.x; q < lvl_ptr[l + 1]; q += gridDim.x)
     {
       const FwdTask t = tasks[q];
-      fwd_dispatch(t, Ridx, Mr, yacc, yf, smem_top);
+      fwd_dispatch(t, Ridx, Mr, Dinv, yacc, yf, smem_top);
       __syncthreads(); // the staging buffer is reused by the next task
     }
     grid.sync();
@@ -609,12 +648,12 @@ probe_cooperative()
     return;
   }
   g_coop_ok = 0;
-  if (const char* e = std::getenv("B200_NO_TOP_FUSION"))
+  // Measured on B200 (profiles/README.md): the fused kernels are slower than one launch per level (a graph
+  // node costs only ~0.6 us), so they are opt-in.
+  const char* e = std::getenv("B200_TOP_FUSION");
+  if (!e || !*e || *e == '0')
   {
-    if (*e && *e != '0')
-    {
-      return;
-    }
+    return;
   }
   int dev = 0, coop = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop)
@@ -730,7 +769,7 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
     {
       const int cnt     = P.fwd_ptr[l + 1] - P.fwd_ptr[l];
       const size_t smem = sizeof(double) * (size_t)P.lvl_maxh[l];
-      k_fwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.fwd_tasks.p + P.fwd_ptr[l], dp.Ridx.p, nb.Mr, sb.y, sb.yf);
+      k_fwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.fwd_tasks.p + P.fwd_ptr[l], dp.Ridx.p, nb.Mr, nb.Dinv, sb.y, sb.yf);
       lc.tick();
     }
     if (tf.split < P.nlevels)
@@ -739,9 +778,9 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
       const int* lp        = dp.fwd_ptr.p;
       int l0 = tf.split, l1 = P.nlevels;
       const int* ridx  = dp.Ridx.p;
-      const double* mr = nb.Mr;
+      const double *mr = nb.Mr, *di = nb.Dinv;
       double *ya = sb.y, *yf = sb.yf;
-      void* args[] = {&tasks, &lp, &l0, &l1, &ridx, &mr, &ya, &yf};
+      void* args[] = {&tasks, &lp, &l0, &l1, &ridx, &mr, &di, &ya, &yf};
       B200_CUDA(cudaLaunchCooperativeKernel((void*)k_fwd_top, dim3(tf.grid_fwd), dim3(SOLVE_THREADS), args, tf.smem, stream));
       lc.tick();
     }

@@ -1339,11 +1339,26 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
           P.pan_tasks.push_back({T, t, rb, 0});
         }
         // trailing update inside the panel: front columns [c0+w, k), rows >= column
-        for (int j0 = c0 + w; j0 < k; j0 += TILE)
+        // two-level blocking: columns of the same NBO-wide outer block ("near") are updated after every
+        // panel step with K = w; the columns beyond it ("far") once, after the last step of the outer
+        // block, with K = the whole outer block -- DMMA tiles with a decent arithmetic intensity
+        const int ob_begin = (c0 / NBO) * NBO;
+        const int ob_end   = std::min(k, ob_begin + NBO);
+        for (int j0 = c0 + w; j0 < ob_end; j0 += TILE)
         {
           for (int i0 = j0; i0 < h; i0 += TILE)
           {
-            P.upd_tasks.push_back({T, t, UPD_INPANEL, i0, j0});
+            P.upd_tasks.push_back({T, ob_end, UPD_INPANEL, i0, j0, c0, c0 + w});
+          }
+        }
+        if (c0 + w == ob_end)
+        {
+          for (int j0 = ob_end; j0 < k; j0 += TILE)
+          {
+            for (int i0 = j0; i0 < h; i0 += TILE)
+            {
+              P.upd_tasks.push_back({T, k, UPD_INPANEL, i0, j0, ob_begin, ob_end});
+            }
           }
         }
         if (t == P.sn_nt[T] - 1 && r > 0)
@@ -1352,7 +1367,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
           {
             for (int i0 = j0; i0 < r; i0 += TILE)
             {
-              P.upd_tasks.push_back({T, t, UPD_SCHUR, i0, j0});
+              P.upd_tasks.push_back({T, r, UPD_SCHUR, i0, j0, 0, k});
             }
           }
         }

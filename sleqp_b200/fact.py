@@ -52,7 +52,7 @@ PLAN_FIELDS = {
     ).split()},
     **{k: np.int64 for k in "Rptr Lptr Wptr Sdest Sterm_ptr Uoff Tptr".split()},
 }
-PLAN_STRUCTS = {"stages": 10, "ea_tasks": 2, "diag_tasks": 2, "pan_tasks": 4, "upd_tasks": 5, "inv_tasks": 6, "fwd_tasks": 10, "bwd_tasks": 10}  # int32 columns
+PLAN_STRUCTS = {"stages": 10, "ea_tasks": 2, "diag_tasks": 2, "pan_tasks": 4, "upd_tasks": 7, "inv_tasks": 6, "fwd_tasks": 10, "bwd_tasks": 10}  # int32 columns
 
 
 class Symbolic:

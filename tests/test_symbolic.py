@@ -17,6 +17,7 @@ CASES = {
     "chain_n2000": lambda: problems.chain_rosenbrock(2000, 0.1),
     "chain_n33_noactive": lambda: problems.chain_rosenbrock(33, 0.0),
     "no_constraints": lambda: _no_cons(),
+    "poisson2d_g48_wide_supernodes": lambda: problems.poisson_control(48, 2, seed=5),  # supernodes wider than one outer block
 }
 
 
@@ -50,7 +51,7 @@ def test_structure_matches_independent_symbolic(name):
     assert np.all(parent[nz] > np.nonzero(nz)[0])
 
 
-@pytest.mark.parametrize("name", ["config1", "poisson2d_g24", "poisson3d_g6", "chain_n2000"])
+@pytest.mark.parametrize("name", ["config1", "poisson2d_g24", "poisson3d_g6", "chain_n2000", "poisson2d_g48_wide_supernodes"])
 def test_plan_emulation_solves_kkt(name):
     p = CASES[name]()
     cp, ri, v = p.kkt_lower()
