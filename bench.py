@@ -284,6 +284,8 @@ def run_ours(args, rank, world, local_rank):
     launches0 = lib.b200_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    if args.profile_step:
+        torch.cuda.profiler.start()  # ncu --profile-from-start off: capture exactly the timed steps
     for s in range(args.steps):
         with torch.cuda.stream(stream):
             flush.fill_(1.0)  # L2 flush between timed steps, outside the step's event pair
@@ -291,6 +293,8 @@ def run_ours(args, rank, world, local_rank):
         device_step()
         ev[s][1].record(stream)
     barrier()
+    if args.profile_step:
+        torch.cuda.profiler.stop()
     launches = lib.b200_launch_count() - launches0
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     clocks = sampler.stop()
@@ -525,6 +529,7 @@ def main():
     ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (default 1: 2D Poisson control, n~2.5e5)")
     ap.add_argument("--cg-iters", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
     ap.add_argument("--batch", type=int, default=0, help="config 5 mode: this many independent instances sharded over the ranks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
