@@ -161,11 +161,10 @@ k_axpy1(int n, const double* __restrict__ x, double* __restrict__ y)
 // Reads the row-major copy Mr of the inverse panel: a warp owns RG rows at a time, lanes stride the
 // (contiguous) columns with 8 independent loads in flight; the first round of panel loads is issued
 // before b_T is staged. Dynamic shared memory: bT[k].
-template <int RG>
+template <int RG, int U>
 __device__ __forceinline__ void
 fwd_body(const FwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mr, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf, double* bT)
 {
-  constexpr int U = 8 / RG;
   const int k     = t.k;
   const double* P = Mr + t.Lptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -291,15 +290,19 @@ k_fwd_chunk(const FwdTask* __restrict__ tasks, const int* __restrict__ Ridx, con
   const int rg     = (t.nrows + NW - 1) / NW; // rows per warp: 1..4
   if (rg == 1)
   {
-    fwd_body<1>(t, Ridx, Mr, Dinv, yacc, yf, bT);
+    fwd_body<1, 8>(t, Ridx, Mr, Dinv, yacc, yf, bT);
   }
   else if (rg == 2)
   {
-    fwd_body<2>(t, Ridx, Mr, Dinv, yacc, yf, bT);
+    fwd_body<2, 4>(t, Ridx, Mr, Dinv, yacc, yf, bT);
+  }
+  else if (rg <= 4)
+  {
+    fwd_body<4, 2>(t, Ridx, Mr, Dinv, yacc, yf, bT);
   }
   else
   {
-    fwd_body<4>(t, Ridx, Mr, Dinv, yacc, yf, bT);
+    fwd_body<8, 2>(t, Ridx, Mr, Dinv, yacc, yf, bT); // narrow supernodes: 8 rows per warp
   }
 }
 
@@ -307,7 +310,7 @@ k_fwd_chunk(const FwdTask* __restrict__ tasks, const int* __restrict__ Ridx, con
 // One CTA per (supernode, column chunk):  x_T = Minv^T [D^-1 y_T; x_rows].  A warp owns CG columns at a
 // time (rows are contiguous in the column-major panel), lanes stride the rows with 8 independent loads
 // in flight (first round issued before the vector is gathered), shuffle reduction. Dynamic shared memory: v[h].
-template <int CG>
+template <int CG, int U>
 __device__ __forceinline__ void
 bwd_body(const BwdTask& t,
          const int* __restrict__ Ridx,
@@ -317,7 +320,6 @@ bwd_body(const BwdTask& t,
          double* __restrict__ x,
          double* v)
 {
-  constexpr int U = 8 / CG;
   const int k = t.k, h = t.h;
   const double* P = Mt + t.Lptr;
   const int* rows = Ridx + t.Rptr;
@@ -445,15 +447,15 @@ k_bwd_chunk(const BwdTask* __restrict__ tasks,
   const int cg     = (t.ncols + NW - 1) / NW; // columns per warp: 1..4
   if (cg == 1)
   {
-    bwd_body<1>(t, Ridx, Mt, D, y, x, v);
+    bwd_body<1, 8>(t, Ridx, Mt, D, y, x, v);
   }
   else if (cg == 2)
   {
-    bwd_body<2>(t, Ridx, Mt, D, y, x, v);
+    bwd_body<2, 4>(t, Ridx, Mt, D, y, x, v);
   }
   else
   {
-    bwd_body<4>(t, Ridx, Mt, D, y, x, v);
+    bwd_body<4, 2>(t, Ridx, Mt, D, y, x, v);
   }
 }
 
@@ -468,15 +470,19 @@ fwd_dispatch(const FwdTask& t, const int* __restrict__ Ridx, const double* __res
   const int rg     = (t.nrows + NW - 1) / NW;
   if (rg == 1)
   {
-    fwd_body<1>(t, Ridx, Mr, Dinv, yacc, yf, bT);
+    fwd_body<1, 8>(t, Ridx, Mr, Dinv, yacc, yf, bT);
   }
   else if (rg == 2)
   {
-    fwd_body<2>(t, Ridx, Mr, Dinv, yacc, yf, bT);
+    fwd_body<2, 4>(t, Ridx, Mr, Dinv, yacc, yf, bT);
+  }
+  else if (rg <= 4)
+  {
+    fwd_body<4, 2>(t, Ridx, Mr, Dinv, yacc, yf, bT);
   }
   else
   {
-    fwd_body<4>(t, Ridx, Mr, Dinv, yacc, yf, bT);
+    fwd_body<8, 2>(t, Ridx, Mr, Dinv, yacc, yf, bT); // narrow supernodes: 8 rows per warp
   }
 }
 
@@ -487,15 +493,15 @@ bwd_dispatch(const BwdTask& t, const int* __restrict__ Ridx, const double* __res
   const int cg_    = (t.ncols + NW - 1) / NW;
   if (cg_ == 1)
   {
-    bwd_body<1>(t, Ridx, Mt, D, y, x, v);
+    bwd_body<1, 8>(t, Ridx, Mt, D, y, x, v);
   }
   else if (cg_ == 2)
   {
-    bwd_body<2>(t, Ridx, Mt, D, y, x, v);
+    bwd_body<2, 4>(t, Ridx, Mt, D, y, x, v);
   }
   else
   {
-    bwd_body<4>(t, Ridx, Mt, D, y, x, v);
+    bwd_body<4, 2>(t, Ridx, Mt, D, y, x, v);
   }
 }
 

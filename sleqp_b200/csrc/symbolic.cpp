@@ -1556,13 +1556,16 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         const int k = P.sn_first[T + 1] - P.sn_first[T];
         const int h = (int)(P.Wptr[T + 1] - P.Wptr[T]);
         P.lvl_maxh[l] = std::max(P.lvl_maxh[l], h);
-        int nrows = k > 1024 ? 16 : std::min(16, std::max(4, (4096 + k - 1) / k)); // a warp works on up to 4 rows at once
+        // a warp works on up to 4 rows at once (8 for narrow supernodes: few columns, so more rows keep the
+        // loads in flight and the leaf levels need half the CTAs)
+        int nrows = k <= 64 ? 32 : (k > 1024 ? 16 : std::min(16, std::max(4, (4096 + k - 1) / k)));
         nrows     = (nrows + 3) & ~3;
         for (int row0 = 0; row0 < h; row0 += nrows)
         {
           P.fwd_tasks.push_back({T, row0, std::min(nrows, h - row0), P.sn_first[T], k, 0, P.Lptr[T], P.Rptr[T]});
         }
-        int ncols = std::min(16, std::max(4, (4096 + h - 1) / h)); // a warp works on up to 4 columns at once
+        // a warp works on up to 4 columns at once (8 per warp was measured slower for the short fronts)
+        int ncols = std::min(16, std::max(4, (4096 + h - 1) / h));
         ncols     = (ncols + 3) & ~3;
         for (int col0 = 0; col0 < k; col0 += ncols)
         {
