@@ -195,6 +195,29 @@ B200_API void* b200_mat_stream(b200_mat* handle);
 B200_API int b200_mat_set_stream(b200_mat* handle, void* stream);
 B200_API int b200_mat_free(b200_mat** handle);
 
+/* ---- device-resident projected CG (SleqpTRSolver.solve, src/main/tr/tr_solver.c:54; algorithm of
+ * src/main/tr/steihaug_solver.c:223-496) ------------------------------------------------------------------- */
+
+typedef struct b200_cg b200_cg;
+
+enum
+{
+  B200_CG_INTERIOR      = 0, /* |r.g| below tolerance: returns z (steihaug_solver.c:318-327) */
+  B200_CG_BOUNDARY      = 1, /* step hit the trust region (steihaug_solver.c:419-441) */
+  B200_CG_NEG_CURVATURE = 2, /* d^T H d <= 0 (steihaug_solver.c:349-402) */
+  B200_CG_MAX_ITER      = 3  /* iteration cap: like the reference, the step is ZERO (steihaug_solver.c:302-305) */
+};
+
+/* Borrows a factorization handle (K = [I A_W^T; A_W 0] already factorized) and a matrix handle holding the
+ * Hessian of the Lagrangian (n x n, full symmetric CSC); both must outlive the CG handle and live on one device. */
+B200_API int b200_cg_create(b200_cg** handle, b200_fact* fact, b200_mat* hess);
+/* min g^T p + 1/2 p^T H p  s.t.  A_W p = 0, |p| <= trust_radius. gradient: sparse host vector of dimension n;
+ * rel_tol = stat_tol * 1e-2 in the reference (steihaug_solver.c:21,241); max_iter < 0: unlimited.
+ * step_out: n doubles (host). */
+B200_API int b200_cg_solve(b200_cg* handle, int n, int nnz_g, const int* g_idx, const double* g_val, double trust_radius, double rel_tol,
+                           int max_iter, double* step_out, int* iterations, int* termination);
+B200_API int b200_cg_free(b200_cg** handle);
+
 /* ---- misc ------------------------------------------------------------------------------ */
 B200_API int b200_device_count(void);
 /* Number of kernel launches issued by this library on this process so far (bench.py's

@@ -258,3 +258,35 @@ class Mat:
             self.release()
         except Exception:
             pass
+
+
+class ProjectedCG:
+    """Device-resident Steihaug projected CG (SleqpTRSolver, src/main/tr/steihaug_solver.c:223-496) over a
+    factorized KKT system and a Hessian held in device memory: min g^T p + 1/2 p^T H p, A_W p = 0, |p| <= radius."""
+
+    INTERIOR, BOUNDARY, NEG_CURVATURE, MAX_ITER = range(4)
+
+    def __init__(self, fact: Fact, hess: Mat):
+        self._h = C.c_void_p()
+        self._fact, self._hess = fact, hess  # keep the borrowed handles alive
+        check(lib().b200_cg_create(C.byref(self._h), fact._h, hess._h))
+
+    def solve(self, n, g_idx, g_val, trust_radius, rel_tol=1e-8, max_iter=100):
+        """Returns (step[n], iterations, termination)."""
+        g_idx, g_val = _i32(g_idx), _f64(g_val)
+        step = np.empty(int(n), dtype=np.float64)
+        it, term = C.c_int(), C.c_int()
+        check(lib().b200_cg_solve(self._h, int(n), int(len(g_idx)), _pi(g_idx), _pd(g_val), float(trust_radius), float(rel_tol),
+                                  int(max_iter), _pd(step), C.byref(it), C.byref(term)))
+        return step, it.value, term.value
+
+    def release(self):
+        if self._h:
+            check(lib().b200_cg_free(C.byref(self._h)))
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass

@@ -170,3 +170,23 @@ def config(idx: int, **kw) -> KKTProblem:
     if idx == 4:
         return poisson_control(kw.pop("g", 128), 2, name="config5_poisson2d_g128", **kw)
     raise ValueError(idx)
+
+
+def eqp_harness_problem(n: int = 400) -> tuple[KKTProblem, np.ndarray]:
+    """The problem oracle/eqp_harness.c builds in C (same x0 from its xorshift64, same working set: every 20th
+    variable at its bound + every constraint). Returns (problem, objective gradient at x0)."""
+    mask = (1 << 64) - 1
+    state = 88172645463325252
+    x = np.empty(n)
+    for i in range(n):
+        state ^= (state << 13) & mask
+        state ^= state >> 7
+        state ^= (state << 17) & mask
+        x[i] = 0.5 + (state >> 11) / 9007199254740992.0
+    J, m = _chain_jacobian(x)
+    grad = np.zeros(n)
+    grad[:-1] += -400.0 * x[:-1] * (x[1:] - x[:-1] ** 2) - 2.0 * (1.0 - x[:-1])
+    grad[1:] += 200.0 * (x[1:] - x[:-1] ** 2)
+    p = KKTProblem(name=f"eqp_harness_n{n}", n=n, m=m, J=J, H=_rosenbrock_hessian(x), active_vars=np.arange(0, n, 20, dtype=np.int64),
+                   active_cons=np.arange(m, dtype=np.int64), meta=dict(x0=x))
+    return p, grad

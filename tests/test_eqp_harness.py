@@ -50,3 +50,73 @@ def test_b200_backend_reproduces_reference_eqp_iterates(golden):
     assert "B200" in err
     _compare(got, {k: want[k] for k in want.files}, 1e-8)
     assert got["backend"][0] == 2  # SLEQP_FACT_FLAGS_LOWER
+
+
+def _harness_setup():
+    from sleqp_b200 import problems
+
+    p, grad = problems.eqp_harness_problem(N)
+    return p, grad
+
+
+def test_oracle_cg_restatement_matches_reference_fixture(golden):
+    """oracle.steihaug_projected_cg (numpy restatement of steihaug_solver.c) on the harness problem, with the
+    projection done by a sparse LU of K, reproduces what the reference's own Steihaug solver printed."""
+    from oracle import sleqp_oracle as orc
+
+    want = golden(f"eqp_harness_lapack_n{N}.npz")
+    p, grad = _harness_setup()
+    cp, ri, v = p.kkt_lower()
+    lu = orc.SparseLU()
+    lu.set_matrix(p.N, cp, ri, v)
+    H = p.H.tocsr()
+
+    def project(r):
+        return lu.solve(np.arange(p.n), r)[: p.n].copy()
+
+    # the projection and the objective gradient themselves
+    assert np.abs(project(grad) - want["project_nullspace"]).max() <= 1e-9 * np.abs(want["project_nullspace"]).max()
+    step, it, how = orc.steihaug_projected_cg(project, lambda d: H @ d, grad, 1e8, 1e-4, 4 * N)
+    assert how == "interior" and it > 10
+    assert np.abs(step - want["cg_converged_step"]).max() <= 1e-8 * max(1.0, np.abs(want["cg_converged_step"]).max())
+    full = np.linalg.norm(want["cg_converged_step"])
+    for i in range(RADII):
+        radius = full * (0.6 + 0.4 * (i + 0.5) / RADII)
+        s, _, how = orc.steihaug_projected_cg(project, lambda d: H @ d, grad, radius, 1e-4, 4 * N)
+        assert how == "boundary"
+        assert np.abs(s - want[f"cg_path_sample_{i}"]).max() <= 1e-8 * max(1.0, np.abs(want[f"cg_path_sample_{i}"]).max())
+
+
+@pytest.mark.gpu
+def test_device_resident_projected_cg_matches_reference_iterates(golden):
+    """the whole projected-CG loop on the device (b200_cg_solve) against the iterates
+    of the reference's Steihaug solver (fixture from oracle/eqp_harness.c over the reference LAPACK backend)."""
+    from sleqp_b200 import Fact, Mat, ProjectedCG
+
+    want = golden(f"eqp_harness_lapack_n{N}.npz")
+    p, grad = _harness_setup()
+    f = Fact()
+    f.set_matrix(p.N, *p.kkt_lower())
+    H = p.H.tocsc()
+    H.sort_indices()
+    mh = Mat()
+    mh.set(p.n, p.n, H.indptr, H.indices, H.data)
+    cg = ProjectedCG(f, mh)
+    gi = np.arange(p.n, dtype=np.int32)
+    step, it, how = cg.solve(p.n, gi, grad, 1e8, 1e-4, 4 * N)
+    assert how == ProjectedCG.INTERIOR and it > 10
+    ref = want["cg_converged_step"]
+    assert np.abs(step - ref).max() <= 1e-8 * max(1.0, np.abs(ref).max())
+    full = np.linalg.norm(ref)
+    for i in range(RADII):
+        radius = full * (0.6 + 0.4 * (i + 0.5) / RADII)
+        s, _, how = cg.solve(p.n, gi, grad, radius, 1e-4, 4 * N)
+        assert how == ProjectedCG.BOUNDARY
+        ref = want[f"cg_path_sample_{i}"]
+        assert np.abs(s - ref).max() <= 1e-8 * max(1.0, np.abs(ref).max()), i
+    # iteration cap: zero step, like the reference
+    s, it, how = cg.solve(p.n, gi, grad, 1e8, 1e-4, 3)
+    assert how == ProjectedCG.MAX_ITER and it == 3 and not s.any()
+    # feasibility of the step: A_W p = 0
+    assert np.abs(p.working_rows() @ step).max() <= 1e-9
+    cg.release()
