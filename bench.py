@@ -366,6 +366,40 @@ def run_ours(args, rank, world, local_rank):
         fact.solution(b, e, 1e-20)
     e2e_solve_ms = 1e3 * (time.perf_counter() - t0) / len(rhs[2:7])
 
+    # device-resident projected CG: the same inner loop without the per-iteration boundary crossing
+    from sleqp_b200 import ProjectedCG
+
+    mH.set_stream(0)
+    cgs = ProjectedCG(fact, mH)
+    g_idx = np.arange(p.n, dtype=np.int32)
+    g_val = w["rng"].standard_normal(p.n)
+    cgs.solve(p.n, g_idx, g_val, 1e8, 1e-6, k)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, cg_it, cg_how = cgs.solve(p.n, g_idx, g_val, 1e8, 1e-6, k)
+    cg_ms = 1e3 * (time.perf_counter() - t0)
+    # the same EQP step end to end with the CG loop on the device: host K in, host step out
+    def host_step_device_cg():
+        fact.set_matrix(p.N, w["cp"], w["ri"], w["v"])
+        for kind, idx, val, b, e in rhs[:2]:
+            fact.solve(idx, val, p.N)
+            fact.solution(b, e, 1e-20)
+        mJ.mult_vec_trans(vh_idx, vh, 0.0, out=buf_n)
+        out = cgs.solve(p.n, g_idx, g_val, 1e8, 1e-6, k)
+        mJ.mult_vec(xh_idx, xh, out=buf_m)
+        return out
+
+    host_step_device_cg()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_step_device_cg()
+    torch.cuda.synchronize()
+    e2e_cg_ms = shard.max_over_ranks(1e3 * (time.perf_counter() - t0) / e2e_steps, dist, dev)
+    device_cg = {"e2e_step_ms": e2e_cg_ms, "e2e_value": world * 1e3 / e2e_cg_ms, "iterations": int(cg_it), "exit": int(cg_how), "ms": cg_ms, "ms_per_iteration": cg_ms / max(1, cg_it),
+                 "note": "b200_cg_solve: gradient in, step out; 1 SpMV + 1 KKT solve + vector kernels per iteration on the device"}
+    cgs.release()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample(w, rhs, k)
@@ -384,6 +418,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
+            "device_cg": device_cg,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -392,7 +427,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     mJ.set_stream(0)
     mH.set_stream(0)
-    for obj in (mJ, mH, fact):
+    for obj in (mJ, mH, fact):  # (the CG handle was released above)
         obj.release()
     if dist is not None:
         dist.barrier()
