@@ -125,6 +125,20 @@ struct PinnedBuf
   }
 };
 
+// True if `p` is page-locked host memory (cudaMallocHost / cudaHostRegister): the copy engines can read or write it
+// directly, so the library skips its own pinned staging copy.
+inline bool
+is_pinned_host(const void* p)
+{
+  cudaPointerAttributes attr;
+  if (!p || cudaPointerGetAttributes(&attr, p) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  return attr.type == cudaMemoryTypeHost;
+}
+
 // Per-supernode geometry on the device.
 struct SnMeta
 {

@@ -40,7 +40,7 @@ struct b200_fact
 {
   int device          = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_copy = nullptr;
 
   DevPlan dp;
   // factor
@@ -349,6 +349,7 @@ b200_fact_create(b200_fact** handle, int device)
     B200_CUDA(cudaEventCreate(&F->ev_b));
     B200_CUDA(cudaEventCreate(&F->ev_c));
     B200_CUDA(cudaEventCreate(&F->ev_d));
+    B200_CUDA(cudaEventCreateWithFlags(&F->ev_copy, cudaEventDisableTiming));
     configure_solve_kernels();
     configure_numeric_kernels();
     *handle = F.release();
@@ -625,6 +626,7 @@ b200_fact_solve(b200_fact* F, int nnz_rhs, const int* idx, const double* val, in
     // the previous solve may still be reading the staging buffers
     B200_CUDA(cudaStreamSynchronize(F->stream));
     LaunchCounter eager;
+    bool copy_pending = false;
     B200_CUDA(cudaEventRecord(F->ev_c, F->stream));
     if (nnz_rhs > 0)
     {
@@ -633,10 +635,20 @@ b200_fact_solve(b200_fact* F, int nnz_rhs, const int* idx, const double* val, in
         return set_error(B200_ERR_ARG, "rhs index out of range");
       }
       const bool contiguous = (idx[nnz_rhs - 1] - idx[0]) == nnz_rhs - 1; // ascending indices (pub_vec.h:13-14)
-      F->h_rhs_val.reserve((size_t)nnz_rhs);
       F->rhs_val.reserve((size_t)nnz_rhs);
-      std::memcpy(F->h_rhs_val.p, val, sizeof(double) * (size_t)nnz_rhs);
-      B200_CUDA(cudaMemcpyAsync(F->rhs_val.p, F->h_rhs_val.p, sizeof(double) * (size_t)nnz_rhs, cudaMemcpyHostToDevice, F->stream));
+      // the right-hand side is borrowed for the duration of the call: pageable memory is staged through the
+      // handle's pinned buffer, page-locked memory is read by the copy engine directly (and waited for below)
+      bool direct = is_pinned_host(val);
+      if (direct)
+      {
+        B200_CUDA(cudaMemcpyAsync(F->rhs_val.p, val, sizeof(double) * (size_t)nnz_rhs, cudaMemcpyHostToDevice, F->stream));
+      }
+      else
+      {
+        F->h_rhs_val.reserve((size_t)nnz_rhs);
+        std::memcpy(F->h_rhs_val.p, val, sizeof(double) * (size_t)nnz_rhs);
+        B200_CUDA(cudaMemcpyAsync(F->rhs_val.p, F->h_rhs_val.p, sizeof(double) * (size_t)nnz_rhs, cudaMemcpyHostToDevice, F->stream));
+      }
       const int* d_idx = nullptr;
       if (!contiguous)
       {
@@ -646,6 +658,11 @@ b200_fact_solve(b200_fact* F, int nnz_rhs, const int* idx, const double* val, in
         B200_CUDA(cudaMemcpyAsync(F->rhs_idx.p, F->h_rhs_idx.p, sizeof(int) * (size_t)nnz_rhs, cudaMemcpyHostToDevice, F->stream));
         d_idx = F->rhs_idx.p;
       }
+      if (direct)
+      {
+        B200_CUDA(cudaEventRecord(F->ev_copy, F->stream));
+      }
+      copy_pending = direct;
       enqueue_scatter_rhs(F->rhs.p, P.N, nnz_rhs, d_idx, idx[0], F->rhs_val.p, F->stream, eager);
     }
     else
@@ -654,6 +671,10 @@ b200_fact_solve(b200_fact* F, int nnz_rhs, const int* idx, const double* val, in
     }
     launch_solve(F, F->refine);
     B200_CUDA(cudaEventRecord(F->ev_d, F->stream));
+    if (copy_pending)
+    {
+      B200_CUDA(cudaEventSynchronize(F->ev_copy)); // the caller may reuse its buffer as soon as we return
+    }
     F->timed_solve = true;
     F->solved      = true;
     return (int)B200_OK;
@@ -691,6 +712,15 @@ b200_fact_solution_ptr(b200_fact* F, int begin, int end, const double** out)
 int
 b200_fact_solution(b200_fact* F, int begin, int end, double* out_dense)
 {
+  if (F && F->solved && out_dense && end > begin && begin >= 0 && F->dp.plan && end <= F->dp.plan->N && is_pinned_host(out_dense))
+  {
+    return guarded([&]() {
+      B200_CUDA(cudaSetDevice(F->device));
+      B200_CUDA(cudaMemcpyAsync(out_dense, F->z.p + begin, sizeof(double) * (size_t)(end - begin), cudaMemcpyDeviceToHost, F->stream));
+      B200_CUDA(cudaStreamSynchronize(F->stream));
+      return (int)B200_OK;
+    });
+  }
   const double* p = nullptr;
   int rc          = b200_fact_solution_ptr(F, begin, end, &p);
   if (rc != B200_OK)
@@ -894,7 +924,7 @@ b200_fact_free(b200_fact** handle)
     cudaStreamSynchronize(F->stream);
   }
   F->drop_graphs();
-  for (cudaEvent_t e : {F->ev_a, F->ev_b, F->ev_c, F->ev_d})
+  for (cudaEvent_t e : {F->ev_a, F->ev_b, F->ev_c, F->ev_d, F->ev_copy})
   {
     if (e)
     {

@@ -160,10 +160,17 @@ stage_sparse(b200_mat* M, int dim, int nnz, const int* idx, const double* val, d
   {
     return;
   }
-  M->h_val.reserve((size_t)nnz);
   M->sp_val.reserve((size_t)nnz);
-  std::memcpy(M->h_val.p, val, sizeof(double) * (size_t)nnz);
-  B200_CUDA(cudaMemcpyAsync(M->sp_val.p, M->h_val.p, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, M->stream));
+  if (is_pinned_host(val)) // borrowed buffer, but every caller synchronises the stream before returning
+  {
+    B200_CUDA(cudaMemcpyAsync(M->sp_val.p, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, M->stream));
+  }
+  else
+  {
+    M->h_val.reserve((size_t)nnz);
+    std::memcpy(M->h_val.p, val, sizeof(double) * (size_t)nnz);
+    B200_CUDA(cudaMemcpyAsync(M->sp_val.p, M->h_val.p, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, M->stream));
+  }
   const bool contiguous = (idx[nnz - 1] - idx[0]) == nnz - 1;
   const int* d_idx      = nullptr;
   if (!contiguous)
@@ -367,12 +374,13 @@ b200_mat_mult_vec(b200_mat* M, int nnz_x, const int* idx, const double* val, dou
     B200_CUDA(cudaSetDevice(M->device));
     stage_sparse(M, M->num_cols, nnz_x, idx, val, M->x.p);
     launch_spmv(M->num_rows, M->nnz, M->csr_ptr.p, M->csr_col.p, M->csr_val.p, M->x.p, M->y.p, M->stream);
+    const bool direct = is_pinned_host(result_dense);
     if (M->num_rows > 0)
     {
-      B200_CUDA(cudaMemcpyAsync(M->h_out.p, M->y.p, sizeof(double) * (size_t)M->num_rows, cudaMemcpyDeviceToHost, M->stream));
+      B200_CUDA(cudaMemcpyAsync(direct ? result_dense : M->h_out.p, M->y.p, sizeof(double) * (size_t)M->num_rows, cudaMemcpyDeviceToHost, M->stream));
     }
     B200_CUDA(cudaStreamSynchronize(M->stream));
-    if (M->num_rows > 0)
+    if (M->num_rows > 0 && !direct)
     {
       std::memcpy(result_dense, M->h_out.p, sizeof(double) * (size_t)M->num_rows);
     }
@@ -396,12 +404,13 @@ b200_mat_mult_vec_trans(b200_mat* M, int nnz_v, const int* idx, const double* va
     B200_CUDA(cudaSetDevice(M->device));
     stage_sparse(M, M->num_rows, nnz_v, idx, val, M->x.p);
     launch_spmv(M->num_cols, M->nnz, M->cols.p, M->rows.p, M->data.p, M->x.p, M->y.p, M->stream);
+    const bool direct = is_pinned_host(result_dense);
     if (M->num_cols > 0)
     {
-      B200_CUDA(cudaMemcpyAsync(M->h_out.p, M->y.p, sizeof(double) * (size_t)M->num_cols, cudaMemcpyDeviceToHost, M->stream));
+      B200_CUDA(cudaMemcpyAsync(direct ? result_dense : M->h_out.p, M->y.p, sizeof(double) * (size_t)M->num_cols, cudaMemcpyDeviceToHost, M->stream));
     }
     B200_CUDA(cudaStreamSynchronize(M->stream));
-    if (M->num_cols > 0)
+    if (M->num_cols > 0 && !direct)
     {
       std::memcpy(result_dense, M->h_out.p, sizeof(double) * (size_t)M->num_cols);
     }

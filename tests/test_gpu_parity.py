@@ -221,7 +221,7 @@ def test_spmv_on_workloads():
 def test_large_configs_by_residual():
     """BASELINE.json sizes, checked through size-independent properties: residual of the
     unperturbed K, feasibility of the projection (A_W P r = 0), idempotence P(P r) = P r."""
-    for p in (problems.config(2), problems.config(1)):
+    for p in (problems.config(2), problems.config(1), problems.poisson_control(32, 3, name="config4_poisson3d_g32")):
         cp, ri, v = p.kkt_lower()
         f = Fact()
         f.set_matrix(p.N, cp, ri, v)
