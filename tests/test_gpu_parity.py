@@ -269,3 +269,27 @@ def test_drop_in_through_reference_code():
             assert np.abs(a - b).max() <= SOL_TOL * max(1.0, np.abs(b).max()), (p.name, kind)
     ours.release()
     theirs.release()
+
+
+@pytest.mark.parametrize("eps", [1e-3, 1e-5])
+def test_nearly_dependent_rows_use_refinement(eps):
+    """A working-set row that is a 1 + eps copy of another one: the Schur pivots lose ~eps^2 of relative accuracy,
+    iterative refinement against the unperturbed K restores the 1e-10 residual."""
+    base = problems.chain_rosenbrock(400, 0.1, seed=3)
+    rng = np.random.default_rng(1)
+    r10 = base.J.tocsr()[10].toarray().ravel()
+    new = r10 + eps * rng.standard_normal(base.n) * (r10 != 0)
+    J2 = sp.vstack([base.J.tocsr(), sp.csr_matrix(new)]).tocsc()
+    J2.sort_indices()
+    p = problems.KKTProblem(name="ill", n=base.n, m=base.m + 1, J=J2, H=base.H, active_vars=base.active_vars, active_cons=np.arange(base.m + 1))
+    f = Fact()
+    f.set_matrix(p.N, *p.kkt_lower())
+    assert f.stats()["refine_steps"] >= 1
+    assert f.cond() > 1e6
+    K = p.kkt_full()
+    for kind in KINDS:
+        idx, val = p.rhs(kind, 2)
+        f.solve(idx, val, p.N)
+        x = f.solution_dense(0, p.N)
+        b = orc.vec_to_raw(idx, val, p.N)
+        assert np.linalg.norm(K @ x - b) <= RES_TOL * np.linalg.norm(b), kind
