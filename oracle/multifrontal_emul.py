@@ -157,7 +157,7 @@ class Emulated:
                 W[int(p["Wptr"][T]) + rows[~top]] = out[~top]
         for lv in range(int(p["n_levels"]) - 1, -1, -1):
             for T, col0, ncols in p["bwd_tasks"][int(p["bwd_ptr"][lv]) : int(p["bwd_ptr"][lv + 1]), :3]:
-                T, col0, ncols = int(T), int(col0), int(ncols)
+                T, col0, ncols = int(T), int(col0), abs(int(ncols))  # negative: tall-front variant, same math
                 f, k, r, h = self._geom(T)
                 rows = p["Ridx"][int(p["Rptr"][T]) : int(p["Rptr"][T + 1])]
                 M = self.mpanel(T)

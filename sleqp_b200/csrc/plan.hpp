@@ -80,13 +80,13 @@ struct TrTask
 // load (the task) instead of two (task -> supernode record).
 struct FwdTask
 {
-  int sn, row0, nrows, first, k, pad;
+  int sn, row0, nrows, first, k, wide; // wide: all warps of the CTA share each row (fronts with many columns)
   long long Lptr, Rptr;
 };
 
 struct BwdTask
 {
-  int sn, col0, ncols, first, k, h;
+  int sn, col0, ncols, first, k, h; // ncols < 0: tall front, the CTA's warps share each of its -ncols columns
   long long Lptr, Rptr;
 };
 

@@ -281,12 +281,103 @@ fwd_body(const FwdTask& t, const int* __restrict__ Ridx, const double* __restric
   }
 }
 
+// Wide fronts (k >= 512): the CTA owns RG rows and its four warps split the columns of each of them, so a CTA
+// needs at most two rounds of loads; b_T is not staged, yacc is read directly (it is L2-resident: every CTA of
+// the supernode reads the same k values).
+template <int RG>
+__device__ __forceinline__ void
+fwd_wide(const FwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mr, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf, double* red)
+{
+  constexpr int U  = 8 / RG;
+  constexpr int NW = SOLVE_THREADS / 32;
+  const int k      = t.k;
+  const double* P  = Mr + t.Lptr;
+  const double* bT = yacc + t.first;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nvalid = min(RG, t.nrows);
+  const int r0     = t.row0;
+  const int rlast  = r0 + nvalid - 1;
+  const int jend   = rlast < k ? rlast + 1 : k;
+  double acc[RG];
+#pragma unroll
+  for (int a = 0; a < RG; ++a)
+  {
+    acc[a] = 0.0;
+  }
+  for (int j0 = 0; j0 < jend; j0 += SOLVE_THREADS * U)
+  {
+    double pv[RG][U], bv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const int j = j0 + u * SOLVE_THREADS + tid;
+      bv[u]       = j < jend ? bT[j] : 0.0;
+#pragma unroll
+      for (int a = 0; a < RG; ++a)
+      {
+        pv[a][u] = (a < nvalid && j < jend) ? P[(long long)(r0 + a) * k + j] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int a = 0; a < RG; ++a)
+      {
+        acc[a] += pv[a][u] * bv[u];
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < RG; ++a)
+  {
+    double v = acc[a];
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    if (lane == 0)
+    {
+      red[a * NW + warp] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < nvalid)
+  {
+    double mine = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+    {
+      mine += red[tid * NW + w];
+    }
+    const int r = r0 + tid;
+    if (r < k)
+    {
+      yf[t.first + r] = mine * Dinv[t.first + r];
+    }
+    else
+    {
+      atomicAdd(yacc + Ridx[t.Rptr + r - k], mine);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(SOLVE_THREADS)
 k_fwd_chunk(const FwdTask* __restrict__ tasks, const int* __restrict__ Ridx, const double* __restrict__ Mr, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf)
 {
   extern __shared__ double bT[];
   const FwdTask t  = tasks[blockIdx.x];
   constexpr int NW = SOLVE_THREADS / 32;
+  if (t.wide)
+  {
+    if (t.nrows == 1)
+    {
+      fwd_wide<1>(t, Ridx, Mr, Dinv, yacc, yf, bT);
+    }
+    else
+    {
+      fwd_wide<2>(t, Ridx, Mr, Dinv, yacc, yf, bT);
+    }
+    return;
+  }
   const int rg     = (t.nrows + NW - 1) / NW; // rows per warp: 1..4
   if (rg == 1)
   {
@@ -433,6 +524,81 @@ bwd_body(const BwdTask& t,
   }
 }
 
+// Tall fronts (h >= 512): the CTA owns CG columns and its four warps split the rows of each of them; the input
+// vector is not staged: v_i = y_i (top block, already D^-1 y) or x[rows_i] is gathered alongside the panel loads.
+template <int CG>
+__device__ __forceinline__ void
+bwd_tall(const BwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ y, double* __restrict__ x, double* red)
+{
+  constexpr int U  = 8 / CG;
+  constexpr int NW = SOLVE_THREADS / 32;
+  const int k = t.k, h = t.h;
+  const double* P = Mt + t.Lptr;
+  const int* rows = Ridx + t.Rptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nvalid = min(CG, -t.ncols);
+  const int j0     = t.col0;
+  double acc[CG];
+#pragma unroll
+  for (int c = 0; c < CG; ++c)
+  {
+    acc[c] = 0.0;
+  }
+  for (int i0 = j0; i0 < h; i0 += SOLVE_THREADS * U)
+  {
+    int src[U];
+    double pv[CG][U], vv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const int i = i0 + u * SOLVE_THREADS + tid;
+      src[u]      = i < k ? t.first + i : (i < h ? rows[i - k] : 0);
+#pragma unroll
+      for (int c = 0; c < CG; ++c)
+      {
+        pv[c][u] = (c < nvalid && i < h) ? P[(long long)(j0 + c) * h + i] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+    {
+      const int i = i0 + u * SOLVE_THREADS + tid;
+      vv[u]       = i < k ? y[src[u]] : (i < h ? x[src[u]] : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int c = 0; c < CG; ++c)
+      {
+        acc[c] += pv[c][u] * vv[u];
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < CG; ++c)
+  {
+    double v = acc[c];
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    if (lane == 0)
+    {
+      red[c * NW + warp] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < nvalid)
+  {
+    double mine = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+    {
+      mine += red[tid * NW + w];
+    }
+    x[t.first + j0 + tid] = mine;
+  }
+}
+
 __global__ void __launch_bounds__(SOLVE_THREADS)
 k_bwd_chunk(const BwdTask* __restrict__ tasks,
             const int* __restrict__ Ridx,
@@ -444,6 +610,18 @@ k_bwd_chunk(const BwdTask* __restrict__ tasks,
   extern __shared__ double v[];
   const BwdTask t  = tasks[blockIdx.x];
   constexpr int NW = SOLVE_THREADS / 32;
+  if (t.ncols < 0)
+  {
+    if (t.ncols == -1)
+    {
+      bwd_tall<1>(t, Ridx, Mt, y, x, v);
+    }
+    else
+    {
+      bwd_tall<2>(t, Ridx, Mt, y, x, v);
+    }
+    return;
+  }
   const int cg     = (t.ncols + NW - 1) / NW; // columns per warp: 1..4
   if (cg == 1)
   {
@@ -467,6 +645,18 @@ __device__ __forceinline__ void
 fwd_dispatch(const FwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mr, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf, double* bT)
 {
   constexpr int NW = SOLVE_THREADS / 32;
+  if (t.wide)
+  {
+    if (t.nrows == 1)
+    {
+      fwd_wide<1>(t, Ridx, Mr, Dinv, yacc, yf, bT);
+    }
+    else
+    {
+      fwd_wide<2>(t, Ridx, Mr, Dinv, yacc, yf, bT);
+    }
+    return;
+  }
   const int rg     = (t.nrows + NW - 1) / NW;
   if (rg == 1)
   {
@@ -490,6 +680,18 @@ __device__ __forceinline__ void
 bwd_dispatch(const BwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ D, const double* __restrict__ y, double* __restrict__ x, double* v)
 {
   constexpr int NW = SOLVE_THREADS / 32;
+  if (t.ncols < 0)
+  {
+    if (t.ncols == -1)
+    {
+      bwd_tall<1>(t, Ridx, Mt, y, x, v);
+    }
+    else
+    {
+      bwd_tall<2>(t, Ridx, Mt, y, x, v);
+    }
+    return;
+  }
   const int cg_    = (t.ncols + NW - 1) / NW;
   if (cg_ == 1)
   {

@@ -1558,18 +1558,34 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         P.lvl_maxh[l] = std::max(P.lvl_maxh[l], h);
         // a warp works on up to 4 rows at once (8 for narrow supernodes: few columns, so more rows keep the
         // loads in flight and the leaf levels need half the CTAs)
-        int nrows = k <= 64 ? 32 : (k > 1024 ? 16 : std::min(16, std::max(4, (4096 + k - 1) / k)));
+        int nrows = k <= 64 ? 32 : std::min(16, std::max(4, (4096 + k - 1) / k));
         nrows     = (nrows + 3) & ~3;
+        // wide fronts: one or two rows per CTA, the four warps split the columns (<= 2 rounds of loads per CTA
+        // instead of k / 256), the right-hand side is read straight from the accumulator
+        const int wide = k >= 512 ? 1 : 0;
+        if (wide)
+        {
+          nrows = k >= 1024 ? 1 : 2;
+        }
         for (int row0 = 0; row0 < h; row0 += nrows)
         {
-          P.fwd_tasks.push_back({T, row0, std::min(nrows, h - row0), P.sn_first[T], k, 0, P.Lptr[T], P.Rptr[T]});
+          P.fwd_tasks.push_back({T, row0, std::min(nrows, h - row0), P.sn_first[T], k, wide, P.Lptr[T], P.Rptr[T]});
         }
         // a warp works on up to 4 columns at once (8 per warp was measured slower for the short fronts)
         int ncols = std::min(16, std::max(4, (4096 + h - 1) / h));
         ncols     = (ncols + 3) & ~3;
+        // tall fronts: one or two columns per CTA, the four warps split the rows (<= 2 rounds of loads per CTA)
+        // (measured on B200: no gain at config 2, 20 % slower at 3D g=48 -- the input vector is then gathered once per
+        // column instead of once per 4 columns -- so the tall variant stays off)
+        const bool tall = false;
+        if (tall)
+        {
+          ncols = h >= 1024 ? 1 : 2;
+        }
         for (int col0 = 0; col0 < k; col0 += ncols)
         {
-          P.bwd_tasks.push_back({T, col0, std::min(ncols, k - col0), P.sn_first[T], k, h, P.Lptr[T], P.Rptr[T]});
+          const int nc = std::min(ncols, k - col0);
+          P.bwd_tasks.push_back({T, col0, tall ? -nc : nc, P.sn_first[T], k, h, P.Lptr[T], P.Rptr[T]});
         }
       }
       P.fwd_ptr[l + 1] = (int)P.fwd_tasks.size();
