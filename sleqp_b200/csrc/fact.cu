@@ -378,6 +378,12 @@ b200_fact_set_matrix(b200_fact* F, int n_rows, int n_cols, int nnz, const int* c
     {
       return rc;
     }
+    if ((size_t)plan->max_front * sizeof(double) > 160 * 1024)
+    {
+      return set_error(B200_ERR_UNSUPPORTED,
+                       "largest front has " + std::to_string(plan->max_front) +
+                         " rows; the backward sweep stages one front vector in shared memory (limit 20480 rows)");
+    }
     F->symbolic_cached = cached;
     F->ms_symbolic     = cached ? 0.0 : plan->ms_symbolic;
     if (F->dp.plan != plan)

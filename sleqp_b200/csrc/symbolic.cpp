@@ -12,9 +12,15 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <numeric>
+#include <thread>
 
 namespace b200
 {
@@ -99,6 +105,8 @@ hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double*
 
 // ---------------------------------------------------------------------------------------
 // Nested dissection on rooted level structures (George 1973; George & Liu 1978).
+// Subproblems are independent once split, so they are processed by a small pool of host threads
+// (the analysis is on the critical path of every set_matrix with a new working set).
 // ---------------------------------------------------------------------------------------
 namespace
 {
@@ -110,45 +118,61 @@ struct Graph
   const std::vector<int>& adj;
 };
 
-struct NDWork
+// Node-indexed scratch shared by all threads (they work on disjoint node sets; `tag` is also read for
+// neighbours that belong to other subproblems, hence atomic with relaxed ordering) ...
+struct NDShared
 {
-  std::vector<int> tag;   // subproblem id a node currently belongs to
-  std::vector<int> level; // BFS level
-  std::vector<int> seen;  // BFS visit stamp
+  std::vector<std::atomic<int>> tag; // subproblem id a node currently belongs to
+  std::vector<int> level;            // BFS level
+  std::vector<int> seen;             // BFS visit stamp
+  std::atomic<int> next_id{1};
+  std::atomic<int> next_stamp{1};
+  explicit NDShared(int m) : tag(m), level(m, 0), seen(m, 0)
+  {
+    for (auto& t : tag)
+    {
+      t.store(0, std::memory_order_relaxed);
+    }
+  }
+};
+
+// ... and per-thread scratch
+struct NDLocal
+{
   std::vector<int> queue;
-  int stamp = 0;
+  std::vector<int> level_ptr, lp2;
 };
 
 // BFS restricted to nodes with tag == id, starting from root. Returns number of levels; fills
-// w.queue with the visit order (first `count` entries) and w.level.
+// loc.queue with the visit order (first `count` entries) and sh.level.
 static int
-bfs(const Graph& g, NDWork& w, int root, int id, int& count, std::vector<int>& level_ptr)
+bfs(const Graph& g, NDShared& sh, NDLocal& loc, int root, int id, int& count, std::vector<int>& level_ptr)
 {
-  ++w.stamp;
+  const int stamp = sh.next_stamp.fetch_add(1, std::memory_order_relaxed);
   int head = 0, tail = 0;
-  w.queue[tail++] = root;
-  w.seen[root]    = w.stamp;
-  w.level[root]   = 0;
+  loc.queue[tail++] = root;
+  sh.seen[root]     = stamp;
+  sh.level[root]    = 0;
   level_ptr.clear();
   level_ptr.push_back(0);
   int cur_level = 0;
   while (head < tail)
   {
-    int v = w.queue[head];
-    if (w.level[v] != cur_level)
+    int v = loc.queue[head];
+    if (sh.level[v] != cur_level)
     {
-      cur_level = w.level[v];
+      cur_level = sh.level[v];
       level_ptr.push_back(head);
     }
     ++head;
     for (int p = g.xadj[v]; p < g.xadj[v + 1]; ++p)
     {
       int u = g.adj[p];
-      if (w.tag[u] == id && w.seen[u] != w.stamp)
+      if (sh.tag[u].load(std::memory_order_relaxed) == id && sh.seen[u] != stamp)
       {
-        w.seen[u]       = w.stamp;
-        w.level[u]      = cur_level + 1;
-        w.queue[tail++] = u;
+        sh.seen[u]        = stamp;
+        sh.level[u]       = cur_level + 1;
+        loc.queue[tail++] = u;
       }
     }
   }
@@ -164,20 +188,231 @@ struct Sub
   bool connected;
 };
 
+// Processes one subproblem: writes final positions into perm, appends the children to `out`.
+static void
+nd_step(const Graph& g, NDShared& sh, NDLocal& loc, Sub sub, int leaf_size, std::vector<int>& perm, std::vector<Sub>& out)
+{
+  const int ns = (int)sub.nodes.size();
+  if (ns == 0)
+  {
+    return;
+  }
+  const int id = sh.next_id.fetch_add(1, std::memory_order_relaxed);
+  for (int v : sub.nodes)
+  {
+    sh.tag[v].store(id, std::memory_order_relaxed);
+  }
+  std::vector<int>& level_ptr = loc.level_ptr;
+
+  if (!sub.connected)
+  {
+    // split into connected components; each gets a consecutive range. Nodes already taken get tag -id.
+    int lo = sub.lo;
+    std::vector<Sub> comps;
+    for (int v : sub.nodes)
+    {
+      if (sh.tag[v].load(std::memory_order_relaxed) != id)
+      {
+        continue;
+      }
+      int cnt;
+      bfs(g, sh, loc, v, id, cnt, level_ptr);
+      Sub c;
+      c.nodes.assign(loc.queue.begin(), loc.queue.begin() + cnt);
+      c.connected = true;
+      c.lo        = lo;
+      lo += cnt;
+      for (int u : c.nodes)
+      {
+        sh.tag[u].store(-id, std::memory_order_relaxed);
+      }
+      comps.push_back(std::move(c));
+    }
+    if (comps.size() == 1)
+    {
+      sub = std::move(comps[0]);
+      for (int u : sub.nodes)
+      {
+        sh.tag[u].store(id, std::memory_order_relaxed);
+      }
+    }
+    else
+    {
+      for (auto& c : comps)
+      {
+        if ((int)c.nodes.size() <= leaf_size)
+        {
+          for (size_t i = 0; i < c.nodes.size(); ++i)
+          {
+            perm[c.lo + (int)i] = c.nodes[i]; // BFS order
+          }
+        }
+        else
+        {
+          out.push_back(std::move(c));
+        }
+      }
+      return;
+    }
+  }
+
+  // connected subgraph
+  if (ns <= leaf_size)
+  {
+    int cnt;
+    bfs(g, sh, loc, sub.nodes[0], id, cnt, level_ptr);
+    for (int i = 0; i < cnt; ++i)
+    {
+      perm[sub.lo + i] = loc.queue[i];
+    }
+    return;
+  }
+
+  // pseudo-peripheral root
+  int root = sub.nodes[0];
+  int cnt;
+  int nlev = bfs(g, sh, loc, root, id, cnt, level_ptr);
+  for (int iter = 0; iter < 3; ++iter)
+  {
+    // pick a minimum-degree node of the last level
+    int best = -1, bestdeg = 0x7fffffff;
+    for (int q = level_ptr[nlev - 1]; q < level_ptr[nlev]; ++q)
+    {
+      int v   = loc.queue[q];
+      int deg = g.xadj[v + 1] - g.xadj[v];
+      if (deg < bestdeg)
+      {
+        bestdeg = deg;
+        best    = v;
+      }
+    }
+    int cnt2;
+    int nlev2 = bfs(g, sh, loc, best, id, cnt2, loc.lp2);
+    if (nlev2 > nlev)
+    {
+      root      = best;
+      nlev      = nlev2;
+      level_ptr = loc.lp2;
+      cnt       = cnt2;
+    }
+    else
+    {
+      // restore the level structure of `root`
+      nlev = bfs(g, sh, loc, root, id, cnt, level_ptr);
+      break;
+    }
+  }
+
+  if (nlev < 3)
+  {
+    // no interior level: cannot be separated by a level set; emit as one block
+    for (int i = 0; i < cnt; ++i)
+    {
+      perm[sub.lo + i] = loc.queue[i];
+    }
+    return;
+  }
+
+  // choose the separator level: smallest level among the balanced ones
+  int s = -1;
+  {
+    const double lo_frac = 0.3;
+    int best_size        = 0x7fffffff;
+    int median_level     = 1;
+    for (int l = 0; l < nlev; ++l)
+    {
+      if (level_ptr[l] <= ns / 2 && ns / 2 < level_ptr[l + 1])
+      {
+        median_level = l;
+      }
+    }
+    median_level = std::min(std::max(median_level, 1), nlev - 2);
+    for (int l = 1; l <= nlev - 2; ++l)
+    {
+      int below = level_ptr[l];
+      int above = ns - level_ptr[l + 1];
+      if (below >= lo_frac * ns && above >= lo_frac * ns)
+      {
+        int size = level_ptr[l + 1] - level_ptr[l];
+        if (size < best_size || (size == best_size && std::abs(l - median_level) < std::abs(s - median_level)))
+        {
+          best_size = size;
+          s         = l;
+        }
+      }
+    }
+    if (s < 0)
+    {
+      s = median_level;
+    }
+  }
+
+  // thin the separator: level-s nodes without a neighbour in level s+1 join part A
+  Sub A, B;
+  std::vector<int> sep;
+  A.nodes.reserve((size_t)level_ptr[s + 1]);
+  B.nodes.reserve((size_t)(cnt - level_ptr[s + 1]));
+  for (int q = 0; q < level_ptr[s]; ++q)
+  {
+    A.nodes.push_back(loc.queue[q]);
+  }
+  for (int q = level_ptr[s]; q < level_ptr[s + 1]; ++q)
+  {
+    int v         = loc.queue[q];
+    bool touchesB = false;
+    for (int p = g.xadj[v]; p < g.xadj[v + 1] && !touchesB; ++p)
+    {
+      int u = g.adj[p];
+      if (sh.tag[u].load(std::memory_order_relaxed) == id && sh.level[u] == s + 1)
+      {
+        touchesB = true;
+      }
+    }
+    if (touchesB)
+    {
+      sep.push_back(v);
+    }
+    else
+    {
+      A.nodes.push_back(v);
+    }
+  }
+  for (int q = level_ptr[s + 1]; q < cnt; ++q)
+  {
+    B.nodes.push_back(loc.queue[q]);
+  }
+  // separator last
+  const int hi = sub.lo + ns;
+  for (size_t i = 0; i < sep.size(); ++i)
+  {
+    perm[hi - (int)sep.size() + (int)i] = sep[i];
+  }
+  A.lo        = sub.lo;
+  A.connected = false; // (levels < s are connected through the BFS tree, but the thinned-in nodes may not be)
+  B.lo        = sub.lo + (int)A.nodes.size();
+  B.connected = false;
+  out.push_back(std::move(A));
+  out.push_back(std::move(B));
+}
+
 } // namespace
 
 static void
 nested_dissection(int m, const std::vector<int>& xadj, const std::vector<int>& adj, int leaf_size, std::vector<int>& perm)
 {
   Graph g{m, xadj, adj};
-  NDWork w;
-  w.tag.assign(m, 0);
-  w.level.assign(m, 0);
-  w.seen.assign(m, 0);
-  w.queue.assign(m, 0);
+  NDShared sh(m);
   perm.assign(m, -1);
-
+  if (m == 0)
+  {
+    return;
+  }
+  // deterministic result: every subproblem's outcome depends only on its node list (ids/stamps are just
+  // unique labels), whatever thread handles it
+  std::mutex mu;
+  std::condition_variable cv;
   std::vector<Sub> stack;
+  int in_flight = 0;
   {
     Sub root;
     root.nodes.resize(m);
@@ -186,219 +421,60 @@ nested_dissection(int m, const std::vector<int>& xadj, const std::vector<int>& a
     root.connected = false;
     stack.push_back(std::move(root));
   }
-  int next_id = 1;
-  std::vector<int> level_ptr;
-
-  while (!stack.empty())
+  unsigned hw        = std::thread::hardware_concurrency();
+  const int nthreads = m < 20000 ? 1 : (int)std::min<unsigned>(8, std::max<unsigned>(1, hw));
+  std::atomic<int> tcount{0};
+  auto worker = [&]() {
+    NDLocal loc;
+    loc.queue.assign(m, 0);
+    std::vector<Sub> out;
+    long done = 0, nodes_done = 0;
+    const int me = tcount.fetch_add(1);
+    struct Report { long& d; long& n; int me; ~Report() { if (std::getenv("B200_SYM_TRACE")) std::fprintf(stderr, "[b200 nd] thread %d: %ld subproblems, %ld nodes\n", me, d, n); } } report{done, nodes_done, me};
+    for (;;)
+    {
+      Sub sub;
+      {
+        std::unique_lock<std::mutex> lock(mu);
+        cv.wait(lock, [&] { return !stack.empty() || in_flight == 0; });
+        if (stack.empty())
+        {
+          return; // nothing queued and nothing running: done
+        }
+        sub = std::move(stack.back());
+        stack.pop_back();
+        ++in_flight;
+      }
+      out.clear();
+      ++done;
+      nodes_done += (long)sub.nodes.size();
+      nd_step(g, sh, loc, std::move(sub), leaf_size, perm, out);
+      {
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto& c : out)
+        {
+          stack.push_back(std::move(c));
+        }
+        --in_flight;
+      }
+      cv.notify_all();
+    }
+  };
+  if (nthreads == 1)
   {
-    Sub sub = std::move(stack.back());
-    stack.pop_back();
-    const int ns = (int)sub.nodes.size();
-    if (ns == 0)
+    worker();
+  }
+  else
+  {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
     {
-      continue;
+      pool.emplace_back(worker);
     }
-    const int id = next_id++;
-    for (int v : sub.nodes)
+    for (auto& t : pool)
     {
-      w.tag[v] = id;
+      t.join();
     }
-
-    if (!sub.connected)
-    {
-      // split into connected components; each gets a consecutive range
-      int lo = sub.lo;
-      ++w.stamp;
-      const int comp_stamp = w.stamp;
-      std::vector<int> comp_mark; // reuse seen[] through separate BFS calls: need own marker
-      // We cannot use w.seen across bfs() calls (stamp changes), so keep a local flag array
-      // indexed by position in sub.nodes via tag trick: move processed nodes to tag = -id.
-      (void)comp_stamp;
-      std::vector<Sub> comps;
-      for (int v : sub.nodes)
-      {
-        if (w.tag[v] != id)
-        {
-          continue;
-        }
-        int cnt;
-        bfs(g, w, v, id, cnt, level_ptr);
-        Sub c;
-        c.nodes.assign(w.queue.begin(), w.queue.begin() + cnt);
-        c.connected = true;
-        c.lo        = lo;
-        lo += cnt;
-        for (int u : c.nodes)
-        {
-          w.tag[u] = -id; // taken
-        }
-        comps.push_back(std::move(c));
-      }
-      if (comps.size() == 1)
-      {
-        // re-tag and fall through to the connected case
-        sub = std::move(comps[0]);
-        for (int u : sub.nodes)
-        {
-          w.tag[u] = id;
-        }
-      }
-      else
-      {
-        for (auto& c : comps)
-        {
-          if ((int)c.nodes.size() <= leaf_size)
-          {
-            for (size_t i = 0; i < c.nodes.size(); ++i)
-            {
-              perm[c.lo + (int)i] = c.nodes[i]; // BFS order
-            }
-          }
-          else
-          {
-            stack.push_back(std::move(c));
-          }
-        }
-        continue;
-      }
-    }
-
-    // connected subgraph
-    if (ns <= leaf_size)
-    {
-      int cnt;
-      bfs(g, w, sub.nodes[0], id, cnt, level_ptr);
-      for (int i = 0; i < cnt; ++i)
-      {
-        perm[sub.lo + i] = w.queue[i];
-      }
-      continue;
-    }
-
-    // pseudo-peripheral root
-    int root = sub.nodes[0];
-    int cnt;
-    int nlev = bfs(g, w, root, id, cnt, level_ptr);
-    for (int iter = 0; iter < 6; ++iter)
-    {
-      // pick a minimum-degree node of the last level
-      int best = -1, bestdeg = 0x7fffffff;
-      for (int q = level_ptr[nlev - 1]; q < level_ptr[nlev]; ++q)
-      {
-        int v   = w.queue[q];
-        int deg = g.xadj[v + 1] - g.xadj[v];
-        if (deg < bestdeg)
-        {
-          bestdeg = deg;
-          best    = v;
-        }
-      }
-      std::vector<int> lp2;
-      int cnt2;
-      int nlev2 = bfs(g, w, best, id, cnt2, lp2);
-      if (nlev2 > nlev)
-      {
-        root      = best;
-        nlev      = nlev2;
-        level_ptr = lp2;
-        cnt       = cnt2;
-      }
-      else
-      {
-        // restore the level structure of `root`
-        nlev = bfs(g, w, root, id, cnt, level_ptr);
-        break;
-      }
-    }
-
-    if (nlev < 3)
-    {
-      // no interior level: cannot be separated by a level set; emit as one block
-      for (int i = 0; i < cnt; ++i)
-      {
-        perm[sub.lo + i] = w.queue[i];
-      }
-      continue;
-    }
-
-    // choose the separator level: smallest level among the balanced ones
-    int s = -1;
-    {
-      const double lo_frac = 0.3;
-      int best_size        = 0x7fffffff;
-      int median_level     = 1;
-      for (int l = 0; l < nlev; ++l)
-      {
-        if (level_ptr[l] <= ns / 2 && ns / 2 < level_ptr[l + 1])
-        {
-          median_level = l;
-        }
-      }
-      median_level = std::min(std::max(median_level, 1), nlev - 2);
-      for (int l = 1; l <= nlev - 2; ++l)
-      {
-        int below = level_ptr[l];
-        int above = ns - level_ptr[l + 1];
-        if (below >= lo_frac * ns && above >= lo_frac * ns)
-        {
-          int size = level_ptr[l + 1] - level_ptr[l];
-          if (size < best_size || (size == best_size && std::abs(l - median_level) < std::abs(s - median_level)))
-          {
-            best_size = size;
-            s         = l;
-          }
-        }
-      }
-      if (s < 0)
-      {
-        s = median_level;
-      }
-    }
-
-    // thin the separator: level-s nodes without a neighbour in level s+1 join part A
-    Sub A, B;
-    std::vector<int> sep;
-    for (int q = 0; q < level_ptr[s]; ++q)
-    {
-      A.nodes.push_back(w.queue[q]);
-    }
-    for (int q = level_ptr[s]; q < level_ptr[s + 1]; ++q)
-    {
-      int v         = w.queue[q];
-      bool touchesB = false;
-      for (int p = g.xadj[v]; p < g.xadj[v + 1] && !touchesB; ++p)
-      {
-        int u = g.adj[p];
-        if (w.tag[u] == id && w.level[u] == s + 1)
-        {
-          touchesB = true;
-        }
-      }
-      if (touchesB)
-      {
-        sep.push_back(v);
-      }
-      else
-      {
-        A.nodes.push_back(v);
-      }
-    }
-    for (int q = level_ptr[s + 1]; q < cnt; ++q)
-    {
-      B.nodes.push_back(w.queue[q]);
-    }
-    // separator last
-    const int hi = sub.lo + ns;
-    for (size_t i = 0; i < sep.size(); ++i)
-    {
-      perm[hi - (int)sep.size() + (int)i] = sep[i];
-    }
-    A.lo        = sub.lo;
-    A.connected = false;
-    B.lo        = sub.lo + (int)A.nodes.size();
-    B.connected = false;
-    stack.push_back(std::move(A));
-    stack.push_back(std::move(B));
   }
 }
 
@@ -415,6 +491,16 @@ int
 analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only, Plan& P, std::string& err)
 {
   auto t0 = std::chrono::steady_clock::now();
+  auto t_last = t0;
+  const bool trace = std::getenv("B200_SYM_TRACE") != nullptr;
+  auto tick = [&](const char* what) {
+    if (trace)
+    {
+      auto now = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[b200 symbolic] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+      t_last = now;
+    }
+  };
   if (n < 0 || nnz < 0 || !colptr || (nnz > 0 && (!rowidx || !val)))
   {
     return fail(err, B200_ERR_ARG, "null or negative-sized input");
@@ -526,7 +612,13 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
   // A by column (E), rows ascending
-  std::sort(Aent.begin(), Aent.end(), [](const Ent& x, const Ent& y) { return x.c != y.c ? x.c < y.c : x.r < y.r; });
+  {
+    auto less = [](const Ent& x, const Ent& y) { return x.c != y.c ? x.c < y.c : x.r < y.r; };
+    if (!std::is_sorted(Aent.begin(), Aent.end(), less)) // the reference layout (all A entries in variable columns) arrives sorted
+    {
+      std::sort(Aent.begin(), Aent.end(), less);
+    }
+  }
   const int nnzA = (int)Aent.size();
   P.Acsc_ptr.assign(nE + 1, 0);
   P.Acsc_row.resize(nnzA);
@@ -597,6 +689,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
 
+  tick("classify + split");
   // ---- adjacency of S = G - A D^-1 A^T (original R labels) -----------------------------
   {
     double work = 0;
@@ -646,6 +739,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
 
+  tick("S pattern");
   // ---- fill-reducing ordering -----------------------------------------------------------
   std::vector<int> perm0;
   nested_dissection(m, xadj, adj, /*leaf_size=*/24, perm0);
@@ -655,6 +749,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     pinv0[perm0[k]] = k;
   }
 
+  tick("nested dissection");
   // ---- elimination tree (Liu) -------------------------------------------------------------
   std::vector<int> parent0(m, -1);
   {
@@ -747,6 +842,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   }
   std::vector<int>().swap(adj);
 
+  tick("etree + postorder + relabel");
   // ---- column counts (Gilbert, Ng, Peyton 1994) ------------------------------------------------
   const std::vector<int>& parent = P.parent;
   P.colcount.assign(m, 0);
@@ -815,6 +911,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   }
   const std::vector<int>& cc = P.colcount;
 
+  tick("column counts");
   // ---- supernodes: dense leaf subtrees + fundamental + relaxed chains -----------------------------
   std::vector<int> blk(m, -1);
   {
@@ -919,6 +1016,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
 
+  tick("supernodes");
   // ---- row structures ---------------------------------------------------------------------------------
   P.Rptr.assign(ns + 1, 0);
   P.Ridx.clear();
@@ -1008,6 +1106,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
 
+  tick("row structures + rel");
   // ---- storage offsets, levels, statistics ---------------------------------------------------------
   P.Lptr.assign(ns + 1, 0);
   P.Wptr.assign(ns + 1, 0);
@@ -1064,6 +1163,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
 
+  tick("offsets + levels");
   // ---- assembly map of S into the panels ------------------------------------------------------------------
   {
     // lower pattern of S by column (new labels), rows ascending incl. diagonal
@@ -1137,9 +1237,11 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
     // product terms, two passes
     P.Sterm_ptr.assign((size_t)P.nnzS + 1, 0);
+    std::vector<i64> term_ids; // entry id of every product term, computed once in pass 0
     for (int pass = 0; pass < 2; ++pass)
     {
       std::vector<i64> fill;
+      size_t tq = 0;
       if (pass == 1)
       {
         for (i64 q = 0; q < P.nnzS; ++q)
@@ -1159,18 +1261,21 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
           int a = P.pinv[P.Acsc_row[s]];
           for (int t = P.Acsc_ptr[e]; t <= s; ++t)
           {
-            int b  = P.pinv[P.Acsc_row[t]];
-            i64 id = entry_id(std::max(a, b), std::min(a, b));
-            if (id < 0)
-            {
-              return fail(err, B200_ERR_ARG, "internal: product term missing from the S pattern");
-            }
+            i64 id;
             if (pass == 0)
             {
+              const int b = P.pinv[P.Acsc_row[t]];
+              id          = entry_id(std::max(a, b), std::min(a, b));
+              if (id < 0)
+              {
+                return fail(err, B200_ERR_ARG, "internal: product term missing from the S pattern");
+              }
+              term_ids.push_back(id);
               ++P.Sterm_ptr[id + 1];
             }
             else
             {
+              id = term_ids[tq++];
               i64 o        = fill[id]++;
               P.Sterm_a[o] = P.Acsc_src[s];
               P.Sterm_b[o] = P.Acsc_src[t];
@@ -1182,6 +1287,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
 
+  tick("assembly map");
   // ---- numeric schedule: stages of panel steps -------------------------------------------------------------
   P.sn_base.assign(ns, 0);
   P.sn_nt.assign(ns, 1);
@@ -1378,6 +1484,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
 
+  tick("stages + U alloc + tasks");
   // ---- selective inversion schedule ------------------------------------------------------------------------------
   // After the factorization every panel [L11; L21] is turned into Minv = [L11^-1; -L21 L11^-1], so that both
   // sweeps of a solve are plain matrix-vector products per supernode (Raghavan's selective inversion). L11^-1
@@ -1486,6 +1593,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
 
+  tick("inversion + transpose tasks");
   // ---- solve tasks: row chunks (forward) / column chunks (backward) of every supernode, per level ---------------
   {
     P.sn_ncol.assign(ns, 0);
@@ -1593,6 +1701,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
 
+  tick("solve tasks + contributors");
   // ---- hash of the full permutation -----------------------------------------------------------------------------
   {
     std::vector<int> fp(n);
