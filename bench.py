@@ -213,7 +213,7 @@ def run_reference(args, rank, world):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["p"].name, "N": p.N, "nnz_K": int(len(w["ri"])), "cg_iters": k, "solves_per_step": len(rhs)},
         "factor_ms": 1e3 * float(np.mean(fac)), "solve_ms": 1e3 * float(np.mean(sol)),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference" if ref is not None else "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -14,6 +14,8 @@
 //   k_inv_gemm      64x64 DMMA tiles of the triangular products of the selective inversion
 #include "numeric.cuh"
 
+#include <mutex>
+
 namespace b200
 {
 
@@ -721,12 +723,22 @@ k_transpose(const TrTask* __restrict__ tasks, const SnMeta* __restrict__ sn, con
 void
 configure_numeric_kernels()
 {
-  static bool done = false;
-  if (!done)
+  static std::once_flag once;
+  static std::string failure;
+  std::call_once(once, [] {
+    try
+    {
+      B200_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+      B200_CUDA(cudaFuncSetAttribute(k_inv_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+    }
+    catch (const CudaError& e)
+    {
+      failure = e.what();
+    }
+  });
+  if (!failure.empty())
   {
-    B200_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-    B200_CUDA(cudaFuncSetAttribute(k_inv_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-    done = true;
+    throw CudaError(failure);
   }
 }
 

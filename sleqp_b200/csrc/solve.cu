@@ -10,6 +10,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <mutex>
 #include <cstdlib>
 
 namespace cg = cooperative_groups;
@@ -1044,13 +1045,24 @@ residual(const DevPlan& dp, const NumericBuffers& nb, const double* rhs, const d
 void
 configure_solve_kernels()
 {
-  static bool done = false;
-  if (!done)
+  // once per process, thread-safe (handles are created concurrently by independent solver threads)
+  static std::once_flag once;
+  static std::string failure;
+  std::call_once(once, [] {
+    try
+    {
+      B200_CUDA(cudaFuncSetAttribute(k_fwd_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
+      B200_CUDA(cudaFuncSetAttribute(k_bwd_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
+      probe_cooperative();
+    }
+    catch (const CudaError& e)
+    {
+      failure = e.what();
+    }
+  });
+  if (!failure.empty())
   {
-    B200_CUDA(cudaFuncSetAttribute(k_fwd_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
-    B200_CUDA(cudaFuncSetAttribute(k_bwd_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
-    probe_cooperative();
-    done = true;
+    throw CudaError(failure);
   }
 }
 
