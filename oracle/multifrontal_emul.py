@@ -166,6 +166,61 @@ class Emulated:
                 x[f + col0 : f + col0 + ncols] = Mfull[:, col0 : col0 + ncols].T @ v
         return x
 
+    def solve_reduced_flow(self, b_new):
+        """The dataflow device solve (solve.cu k_fwd_flow / k_bwd_flow): warp tasks executed one at a time in ticket
+        order. Asserts what the kernels rely on: every counter a task waits for has already reached its target when
+        the tasks run sequentially in ticket order (=> no deadlock for any number of resident warps), every task is
+        covered by exactly one ticket, and the raw column-major inverse panels (no masking of the entries above the
+        diagonal) give the right answer."""
+        p = self.p
+        ns = int(p["n_supernodes"])
+        Ridx, Mt = p["Ridx"], self.Mt
+        Dinv = 1.0 / self.D
+
+        def fields(t):
+            lptr = int(np.array(t[0:2], dtype=np.int32).view(np.int64)[0])
+            return (lptr,) + tuple(int(v) for v in t[2:13])
+
+        def tickets(grp, n):
+            assert grp[0] == 0 and grp[-1] == n and np.all(np.diff(grp) > 0)
+            return [t for g in range(len(grp) - 1) for t in range(int(grp[g]), int(grp[g + 1]))]
+
+        yacc = np.array(b_new, dtype=np.float64)
+        yf = np.zeros(self.m)
+        x = np.zeros(self.m)
+        cnt = np.zeros(ns, dtype=np.int64)
+        tasks = p["ffl_tasks"]
+        for t in tickets(p["ffl_grp"], len(tasks)):
+            lptr, rptr, first, k, h, i0, i1, j0, j1, wait_idx, need, signal_idx = fields(tasks[t])
+            assert 0 < i1 - i0 <= 32 and 0 < j1 - j0 <= 16 and i1 <= h and j1 <= k
+            if wait_idx >= 0:
+                assert cnt[wait_idx] == need, "forward task claimed before its producers"
+            b = yacc[first + j0 : first + j1]
+            for r in range(i0, i1):
+                acc = sum(Mt[lptr + j * h + r] * b[j - j0] for j in range(j0, j1))
+                if r < k:
+                    yf[first + r] += acc * Dinv[first + r]
+                else:
+                    yacc[Ridx[rptr + r - k]] += acc
+            if signal_idx >= 0:
+                cnt[signal_idx] += 1
+        cnt[:] = 0
+        tasks = p["bfl_tasks"]
+        for t in tickets(p["bfl_grp"], len(tasks)):
+            lptr, rptr, first, k, h, i0, i1, j0, j1, wait_idx, need, signal_idx = fields(tasks[t])
+            assert 0 < j1 - j0 <= 8 and j1 <= k and j0 <= i0 < i1 <= h
+            if wait_idx >= 0:
+                assert cnt[wait_idx] == need, "backward task claimed before its producers"
+            else:
+                assert i1 <= k or int(p["sn_parent"][int(p["sn_of_col"][first])]) < 0
+            ii = np.arange(i0, i1)
+            v = np.where(ii < k, yf[np.minimum(first + ii, self.m - 1)], x[Ridx[rptr + np.maximum(ii - k, 0)]] if h > k else 0.0)
+            for j in range(j0, j1):
+                x[first + j] += Mt[lptr + j * h + ii] @ v
+            if signal_idx >= 0:
+                cnt[signal_idx] += 1
+        return x
+
     def _extend_add(self, c, jb):
         p = self.p
         par = int(p["sn_parent"][c])
@@ -307,7 +362,7 @@ class Emulated:
                 x[f : f + k] = np.linalg.solve(L11.T, t)
         return x
 
-    def solve(self, rhs, refine=1, minv=True):
+    def solve(self, rhs, refine=1, minv=True, flow=False):
         """Full K solve in original K indices, block elimination around the reduced system."""
         p, kv = self.p, self.kval
         ke, kr = p["k_of_e"], p["k_of_r"]
@@ -320,7 +375,7 @@ class Emulated:
         def once(b):
             t = b[ke] / dE
             bR = b[kr] - A @ t
-            lam_new = (self.solve_reduced_minv if minv else self.solve_reduced)(bR[p["perm"]])
+            lam_new = (self.solve_reduced_flow if flow else self.solve_reduced_minv if minv else self.solve_reduced)(bR[p["perm"]])
             lam = np.empty(self.m)
             lam[p["perm"]] = lam_new
             z = np.empty(self.N)

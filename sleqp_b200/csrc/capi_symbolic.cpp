@@ -237,6 +237,8 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
   FIELD(fwd_ptr)
   FIELD(bwd_ptr)
   FIELD(lvl_maxh)
+  FIELD(ffl_grp)
+  FIELD(bfl_grp)
 #undef FIELD
   if (f == "stages")
   {
@@ -266,6 +268,14 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
   if (f == "bwd_tasks")
   {
     return export_vec(P.bwd_tasks, out, count);
+  }
+  if (f == "ffl_tasks")
+  {
+    return export_vec(P.ffl_tasks, out, count);
+  }
+  if (f == "bfl_tasks")
+  {
+    return export_vec(P.bfl_tasks, out, count);
   }
   if (f == "upd_tasks")
   {

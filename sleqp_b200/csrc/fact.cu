@@ -48,7 +48,7 @@ struct b200_fact
   DevBuf<int> nper;
   // solve
   DevBuf<double> rhs, z, res, dz, bR, y, yf, x, W;
-  DevBuf<int> rhs_idx;
+  DevBuf<int> rhs_idx, flow;
   DevBuf<double> rhs_val;
   PinnedBuf<int> h_rhs_idx;
   PinnedBuf<double> h_rhs_val, h_sol, h_scal;
@@ -98,6 +98,7 @@ struct b200_fact
     sb.yf  = yf.p;
     sb.x   = x.p;
     sb.W   = W.p;
+    sb.flow = flow.p;
     return sb;
   }
   void drop_graphs()
@@ -210,6 +211,10 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   dp.fwd_ptr.upload(P.fwd_ptr, s);
   dp.bwd_ptr.upload(P.bwd_ptr, s);
   dp.bwd_tasks.upload(P.bwd_tasks, s);
+  dp.ffl_tasks.upload(P.ffl_tasks, s);
+  dp.bfl_tasks.upload(P.bfl_tasks, s);
+  dp.ffl_grp.upload(P.ffl_grp, s);
+  dp.bfl_grp.upload(P.bfl_grp, s);
   dp.k_of_e.upload(P.k_of_e, s);
   dp.k_of_r.upload(P.k_of_r, s);
   dp.pinv.upload(P.pinv, s);
@@ -251,6 +256,7 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   F->y.reserve(m + 8);
   F->yf.reserve(m + 8);
   F->x.reserve(m + 8);
+  F->flow.reserve(2 * (size_t)P.nsuper + 8);
   F->h_sol.reserve(N + 8);
   F->h_scal.reserve(8);
   F->h_nper.reserve(2);

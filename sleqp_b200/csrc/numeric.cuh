@@ -36,6 +36,7 @@ struct SolveBuffers
   double* yf;   // m, forward result (new labels)
   double* x;    // m, solution of the reduced system (new labels)
   double* W;    // front vectors (sum of front heights)
+  int* flow;    // dataflow sweeps: [0, ns) forward counters, [ns, 2 ns) backward counters, then the two ticket counters
 };
 
 // raise the dynamic shared-memory limit of the solve kernels (once per process, before capture)

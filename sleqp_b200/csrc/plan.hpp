@@ -90,6 +90,31 @@ struct BwdTask
   long long Lptr, Rptr;
 };
 
+// Warp task of the dataflow sweeps (solve.cu: k_fwd_flow / k_bwd_flow). One warp owns a block of a supernode's
+// column-major inverse panel: rows [i0, i1) x columns [j0, j1).
+//   forward : i1 - i0 <= 32 (one lane per row), j1 - j0 <= 16; partial sums are added to yf (top block rows) or
+//             pushed to their final rows of the accumulator (tail rows);
+//   backward: j1 - j0 <= 8 (eight columns in flight per lane), lanes stride the rows; partial sums are added to x.
+// Dependencies are counters, one per supernode: a task waits until cnt[wait_idx] >= need (wait_idx < 0: no wait)
+// and adds 1 to cnt[signal_idx] when its results are visible (signal_idx < 0: nobody waits for it).
+//   forward : wait on the own supernode (its children signal it), signal the parent;
+//   backward: wait on the parent (only tasks that touch tail rows), signal the own supernode.
+// Tasks are stored in topological order and handed out by a ticket counter in that order, so a waiting warp only
+// ever waits for tasks that are already claimed by running warps: no deadlock however few warps are resident.
+struct alignas(16) SweepTask
+{
+  long long Lptr; // panel offset (doubles)
+  int Rptr;       // offset of the supernode's update rows in Ridx
+  int first;      // first column (new labels)
+  int k, h;
+  int i0, i1;
+  int j0, j1;
+  int wait_idx, need;
+  int signal_idx;
+  int pad0, pad1, pad2;
+};
+static_assert(sizeof(SweepTask) == 64, "SweepTask layout");
+
 struct Stage
 {
   int zero_begin, zero_end;
@@ -168,6 +193,9 @@ struct Plan
   std::vector<BwdTask> bwd_tasks;
   std::vector<int> fwd_ptr, bwd_ptr; // per level ranges into the task arrays
   std::vector<int> lvl_maxh;
+  // dataflow sweeps: tasks in ticket order, ticket g covers tasks [grp[g], grp[g + 1])
+  std::vector<SweepTask> ffl_tasks, bfl_tasks;
+  std::vector<int> ffl_grp, bfl_grp;
 
   // statistics
   i64 nnzL = 0, nnzL_stored = 0;

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <string>
 #include <cstdlib>
 
 namespace cg = cooperative_groups;
@@ -638,6 +639,266 @@ k_bwd_chunk(const BwdTask* __restrict__ tasks,
   }
 }
 
+// ---- dataflow sweeps -----------------------------------------------------------------------------------------
+// One launch per sweep. Persistent warps draw tickets (groups of SweepTasks in topological order, plan.hpp) and
+// synchronise through per-supernode counters instead of kernel boundaries: the panel loads of a task are issued
+// BEFORE its warp waits for the producers, so along the critical path of the tree a level costs one counter poll
+// + one L2 round trip for the vector, not a kernel drain + launch + three DRAM round trips.
+// Both sweeps read the column-major inverse panels Mt.
+constexpr int FLOW_THREADS      = 256;
+constexpr int FLOW_CTAS_PER_SM  = 4;
+
+__device__ __forceinline__ int
+ld_acquire(const int* p)
+{
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// all lanes poll the same word (one request per poll); back off exponentially: far-away producers need no tight loop
+__device__ __forceinline__ void
+wait_counter(const int* cnt, int need)
+{
+  unsigned ns = 32;
+  while (ld_acquire(cnt) < need)
+  {
+    __nanosleep(ns);
+    if (ns < 512)
+    {
+      ns *= 2;
+    }
+  }
+}
+
+__device__ __forceinline__ void
+signal_counter(int* cnt, int lane)
+{
+  __threadfence(); // every lane: its own atomics are visible device-wide before the counter moves
+  __syncwarp();
+  if (lane == 0)
+  {
+    atomicAdd(cnt, 1);
+  }
+}
+
+// Forward task: rows [i0, i1) (lane = row), columns [j0, j1) with j1 - j0 <= 16.
+//   out_r = sum_j Mt[j * h + r] * b_j,   b = yacc[first + j]
+// bsh: 16 doubles of shared memory private to the warp (broadcast of b).
+__device__ __forceinline__ void
+fwd_flow_task(const SweepTask& T, int lane, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf, int* __restrict__ cnt, double* bsh)
+{
+  constexpr int FB = 16; // panel loads in flight per lane = the widest task (FWD_COLS in symbolic.cpp)
+  const int h      = T.h;
+  const int r      = T.i0 + lane;
+  const bool rv    = r < T.i1;
+  const int nc     = T.j1 - T.j0;
+  const double* P  = Mt + T.Lptr + (long long)T.j0 * h + (rv ? r : T.i0);
+  double pre[FB];
+#pragma unroll
+  for (int u = 0; u < FB; ++u)
+  {
+    pre[u] = (rv && u < nc) ? __ldg(P + (long long)u * h) : 0.0;
+  }
+  // destination of this lane's row (independent of the producers)
+  double* dst  = nullptr;
+  double scale = 1.0;
+  if (rv)
+  {
+    if (r < T.k)
+    {
+      dst   = yf + T.first + r;
+      scale = Dinv[T.first + r]; // D^-1 y: the diagonal solve is folded into the forward sweep
+    }
+    else
+    {
+      dst = yacc + Ridx[T.Rptr + r - T.k];
+    }
+  }
+  if (T.wait_idx >= 0)
+  {
+    wait_counter(cnt + T.wait_idx, T.need);
+  }
+  __syncwarp(); // the previous task's reads of bsh are done
+  if (lane < FB)
+  {
+    bsh[lane] = lane < nc ? __ldcg(yacc + T.first + T.j0 + lane) : 0.0;
+  }
+  __syncwarp();
+  double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+  for (int u = 0; u < FB; u += 2)
+  {
+    acc0 += pre[u] * bsh[u];
+    acc1 += pre[u + 1] * bsh[u + 1];
+  }
+  if (rv)
+  {
+    atomicAdd(dst, (acc0 + acc1) * scale);
+  }
+  if (T.signal_idx >= 0)
+  {
+    signal_counter(cnt + T.signal_idx, lane);
+  }
+}
+
+__global__ void __launch_bounds__(FLOW_THREADS, FLOW_CTAS_PER_SM)
+k_fwd_flow(const SweepTask* __restrict__ tasks, const int* __restrict__ grp, int ngroups, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf, int* __restrict__ cnt, int* __restrict__ ticket)
+{
+  __shared__ double bsh_all[FLOW_THREADS];
+  const int lane = threadIdx.x & 31;
+  double* bsh    = bsh_all + (threadIdx.x & ~31);
+  for (;;)
+  {
+    int g = 0;
+    if (lane == 0)
+    {
+      g = atomicAdd(ticket, 1);
+    }
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= ngroups)
+    {
+      return;
+    }
+    const int t1 = grp[g + 1];
+    for (int t = grp[g]; t < t1; ++t)
+    {
+      const SweepTask T = tasks[t];
+      fwd_flow_task(T, lane, Ridx, Mt, Dinv, yacc, yf, cnt, bsh);
+    }
+  }
+}
+
+// Backward task: columns [j0, j1) with j1 - j0 <= 8, rows [i0, i1), lanes stride the rows.
+//   x_j += sum_i Mt[j * h + i] * v_i,   v_i = yf[first + i] (top block, already D^-1 y) or x[rows[i - k]]
+__device__ __forceinline__ void
+bwd_flow_task(const SweepTask& T, int lane, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ yf, double* __restrict__ x, int* __restrict__ cnt)
+{
+  constexpr int CG = 8;
+  const int h = T.h, k = T.k;
+  const int nc    = T.j1 - T.j0;
+  const double* P = Mt + T.Lptr + (long long)T.j0 * h;
+  int i           = T.i0 + lane;
+  double p[CG];
+#pragma unroll
+  for (int c = 0; c < CG; ++c)
+  {
+    p[c] = (c < nc && i < T.i1) ? __ldg(P + (long long)c * h + i) : 0.0;
+  }
+  int src = i < T.i1 ? (i < k ? T.first + i : Ridx[T.Rptr + i - k]) : 0;
+  if (T.wait_idx >= 0)
+  {
+    wait_counter(cnt + T.wait_idx, T.need);
+  }
+  double acc[CG];
+#pragma unroll
+  for (int c = 0; c < CG; ++c)
+  {
+    acc[c] = 0.0;
+  }
+  for (;;)
+  {
+    const double v = i < T.i1 ? (i < k ? yf[src] : __ldcg(x + src)) : 0.0;
+#pragma unroll
+    for (int c = 0; c < CG; ++c)
+    {
+      acc[c] += p[c] * v;
+    }
+    i += 32;
+    if (i - lane >= T.i1) // warp-uniform
+    {
+      break;
+    }
+#pragma unroll
+    for (int c = 0; c < CG; ++c)
+    {
+      p[c] = (c < nc && i < T.i1) ? __ldg(P + (long long)c * h + i) : 0.0;
+    }
+    src = i < T.i1 ? (i < k ? T.first + i : Ridx[T.Rptr + i - k]) : 0;
+  }
+  // transposing butterfly: 8 sums over 32 lanes with 4 + 2 + 1 + 1 + 1 shuffles; afterwards lane 4c' holds column
+  // c = bit2 + 2 bit3 + 4 bit4 of the lane index
+  double a4[4], a2[2], a1;
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+    {
+      const double send = up ? acc[c] : acc[c + 4];
+      const double keep = up ? acc[c + 4] : acc[c];
+      a4[c]             = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+    {
+      const double send = up ? a4[c] : a4[c + 2];
+      const double keep = up ? a4[c + 2] : a4[c];
+      a2[c]             = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up     = lane & 4;
+    const double send = up ? a2[0] : a2[1];
+    const double keep = up ? a2[1] : a2[0];
+    a1                = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+  const int col = ((lane >> 2) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 4) & 1);
+  if ((lane & 3) == 0 && col < nc)
+  {
+    atomicAdd(x + T.first + T.j0 + col, a1);
+  }
+  if (T.signal_idx >= 0)
+  {
+    signal_counter(cnt + T.signal_idx, lane);
+  }
+}
+
+__global__ void __launch_bounds__(FLOW_THREADS, FLOW_CTAS_PER_SM)
+k_bwd_flow(const SweepTask* __restrict__ tasks, const int* __restrict__ grp, int ngroups, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ yf, double* __restrict__ x, int* __restrict__ cnt, int* __restrict__ ticket)
+{
+  const int lane = threadIdx.x & 31;
+  for (;;)
+  {
+    int g = 0;
+    if (lane == 0)
+    {
+      g = atomicAdd(ticket, 1);
+    }
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= ngroups)
+    {
+      return;
+    }
+    const int t1 = grp[g + 1];
+    for (int t = grp[g]; t < t1; ++t)
+    {
+      const SweepTask T = tasks[t];
+      bwd_flow_task(T, lane, Ridx, Mt, yf, x, cnt);
+    }
+  }
+}
+
+// zeroes what the dataflow sweeps accumulate into (one thread per reduced row; nflow <= m + 2 is checked on the host)
+__global__ void
+k_flow_reset(int m, int nflow, double* __restrict__ yf, double* __restrict__ x, int* __restrict__ flow)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m)
+  {
+    yf[i] = 0.0;
+    x[i]  = 0.0;
+  }
+  if (i < nflow)
+  {
+    flow[i] = 0;
+  }
+}
+
 // ---- fused top of the tree ---------------------------------------------------------------------------
 // The upper levels of the supernodal tree have few chunks each (tens to a few hundred CTAs) and cost a full
 // kernel launch + drain (~13 us) per level. These cooperative kernels walk all of them in one launch with a
@@ -844,6 +1105,8 @@ struct TopFusion
   size_t smem;
 };
 
+int g_flow      = 1;  // dataflow sweeps (default) or one launch per level (B200_SWEEP=level)
+int g_sms       = 148;
 int g_coop_ok   = -1; // -1 unknown, 0 unusable, 1 usable (process-wide)
 int g_coop_ctas = 0;  // co-resident CTAs of the fused kernels with the worst-case shared memory
 
@@ -957,6 +1220,59 @@ plan_top_fusion(const Plan& P)
 } // namespace
 
 static void
+solve_levels(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc, cudaEvent_t* ev)
+{
+  // one launch per level of the supernodal tree (B200_SWEEP=level; kept for A/B measurements)
+  auto mark = [&](int i) {
+    if (ev)
+    {
+      B200_CUDA(cudaEventRecord(ev[i], stream));
+    }
+  };
+  const Plan& P = *dp.plan;
+  const TopFusion tf = plan_top_fusion(P);
+  for (int l = 0; l < tf.split; ++l)
+  {
+    const int cnt     = P.fwd_ptr[l + 1] - P.fwd_ptr[l];
+    const size_t smem = sizeof(double) * (size_t)P.lvl_maxh[l];
+    k_fwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.fwd_tasks.p + P.fwd_ptr[l], dp.Ridx.p, nb.Mr, nb.Dinv, sb.y, sb.yf);
+    lc.tick();
+  }
+  if (tf.split < P.nlevels)
+  {
+    const FwdTask* tasks = dp.fwd_tasks.p;
+    const int* lp        = dp.fwd_ptr.p;
+    int l0 = tf.split, l1 = P.nlevels;
+    const int* ridx  = dp.Ridx.p;
+    const double *mr = nb.Mr, *di = nb.Dinv;
+    double *ya = sb.y, *yf = sb.yf;
+    void* args[] = {&tasks, &lp, &l0, &l1, &ridx, &mr, &di, &ya, &yf};
+    B200_CUDA(cudaLaunchCooperativeKernel((void*)k_fwd_top, dim3(tf.grid_fwd), dim3(SOLVE_THREADS), args, tf.smem, stream));
+    lc.tick();
+  }
+  mark(2);
+  if (tf.split < P.nlevels)
+  {
+    const BwdTask* tasks = dp.bwd_tasks.p;
+    const int* lp        = dp.bwd_ptr.p;
+    int l0 = tf.split, l1 = P.nlevels;
+    const int* ridx  = dp.Ridx.p;
+    const double *mt = nb.Mt, *dd = nb.D, *yf = sb.yf;
+    double* xx       = sb.x;
+    void* args[] = {&tasks, &lp, &l0, &l1, &ridx, &mt, &dd, &yf, &xx};
+    B200_CUDA(cudaLaunchCooperativeKernel((void*)k_bwd_top, dim3(tf.grid_bwd), dim3(SOLVE_THREADS), args, tf.smem, stream));
+    lc.tick();
+  }
+  for (int l = tf.split - 1; l >= 0; --l)
+  {
+    const int cnt     = P.bwd_ptr[l + 1] - P.bwd_ptr[l];
+    const size_t smem = sizeof(double) * (size_t)P.lvl_maxh[l];
+    k_bwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.bwd_tasks.p + P.bwd_ptr[l], dp.Ridx.p, nb.Mt, nb.D, sb.yf, sb.x);
+    lc.tick();
+  }
+}
+
+static void
 solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, const double* in, double* out, cudaStream_t stream, LaunchCounter& lc, cudaEvent_t* ev = nullptr)
 {
   auto mark = [&](int i) {
@@ -973,45 +1289,26 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
     k_pre<<<nblocks(P.m, T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.k_of_e.p, dp.pinv.p, dp.Acsr_ptr.p, dp.Acsr_col.p, nb.Acsr_val, nb.dE, in, sb.y);
     lc.tick();
     mark(1);
-    const TopFusion tf = plan_top_fusion(P);
-    for (int l = 0; l < tf.split; ++l)
+    if (g_flow)
     {
-      const int cnt     = P.fwd_ptr[l + 1] - P.fwd_ptr[l];
-      const size_t smem = sizeof(double) * (size_t)P.lvl_maxh[l];
-      k_fwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.fwd_tasks.p + P.fwd_ptr[l], dp.Ridx.p, nb.Mr, nb.Dinv, sb.y, sb.yf);
+      const int ns    = P.nsuper;
+      const int nflow = 2 * ns + 2;
+      k_flow_reset<<<nblocks(std::max(P.m, nflow), T), T, 0, stream>>>(P.m, nflow, sb.yf, sb.x, sb.flow);
+      lc.tick();
+      const int nfg = (int)P.ffl_grp.size() - 1, nbg = (int)P.bfl_grp.size() - 1;
+      const int warps_per_cta = FLOW_THREADS / 32;
+      const int max_ctas      = g_sms * FLOW_CTAS_PER_SM;
+      k_fwd_flow<<<std::max(1, std::min(max_ctas, (nfg + warps_per_cta - 1) / warps_per_cta)), FLOW_THREADS, 0, stream>>>(
+        dp.ffl_tasks.p, dp.ffl_grp.p, nfg, dp.Ridx.p, nb.Mt, nb.Dinv, sb.y, sb.yf, sb.flow, sb.flow + 2 * ns);
+      lc.tick();
+      mark(2);
+      k_bwd_flow<<<std::max(1, std::min(max_ctas, (nbg + warps_per_cta - 1) / warps_per_cta)), FLOW_THREADS, 0, stream>>>(
+        dp.bfl_tasks.p, dp.bfl_grp.p, nbg, dp.Ridx.p, nb.Mt, sb.yf, sb.x, sb.flow + ns, sb.flow + 2 * ns + 1);
       lc.tick();
     }
-    if (tf.split < P.nlevels)
+    else
     {
-      const FwdTask* tasks = dp.fwd_tasks.p;
-      const int* lp        = dp.fwd_ptr.p;
-      int l0 = tf.split, l1 = P.nlevels;
-      const int* ridx  = dp.Ridx.p;
-      const double *mr = nb.Mr, *di = nb.Dinv;
-      double *ya = sb.y, *yf = sb.yf;
-      void* args[] = {&tasks, &lp, &l0, &l1, &ridx, &mr, &di, &ya, &yf};
-      B200_CUDA(cudaLaunchCooperativeKernel((void*)k_fwd_top, dim3(tf.grid_fwd), dim3(SOLVE_THREADS), args, tf.smem, stream));
-      lc.tick();
-    }
-    mark(2);
-    if (tf.split < P.nlevels)
-    {
-      const BwdTask* tasks = dp.bwd_tasks.p;
-      const int* lp        = dp.bwd_ptr.p;
-      int l0 = tf.split, l1 = P.nlevels;
-      const int* ridx  = dp.Ridx.p;
-      const double *mt = nb.Mt, *dd = nb.D, *yf = sb.yf;
-      double* xx       = sb.x;
-      void* args[] = {&tasks, &lp, &l0, &l1, &ridx, &mt, &dd, &yf, &xx};
-      B200_CUDA(cudaLaunchCooperativeKernel((void*)k_bwd_top, dim3(tf.grid_bwd), dim3(SOLVE_THREADS), args, tf.smem, stream));
-      lc.tick();
-    }
-    for (int l = tf.split - 1; l >= 0; --l)
-    {
-      const int cnt     = P.bwd_ptr[l + 1] - P.bwd_ptr[l];
-      const size_t smem = sizeof(double) * (size_t)P.lvl_maxh[l];
-      k_bwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.bwd_tasks.p + P.bwd_ptr[l], dp.Ridx.p, nb.Mt, nb.D, sb.yf, sb.x);
-      lc.tick();
+      solve_levels(dp, nb, sb, stream, lc, ev);
     }
     mark(3);
     k_post_r<<<nblocks(P.m, T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.pinv.p, sb.x, out);
@@ -1054,6 +1351,11 @@ configure_solve_kernels()
       B200_CUDA(cudaFuncSetAttribute(k_fwd_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
       B200_CUDA(cudaFuncSetAttribute(k_bwd_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
       probe_cooperative();
+      const char* sw = std::getenv("B200_SWEEP");
+      g_flow         = !(sw && std::string(sw) == "level");
+      int dev        = 0;
+      B200_CUDA(cudaGetDevice(&dev));
+      B200_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     catch (const CudaError& e)
     {

@@ -66,6 +66,10 @@ def test_plan_emulation_solves_kkt(name):
         assert np.linalg.norm(K @ z - b) <= 1e-12 * np.linalg.norm(b)
         zr = spla.spsolve(K.tocsc(), b)
         assert np.linalg.norm(z - zr) <= 1e-10 * np.linalg.norm(zr)
+        # the dataflow sweep tasks (what the device runs): ticket order respects every dependency counter
+        zf = em.solve(b, refine=0, flow=True)
+        assert np.linalg.norm(K @ zf - b) <= 1e-12 * np.linalg.norm(b)
+        assert np.linalg.norm(zf - z) <= 1e-12 * np.linalg.norm(z)
 
 
 def test_contributor_lists_invert_the_relative_indices():
