@@ -166,31 +166,43 @@ class Emulated:
                 x[f + col0 : f + col0 + ncols] = Mfull[:, col0 : col0 + ncols].T @ v
         return x
 
+    def row_major_copy(self):
+        """Mr as k_transpose leaves it: only the 32x32 tiles of tr_tasks are written, the rest of the buffer is
+        whatever cudaMalloc returned (NaN here)."""
+        p = self.p
+        Mr = np.full(self.Mt.shape, np.nan)
+        for T, i0, j0 in p["tr_tasks"]:
+            T, i0, j0 = int(T), int(i0), int(j0)
+            f, k, r, h = self._geom(T)
+            o = int(p["Lptr"][T])
+            src = self.Mt[o : o + h * k].reshape((k, h)).T  # h x k view of the column-major panel
+            dst = Mr[o : o + h * k].reshape((h, k))
+            i1, j1 = min(h, i0 + 32), min(k, j0 + 32)
+            dst[i0:i1, j0:j1] = src[i0:i1, j0:j1]
+        return Mr
+
     def solve_reduced_flow(self, b_new):
-        """The dataflow device solve (solve.cu k_fwd_flow / k_bwd_flow): warp tasks executed one at a time in ticket
-        order. Asserts what the kernels rely on: every counter a task waits for has already reached its target when
-        the tasks run sequentially in ticket order (=> no deadlock for any number of resident warps), every task is
-        covered by exactly one ticket, and the raw column-major inverse panels (no masking of the entries above the
-        diagonal) give the right answer."""
+        """The dataflow device solve (solve.cu k_flow): warp tasks executed one at a time in ticket order. Asserts
+        what the kernels rely on: every counter a task waits for has already reached its target when the tasks run
+        sequentially in list order (the order the ticket counters hand them out in, shard by shard => no deadlock for
+        any number of resident warps), and the raw panels (no masking of the entries above the diagonal; the row-major copy only
+        where k_transpose wrote it) give the right answer."""
         p = self.p
         ns = int(p["n_supernodes"])
         Ridx, Mt = p["Ridx"], self.Mt
+        Mr = self.row_major_copy()
         Dinv = 1.0 / self.D
 
         def fields(t):
             lptr = int(np.array(t[0:2], dtype=np.int32).view(np.int64)[0])
             return (lptr,) + tuple(int(v) for v in t[2:13])
 
-        def tickets(grp, n):
-            assert grp[0] == 0 and grp[-1] == n and np.all(np.diff(grp) > 0)
-            return [t for g in range(len(grp) - 1) for t in range(int(grp[g]), int(grp[g + 1]))]
-
         yacc = np.array(b_new, dtype=np.float64)
         yf = np.zeros(self.m)
         x = np.zeros(self.m)
         cnt = np.zeros(ns, dtype=np.int64)
         tasks = p["ffl_tasks"]
-        for t in tickets(p["ffl_grp"], len(tasks)):
+        for t in range(len(tasks)):
             lptr, rptr, first, k, h, i0, i1, j0, j1, wait_idx, need, signal_idx = fields(tasks[t])
             assert 0 < i1 - i0 <= 32 and 0 < j1 - j0 <= 16 and i1 <= h and j1 <= k
             if wait_idx >= 0:
@@ -206,19 +218,20 @@ class Emulated:
                 cnt[signal_idx] += 1
         cnt[:] = 0
         tasks = p["bfl_tasks"]
-        for t in tickets(p["bfl_grp"], len(tasks)):
+        for t in range(len(tasks)):
             lptr, rptr, first, k, h, i0, i1, j0, j1, wait_idx, need, signal_idx = fields(tasks[t])
-            assert 0 < j1 - j0 <= 8 and j1 <= k and j0 <= i0 < i1 <= h
+            assert 0 < j1 - j0 <= 32 and j0 % 32 == 0 and 0 < i1 - i0 <= 16 and i0 % 16 == 0 and j1 <= k and i1 <= h
             if wait_idx >= 0:
                 assert cnt[wait_idx] == need, "backward task claimed before its producers"
             else:
                 assert i1 <= k or int(p["sn_parent"][int(p["sn_of_col"][first])]) < 0
             ii = np.arange(i0, i1)
-            v = np.where(ii < k, yf[np.minimum(first + ii, self.m - 1)], x[Ridx[rptr + np.maximum(ii - k, 0)]] if h > k else 0.0)
+            v = np.array([yf[first + i] if i < k else x[Ridx[rptr + i - k]] for i in ii])
             for j in range(j0, j1):
-                x[first + j] += Mt[lptr + j * h + ii] @ v
+                x[first + j] += Mr[lptr + ii * k + j] @ v
             if signal_idx >= 0:
                 cnt[signal_idx] += 1
+        assert np.all(np.isfinite(x))
         return x
 
     def _extend_add(self, c, jb):

@@ -237,8 +237,6 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
   FIELD(fwd_ptr)
   FIELD(bwd_ptr)
   FIELD(lvl_maxh)
-  FIELD(ffl_grp)
-  FIELD(bfl_grp)
 #undef FIELD
   if (f == "stages")
   {
@@ -268,6 +266,10 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
   if (f == "bwd_tasks")
   {
     return export_vec(P.bwd_tasks, out, count);
+  }
+  if (f == "tr_tasks")
+  {
+    return export_vec(P.tr_tasks, out, count);
   }
   if (f == "ffl_tasks")
   {

@@ -179,7 +179,6 @@ struct DevPlan
   DevBuf<int> fwd_ptr, bwd_ptr; // per-level task offsets (for the fused top-of-tree kernels)
   DevBuf<BwdTask> bwd_tasks;
   DevBuf<SweepTask> ffl_tasks, bfl_tasks; // dataflow sweeps
-  DevBuf<int> ffl_grp, bfl_grp;
   // E-part / residual operators
   DevBuf<int> k_of_e, k_of_r, pinv, perm, dE_src;
   DevBuf<int> Acsc_ptr, Acsc_row, Acsc_src, Acsr_ptr, Acsr_col, Acsr_src, Gsym_ptr, Gsym_col, Gsym_src;

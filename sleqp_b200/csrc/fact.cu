@@ -213,8 +213,6 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   dp.bwd_tasks.upload(P.bwd_tasks, s);
   dp.ffl_tasks.upload(P.ffl_tasks, s);
   dp.bfl_tasks.upload(P.bfl_tasks, s);
-  dp.ffl_grp.upload(P.ffl_grp, s);
-  dp.bfl_grp.upload(P.bfl_grp, s);
   dp.k_of_e.upload(P.k_of_e, s);
   dp.k_of_r.upload(P.k_of_r, s);
   dp.pinv.upload(P.pinv, s);
@@ -256,7 +254,7 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   F->y.reserve(m + 8);
   F->yf.reserve(m + 8);
   F->x.reserve(m + 8);
-  F->flow.reserve(2 * (size_t)P.nsuper + 8);
+  F->flow.reserve(2 * (size_t)P.nsuper + 2 * (FLOW_THREADS / 32) * 32 + 8);
   F->h_sol.reserve(N + 8);
   F->h_scal.reserve(8);
   F->h_nper.reserve(2);
@@ -573,9 +571,48 @@ b200_fact_profile_solve(b200_fact* F, int reps, double* ms_out)
   return guarded([&]() {
     B200_CUDA(cudaSetDevice(F->device));
     const NumericBuffers nb = F->nbuf();
-    const SolveBuffers sb   = F->sbuf();
+    SolveBuffers sb         = F->sbuf();
     LaunchCounter eager;
     double acc[4] = {0, 0, 0, 0};
+    // optional per-level timeline of the dataflow sweeps (stderr)
+    const char* tr_env = std::getenv("B200_FLOW_TRACE");
+    const bool tracing = tr_env && *tr_env && *tr_env != '0';
+    const int nl       = F->dp.plan->nlevels;
+    struct TraceRec
+    {
+      unsigned long long* rec;
+      int nlevels;
+      int pad;
+    };
+    int sms = 0;
+    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, F->device));
+    int ctas_per_sm = FLOW_CTAS_PER_SM;
+    if (const char* fc = std::getenv("B200_FLOW_CTAS"))
+    {
+      ctas_per_sm = std::min(FLOW_CTAS_PER_SM, std::max(1, std::atoi(fc)));
+    }
+    const size_t nwarps = (size_t)sms * ctas_per_sm * (FLOW_THREADS / 32);
+    const size_t per    = nwarps * (3 * (size_t)std::max(nl, 1) + 8); // level records, then 8 phase sums per warp
+    DevBuf<unsigned long long> tr_data;
+    DevBuf<TraceRec> tr_rec;
+    std::vector<unsigned long long> tr_init;
+    if (tracing && nl > 0)
+    {
+      tr_init.assign(2 * per, 0ull);
+      for (int sweep = 0; sweep < 2; ++sweep)
+      {
+        for (size_t w = 0; w < nwarps; ++w)
+        {
+          std::fill(tr_init.begin() + sweep * per + w * 3 * nl, tr_init.begin() + sweep * per + (w * 3 + 2) * nl, ~0ull); // the two minima
+        }
+      }
+      tr_data.reserve(tr_init.size());
+      std::vector<TraceRec> rec = {{tr_data.p, nl, 0}, {tr_data.p + per, nl, 0}};
+      tr_rec.upload(rec, F->stream);
+      B200_CUDA(cudaStreamSynchronize(F->stream));
+      sb.trace_fwd = tr_rec.p;
+      sb.trace_bwd = tr_rec.p + 1;
+    }
     cudaEvent_t ev[5];
     for (auto& e : ev)
     {
@@ -583,8 +620,55 @@ b200_fact_profile_solve(b200_fact* F, int reps, double* ms_out)
     }
     for (int it = 0; it < reps + 1; ++it)
     {
+      if (tracing && nl > 0)
+      {
+        B200_CUDA(cudaMemcpyAsync(tr_data.p, tr_init.data(), sizeof(unsigned long long) * tr_init.size(), cudaMemcpyHostToDevice, F->stream));
+      }
       enqueue_solve_phases(F->dp, nb, sb, F->stream, eager, ev);
       B200_CUDA(cudaStreamSynchronize(F->stream));
+      if (tracing && nl > 0 && it == reps)
+      {
+        std::vector<unsigned long long> t(tr_init.size());
+        B200_CUDA(cudaMemcpy(t.data(), tr_data.p, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost));
+        for (int sweep = 0; sweep < 2; ++sweep)
+        {
+          std::vector<unsigned long long> c(3 * (size_t)nl);
+          for (int q = 0; q < 3; ++q)
+          {
+            for (int l = 0; l < nl; ++l)
+            {
+              unsigned long long v = q == 2 ? 0ull : ~0ull;
+              for (size_t w = 0; w < nwarps; ++w)
+              {
+                const unsigned long long e = t[sweep * per + (w * 3 + q) * nl + l];
+                v                          = q == 2 ? std::max(v, e) : std::min(v, e);
+              }
+              c[(size_t)q * nl + l] = v;
+            }
+          }
+          unsigned long long t0 = ~0ull;
+          for (int l = 0; l < nl; ++l)
+          {
+            t0 = std::min(t0, c[l]);
+          }
+          std::fprintf(stderr, "[flow trace] %s sweep, us since the first claim: level  first-claim  first-ready  last-end\n", sweep ? "backward" : "forward");
+          for (int l = 0; l < nl; ++l)
+          {
+            std::fprintf(stderr, "[flow trace]   %3d  %9.2f  %9.2f  %9.2f\n", l, (c[l] - t0) * 1e-3, (c[nl + l] - t0) * 1e-3, (c[2 * nl + l] - t0) * 1e-3);
+          }
+          double ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          for (size_t w = 0; w < nwarps; ++w)
+          {
+            for (int q = 0; q < 8; ++q)
+            {
+              ph[q] += (double)t[sweep * per + nwarps * 3 * nl + w * 8 + q];
+            }
+          }
+          const double nt = std::max(1.0, ph[5]);
+          std::fprintf(stderr, "[flow trace]   %.0f tasks; cycles per task: record fetch %.0f  wait %.0f  vector (+ rest of the panel) %.0f  fma %.0f  publish + draw %.0f\n", ph[5],
+                       ph[0] / nt, ph[1] / nt, ph[2] / nt, ph[3] / nt, ph[4] / nt);
+        }
+      }
       if (it == 0)
       {
         continue; // warm-up

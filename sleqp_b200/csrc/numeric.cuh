@@ -36,6 +36,8 @@ struct SolveBuffers
   double* yf;   // m, forward result (new labels)
   double* x;    // m, solution of the reduced system (new labels)
   double* W;    // front vectors (sum of front heights)
+  const void* trace_fwd = nullptr; // device FlowTrace records (profile entry point with B200_FLOW_TRACE=1 only)
+  const void* trace_bwd = nullptr;
   int* flow;    // dataflow sweeps: [0, ns) forward counters, [ns, 2 ns) backward counters, then the two ticket counters
 };
 

@@ -23,6 +23,8 @@ constexpr int RB       = 128; // rows per TRSM row-block CTA
 constexpr int TILE     = 64;  // output tile edge of the DMMA update kernel
 constexpr int NBO      = 128; // outer block: columns beyond it are updated once per outer block with K = NBO
 constexpr int EA_COLS  = 4;   // update-matrix columns per extend-add task (one warp each)
+constexpr int FLOW_THREADS     = 256; // dataflow sweep kernels: persistent CTAs of 8 warps,
+constexpr int FLOW_CTAS_PER_SM = 4;   // four per SM (64 registers per thread)
 constexpr int LEAF_MAX = 32;  // etree subtrees up to this many columns become one dense supernode
 
 // kinds of update tasks
@@ -90,17 +92,18 @@ struct BwdTask
   long long Lptr, Rptr;
 };
 
-// Warp task of the dataflow sweeps (solve.cu: k_fwd_flow / k_bwd_flow). One warp owns a block of a supernode's
-// column-major inverse panel: rows [i0, i1) x columns [j0, j1).
-//   forward : i1 - i0 <= 32 (one lane per row), j1 - j0 <= 16; partial sums are added to yf (top block rows) or
-//             pushed to their final rows of the accumulator (tail rows);
-//   backward: j1 - j0 <= 8 (eight columns in flight per lane), lanes stride the rows; partial sums are added to x.
+// Warp task of the dataflow sweeps (solve.cu: k_flow). One warp owns a block of a supernode's inverse panel,
+// rows [i0, i1) x columns [j0, j1), one lane per output and at most 16 panel entries per lane:
+//   forward : lanes = rows (i1 - i0 <= 32), depth = columns (j1 - j0 <= 16), column-major panel Mt; partial sums
+//             are added to yf (top block rows) or pushed to their final rows of the accumulator (tail rows);
+//   backward: lanes = columns (j1 - j0 <= 32, j0 a multiple of 32), depth = rows (i1 - i0 <= 16, i0 a multiple of
+//             16), row-major copy Mr; partial sums are added to x.
 // Dependencies are counters, one per supernode: a task waits until cnt[wait_idx] >= need (wait_idx < 0: no wait)
 // and adds 1 to cnt[signal_idx] when its results are visible (signal_idx < 0: nobody waits for it).
 //   forward : wait on the own supernode (its children signal it), signal the parent;
 //   backward: wait on the parent (only tasks that touch tail rows), signal the own supernode.
-// Tasks are stored in topological order and handed out by a ticket counter in that order, so a waiting warp only
-// ever waits for tasks that are already claimed by running warps: no deadlock however few warps are resident.
+// Tasks are stored in topological order and handed out by ticket counters in that order (solve.cu), so the lowest
+// unfinished task is always running or about to be drawn: no deadlock however few warps are resident.
 struct alignas(16) SweepTask
 {
   long long Lptr; // panel offset (doubles)
@@ -111,7 +114,7 @@ struct alignas(16) SweepTask
   int j0, j1;
   int wait_idx, need;
   int signal_idx;
-  int pad0, pad1, pad2;
+  int pad0, pad1, pad2; // pad0: level of the supernode (timeline traces)
 };
 static_assert(sizeof(SweepTask) == 64, "SweepTask layout");
 
@@ -193,9 +196,8 @@ struct Plan
   std::vector<BwdTask> bwd_tasks;
   std::vector<int> fwd_ptr, bwd_ptr; // per level ranges into the task arrays
   std::vector<int> lvl_maxh;
-  // dataflow sweeps: tasks in ticket order, ticket g covers tasks [grp[g], grp[g + 1])
+  // dataflow sweeps: tasks in topological (ticket) order
   std::vector<SweepTask> ffl_tasks, bfl_tasks;
-  std::vector<int> ffl_grp, bfl_grp;
 
   // statistics
   i64 nnzL = 0, nnzL_stored = 0;

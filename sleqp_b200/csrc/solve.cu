@@ -640,13 +640,66 @@ k_bwd_chunk(const BwdTask* __restrict__ tasks,
 }
 
 // ---- dataflow sweeps -----------------------------------------------------------------------------------------
-// One launch per sweep. Persistent warps draw tickets (groups of SweepTasks in topological order, plan.hpp) and
-// synchronise through per-supernode counters instead of kernel boundaries: the panel loads of a task are issued
-// BEFORE its warp waits for the producers, so along the critical path of the tree a level costs one counter poll
-// + one L2 round trip for the vector, not a kernel drain + launch + three DRAM round trips.
-// Both sweeps read the column-major inverse panels Mt.
-constexpr int FLOW_THREADS      = 256;
-constexpr int FLOW_CTAS_PER_SM  = 4;
+// One launch per sweep. Persistent warps draw SweepTasks (plan.hpp) by ticket in topological order and synchronise
+// through per-supernode counters instead of kernel boundaries: the panel loads of a task are issued BEFORE its
+// warp waits for the producers, so a level of the tree costs a counter poll + an L2 round trip for the vector, not
+// a kernel drain + launch + three DRAM round trips.
+//
+// Both sweeps use the same mapping, "one lane per output, 16 panel entries in flight per lane, no shuffles":
+//   forward  reads the column-major inverse panels Mt : lane = front row r,    out_r = sum_j Mt[j h + r] b_j
+//   backward reads the row-major copy Mr              : lane = front column j, out_j = sum_i Mr[i k + j] v_i
+// so a warp load is 32 consecutive doubles in either sweep. Partial sums go out as FP64 atomics.
+//
+// What the measurements on B200 decided (profiles/README.md): one ticket counter for all warps serialises the sweep
+// (~0.5 same-address atomics with return per ns) -> sharded counters; drawing tickets ahead or in per-CTA batches
+// keeps ready tasks hostage behind waiting warps (priority inversion, 30-90 % slower) -> one task per warp at a
+// time; the draw of the next ticket is issued before the publication fence so the two round trips overlap.
+
+__device__ __forceinline__ unsigned long long
+global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Optional timeline of a sweep (B200_FLOW_TRACE=1, profile entry point only): per level the first claim, the first
+// satisfied wait and the last finished task, plus the cycles the warps spent per phase of a task. Every warp
+// records into its own rows (no shared words, so tracing does not serialise the sweep; it still costs three extra
+// memory round trips per task); the host reduces over the warps. trace == nullptr in every product launch.
+// Layout: rec[(warp * 3 + q) * nlevels + level], q = 0 first claim (min), 1 first ready (min), 2 last end (max),
+// then 8 phase sums per warp.
+struct FlowTrace
+{
+  unsigned long long* rec;
+  int nlevels;
+  int pad;
+};
+
+__device__ __forceinline__ void
+trace_mark(const FlowTrace* tr, int q, int level)
+{
+  const int warp        = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  unsigned long long* p = tr->rec + ((size_t)warp * 3 + q) * tr->nlevels + level;
+  const unsigned long long t = global_ns();
+  if (q == 2 || t < *p)
+  {
+    *p = t;
+  }
+}
+
+__device__ __forceinline__ long long
+clk_after(double dep)
+{
+  long long c;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(c) : "d"(dep) : "memory");
+  return c;
+}
+
+struct FlowPhases
+{
+  long long fetch = 0, wait = 0, vec = 0, fma = 0, publish = 0, tasks = 0;
+};
 
 __device__ __forceinline__ int
 ld_acquire(const int* p)
@@ -656,234 +709,309 @@ ld_acquire(const int* p)
   return v;
 }
 
-// all lanes poll the same word (one request per poll); back off exponentially: far-away producers need no tight loop
-__device__ __forceinline__ void
-wait_counter(const int* cnt, int need)
+__device__ __forceinline__ int
+ld_relaxed(const int* p)
 {
-  unsigned ns = 32;
-  while (ld_acquire(cnt) < need)
-  {
-    __nanosleep(ns);
-    if (ns < 512)
-    {
-      ns *= 2;
-    }
-  }
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
+// a release is all the counter hand-over needs: __threadfence() is fence.sc (MEMBAR.SC)
 __device__ __forceinline__ void
-signal_counter(int* cnt, int lane)
+fence_acq_rel()
 {
-  __threadfence(); // every lane: its own atomics are visible device-wide before the counter moves
-  __syncwarp();
-  if (lane == 0)
-  {
-    atomicAdd(cnt, 1);
-  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
-// Forward task: rows [i0, i1) (lane = row), columns [j0, j1) with j1 - j0 <= 16.
-//   out_r = sum_j Mt[j * h + r] * b_j,   b = yacc[first + j]
-// bsh: 16 doubles of shared memory private to the warp (broadcast of b).
+// All lanes poll the same word (one request per poll). While no producer has signalled yet the consumer is far
+// from ready: it polls rarely and with relaxed loads (an acquire load invalidates the SM's whole L1, CCTL.IVALL, and
+// thousands of warps hold tasks of the narrow top levels for most of the sweep). Once the count moves the
+// producers are finishing: tight acquire polls, and the poll that succeeds is the acquire the vector loads need.
 __device__ __forceinline__ void
-fwd_flow_task(const SweepTask& T, int lane, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf, int* __restrict__ cnt, double* bsh)
+wait_counter(const int* cnt, int need, unsigned far_sleep)
 {
-  constexpr int FB = 16; // panel loads in flight per lane = the widest task (FWD_COLS in symbolic.cpp)
-  const int h      = T.h;
-  const int r      = T.i0 + lane;
-  const bool rv    = r < T.i1;
-  const int nc     = T.j1 - T.j0;
-  const double* P  = Mt + T.Lptr + (long long)T.j0 * h + (rv ? r : T.i0);
-  double pre[FB];
-#pragma unroll
-  for (int u = 0; u < FB; ++u)
+  int c = ld_acquire(cnt);
+  while (c < need)
   {
-    pre[u] = (rv && u < nc) ? __ldg(P + (long long)u * h) : 0.0;
-  }
-  // destination of this lane's row (independent of the producers)
-  double* dst  = nullptr;
-  double scale = 1.0;
-  if (rv)
-  {
-    if (r < T.k)
+    if (c == 0)
     {
-      dst   = yf + T.first + r;
-      scale = Dinv[T.first + r]; // D^-1 y: the diagonal solve is folded into the forward sweep
+      __nanosleep(far_sleep);
+      c = ld_relaxed(cnt);
+      if (c >= need)
+      {
+        c = ld_acquire(cnt);
+      }
     }
     else
     {
-      dst = yacc + Ridx[T.Rptr + r - T.k];
+      __nanosleep(32);
+      c = ld_acquire(cnt);
     }
+  }
+}
+
+// Tickets. The task list is dealt over FLOW_SHARDS interleaved sequences with one counter each (128 bytes apart:
+// different L2 slices): shard s holds the tasks s, s + FLOW_SHARDS, s + 2 FLOW_SHARDS, ... Warp w of every CTA
+// serves shard w, so ANY resident CTA serves all shards in order and the lowest unfinished task is always either
+// running or about to be drawn by a free warp: no deadlock however few CTAs are resident. A warp whose shard is
+// exhausted helps with the others.
+constexpr int FLOW_SHARDS       = FLOW_THREADS / 32;
+constexpr int FLOW_TICKET_PITCH = 32; // ints between two counters
+
+struct FlowSched
+{
+  int ntasks;
+  int far_sleep; // poll interval while no producer has signalled yet (ns)
+};
+
+// flow_take_issue only issues the atomic of the warp's current shard (its result stays in lane 0);
+// flow_take_finish completes the draw, moving on to the other shards when that one is exhausted, and returns the
+// task index or -1 when every shard is exhausted.
+__device__ __forceinline__ int
+flow_take_issue(int* __restrict__ ticket, int lane, int shard)
+{
+  return lane == 0 ? atomicAdd(ticket + shard * FLOW_TICKET_PITCH, 1) : 0;
+}
+
+__device__ __forceinline__ int
+flow_take_finish(int issued, int* __restrict__ ticket, int ntasks, int lane, int& shard, int& tried)
+{
+  int t = -1;
+  if (lane == 0)
+  {
+    int i = issued;
+    for (;;)
+    {
+      const long long cand = (long long)i * FLOW_SHARDS + shard;
+      if (cand < ntasks)
+      {
+        t = (int)cand;
+        break;
+      }
+      shard = (shard + 1) % FLOW_SHARDS;
+      if (++tried >= FLOW_SHARDS)
+      {
+        break;
+      }
+      i = atomicAdd(ticket + shard * FLOW_TICKET_PITCH, 1);
+    }
+  }
+  return __shfl_sync(0xffffffffu, t, 0);
+}
+
+constexpr int FLOW_DEPTH = 16; // panel entries in flight per lane = depth of a task
+
+// One task up to (not including) the publication of its completion.
+//   FWD: lanes are rows [i0, i1), depth is columns [j0, j1), panel element (r, j) at Mt[j * h + r].
+//   BWD: lanes are columns [j0, j1), depth is rows [i0, i1), panel element (i, j) at Mr[i * k + j].
+// vsh: FLOW_DEPTH doubles of shared memory private to the warp (broadcast of the vector).
+template <bool FWD, bool TRACE>
+__device__ __forceinline__ void
+flow_task(const SweepTask& T,
+          int lane,
+          const int* __restrict__ Ridx,
+          const double* __restrict__ M,
+          const double* __restrict__ Dinv,
+          double* __restrict__ yacc,
+          double* __restrict__ yf,
+          double* __restrict__ x,
+          const int* __restrict__ cnt,
+          double* vsh,
+          const FlowTrace* trace,
+          unsigned far_sleep,
+          FlowPhases& ph)
+{
+  long long c0 = 0, c1 = 0, c2 = 0;
+  if (TRACE)
+  {
+    c0 = clk_after((double)T.k);
+  }
+  const int k = T.k, h = T.h;
+  const int ld    = FWD ? h : k;
+  const int o     = (FWD ? T.i0 : T.j0) + lane; // this lane's output index in the front
+  const bool ov   = o < (FWD ? T.i1 : T.j1);
+  const int d0    = FWD ? T.j0 : T.i0; // depth range
+  const int nd    = (FWD ? T.j1 : T.i1) - d0;
+  const double* P = M + T.Lptr + (long long)d0 * ld + (ov ? o : (FWD ? T.i0 : T.j0));
+  double pre[FLOW_DEPTH];
+#pragma unroll
+  for (int u = 0; u < FLOW_DEPTH; ++u)
+  {
+    pre[u] = (ov && u < nd) ? __ldcs(P + (long long)u * ld) : 0.0; // streaming: must not evict the small hot arrays from L2
+  }
+  // where this lane's result goes, and where its share of the vector comes from (both independent of the producers)
+  double* dst  = nullptr;
+  double scale = 1.0;
+  if (ov)
+  {
+    if (FWD)
+    {
+      if (o < k)
+      {
+        dst   = yf + T.first + o;
+        scale = Dinv[T.first + o]; // D^-1 y: the diagonal solve is folded into the forward sweep
+      }
+      else
+      {
+        dst = yacc + Ridx[T.Rptr + o - k];
+      }
+    }
+    else
+    {
+      dst = x + T.first + o;
+    }
+  }
+  const double* vsrc = nullptr;
+  bool vplain        = false; // written by an earlier kernel: no coherence concern
+  if (lane < nd)
+  {
+    const int d = d0 + lane;
+    if (FWD)
+    {
+      vsrc = yacc + T.first + d;
+    }
+    else if (d < k)
+    {
+      vsrc   = yf + T.first + d; // already D^-1 y
+      vplain = true;
+    }
+    else
+    {
+      vsrc = x + Ridx[T.Rptr + d - k];
+    }
+  }
+  if (TRACE && lane == 0)
+  {
+    trace_mark(trace, 0, T.pad0);
   }
   if (T.wait_idx >= 0)
   {
-    wait_counter(cnt + T.wait_idx, T.need);
+    wait_counter(cnt + T.wait_idx, T.need, far_sleep);
   }
-  __syncwarp(); // the previous task's reads of bsh are done
-  if (lane < FB)
+  if (TRACE)
   {
-    bsh[lane] = lane < nc ? __ldcg(yacc + T.first + T.j0 + lane) : 0.0;
+    c1 = clk_after(0.0);
+    if (lane == 0)
+    {
+      trace_mark(trace, 1, T.pad0);
+    }
+  }
+  __syncwarp(); // the previous task's reads of vsh are done
+  if (lane < FLOW_DEPTH)
+  {
+    vsh[lane] = vsrc ? (vplain ? *vsrc : __ldcg(vsrc)) : 0.0;
   }
   __syncwarp();
+  if (TRACE)
+  {
+    c2 = clk_after(vsh[0]);
+  }
   double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-  for (int u = 0; u < FB; u += 2)
+  for (int u = 0; u < FLOW_DEPTH; u += 2)
   {
-    acc0 += pre[u] * bsh[u];
-    acc1 += pre[u + 1] * bsh[u + 1];
+    acc0 += pre[u] * vsh[u];
+    acc1 += pre[u + 1] * vsh[u + 1];
   }
-  if (rv)
+  if (ov)
   {
     atomicAdd(dst, (acc0 + acc1) * scale);
   }
-  if (T.signal_idx >= 0)
+  if (TRACE)
   {
-    signal_counter(cnt + T.signal_idx, lane);
-  }
-}
-
-__global__ void __launch_bounds__(FLOW_THREADS, FLOW_CTAS_PER_SM)
-k_fwd_flow(const SweepTask* __restrict__ tasks, const int* __restrict__ grp, int ngroups, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf, int* __restrict__ cnt, int* __restrict__ ticket)
-{
-  __shared__ double bsh_all[FLOW_THREADS];
-  const int lane = threadIdx.x & 31;
-  double* bsh    = bsh_all + (threadIdx.x & ~31);
-  for (;;)
-  {
-    int g = 0;
+    const long long c3 = clk_after(acc0 + acc1);
+    ph.wait += c1 - c0;
+    ph.vec += c2 - c1;
+    ph.fma += c3 - c2;
+    ph.tasks += 1;
     if (lane == 0)
     {
-      g = atomicAdd(ticket, 1);
-    }
-    g = __shfl_sync(0xffffffffu, g, 0);
-    if (g >= ngroups)
-    {
-      return;
-    }
-    const int t1 = grp[g + 1];
-    for (int t = grp[g]; t < t1; ++t)
-    {
-      const SweepTask T = tasks[t];
-      fwd_flow_task(T, lane, Ridx, Mt, Dinv, yacc, yf, cnt, bsh);
+      trace_mark(trace, 2, T.pad0);
     }
   }
 }
 
-// Backward task: columns [j0, j1) with j1 - j0 <= 8, rows [i0, i1), lanes stride the rows.
-//   x_j += sum_i Mt[j * h + i] * v_i,   v_i = yf[first + i] (top block, already D^-1 y) or x[rows[i - k]]
-__device__ __forceinline__ void
-bwd_flow_task(const SweepTask& T, int lane, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ yf, double* __restrict__ x, int* __restrict__ cnt)
-{
-  constexpr int CG = 8;
-  const int h = T.h, k = T.k;
-  const int nc    = T.j1 - T.j0;
-  const double* P = Mt + T.Lptr + (long long)T.j0 * h;
-  int i           = T.i0 + lane;
-  double p[CG];
-#pragma unroll
-  for (int c = 0; c < CG; ++c)
-  {
-    p[c] = (c < nc && i < T.i1) ? __ldg(P + (long long)c * h + i) : 0.0;
-  }
-  int src = i < T.i1 ? (i < k ? T.first + i : Ridx[T.Rptr + i - k]) : 0;
-  if (T.wait_idx >= 0)
-  {
-    wait_counter(cnt + T.wait_idx, T.need);
-  }
-  double acc[CG];
-#pragma unroll
-  for (int c = 0; c < CG; ++c)
-  {
-    acc[c] = 0.0;
-  }
-  for (;;)
-  {
-    const double v = i < T.i1 ? (i < k ? yf[src] : __ldcg(x + src)) : 0.0;
-#pragma unroll
-    for (int c = 0; c < CG; ++c)
-    {
-      acc[c] += p[c] * v;
-    }
-    i += 32;
-    if (i - lane >= T.i1) // warp-uniform
-    {
-      break;
-    }
-#pragma unroll
-    for (int c = 0; c < CG; ++c)
-    {
-      p[c] = (c < nc && i < T.i1) ? __ldg(P + (long long)c * h + i) : 0.0;
-    }
-    src = i < T.i1 ? (i < k ? T.first + i : Ridx[T.Rptr + i - k]) : 0;
-  }
-  // transposing butterfly: 8 sums over 32 lanes with 4 + 2 + 1 + 1 + 1 shuffles; afterwards lane 4c' holds column
-  // c = bit2 + 2 bit3 + 4 bit4 of the lane index
-  double a4[4], a2[2], a1;
-  {
-    const bool up = lane & 16;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-    {
-      const double send = up ? acc[c] : acc[c + 4];
-      const double keep = up ? acc[c + 4] : acc[c];
-      a4[c]             = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-  {
-    const bool up = lane & 8;
-#pragma unroll
-    for (int c = 0; c < 2; ++c)
-    {
-      const double send = up ? a4[c] : a4[c + 2];
-      const double keep = up ? a4[c + 2] : a4[c];
-      a2[c]             = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-  }
-  {
-    const bool up     = lane & 4;
-    const double send = up ? a2[0] : a2[1];
-    const double keep = up ? a2[1] : a2[0];
-    a1                = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-  const int col = ((lane >> 2) & 1) + 2 * ((lane >> 3) & 1) + 4 * ((lane >> 4) & 1);
-  if ((lane & 3) == 0 && col < nc)
-  {
-    atomicAdd(x + T.first + T.j0 + col, a1);
-  }
-  if (T.signal_idx >= 0)
-  {
-    signal_counter(cnt + T.signal_idx, lane);
-  }
-}
-
+template <bool FWD, bool TRACE>
 __global__ void __launch_bounds__(FLOW_THREADS, FLOW_CTAS_PER_SM)
-k_bwd_flow(const SweepTask* __restrict__ tasks, const int* __restrict__ grp, int ngroups, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ yf, double* __restrict__ x, int* __restrict__ cnt, int* __restrict__ ticket)
+k_flow(const SweepTask* __restrict__ tasks,
+       FlowSched sched,
+       const int* __restrict__ Ridx,
+       const double* __restrict__ M,
+       const double* __restrict__ Dinv,
+       double* __restrict__ yacc,
+       double* __restrict__ yf,
+       double* __restrict__ x,
+       int* __restrict__ cnt,
+       int* __restrict__ ticket,
+       const FlowTrace* __restrict__ trace)
 {
-  const int lane = threadIdx.x & 31;
-  for (;;)
+  __shared__ double vsh_all[FLOW_THREADS / 32 * FLOW_DEPTH];
+  __shared__ __align__(16) SweepTask slot_all[FLOW_THREADS / 32]; // the warp's task record, fetched with cp.async
+  const int lane  = threadIdx.x & 31;
+  double* vsh     = vsh_all + (threadIdx.x >> 5) * FLOW_DEPTH;
+  SweepTask* slot = slot_all + (threadIdx.x >> 5);
+  FlowPhases ph;
+  long long cf = TRACE ? clk_after(0.0) : 0;
+  int shard = threadIdx.x >> 5, tried = 0;
+  int cur   = flow_take_finish(flow_take_issue(ticket, lane, shard), ticket, sched.ntasks, lane, shard, tried);
+  while (cur >= 0)
   {
-    int g = 0;
-    if (lane == 0)
+    if (lane < 4)
     {
-      g = atomicAdd(ticket, 1);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared((const char*)slot + 16 * lane);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"((const char*)(tasks + cur) + 16 * lane) : "memory");
     }
-    g = __shfl_sync(0xffffffffu, g, 0);
-    if (g >= ngroups)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const SweepTask T = *slot;
+    __syncwarp(); // the record is in registers: the slot may be overwritten
+    if (TRACE)
     {
-      return;
+      ph.fetch += clk_after((double)T.h) - cf;
     }
-    const int t1 = grp[g + 1];
-    for (int t = grp[g]; t < t1; ++t)
+    flow_task<FWD, TRACE>(T, lane, Ridx, M, Dinv, yacc, yf, x, cnt, vsh, trace, (unsigned)sched.far_sleep, ph);
+    if (TRACE)
     {
-      const SweepTask T = tasks[t];
-      bwd_flow_task(T, lane, Ridx, Mt, yf, x, cnt);
+      cf = clk_after(0.0);
     }
+    // publication. The draw of the next ticket is issued first so that its round trip overlaps with the fence;
+    // nothing can block between the draw and the signal.
+    const bool open  = tried < FLOW_SHARDS;
+    const int issued = open ? flow_take_issue(ticket, lane, shard) : 0;
+    if (T.signal_idx >= 0)
+    {
+      fence_acq_rel(); // every lane: its own atomics are visible device-wide before the counter moves
+      __syncwarp();
+      if (lane == 0)
+      {
+        atomicAdd(cnt + T.signal_idx, 1);
+      }
+    }
+    cur = open ? flow_take_finish(issued, ticket, sched.ntasks, lane, shard, tried) : -1;
+    if (TRACE)
+    {
+      const long long c = clk_after((double)cur);
+      ph.publish += c - cf;
+      cf = c;
+    }
+  }
+  if (TRACE && lane == 0)
+  {
+    const int warp        = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps      = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long* p = trace->rec + (size_t)nwarps * 3 * trace->nlevels + (size_t)warp * 8;
+    p[0] = ph.fetch;
+    p[1] = ph.wait;
+    p[2] = ph.vec;
+    p[3] = ph.fma;
+    p[4] = ph.publish;
+    p[5] = ph.tasks;
   }
 }
 
-// zeroes what the dataflow sweeps accumulate into (one thread per reduced row; nflow <= m + 2 is checked on the host)
+// zeroes what the dataflow sweeps accumulate into (one thread per reduced row / counter)
 __global__ void
 k_flow_reset(int m, int nflow, double* __restrict__ yf, double* __restrict__ x, int* __restrict__ flow)
 {
@@ -1107,6 +1235,8 @@ struct TopFusion
 
 int g_flow      = 1;  // dataflow sweeps (default) or one launch per level (B200_SWEEP=level)
 int g_sms       = 148;
+int g_flow_sleep = 512;
+int g_flow_ctas  = FLOW_CTAS_PER_SM; // B200_FLOW_CTAS: fewer resident CTAs per SM (experiments)
 int g_coop_ok   = -1; // -1 unknown, 0 unusable, 1 usable (process-wide)
 int g_coop_ctas = 0;  // co-resident CTAs of the fused kernels with the worst-case shared memory
 
@@ -1292,18 +1422,27 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
     if (g_flow)
     {
       const int ns    = P.nsuper;
-      const int nflow = 2 * ns + 2;
+      const int nflow = 2 * ns + 2 * FLOW_SHARDS * FLOW_TICKET_PITCH;
       k_flow_reset<<<nblocks(std::max(P.m, nflow), T), T, 0, stream>>>(P.m, nflow, sb.yf, sb.x, sb.flow);
       lc.tick();
-      const int nfg = (int)P.ffl_grp.size() - 1, nbg = (int)P.bfl_grp.size() - 1;
       const int warps_per_cta = FLOW_THREADS / 32;
-      const int max_ctas      = g_sms * FLOW_CTAS_PER_SM;
-      k_fwd_flow<<<std::max(1, std::min(max_ctas, (nfg + warps_per_cta - 1) / warps_per_cta)), FLOW_THREADS, 0, stream>>>(
-        dp.ffl_tasks.p, dp.ffl_grp.p, nfg, dp.Ridx.p, nb.Mt, nb.Dinv, sb.y, sb.yf, sb.flow, sb.flow + 2 * ns);
+      const int max_ctas      = g_sms * g_flow_ctas;
+      auto grid = [&](size_t ntasks) {
+        const long long ctas = ((long long)ntasks + FLOW_SHARDS - 1) / FLOW_SHARDS;
+        return (unsigned)std::max<long long>(1, std::min<long long>(max_ctas, ctas));
+      };
+      const FlowSched fs{(int)P.ffl_tasks.size(), g_flow_sleep};
+      const FlowSched bs{(int)P.bfl_tasks.size(), g_flow_sleep};
+      int* const tickets_f = sb.flow + 2 * ns;
+      int* const tickets_b = tickets_f + FLOW_SHARDS * FLOW_TICKET_PITCH;
+      auto kf = sb.trace_fwd ? k_flow<true, true> : k_flow<true, false>;
+      auto kb = sb.trace_bwd ? k_flow<false, true> : k_flow<false, false>;
+      kf<<<sb.trace_fwd ? max_ctas : grid(P.ffl_tasks.size()), FLOW_THREADS, 0, stream>>>(dp.ffl_tasks.p, fs, dp.Ridx.p, nb.Mt, nb.Dinv, sb.y, sb.yf, sb.x, sb.flow, tickets_f,
+                                                                  (const FlowTrace*)sb.trace_fwd);
       lc.tick();
       mark(2);
-      k_bwd_flow<<<std::max(1, std::min(max_ctas, (nbg + warps_per_cta - 1) / warps_per_cta)), FLOW_THREADS, 0, stream>>>(
-        dp.bfl_tasks.p, dp.bfl_grp.p, nbg, dp.Ridx.p, nb.Mt, sb.yf, sb.x, sb.flow + ns, sb.flow + 2 * ns + 1);
+      kb<<<sb.trace_bwd ? max_ctas : grid(P.bfl_tasks.size()), FLOW_THREADS, 0, stream>>>(dp.bfl_tasks.p, bs, dp.Ridx.p, nb.Mr, nb.Dinv, sb.y, sb.yf, sb.x, sb.flow + ns, tickets_b,
+                                                                   (const FlowTrace*)sb.trace_bwd);
       lc.tick();
     }
     else
@@ -1353,6 +1492,14 @@ configure_solve_kernels()
       probe_cooperative();
       const char* sw = std::getenv("B200_SWEEP");
       g_flow         = !(sw && std::string(sw) == "level");
+      if (const char* fc = std::getenv("B200_FLOW_CTAS"))
+      {
+        g_flow_ctas = std::min(FLOW_CTAS_PER_SM, std::max(1, std::atoi(fc)));
+      }
+      if (const char* fs = std::getenv("B200_FLOW_SLEEP"))
+      {
+        g_flow_sleep = std::max(32, std::atoi(fs));
+      }
       int dev        = 0;
       B200_CUDA(cudaGetDevice(&dev));
       B200_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));

@@ -915,6 +915,11 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   // ---- supernodes: dense leaf subtrees + fundamental + relaxed chains -----------------------------
   std::vector<int> blk(m, -1);
   {
+    int LEAF_MAX = b200::LEAF_MAX;
+    if (const char* e = std::getenv("B200_LEAF_MAX")) // experiments only
+    {
+      LEAF_MAX = std::max(1, std::atoi(e));
+    }
     std::vector<int> size(m, 1);
     for (int j = 0; j < m; ++j)
     {
@@ -1703,64 +1708,44 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
 
   // ---- dataflow sweeps: warp tasks in ticket order, dependency counters per supernode -------------------------
   {
-    constexpr int FLOW_WARPS = 148 * 32; // resident warps the grouping aims to keep busy
-    constexpr int FWD_ROWS = 32, FWD_COLS = 16, BWD_COLS = 8;
+    constexpr int LANES = 32, DEPTH = 16;
     if ((i64)P.Ridx.size() > 0x7ffffff0)
     {
       return fail(err, B200_ERR_UNSUPPORTED, "row-index array exceeds 2^31 entries");
     }
-    std::vector<int> nf(ns, 0), nbk(ns, 0);
-    // rows per backward task: one round of loads where the level cannot fill the machine anyway, four otherwise
-    std::vector<int> bwd_rows(P.nlevels, 32);
-    for (int l = 0; l < P.nlevels; ++l)
-    {
-      i64 work = 0;
-      for (int q = P.lvl_ptr[l]; q < P.lvl_ptr[l + 1]; ++q)
+    // forward: lanes = rows, depth = columns (row r of the triangular top block needs columns <= r)
+    // backward: lanes = columns (blocks aligned to 32 like the tiles of the row-major copy), depth = rows (column j
+    //           needs rows >= j)
+    auto fwd_blocks = [&](int k, int h, auto&& emit) {
+      for (int i0 = 0; i0 < h; i0 += LANES)
       {
-        const int T = P.lvl_sn[q];
-        work += (P.Wptr[T + 1] - P.Wptr[T]) * (i64)(P.sn_first[T + 1] - P.sn_first[T]);
+        const int i1 = std::min(h, i0 + LANES);
+        const int je = std::min(k, i1);
+        for (int j0 = 0; j0 < je; j0 += DEPTH)
+        {
+          emit(i0, i1, j0, std::min(je, j0 + DEPTH));
+        }
       }
-      bwd_rows[l] = work / (BWD_COLS * 32) >= 4 * (i64)FLOW_WARPS ? 128 : (work / (BWD_COLS * 32) >= 2 * (i64)FLOW_WARPS ? 64 : 32);
-    }
+    };
+    auto bwd_blocks = [&](int k, int h, auto&& emit) {
+      for (int j0 = 0; j0 < k; j0 += LANES)
+      {
+        for (int i0 = j0; i0 < h; i0 += DEPTH) // j0 is a multiple of 32, so the depth blocks are aligned to 16
+        {
+          emit(i0, std::min(h, i0 + DEPTH), j0, std::min(k, j0 + LANES));
+        }
+      }
+    };
+    std::vector<int> nf(ns, 0), nbk(ns, 0);
     for (int T = 0; T < ns; ++T)
     {
       const int k = P.sn_first[T + 1] - P.sn_first[T];
       const int h = (int)(P.Wptr[T + 1] - P.Wptr[T]);
-      for (int i0 = 0; i0 < h; i0 += FWD_ROWS)
-      {
-        const int je = std::min(k, std::min(h, i0 + FWD_ROWS));
-        nf[T] += (je + FWD_COLS - 1) / FWD_COLS;
-      }
-      const int rb = bwd_rows[P.sn_level[T]];
-      for (int j0 = 0; j0 < k; j0 += BWD_COLS)
-      {
-        nbk[T] += (h - j0 + rb - 1) / rb;
-      }
+      fwd_blocks(k, h, [&](int, int, int, int) { ++nf[T]; });
+      bwd_blocks(k, h, [&](int, int, int, int) { ++nbk[T]; });
     }
-    auto close_groups = [&](std::vector<int>& grp, const std::vector<SweepTask>& tasks, size_t level_begin) {
-      // tickets of one level: enough of them to occupy every resident warp, at most 16 tasks / 4096 entries each
-      const size_t n   = tasks.size() - level_begin;
-      const size_t per = std::min<size_t>(16, std::max<size_t>(1, n / FLOW_WARPS));
-      size_t cnt = 0;
-      i64 work   = 0;
-      for (size_t t = level_begin; t < tasks.size(); ++t)
-      {
-        if (cnt == 0)
-        {
-          grp.push_back((int)t);
-        }
-        ++cnt;
-        work += (i64)(tasks[t].i1 - tasks[t].i0) * (tasks[t].j1 - tasks[t].j0);
-        if (cnt >= per || work >= 4096)
-        {
-          cnt  = 0;
-          work = 0;
-        }
-      }
-    };
     for (int l = 0; l < P.nlevels; ++l)
     {
-      const size_t begin = P.ffl_tasks.size();
       std::vector<int> order(P.lvl_sn.begin() + P.lvl_ptr[l], P.lvl_sn.begin() + P.lvl_ptr[l + 1]);
       std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return (P.Wptr[x + 1] - P.Wptr[x]) > (P.Wptr[y + 1] - P.Wptr[y]); });
       for (int T : order)
@@ -1773,22 +1758,13 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
           need += nf[P.child_idx[q]];
         }
         const int wait_idx = need > 0 ? T : -1;
-        for (int i0 = 0; i0 < h; i0 += FWD_ROWS)
-        {
-          const int i1 = std::min(h, i0 + FWD_ROWS);
-          const int je = std::min(k, i1); // the top block is lower triangular
-          for (int j0 = 0; j0 < je; j0 += FWD_COLS)
-          {
-            P.ffl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, std::min(je, j0 + FWD_COLS), wait_idx, need, P.sn_parent[T], 0, 0, 0});
-          }
-        }
+        fwd_blocks(k, h, [&](int i0, int i1, int j0, int j1) {
+          P.ffl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, j1, wait_idx, need, P.sn_parent[T], l, 0, 0});
+        });
       }
-      close_groups(P.ffl_grp, P.ffl_tasks, begin);
     }
-    P.ffl_grp.push_back((int)P.ffl_tasks.size());
     for (int l = P.nlevels - 1; l >= 0; --l)
     {
-      const size_t begin = P.bfl_tasks.size();
       std::vector<int> order(P.lvl_sn.begin() + P.lvl_ptr[l], P.lvl_sn.begin() + P.lvl_ptr[l + 1]);
       std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return (P.Wptr[x + 1] - P.Wptr[x]) > (P.Wptr[y + 1] - P.Wptr[y]); });
       for (int T : order)
@@ -1796,21 +1772,13 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         const int k   = P.sn_first[T + 1] - P.sn_first[T];
         const int h   = (int)(P.Wptr[T + 1] - P.Wptr[T]);
         const int par = P.sn_parent[T];
-        const int rb  = bwd_rows[l];
         const int signal_idx = P.child_ptr[T + 1] > P.child_ptr[T] ? T : -1;
-        for (int j0 = 0; j0 < k; j0 += BWD_COLS)
-        {
-          for (int i0 = j0; i0 < h; i0 += rb) // column j needs rows >= j only
-          {
-            const int i1       = std::min(h, i0 + rb);
-            const bool tail    = i1 > k; // touches x of the ancestors
-            P.bfl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, std::min(k, j0 + BWD_COLS), (tail && par >= 0) ? par : -1, (tail && par >= 0) ? nbk[par] : 0, signal_idx, 0, 0, 0});
-          }
-        }
+        bwd_blocks(k, h, [&](int i0, int i1, int j0, int j1) {
+          const bool tail = i1 > k && par >= 0; // touches x of the ancestors
+          P.bfl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, j1, tail ? par : -1, tail ? nbk[par] : 0, signal_idx, l, 0, 0});
+        });
       }
-      close_groups(P.bfl_grp, P.bfl_tasks, begin);
     }
-    P.bfl_grp.push_back((int)P.bfl_tasks.size());
   }
 
   tick("solve tasks + contributors");

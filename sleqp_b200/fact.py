@@ -48,12 +48,12 @@ PLAN_FIELDS = {
         "e_of_k r_of_k k_of_e k_of_r dE_src Acsc_ptr Acsc_row Acsc_src Acsr_ptr Acsr_col Acsr_src "
         "Gsym_ptr Gsym_col Gsym_src perm pinv parent colcount sn_first sn_of_col sn_parent sn_level "
         "Ridx rel child_ptr child_idx Sgsrc Sterm_a Sterm_b Sterm_d sn_base sn_nt zero_sn lvl_ptr lvl_sn "
-        "inv_phase_ptr sn_ncol fwd_ptr bwd_ptr lvl_maxh cptr cidx ffl_grp bfl_grp"
+        "inv_phase_ptr sn_ncol fwd_ptr bwd_ptr lvl_maxh cptr cidx"
     ).split()},
     **{k: np.int64 for k in "Rptr Lptr Wptr Sdest Sterm_ptr Uoff Tptr".split()},
 }
 PLAN_STRUCTS = {"stages": 10, "ea_tasks": 2, "diag_tasks": 2, "pan_tasks": 4, "upd_tasks": 7, "inv_tasks": 6, "fwd_tasks": 10, "bwd_tasks": 10,
-                "ffl_tasks": 16, "bfl_tasks": 16}  # int32 columns
+                "ffl_tasks": 16, "bfl_tasks": 16, "tr_tasks": 3}  # int32 columns
 
 
 class Symbolic:
