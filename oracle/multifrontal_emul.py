@@ -26,6 +26,7 @@ class Emulated:
         self.nE = int(plan["n_elim"])
         self.N = int(plan["n"])
         self.n_perturbed = 0
+        self.L11 = {}  # unit lower factors of the diagonal blocks, keyed by (supernode, panel step)
         self._factor()
         self._invert()
 
@@ -81,10 +82,9 @@ class Emulated:
                 self.umat(T)[:, :] = 0.0
             for c, jb in p["ea_tasks"][eb:ee]:
                 self._extend_add(int(c), int(jb))
-            for T, t in p["diag_tasks"][db:de]:
-                self._panel(int(T), int(t), 0, -1, scratch, diag_only=True)
+            assert [tuple(x) for x in p["diag_tasks"][db:de]] == [(T, t) for T, t, rb, _ in p["pan_tasks"][pb:pe] if rb == 0]
             for T, t, rb, _pad in p["pan_tasks"][pb:pe]:
-                self._panel(int(T), int(t), int(rb), -1, scratch, trsm_only=True)
+                self._panel(int(T), int(t), int(rb))
             for T, t, kind, i0, j0, kb, ke in p["upd_tasks"][ub:ue]:
                 self._update(int(T), int(t), int(kind), int(i0), int(j0), scratch, bool(has_children[T]), int(kb), int(ke))
 
@@ -105,7 +105,7 @@ class Emulated:
             P, M = self.panel(T), self.mpanel(T)
             for c0 in range(0, k, NB):
                 w = min(NB, k - c0)
-                L11 = np.tril(P[c0 : c0 + w, c0 : c0 + w], -1) + np.eye(w)
+                L11 = self.L11[(T, c0 // NB)]
                 M[c0 : c0 + w, c0 : c0 + w] = np.tril(np.linalg.inv(L11))
         ph = p["inv_phase_ptr"]
         for q in range(len(ph) - 1):
@@ -270,34 +270,26 @@ class Emulated:
                 A[c:, c] -= A[c:, j] * dj * A[c, j]
         return A, d, nper
 
-    def _panel(self, T, t, rb, slot, scratch, diag_only=False, trsm_only=False):
+    def _panel(self, T, t, rb):
+        """k_panel: every CTA of a panel step factors the (still unfactored, read-only) diagonal block itself and
+        solves for its RB rows of L21; CTA 0 publishes the pivots and the unit lower factor (for the inversion)."""
         f, k, r, h = self._geom(T)
         P = self.panel(T)
         c0 = t * NB
         w = min(NB, k - c0)
-        if trsm_only:
-            # k_trsm reads the factored block published by k_diag
-            L11 = np.tril(P[c0 : c0 + w, c0 : c0 + w], -1) + np.eye(w)
-            d, nper = self.D[f + c0 : f + c0 + w].copy(), 0
-        else:
-            L11, d, nper = self._factor_diag(P[c0 : c0 + w, c0 : c0 + w])
+        L11, d, nper = self._factor_diag(P[c0 : c0 + w, c0 : c0 + w])
         r0 = c0 + w + rb * RB
         r1 = min(h, r0 + RB)
-        if r1 > r0 and not diag_only:
+        if r1 > r0:
             X = P[r0:r1, c0 : c0 + w].copy()
             # solve X_new * D * L11^T = X
             for j in range(w):
                 X[:, j] = (X[:, j] - (X[:, :j] * d[:j]) @ L11[j, :j]) / d[j]
             P[r0:r1, c0 : c0 + w] = X
-        if rb == 0 and not trsm_only:
+        if rb == 0:
             self.n_perturbed += nper
             self.D[f + c0 : f + c0 + w] = d
-            if slot < 0:
-                il = np.tril_indices(w)
-                blk = P[c0 : c0 + w, c0 : c0 + w]
-                blk[il] = L11[il]
-            else:
-                scratch[slot * NB * NB : slot * NB * NB + w * w] = L11.T.ravel()  # column-major w x w
+            self.L11[(T, t)] = np.tril(L11, -1) + np.eye(w)
 
     def _update(self, T, t, kind, i0, j0, scratch, accumulate, kb=None, ke=None):
         f, k, r, h = self._geom(T)
@@ -338,6 +330,16 @@ class Emulated:
         raise ValueError(kind)
 
     # ---------------------------------------------------------------- solve
+    def _L11_full(self, T):
+        """Unit lower k x k factor of supernode T: off-diagonal blocks from the panel, diagonal blocks as published by
+        CTA 0 of every panel step (the panel keeps the assembled values there)."""
+        f, k, r, h = self._geom(T)
+        out = np.tril(self.panel(T)[:k, :k], -1) + np.eye(k)
+        for c0 in range(0, k, NB):
+            w = min(NB, k - c0)
+            out[c0 : c0 + w, c0 : c0 + w] = self.L11[(T, c0 // NB)]
+        return out
+
     def solve_reduced(self, b_new):
         """Solve S x = b in the permuted (new) labels with the multifrontal front vectors."""
         p = self.p
@@ -358,7 +360,7 @@ class Emulated:
                     wc = W[int(p["Wptr"][c]) + kc : int(p["Wptr"][c]) + hc]
                     np.add.at(w, rel, wc)
                 P = self.panel(T)
-                L11 = np.tril(P[:k, :k], -1) + np.eye(k)
+                L11 = self._L11_full(T)
                 y = np.linalg.solve(L11, w[:k])
                 w[:k] = y
                 w[k:] -= P[k:, :k] @ y
@@ -370,7 +372,7 @@ class Emulated:
                 f, k, r, h = self._geom(T)
                 rows = p["Ridx"][int(p["Rptr"][T]) : int(p["Rptr"][T + 1])]
                 P = self.panel(T)
-                L11 = np.tril(P[:k, :k], -1) + np.eye(k)
+                L11 = self._L11_full(T)
                 t = x[f : f + k] - P[k:, :k].T @ x[rows]
                 x[f : f + k] = np.linalg.solve(L11.T, t)
         return x

@@ -170,37 +170,61 @@ dmma(double& c0, double& c1, double a, double b)
 // History (ncu, profiles/): a single fused kernel with the factorization unrolled on one warp was
 // instruction-fetch bound (42 us per CTA), a 128-thread rolled version issue-bound (~200 SASS instructions
 // per pivot on one warp per scheduler, 27 us); this split is ~3x faster per stage.
-constexpr int LDP      = 36; // leading dimension of the B-fragment operand: (4 k + n) mod 16 is conflict-free
-constexpr int DIAG_THR = 256;
+constexpr int LDP = 36; // leading dimension of the B-fragment operand: (4 k + n) mod 16 is conflict-free
 
-__global__ void __launch_bounds__(DIAG_THR)
-k_diag(const DiagTask* __restrict__ tasks,
-       const SnMeta* __restrict__ sn,
-       double* __restrict__ L,
-       double* __restrict__ Mt,
-       double* __restrict__ D,
-       double* __restrict__ Dinv,
-       const double* __restrict__ scal,
-       int* __restrict__ n_perturbed)
+// One panel step of one supernode: CTA rb owns RB rows below the NB x NB diagonal block (8 warps x 16 rows).
+// EVERY CTA of the step factors the diagonal block itself (shared memory, 256 threads, ~32 barriers) instead of
+// waiting for a separate kernel to publish it: the redundant arithmetic is free, the kernel boundary it replaces
+// cost ~10 us per step on the critical path of the factorization. The diagonal block of L is left as assembled
+// (nobody reads it afterwards: pivots, inverse block and L21 carry everything); CTA 0 publishes the pivots and
+// the inverse of the unit lower factor.
+constexpr int PANEL_THR = 256;
+
+__global__ void __launch_bounds__(PANEL_THR, 2)
+k_panel(const PanelTask* __restrict__ tasks,
+        const SnMeta* __restrict__ sn,
+        double* __restrict__ L,
+        double* __restrict__ Mt,
+        double* __restrict__ D,
+        double* __restrict__ Dinv,
+        const double* __restrict__ scal,
+        int* __restrict__ n_perturbed)
 {
-  __shared__ double A[NB][NB + 1];    // becomes the unit lower factor (strict lower part)
+  __shared__ double A[NB][NB + 1];    // becomes the unit lower factor (strict lower part, unscaled columns)
   __shared__ double Ainv[NB][NB + 1]; // becomes its inverse
   __shared__ double dsh[NB], dinv[NB];
-  const DiagTask t = tasks[blockIdx.x];
-  const SnMeta s   = sn[t.sn];
-  const int h      = s.k + s.r;
-  const int c0     = t.t * NB;
-  const int w      = min(NB, s.k - c0);
-  double* P        = L + s.Lptr;
+  __shared__ double Wm[NB][LDP]; // Wm[k][n] = L11^-1[n][k] / d_n
+  const PanelTask t = tasks[blockIdx.x];
+  const SnMeta s    = sn[t.sn];
+  const int h       = s.k + s.r;
+  const int c0      = t.t * NB;
+  const int w       = min(NB, s.k - c0);
+  double* P         = L + s.Lptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NWD = DIAG_THR / 32, EPT = NB / NWD; // entries per thread and pivot
+  constexpr int NWD = PANEL_THR / 32, EPT = NB / NWD; // entries per thread and pivot
+  constexpr int MI  = RB / NWD / 8;                   // 8-row DMMA fragments per warp
+  static_assert(RB == NWD * 8 * MI, "RB rows are split evenly over the warps");
 
+  // A fragments of this warp's rows straight from global memory (in flight during the factorization)
+  const int r0 = c0 + w + t.rb * RB + warp * (8 * MI);
+  double af[MI][8];
+  if (r0 < h)
+  {
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4)
+      {
+        const int row = r0 + mi * 8 + (lane >> 2), col = k4 * 4 + (lane & 3);
+        af[mi][k4]    = (row < h && col < w) ? P[(long long)(c0 + col) * h + row] : 0.0;
+      }
+  }
 #pragma unroll
   for (int u = 0; u < EPT; ++u)
   {
-    const int c    = warp + NWD * u;
-    A[lane][c]     = (lane < w && c <= lane) ? P[(long long)(c0 + c) * h + c0 + lane] : 0.0;
-    Ainv[lane][c]  = lane == c ? 1.0 : 0.0;
+    const int c   = warp + NWD * u;
+    A[lane][c]    = (lane < w && c <= lane) ? P[(long long)(c0 + c) * h + c0 + lane] : 0.0;
+    Ainv[lane][c] = lane == c ? 1.0 : 0.0;
   }
   const double tau = scal[1];
   int nper         = 0;
@@ -249,70 +273,42 @@ k_diag(const DiagTask* __restrict__ tasks,
     }
     __syncthreads();
   }
-  if (tid == 0 && nper)
+  if (t.rb == 0)
   {
-    atomicAdd(n_perturbed, nper);
-  }
-  if (tid < w)
-  {
-    D[s.first + c0 + tid]    = dsh[tid];
-    Dinv[s.first + c0 + tid] = dinv[tid];
-  }
-  double* M = Mt + s.Lptr;
-#pragma unroll
-  for (int u = 0; u < EPT; ++u)
-  {
-    const int c = warp + NWD * u;
-    if (lane < w && c <= lane)
+    if (tid == 0 && nper)
     {
-      P[(long long)(c0 + c) * h + c0 + lane] = lane == c ? 1.0 : A[lane][c] * dinv[c];
-      M[(long long)(c0 + c) * h + c0 + lane] = Ainv[lane][c];
+      atomicAdd(n_perturbed, nper);
+    }
+    if (tid < w)
+    {
+      D[s.first + c0 + tid]    = dsh[tid];
+      Dinv[s.first + c0 + tid] = dinv[tid];
+    }
+    double* M = Mt + s.Lptr;
+#pragma unroll
+    for (int u = 0; u < EPT; ++u)
+    {
+      const int c = warp + NWD * u;
+      if (lane < w && c <= lane)
+      {
+        M[(long long)(c0 + c) * h + c0 + lane] = Ainv[lane][c];
+      }
     }
   }
-}
-
-__global__ void __launch_bounds__(RB)
-k_trsm(const PanelTask* __restrict__ tasks,
-       const SnMeta* __restrict__ sn,
-       double* __restrict__ L,
-       const double* __restrict__ Mt,
-       const double* __restrict__ D)
-{
-  __shared__ double Wm[NB][LDP]; // Wm[k][n] = L11^-1[n][k] / d_n
-  const PanelTask t = tasks[blockIdx.x];
-  const SnMeta s    = sn[t.sn];
-  const int h       = s.k + s.r;
-  const int c0      = t.t * NB;
-  const int w       = min(NB, s.k - c0);
-  double* P         = L + s.Lptr;
-  const double* M   = Mt + s.Lptr;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r0 = c0 + w + t.rb * RB + warp * 32;
-  double af[4][8];
-  if (r0 < h)
+  // L21 = F21 * L11^-T D^-1 as a 32x32x32 DMMA product per warp with the inverted block
+  for (int idx = tid; idx < NB * NB; idx += PANEL_THR)
   {
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4)
-      {
-        const int row = r0 + mi * 8 + (lane >> 2), col = k4 * 4 + (lane & 3);
-        af[mi][k4]    = (row < h && col < w) ? P[(long long)(c0 + col) * h + row] : 0.0;
-      }
-  }
-  for (int idx = tid; idx < NB * NB; idx += RB)
-  {
-    const int n = idx % NB, kk = idx / NB; // consecutive threads -> consecutive rows n of column kk
-    Wm[kk][n]   = (n < w && kk <= n) ? M[(long long)(c0 + kk) * h + c0 + n] / D[s.first + c0 + n] : 0.0;
+    const int n = idx % NB, kk = idx / NB;
+    Wm[kk][n]   = (n < w && kk <= n) ? Ainv[n][kk] * dinv[n] : 0.0;
   }
   __syncthreads();
   if (r0 >= h)
   {
     return;
   }
-  double acc[4][4][2];
+  double acc[MI][4][2];
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
+  for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
     for (int nj = 0; nj < 4; ++nj)
     {
@@ -329,7 +325,7 @@ k_trsm(const PanelTask* __restrict__ tasks,
       bf[nj] = Wm[k4 * 4 + (lane & 3)][nj * 8 + (lane >> 2)];
     }
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
+    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
       for (int nj = 0; nj < 4; ++nj)
       {
@@ -337,7 +333,7 @@ k_trsm(const PanelTask* __restrict__ tasks,
       }
   }
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
+  for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
     for (int nj = 0; nj < 4; ++nj)
 #pragma unroll
@@ -775,14 +771,9 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
       k_extend_add<<<(unsigned)(st.ea_end - st.ea_begin), 32 * EA_COLS, 0, stream>>>(dp.ea_tasks.p + st.ea_begin, dp.sn.p, dp.rel.p, nb.L, nb.U);
       lc.tick("extend_add");
     }
-    if (st.diag_end > st.diag_begin)
-    {
-      k_diag<<<(unsigned)(st.diag_end - st.diag_begin), DIAG_THR, 0, stream>>>(dp.diag_tasks.p + st.diag_begin, dp.sn.p, nb.L, nb.Mt, nb.D, nb.Dinv, nb.scal, nb.n_perturbed);
-      lc.tick("panel");
-    }
     if (st.pan_end > st.pan_begin)
     {
-      k_trsm<<<(unsigned)(st.pan_end - st.pan_begin), RB, 0, stream>>>(dp.pan_tasks.p + st.pan_begin, dp.sn.p, nb.L, nb.Mt, nb.D);
+      k_panel<<<(unsigned)(st.pan_end - st.pan_begin), PANEL_THR, 0, stream>>>(dp.pan_tasks.p + st.pan_begin, dp.sn.p, nb.L, nb.Mt, nb.D, nb.Dinv, nb.scal, nb.n_perturbed);
       lc.tick("panel");
     }
     if (st.upd_end > st.upd_begin)

@@ -19,7 +19,7 @@ namespace b200
 typedef int64_t i64;
 
 constexpr int NB       = 32;  // panel width of the blocked dense LDL^T
-constexpr int RB       = 128; // rows per TRSM row-block CTA
+constexpr int RB       = 128; // rows of L21 per CTA of a panel step (8 warps x 16 rows)
 constexpr int TILE     = 64;  // output tile edge of the DMMA update kernel
 constexpr int NBO      = 128; // outer block: columns beyond it are updated once per outer block with K = NBO
 constexpr int EA_COLS  = 4;   // update-matrix columns per extend-add task (one warp each)
@@ -48,7 +48,8 @@ struct DiagTask
 
 struct PanelTask
 {
-  int sn, t, rb, pad; // RB rows of L21 below the diagonal block
+  int sn, t, rb, pad; // panel step t of a supernode: CTA rb owns RB rows of L21 below the diagonal block (there is
+                      // always a CTA 0, it publishes the pivots and the inverse of the diagonal block)
 };
 
 struct EaTask

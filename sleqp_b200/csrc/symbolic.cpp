@@ -1445,7 +1445,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         const int w  = std::min(NB, k - c0);
         const int below = h - c0 - w;
         P.diag_tasks.push_back({T, t});
-        for (int rb = 0; rb * RB < below; ++rb)
+        for (int rb = 0; rb == 0 || rb * RB < below; ++rb)
         {
           P.pan_tasks.push_back({T, t, rb, 0});
         }
