@@ -88,13 +88,13 @@ class ClockSampler:
 
 def ncu_traffic_per_launch(kernel, workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of the same workload (profiles/, one sweep = one launch per tree level); None if
-    there is no capture for this workload."""
+    `ncu --set full` capture of the same workload (profiles/, one sweep = one launch); None if there is no capture
+    for this workload."""
     import csv
 
     if "config2" not in workload:
         return None
-    path = os.path.join(ROOT, "profiles", f"ncu_full_{kernel}_config2.csv")
+    path = os.path.join(ROOT, "profiles", f"r01_ncu_full_{kernel}_config2.csv")
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
@@ -322,18 +322,19 @@ def run_ours(args, rank, world, local_rank):
     solve_ms = float(phases.sum())
     peaks, peak_src = load_peaks()
     n_solves = len(rhs)
-    share = {"numeric_factor(graph)": factor_ms, "k_fwd_chunk": phases[1] * n_solves, "k_bwd_chunk": phases[2] * n_solves,
+    # one dataflow kernel launch per sweep (solve.cu: k_flow<forward> / k_flow<backward>); the forward phase also
+    # holds the reset of the accumulators (k_flow_reset, ~2 us)
+    share = {"numeric_factor(graph)": factor_ms, "k_flow_fwd": phases[1] * n_solves, "k_flow_bwd": phases[2] * n_solves,
              "k_pre+k_post": (phases[0] + phases[3]) * n_solves}
-    dom = max(("k_fwd_chunk", "k_bwd_chunk"), key=lambda x: share[x])
-    nlev = st["n_levels"]
+    dom = max(("k_flow_fwd", "k_flow_bwd"), key=lambda x: share[x])
     # algorithmic bytes of one sweep: the factor once (exact nnz(L), 8 B), the row indices of
     # every supernode (4 B), the right-hand side in and out (8 B each), plus the pivots for the backward sweep
-    sweep_bytes = 8 * st["nnz_L"] + 4 * st["n_row_idx"] + 16 * st["n_reduced"] + (8 * st["n_reduced"] if dom == "k_bwd_chunk" else 0)
-    sweep_ms = float(phases[1] if dom == "k_fwd_chunk" else phases[2])
+    sweep_bytes = 8 * st["nnz_L"] + 4 * st["n_row_idx"] + 16 * st["n_reduced"] + (8 * st["n_reduced"] if dom == "k_flow_bwd" else 0)
+    sweep_ms = float(phases[1] if dom == "k_flow_fwd" else phases[2])
     achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": ncu_traffic_per_launch(dom, p.name), "peak_source": peak_src, "launches_per_sweep": nlev,
-                "bytes_per_launch": sweep_bytes / nlev, "ms_per_launch": sweep_ms / nlev,
+                "traffic": ncu_traffic_per_launch(dom, p.name), "peak_source": peak_src, "launches_per_sweep": 1,
+                "bytes_per_launch": sweep_bytes, "ms_per_launch": sweep_ms, "tree_levels": st["n_levels"],
                 "step_share_ms": {k_: float(v_) for k_, v_ in share.items()}}
 
     # ---- end to end through the plugin calls with host buffers ------------------------------------------
@@ -369,7 +370,8 @@ def run_ours(args, rank, world, local_rank):
         return out
 
     h2d = 8 * len(w["v"]) + sum(8 * len(val) for _, _, val, _, _ in rhs) + 8 * p.m + 8 * p.n * (k + 1)
-    d2h = sum(8 * (e - b) for _, _, _, b, e in rhs) + 8 * p.n + 8 * p.n * k + 8 * p.m
+    # a solution slice comes back sparsified: values (8 B) + indices (4 B), copied at full length (fact.cu)
+    d2h = sum(12 * (e - b) for _, _, _, b, e in rhs) + 8 * p.n + 8 * p.n * k + 8 * p.m
     e2e_steps = max(3, min(args.steps, 10))
     host_step()
     barrier()

@@ -27,6 +27,7 @@
 #ifndef SLEQP_B200_H
 #define SLEQP_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -219,6 +220,12 @@ B200_API int b200_cg_solve(b200_cg* handle, int n, int nnz_g, const int* g_idx, 
 B200_API int b200_cg_free(b200_cg** handle);
 
 /* ---- misc ------------------------------------------------------------------------------ */
+/* Page-locks / releases a caller-owned host buffer (cudaHostRegister). Every entry point that takes a host
+ * buffer lets the copy engine read or write it directly when it is page-locked and stages through the
+ * handle's own pinned buffer otherwise; an integrator that keeps its vectors alive across calls (as the
+ * aug_jac does with its rhs / sol caches, standard_aug_jac.c:306-435) pins them once. */
+B200_API int b200_host_pin(void* ptr, size_t bytes);
+B200_API int b200_host_unpin(void* ptr);
 B200_API int b200_device_count(void);
 /* Number of kernel launches issued by this library on this process so far (bench.py's
  * "gpu_launches" claim; graph replays count their kernel nodes). */

@@ -77,12 +77,11 @@ class Emulated:
         scratch = np.full(max(1, int(p["n_scratch_slots"]) if "n_scratch_slots" in p else 1) * NB * NB, np.nan)
         has_children = np.diff(p["child_ptr"]) > 0
         for st in p["stages"]:
-            zb, ze, eb, ee, db, de, pb, pe, ub, ue = (int(x) for x in st)
+            zb, ze, eb, ee, pb, pe, ub, ue = (int(x) for x in st)
             for T in p["zero_sn"][zb:ze]:
                 self.umat(T)[:, :] = 0.0
             for c, jb in p["ea_tasks"][eb:ee]:
                 self._extend_add(int(c), int(jb))
-            assert [tuple(x) for x in p["diag_tasks"][db:de]] == [(T, t) for T, t, rb, _ in p["pan_tasks"][pb:pe] if rb == 0]
             for T, t, rb, _pad in p["pan_tasks"][pb:pe]:
                 self._panel(int(T), int(t), int(rb))
             for T, t, kind, i0, j0, kb, ke in p["upd_tasks"][ub:ue]:
@@ -123,48 +122,6 @@ class Emulated:
                 else:  # Z: Minv[k + i, j] = -sum_q L21[i, q] Linv[q, j]
                     i1, j1 = min(i0 + TILE, r), min(j0 + TILE, k)
                     M[k + i0 : k + i1, j0:j1] = -(P[k + i0 : k + i1, kb:ke] @ M[kb:ke, j0:j1])
-
-    def solve_reduced_minv(self, b_new):
-        """The v2 device solve: per supernode y = Minv b (forward), x = Minv^T [z; x_rows] (backward),
-        executed chunk task by chunk task."""
-        p = self.p
-        W = np.full(int(p["Wptr"][-1]), np.nan)
-        y = np.full(self.m, np.nan)
-        x = np.full(self.m, np.nan)
-        for lv in range(int(p["n_levels"])):
-            for T, row0, nrows in p["fwd_tasks"][int(p["fwd_ptr"][lv]) : int(p["fwd_ptr"][lv + 1]), :3]:
-                T, row0, nrows = int(T), int(row0), int(nrows)
-                f, k, r, h = self._geom(T)
-                M = self.mpanel(T)
-                bT = b_new[f : f + k].copy()
-                out = np.zeros(nrows)
-                for c in p["child_idx"][int(p["child_ptr"][T]) : int(p["child_ptr"][T + 1])]:
-                    c = int(c)
-                    fc, kc, rc, hc = self._geom(c)
-                    rel = p["rel"][int(p["Rptr"][c]) : int(p["Rptr"][c + 1])]
-                    wc = W[int(p["Wptr"][c]) + kc : int(p["Wptr"][c]) + hc]
-                    nc = int(p["sn_ncol"][c])
-                    assert np.all(rel[:nc] < k) and np.all(rel[nc:] >= k)
-                    np.add.at(bT, rel[:nc], wc[:nc])
-                    lo, hi = np.searchsorted(rel, [max(row0, k), row0 + nrows])
-                    np.add.at(out, rel[lo:hi] - row0, wc[lo:hi])
-                rows = np.arange(row0, row0 + nrows)
-                Mc = M[rows, :k].copy()
-                top = rows < k
-                Mc[top] = np.tril(M[:k, :k])[rows[top]]
-                out += Mc @ bT
-                y[f + rows[top]] = out[top]
-                W[int(p["Wptr"][T]) + rows[~top]] = out[~top]
-        for lv in range(int(p["n_levels"]) - 1, -1, -1):
-            for T, col0, ncols in p["bwd_tasks"][int(p["bwd_ptr"][lv]) : int(p["bwd_ptr"][lv + 1]), :3]:
-                T, col0, ncols = int(T), int(col0), abs(int(ncols))  # negative: tall-front variant, same math
-                f, k, r, h = self._geom(T)
-                rows = p["Ridx"][int(p["Rptr"][T]) : int(p["Rptr"][T + 1])]
-                M = self.mpanel(T)
-                v = np.concatenate([y[f : f + k] / self.D[f : f + k], x[rows]])
-                Mfull = np.vstack([np.tril(M[:k, :k]), M[k:, :k]])
-                x[f + col0 : f + col0 + ncols] = Mfull[:, col0 : col0 + ncols].T @ v
-        return x
 
     def row_major_copy(self):
         """Mr as k_transpose leaves it: only the 32x32 tiles of tr_tasks are written, the rest of the buffer is
@@ -377,7 +334,7 @@ class Emulated:
                 x[f : f + k] = np.linalg.solve(L11.T, t)
         return x
 
-    def solve(self, rhs, refine=1, minv=True, flow=False):
+    def solve(self, rhs, refine=1, flow=True):
         """Full K solve in original K indices, block elimination around the reduced system."""
         p, kv = self.p, self.kval
         ke, kr = p["k_of_e"], p["k_of_r"]
@@ -390,7 +347,7 @@ class Emulated:
         def once(b):
             t = b[ke] / dE
             bR = b[kr] - A @ t
-            lam_new = (self.solve_reduced_flow if flow else self.solve_reduced_minv if minv else self.solve_reduced)(bR[p["perm"]])
+            lam_new = (self.solve_reduced_flow if flow else self.solve_reduced)(bR[p["perm"]])
             lam = np.empty(self.m)
             lam[p["perm"]] = lam_new
             z = np.empty(self.N)

@@ -231,25 +231,15 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
   FIELD(lvl_sn)
   FIELD(inv_phase_ptr)
   FIELD(Tptr)
-  FIELD(sn_ncol)
-  FIELD(cptr)
-  FIELD(cidx)
-  FIELD(fwd_ptr)
-  FIELD(bwd_ptr)
-  FIELD(lvl_maxh)
 #undef FIELD
   if (f == "stages")
   {
-    static_assert(sizeof(Stage) == 10 * sizeof(int), "Stage layout");
+    static_assert(sizeof(Stage) == 8 * sizeof(int), "Stage layout");
     return export_vec(P.stages, out, count);
   }
   if (f == "ea_tasks")
   {
     return export_vec(P.ea_tasks, out, count);
-  }
-  if (f == "diag_tasks")
-  {
-    return export_vec(P.diag_tasks, out, count);
   }
   if (f == "pan_tasks")
   {
@@ -258,14 +248,6 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
   if (f == "inv_tasks")
   {
     return export_vec(P.inv_tasks, out, count);
-  }
-  if (f == "fwd_tasks")
-  {
-    return export_vec(P.fwd_tasks, out, count);
-  }
-  if (f == "bwd_tasks")
-  {
-    return export_vec(P.bwd_tasks, out, count);
   }
   if (f == "tr_tasks")
   {

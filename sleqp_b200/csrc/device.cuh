@@ -145,7 +145,6 @@ struct SnMeta
   long long Lptr;
   long long Uoff;
   long long Rptr;
-  long long Wptr;
   long long Tptr;
   int first;
   int k;
@@ -153,8 +152,7 @@ struct SnMeta
   int parent;
   int child_begin;
   int child_end;
-  int ncol; // update rows that are columns of the parent (a prefix of the row list)
-  int pad0, pad1, pad2;
+  int pad0, pad1, pad2, pad3, pad4, pad5;
 };
 
 // Device copy of a Plan (per handle).
@@ -162,22 +160,18 @@ struct DevPlan
 {
   std::shared_ptr<const Plan> plan;
   DevBuf<SnMeta> sn;
-  DevBuf<int> Ridx, rel, child_idx, cptr, cidx;
+  DevBuf<int> Ridx, rel, child_idx;
   // assembly
   DevBuf<long long> Sdest, Sterm_ptr, Sdiag;
   DevBuf<int> Sgsrc, Sterm_a, Sterm_b, Sterm_d;
   // tasks
   DevBuf<int> zero_sn;
   DevBuf<EaTask> ea_tasks;
-  DevBuf<DiagTask> diag_tasks;
   DevBuf<PanelTask> pan_tasks;
   DevBuf<Task5> upd_tasks;
   DevBuf<int> lvl_sn;
   DevBuf<InvTask> inv_tasks;
   DevBuf<TrTask> tr_tasks;
-  DevBuf<FwdTask> fwd_tasks;
-  DevBuf<int> fwd_ptr, bwd_ptr; // per-level task offsets (for the fused top-of-tree kernels)
-  DevBuf<BwdTask> bwd_tasks;
   DevBuf<SweepTask> ffl_tasks, bfl_tasks; // dataflow sweeps
   // E-part / residual operators
   DevBuf<int> k_of_e, k_of_r, pinv, perm, dE_src;

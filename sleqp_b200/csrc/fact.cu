@@ -47,8 +47,9 @@ struct b200_fact
   DevBuf<double> val, L, Mt, Mr, tmp, U, D, Dinv, scratch, scal, dE, Acsc_val, Acsr_val, Gsym_val;
   DevBuf<int> nper;
   // solve
-  DevBuf<double> rhs, z, res, dz, bR, y, yf, x, W;
-  DevBuf<int> rhs_idx, flow;
+  DevBuf<double> rhs, z, res, dz, bR, y, yf, x;
+  DevBuf<int> rhs_idx, flow, cp_idx, cp_cnt; // cp_*: device-side sparsification of a solution slice
+  DevBuf<double> cp_val;
   DevBuf<double> rhs_val;
   PinnedBuf<int> h_rhs_idx;
   PinnedBuf<double> h_rhs_val, h_sol, h_scal;
@@ -97,7 +98,6 @@ struct b200_fact
     sb.y   = y.p;
     sb.yf  = yf.p;
     sb.x   = x.p;
-    sb.W   = W.p;
     sb.flow = flow.p;
     return sb;
   }
@@ -169,9 +169,7 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
     m.Lptr        = P.Lptr[T];
     m.Uoff        = P.Uoff[T];
     m.Rptr        = P.Rptr[T];
-    m.Wptr        = P.Wptr[T];
     m.Tptr        = P.Tptr[T];
-    m.ncol        = P.sn_ncol[T];
     m.first       = P.sn_first[T];
     m.k           = P.sn_first[T + 1] - P.sn_first[T];
     m.r           = (int)(P.Rptr[T + 1] - P.Rptr[T]);
@@ -201,16 +199,11 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   dp.Sterm_d.upload(P.Sterm_d, s);
   dp.zero_sn.upload(P.zero_sn, s);
   dp.ea_tasks.upload(P.ea_tasks, s);
-  dp.diag_tasks.upload(P.diag_tasks, s);
   dp.pan_tasks.upload(P.pan_tasks, s);
   dp.upd_tasks.upload(P.upd_tasks, s);
   dp.lvl_sn.upload(P.lvl_sn, s);
   dp.inv_tasks.upload(P.inv_tasks, s);
   dp.tr_tasks.upload(P.tr_tasks, s);
-  dp.fwd_tasks.upload(P.fwd_tasks, s);
-  dp.fwd_ptr.upload(P.fwd_ptr, s);
-  dp.bwd_ptr.upload(P.bwd_ptr, s);
-  dp.bwd_tasks.upload(P.bwd_tasks, s);
   dp.ffl_tasks.upload(P.ffl_tasks, s);
   dp.bfl_tasks.upload(P.bfl_tasks, s);
   dp.k_of_e.upload(P.k_of_e, s);
@@ -316,6 +309,32 @@ b200_device_count(void)
     return 0;
   }
   return n;
+}
+
+int
+b200_host_pin(void* ptr, size_t bytes)
+{
+  if (!ptr || bytes == 0)
+  {
+    return set_error(B200_ERR_ARG, "null buffer");
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return (int)B200_OK;
+  });
+}
+
+int
+b200_host_unpin(void* ptr)
+{
+  if (!ptr)
+  {
+    return set_error(B200_ERR_ARG, "null buffer");
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaHostUnregister(ptr));
+    return (int)B200_OK;
+  });
 }
 
 int64_t
@@ -837,6 +856,28 @@ b200_fact_solution(b200_fact* F, int begin, int end, double* out_dense)
 int
 b200_fact_solution_sparse(b200_fact* F, int begin, int end, double zero_eps, int* idx_out, double* val_out, int* nnz_out)
 {
+  // Page-locked outputs: the slice is sparsified on the device (sleqp_vec_set_from_raw, vec.c:72-104) and both
+  // arrays are DMA'd straight into the caller's buffers -- no host pass over the values. (The arrays are copied at
+  // full length so that one synchronisation serves the count and the data.)
+  if (F && F->solved && nnz_out && idx_out && val_out && end > begin && begin >= 0 && F->dp.plan && end <= F->dp.plan->N && is_pinned_host(val_out) && is_pinned_host(idx_out))
+  {
+    return guarded([&]() {
+      B200_CUDA(cudaSetDevice(F->device));
+      const int n       = end - begin;
+      const int nchunks = compact_chunks(n);
+      F->cp_idx.reserve((size_t)n);
+      F->cp_val.reserve((size_t)n);
+      F->cp_cnt.reserve((size_t)nchunks + 1);
+      LaunchCounter eager;
+      enqueue_compact(F->z.p + begin, n, zero_eps, F->cp_cnt.p, F->cp_idx.p, F->cp_val.p, F->stream, eager);
+      B200_CUDA(cudaMemcpyAsync(F->h_nper.p + 1, F->cp_cnt.p + nchunks, sizeof(int), cudaMemcpyDeviceToHost, F->stream));
+      B200_CUDA(cudaMemcpyAsync(val_out, F->cp_val.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, F->stream));
+      B200_CUDA(cudaMemcpyAsync(idx_out, F->cp_idx.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, F->stream));
+      B200_CUDA(cudaStreamSynchronize(F->stream));
+      *nnz_out = F->h_nper.p[1];
+      return (int)B200_OK;
+    });
+  }
   const double* p = nullptr;
   int rc          = b200_fact_solution_ptr(F, begin, end, &p);
   if (rc != B200_OK)

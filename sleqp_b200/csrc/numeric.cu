@@ -6,7 +6,7 @@
 // (fact_cholmod.c:137). Kernels (all FP64):
 //   k_assemble      one thread per entry of tril(S): gathers its product terms      (HBM-bound)
 //   k_extend_add    child update matrix -> parent front (relative indices)         (HBM-bound)
-//   k_diag/k_trsm   NB-wide panel step: LDL^T + inverse of the diagonal block in shared memory, then
+//   k_panel         NB-wide panel step: LDL^T + inverse of the diagonal block in shared memory, then
 //                   L21 = F21 L11^-T D^-1 as a DMMA product with the inverted block       (latency/HBM)
 //   k_update        64x64 output tiles of C -= L_i D L_j^T on the FP64 tensor cores
 //                   (mma.sync m8n8k4.f64 = DMMA), operands staged through shared memory
@@ -157,19 +157,17 @@ dmma(double& c0, double& c1, double a, double b)
 // ---------------------------------------------------------------------------------------------
 // Panel step t of supernode T, columns [c0, c0+w) of the front (w <= NB), in two kernels:
 //
-// k_diag  (one CTA of 256 threads per step): right-looking LDL^T of the w x w diagonal block with static
-//   pivoting and, in the same sweep, the inverse of its unit lower factor (the elimination steps applied
-//   to the identity). Thread (lane = row i, warp = column class c mod 8) owns 4 entries of the 32 x 32
-//   work per pivot; one barrier per pivot; shared-memory read-modify-writes are batched (all loads, then
-//   all stores). Column j stays unscaled (f_ij) inside the loop: l_ij d_j l_cj = f_ij f_cj / d_j.
-//   Publishes L11 (in place), the pivots and L11^-1 (into the inverse panel).
-// k_trsm  (one CTA of 128 threads per RB rows): L21 = F21 * L11^-T D^-1 as a 32x32x32 DMMA product per
-//   warp with the inverted block: A fragments straight from global memory, B fragments
-//   Wm[k][n] = L11^-1[n][k] / d_n from shared memory. The triangular solve is a tensor-core GEMM.
+// k_panel (one CTA of 256 threads per RB rows of a panel step): right-looking LDL^T of the w x w diagonal block with
+//   static pivoting and, in the same sweep, the inverse of its unit lower factor (the elimination steps applied to
+//   the identity). Thread (lane = row i, warp = column class c mod 8) owns 4 entries of the 32 x 32 work per pivot;
+//   one barrier per pivot; shared-memory read-modify-writes are batched (all loads, then all stores). Column j stays
+//   unscaled (f_ij) inside the loop: l_ij d_j l_cj = f_ij f_cj / d_j. Then L21 = F21 * L11^-T D^-1 as a DMMA product
+//   with the inverted block: A fragments straight from global memory (loaded before the factorization starts), B
+//   fragments Wm[k][n] = L11^-1[n][k] / d_n from shared memory. The triangular solve is a tensor-core GEMM.
 //
-// History (ncu, profiles/): a single fused kernel with the factorization unrolled on one warp was
-// instruction-fetch bound (42 us per CTA), a 128-thread rolled version issue-bound (~200 SASS instructions
-// per pivot on one warp per scheduler, 27 us); this split is ~3x faster per stage.
+// History (ncu, profiles/): a single fused kernel with the factorization unrolled on one warp was instruction-fetch
+// bound (42 us per CTA), a 128-thread rolled version issue-bound (27 us); a 256-thread factorization kernel followed
+// by a separate DMMA kernel cost two launches per step; every CTA factoring the block itself removes one of them.
 constexpr int LDP = 36; // leading dimension of the B-fragment operand: (4 k + n) mod 16 is conflict-free
 
 // One panel step of one supernode: CTA rb owns RB rows below the NB x NB diagonal block (8 warps x 16 rows).

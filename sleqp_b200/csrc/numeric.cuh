@@ -11,7 +11,7 @@ struct NumericBuffers
   const double* val; // values of tril(K), same order as the caller's CSC
   double* L;         // supernodal panels [L11; L21]
   double* Mt;        // inverse panels [L11^-1; -L21 L11^-1] (what the solves read)
-  double* Mr;        // row-major copy of the inverse panels (forward sweep reads rows)
+  double* Mr;        // row-major copy of the inverse panels (the backward sweep reads it)
   double* tmp;       // k x k scratch of the selective inversion
   double* U;         // update-matrix workspace
   double* D;         // pivots of S (new labels)
@@ -35,13 +35,12 @@ struct SolveBuffers
   double* y;    // m, right-hand side of the reduced system, accumulates the updates of the forward sweep
   double* yf;   // m, forward result (new labels)
   double* x;    // m, solution of the reduced system (new labels)
-  double* W;    // front vectors (sum of front heights)
   const void* trace_fwd = nullptr; // device FlowTrace records (profile entry point with B200_FLOW_TRACE=1 only)
   const void* trace_bwd = nullptr;
   int* flow;    // dataflow sweeps: [0, ns) forward counters, [ns, 2 ns) backward counters, then the two ticket counters
 };
 
-// raise the dynamic shared-memory limit of the solve kernels (once per process, before capture)
+// one-time process-wide configuration of the kernels (before any capture)
 void configure_solve_kernels();
 void configure_numeric_kernels();
 
@@ -66,6 +65,11 @@ void enqueue_probe_rhs(double* rhs, int n, cudaStream_t stream, LaunchCounter& l
 
 // min/max |d| over both pivot sets -> scal[2], scal[3]
 void enqueue_pivot_range(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc);
+
+// Sparsification of x[0, n) on the device (sleqp_vec_set_from_raw, vec.c:72-104): the entries with |x_i| > eps in
+// ascending order -> (idx_out, val_out), their number -> chunk_cnt[compact_chunks(n)]. chunk_cnt: compact_chunks(n) + 1 ints.
+void enqueue_compact(const double* x, int n, double eps, int* chunk_cnt, int* idx_out, double* val_out, cudaStream_t stream, LaunchCounter& lc);
+int compact_chunks(int n);
 
 // out[i] = dE[i] for i < nE, D[i - nE] otherwise
 void enqueue_copy_pivots(const DevPlan& dp, const NumericBuffers& nb, double* out, cudaStream_t stream, LaunchCounter& lc);

@@ -41,11 +41,6 @@ struct Task5
   int kb, ke;                 // inner (front column) range
 };
 
-struct DiagTask
-{
-  int sn, t; // factor + invert the NB x NB diagonal block of panel step t
-};
-
 struct PanelTask
 {
   int sn, t, rb, pad; // panel step t of a supernode: CTA rb owns RB rows of L21 below the diagonal block (there is
@@ -79,20 +74,6 @@ struct TrTask
   int sn, i0, j0; // 32x32 tile of a panel to transpose into the row-major copy
 };
 
-// The sweep tasks carry the geometry they need, so a CTA starts loading panel data after ONE dependent
-// load (the task) instead of two (task -> supernode record).
-struct FwdTask
-{
-  int sn, row0, nrows, first, k, wide; // wide: all warps of the CTA share each row (fronts with many columns)
-  long long Lptr, Rptr;
-};
-
-struct BwdTask
-{
-  int sn, col0, ncols, first, k, h; // ncols < 0: tall front, the CTA's warps share each of its -ncols columns
-  long long Lptr, Rptr;
-};
-
 // Warp task of the dataflow sweeps (solve.cu: k_flow). One warp owns a block of a supernode's inverse panel,
 // rows [i0, i1) x columns [j0, j1), one lane per output and at most 16 panel entries per lane:
 //   forward : lanes = rows (i1 - i0 <= 32), depth = columns (j1 - j0 <= 16), column-major panel Mt; partial sums
@@ -123,7 +104,6 @@ struct Stage
 {
   int zero_begin, zero_end;
   int ea_begin, ea_end;
-  int diag_begin, diag_end;
   int pan_begin, pan_end;
   int upd_begin, upd_end;
 };
@@ -155,7 +135,7 @@ struct Plan
   std::vector<int> Ridx; // update rows (new labels), ascending
   std::vector<int> rel;  // position of each update row in the parent's front
   std::vector<i64> Lptr; // nsuper+1, panel offsets (doubles); panel is h x k column-major
-  std::vector<i64> Wptr; // nsuper+1, prefix sum of front heights (solve front vectors)
+  std::vector<i64> Wptr; // nsuper+1, prefix sum of front heights
   std::vector<int> child_ptr, child_idx;
 
   // assembly of S straight into the panels: S_e = val[gsrc] - sum_t val[a]*val[b]/val[d]
@@ -175,7 +155,6 @@ struct Plan
   std::vector<Stage> stages;
   std::vector<int> zero_sn;
   std::vector<EaTask> ea_tasks;
-  std::vector<DiagTask> diag_tasks;
   std::vector<PanelTask> pan_tasks;
   std::vector<Task5> upd_tasks;
   int n_scratch_slots = 0;
@@ -186,17 +165,9 @@ struct Plan
   std::vector<TrTask> tr_tasks;
   std::vector<i64> Tptr; // nsuper+1, k x k scratch of the inversion (only supernodes wider than NB)
 
-  // solve schedule (levels of the supernodal tree)
+  // levels of the supernodal tree (height above the leaves)
   int nlevels = 0;
   std::vector<int> lvl_ptr, lvl_sn;
-  // contributor lists (inverse of rel): front row i of supernode T (global index Wptr[T] + i) receives
-  // W[cidx[e]] for e in [cptr[Wptr[T] + i], cptr[Wptr[T] + i + 1]), children in ascending order
-  std::vector<int> cptr, cidx;
-  std::vector<int> sn_ncol; // number of a supernode's update rows that are columns of its parent
-  std::vector<FwdTask> fwd_tasks;
-  std::vector<BwdTask> bwd_tasks;
-  std::vector<int> fwd_ptr, bwd_ptr; // per level ranges into the task arrays
-  std::vector<int> lvl_maxh;
   // dataflow sweeps: tasks in topological (ticket) order
   std::vector<SweepTask> ffl_tasks, bfl_tasks;
 

@@ -2,24 +2,19 @@
 // vendor calls replaced: umfpack_di_solve fact_umfpack.c:220, cholmod_l_solve fact_cholmod.c:184).
 //
 //   K = [D A^T; A G]:  t = b_E / d,  b_R' = b_R - A t,  S y = b_R',  z_R = y,  z_E = (b_E - A^T y) / d
-// The reduced system is solved with level-scheduled supernodal forward / diagonal / backward
-// sweeps over the inverse panels (selective inversion): every supernode step is a matrix-vector product.
+// The reduced system is solved with two dataflow sweeps (one kernel launch each) over the inverse panels (selective
+// inversion): every supernode step is a matrix-vector product, cut into warp tasks that synchronise through
+// per-supernode counters.
 // Iterative refinement runs against the unperturbed K (SURVEY.md hard part 1).
 #include "numeric.cuh"
-
-#include <cooperative_groups.h>
 
 #include <algorithm>
 #include <mutex>
 #include <string>
 #include <cstdlib>
 
-namespace cg = cooperative_groups;
-
 namespace b200
 {
-
-constexpr int SOLVE_THREADS = 128;
 
 // ---- E-block elimination and back-substitution -------------------------------------------------
 __global__ void
@@ -150,492 +145,6 @@ k_axpy1(int n, const double* __restrict__ x, double* __restrict__ y)
   if (i < n)
   {
     y[i] += x[i];
-  }
-}
-
-// ---- forward sweep ---------------------------------------------------------------------------------
-// One CTA per (supernode, row chunk). With the inverse panel Minv = [L11^-1; -L21 L11^-1] the whole
-// supernode step is one matrix-vector product  [y_T; delta_tail] = Minv * b_T. The right-hand side lives in
-// one global accumulator `yacc`: b_T = yacc[cols of T] already holds every update from T's descendants
-// (they ran in earlier launches); tail results are pushed straight to their final rows with native FP64
-// atomics (yacc[row] += delta), so there is no per-supernode front vector, no pass-through copying and the
-// dependent-load chain of a CTA is task -> yacc -> panel. Rows of the top block go to `yf`.
-// Reads the row-major copy Mr of the inverse panel: a warp owns RG rows at a time, lanes stride the
-// (contiguous) columns with 8 independent loads in flight; the first round of panel loads is issued
-// before b_T is staged. Dynamic shared memory: bT[k].
-template <int RG, int U>
-__device__ __forceinline__ void
-fwd_body(const FwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mr, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf, double* bT)
-{
-  const int k     = t.k;
-  const double* P = Mr + t.Lptr;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g0     = warp * RG;
-  const int nvalid = min(RG, t.nrows - g0); // <= 0: this warp has no rows
-  const int r0     = t.row0 + g0;
-  // the top block is lower triangular: row r only needs columns <= r; rows of one group share the bound
-  // of the last row (entries beyond a row's diagonal are zeros)
-  const int rlast = r0 + nvalid - 1;
-  const int jend  = nvalid <= 0 ? 0 : (rlast < k ? rlast + 1 : k);
-
-  double pre[RG][U];
-#pragma unroll
-  for (int a = 0; a < RG; ++a)
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      const int j = lane + 32 * u;
-      pre[a][u]   = (a < nvalid && j < jend) ? P[(long long)(r0 + a) * k + j] : 0.0;
-    }
-  // staged in batches of 4 independent loads per thread
-  for (int j = tid; j < k; j += 4 * SOLVE_THREADS)
-  {
-    double tmp[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-    {
-      const int jj = j + u * SOLVE_THREADS;
-      tmp[u]       = jj < k ? yacc[t.first + jj] : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-    {
-      const int jj = j + u * SOLVE_THREADS;
-      if (jj < k)
-      {
-        bT[jj] = tmp[u];
-      }
-    }
-  }
-  __syncthreads();
-  if (nvalid <= 0)
-  {
-    return; // no barrier follows inside this body
-  }
-  double acc[RG][U];
-#pragma unroll
-  for (int a = 0; a < RG; ++a)
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      const int j = lane + 32 * u;
-      acc[a][u]   = j < jend ? pre[a][u] * bT[j] : 0.0;
-    }
-  int j = lane + 32 * U;
-  for (; j + 32 * (U - 1) < jend; j += 32 * U)
-  {
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      const double bj = bT[j + 32 * u];
-#pragma unroll
-      for (int a = 0; a < RG; ++a)
-      {
-        if (a < nvalid)
-        {
-          acc[a][u] += P[(long long)(r0 + a) * k + j + 32 * u] * bj;
-        }
-      }
-    }
-  }
-  for (; j < jend; j += 32)
-  {
-    const double bj = bT[j];
-#pragma unroll
-    for (int a = 0; a < RG; ++a)
-    {
-      if (a < nvalid)
-      {
-        acc[a][0] += P[(long long)(r0 + a) * k + j] * bj;
-      }
-    }
-  }
-  double mine = 0.0;
-#pragma unroll
-  for (int a = 0; a < RG; ++a)
-  {
-    double v = 0.0;
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      v += acc[a][u];
-    }
-    for (int o = 16; o > 0; o >>= 1)
-    {
-      v += __shfl_xor_sync(0xffffffffu, v, o);
-    }
-    if (lane == a)
-    {
-      mine = v;
-    }
-  }
-  if (lane < nvalid)
-  {
-    const int r = r0 + lane;
-    if (r < k)
-    {
-      yf[t.first + r] = mine * Dinv[t.first + r]; // D^-1 y: the diagonal solve is folded into the forward sweep
-    }
-    else
-    {
-      atomicAdd(yacc + Ridx[t.Rptr + r - k], mine);
-    }
-  }
-}
-
-// Wide fronts (k >= 512): the CTA owns RG rows and its four warps split the columns of each of them, so a CTA
-// needs at most two rounds of loads; b_T is not staged, yacc is read directly (it is L2-resident: every CTA of
-// the supernode reads the same k values).
-template <int RG>
-__device__ __forceinline__ void
-fwd_wide(const FwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mr, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf, double* red)
-{
-  constexpr int U  = 8 / RG;
-  constexpr int NW = SOLVE_THREADS / 32;
-  const int k      = t.k;
-  const double* P  = Mr + t.Lptr;
-  const double* bT = yacc + t.first;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nvalid = min(RG, t.nrows);
-  const int r0     = t.row0;
-  const int rlast  = r0 + nvalid - 1;
-  const int jend   = rlast < k ? rlast + 1 : k;
-  double acc[RG];
-#pragma unroll
-  for (int a = 0; a < RG; ++a)
-  {
-    acc[a] = 0.0;
-  }
-  for (int j0 = 0; j0 < jend; j0 += SOLVE_THREADS * U)
-  {
-    double pv[RG][U], bv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      const int j = j0 + u * SOLVE_THREADS + tid;
-      bv[u]       = j < jend ? bT[j] : 0.0;
-#pragma unroll
-      for (int a = 0; a < RG; ++a)
-      {
-        pv[a][u] = (a < nvalid && j < jend) ? P[(long long)(r0 + a) * k + j] : 0.0;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int a = 0; a < RG; ++a)
-      {
-        acc[a] += pv[a][u] * bv[u];
-      }
-  }
-#pragma unroll
-  for (int a = 0; a < RG; ++a)
-  {
-    double v = acc[a];
-    for (int o = 16; o > 0; o >>= 1)
-    {
-      v += __shfl_xor_sync(0xffffffffu, v, o);
-    }
-    if (lane == 0)
-    {
-      red[a * NW + warp] = v;
-    }
-  }
-  __syncthreads();
-  if (tid < nvalid)
-  {
-    double mine = 0.0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w)
-    {
-      mine += red[tid * NW + w];
-    }
-    const int r = r0 + tid;
-    if (r < k)
-    {
-      yf[t.first + r] = mine * Dinv[t.first + r];
-    }
-    else
-    {
-      atomicAdd(yacc + Ridx[t.Rptr + r - k], mine);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(SOLVE_THREADS)
-k_fwd_chunk(const FwdTask* __restrict__ tasks, const int* __restrict__ Ridx, const double* __restrict__ Mr, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf)
-{
-  extern __shared__ double bT[];
-  const FwdTask t  = tasks[blockIdx.x];
-  constexpr int NW = SOLVE_THREADS / 32;
-  if (t.wide)
-  {
-    if (t.nrows == 1)
-    {
-      fwd_wide<1>(t, Ridx, Mr, Dinv, yacc, yf, bT);
-    }
-    else
-    {
-      fwd_wide<2>(t, Ridx, Mr, Dinv, yacc, yf, bT);
-    }
-    return;
-  }
-  const int rg     = (t.nrows + NW - 1) / NW; // rows per warp: 1..4
-  if (rg == 1)
-  {
-    fwd_body<1, 8>(t, Ridx, Mr, Dinv, yacc, yf, bT);
-  }
-  else if (rg == 2)
-  {
-    fwd_body<2, 4>(t, Ridx, Mr, Dinv, yacc, yf, bT);
-  }
-  else if (rg <= 4)
-  {
-    fwd_body<4, 2>(t, Ridx, Mr, Dinv, yacc, yf, bT);
-  }
-  else
-  {
-    fwd_body<8, 2>(t, Ridx, Mr, Dinv, yacc, yf, bT); // narrow supernodes: 8 rows per warp
-  }
-}
-
-// ---- diagonal + backward sweep -----------------------------------------------------------------------
-// One CTA per (supernode, column chunk):  x_T = Minv^T [D^-1 y_T; x_rows].  A warp owns CG columns at a
-// time (rows are contiguous in the column-major panel), lanes stride the rows with 8 independent loads
-// in flight (first round issued before the vector is gathered), shuffle reduction. Dynamic shared memory: v[h].
-template <int CG, int U>
-__device__ __forceinline__ void
-bwd_body(const BwdTask& t,
-         const int* __restrict__ Ridx,
-         const double* __restrict__ Mt,
-         const double* __restrict__ D,
-         const double* __restrict__ y,
-         double* __restrict__ x,
-         double* v)
-{
-  const int k = t.k, h = t.h;
-  const double* P = Mt + t.Lptr;
-  const int* rows = Ridx + t.Rptr;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g0     = warp * CG;
-  const int nvalid = min(CG, t.ncols - g0);
-  const int j0     = t.col0 + g0;
-  // column j needs rows >= j; the columns of a group start at the first one's diagonal (the entries above a
-  // diagonal are zeros)
-  double pre[CG][U];
-#pragma unroll
-  for (int c = 0; c < CG; ++c)
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      const int i = j0 + lane + 32 * u;
-      pre[c][u]   = (c < nvalid && i < h) ? P[(long long)(j0 + c) * h + i] : 0.0;
-    }
-  // v = [D^-1 y_T; x_rows], staged in batches of 4 independent (two-hop) loads per thread
-  for (int i = t.col0 + tid; i < h; i += 4 * SOLVE_THREADS)
-  {
-    int src[4];
-    double tmp[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-    {
-      const int ii = i + u * SOLVE_THREADS;
-      src[u]       = ii < k ? t.first + ii : (ii < h ? rows[ii - k] : 0);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-    {
-      const int ii = i + u * SOLVE_THREADS;
-      tmp[u]       = ii < k ? y[src[u]] : (ii < h ? x[src[u]] : 0.0);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-    {
-      const int ii = i + u * SOLVE_THREADS;
-      if (ii < h)
-      {
-        v[ii] = tmp[u];
-      }
-    }
-  }
-  __syncthreads();
-  if (nvalid <= 0)
-  {
-    return;
-  }
-  double acc[CG][U];
-#pragma unroll
-  for (int c = 0; c < CG; ++c)
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      const int i = j0 + lane + 32 * u;
-      acc[c][u]   = i < h ? pre[c][u] * v[i] : 0.0;
-    }
-  int i = j0 + lane + 32 * U;
-  for (; i + 32 * (U - 1) < h; i += 32 * U)
-  {
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      const double vi = v[i + 32 * u];
-#pragma unroll
-      for (int c = 0; c < CG; ++c)
-      {
-        if (c < nvalid)
-        {
-          acc[c][u] += P[(long long)(j0 + c) * h + i + 32 * u] * vi;
-        }
-      }
-    }
-  }
-  for (; i < h; i += 32)
-  {
-    const double vi = v[i];
-#pragma unroll
-    for (int c = 0; c < CG; ++c)
-    {
-      if (c < nvalid)
-      {
-        acc[c][0] += P[(long long)(j0 + c) * h + i] * vi;
-      }
-    }
-  }
-  double mine = 0.0;
-#pragma unroll
-  for (int c = 0; c < CG; ++c)
-  {
-    double a = 0.0;
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      a += acc[c][u];
-    }
-    for (int o = 16; o > 0; o >>= 1)
-    {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-    }
-    if (lane == c)
-    {
-      mine = a;
-    }
-  }
-  if (lane < nvalid)
-  {
-    x[t.first + j0 + lane] = mine;
-  }
-}
-
-// Tall fronts (h >= 512): the CTA owns CG columns and its four warps split the rows of each of them; the input
-// vector is not staged: v_i = y_i (top block, already D^-1 y) or x[rows_i] is gathered alongside the panel loads.
-template <int CG>
-__device__ __forceinline__ void
-bwd_tall(const BwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ y, double* __restrict__ x, double* red)
-{
-  constexpr int U  = 8 / CG;
-  constexpr int NW = SOLVE_THREADS / 32;
-  const int k = t.k, h = t.h;
-  const double* P = Mt + t.Lptr;
-  const int* rows = Ridx + t.Rptr;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nvalid = min(CG, -t.ncols);
-  const int j0     = t.col0;
-  double acc[CG];
-#pragma unroll
-  for (int c = 0; c < CG; ++c)
-  {
-    acc[c] = 0.0;
-  }
-  for (int i0 = j0; i0 < h; i0 += SOLVE_THREADS * U)
-  {
-    int src[U];
-    double pv[CG][U], vv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      const int i = i0 + u * SOLVE_THREADS + tid;
-      src[u]      = i < k ? t.first + i : (i < h ? rows[i - k] : 0);
-#pragma unroll
-      for (int c = 0; c < CG; ++c)
-      {
-        pv[c][u] = (c < nvalid && i < h) ? P[(long long)(j0 + c) * h + i] : 0.0;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-    {
-      const int i = i0 + u * SOLVE_THREADS + tid;
-      vv[u]       = i < k ? y[src[u]] : (i < h ? x[src[u]] : 0.0);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int c = 0; c < CG; ++c)
-      {
-        acc[c] += pv[c][u] * vv[u];
-      }
-  }
-#pragma unroll
-  for (int c = 0; c < CG; ++c)
-  {
-    double v = acc[c];
-    for (int o = 16; o > 0; o >>= 1)
-    {
-      v += __shfl_xor_sync(0xffffffffu, v, o);
-    }
-    if (lane == 0)
-    {
-      red[c * NW + warp] = v;
-    }
-  }
-  __syncthreads();
-  if (tid < nvalid)
-  {
-    double mine = 0.0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w)
-    {
-      mine += red[tid * NW + w];
-    }
-    x[t.first + j0 + tid] = mine;
-  }
-}
-
-__global__ void __launch_bounds__(SOLVE_THREADS)
-k_bwd_chunk(const BwdTask* __restrict__ tasks,
-            const int* __restrict__ Ridx,
-            const double* __restrict__ Mt,
-            const double* __restrict__ D,
-            const double* __restrict__ y,
-            double* __restrict__ x)
-{
-  extern __shared__ double v[];
-  const BwdTask t  = tasks[blockIdx.x];
-  constexpr int NW = SOLVE_THREADS / 32;
-  if (t.ncols < 0)
-  {
-    if (t.ncols == -1)
-    {
-      bwd_tall<1>(t, Ridx, Mt, y, x, v);
-    }
-    else
-    {
-      bwd_tall<2>(t, Ridx, Mt, y, x, v);
-    }
-    return;
-  }
-  const int cg     = (t.ncols + NW - 1) / NW; // columns per warp: 1..4
-  if (cg == 1)
-  {
-    bwd_body<1, 8>(t, Ridx, Mt, D, y, x, v);
-  }
-  else if (cg == 2)
-  {
-    bwd_body<2, 4>(t, Ridx, Mt, D, y, x, v);
-  }
-  else
-  {
-    bwd_body<4, 2>(t, Ridx, Mt, D, y, x, v);
   }
 }
 
@@ -1027,120 +536,6 @@ k_flow_reset(int m, int nflow, double* __restrict__ yf, double* __restrict__ x, 
   }
 }
 
-// ---- fused top of the tree ---------------------------------------------------------------------------
-// The upper levels of the supernodal tree have few chunks each (tens to a few hundred CTAs) and cost a full
-// kernel launch + drain (~13 us) per level. These cooperative kernels walk all of them in one launch with a
-// grid barrier between levels; every CTA strides over the level's tasks.
-__device__ __forceinline__ void
-fwd_dispatch(const FwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mr, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf, double* bT)
-{
-  constexpr int NW = SOLVE_THREADS / 32;
-  if (t.wide)
-  {
-    if (t.nrows == 1)
-    {
-      fwd_wide<1>(t, Ridx, Mr, Dinv, yacc, yf, bT);
-    }
-    else
-    {
-      fwd_wide<2>(t, Ridx, Mr, Dinv, yacc, yf, bT);
-    }
-    return;
-  }
-  const int rg     = (t.nrows + NW - 1) / NW;
-  if (rg == 1)
-  {
-    fwd_body<1, 8>(t, Ridx, Mr, Dinv, yacc, yf, bT);
-  }
-  else if (rg == 2)
-  {
-    fwd_body<2, 4>(t, Ridx, Mr, Dinv, yacc, yf, bT);
-  }
-  else if (rg <= 4)
-  {
-    fwd_body<4, 2>(t, Ridx, Mr, Dinv, yacc, yf, bT);
-  }
-  else
-  {
-    fwd_body<8, 2>(t, Ridx, Mr, Dinv, yacc, yf, bT); // narrow supernodes: 8 rows per warp
-  }
-}
-
-__device__ __forceinline__ void
-bwd_dispatch(const BwdTask& t, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ D, const double* __restrict__ y, double* __restrict__ x, double* v)
-{
-  constexpr int NW = SOLVE_THREADS / 32;
-  if (t.ncols < 0)
-  {
-    if (t.ncols == -1)
-    {
-      bwd_tall<1>(t, Ridx, Mt, y, x, v);
-    }
-    else
-    {
-      bwd_tall<2>(t, Ridx, Mt, y, x, v);
-    }
-    return;
-  }
-  const int cg_    = (t.ncols + NW - 1) / NW;
-  if (cg_ == 1)
-  {
-    bwd_body<1, 8>(t, Ridx, Mt, D, y, x, v);
-  }
-  else if (cg_ == 2)
-  {
-    bwd_body<2, 4>(t, Ridx, Mt, D, y, x, v);
-  }
-  else
-  {
-    bwd_body<4, 2>(t, Ridx, Mt, D, y, x, v);
-  }
-}
-
-__global__ void __launch_bounds__(SOLVE_THREADS)
-k_fwd_top(const FwdTask* __restrict__ tasks, const int* __restrict__ lvl_ptr, int l0, int l1, const int* __restrict__ Ridx, const double* __restrict__ Mr, const double* __restrict__ Dinv, double* __restrict__ yacc, double* __restrict__ yf)
-{
-  extern __shared__ double smem_top[];
-  cg::grid_group grid = cg::this_grid();
-  for (int l = l0; l < l1; ++l)
-  {
-    for (int q = lvl_ptr[l] + blockIdx.x; q < lvl_ptr[l + 1]; q += gridDim.x)
-    {
-      const FwdTask t = tasks[q];
-      fwd_dispatch(t, Ridx, Mr, Dinv, yacc, yf, smem_top);
-      __syncthreads(); // the staging buffer is reused by the next task
-    }
-    grid.sync();
-  }
-}
-
-__global__ void __launch_bounds__(SOLVE_THREADS)
-k_bwd_top(const BwdTask* __restrict__ tasks, const int* __restrict__ lvl_ptr, int l0, int l1, const int* __restrict__ Ridx, const double* __restrict__ Mt, const double* __restrict__ D, const double* __restrict__ y, double* __restrict__ x)
-{
-  extern __shared__ double smem_top[];
-  cg::grid_group grid = cg::this_grid();
-  for (int l = l1 - 1; l >= l0; --l)
-  {
-    for (int q = lvl_ptr[l] + blockIdx.x; q < lvl_ptr[l + 1]; q += gridDim.x)
-    {
-      const BwdTask t = tasks[q];
-      bwd_dispatch(t, Ridx, Mt, D, y, x, smem_top);
-      __syncthreads();
-    }
-    grid.sync();
-  }
-}
-
-__global__ void
-k_coop_probe(int* out)
-{
-  cg::this_grid().sync();
-  if (out && blockIdx.x == 0 && threadIdx.x == 0)
-  {
-    *out = 1;
-  }
-}
-
 // ---- small utilities -----------------------------------------------------------------------------------
 __global__ void
 k_scatter(int nnz, const int* __restrict__ idx, int first, const double* __restrict__ val, double* __restrict__ out)
@@ -1206,6 +601,143 @@ k_absrange(int n, const double* __restrict__ x, unsigned long long* __restrict__
   }
 }
 
+// ---- sparsification of a solution slice on the device (what sleqp_vec_set_from_raw does on the host, vec.c:72-104):
+// keeps the entries with |v| > eps in ascending order. Three small kernels: per-chunk counts, scan of the counts,
+// ordered write (ballot ranks inside a warp, shared-memory scan over the warps).
+constexpr int CP_THREADS = 256, CP_PER = 4, CP_CHUNK = CP_THREADS * CP_PER;
+
+__global__ void __launch_bounds__(CP_THREADS)
+k_compact_count(int n, const double* __restrict__ x, double eps, int* __restrict__ chunk_cnt)
+{
+  __shared__ int wsum[CP_THREADS / 32];
+  const int base = blockIdx.x * CP_CHUNK;
+  int c          = 0;
+#pragma unroll
+  for (int r = 0; r < CP_PER; ++r)
+  {
+    const int i = base + r * CP_THREADS + threadIdx.x;
+    c += i < n && fabs(x[i]) > eps;
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0)
+  {
+    wsum[threadIdx.x >> 5] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    int t = 0;
+    for (int w = 0; w < CP_THREADS / 32; ++w)
+    {
+      t += wsum[w];
+    }
+    chunk_cnt[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of the chunk counts in place (one CTA); chunk_cnt[nchunks] = total
+__global__ void __launch_bounds__(1024)
+k_compact_scan(int nchunks, int* __restrict__ chunk_cnt)
+{
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0)
+  {
+    carry = 0;
+  }
+  __syncthreads();
+  for (int b0 = 0; b0 < nchunks; b0 += 1024)
+  {
+    const int i = b0 + threadIdx.x;
+    const int v = i < nchunks ? chunk_cnt[i] : 0;
+    int incl    = v;
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o)
+      {
+        incl += t;
+      }
+    }
+    if ((threadIdx.x & 31) == 31)
+    {
+      wsum[threadIdx.x >> 5] = incl;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+      int w = wsum[threadIdx.x];
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o)
+        {
+          w += t;
+        }
+      }
+      wsum[threadIdx.x] = w; // inclusive over the warps
+    }
+    __syncthreads();
+    const int before = carry + (threadIdx.x >= 32 ? wsum[(threadIdx.x >> 5) - 1] : 0);
+    if (i < nchunks)
+    {
+      chunk_cnt[i] = before + incl - v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      carry += wsum[31];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+  {
+    chunk_cnt[nchunks] = carry;
+  }
+}
+
+__global__ void __launch_bounds__(CP_THREADS)
+k_compact_write(int n, const double* __restrict__ x, double eps, const int* __restrict__ chunk_off, int* __restrict__ idx_out, double* __restrict__ val_out)
+{
+  __shared__ int wcnt[CP_PER][CP_THREADS / 32];
+  const int base = blockIdx.x * CP_CHUNK;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double v[CP_PER];
+  unsigned bal[CP_PER];
+#pragma unroll
+  for (int r = 0; r < CP_PER; ++r)
+  {
+    const int i = base + r * CP_THREADS + threadIdx.x;
+    v[r]        = i < n ? x[i] : 0.0;
+    bal[r]      = __ballot_sync(0xffffffffu, i < n && fabs(v[r]) > eps);
+    if (lane == 0)
+    {
+      wcnt[r][warp] = __popc(bal[r]);
+    }
+  }
+  __syncthreads();
+  int off = chunk_off[blockIdx.x];
+#pragma unroll
+  for (int r = 0; r < CP_PER; ++r)
+  {
+    int before = 0;
+    for (int w = 0; w < CP_THREADS / 32; ++w)
+    {
+      before += w < warp ? wcnt[r][w] : 0;
+    }
+    if (bal[r] >> lane & 1u)
+    {
+      const int pos = off + before + __popc(bal[r] & ((1u << lane) - 1u));
+      idx_out[pos]  = r * CP_THREADS + threadIdx.x + base;
+      val_out[pos]  = v[r];
+    }
+    for (int w = 0; w < CP_THREADS / 32; ++w)
+    {
+      off += wcnt[r][w];
+    }
+  }
+}
+
 __global__ void
 k_init_range(double* scal)
 {
@@ -1220,187 +752,12 @@ nblocks(long long n, int threads)
   return (unsigned)((n + threads - 1) / threads);
 }
 
-constexpr size_t SOLVE_SMEM_LIMIT = 160 * 1024;
-
-// ---- which levels go into the fused cooperative kernels ----------------------------------------------------
 namespace
 {
-struct TopFusion
-{
-  int split;    // levels [split, nlevels) are fused; split == nlevels disables the fusion
-  int grid_fwd; // cooperative grid sizes
-  int grid_bwd;
-  size_t smem;
-};
-
-int g_flow      = 1;  // dataflow sweeps (default) or one launch per level (B200_SWEEP=level)
-int g_sms       = 148;
-int g_flow_sleep = 512;
+int g_sms        = 148;
+int g_flow_sleep = 512;              // B200_FLOW_SLEEP: poll interval of far-away consumers (ns)
 int g_flow_ctas  = FLOW_CTAS_PER_SM; // B200_FLOW_CTAS: fewer resident CTAs per SM (experiments)
-int g_coop_ok   = -1; // -1 unknown, 0 unusable, 1 usable (process-wide)
-int g_coop_ctas = 0;  // co-resident CTAs of the fused kernels with the worst-case shared memory
-
-// Cooperative launches must be capturable into a CUDA graph and the device must support them; probed once,
-// outside of any capture (configure_solve_kernels).
-void
-probe_cooperative()
-{
-  if (g_coop_ok >= 0)
-  {
-    return;
-  }
-  g_coop_ok = 0;
-  // Measured on B200 (profiles/README.md): the fused kernels are slower than one launch per level (a graph
-  // node costs only ~0.6 us), so they are opt-in.
-  const char* e = std::getenv("B200_TOP_FUSION");
-  if (!e || !*e || *e == '0')
-  {
-    return;
-  }
-  int dev = 0, coop = 0, sms = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop)
-  {
-    cudaGetLastError();
-    return;
-  }
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaStream_t s = nullptr;
-  cudaGraph_t g  = nullptr;
-  cudaGraphExec_t ge = nullptr;
-  bool ok = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
-  if (ok)
-  {
-    int* out     = nullptr;
-    void* args[] = {&out};
-    ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-    if (ok)
-    {
-      const bool launched = cudaLaunchCooperativeKernel((void*)k_coop_probe, dim3(2), dim3(32), args, 0, s) == cudaSuccess;
-      const bool ended    = cudaStreamEndCapture(s, &g) == cudaSuccess;
-      ok                  = launched && ended && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess;
-      if (ok)
-      {
-        ok = cudaGraphLaunch(ge, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess;
-      }
-    }
-  }
-  if (ge)
-  {
-    cudaGraphExecDestroy(ge);
-  }
-  if (g)
-  {
-    cudaGraphDestroy(g);
-  }
-  if (s)
-  {
-    cudaStreamDestroy(s);
-  }
-  cudaGetLastError();
-  if (!ok)
-  {
-    return;
-  }
-  // worst-case shared memory of the fused kernels: 32 KB (fronts up to 4096 rows); larger levels stay unfused
-  int per_sm_f = 0, per_sm_b = 0;
-  const size_t smem = 32 * 1024;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, k_fwd_top, SOLVE_THREADS, smem) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_bwd_top, SOLVE_THREADS, smem) != cudaSuccess)
-  {
-    cudaGetLastError();
-    return;
-  }
-  g_coop_ctas = sms * std::max(1, std::min(std::min(per_sm_f, per_sm_b), 4));
-  g_coop_ok   = g_coop_ctas > 0;
-}
-
-TopFusion
-plan_top_fusion(const Plan& P)
-{
-  TopFusion tf{P.nlevels, 0, 0, 0};
-  if (g_coop_ok != 1 || P.nlevels < 3)
-  {
-    return tf;
-  }
-  // fuse the maximal run of top levels whose task counts fit the co-resident grid and whose fronts fit 32 KB
-  int split = P.nlevels;
-  int maxf = 0, maxb = 0, maxh = 0;
-  for (int l = P.nlevels - 1; l >= 1; --l)
-  {
-    const int nf = P.fwd_ptr[l + 1] - P.fwd_ptr[l], nb = P.bwd_ptr[l + 1] - P.bwd_ptr[l];
-    if (nf > 2 * g_coop_ctas || nb > 2 * g_coop_ctas || P.lvl_maxh[l] > 4096)
-    {
-      break;
-    }
-    split = l;
-    maxf  = std::max(maxf, nf);
-    maxb  = std::max(maxb, nb);
-    maxh  = std::max(maxh, P.lvl_maxh[l]);
-  }
-  if (P.nlevels - split < 2)
-  {
-    return tf;
-  }
-  tf.split    = split;
-  tf.grid_fwd = std::max(1, std::min(g_coop_ctas, maxf));
-  tf.grid_bwd = std::max(1, std::min(g_coop_ctas, maxb));
-  tf.smem     = sizeof(double) * (size_t)maxh;
-  return tf;
-}
 } // namespace
-
-static void
-solve_levels(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc, cudaEvent_t* ev)
-{
-  // one launch per level of the supernodal tree (B200_SWEEP=level; kept for A/B measurements)
-  auto mark = [&](int i) {
-    if (ev)
-    {
-      B200_CUDA(cudaEventRecord(ev[i], stream));
-    }
-  };
-  const Plan& P = *dp.plan;
-  const TopFusion tf = plan_top_fusion(P);
-  for (int l = 0; l < tf.split; ++l)
-  {
-    const int cnt     = P.fwd_ptr[l + 1] - P.fwd_ptr[l];
-    const size_t smem = sizeof(double) * (size_t)P.lvl_maxh[l];
-    k_fwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.fwd_tasks.p + P.fwd_ptr[l], dp.Ridx.p, nb.Mr, nb.Dinv, sb.y, sb.yf);
-    lc.tick();
-  }
-  if (tf.split < P.nlevels)
-  {
-    const FwdTask* tasks = dp.fwd_tasks.p;
-    const int* lp        = dp.fwd_ptr.p;
-    int l0 = tf.split, l1 = P.nlevels;
-    const int* ridx  = dp.Ridx.p;
-    const double *mr = nb.Mr, *di = nb.Dinv;
-    double *ya = sb.y, *yf = sb.yf;
-    void* args[] = {&tasks, &lp, &l0, &l1, &ridx, &mr, &di, &ya, &yf};
-    B200_CUDA(cudaLaunchCooperativeKernel((void*)k_fwd_top, dim3(tf.grid_fwd), dim3(SOLVE_THREADS), args, tf.smem, stream));
-    lc.tick();
-  }
-  mark(2);
-  if (tf.split < P.nlevels)
-  {
-    const BwdTask* tasks = dp.bwd_tasks.p;
-    const int* lp        = dp.bwd_ptr.p;
-    int l0 = tf.split, l1 = P.nlevels;
-    const int* ridx  = dp.Ridx.p;
-    const double *mt = nb.Mt, *dd = nb.D, *yf = sb.yf;
-    double* xx       = sb.x;
-    void* args[] = {&tasks, &lp, &l0, &l1, &ridx, &mt, &dd, &yf, &xx};
-    B200_CUDA(cudaLaunchCooperativeKernel((void*)k_bwd_top, dim3(tf.grid_bwd), dim3(SOLVE_THREADS), args, tf.smem, stream));
-    lc.tick();
-  }
-  for (int l = tf.split - 1; l >= 0; --l)
-  {
-    const int cnt     = P.bwd_ptr[l + 1] - P.bwd_ptr[l];
-    const size_t smem = sizeof(double) * (size_t)P.lvl_maxh[l];
-    k_bwd_chunk<<<cnt, SOLVE_THREADS, smem, stream>>>(dp.bwd_tasks.p + P.bwd_ptr[l], dp.Ridx.p, nb.Mt, nb.D, sb.yf, sb.x);
-    lc.tick();
-  }
-}
 
 static void
 solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, const double* in, double* out, cudaStream_t stream, LaunchCounter& lc, cudaEvent_t* ev = nullptr)
@@ -1418,37 +775,29 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
   {
     k_pre<<<nblocks(P.m, T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.k_of_e.p, dp.pinv.p, dp.Acsr_ptr.p, dp.Acsr_col.p, nb.Acsr_val, nb.dE, in, sb.y);
     lc.tick();
+    const int ns    = P.nsuper;
+    const int nflow = 2 * ns + 2 * FLOW_SHARDS * FLOW_TICKET_PITCH;
+    k_flow_reset<<<nblocks(std::max(P.m, nflow), T), T, 0, stream>>>(P.m, nflow, sb.yf, sb.x, sb.flow);
+    lc.tick();
     mark(1);
-    if (g_flow)
-    {
-      const int ns    = P.nsuper;
-      const int nflow = 2 * ns + 2 * FLOW_SHARDS * FLOW_TICKET_PITCH;
-      k_flow_reset<<<nblocks(std::max(P.m, nflow), T), T, 0, stream>>>(P.m, nflow, sb.yf, sb.x, sb.flow);
-      lc.tick();
-      const int warps_per_cta = FLOW_THREADS / 32;
-      const int max_ctas      = g_sms * g_flow_ctas;
-      auto grid = [&](size_t ntasks) {
-        const long long ctas = ((long long)ntasks + FLOW_SHARDS - 1) / FLOW_SHARDS;
-        return (unsigned)std::max<long long>(1, std::min<long long>(max_ctas, ctas));
-      };
-      const FlowSched fs{(int)P.ffl_tasks.size(), g_flow_sleep};
-      const FlowSched bs{(int)P.bfl_tasks.size(), g_flow_sleep};
-      int* const tickets_f = sb.flow + 2 * ns;
-      int* const tickets_b = tickets_f + FLOW_SHARDS * FLOW_TICKET_PITCH;
-      auto kf = sb.trace_fwd ? k_flow<true, true> : k_flow<true, false>;
-      auto kb = sb.trace_bwd ? k_flow<false, true> : k_flow<false, false>;
-      kf<<<sb.trace_fwd ? max_ctas : grid(P.ffl_tasks.size()), FLOW_THREADS, 0, stream>>>(dp.ffl_tasks.p, fs, dp.Ridx.p, nb.Mt, nb.Dinv, sb.y, sb.yf, sb.x, sb.flow, tickets_f,
-                                                                  (const FlowTrace*)sb.trace_fwd);
-      lc.tick();
-      mark(2);
-      kb<<<sb.trace_bwd ? max_ctas : grid(P.bfl_tasks.size()), FLOW_THREADS, 0, stream>>>(dp.bfl_tasks.p, bs, dp.Ridx.p, nb.Mr, nb.Dinv, sb.y, sb.yf, sb.x, sb.flow + ns, tickets_b,
-                                                                   (const FlowTrace*)sb.trace_bwd);
-      lc.tick();
-    }
-    else
-    {
-      solve_levels(dp, nb, sb, stream, lc, ev);
-    }
+    const int max_ctas      = g_sms * g_flow_ctas;
+    auto grid = [&](size_t ntasks) {
+      const long long ctas = ((long long)ntasks + FLOW_SHARDS - 1) / FLOW_SHARDS;
+      return (unsigned)std::max<long long>(1, std::min<long long>(max_ctas, ctas));
+    };
+    const FlowSched fs{(int)P.ffl_tasks.size(), g_flow_sleep};
+    const FlowSched bs{(int)P.bfl_tasks.size(), g_flow_sleep};
+    int* const tickets_f = sb.flow + 2 * ns;
+    int* const tickets_b = tickets_f + FLOW_SHARDS * FLOW_TICKET_PITCH;
+    auto kf = sb.trace_fwd ? k_flow<true, true> : k_flow<true, false>;
+    auto kb = sb.trace_bwd ? k_flow<false, true> : k_flow<false, false>;
+    kf<<<sb.trace_fwd ? max_ctas : grid(P.ffl_tasks.size()), FLOW_THREADS, 0, stream>>>(dp.ffl_tasks.p, fs, dp.Ridx.p, nb.Mt, nb.Dinv, sb.y, sb.yf, sb.x, sb.flow, tickets_f,
+                                                                (const FlowTrace*)sb.trace_fwd);
+    lc.tick();
+    mark(2);
+    kb<<<sb.trace_bwd ? max_ctas : grid(P.bfl_tasks.size()), FLOW_THREADS, 0, stream>>>(dp.bfl_tasks.p, bs, dp.Ridx.p, nb.Mr, nb.Dinv, sb.y, sb.yf, sb.x, sb.flow + ns, tickets_b,
+                                                                 (const FlowTrace*)sb.trace_bwd);
+    lc.tick();
     mark(3);
     k_post_r<<<nblocks(P.m, T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.pinv.p, sb.x, out);
     lc.tick();
@@ -1487,11 +836,6 @@ configure_solve_kernels()
   std::call_once(once, [] {
     try
     {
-      B200_CUDA(cudaFuncSetAttribute(k_fwd_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
-      B200_CUDA(cudaFuncSetAttribute(k_bwd_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM_LIMIT));
-      probe_cooperative();
-      const char* sw = std::getenv("B200_SWEEP");
-      g_flow         = !(sw && std::string(sw) == "level");
       if (const char* fc = std::getenv("B200_FLOW_CTAS"))
       {
         g_flow_ctas = std::min(FLOW_CTAS_PER_SM, std::max(1, std::atoi(fc)));
@@ -1592,6 +936,31 @@ enqueue_pivot_range(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t st
     lc.tick();
   }
   B200_CUDA(cudaGetLastError());
+}
+
+void
+enqueue_compact(const double* x, int n, double eps, int* chunk_cnt, int* idx_out, double* val_out, cudaStream_t stream, LaunchCounter& lc)
+{
+  const int nchunks = (n + CP_CHUNK - 1) / CP_CHUNK;
+  if (nchunks > 0)
+  {
+    k_compact_count<<<nchunks, CP_THREADS, 0, stream>>>(n, x, eps, chunk_cnt);
+    lc.tick();
+  }
+  k_compact_scan<<<1, 1024, 0, stream>>>(nchunks, chunk_cnt);
+  lc.tick();
+  if (nchunks > 0)
+  {
+    k_compact_write<<<nchunks, CP_THREADS, 0, stream>>>(n, x, eps, chunk_cnt, idx_out, val_out);
+    lc.tick();
+  }
+  B200_CUDA(cudaGetLastError());
+}
+
+int
+compact_chunks(int n)
+{
+  return (n + CP_CHUNK - 1) / CP_CHUNK;
 }
 
 void

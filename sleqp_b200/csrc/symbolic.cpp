@@ -1432,7 +1432,6 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       }
       st.zero_end  = (int)P.zero_sn.size();
       st.ea_end    = (int)P.ea_tasks.size();
-      st.diag_begin = (int)P.diag_tasks.size();
       st.pan_begin  = (int)P.pan_tasks.size();
       st.upd_begin  = (int)P.upd_tasks.size();
       for (int T : active[s])
@@ -1444,7 +1443,6 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         const int c0 = t * NB;
         const int w  = std::min(NB, k - c0);
         const int below = h - c0 - w;
-        P.diag_tasks.push_back({T, t});
         for (int rb = 0; rb == 0 || rb * RB < below; ++rb)
         {
           P.pan_tasks.push_back({T, t, rb, 0});
@@ -1483,7 +1481,6 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
           }
         }
       }
-      st.diag_end       = (int)P.diag_tasks.size();
       st.pan_end        = (int)P.pan_tasks.size();
       st.upd_end        = (int)P.upd_tasks.size();
     }
@@ -1599,113 +1596,6 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   }
 
   tick("inversion + transpose tasks");
-  // ---- solve tasks: row chunks (forward) / column chunks (backward) of every supernode, per level ---------------
-  {
-    P.sn_ncol.assign(ns, 0);
-    for (int T = 0; T < ns; ++T)
-    {
-      const int p = P.sn_parent[T];
-      if (p < 0)
-      {
-        continue;
-      }
-      const int kp = P.sn_first[p + 1] - P.sn_first[p];
-      int cnt      = 0;
-      for (i64 q = P.Rptr[T]; q < P.Rptr[T + 1] && P.rel[q] < kp; ++q)
-      {
-        ++cnt;
-      }
-      P.sn_ncol[T] = cnt;
-    }
-    {
-      const i64 totalh = P.Wptr[ns];
-      if (totalh > 0x7ffffff0 || (i64)P.Ridx.size() > 0x7ffffff0)
-      {
-        return fail(err, B200_ERR_UNSUPPORTED, "front-vector workspace exceeds 2^31 entries");
-      }
-      P.cptr.assign((size_t)totalh + 1, 0);
-      for (int c = 0; c < ns; ++c)
-      {
-        const int p = P.sn_parent[c];
-        if (p < 0)
-        {
-          continue;
-        }
-        for (i64 q = P.Rptr[c]; q < P.Rptr[c + 1]; ++q)
-        {
-          ++P.cptr[(size_t)(P.Wptr[p] + P.rel[q]) + 1];
-        }
-      }
-      for (i64 i = 0; i < totalh; ++i)
-      {
-        P.cptr[i + 1] += P.cptr[i];
-      }
-      P.cidx.resize((size_t)P.cptr[totalh]);
-      std::vector<int> fill(P.cptr.begin(), P.cptr.end() - 1);
-      for (int c = 0; c < ns; ++c) // ascending child index => deterministic summation order
-      {
-        const int p = P.sn_parent[c];
-        if (p < 0)
-        {
-          continue;
-        }
-        const int kc = P.sn_first[c + 1] - P.sn_first[c];
-        for (i64 q = P.Rptr[c]; q < P.Rptr[c + 1]; ++q)
-        {
-          P.cidx[fill[(size_t)(P.Wptr[p] + P.rel[q])]++] = (int)(P.Wptr[c] + kc + (q - P.Rptr[c]));
-        }
-      }
-    }
-    P.fwd_ptr.assign(P.nlevels + 1, 0);
-    P.bwd_ptr.assign(P.nlevels + 1, 0);
-    P.lvl_maxh.assign(P.nlevels, 0);
-    for (int l = 0; l < P.nlevels; ++l)
-    {
-      // big supernodes first: their CTAs are the long ones
-      std::vector<int> order(P.lvl_sn.begin() + P.lvl_ptr[l], P.lvl_sn.begin() + P.lvl_ptr[l + 1]);
-      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return (P.Wptr[x + 1] - P.Wptr[x]) > (P.Wptr[y + 1] - P.Wptr[y]); });
-      for (int T : order)
-      {
-        const int k = P.sn_first[T + 1] - P.sn_first[T];
-        const int h = (int)(P.Wptr[T + 1] - P.Wptr[T]);
-        P.lvl_maxh[l] = std::max(P.lvl_maxh[l], h);
-        // a warp works on up to 4 rows at once (8 for narrow supernodes: few columns, so more rows keep the
-        // loads in flight and the leaf levels need half the CTAs)
-        int nrows = k <= 64 ? 32 : std::min(16, std::max(4, (4096 + k - 1) / k));
-        nrows     = (nrows + 3) & ~3;
-        // wide fronts: one or two rows per CTA, the four warps split the columns (<= 2 rounds of loads per CTA
-        // instead of k / 256), the right-hand side is read straight from the accumulator
-        const int wide = k >= 512 ? 1 : 0;
-        if (wide)
-        {
-          nrows = k >= 1024 ? 1 : 2;
-        }
-        for (int row0 = 0; row0 < h; row0 += nrows)
-        {
-          P.fwd_tasks.push_back({T, row0, std::min(nrows, h - row0), P.sn_first[T], k, wide, P.Lptr[T], P.Rptr[T]});
-        }
-        // a warp works on up to 4 columns at once (8 per warp was measured slower for the short fronts)
-        int ncols = std::min(16, std::max(4, (4096 + h - 1) / h));
-        ncols     = (ncols + 3) & ~3;
-        // tall fronts: one or two columns per CTA, the four warps split the rows (<= 2 rounds of loads per CTA)
-        // (measured on B200: no gain at config 2, 20 % slower at 3D g=48 -- the input vector is then gathered once per
-        // column instead of once per 4 columns -- so the tall variant stays off)
-        const bool tall = false;
-        if (tall)
-        {
-          ncols = h >= 1024 ? 1 : 2;
-        }
-        for (int col0 = 0; col0 < k; col0 += ncols)
-        {
-          const int nc = std::min(ncols, k - col0);
-          P.bwd_tasks.push_back({T, col0, tall ? -nc : nc, P.sn_first[T], k, h, P.Lptr[T], P.Rptr[T]});
-        }
-      }
-      P.fwd_ptr[l + 1] = (int)P.fwd_tasks.size();
-      P.bwd_ptr[l + 1] = (int)P.bwd_tasks.size();
-    }
-  }
-
   // ---- dataflow sweeps: warp tasks in ticket order, dependency counters per supernode -------------------------
   {
     constexpr int LANES = 32, DEPTH = 16;
@@ -1781,7 +1671,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
 
-  tick("solve tasks + contributors");
+  tick("sweep tasks");
   // ---- hash of the full permutation -----------------------------------------------------------------------------
   {
     std::vector<int> fp(n);

@@ -48,11 +48,11 @@ PLAN_FIELDS = {
         "e_of_k r_of_k k_of_e k_of_r dE_src Acsc_ptr Acsc_row Acsc_src Acsr_ptr Acsr_col Acsr_src "
         "Gsym_ptr Gsym_col Gsym_src perm pinv parent colcount sn_first sn_of_col sn_parent sn_level "
         "Ridx rel child_ptr child_idx Sgsrc Sterm_a Sterm_b Sterm_d sn_base sn_nt zero_sn lvl_ptr lvl_sn "
-        "inv_phase_ptr sn_ncol fwd_ptr bwd_ptr lvl_maxh cptr cidx"
+        "inv_phase_ptr"
     ).split()},
     **{k: np.int64 for k in "Rptr Lptr Wptr Sdest Sterm_ptr Uoff Tptr".split()},
 }
-PLAN_STRUCTS = {"stages": 10, "ea_tasks": 2, "diag_tasks": 2, "pan_tasks": 4, "upd_tasks": 7, "inv_tasks": 6, "fwd_tasks": 10, "bwd_tasks": 10,
+PLAN_STRUCTS = {"stages": 8, "ea_tasks": 2, "pan_tasks": 4, "upd_tasks": 7, "inv_tasks": 6,
                 "ffl_tasks": 16, "bfl_tasks": 16, "tr_tasks": 3}  # int32 columns
 
 
@@ -141,13 +141,21 @@ class Fact:
         (sleqp_vec_set_from_raw, vec.c:72-104). Returns (indices, values)."""
         n = int(end - begin)
         if getattr(self, "_sol_cap", 0) < n:  # grown on demand and reused, like the caller-owned SleqpVec
+            self._unpin_solution_buffers()
             self._sol_cap = max(n, 1)
             self._sol_idx = np.empty(self._sol_cap, dtype=np.int32)
             self._sol_val = np.empty(self._sol_cap, dtype=np.float64)
+            # page-locked once: the sparsified slice is then DMA'd straight into them (b200_host_pin)
+            self._sol_pinned = [a for a in (self._sol_idx, self._sol_val) if lib().b200_host_pin(a.ctypes.data_as(C.c_void_p), a.nbytes) == 0]
         idx, val = self._sol_idx, self._sol_val
         nnz = C.c_int()
         check(lib().b200_fact_solution_sparse(self._h, int(begin), int(end), float(zero_eps), _pi(idx), _pd(val), C.byref(nnz)))
         return idx[: nnz.value], val[: nnz.value]
+
+    def _unpin_solution_buffers(self):
+        for a in getattr(self, "_sol_pinned", []):
+            lib().b200_host_unpin(a.ctypes.data_as(C.c_void_p))
+        self._sol_pinned = []
 
     def solve_device(self, d_rhs_ptr: int, d_sol_ptr: int):
         check(lib().b200_fact_solve_device(self._h, C.c_void_p(d_rhs_ptr), C.c_void_p(d_sol_ptr)))
@@ -199,6 +207,7 @@ class Fact:
     def release(self):
         """sleqp_fact_release (fact.c:143-161) -> callbacks.free."""
         if self._h:
+            self._unpin_solution_buffers()
             check(lib().b200_fact_free(C.byref(self._h)))
             self._h = C.c_void_p()
 

@@ -73,8 +73,8 @@ def test_analysis_and_plan_on_random_structures(seed):
         zr = spla.spsolve(K, b)
         assert np.linalg.norm(K @ z - b) <= 1e-9 * np.linalg.norm(b)
         assert np.linalg.norm(z - zr) <= 1e-7 * max(1.0, np.linalg.norm(zr))
-        zf = em.solve(b, refine=1, flow=True)  # dataflow sweep tasks in ticket order
-        assert np.linalg.norm(zf - z) <= 1e-9 * max(1.0, np.linalg.norm(z))
+        zs = em.solve(b, refine=1, flow=False)  # plain substitution with the factor as a cross-check of the task lists
+        assert np.linalg.norm(zs - z) <= 1e-9 * max(1.0, np.linalg.norm(z))
 
 
 @pytest.mark.gpu

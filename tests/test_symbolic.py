@@ -62,31 +62,14 @@ def test_plan_emulation_solves_kkt(name):
     for kind in ("project_nullspace", "solve_min_norm", "solve_lsq"):
         idx, val = p.rhs(kind, 3)
         b = orc.vec_to_raw(idx, val, p.N)
+        # the dataflow sweep tasks (what the device runs): list order respects every dependency counter
         z = em.solve(b, refine=0)
         assert np.linalg.norm(K @ z - b) <= 1e-12 * np.linalg.norm(b)
         zr = spla.spsolve(K.tocsc(), b)
         assert np.linalg.norm(z - zr) <= 1e-10 * np.linalg.norm(zr)
-        # the dataflow sweep tasks (what the device runs): ticket order respects every dependency counter
-        zf = em.solve(b, refine=0, flow=True)
-        assert np.linalg.norm(K @ zf - b) <= 1e-12 * np.linalg.norm(b)
-        assert np.linalg.norm(zf - z) <= 1e-12 * np.linalg.norm(z)
-
-
-def test_contributor_lists_invert_the_relative_indices():
-    p = problems.poisson_control(24, 2, seed=2)
-    pl = Symbolic(p.N, *p.kkt_lower()).plan()
-    ns = int(pl["n_supernodes"])
-    k = np.diff(pl["sn_first"])
-    want = [[] for _ in range(int(pl["Wptr"][-1]))]
-    for c in range(ns):
-        par = int(pl["sn_parent"][c])
-        if par < 0:
-            continue
-        rel = pl["rel"][int(pl["Rptr"][c]): int(pl["Rptr"][c + 1])]
-        for t, r in enumerate(rel):
-            want[int(pl["Wptr"][par]) + int(r)].append(int(pl["Wptr"][c]) + int(k[c]) + t)
-    got = [list(pl["cidx"][pl["cptr"][i]: pl["cptr"][i + 1]]) for i in range(len(want))]
-    assert got == want
+        # plain supernodal substitution with the factor itself (no inverse panels) as a cross-check
+        zs = em.solve(b, refine=0, flow=False)
+        assert np.linalg.norm(zs - z) <= 1e-10 * np.linalg.norm(z)
 
 
 def test_same_pattern_same_structure_different_values():
