@@ -782,7 +782,9 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
     mark(1);
     const int max_ctas      = g_sms * g_flow_ctas;
     auto grid = [&](size_t ntasks) {
-      const long long ctas = ((long long)ntasks + FLOW_SHARDS - 1) / FLOW_SHARDS;
+      // at least ~4 tasks per warp: small systems (batched multistart, many handles on one GPU) leave room for the
+      // sweeps of other handles instead of parking spinning warps on every SM
+      const long long ctas = ((long long)ntasks + 4 * FLOW_SHARDS - 1) / (4 * FLOW_SHARDS);
       return (unsigned)std::max<long long>(1, std::min<long long>(max_ctas, ctas));
     };
     const FlowSched fs{(int)P.ffl_tasks.size(), g_flow_sleep};
