@@ -27,13 +27,24 @@ k_pre(int m,
       const double* __restrict__ Aval,
       const double* __restrict__ dE,
       const double* __restrict__ rhs,
-      double* __restrict__ bR)
+      double* __restrict__ bR,
+      int nflow,
+      double* __restrict__ yf,
+      double* __restrict__ x,
+      int* __restrict__ flow)
 {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
+  // what the dataflow sweeps accumulate into starts at zero (counters and tickets: nflow ints)
+  if (r < nflow)
+  {
+    flow[r] = 0;
+  }
   if (r >= m)
   {
     return;
   }
+  yf[r] = 0.0;
+  x[r]  = 0.0;
   double acc = rhs[k_of_r[r]];
   for (int q = Aptr[r]; q < Aptr[r + 1]; ++q)
   {
@@ -43,29 +54,29 @@ k_pre(int m,
   bR[pinv[r]] = acc;
 }
 
+// z_R = y (original labels) and z_E = (b_E - A^T y) / d in one launch: thread i < m handles reduced row i, the others
+// one eliminated variable each
 __global__ void
-k_post_r(int m, const int* __restrict__ k_of_r, const int* __restrict__ pinv, const double* __restrict__ y, double* __restrict__ z)
+k_post(int m,
+       int nE,
+       const int* __restrict__ k_of_r,
+       const int* __restrict__ k_of_e,
+       const int* __restrict__ pinv,
+       const int* __restrict__ Aptr,
+       const int* __restrict__ Arow,
+       const double* __restrict__ Aval,
+       const double* __restrict__ dE,
+       const double* __restrict__ rhs,
+       const double* __restrict__ y,
+       double* __restrict__ z)
 {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < m)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m)
   {
-    z[k_of_r[r]] = y[pinv[r]];
+    z[k_of_r[i]] = y[pinv[i]];
+    return;
   }
-}
-
-__global__ void
-k_post_e(int nE,
-         const int* __restrict__ k_of_e,
-         const int* __restrict__ pinv,
-         const int* __restrict__ Aptr,
-         const int* __restrict__ Arow,
-         const double* __restrict__ Aval,
-         const double* __restrict__ dE,
-         const double* __restrict__ rhs,
-         const double* __restrict__ y,
-         double* __restrict__ z)
-{
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = i - m;
   if (e >= nE)
   {
     return;
@@ -520,22 +531,6 @@ k_flow(const SweepTask* __restrict__ tasks,
   }
 }
 
-// zeroes what the dataflow sweeps accumulate into (one thread per reduced row / counter)
-__global__ void
-k_flow_reset(int m, int nflow, double* __restrict__ yf, double* __restrict__ x, int* __restrict__ flow)
-{
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m)
-  {
-    yf[i] = 0.0;
-    x[i]  = 0.0;
-  }
-  if (i < nflow)
-  {
-    flow[i] = 0;
-  }
-}
-
 // ---- small utilities -----------------------------------------------------------------------------------
 __global__ void
 k_scatter(int nnz, const int* __restrict__ idx, int first, const double* __restrict__ val, double* __restrict__ out)
@@ -773,11 +768,10 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
   const int T   = 256;
   if (P.m > 0)
   {
-    k_pre<<<nblocks(P.m, T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.k_of_e.p, dp.pinv.p, dp.Acsr_ptr.p, dp.Acsr_col.p, nb.Acsr_val, nb.dE, in, sb.y);
-    lc.tick();
     const int ns    = P.nsuper;
     const int nflow = 2 * ns + 2 * FLOW_SHARDS * FLOW_TICKET_PITCH;
-    k_flow_reset<<<nblocks(std::max(P.m, nflow), T), T, 0, stream>>>(P.m, nflow, sb.yf, sb.x, sb.flow);
+    k_pre<<<nblocks(std::max(P.m, nflow), T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.k_of_e.p, dp.pinv.p, dp.Acsr_ptr.p, dp.Acsr_col.p, nb.Acsr_val, nb.dE, in, sb.y, nflow, sb.yf, sb.x,
+                                                             sb.flow);
     lc.tick();
     mark(1);
     const int max_ctas      = g_sms * g_flow_ctas;
@@ -801,12 +795,10 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
                                                                  (const FlowTrace*)sb.trace_bwd);
     lc.tick();
     mark(3);
-    k_post_r<<<nblocks(P.m, T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.pinv.p, sb.x, out);
-    lc.tick();
   }
-  if (P.nE > 0)
+  if (P.m + P.nE > 0)
   {
-    k_post_e<<<nblocks(P.nE, T), T, 0, stream>>>(P.nE, dp.k_of_e.p, dp.pinv.p, dp.Acsc_ptr.p, dp.Acsc_row.p, nb.Acsc_val, nb.dE, in, sb.x, out);
+    k_post<<<nblocks((long long)P.m + P.nE, T), T, 0, stream>>>(P.m, P.nE, dp.k_of_r.p, dp.k_of_e.p, dp.pinv.p, dp.Acsc_ptr.p, dp.Acsc_row.p, nb.Acsc_val, nb.dE, in, sb.x, out);
     lc.tick();
   }
   mark(4);
