@@ -89,7 +89,8 @@ def test_known_answers():
     lambda: problems.poisson_control(10, 3, seed=4),
     lambda: problems.chain_rosenbrock(5000, 0.15, seed=5),
     lambda: problems.chain_rosenbrock(33, 0.0),
-], ids=["config1", "p2d_g8", "p2d_g40", "p3d_g10", "chain_5000", "chain_33"])
+    lambda: problems.poisson_control(100, 2, seed=1),  # supernodes of 400 columns: three outer blocks of the panel steps
+], ids=["config1", "p2d_g8", "p2d_g40", "p3d_g10", "chain_5000", "chain_33", "p2d_g100"])
 def test_small_and_medium_problems(make):
     _check_problem(make(), seeds=(1, 2))
 

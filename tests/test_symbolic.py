@@ -18,6 +18,7 @@ CASES = {
     "chain_n33_noactive": lambda: problems.chain_rosenbrock(33, 0.0),
     "no_constraints": lambda: _no_cons(),
     "poisson2d_g48_wide_supernodes": lambda: problems.poisson_control(48, 2, seed=5),  # supernodes wider than one outer block
+    "poisson2d_g100_three_outer_blocks": lambda: problems.poisson_control(100, 2, seed=1),  # k = 402: far updates, K = 128 prologues
 }
 
 
@@ -51,7 +52,7 @@ def test_structure_matches_independent_symbolic(name):
     assert np.all(parent[nz] > np.nonzero(nz)[0])
 
 
-@pytest.mark.parametrize("name", ["config1", "poisson2d_g24", "poisson3d_g6", "chain_n2000", "poisson2d_g48_wide_supernodes"])
+@pytest.mark.parametrize("name", ["config1", "poisson2d_g24", "poisson3d_g6", "chain_n2000", "poisson2d_g48_wide_supernodes", "poisson2d_g100_three_outer_blocks"])
 def test_plan_emulation_solves_kkt(name):
     p = CASES[name]()
     cp, ri, v = p.kkt_lower()
