@@ -76,10 +76,10 @@ struct TrTask
 
 // Warp task of the dataflow sweeps (solve.cu: k_flow). One warp owns a block of a supernode's inverse panel,
 // rows [i0, i1) x columns [j0, j1), one lane per output and at most 16 panel entries per lane:
-//   forward : lanes = rows (i1 - i0 <= 32), depth = columns (j1 - j0 <= 16), column-major panel Mt; partial sums
+//   forward : lanes = rows (i1 - i0 <= 32), depth = columns (j1 - j0 <= 16, or 32 in the wide levels), column-major panel Mt; partial sums
 //             are added to yf (top block rows) or pushed to their final rows of the accumulator (tail rows);
-//   backward: lanes = columns (j1 - j0 <= 32, j0 a multiple of 32), depth = rows (i1 - i0 <= 16, i0 a multiple of
-//             16), row-major copy Mr; partial sums are added to x.
+//   backward: lanes = columns (j1 - j0 <= 32, j0 a multiple of 32), depth = rows (i1 - i0 <= 16 or 32, i0 a multiple
+//             of 16), row-major copy Mr; partial sums are added to x.
 // Dependencies are counters, one per supernode: a task waits until cnt[wait_idx] >= need (wait_idx < 0: no wait)
 // and adds 1 to cnt[signal_idx] when its results are visible (signal_idx < 0: nobody waits for it).
 //   forward : wait on the own supernode (its children signal it), signal the parent;

@@ -320,12 +320,13 @@ flow_take_finish(int issued, int* __restrict__ ticket, int ntasks, int lane, int
   return __shfl_sync(0xffffffffu, t, 0);
 }
 
-constexpr int FLOW_DEPTH = 16; // panel entries in flight per lane = depth of a task
+constexpr int FLOW_DEPTH     = 16; // panel entries in flight per lane = one batch of loads
+constexpr int FLOW_MAX_DEPTH = 32; // depth of a task: one batch in the narrow levels, two in the wide ones (symbolic.cpp)
 
 // One task up to (not including) the publication of its completion.
 //   FWD: lanes are rows [i0, i1), depth is columns [j0, j1), panel element (r, j) at Mt[j * h + r].
 //   BWD: lanes are columns [j0, j1), depth is rows [i0, i1), panel element (i, j) at Mr[i * k + j].
-// vsh: FLOW_DEPTH doubles of shared memory private to the warp (broadcast of the vector).
+// vsh: FLOW_MAX_DEPTH doubles of shared memory private to the warp (broadcast of the vector).
 template <bool FWD, bool TRACE>
 __device__ __forceinline__ void
 flow_task(const SweepTask& T,
@@ -418,10 +419,7 @@ flow_task(const SweepTask& T,
     }
   }
   __syncwarp(); // the previous task's reads of vsh are done
-  if (lane < FLOW_DEPTH)
-  {
-    vsh[lane] = vsrc ? (vplain ? *vsrc : __ldcg(vsrc)) : 0.0;
-  }
+  vsh[lane] = vsrc ? (vplain ? *vsrc : __ldcg(vsrc)) : 0.0;
   __syncwarp();
   if (TRACE)
   {
@@ -433,6 +431,20 @@ flow_task(const SweepTask& T,
   {
     acc0 += pre[u] * vsh[u];
     acc1 += pre[u + 1] * vsh[u + 1];
+  }
+  if (nd > FLOW_DEPTH) // second batch of a deep task (wide levels only)
+  {
+#pragma unroll
+    for (int u = 0; u < FLOW_DEPTH; ++u)
+    {
+      pre[u] = (ov && FLOW_DEPTH + u < nd) ? __ldcs(P + (long long)(FLOW_DEPTH + u) * ld) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < FLOW_DEPTH; u += 2)
+    {
+      acc0 += pre[u] * vsh[FLOW_DEPTH + u];
+      acc1 += pre[u + 1] * vsh[FLOW_DEPTH + u + 1];
+    }
   }
   if (ov)
   {
@@ -466,10 +478,10 @@ k_flow(const SweepTask* __restrict__ tasks,
        int* __restrict__ ticket,
        const FlowTrace* __restrict__ trace)
 {
-  __shared__ double vsh_all[FLOW_THREADS / 32 * FLOW_DEPTH];
+  __shared__ double vsh_all[FLOW_THREADS / 32 * FLOW_MAX_DEPTH];
   __shared__ __align__(16) SweepTask slot_all[FLOW_THREADS / 32]; // the warp's task record, fetched with cp.async
   const int lane  = threadIdx.x & 31;
-  double* vsh     = vsh_all + (threadIdx.x >> 5) * FLOW_DEPTH;
+  double* vsh     = vsh_all + (threadIdx.x >> 5) * FLOW_MAX_DEPTH;
   SweepTask* slot = slot_all + (threadIdx.x >> 5);
   FlowPhases ph;
   long long cf = TRACE ? clk_after(0.0) : 0;

@@ -12,7 +12,6 @@
 
 #include <algorithm>
 #include <chrono>
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -1598,15 +1597,31 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   tick("inversion + transpose tasks");
   // ---- dataflow sweeps: warp tasks in ticket order, dependency counters per supernode -------------------------
   {
-    constexpr int LANES = 32, DEPTH = 16;
+    constexpr int LANES = 32;
+    constexpr int FLOW_WARPS = 148 * FLOW_CTAS_PER_SM * (FLOW_THREADS / 32);
     if ((i64)P.Ridx.size() > 0x7ffffff0)
     {
       return fail(err, B200_ERR_UNSUPPORTED, "row-index array exceeds 2^31 entries");
     }
+    // Depth of a task: 16 panel entries per lane (one batch of loads, all in flight before the warp waits) where a
+    // level has fewer tasks than the machine has warps -- the narrow levels are latency-bound --, 32 (two batches)
+    // where it has more: there the fixed cost of a task (record, publication, ticket) is what limits the bandwidth.
+    std::vector<int> depth_of_level(P.nlevels, 16);
+    for (int l = 0; l < P.nlevels; ++l)
+    {
+      i64 entries = 0;
+      for (int q = P.lvl_ptr[l]; q < P.lvl_ptr[l + 1]; ++q)
+      {
+        const int T = P.lvl_sn[q];
+        entries += (P.Wptr[T + 1] - P.Wptr[T]) * (i64)(P.sn_first[T + 1] - P.sn_first[T]);
+      }
+      // (measured on B200: a lower threshold or a depth of 64 is slower on every configuration)
+      depth_of_level[l] = entries / (LANES * 16) >= (i64)FLOW_WARPS ? 32 : 16;
+    }
     // forward: lanes = rows, depth = columns (row r of the triangular top block needs columns <= r)
     // backward: lanes = columns (blocks aligned to 32 like the tiles of the row-major copy), depth = rows (column j
     //           needs rows >= j)
-    auto fwd_blocks = [&](int k, int h, auto&& emit) {
+    auto fwd_blocks = [&](int k, int h, int DEPTH, auto&& emit) {
       for (int i0 = 0; i0 < h; i0 += LANES)
       {
         const int i1 = std::min(h, i0 + LANES);
@@ -1617,7 +1632,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         }
       }
     };
-    auto bwd_blocks = [&](int k, int h, auto&& emit) {
+    auto bwd_blocks = [&](int k, int h, int DEPTH, auto&& emit) {
       for (int j0 = 0; j0 < k; j0 += LANES)
       {
         for (int i0 = j0; i0 < h; i0 += DEPTH) // j0 is a multiple of 32, so the depth blocks are aligned to 16
@@ -1631,8 +1646,8 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     {
       const int k = P.sn_first[T + 1] - P.sn_first[T];
       const int h = (int)(P.Wptr[T + 1] - P.Wptr[T]);
-      fwd_blocks(k, h, [&](int, int, int, int) { ++nf[T]; });
-      bwd_blocks(k, h, [&](int, int, int, int) { ++nbk[T]; });
+      fwd_blocks(k, h, depth_of_level[P.sn_level[T]], [&](int, int, int, int) { ++nf[T]; });
+      bwd_blocks(k, h, depth_of_level[P.sn_level[T]], [&](int, int, int, int) { ++nbk[T]; });
     }
     for (int l = 0; l < P.nlevels; ++l)
     {
@@ -1648,7 +1663,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
           need += nf[P.child_idx[q]];
         }
         const int wait_idx = need > 0 ? T : -1;
-        fwd_blocks(k, h, [&](int i0, int i1, int j0, int j1) {
+        fwd_blocks(k, h, depth_of_level[l], [&](int i0, int i1, int j0, int j1) {
           P.ffl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, j1, wait_idx, need, P.sn_parent[T], l, 0, 0});
         });
       }
@@ -1663,7 +1678,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         const int h   = (int)(P.Wptr[T + 1] - P.Wptr[T]);
         const int par = P.sn_parent[T];
         const int signal_idx = P.child_ptr[T + 1] > P.child_ptr[T] ? T : -1;
-        bwd_blocks(k, h, [&](int i0, int i1, int j0, int j1) {
+        bwd_blocks(k, h, depth_of_level[l], [&](int i0, int i1, int j0, int j1) {
           const bool tail = i1 > k && par >= 0; // touches x of the ancestors
           P.bfl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, j1, tail ? par : -1, tail ? nbk[par] : 0, signal_idx, l, 0, 0});
         });
