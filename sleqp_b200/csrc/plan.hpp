@@ -96,7 +96,8 @@ struct alignas(16) SweepTask
   int j0, j1;
   int wait_idx, need;
   int signal_idx;
-  int pad0, pad1, pad2; // pad0: level of the supernode (timeline traces)
+  int pad0, pad1, pad2; // pad0: level of the supernode (timeline traces); pad1: 1 in the narrow levels (fewer tasks than
+                        // warps: latency-critical, the completion is signalled before the next ticket is drawn)
 };
 static_assert(sizeof(SweepTask) == 64, "SweepTask layout");
 

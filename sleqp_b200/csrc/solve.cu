@@ -248,6 +248,7 @@ fence_acq_rel()
 // from ready: it polls rarely and with relaxed loads (an acquire load invalidates the SM's whole L1, CCTL.IVALL, and
 // thousands of warps hold tasks of the narrow top levels for most of the sweep). Once the count moves the
 // producers are finishing: tight acquire polls, and the poll that succeeds is the acquire the vector loads need.
+// (Back-to-back relaxed polls in that phase measured slightly slower.)
 __device__ __forceinline__ void
 wait_counter(const int* cnt, int need, unsigned far_sleep)
 {
@@ -508,10 +509,12 @@ k_flow(const SweepTask* __restrict__ tasks,
     {
       cf = clk_after(0.0);
     }
-    // publication. The draw of the next ticket is issued first so that its round trip overlaps with the fence;
-    // nothing can block between the draw and the signal.
-    const bool open  = tried < FLOW_SHARDS;
-    const int issued = open ? flow_take_issue(ticket, lane, shard) : 0;
+    // publication. In the wide levels the draw of the next ticket is issued first, so that its round trip overlaps
+    // with the fence (nothing can block between the draw and the signal). In the narrow levels consumers are
+    // waiting for exactly this signal and the fence must not wait for the ticket atomic: signal first.
+    const bool open     = tried < FLOW_SHARDS;
+    const bool critical = T.pad1 != 0;
+    int issued          = (open && !critical) ? flow_take_issue(ticket, lane, shard) : 0;
     if (T.signal_idx >= 0)
     {
       fence_acq_rel(); // every lane: its own atomics are visible device-wide before the counter moves
@@ -520,6 +523,10 @@ k_flow(const SweepTask* __restrict__ tasks,
       {
         atomicAdd(cnt + T.signal_idx, 1);
       }
+    }
+    if (open && critical)
+    {
+      issued = flow_take_issue(ticket, lane, shard);
     }
     cur = open ? flow_take_finish(issued, ticket, sched.ntasks, lane, shard, tried) : -1;
     if (TRACE)

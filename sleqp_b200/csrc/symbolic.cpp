@@ -1664,7 +1664,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         }
         const int wait_idx = need > 0 ? T : -1;
         fwd_blocks(k, h, depth_of_level[l], [&](int i0, int i1, int j0, int j1) {
-          P.ffl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, j1, wait_idx, need, P.sn_parent[T], l, 0, 0});
+          P.ffl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, j1, wait_idx, need, P.sn_parent[T], l, depth_of_level[l] == 16, 0});
         });
       }
     }
@@ -1680,7 +1680,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         const int signal_idx = P.child_ptr[T + 1] > P.child_ptr[T] ? T : -1;
         bwd_blocks(k, h, depth_of_level[l], [&](int i0, int i1, int j0, int j1) {
           const bool tail = i1 > k && par >= 0; // touches x of the ancestors
-          P.bfl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, j1, tail ? par : -1, tail ? nbk[par] : 0, signal_idx, l, 0, 0});
+          P.bfl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, j1, tail ? par : -1, tail ? nbk[par] : 0, signal_idx, l, depth_of_level[l] == 16, 0});
         });
       }
     }
