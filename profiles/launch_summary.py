@@ -18,9 +18,9 @@ def main(path, nlev=13):
         seq.append((name, v, row['Grid Size']))
     for k, (c, t, mx) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:16]:
         print(f"{k[:50]:50s} n={c:5d} total={t/1e3:9.3f} ms  avg={t/c:9.1f} us max={mx:9.1f} us  share={t/tot*100:5.1f}%")
-    for kn in ('k_fwd_chunk', 'k_bwd_chunk'):
+    for kn in ('void k_flow<1, 0>', 'void k_flow<0, 0>'):  # forward / backward dataflow sweep: one launch per sweep
         idx = [i for i, (n, _, _) in enumerate(seq) if n == kn][-nlev:]
-        print(kn, 'last sweep per level (us, grid):', [(round(seq[i][1], 1), seq[i][2].split(',')[0].strip('(')) for i in idx])
+        print(kn, 'last launches (us, grid):', [(round(seq[i][1], 1), seq[i][2].split(',')[0].strip('(')) for i in idx])
 
 if __name__ == '__main__':
     main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 13)
