@@ -16,6 +16,8 @@ for p in (problems.config(0), problems.poisson_control(30, 2, seed=1), problems.
         idx, val = p.rhs(kind, 1)
         f.solve(idx[::2], val[::2], p.N)
         x = f.solution_dense(0, p.N)
+        si, sv = f.solution(0, p.N, float(np.median(np.abs(x))))  # device-side sparsification (page-locked buffers)
+        assert len(si) == int((np.abs(x) > float(np.median(np.abs(x)))).sum())
         b = np.zeros(p.N)
         b[idx[::2]] = val[::2]
         assert np.linalg.norm(K @ x - b) <= 1e-10 * np.linalg.norm(b)

@@ -711,10 +711,11 @@ k_compact_scan(int nchunks, int* __restrict__ chunk_cnt)
 }
 
 __global__ void __launch_bounds__(CP_THREADS)
-k_compact_write(int n, const double* __restrict__ x, double eps, const int* __restrict__ chunk_off, int* __restrict__ idx_out, double* __restrict__ val_out)
+k_compact_write(int n, int nchunks, const double* __restrict__ x, double eps, const int* __restrict__ chunk_off, int* __restrict__ idx_out, double* __restrict__ val_out)
 {
   __shared__ int wcnt[CP_PER][CP_THREADS / 32];
-  const int base = blockIdx.x * CP_CHUNK;
+  const int base  = blockIdx.x * CP_CHUNK;
+  const int total = chunk_off[nchunks];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double v[CP_PER];
   unsigned bal[CP_PER];
@@ -722,6 +723,11 @@ k_compact_write(int n, const double* __restrict__ x, double eps, const int* __re
   for (int r = 0; r < CP_PER; ++r)
   {
     const int i = base + r * CP_THREADS + threadIdx.x;
+    if (i < n && i >= total) // the slots behind the kept entries: the arrays are copied to the host at full length
+    {
+      idx_out[i] = 0;
+      val_out[i] = 0.0;
+    }
     v[r]        = i < n ? x[i] : 0.0;
     bal[r]      = __ballot_sync(0xffffffffu, i < n && fabs(v[r]) > eps);
     if (lane == 0)
@@ -964,7 +970,7 @@ enqueue_compact(const double* x, int n, double eps, int* chunk_cnt, int* idx_out
   lc.tick();
   if (nchunks > 0)
   {
-    k_compact_write<<<nchunks, CP_THREADS, 0, stream>>>(n, x, eps, chunk_cnt, idx_out, val_out);
+    k_compact_write<<<nchunks, CP_THREADS, 0, stream>>>(n, nchunks, x, eps, chunk_cnt, idx_out, val_out);
     lc.tick();
   }
   B200_CUDA(cudaGetLastError());
