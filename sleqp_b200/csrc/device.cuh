@@ -176,6 +176,7 @@ struct DevPlan
   // E-part / residual operators
   DevBuf<int> k_of_e, k_of_r, pinv, perm, dE_src;
   DevBuf<int> Acsc_ptr, Acsc_row, Acsc_src, Acsr_ptr, Acsr_col, Acsr_src, Gsym_ptr, Gsym_col, Gsym_src;
+  DevBuf<int> Acsr_k, Acsr_dsrc, Acsc_p;
 };
 
 } // namespace b200

@@ -44,7 +44,7 @@ struct b200_fact
 
   DevPlan dp;
   // factor
-  DevBuf<double> val, L, Mt, Mr, tmp, U, D, Dinv, scratch, scal, dE, Acsc_val, Acsr_val, Gsym_val;
+  DevBuf<double> val, L, Mt, Mr, tmp, U, D, Dinv, scratch, scal, dE, Acsc_val, Acsr_val, Acsr_sval, Gsym_val;
   DevBuf<int> nper;
   // solve
   DevBuf<double> rhs, z, res, dz, bR, y, yf, x;
@@ -84,6 +84,7 @@ struct b200_fact
     nb.dE          = dE.p;
     nb.Acsc_val    = Acsc_val.p;
     nb.Acsr_val    = Acsr_val.p;
+    nb.Acsr_sval   = Acsr_sval.p;
     nb.Gsym_val    = Gsym_val.p;
     return nb;
   }
@@ -217,6 +218,9 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   dp.Acsr_ptr.upload(P.Acsr_ptr, s);
   dp.Acsr_col.upload(P.Acsr_col, s);
   dp.Acsr_src.upload(P.Acsr_src, s);
+  dp.Acsr_k.upload(P.Acsr_k, s);
+  dp.Acsr_dsrc.upload(P.Acsr_dsrc, s);
+  dp.Acsc_p.upload(P.Acsc_p, s);
   dp.Gsym_ptr.upload(P.Gsym_ptr, s);
   dp.Gsym_col.upload(P.Gsym_col, s);
   dp.Gsym_src.upload(P.Gsym_src, s);
@@ -238,6 +242,7 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   F->dE.reserve((size_t)P.nE + 8);
   F->Acsc_val.reserve(P.Acsc_src.size() + 8);
   F->Acsr_val.reserve(P.Acsr_src.size() + 8);
+  F->Acsr_sval.reserve(P.Acsr_src.size() + 8);
   F->Gsym_val.reserve(P.Gsym_src.size() + 8);
   F->rhs.reserve(N + 8);
   F->z.reserve(N + 8);

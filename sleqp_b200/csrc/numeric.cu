@@ -56,6 +56,16 @@ k_gather(int n, const int* __restrict__ src, const double* __restrict__ val, dou
   }
 }
 
+__global__ void
+k_gather_scaled(int n, const int* __restrict__ src, const int* __restrict__ dsrc, const double* __restrict__ val, double* __restrict__ out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+  {
+    out[i] = val[src[i]] / val[dsrc[i]];
+  }
+}
+
 // scal[0] = max_j |S_jj|, scal[1] = 64 eps * that  (static pivot threshold)
 __global__ void
 k_diagmax(int m, const long long* __restrict__ Sdiag, const double* __restrict__ L, unsigned long long* __restrict__ scal_bits)
@@ -808,6 +818,8 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
     k_gather<<<(nnzA + threads - 1) / threads, threads, 0, stream>>>(nnzA, dp.Acsc_src.p, nb.val, nb.Acsc_val);
     lc.tick();
     k_gather<<<(nnzA + threads - 1) / threads, threads, 0, stream>>>(nnzA, dp.Acsr_src.p, nb.val, nb.Acsr_val);
+    lc.tick();
+    k_gather_scaled<<<(nnzA + threads - 1) / threads, threads, 0, stream>>>(nnzA, dp.Acsr_src.p, dp.Acsr_dsrc.p, nb.val, nb.Acsr_sval);
     lc.tick();
   }
   const int nnzG = (int)P.Gsym_src.size();

@@ -22,6 +22,7 @@ struct NumericBuffers
   double* dE;        // pivots of the E block
   double* Acsc_val;
   double* Acsr_val;
+  double* Acsr_sval; // A entries divided by the pivot of their column (k_pre)
   double* Gsym_val;
 };
 

@@ -122,6 +122,9 @@ struct Plan
   std::vector<int> Acsc_ptr, Acsc_row, Acsc_src; // by E column; rows = original R index
   std::vector<int> Acsr_ptr, Acsr_col, Acsr_src; // by R row (original index); cols = E index
   std::vector<int> Gsym_ptr, Gsym_col, Gsym_src; // symmetric R-R coupling by R row (original)
+  // resolved index chains for the solve: K index of the column's variable and value index of its pivot (by CSR
+  // entry), permuted reduced row (by CSC entry)
+  std::vector<int> Acsr_k, Acsr_dsrc, Acsc_p;
 
   // ordering of the reduced system
   std::vector<int> perm, pinv; // new -> old R index, old -> new

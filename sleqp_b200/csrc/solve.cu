@@ -17,15 +17,15 @@ namespace b200
 {
 
 // ---- E-block elimination and back-substitution -------------------------------------------------
+// b_R' = b_R - A D^-1 b_E in the permuted labels of the reduced system. Asval = A entries divided by the pivot of
+// their column, Ak = K index of that column's variable (both resolved once: plan.hpp); four entries in flight.
 __global__ void
 k_pre(int m,
       const int* __restrict__ k_of_r,
-      const int* __restrict__ k_of_e,
       const int* __restrict__ pinv,
       const int* __restrict__ Aptr,
-      const int* __restrict__ Acol,
-      const double* __restrict__ Aval,
-      const double* __restrict__ dE,
+      const int* __restrict__ Ak,
+      const double* __restrict__ Asval,
       const double* __restrict__ rhs,
       double* __restrict__ bR,
       int nflow,
@@ -45,11 +45,28 @@ k_pre(int m,
   }
   yf[r] = 0.0;
   x[r]  = 0.0;
-  double acc = rhs[k_of_r[r]];
-  for (int q = Aptr[r]; q < Aptr[r + 1]; ++q)
+  double acc  = rhs[k_of_r[r]];
+  const int e = Aptr[r + 1];
+  for (int q = Aptr[r]; q < e; q += 4)
   {
-    const int e = Acol[q];
-    acc -= Aval[q] * (rhs[k_of_e[e]] / dE[e]);
+    int kk[4];
+    double a[4], v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      kk[u] = q + u < e ? Ak[q + u] : 0;
+      a[u]  = q + u < e ? Asval[q + u] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      v[u] = q + u < e ? rhs[kk[u]] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      acc -= a[u] * v[u];
+    }
   }
   bR[pinv[r]] = acc;
 }
@@ -63,7 +80,7 @@ k_post(int m,
        const int* __restrict__ k_of_e,
        const int* __restrict__ pinv,
        const int* __restrict__ Aptr,
-       const int* __restrict__ Arow,
+       const int* __restrict__ Ap, // permuted reduced row of every CSC entry
        const double* __restrict__ Aval,
        const double* __restrict__ dE,
        const double* __restrict__ rhs,
@@ -81,13 +98,32 @@ k_post(int m,
   {
     return;
   }
-  const int k = k_of_e[e];
-  double acc  = rhs[k];
-  for (int q = Aptr[e]; q < Aptr[e + 1]; ++q)
+  const int k   = k_of_e[e];
+  const int end = Aptr[e + 1];
+  double acc    = rhs[k];
+  const double d = dE[e];
+  for (int q = Aptr[e]; q < end; q += 4)
   {
-    acc -= Aval[q] * y[pinv[Arow[q]]];
+    int pp[4];
+    double a[4], v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      pp[u] = q + u < end ? Ap[q + u] : 0;
+      a[u]  = q + u < end ? Aval[q + u] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      v[u] = q + u < end ? y[pp[u]] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      acc -= a[u] * v[u];
+    }
   }
-  z[k] = acc / dE[e];
+  z[k] = acc / d;
 }
 
 // res = rhs - K z
@@ -795,7 +831,7 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
   {
     const int ns    = P.nsuper;
     const int nflow = 2 * ns + 2 * FLOW_SHARDS * FLOW_TICKET_PITCH;
-    k_pre<<<nblocks(std::max(P.m, nflow), T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.k_of_e.p, dp.pinv.p, dp.Acsr_ptr.p, dp.Acsr_col.p, nb.Acsr_val, nb.dE, in, sb.y, nflow, sb.yf, sb.x,
+    k_pre<<<nblocks(std::max(P.m, nflow), T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.pinv.p, dp.Acsr_ptr.p, dp.Acsr_k.p, nb.Acsr_sval, in, sb.y, nflow, sb.yf, sb.x,
                                                              sb.flow);
     lc.tick();
     mark(1);
@@ -823,7 +859,7 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
   }
   if (P.m + P.nE > 0)
   {
-    k_post<<<nblocks((long long)P.m + P.nE, T), T, 0, stream>>>(P.m, P.nE, dp.k_of_r.p, dp.k_of_e.p, dp.pinv.p, dp.Acsc_ptr.p, dp.Acsc_row.p, nb.Acsc_val, nb.dE, in, sb.x, out);
+    k_post<<<nblocks((long long)P.m + P.nE, T), T, 0, stream>>>(P.m, P.nE, dp.k_of_r.p, dp.k_of_e.p, dp.pinv.p, dp.Acsc_ptr.p, dp.Acsc_p.p, nb.Acsc_val, nb.dE, in, sb.x, out);
     lc.tick();
   }
   mark(4);

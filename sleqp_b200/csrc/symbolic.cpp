@@ -1686,6 +1686,20 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
 
+  // ---- operators of the E-block elimination with their index chains resolved once (k_pre / k_post: one dependent
+  //      load less per entry) -------------------------------------------------------------------------------------
+  P.Acsr_k.resize(P.Acsr_col.size());
+  P.Acsr_dsrc.resize(P.Acsr_col.size());
+  for (size_t q = 0; q < P.Acsr_col.size(); ++q)
+  {
+    P.Acsr_k[q]    = P.k_of_e[P.Acsr_col[q]];
+    P.Acsr_dsrc[q] = P.dE_src[P.Acsr_col[q]];
+  }
+  P.Acsc_p.resize(P.Acsc_row.size());
+  for (size_t q = 0; q < P.Acsc_row.size(); ++q)
+  {
+    P.Acsc_p[q] = P.pinv[P.Acsc_row[q]];
+  }
   tick("sweep tasks");
   // ---- hash of the full permutation -----------------------------------------------------------------------------
   {
