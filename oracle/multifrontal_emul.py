@@ -76,16 +76,34 @@ class Emulated:
         self.tau = 64 * np.finfo(float).eps * smax
         scratch = np.full(max(1, int(p["n_scratch_slots"]) if "n_scratch_slots" in p else 1) * NB * NB, np.nan)
         has_children = np.diff(p["child_ptr"]) > 0
+        # Look-ahead on the device (two streams): per stage the panel step and the update tiles of the NEXT panel's
+        # columns [ub, um) on the main stream, the remaining tiles [um, ue) on the side stream next to the following
+        # panel step. rest(s) waits for panel(s); the look-ahead tiles of stage s and any extend-add wait for
+        # rest(s - 1). The emulation runs the LATEST order that allows: rest(s - 1) after panel(s).
+        pending = None  # rest tiles of the previous stage not yet executed
+
+        def run_updates(lo, hi):
+            for T, t, kind, i0, j0, kb, ke in p["upd_tasks"][lo:hi]:
+                self._update(int(T), int(t), int(kind), int(i0), int(j0), scratch, bool(has_children[T]), int(kb), int(ke))
+
         for st in p["stages"]:
-            zb, ze, eb, ee, pb, pe, ub, ue = (int(x) for x in st)
+            zb, ze, eb, ee, pb, pe, ub, um, ue, _pad = (int(x) for x in st)
+            assert ub <= um <= ue
+            if pending is not None and (ee > eb or ze > zb):
+                run_updates(*pending)
+                pending = None
             for T in p["zero_sn"][zb:ze]:
                 self.umat(T)[:, :] = 0.0
             for c, jb in p["ea_tasks"][eb:ee]:
                 self._extend_add(int(c), int(jb))
-            for T, t, rb, _pad in p["pan_tasks"][pb:pe]:
+            for T, t, rb, _pad2 in p["pan_tasks"][pb:pe]:
                 self._panel(int(T), int(t), int(rb))
-            for T, t, kind, i0, j0, kb, ke in p["upd_tasks"][ub:ue]:
-                self._update(int(T), int(t), int(kind), int(i0), int(j0), scratch, bool(has_children[T]), int(kb), int(ke))
+            if pending is not None:
+                run_updates(*pending)
+            run_updates(ub, um)
+            pending = (um, ue)
+        if pending is not None:
+            run_updates(*pending)
 
     # ---------------------------------------------------------------- selective inversion
     def mpanel(self, T):

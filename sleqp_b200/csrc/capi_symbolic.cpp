@@ -234,7 +234,7 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
 #undef FIELD
   if (f == "stages")
   {
-    static_assert(sizeof(Stage) == 8 * sizeof(int), "Stage layout");
+    static_assert(sizeof(Stage) == 10 * sizeof(int), "Stage layout");
     return export_vec(P.stages, out, count);
   }
   if (f == "ea_tasks")

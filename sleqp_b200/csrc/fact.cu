@@ -41,6 +41,7 @@ struct b200_fact
   int device          = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_copy = nullptr;
+  NumericOverlap overlap = {}; // side stream + events of the factorization graph (look-ahead)
 
   DevPlan dp;
   // factor
@@ -378,6 +379,15 @@ b200_fact_create(b200_fact** handle, int device)
     B200_CUDA(cudaEventCreate(&F->ev_c));
     B200_CUDA(cudaEventCreate(&F->ev_d));
     B200_CUDA(cudaEventCreateWithFlags(&F->ev_copy, cudaEventDisableTiming));
+    B200_CUDA(cudaStreamCreateWithFlags(&F->overlap.side, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : F->overlap.panel_done)
+    {
+      B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    for (cudaEvent_t& e : F->overlap.rest_done)
+    {
+      B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     configure_solve_kernels();
     configure_numeric_kernels();
     *handle = F.release();
@@ -435,7 +445,7 @@ b200_fact_set_matrix(b200_fact* F, int n_rows, int n_cols, int nnz, const int* c
     {
       const NumericBuffers nb = F->nbuf();
       run_graph(F, F->g_numeric, [&](LaunchCounter& lc) {
-        enqueue_numeric(F->dp, nb, F->stream, lc);
+        enqueue_numeric(F->dp, nb, F->stream, lc, &F->overlap);
         enqueue_pivot_range(F->dp, nb, F->stream, lc);
       });
     }
@@ -510,7 +520,7 @@ b200_fact_refactor_device(b200_fact* F, const double* d_val)
     B200_CUDA(cudaMemcpyAsync(F->val.p, d_val, sizeof(double) * (size_t)P.nnzK_input, cudaMemcpyDeviceToDevice, F->stream));
     const NumericBuffers nb = F->nbuf();
     run_graph(F, F->g_numeric, [&](LaunchCounter& lc) {
-      enqueue_numeric(F->dp, nb, F->stream, lc);
+      enqueue_numeric(F->dp, nb, F->stream, lc, &F->overlap);
       enqueue_pivot_range(F->dp, nb, F->stream, lc);
     });
     B200_CUDA(cudaEventRecord(F->ev_b, F->stream));
@@ -1066,12 +1076,17 @@ b200_fact_free(b200_fact** handle)
     cudaStreamSynchronize(F->stream);
   }
   F->drop_graphs();
-  for (cudaEvent_t e : {F->ev_a, F->ev_b, F->ev_c, F->ev_d, F->ev_copy})
+  for (cudaEvent_t e : {F->ev_a, F->ev_b, F->ev_c, F->ev_d, F->ev_copy, F->overlap.panel_done[0], F->overlap.panel_done[1], F->overlap.rest_done[0], F->overlap.rest_done[1],
+                        F->overlap.rest_done[2]})
   {
     if (e)
     {
       cudaEventDestroy(e);
     }
+  }
+  if (F->overlap.side)
+  {
+    cudaStreamDestroy(F->overlap.side);
   }
   if (F->stream)
   {

@@ -747,7 +747,7 @@ configure_numeric_kernels()
 }
 
 void
-enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc)
+enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc, const NumericOverlap* ov)
 {
   const Plan& P = *dp.plan;
   B200_CUDA(cudaMemsetAsync(nb.scal, 0, sizeof(double) * 4, stream));
@@ -766,8 +766,19 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
     k_set_tau<<<1, 1, 0, stream>>>(nb.scal);
     lc.tick();
   }
-  for (const Stage& st : P.stages)
+  // Look-ahead over two streams. Main: zero-fill / extend-add of the supernodes that start, the panel step, then the
+  // update tiles of the NEXT panel's columns. Side: the rest of the stage's update tiles (and the Schur complements),
+  // next to the following panel step. rest(s) needs panel(s); the look-ahead tiles of stage s and anything that
+  // assembles children need rest(s - 1) (same tiles / the children's Schur complements).
+  const int nstages = (int)P.stages.size();
+  for (int si = 0; si < nstages; ++si)
   {
+    const Stage& st = P.stages[si];
+    const bool assembles = st.zero_end > st.zero_begin || st.ea_end > st.ea_begin;
+    if (ov && assembles && si >= 1)
+    {
+      B200_CUDA(cudaStreamWaitEvent(stream, ov->rest_done[(si - 1) % 3], 0));
+    }
     if (st.zero_end > st.zero_begin)
     {
       dim3 grid((unsigned)(st.zero_end - st.zero_begin), 16);
@@ -784,11 +795,35 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
       k_panel<<<(unsigned)(st.pan_end - st.pan_begin), PANEL_THR, 0, stream>>>(dp.pan_tasks.p + st.pan_begin, dp.sn.p, nb.L, nb.Mt, nb.D, nb.Dinv, nb.scal, nb.n_perturbed);
       lc.tick("panel");
     }
-    if (st.upd_end > st.upd_begin)
+    cudaStream_t rest_stream = stream;
+    if (ov)
     {
-      k_update<<<(unsigned)(st.upd_end - st.upd_begin), 128, TILE_SMEM, stream>>>(dp.upd_tasks.p + st.upd_begin, dp.sn.p, nb.L, nb.U, nb.D);
+      B200_CUDA(cudaEventRecord(ov->panel_done[si % 2], stream));
+      B200_CUDA(cudaStreamWaitEvent(ov->side, ov->panel_done[si % 2], 0));
+      rest_stream = ov->side;
+      if (si >= 1)
+      {
+        B200_CUDA(cudaStreamWaitEvent(stream, ov->rest_done[(si - 1) % 3], 0));
+      }
+    }
+    if (st.upd_mid > st.upd_begin)
+    {
+      k_update<<<(unsigned)(st.upd_mid - st.upd_begin), 128, TILE_SMEM, stream>>>(dp.upd_tasks.p + st.upd_begin, dp.sn.p, nb.L, nb.U, nb.D);
       lc.tick("update");
     }
+    if (st.upd_end > st.upd_mid)
+    {
+      k_update<<<(unsigned)(st.upd_end - st.upd_mid), 128, TILE_SMEM, rest_stream>>>(dp.upd_tasks.p + st.upd_mid, dp.sn.p, nb.L, nb.U, nb.D);
+      lc.tick("update");
+    }
+    if (ov)
+    {
+      B200_CUDA(cudaEventRecord(ov->rest_done[si % 3], ov->side));
+    }
+  }
+  if (ov && nstages > 0)
+  {
+    B200_CUDA(cudaStreamWaitEvent(stream, ov->rest_done[(nstages - 1) % 3], 0)); // join
   }
   // selective inversion
   for (size_t ph = 0; ph + 1 < P.inv_phase_ptr.size(); ++ph)

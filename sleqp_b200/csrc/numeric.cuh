@@ -45,7 +45,17 @@ struct SolveBuffers
 void configure_solve_kernels();
 void configure_numeric_kernels();
 
-void enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc);
+// Second stream + events of the look-ahead: the update tiles of a stage that do not touch the next panel's columns
+// run next to the next panel step (numeric.cu).
+struct NumericOverlap
+{
+  cudaStream_t side;
+  cudaEvent_t panel_done[2]; // rings over the stages
+  cudaEvent_t rest_done[3];
+};
+
+// ov == nullptr: everything on `stream` in stage order (profiling entry point: per-class timings)
+void enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc, const NumericOverlap* ov = nullptr);
 
 // One solve K z = rhs with `refine` refinement steps, everything on `stream`.
 void enqueue_solve(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, int refine, cudaStream_t stream, LaunchCounter& lc);

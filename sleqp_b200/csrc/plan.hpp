@@ -106,7 +106,10 @@ struct Stage
   int zero_begin, zero_end;
   int ea_begin, ea_end;
   int pan_begin, pan_end;
-  int upd_begin, upd_end;
+  // update tiles of the stage: [upd_begin, upd_mid) touch the columns of the NEXT panel step only ("look-ahead" part,
+  // on the critical path), [upd_mid, upd_end) everything else (runs next to the next panel step on a second stream)
+  int upd_begin, upd_mid, upd_end;
+  int pad;
 };
 
 struct Plan

@@ -1446,36 +1446,65 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         {
           P.pan_tasks.push_back({T, t, rb, 0});
         }
-        // trailing update inside the panel: front columns [c0+w, k), rows >= column
-        // two-level blocking: columns of the same NBO-wide outer block ("near") are updated after every
-        // panel step with K = w; the columns beyond it ("far") once, after the last step of the outer
-        // block, with K = the whole outer block -- DMMA tiles with a decent arithmetic intensity
-        const int ob_begin = (c0 / NBO) * NBO;
-        const int ob_end   = std::min(k, ob_begin + NBO);
-        for (int j0 = c0 + w; j0 < ob_end; j0 += TILE)
+      }
+      // Trailing update inside the panel: front columns [c0+w, k), rows >= column. Two-level blocking: columns of the
+      // same NBO-wide outer block ("near") are updated after every panel step with K = w; the columns beyond it ("far")
+      // once, after the last step of the outer block, with K = the whole outer block -- DMMA tiles with a decent
+      // arithmetic intensity. Look-ahead: the tiles of the NEXT panel's NB columns come first (pass 0); the next
+      // panel step waits for those only, the rest (pass 1, incl. the Schur complement) runs next to it.
+      for (int pass = 0; pass < 2; ++pass)
+      {
+        if (pass == 1)
         {
-          for (int i0 = j0; i0 < h; i0 += TILE)
-          {
-            P.upd_tasks.push_back({T, ob_end, UPD_INPANEL, i0, j0, c0, c0 + w});
-          }
+          st.upd_mid = (int)P.upd_tasks.size();
         }
-        if (c0 + w == ob_end)
+        for (int T : active[s])
         {
-          for (int j0 = ob_end; j0 < k; j0 += TILE)
-          {
-            for (int i0 = j0; i0 < h; i0 += TILE)
+          const int t  = s - P.sn_base[T];
+          const int k  = P.sn_first[T + 1] - P.sn_first[T];
+          const int r  = (int)(P.Rptr[T + 1] - P.Rptr[T]);
+          const int h  = k + r;
+          const int c0 = t * NB;
+          const int w  = std::min(NB, k - c0);
+          const int ob_begin = (c0 / NBO) * NBO;
+          const int ob_end   = std::min(k, ob_begin + NBO);
+          const int np0 = c0 + w, np1 = std::min(k, np0 + NB); // columns of the next panel step
+          auto tiles = [&](int jb, int je, int kb, int ke) {  // columns [jb, je), all rows below
+            for (int j0 = jb; j0 < je; j0 += TILE)
             {
-              P.upd_tasks.push_back({T, k, UPD_INPANEL, i0, j0, ob_begin, ob_end});
+              for (int i0 = j0; i0 < h; i0 += TILE)
+              {
+                P.upd_tasks.push_back({T, je, UPD_INPANEL, i0, j0, kb, ke});
+              }
+            }
+          };
+          if (pass == 0)
+          {
+            if (np0 < ob_end)
+            {
+              tiles(np0, np1, c0, c0 + w); // near
+            }
+            else if (np0 < k)
+            {
+              tiles(np0, np1, ob_begin, ob_end); // the next panel opens a new outer block: its share of the far update
             }
           }
-        }
-        if (t == P.sn_nt[T] - 1 && r > 0)
-        {
-          for (int j0 = 0; j0 < r; j0 += TILE)
+          else
           {
-            for (int i0 = j0; i0 < r; i0 += TILE)
+            tiles(std::min(ob_end, np0 + NB), ob_end, c0, c0 + w);
+            if (c0 + w == ob_end)
             {
-              P.upd_tasks.push_back({T, r, UPD_SCHUR, i0, j0, 0, k});
+              tiles(std::min(k, ob_end + NB), k, ob_begin, ob_end);
+            }
+            if (t == P.sn_nt[T] - 1 && r > 0)
+            {
+              for (int j0 = 0; j0 < r; j0 += TILE)
+              {
+                for (int i0 = j0; i0 < r; i0 += TILE)
+                {
+                  P.upd_tasks.push_back({T, r, UPD_SCHUR, i0, j0, 0, k});
+                }
+              }
             }
           }
         }

@@ -52,7 +52,7 @@ PLAN_FIELDS = {
     ).split()},
     **{k: np.int64 for k in "Rptr Lptr Wptr Sdest Sterm_ptr Uoff Tptr".split()},
 }
-PLAN_STRUCTS = {"stages": 8, "ea_tasks": 2, "pan_tasks": 4, "upd_tasks": 7, "inv_tasks": 6,
+PLAN_STRUCTS = {"stages": 10, "ea_tasks": 2, "pan_tasks": 4, "upd_tasks": 7, "inv_tasks": 6,
                 "ffl_tasks": 16, "bfl_tasks": 16, "tr_tasks": 3}  # int32 columns
 
 
