@@ -280,20 +280,23 @@ fence_acq_rel()
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
-// All lanes poll the same word (one request per poll). While no producer has signalled yet the consumer is far
+// All lanes poll the same word (one request per poll). While many producers are still missing the consumer is far
 // from ready: it polls rarely and with relaxed loads (an acquire load invalidates the SM's whole L1, CCTL.IVALL, and
-// thousands of warps hold tasks of the narrow top levels for most of the sweep). Once the count moves the
-// producers are finishing: tight acquire polls, and the poll that succeeds is the acquire the vector loads need.
-// (Back-to-back relaxed polls in that phase measured slightly slower.)
+// thousands of warps hold tasks of the narrow top levels for most of the sweep: tight polls of all of them on the
+// counter of a big supernode keep its L2 slice so busy that the producers' signals queue behind them). Once only
+// FLOW_NEAR signals are missing: tight acquire polls, and the poll that succeeds is the acquire the vector loads
+// need. (Back-to-back relaxed polls in that phase measured slightly slower.)
+constexpr int FLOW_NEAR = 64;
 __device__ __forceinline__ void
 wait_counter(const int* cnt, int need, unsigned far_sleep)
 {
   int c = ld_acquire(cnt);
   while (c < need)
   {
-    if (c == 0)
+    if (need - c > FLOW_NEAR)
     {
-      __nanosleep(far_sleep);
+      // the more signals are missing the longer the nap (4 ns per missing signal, far_sleep .. 8 far_sleep)
+      __nanosleep(min(8u * far_sleep, max(far_sleep, 4u * (unsigned)(need - c))));
       c = ld_relaxed(cnt);
       if (c >= need)
       {
