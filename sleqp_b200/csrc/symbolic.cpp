@@ -914,11 +914,6 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   // ---- supernodes: dense leaf subtrees + fundamental + relaxed chains -----------------------------
   std::vector<int> blk(m, -1);
   {
-    int LEAF_MAX = b200::LEAF_MAX;
-    if (const char* e = std::getenv("B200_LEAF_MAX")) // experiments only
-    {
-      LEAF_MAX = std::max(1, std::atoi(e));
-    }
     std::vector<int> size(m, 1);
     for (int j = 0; j < m; ++j)
     {
