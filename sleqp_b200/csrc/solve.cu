@@ -288,15 +288,15 @@ fence_acq_rel()
 // need. (Back-to-back relaxed polls in that phase measured slightly slower.)
 constexpr int FLOW_NEAR = 64;
 __device__ __forceinline__ void
-wait_counter(const int* cnt, int need, unsigned far_sleep)
+wait_counter(const int* cnt, int need, unsigned far_sleep, int near, unsigned per_signal)
 {
   int c = ld_acquire(cnt);
   while (c < need)
   {
-    if (need - c > FLOW_NEAR)
+    if (need - c > near)
     {
       // the more signals are missing the longer the nap (4 ns per missing signal, far_sleep .. 8 far_sleep)
-      __nanosleep(min(8u * far_sleep, max(far_sleep, 4u * (unsigned)(need - c))));
+      __nanosleep(min(8u * far_sleep, max(far_sleep, per_signal * (unsigned)(need - c))));
       c = ld_relaxed(cnt);
       if (c >= need)
       {
@@ -322,7 +322,9 @@ constexpr int FLOW_TICKET_PITCH = 32; // ints between two counters
 struct FlowSched
 {
   int ntasks;
-  int far_sleep; // poll interval while no producer has signalled yet (ns)
+  int far_sleep; // shortest nap of a consumer that is far from ready (ns)
+  int near;      // tight polls once at most this many signals are missing
+  int per_signal; // nap per missing signal (ns)
 };
 
 // flow_take_issue only issues the atomic of the warp's current shard (its result stays in lane 0);
@@ -381,6 +383,8 @@ flow_task(const SweepTask& T,
           double* vsh,
           const FlowTrace* trace,
           unsigned far_sleep,
+          int near,
+          unsigned per_signal,
           FlowPhases& ph)
 {
   long long c0 = 0, c1 = 0, c2 = 0;
@@ -448,7 +452,7 @@ flow_task(const SweepTask& T,
   }
   if (T.wait_idx >= 0)
   {
-    wait_counter(cnt + T.wait_idx, T.need, far_sleep);
+    wait_counter(cnt + T.wait_idx, T.need, far_sleep, near, per_signal);
   }
   if (TRACE)
   {
@@ -543,7 +547,7 @@ k_flow(const SweepTask* __restrict__ tasks,
     {
       ph.fetch += clk_after((double)T.h) - cf;
     }
-    flow_task<FWD, TRACE>(T, lane, Ridx, M, Dinv, yacc, yf, x, cnt, vsh, trace, (unsigned)sched.far_sleep, ph);
+    flow_task<FWD, TRACE>(T, lane, Ridx, M, Dinv, yacc, yf, x, cnt, vsh, trace, (unsigned)sched.far_sleep, sched.near, (unsigned)sched.per_signal, ph);
     if (TRACE)
     {
       cf = clk_after(0.0);
@@ -815,6 +819,7 @@ namespace
 {
 int g_sms        = 148;
 int g_flow_sleep = 512;              // B200_FLOW_SLEEP: poll interval of far-away consumers (ns)
+int g_flow_near = FLOW_NEAR, g_flow_per_signal = 4; // B200_FLOW_NEAR, B200_FLOW_PER_SIGNAL (experiments)
 int g_flow_ctas  = FLOW_CTAS_PER_SM; // B200_FLOW_CTAS: fewer resident CTAs per SM (experiments)
 } // namespace
 
@@ -845,8 +850,8 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
       const long long ctas = ((long long)ntasks + 4 * FLOW_SHARDS - 1) / (4 * FLOW_SHARDS);
       return (unsigned)std::max<long long>(1, std::min<long long>(max_ctas, ctas));
     };
-    const FlowSched fs{(int)P.ffl_tasks.size(), g_flow_sleep};
-    const FlowSched bs{(int)P.bfl_tasks.size(), g_flow_sleep};
+    const FlowSched fs{(int)P.ffl_tasks.size(), g_flow_sleep, g_flow_near, g_flow_per_signal};
+    const FlowSched bs{(int)P.bfl_tasks.size(), g_flow_sleep, g_flow_near, g_flow_per_signal};
     int* const tickets_f = sb.flow + 2 * ns;
     int* const tickets_b = tickets_f + FLOW_SHARDS * FLOW_TICKET_PITCH;
     auto kf = sb.trace_fwd ? k_flow<true, true> : k_flow<true, false>;
@@ -897,6 +902,14 @@ configure_solve_kernels()
       if (const char* fc = std::getenv("B200_FLOW_CTAS"))
       {
         g_flow_ctas = std::min(FLOW_CTAS_PER_SM, std::max(1, std::atoi(fc)));
+      }
+      if (const char* fn = std::getenv("B200_FLOW_NEAR"))
+      {
+        g_flow_near = std::max(0, std::atoi(fn));
+      }
+      if (const char* fp = std::getenv("B200_FLOW_PER_SIGNAL"))
+      {
+        g_flow_per_signal = std::max(0, std::atoi(fp));
       }
       if (const char* fs = std::getenv("B200_FLOW_SLEEP"))
       {
