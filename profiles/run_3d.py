@@ -35,4 +35,8 @@ for g in [int(a) for a in sys.argv[1:]] or [48]:
           f"numeric={st['ms_numeric']:.1f}ms ({gf / st['ms_numeric']:.1f} TF/s on {gf:.0f} GF) solve={st['ms_solve']:.2f}ms residuals={res} refine={st['refine_steps']}")
     print("  numeric by class (ms):", {k: round(x, 2) for k, x in prof.items()}, " update DMMA rate:", round(gf / max(prof['update'], 1e-9), 2), "TF/s")
     print("  solve phases (ms):", ph.round(3).tolist())
+    # sweeps against the HBM roofline (algorithmic bytes as in bench.py: exact nnz(L), row indices, vectors)
+    sweep_bytes = 8 * st["nnz_L"] + 4 * st["n_row_idx"] + 16 * st["n_reduced"]
+    for name, ms in (("forward", ph[1]), ("backward", ph[2])):
+        print(f"  {name} sweep: {sweep_bytes / 1e6:.0f} MB in {ms * 1e3:.0f} us = {sweep_bytes / ms / 1e6:.0f} GB/s = {100 * sweep_bytes / ms / 1e6 / 6545.6:.1f} % of the measured HBM peak (6545.6 GB/s)")
     f.release()

@@ -1217,6 +1217,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       }
       P.Sdiag[j] = P.Sdest[Sptr[j]];
     }
+    tick("  assembly: destinations");
     auto entry_id = [&](int row, int col) -> i64 {
       const int* b  = Srow.data() + Sptr[col];
       const int* e  = Srow.data() + Sptr[col + 1];
@@ -1234,52 +1235,92 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       }
       P.Sgsrc[id] = g.src;
     }
-    // product terms, two passes
-    P.Sterm_ptr.assign((size_t)P.nnzS + 1, 0);
-    std::vector<i64> term_ids; // entry id of every product term, computed once in pass 0
-    for (int pass = 0; pass < 2; ++pass)
+    // product terms. The entry of S every term belongs to is found by binary search in the column of S: that is
+    // the expensive part (c (c + 1) / 2 terms per eliminated variable with c entries) and independent per variable,
+    // so it runs on a few host threads; counting and filling are cheap linear passes.
+    std::vector<i64> tptr((size_t)nE + 1, 0);
+    for (int e = 0; e < nE; ++e)
     {
-      std::vector<i64> fill;
-      size_t tq = 0;
-      if (pass == 1)
-      {
-        for (i64 q = 0; q < P.nnzS; ++q)
+      const i64 c = P.Acsc_ptr[e + 1] - P.Acsc_ptr[e];
+      tptr[e + 1] = tptr[e] + c * (c + 1) / 2;
+    }
+    std::vector<i64> term_ids((size_t)tptr[nE]); // entry id of every product term, in (e, s, t) order
+    {
+      std::atomic<bool> missing{false};
+      auto search = [&](int e0, int e1) {
+        for (int e = e0; e < e1; ++e)
         {
-          P.Sterm_ptr[q + 1] += P.Sterm_ptr[q];
+          i64 o = tptr[e];
+          for (int s = P.Acsc_ptr[e]; s < P.Acsc_ptr[e + 1]; ++s)
+          {
+            const int a = P.pinv[P.Acsc_row[s]];
+            for (int t = P.Acsc_ptr[e]; t <= s; ++t)
+            {
+              const int b  = P.pinv[P.Acsc_row[t]];
+              const i64 id = entry_id(std::max(a, b), std::min(a, b));
+              if (id < 0)
+              {
+                missing = true;
+              }
+              term_ids[(size_t)o++] = id;
+            }
+          }
         }
-        const size_t nt = (size_t)P.Sterm_ptr[P.nnzS];
-        P.Sterm_a.resize(nt);
-        P.Sterm_b.resize(nt);
-        P.Sterm_d.resize(nt);
-        fill.assign(P.Sterm_ptr.begin(), P.Sterm_ptr.end() - 1);
+      };
+      const unsigned hw = std::thread::hardware_concurrency();
+      const int nth     = tptr[nE] < 200000 ? 1 : (int)std::min<unsigned>(8, std::max<unsigned>(1, hw));
+      if (nth == 1)
+      {
+        search(0, nE);
       }
+      else
+      {
+        std::vector<std::thread> pool;
+        for (int th = 0; th < nth; ++th)
+        {
+          // equal shares of the terms, not of the variables
+          const i64 lo = tptr[nE] * th / nth, hi = tptr[nE] * (th + 1) / nth;
+          const int e0 = (int)(std::lower_bound(tptr.begin(), tptr.end(), lo) - tptr.begin());
+          const int e1 = th + 1 == nth ? nE : (int)(std::lower_bound(tptr.begin(), tptr.end(), hi) - tptr.begin());
+          pool.emplace_back(search, std::min(e0, nE), std::min(e1, nE));
+        }
+        for (auto& th : pool)
+        {
+          th.join();
+        }
+      }
+      if (missing)
+      {
+        return fail(err, B200_ERR_ARG, "internal: product term missing from the S pattern");
+      }
+    }
+    tick("  assembly: term search");
+    P.Sterm_ptr.assign((size_t)P.nnzS + 1, 0);
+    for (i64 id : term_ids)
+    {
+      ++P.Sterm_ptr[(size_t)id + 1];
+    }
+    for (i64 q = 0; q < P.nnzS; ++q)
+    {
+      P.Sterm_ptr[q + 1] += P.Sterm_ptr[q];
+    }
+    {
+      const size_t nt = (size_t)P.Sterm_ptr[P.nnzS];
+      P.Sterm_a.resize(nt);
+      P.Sterm_b.resize(nt);
+      P.Sterm_d.resize(nt);
+      std::vector<i64> fill(P.Sterm_ptr.begin(), P.Sterm_ptr.end() - 1);
+      size_t tq = 0;
       for (int e = 0; e < nE; ++e)
       {
         for (int s = P.Acsc_ptr[e]; s < P.Acsc_ptr[e + 1]; ++s)
         {
-          int a = P.pinv[P.Acsc_row[s]];
           for (int t = P.Acsc_ptr[e]; t <= s; ++t)
           {
-            i64 id;
-            if (pass == 0)
-            {
-              const int b = P.pinv[P.Acsc_row[t]];
-              id          = entry_id(std::max(a, b), std::min(a, b));
-              if (id < 0)
-              {
-                return fail(err, B200_ERR_ARG, "internal: product term missing from the S pattern");
-              }
-              term_ids.push_back(id);
-              ++P.Sterm_ptr[id + 1];
-            }
-            else
-            {
-              id = term_ids[tq++];
-              i64 o        = fill[id]++;
-              P.Sterm_a[o] = P.Acsc_src[s];
-              P.Sterm_b[o] = P.Acsc_src[t];
-              P.Sterm_d[o] = P.dE_src[e];
-            }
+            const i64 o  = fill[(size_t)term_ids[tq++]]++;
+            P.Sterm_a[o] = P.Acsc_src[s];
+            P.Sterm_b[o] = P.Acsc_src[t];
+            P.Sterm_d[o] = P.dE_src[e];
           }
         }
       }
