@@ -3,7 +3,9 @@
 #include "numeric.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -409,18 +411,35 @@ b200_fact_set_matrix(b200_fact* F, int n_rows, int n_cols, int nnz, const int* c
   return guarded([&]() {
     B200_CUDA(cudaSetDevice(F->device));
     F->factored = F->solved = false;
+    // B200_TIMING=1: wall-clock of the host-side phases of this call on stderr
+    static const bool timing = std::getenv("B200_TIMING") != nullptr;
+    auto t_last              = std::chrono::steady_clock::now();
+    auto lap                 = [&](const char* what) {
+      if (timing)
+      {
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[b200 set_matrix] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+      }
+    };
+    // the values go to the device while the host hashes the pattern and looks the plan up
+    if (nnz < 0 || (nnz > 0 && !val))
+    {
+      return set_error(B200_ERR_ARG, "malformed CSC values");
+    }
+    F->val.reserve((size_t)nnz + 8);
+    B200_CUDA(cudaEventRecord(F->ev_a, F->stream));
+    if (nnz > 0)
+    {
+      B200_CUDA(cudaMemcpyAsync(F->val.p, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, F->stream));
+    }
     std::shared_ptr<const Plan> plan;
     bool cached = false;
     int rc      = get_plan(n_rows, nnz, colptr, rowidx, val, lower_only, plan, cached);
+    lap("pattern hash + plan lookup");
     if (rc != B200_OK)
     {
       return rc;
-    }
-    if ((size_t)plan->max_front * sizeof(double) > 160 * 1024)
-    {
-      return set_error(B200_ERR_UNSUPPORTED,
-                       "largest front has " + std::to_string(plan->max_front) +
-                         " rows; the backward sweep stages one front vector in shared memory (limit 20480 rows)");
     }
     F->symbolic_cached = cached;
     F->ms_symbolic     = cached ? 0.0 : plan->ms_symbolic;
@@ -436,12 +455,6 @@ b200_fact_set_matrix(b200_fact* F, int n_rows, int n_cols, int nnz, const int* c
       F->rcond    = 1.0;
       return (int)B200_OK;
     }
-    F->val.reserve((size_t)nnz + 8);
-    B200_CUDA(cudaEventRecord(F->ev_a, F->stream));
-    if (nnz > 0)
-    {
-      B200_CUDA(cudaMemcpyAsync(F->val.p, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, F->stream));
-    }
     {
       const NumericBuffers nb = F->nbuf();
       run_graph(F, F->g_numeric, [&](LaunchCounter& lc) {
@@ -451,6 +464,7 @@ b200_fact_set_matrix(b200_fact* F, int n_rows, int n_cols, int nnz, const int* c
     }
     B200_CUDA(cudaEventRecord(F->ev_b, F->stream));
     F->timed_numeric = true;
+    lap("enqueue copy + numeric graph");
     // pivot range and perturbation count
     B200_CUDA(cudaMemcpyAsync(F->h_scal.p, F->scal.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, F->stream));
     B200_CUDA(cudaMemcpyAsync(F->h_nper.p, F->nper.p, sizeof(int), cudaMemcpyDeviceToHost, F->stream));
@@ -458,6 +472,7 @@ b200_fact_set_matrix(b200_fact* F, int n_rows, int n_cols, int nnz, const int* c
     const double dmin = F->h_scal.p[2], dmax = F->h_scal.p[3];
     F->rcond       = (dmax > 0.0 && std::isfinite(dmax) && std::isfinite(dmin)) ? dmin / dmax : 0.0;
     F->n_perturbed = P.m > 0 ? F->h_nper.p[0] : 0;
+    lap("numeric factorization (wait)");
 
     // probe solve: choose the number of refinement steps every solve of this factor performs
     const NumericBuffers nb = F->nbuf();
@@ -487,6 +502,7 @@ b200_fact_set_matrix(b200_fact* F, int n_rows, int n_cols, int nnz, const int* c
     }
     F->refine    = refine;
     F->probe_res = best;
+    lap("probe solve(s) + residual");
     if (!(best <= 1e-6))
     {
       return set_error(B200_ERR_SINGULAR,

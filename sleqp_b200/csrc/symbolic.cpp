@@ -74,32 +74,62 @@ hash_words(uint64_t seed, const void* data, size_t bytes)
 uint64_t
 hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only)
 {
-  int hdr[4] = {n, nnz, lower_only ? 1 : 0, 0};
-  uint64_t h = hash_words(0x5EED, hdr, sizeof(hdr));
-  h          = hash_words(h, colptr, sizeof(int) * (size_t)(n + 1));
-  h          = hash_words(h, rowidx, sizeof(int) * (size_t)nnz);
-  // the E/R classification depends on which diagonals are non-zero: part of the key
-  uint64_t bits = 0, hb = h;
-  for (int j = 0; j < n; ++j)
-  {
-    int p         = colptr[j];
-    const int end = colptr[j + 1];
-    if (!lower_only)
+  // On the critical path of every set_matrix (the plan is looked up by this key before anything can be launched):
+  // large patterns are hashed in four independent slices on host threads, the slice hashes are chained in order.
+  constexpr int SLICES = 4;
+  const int nsl        = (long long)n + nnz >= 400000 ? SLICES : 1;
+  uint64_t part[SLICES] = {0, 0, 0, 0};
+  auto slice = [&](int sl) {
+    const int j0 = (int)((long long)n * sl / nsl), j1 = (int)((long long)n * (sl + 1) / nsl);
+    uint64_t h = hash_words(0x5EED + sl, colptr + j0, sizeof(int) * (size_t)(j1 - j0 + 1));
+    h          = hash_words(h, rowidx + colptr[j0], sizeof(int) * (size_t)(colptr[j1] - colptr[j0]));
+    // the E/R classification depends on which diagonals are non-zero: part of the key
+    uint64_t bits = 0;
+    for (int j = j0; j < j1; ++j)
     {
-      while (p < end && rowidx[p] < j)
+      int p         = colptr[j];
+      const int end = colptr[j + 1];
+      if (!lower_only)
       {
-        ++p;
+        while (p < end && rowidx[p] < j)
+        {
+          ++p;
+        }
+      }
+      const uint64_t nz = (p < end && rowidx[p] == j && val[p] != 0.) ? 1u : 0u;
+      bits              = (bits << 1) | nz;
+      if (((j - j0) & 63) == 63)
+      {
+        h    = mix64(h, bits);
+        bits = 0;
       }
     }
-    const uint64_t nz = (p < end && rowidx[p] == j && val[p] != 0.) ? 1u : 0u;
-    bits              = (bits << 1) | nz;
-    if ((j & 63) == 63)
+    part[sl] = mix64(h, bits ^ 0xD1A6);
+  };
+  if (nsl == 1)
+  {
+    slice(0);
+  }
+  else
+  {
+    std::thread pool[SLICES - 1];
+    for (int sl = 1; sl < nsl; ++sl)
     {
-      hb   = mix64(hb, bits);
-      bits = 0;
+      pool[sl - 1] = std::thread(slice, sl);
+    }
+    slice(0);
+    for (int sl = 1; sl < nsl; ++sl)
+    {
+      pool[sl - 1].join();
     }
   }
-  return mix64(hb, bits ^ 0xD1A6);
+  int hdr[4] = {n, nnz, lower_only ? 1 : 0, nsl};
+  uint64_t h = hash_words(0x5EED, hdr, sizeof(hdr));
+  for (int sl = 0; sl < nsl; ++sl)
+  {
+    h = mix64(h, part[sl]);
+  }
+  return h;
 }
 
 // ---------------------------------------------------------------------------------------
