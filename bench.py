@@ -206,7 +206,7 @@ def run_reference(args, rank, world):
     value = 1e3 / ms
     sample = (f"per step: 1 SuperLU factorization + {n_solve_sample} of {len(rhs)} solves (scaled x{len(rhs)}/{n_solve_sample}) + 1 of {k} Hessian SpMV "
               f"(scaled x{k}) + 1 J^T + 1 J SpMV; SpMV = reference sleqp_mat_mult_vec{'/_trans (oracle/_ref)' if ref is not None else ' (numpy port)'}; "
-              "factor/solve = SciPy SuperLU stand-in for the absent Umfpack")
+              "factor/solve = SciPy SuperLU stand-in for the absent Umfpack (sequential code; `cores` = the threads its BLAS calls may use)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(tot), "warmup": (n_warm + 1 if args.warmup else 0),
         "steps_requested": args.steps, "warmup_requested": args.warmup,
