@@ -117,7 +117,10 @@ B200_API int b200_fact_solution(b200_fact* handle, int begin, int end, double* o
 B200_API int b200_fact_solution_ptr(b200_fact* handle, int begin, int end, const double** out);
 
 /* The slice as a sparse vector, exactly what sleqp_vec_set_from_raw (sparse/vec.c:72-104) would build from it:
- * entries with |v| > zero_eps, ascending. idx_out / val_out must hold end-begin entries. */
+ * entries with |v| > zero_eps, ascending. idx_out / val_out must hold end-begin entries (the contents behind the
+ * first *nnz_out entries are unspecified). When both buffers are page-locked (b200_host_pin, cudaHostAlloc, ...)
+ * the slice is sparsified on the device and copied straight into them; otherwise it goes through the handle's
+ * pinned staging buffer and a host pass. */
 B200_API int b200_fact_solution_sparse(b200_fact* handle, int begin, int end, double zero_eps, int* idx_out, double* val_out, int* nnz_out);
 
 /* Device-resident variants used by the benchmark's "inputs already in HBM" leg and by a
