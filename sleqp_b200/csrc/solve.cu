@@ -273,11 +273,12 @@ ld_relaxed(const int* p)
   return v;
 }
 
-// a release is all the counter hand-over needs: __threadfence() is fence.sc (MEMBAR.SC)
+// a release is all the producer side of the counter hand-over needs: __threadfence() is fence.sc (MEMBAR.SC), and
+// fence.acq_rel also invalidates the SM's L1 (CCTL.IVALL) for its acquire half
 __device__ __forceinline__ void
-fence_acq_rel()
+fence_release()
 {
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  asm volatile("fence.release.gpu;" ::: "memory");
 }
 
 // All lanes poll the same word (one request per poll). While many producers are still missing the consumer is far
@@ -560,7 +561,7 @@ k_flow(const SweepTask* __restrict__ tasks,
     int issued          = (open && !critical) ? flow_take_issue(ticket, lane, shard) : 0;
     if (T.signal_idx >= 0)
     {
-      fence_acq_rel(); // every lane: its own atomics are visible device-wide before the counter moves
+      fence_release(); // every lane: its own atomics are visible device-wide before the counter moves
       __syncwarp();
       if (lane == 0)
       {
