@@ -11,6 +11,7 @@
 // a few fused vector kernels on the factorization's stream, and only three scalars cross PCIe.
 #include "cg.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -56,6 +57,31 @@ k_axpby(int n, double a, const double* x, double b, const double* y, double* out
   }
 }
 
+// out = a * x + (*b) * y with the second coefficient in device memory (out may alias x or y)
+__global__ void
+k_axpby_dev(int n, double a, const double* x, const double* __restrict__ b, const double* y, double* out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+  {
+    out[i] = a * x[i] + (*b) * y[i];
+  }
+}
+
+// the scalars of one CG iteration stay on the device (layout: see b200_cg_solve)
+__global__ void
+k_cg_alpha(double* S)
+{
+  S[10] = S[9] / S[0]; // alpha = r.g / d.Bd                            (steihaug_solver.c:405)
+}
+
+__global__ void
+k_cg_beta(double* S)
+{
+  S[11] = S[6] / S[9]; // beta = (r.g)_new / (r.g)_old                   (:467-469)
+  S[9]  = S[6];
+}
+
 } // namespace b200
 
 struct b200_cg
@@ -65,7 +91,7 @@ struct b200_cg
   int device      = 0;
   cudaStream_t stream = nullptr;
   int n = 0, N = 0;
-  DevBuf<double> z, znext, rfull, gfull, d, Bd, scal;
+  DevBuf<double> z, znext, rfull, gfull, d, dnext, Bd, scal;
   DevBuf<int> g_idx;
   DevBuf<double> g_val;
   PinnedBuf<double> h_scal, h_step, h_val;
@@ -146,8 +172,8 @@ b200_cg_create(b200_cg** handle, b200_fact* fact, b200_mat* hess)
     {
       return rc;
     }
-    C->scal.reserve(8);
-    C->h_scal.reserve(8);
+    C->scal.reserve(16);
+    C->h_scal.reserve(16);
     *handle = C.release();
     return (int)B200_OK;
   });
@@ -188,6 +214,7 @@ b200_cg_solve(b200_cg* C,
     C->z.reserve((size_t)n);
     C->znext.reserve((size_t)n);
     C->d.reserve((size_t)n);
+    C->dnext.reserve((size_t)n);
     C->Bd.reserve((size_t)n);
     C->rfull.reserve((size_t)N); // [r; 0]: the right-hand side of the projection, tail stays zero
     C->gfull.reserve((size_t)N); // K^-1 [r; 0]: its first n entries are g = P r
@@ -250,6 +277,27 @@ b200_cg_solve(b200_cg* C,
     {
       return finish(C->z.p, 0, B200_CG_INTERIOR);
     }
+    // One host synchronisation per iteration. The scalars of the recurrences stay on the device:
+    //   S[0..2] = (d.Bd, d.d, Bd.Bd)   S[3..5] = (z+.d, z+.z+, d.d)   S[6..8] = (r.g, r.r, g.g) after the update
+    //   S[9] = current r.g   S[10] = alpha   S[11] = beta
+    // so the whole iteration -- SpMV, step, residual update, projection, new direction -- is enqueued without
+    // waiting for the host, which then reads S[0..8] once and checks the three exits in the reference's order. The
+    // iterate and the direction are double-buffered: what an exit needs (z, d, Bd of the iteration) is still intact
+    // although the work after the exit test has already run (and is discarded).
+    double* S = C->scal.p;
+    B200_CUDA(cudaMemcpyAsync(S + 9, C->h_scal.p, sizeof(double), cudaMemcpyHostToDevice, s)); // h_scal[0] = r.g (dot3 above)
+    double* z_cur = C->z.p;
+    double* z_new = C->znext.p;
+    double* d_cur = C->d.p;
+    double* d_new = C->dnext.p;
+    auto dot3_async = [&](const double* a, const double* b, double* out) {
+      k_dot3<<<std::min(nb(n), 592u), 256, 0, s>>>(n, a, b, out);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    };
+    auto axpby_dev = [&](double a, const double* xx, const double* bdev, const double* yy, double* out) {
+      k_axpby_dev<<<nb(n), 256, 0, s>>>(n, a, xx, bdev, yy, out);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+    };
     double z_nrm_sq = 0.0;
     for (int it = 0;; ++it)
     {
@@ -259,69 +307,72 @@ b200_cg_solve(b200_cg* C,
       }
       if (std::fabs(r_dot_g) < tol_sq) //                                     (:318-327)
       {
-        return finish(C->z.p, it, B200_CG_INTERIOR);
+        return finish(z_cur, it, B200_CG_INTERIOR);
       }
-      int hrc = b200_mat_mult_vec_device(C->hess, C->d.p, C->Bd.p); //       (:339)
+      B200_CUDA(cudaMemsetAsync(S, 0, 9 * sizeof(double), s));
+      int hrc = b200_mat_mult_vec_device(C->hess, d_cur, C->Bd.p); //          (:339)
       if (hrc != B200_OK)
       {
         return hrc;
       }
-      dot3(C, C->d.p, C->Bd.p, sc); // d.Bd, d.d, Bd.Bd
-      const double dBd = sc[0], d_nrm_sq = sc[1];
+      dot3_async(d_cur, C->Bd.p, S); // d.Bd, d.d, Bd.Bd
+      k_cg_alpha<<<1, 1, 0, s>>>(S);
+      axpby_dev(1.0, z_cur, S + 10, d_cur, z_new); // z+ = z + alpha d
+      dot3_async(z_new, d_cur, S + 3);             // z+.d, z+.z+
+      axpby_dev(1.0, r, S + 10, C->Bd.p, r);       // r += alpha B d           (:449-456)
+      prc = project();                             // g = P[r]                  (:459)
+      if (prc != B200_OK)
+      {
+        return prc;
+      }
+      dot3_async(r, g, S + 6);
+      k_cg_beta<<<1, 1, 0, s>>>(S);
+      axpby_dev(-1.0, g, S + 11, d_cur, d_new); // d+ = -g + beta d           (:472-479)
+      g_launches.fetch_add(2, std::memory_order_relaxed);
+      B200_CUDA(cudaMemcpyAsync(C->h_scal.p, S, 9 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+      const double dBd = C->h_scal.p[0], d_nrm_sq = C->h_scal.p[1];
+      const double z_next_nrm_sq = C->h_scal.p[4], r_dot_g_new = C->h_scal.p[6];
       if (dBd <= 0.0) // negative curvature                                  (:349-402)
       {
         double zs[3];
-        dot3(C, C->z.p, C->d.p, zs); // z.d
+        dot3(C, z_cur, d_cur, zs); // z.d
         const double z_dot_d = zs[0];
         const double inner   = z_dot_d * z_dot_d - d_nrm_sq * (z_nrm_sq - trust_radius * trust_radius);
         const double tau_min = 1. / d_nrm_sq * (-z_dot_d - std::sqrt(inner));
         const double tau_max = 1. / d_nrm_sq * (-z_dot_d + std::sqrt(inner));
         double gs[3], zb[3];
-        // gradient . d: the gradient is r0, which we no longer hold once r was updated; recompute from the
-        // identity g^T d = (r - H z)^T d is avoided by keeping the original sparse gradient on the device
-        B200_CUDA(cudaMemsetAsync(C->znext.p, 0, sizeof(double) * (size_t)n, s));
+        // gradient . d with the original sparse gradient (kept on the device)
+        B200_CUDA(cudaMemsetAsync(z_new, 0, sizeof(double) * (size_t)n, s));
         if (nnz_g > 0)
         {
           LaunchCounter lc;
-          enqueue_scatter_rhs(C->znext.p, n, nnz_g, C->g_idx.p, 0, C->g_val.p, s, lc);
+          enqueue_scatter_rhs(z_new, n, nnz_g, C->g_idx.p, 0, C->g_val.p, s, lc);
         }
-        dot3(C, C->znext.p, C->d.p, gs);
-        dot3(C, C->z.p, C->Bd.p, zb);
+        dot3(C, z_new, d_cur, gs);
+        dot3(C, z_cur, C->Bd.p, zb);
         const double gd = gs[0], zBd = zb[0];
         const double tau_min_obj = tau_min * ((gd + zBd) + 0.5 * tau_min * dBd);
         const double tau_max_obj = tau_max * ((gd + zBd) + 0.5 * tau_max * dBd);
         const double tau         = (tau_min_obj < tau_max_obj) ? tau_min : tau_max;
-        axpby(C, 1.0, C->z.p, tau, C->d.p, C->znext.p);
-        return finish(C->znext.p, it, B200_CG_NEG_CURVATURE);
+        axpby(C, 1.0, z_cur, tau, d_cur, z_new);
+        return finish(z_new, it, B200_CG_NEG_CURVATURE);
       }
-      const double alpha = r_dot_g / dBd; //                                 (:405)
-      axpby(C, 1.0, C->z.p, alpha, C->d.p, C->znext.p);
-      double zn[3];
-      dot3(C, C->znext.p, C->d.p, zn); // znext.d, znext.znext
-      const double z_next_nrm_sq = zn[1];
       if (z_next_nrm_sq >= trust_radius * trust_radius) // boundary       (:419-441, tr_util.c:9-50)
       {
         double zs[3];
-        dot3(C, C->z.p, C->d.p, zs);
+        dot3(C, z_cur, d_cur, zs);
         const double prev_dot_d = zs[0];
         const double p_norm = std::sqrt(zs[1]), d_norm = std::sqrt(zs[2]);
         const double inner  = prev_dot_d * prev_dot_d - d_norm * d_norm * (p_norm * p_norm - trust_radius * trust_radius);
         const double factor = 1. / (d_norm * d_norm) * (-prev_dot_d + std::sqrt(inner));
-        axpby(C, 1.0, C->z.p, factor, C->d.p, C->znext.p);
-        return finish(C->znext.p, it, B200_CG_BOUNDARY);
+        axpby(C, 1.0, z_cur, factor, d_cur, z_new);
+        return finish(z_new, it, B200_CG_BOUNDARY);
       }
-      B200_CUDA(cudaMemcpyAsync(C->z.p, C->znext.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+      std::swap(z_cur, z_new);
+      std::swap(d_cur, d_new);
       z_nrm_sq = z_next_nrm_sq;
-      axpby(C, 1.0, r, alpha, C->Bd.p, r); // r += alpha B d                (:449-456)
-      prc = project();                     // g = P[r]                      (:459)
-      if (prc != B200_OK)
-      {
-        return prc;
-      }
-      dot3(C, r, g, sc);
-      const double beta = sc[0] / r_dot_g; //                                (:467-469)
-      r_dot_g           = sc[0];
-      axpby(C, -1.0, g, beta, C->d.p, C->d.p); // d = -g + beta d           (:472-479)
+      r_dot_g  = r_dot_g_new;
     }
   });
 }
