@@ -8,7 +8,8 @@
 // reference leaves the step at zero, steihaug_solver.c:302-305). What changes is where the data lives:
 // the reference pays, per iteration, a sparse-vector round trip through the SleqpFact boundary (H2D
 // right-hand side, D2H solution, host sparsification); here one iteration is 1 SpMV + 1 KKT solve +
-// a few fused vector kernels on the factorization's stream, and only three scalars cross PCIe.
+// a few fused vector kernels on the factorization's stream; the scalars of the recurrences stay on the
+// device and the host reads nine of them once per iteration to check the exits.
 #include "cg.cuh"
 
 #include <algorithm>
