@@ -179,7 +179,7 @@ class Emulated:
         tasks = p["ffl_tasks"]
         for t in range(len(tasks)):
             lptr, rptr, first, k, h, i0, i1, j0, j1, wait_idx, need, signal_idx = fields(tasks[t])
-            assert 0 < i1 - i0 <= 32 and 0 < j1 - j0 <= 32 and i1 <= h and j1 <= k
+            assert 0 < i1 - i0 <= 32 and 0 < j1 - j0 <= 128 and i1 <= h and j1 <= k
             if wait_idx >= 0:
                 assert cnt[wait_idx] == need, "forward task claimed before its producers"
             b = yacc[first + j0 : first + j1]
@@ -195,7 +195,7 @@ class Emulated:
         tasks = p["bfl_tasks"]
         for t in range(len(tasks)):
             lptr, rptr, first, k, h, i0, i1, j0, j1, wait_idx, need, signal_idx = fields(tasks[t])
-            assert 0 < j1 - j0 <= 32 and j0 % 32 == 0 and 0 < i1 - i0 <= 32 and i0 % 16 == 0 and j1 <= k and i1 <= h
+            assert 0 < j1 - j0 <= 32 and j0 % 32 == 0 and 0 < i1 - i0 <= 128 and i0 % 16 == 0 and j1 <= k and i1 <= h
             if wait_idx >= 0:
                 assert cnt[wait_idx] == need, "backward task claimed before its producers"
             else:

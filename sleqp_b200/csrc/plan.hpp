@@ -25,6 +25,7 @@ constexpr int NBO      = 128; // outer block: columns beyond it are updated once
 constexpr int EA_COLS  = 4;   // update-matrix columns per extend-add task (one warp each)
 constexpr int FLOW_THREADS     = 256; // dataflow sweep kernels: persistent CTAs of 8 warps,
 constexpr int FLOW_CTAS_PER_SM = 4;   // four per SM (64 registers per thread)
+constexpr int FLOW_DEEP        = 128; // depth of a sweep task in the levels that are bandwidth-bound (symbolic.cpp, solve.cu)
 constexpr int LEAF_MAX = 32;  // etree subtrees up to this many columns become one dense supernode
 
 // kinds of update tasks

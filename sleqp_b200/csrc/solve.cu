@@ -364,7 +364,123 @@ flow_take_finish(int issued, int* __restrict__ ticket, int ntasks, int lane, int
 }
 
 constexpr int FLOW_DEPTH     = 16; // panel entries in flight per lane = one batch of loads
-constexpr int FLOW_MAX_DEPTH = 32; // depth of a task: one batch in the narrow levels, two in the wide ones (symbolic.cpp)
+constexpr int FLOW_MAX_DEPTH = FLOW_DEEP; // depth of a task: one batch in the narrow levels, two in the wide ones, a
+                                          // rolling window over FLOW_DEEP entries in the bandwidth-bound ones (symbolic.cpp)
+
+// A task of the bandwidth-bound levels (depth > 32, large 3D fronts): same contract as flow_task below, but the panel
+// is streamed with a rolling window -- the load of entry u of the next batch is issued as soon as entry u of this
+// batch has been consumed, so FLOW_DEPTH loads per lane stay in flight over the whole depth -- and the fixed cost of a
+// task (record, vector, publication, ticket) is amortised over four times as much data. Not inlined: its register
+// needs must not disturb the allocation of the latency-bound path.
+template <bool FWD>
+__device__ __noinline__ void
+flow_task_deep(const SweepTask& T,
+               int lane,
+               const int* __restrict__ Ridx,
+               const double* __restrict__ M,
+               const double* __restrict__ Dinv,
+               double* __restrict__ yacc,
+               double* __restrict__ yf,
+               double* __restrict__ x,
+               const int* __restrict__ cnt,
+               double* vsh,
+               unsigned far_sleep,
+               int near,
+               unsigned per_signal)
+{
+  const int k = T.k, h = T.h;
+  const int ld    = FWD ? h : k;
+  const int o     = (FWD ? T.i0 : T.j0) + lane;
+  const bool ov   = o < (FWD ? T.i1 : T.j1);
+  const int d0    = FWD ? T.j0 : T.i0;
+  const int nd    = (FWD ? T.j1 : T.i1) - d0; // > 32
+  const double* P = M + T.Lptr + (long long)d0 * ld + (ov ? o : (FWD ? T.i0 : T.j0));
+  double pre[FLOW_DEPTH];
+#pragma unroll
+  for (int u = 0; u < FLOW_DEPTH; ++u)
+  {
+    pre[u] = ov ? __ldcs(P + (long long)u * ld) : 0.0;
+  }
+  double* dst  = nullptr;
+  double scale = 1.0;
+  if (ov)
+  {
+    if (FWD)
+    {
+      if (o < k)
+      {
+        dst   = yf + T.first + o;
+        scale = Dinv[T.first + o];
+      }
+      else
+      {
+        dst = yacc + Ridx[T.Rptr + o - k];
+      }
+    }
+    else
+    {
+      dst = x + T.first + o;
+    }
+  }
+  // backward: the row indices behind this lane's share of the vector do not depend on the producers
+  int ri[FLOW_DEEP / 32];
+  if (!FWD)
+  {
+#pragma unroll
+    for (int q = 0; q < FLOW_DEEP / 32; ++q)
+    {
+      const int d = d0 + lane + 32 * q;
+      ri[q]       = (lane + 32 * q < nd && d >= k) ? Ridx[T.Rptr + d - k] : -1;
+    }
+  }
+  if (T.wait_idx >= 0)
+  {
+    wait_counter(cnt + T.wait_idx, T.need, far_sleep, near, per_signal);
+  }
+  __syncwarp(); // the previous task's reads of vsh are done
+#pragma unroll
+  for (int q = 0; q < FLOW_DEEP / 32; ++q)
+  {
+    const int dd = lane + 32 * q;
+    double v     = 0.0;
+    if (dd < nd)
+    {
+      if (FWD)
+      {
+        v = __ldcg(yacc + T.first + d0 + dd);
+      }
+      else
+      {
+        v = ri[q] < 0 ? yf[T.first + d0 + dd] : __ldcg(x + ri[q]);
+      }
+    }
+    vsh[dd] = v;
+  }
+  __syncwarp();
+  double acc0 = 0.0, acc1 = 0.0;
+  const double* vb = vsh;
+  int rem          = nd;
+  int ldv          = ld;
+  do
+  {
+    rem -= FLOW_DEPTH;
+    P += (long long)FLOW_DEPTH * ld;
+    asm volatile("" : "+r"(ldv)); // one multiply-add per address instead of a hoisted table of sixteen 64-bit offsets
+#pragma unroll
+    for (int u = 0; u < FLOW_DEPTH; u += 2)
+    {
+      acc0 += pre[u] * vb[u];
+      pre[u] = (ov && u < rem) ? __ldcs(P + (long long)u * ldv) : 0.0;
+      acc1 += pre[u + 1] * vb[u + 1];
+      pre[u + 1] = (ov && u + 1 < rem) ? __ldcs(P + (long long)(u + 1) * ldv) : 0.0;
+    }
+    vb += FLOW_DEPTH;
+  } while (rem > 0);
+  if (ov)
+  {
+    atomicAdd(dst, (acc0 + acc1) * scale);
+  }
+}
 
 // One task up to (not including) the publication of its completion.
 //   FWD: lanes are rows [i0, i1), depth is columns [j0, j1), panel element (r, j) at Mt[j * h + r].
@@ -543,12 +659,19 @@ k_flow(const SweepTask* __restrict__ tasks,
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     const SweepTask T = *slot;
-    __syncwarp(); // the record is in registers: the slot may be overwritten
+    __syncwarp(); // the record is in registers; the slot is overwritten by the next fetch of this warp only
     if (TRACE)
     {
       ph.fetch += clk_after((double)T.h) - cf;
     }
-    flow_task<FWD, TRACE>(T, lane, Ridx, M, Dinv, yacc, yf, x, cnt, vsh, trace, (unsigned)sched.far_sleep, sched.near, (unsigned)sched.per_signal, ph);
+    if ((FWD ? T.j1 - T.j0 : T.i1 - T.i0) > 32) // bandwidth-bound level; reads the record from the slot (not traced)
+    {
+      flow_task_deep<FWD>(*slot, lane, Ridx, M, Dinv, yacc, yf, x, cnt, vsh, (unsigned)sched.far_sleep, sched.near, (unsigned)sched.per_signal);
+    }
+    else
+    {
+      flow_task<FWD, TRACE>(T, lane, Ridx, M, Dinv, yacc, yf, x, cnt, vsh, trace, (unsigned)sched.far_sleep, sched.near, (unsigned)sched.per_signal, ph);
+    }
     if (TRACE)
     {
       cf = clk_after(0.0);

@@ -1700,8 +1700,14 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
     // Depth of a task: 16 panel entries per lane (one batch of loads, all in flight before the warp waits) where a
     // level has fewer tasks than the machine has warps -- the narrow levels are latency-bound --, 32 (two batches)
-    // where it has more: there the fixed cost of a task (record, publication, ticket) is what limits the bandwidth.
+    // where it has more: there the fixed cost of a task (record, publication, ticket) is what limits the bandwidth;
+    // FLOW_DEEP where even that many tasks are left (large 3D fronts).
     std::vector<int> depth_of_level(P.nlevels, 16);
+    i64 deep_min = FLOW_WARPS / 2; // tasks a level must still have at depth FLOW_DEEP (B200_FLOW_DEEP_TASKS: tests, tuning)
+    if (const char* dm = std::getenv("B200_FLOW_DEEP_TASKS"))
+    {
+      deep_min = std::max<i64>(1, std::atoll(dm));
+    }
     for (int l = 0; l < P.nlevels; ++l)
     {
       i64 entries = 0;
@@ -1710,8 +1716,10 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         const int T = P.lvl_sn[q];
         entries += (P.Wptr[T + 1] - P.Wptr[T]) * (i64)(P.sn_first[T + 1] - P.sn_first[T]);
       }
-      // (measured on B200: a lower threshold or a depth of 64 is slower on every configuration)
-      depth_of_level[l] = entries / (LANES * 16) >= (i64)FLOW_WARPS ? 32 : 16;
+      // (measured on B200: a lower threshold for the second batch is slower on every configuration.) Levels that
+      // still give every warp a task at a depth of FLOW_DEEP are bandwidth-bound: there the panel is streamed with a
+      // rolling window of loads and the fixed cost of a task is amortised over four times as much data.
+      depth_of_level[l] = entries / (LANES * FLOW_DEEP) >= deep_min ? FLOW_DEEP : entries / (LANES * 16) >= (i64)FLOW_WARPS ? 32 : 16;
     }
     // forward: lanes = rows, depth = columns (row r of the triangular top block needs columns <= r)
     // backward: lanes = columns (blocks aligned to 32 like the tiles of the row-major copy), depth = rows (column j

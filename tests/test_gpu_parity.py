@@ -95,6 +95,20 @@ def test_small_and_medium_problems(make):
     _check_problem(make(), seeds=(1, 2))
 
 
+@pytest.mark.parametrize("make", [
+    lambda: problems.poisson_control(44, 2, seed=11),
+    lambda: problems.poisson_control(12, 3, seed=12),
+    lambda: problems.poisson_control(90, 2, seed=13),
+], ids=["p2d_g44", "p3d_g12", "p2d_g90"])
+def test_deep_sweep_tasks(make, monkeypatch):
+    """Sweep tasks of depth 128 (rolling window of loads, solve.cu flow_task_deep): the threshold that reserves them
+    for the bandwidth-bound levels of large 3D fronts is lowered so that these small fronts use them."""
+    monkeypatch.setenv("B200_FLOW_DEEP_TASKS", "1")
+    p = make()
+    f = _check_problem(p, seeds=(1, 2))
+    assert f.stats()["refine_steps"] == 0
+
+
 def test_structure_and_pivots_match_host_analysis_and_emulation():
     p = problems.poisson_control(20, 2, seed=7)
     cp, ri, v = p.kkt_lower()

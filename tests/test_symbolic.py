@@ -73,6 +73,27 @@ def test_plan_emulation_solves_kkt(name):
         assert np.linalg.norm(zs - z) <= 1e-10 * np.linalg.norm(z)
 
 
+@pytest.mark.parametrize("name", ["poisson2d_g48_wide_supernodes", "poisson3d_g6"])
+def test_deep_sweep_tasks_emulate(name, monkeypatch):
+    """The bandwidth-bound levels of large fronts get tasks of depth 128 (symbolic.cpp); the threshold is lowered so
+    that small problems produce them too. Same counters, same result."""
+    monkeypatch.setenv("B200_FLOW_DEEP_TASKS", "1")
+    p = CASES[name]()
+    cp, ri, v = p.kkt_lower()
+    s = Symbolic(p.N, cp, ri, v)
+    plan = s.plan()
+    f = np.asarray(plan["ffl_tasks"]).reshape(-1, 16)
+    b = np.asarray(plan["bfl_tasks"]).reshape(-1, 16)
+    assert (f[:, 9] - f[:, 8]).max() > 32 and (b[:, 7] - b[:, 6]).max() > 32
+    assert (f[:, 9] - f[:, 8]).max() <= 128 and (b[:, 7] - b[:, 6]).max() <= 128
+    em = Emulated(plan, v)
+    K = p.kkt_full()
+    idx, val = p.rhs("solve_lsq", 3)
+    rhs = orc.vec_to_raw(idx, val, p.N)
+    z = em.solve(rhs, refine=0)
+    assert np.linalg.norm(K @ z - rhs) <= 1e-12 * np.linalg.norm(rhs)
+
+
 def test_same_pattern_same_structure_different_values():
     a = problems.chain_rosenbrock(300, 0.2, seed=1)
     b = problems.chain_rosenbrock(300, 0.2, seed=1)
