@@ -679,16 +679,17 @@ k_flow(const SweepTask* __restrict__ tasks,
     // publication. In the wide levels the draw of the next ticket is issued first, so that its round trip overlaps
     // with the fence (nothing can block between the draw and the signal). In the narrow levels consumers are
     // waiting for exactly this signal and the fence must not wait for the ticket atomic: signal first.
-    const bool open     = tried < FLOW_SHARDS;
-    const bool critical = T.pad1 != 0;
-    int issued          = (open && !critical) ? flow_take_issue(ticket, lane, shard) : 0;
-    if (T.signal_idx >= 0)
+    const bool open      = tried < FLOW_SHARDS;
+    const bool critical  = slot->pad1 != 0; // from the slot, not from the register copy: nothing of T stays live across
+    const int signal_idx = slot->signal_idx; // the task (no spills around the call of the deep variant)
+    int issued           = (open && !critical) ? flow_take_issue(ticket, lane, shard) : 0;
+    if (signal_idx >= 0)
     {
       fence_release(); // every lane: its own atomics are visible device-wide before the counter moves
       __syncwarp();
       if (lane == 0)
       {
-        atomicAdd(cnt + T.signal_idx, 1);
+        atomicAdd(cnt + signal_idx, 1);
       }
     }
     if (open && critical)
