@@ -152,11 +152,11 @@ struct Graph
 struct NDShared
 {
   std::vector<std::atomic<int>> tag; // subproblem id a node currently belongs to
-  std::vector<int> level;            // BFS level
+  std::vector<int> level, level2;    // BFS level (two buffers: the pseudo-peripheral search keeps the best structure intact)
   std::vector<int> seen;             // BFS visit stamp
   std::atomic<int> next_id{1};
   std::atomic<int> next_stamp{1};
-  explicit NDShared(int m) : tag(m), level(m, 0), seen(m, 0)
+  explicit NDShared(int m) : tag(m), level(m, 0), level2(m, 0), seen(m, 0)
   {
     for (auto& t : tag)
     {
@@ -168,29 +168,29 @@ struct NDShared
 // ... and per-thread scratch
 struct NDLocal
 {
-  std::vector<int> queue;
+  std::vector<int> queue, queue2;
   std::vector<int> level_ptr, lp2;
 };
 
 // BFS restricted to nodes with tag == id, starting from root. Returns number of levels; fills
-// loc.queue with the visit order (first `count` entries) and sh.level.
+// `queue` with the visit order (first `count` entries) and `level` (node-indexed).
 static int
-bfs(const Graph& g, NDShared& sh, NDLocal& loc, int root, int id, int& count, std::vector<int>& level_ptr)
+bfs(const Graph& g, NDShared& sh, std::vector<int>& queue, std::vector<int>& level, int root, int id, int& count, std::vector<int>& level_ptr)
 {
   const int stamp = sh.next_stamp.fetch_add(1, std::memory_order_relaxed);
   int head = 0, tail = 0;
-  loc.queue[tail++] = root;
-  sh.seen[root]     = stamp;
-  sh.level[root]    = 0;
+  queue[tail++] = root;
+  sh.seen[root] = stamp;
+  level[root]   = 0;
   level_ptr.clear();
   level_ptr.push_back(0);
   int cur_level = 0;
   while (head < tail)
   {
-    int v = loc.queue[head];
-    if (sh.level[v] != cur_level)
+    int v = queue[head];
+    if (level[v] != cur_level)
     {
-      cur_level = sh.level[v];
+      cur_level = level[v];
       level_ptr.push_back(head);
     }
     ++head;
@@ -199,9 +199,9 @@ bfs(const Graph& g, NDShared& sh, NDLocal& loc, int root, int id, int& count, st
       int u = g.adj[p];
       if (sh.tag[u].load(std::memory_order_relaxed) == id && sh.seen[u] != stamp)
       {
-        sh.seen[u]        = stamp;
-        sh.level[u]       = cur_level + 1;
-        loc.queue[tail++] = u;
+        sh.seen[u]    = stamp;
+        level[u]      = cur_level + 1;
+        queue[tail++] = u;
       }
     }
   }
@@ -231,7 +231,9 @@ nd_step(const Graph& g, NDShared& sh, NDLocal& loc, Sub sub, int leaf_size, std:
   {
     sh.tag[v].store(id, std::memory_order_relaxed);
   }
-  std::vector<int>& level_ptr = loc.level_ptr;
+  // loc.queue / sh.level / loc.level_ptr hold the level structure rooted at sub.nodes[0] over the whole subproblem
+  // (left behind by the component scan when there is a single component)
+  bool have_first = false;
 
   if (!sub.connected)
   {
@@ -245,7 +247,7 @@ nd_step(const Graph& g, NDShared& sh, NDLocal& loc, Sub sub, int leaf_size, std:
         continue;
       }
       int cnt;
-      bfs(g, sh, loc, v, id, cnt, level_ptr);
+      bfs(g, sh, loc.queue, sh.level, v, id, cnt, loc.level_ptr);
       Sub c;
       c.nodes.assign(loc.queue.begin(), loc.queue.begin() + cnt);
       c.connected = true;
@@ -259,11 +261,12 @@ nd_step(const Graph& g, NDShared& sh, NDLocal& loc, Sub sub, int leaf_size, std:
     }
     if (comps.size() == 1)
     {
-      sub = std::move(comps[0]);
+      sub = std::move(comps[0]); // nodes now in BFS order from the same first node
       for (int u : sub.nodes)
       {
         sh.tag[u].store(id, std::memory_order_relaxed);
       }
+      have_first = true;
     }
     else
     {
@@ -286,10 +289,14 @@ nd_step(const Graph& g, NDShared& sh, NDLocal& loc, Sub sub, int leaf_size, std:
   }
 
   // connected subgraph
+  int cnt  = ns;
+  int nlev = (int)loc.level_ptr.size() - 1;
+  if (!have_first)
+  {
+    nlev = bfs(g, sh, loc.queue, sh.level, sub.nodes[0], id, cnt, loc.level_ptr);
+  }
   if (ns <= leaf_size)
   {
-    int cnt;
-    bfs(g, sh, loc, sub.nodes[0], id, cnt, level_ptr);
     for (int i = 0; i < cnt; ++i)
     {
       perm[sub.lo + i] = loc.queue[i];
@@ -297,17 +304,18 @@ nd_step(const Graph& g, NDShared& sh, NDLocal& loc, Sub sub, int leaf_size, std:
     return;
   }
 
-  // pseudo-peripheral root
-  int root = sub.nodes[0];
-  int cnt;
-  int nlev = bfs(g, sh, loc, root, id, cnt, level_ptr);
+  // pseudo-peripheral root. The candidate's level structure goes to the other set of buffers, so the best one so far
+  // stays intact and never has to be rebuilt.
+  std::vector<int>*q_cur = &loc.queue, *q_alt = &loc.queue2;
+  std::vector<int>*l_cur = &sh.level, *l_alt = &sh.level2;
+  std::vector<int>*lp_cur = &loc.level_ptr, *lp_alt = &loc.lp2;
   for (int iter = 0; iter < 3; ++iter)
   {
     // pick a minimum-degree node of the last level
     int best = -1, bestdeg = 0x7fffffff;
-    for (int q = level_ptr[nlev - 1]; q < level_ptr[nlev]; ++q)
+    for (int q = (*lp_cur)[nlev - 1]; q < (*lp_cur)[nlev]; ++q)
     {
-      int v   = loc.queue[q];
+      int v   = (*q_cur)[q];
       int deg = g.xadj[v + 1] - g.xadj[v];
       if (deg < bestdeg)
       {
@@ -316,28 +324,30 @@ nd_step(const Graph& g, NDShared& sh, NDLocal& loc, Sub sub, int leaf_size, std:
       }
     }
     int cnt2;
-    int nlev2 = bfs(g, sh, loc, best, id, cnt2, loc.lp2);
+    int nlev2 = bfs(g, sh, *q_alt, *l_alt, best, id, cnt2, *lp_alt);
     if (nlev2 > nlev)
     {
-      root      = best;
-      nlev      = nlev2;
-      level_ptr = loc.lp2;
-      cnt       = cnt2;
+      nlev = nlev2;
+      cnt  = cnt2;
+      std::swap(q_cur, q_alt);
+      std::swap(l_cur, l_alt);
+      std::swap(lp_cur, lp_alt);
     }
     else
     {
-      // restore the level structure of `root`
-      nlev = bfs(g, sh, loc, root, id, cnt, level_ptr);
       break;
     }
   }
+  const std::vector<int>& queue     = *q_cur;
+  const std::vector<int>& level     = *l_cur;
+  const std::vector<int>& level_ptr = *lp_cur;
 
   if (nlev < 3)
   {
     // no interior level: cannot be separated by a level set; emit as one block
     for (int i = 0; i < cnt; ++i)
     {
-      perm[sub.lo + i] = loc.queue[i];
+      perm[sub.lo + i] = queue[i];
     }
     return;
   }
@@ -383,16 +393,16 @@ nd_step(const Graph& g, NDShared& sh, NDLocal& loc, Sub sub, int leaf_size, std:
   B.nodes.reserve((size_t)(cnt - level_ptr[s + 1]));
   for (int q = 0; q < level_ptr[s]; ++q)
   {
-    A.nodes.push_back(loc.queue[q]);
+    A.nodes.push_back(queue[q]);
   }
   for (int q = level_ptr[s]; q < level_ptr[s + 1]; ++q)
   {
-    int v         = loc.queue[q];
+    int v         = queue[q];
     bool touchesB = false;
     for (int p = g.xadj[v]; p < g.xadj[v + 1] && !touchesB; ++p)
     {
       int u = g.adj[p];
-      if (sh.tag[u].load(std::memory_order_relaxed) == id && sh.level[u] == s + 1)
+      if (sh.tag[u].load(std::memory_order_relaxed) == id && level[u] == s + 1)
       {
         touchesB = true;
       }
@@ -408,7 +418,7 @@ nd_step(const Graph& g, NDShared& sh, NDLocal& loc, Sub sub, int leaf_size, std:
   }
   for (int q = level_ptr[s + 1]; q < cnt; ++q)
   {
-    B.nodes.push_back(loc.queue[q]);
+    B.nodes.push_back(queue[q]);
   }
   // separator last
   const int hi = sub.lo + ns;
@@ -456,6 +466,7 @@ nested_dissection(int m, const std::vector<int>& xadj, const std::vector<int>& a
   auto worker = [&]() {
     NDLocal loc;
     loc.queue.assign(m, 0);
+    loc.queue2.assign(m, 0);
     std::vector<Sub> out;
     long done = 0, nodes_done = 0;
     const int me = tcount.fetch_add(1);
