@@ -238,8 +238,8 @@ nd_step(const Graph& g, NDShared& sh, NDLocal& loc, Sub sub, int leaf_size, std:
   if (!sub.connected)
   {
     // split into connected components; each gets a consecutive range. Nodes already taken get tag -id.
+    // Small components (isolated nodes are common: thousands per subproblem) are written out on the spot.
     int lo = sub.lo;
-    std::vector<Sub> comps;
     for (int v : sub.nodes)
     {
       if (sh.tag[v].load(std::memory_order_relaxed) != id)
@@ -248,42 +248,36 @@ nd_step(const Graph& g, NDShared& sh, NDLocal& loc, Sub sub, int leaf_size, std:
       }
       int cnt;
       bfs(g, sh, loc.queue, sh.level, v, id, cnt, loc.level_ptr);
-      Sub c;
-      c.nodes.assign(loc.queue.begin(), loc.queue.begin() + cnt);
-      c.connected = true;
-      c.lo        = lo;
+      if (cnt == ns)
+      {
+        // a single component: continue below with its level structure (nodes in BFS order from the same first node)
+        sub.nodes.assign(loc.queue.begin(), loc.queue.begin() + cnt);
+        have_first = true;
+        break;
+      }
+      for (int i = 0; i < cnt; ++i)
+      {
+        sh.tag[loc.queue[i]].store(-id, std::memory_order_relaxed);
+      }
+      if (cnt <= leaf_size)
+      {
+        for (int i = 0; i < cnt; ++i)
+        {
+          perm[lo + i] = loc.queue[i]; // BFS order
+        }
+      }
+      else
+      {
+        Sub c;
+        c.nodes.assign(loc.queue.begin(), loc.queue.begin() + cnt);
+        c.connected = true;
+        c.lo        = lo;
+        out.push_back(std::move(c));
+      }
       lo += cnt;
-      for (int u : c.nodes)
-      {
-        sh.tag[u].store(-id, std::memory_order_relaxed);
-      }
-      comps.push_back(std::move(c));
     }
-    if (comps.size() == 1)
+    if (!have_first)
     {
-      sub = std::move(comps[0]); // nodes now in BFS order from the same first node
-      for (int u : sub.nodes)
-      {
-        sh.tag[u].store(id, std::memory_order_relaxed);
-      }
-      have_first = true;
-    }
-    else
-    {
-      for (auto& c : comps)
-      {
-        if ((int)c.nodes.size() <= leaf_size)
-        {
-          for (size_t i = 0; i < c.nodes.size(); ++i)
-          {
-            perm[c.lo + (int)i] = c.nodes[i]; // BFS order
-          }
-        }
-        else
-        {
-          out.push_back(std::move(c));
-        }
-      }
       return;
     }
   }
@@ -436,6 +430,8 @@ nd_step(const Graph& g, NDShared& sh, NDLocal& loc, Sub sub, int leaf_size, std:
 
 } // namespace
 
+constexpr int ND_SHARE_MIN = 2048; // subproblems smaller than this stay with the thread that produced them
+
 static void
 nested_dissection(int m, const std::vector<int>& xadj, const std::vector<int>& adj, int leaf_size, std::vector<int>& perm)
 {
@@ -461,13 +457,17 @@ nested_dissection(int m, const std::vector<int>& xadj, const std::vector<int>& a
     stack.push_back(std::move(root));
   }
   unsigned hw        = std::thread::hardware_concurrency();
-  const int nthreads = m < 20000 ? 1 : (int)std::min<unsigned>(8, std::max<unsigned>(1, hw));
+  int nthreads = m < 20000 ? 1 : (int)std::min<unsigned>(8, std::max<unsigned>(1, hw));
+  if (const char* nt = std::getenv("B200_ND_THREADS")) // measurement knob (profiles/symbolic_timing.py)
+  {
+    nthreads = std::max(1, std::min(64, std::atoi(nt)));
+  }
   std::atomic<int> tcount{0};
   auto worker = [&]() {
     NDLocal loc;
     loc.queue.assign(m, 0);
     loc.queue2.assign(m, 0);
-    std::vector<Sub> out;
+    std::vector<Sub> out, local;
     long done = 0, nodes_done = 0;
     const int me = tcount.fetch_add(1);
     struct Report { long& d; long& n; int me; ~Report() { if (std::getenv("B200_SYM_TRACE")) std::fprintf(stderr, "[b200 nd] thread %d: %ld subproblems, %ld nodes\n", me, d, n); } } report{done, nodes_done, me};
@@ -485,16 +485,40 @@ nested_dissection(int m, const std::vector<int>& xadj, const std::vector<int>& a
         stack.pop_back();
         ++in_flight;
       }
-      out.clear();
-      ++done;
-      nodes_done += (long)sub.nodes.size();
-      nd_step(g, sh, loc, std::move(sub), leaf_size, perm, out);
+      // Only large children go back to the shared stack; the rest of the subtree is finished by this thread from a
+      // private stack. (Sharing every child cost two lock hand-offs and a wake-up of all sleepers per subproblem --
+      // ten thousand of them at config 2 -- which ate the whole gain of the threads.)
+      local.clear();
+      local.push_back(std::move(sub));
+      while (!local.empty())
       {
-        std::lock_guard<std::mutex> lock(mu);
+        Sub cur = std::move(local.back());
+        local.pop_back();
+        out.clear();
+        ++done;
+        nodes_done += (long)cur.nodes.size();
+        nd_step(g, sh, loc, std::move(cur), leaf_size, perm, out);
+        bool shared = false;
         for (auto& c : out)
         {
-          stack.push_back(std::move(c));
+          if ((int)c.nodes.size() >= ND_SHARE_MIN && nthreads > 1)
+          {
+            std::lock_guard<std::mutex> lock(mu);
+            stack.push_back(std::move(c));
+            shared = true;
+          }
+          else
+          {
+            local.push_back(std::move(c));
+          }
         }
+        if (shared)
+        {
+          cv.notify_all();
+        }
+      }
+      {
+        std::lock_guard<std::mutex> lock(mu);
         --in_flight;
       }
       cv.notify_all();
