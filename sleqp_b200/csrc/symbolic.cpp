@@ -544,6 +544,35 @@ nested_dissection(int m, const std::vector<int>& xadj, const std::vector<int>& a
 
 // ---------------------------------------------------------------------------------------
 
+// fn(part, lo, hi) over nparts contiguous shares of [0, n), one host thread each (part 0 on the caller's thread).
+template <class F>
+static void
+parallel_ranges(i64 n, int nparts, F&& fn)
+{
+  nparts = (int)std::max<i64>(1, std::min<i64>(nparts, n));
+  if (nparts == 1)
+  {
+    fn(0, (i64)0, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nparts; ++t)
+  {
+    pool.emplace_back([&fn, n, nparts, t]() { fn(t, n * t / nparts, n * (t + 1) / nparts); });
+  }
+  fn(0, (i64)0, n / nparts);
+  for (auto& th : pool)
+  {
+    th.join();
+  }
+}
+
+static int
+host_threads(i64 work, i64 min_work)
+{
+  return work < min_work ? 1 : (int)std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+}
+
 static int
 fail(std::string& err, int code, const std::string& msg)
 {
@@ -1245,7 +1274,9 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     std::vector<int> Srow((size_t)P.nnzS);
     P.Sdest.resize((size_t)P.nnzS);
     P.Sdiag.resize((size_t)m);
-    for (int j = 0; j < m; ++j)
+    std::atomic<bool> outside{false};
+    parallel_ranges(m, host_threads(P.nnzS, 200000), [&](int, i64 jlo, i64 jhi) {
+    for (int j = (int)jlo; j < (int)jhi; ++j)
     {
       i64 o     = Sptr[j];
       Srow[o++] = j;
@@ -1274,13 +1305,19 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
           const int* it = std::lower_bound(rows, rows + nrows, i);
           if (it == rows + nrows || *it != i)
           {
-            return fail(err, B200_ERR_ARG, "internal: S entry outside the supernode structure");
+            outside = true;
+            it      = rows;
           }
           rowpos = k + (it - rows);
         }
         P.Sdest[q] = P.Lptr[T] + (i64)(j - f) * h + rowpos;
       }
       P.Sdiag[j] = P.Sdest[Sptr[j]];
+    }
+    });
+    if (outside)
+    {
+      return fail(err, B200_ERR_ARG, "internal: S entry outside the supernode structure");
     }
     tick("  assembly: destinations");
     auto entry_id = [&](int row, int col) -> i64 {
@@ -1360,11 +1397,20 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       }
     }
     tick("  assembly: term search");
+    // Terms are grouped by the entry of S they belong to, in (e, s, t) order inside a group. Each thread owns a
+    // contiguous range of entries and walks all terms, keeping those of its range: the order inside a group -- and with
+    // it the summation order on the device -- does not depend on the number of threads.
     P.Sterm_ptr.assign((size_t)P.nnzS + 1, 0);
-    for (i64 id : term_ids)
-    {
-      ++P.Sterm_ptr[(size_t)id + 1];
-    }
+    const int nth_fill = host_threads(tptr[nE], 2000000);
+    parallel_ranges(P.nnzS, nth_fill, [&](int, i64 lo, i64 hi) {
+      for (i64 id : term_ids)
+      {
+        if (id >= lo && id < hi)
+        {
+          ++P.Sterm_ptr[(size_t)id + 1];
+        }
+      }
+    });
     for (i64 q = 0; q < P.nnzS; ++q)
     {
       P.Sterm_ptr[q + 1] += P.Sterm_ptr[q];
@@ -1375,20 +1421,27 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       P.Sterm_b.resize(nt);
       P.Sterm_d.resize(nt);
       std::vector<i64> fill(P.Sterm_ptr.begin(), P.Sterm_ptr.end() - 1);
-      size_t tq = 0;
-      for (int e = 0; e < nE; ++e)
-      {
-        for (int s = P.Acsc_ptr[e]; s < P.Acsc_ptr[e + 1]; ++s)
+      parallel_ranges(P.nnzS, nth_fill, [&](int, i64 lo, i64 hi) {
+        size_t tq = 0;
+        for (int e = 0; e < nE; ++e)
         {
-          for (int t = P.Acsc_ptr[e]; t <= s; ++t)
+          for (int s = P.Acsc_ptr[e]; s < P.Acsc_ptr[e + 1]; ++s)
           {
-            const i64 o  = fill[(size_t)term_ids[tq++]]++;
-            P.Sterm_a[o] = P.Acsc_src[s];
-            P.Sterm_b[o] = P.Acsc_src[t];
-            P.Sterm_d[o] = P.dE_src[e];
+            for (int t = P.Acsc_ptr[e]; t <= s; ++t)
+            {
+              const i64 id = term_ids[tq++];
+              if (id < lo || id >= hi)
+              {
+                continue;
+              }
+              const i64 o  = fill[(size_t)id]++;
+              P.Sterm_a[o] = P.Acsc_src[s];
+              P.Sterm_b[o] = P.Acsc_src[t];
+              P.Sterm_d[o] = P.dE_src[e];
+            }
           }
         }
-      }
+      });
     }
   }
 
