@@ -458,7 +458,11 @@ nested_dissection(int m, const std::vector<int>& xadj, const std::vector<int>& a
   }
   unsigned hw        = std::thread::hardware_concurrency();
   int nthreads = m < 20000 ? 1 : (int)std::min<unsigned>(8, std::max<unsigned>(1, hw));
-  if (const char* nt = std::getenv("B200_ND_THREADS")) // measurement knob (profiles/symbolic_timing.py)
+  if (const char* nt = std::getenv("B200_HOST_THREADS"))
+  {
+    nthreads = std::max(1, std::min(64, std::atoi(nt)));
+  }
+  if (const char* nt = std::getenv("B200_ND_THREADS")) // measurement knob (profiles/symbolic_threads.py)
   {
     nthreads = std::max(1, std::min(64, std::atoi(nt)));
   }
@@ -570,6 +574,10 @@ parallel_ranges(i64 n, int nparts, F&& fn)
 static int
 host_threads(i64 work, i64 min_work)
 {
+  if (const char* ht = std::getenv("B200_HOST_THREADS")) // tests: the plan must not depend on the number of threads
+  {
+    return std::max(1, std::min(64, std::atoi(ht)));
+  }
   return work < min_work ? 1 : (int)std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
 }
 
@@ -1369,8 +1377,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
           }
         }
       };
-      const unsigned hw = std::thread::hardware_concurrency();
-      const int nth     = tptr[nE] < 200000 ? 1 : (int)std::min<unsigned>(8, std::max<unsigned>(1, hw));
+      const int nth = host_threads(tptr[nE], 200000);
       if (nth == 1)
       {
         search(0, nE);

@@ -94,6 +94,24 @@ def test_deep_sweep_tasks_emulate(name, monkeypatch):
     assert np.linalg.norm(K @ z - rhs) <= 1e-12 * np.linalg.norm(rhs)
 
 
+def test_plan_does_not_depend_on_the_number_of_host_threads(monkeypatch):
+    """Nested dissection, product-term search and assembly map run on several host threads; ordering, task lists and
+    the order of the product terms inside every entry of S (the summation order on the device) must not depend on how many."""
+    p = problems.poisson_control(60, 2, seed=9)
+    cp, ri, v = p.kkt_lower()
+    plans = []
+    for nth in ("1", "3", "8"):
+        monkeypatch.setenv("B200_HOST_THREADS", nth)
+        s = Symbolic(p.N, cp, ri, v)
+        plans.append((s.stats()["perm_hash"], s.plan()))
+        s.close()
+    for h, plan in plans[1:]:
+        assert h == plans[0][0]
+        for k, a in plans[0][1].items():
+            if k != "ms_symbolic":
+                assert np.array_equal(np.asarray(a), np.asarray(plan[k])), k
+
+
 def test_same_pattern_same_structure_different_values():
     a = problems.chain_rosenbrock(300, 0.2, seed=1)
     b = problems.chain_rosenbrock(300, 0.2, seed=1)
