@@ -1819,23 +1819,35 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     // forward: lanes = rows, depth = columns (row r of the triangular top block needs columns <= r)
     // backward: lanes = columns (blocks aligned to 32 like the tiles of the row-major copy), depth = rows (column j
     //           needs rows >= j)
+    // A deep chunk must really be deep: what is left of a depth range below FLOW_DEEP_MIN goes out in chunks of 32 as in
+    // the other wide levels (small supernodes in a level that qualifies as a whole; the tail of a large one).
+    // And only supernodes with at least FLOW_DEEP columns get them: the small supernodes of a level that qualifies as a
+    // whole (bottom levels of large 2D problems) keep the task shapes they were measured with.
+    constexpr int FLOW_DEEP_MIN = 64;
+    auto depth_of_sn = [&](int T) {
+      const int d = depth_of_level[P.sn_level[T]];
+      return (d > 32 && P.sn_first[T + 1] - P.sn_first[T] < FLOW_DEEP) ? 32 : d;
+    };
+    auto chunk = [&](int remaining, int DEPTH) { return (DEPTH > 32 && remaining < FLOW_DEEP_MIN) ? 32 : DEPTH; };
     auto fwd_blocks = [&](int k, int h, int DEPTH, auto&& emit) {
       for (int i0 = 0; i0 < h; i0 += LANES)
       {
         const int i1 = std::min(h, i0 + LANES);
         const int je = std::min(k, i1);
-        for (int j0 = 0; j0 < je; j0 += DEPTH)
+        for (int j0 = 0, d; j0 < je; j0 += d)
         {
-          emit(i0, i1, j0, std::min(je, j0 + DEPTH));
+          d = chunk(je - j0, DEPTH);
+          emit(i0, i1, j0, std::min(je, j0 + d));
         }
       }
     };
     auto bwd_blocks = [&](int k, int h, int DEPTH, auto&& emit) {
       for (int j0 = 0; j0 < k; j0 += LANES)
       {
-        for (int i0 = j0; i0 < h; i0 += DEPTH) // j0 is a multiple of 32, so the depth blocks are aligned to 16
+        for (int i0 = j0, d; i0 < h; i0 += d) // j0 is a multiple of 32, so the depth blocks are aligned to 16
         {
-          emit(i0, std::min(h, i0 + DEPTH), j0, std::min(k, j0 + LANES));
+          d = chunk(h - i0, DEPTH);
+          emit(i0, std::min(h, i0 + d), j0, std::min(k, j0 + LANES));
         }
       }
     };
@@ -1844,8 +1856,8 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     {
       const int k = P.sn_first[T + 1] - P.sn_first[T];
       const int h = (int)(P.Wptr[T + 1] - P.Wptr[T]);
-      fwd_blocks(k, h, depth_of_level[P.sn_level[T]], [&](int, int, int, int) { ++nf[T]; });
-      bwd_blocks(k, h, depth_of_level[P.sn_level[T]], [&](int, int, int, int) { ++nbk[T]; });
+      fwd_blocks(k, h, depth_of_sn(T), [&](int, int, int, int) { ++nf[T]; });
+      bwd_blocks(k, h, depth_of_sn(T), [&](int, int, int, int) { ++nbk[T]; });
     }
     for (int l = 0; l < P.nlevels; ++l)
     {
@@ -1861,7 +1873,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
           need += nf[P.child_idx[q]];
         }
         const int wait_idx = need > 0 ? T : -1;
-        fwd_blocks(k, h, depth_of_level[l], [&](int i0, int i1, int j0, int j1) {
+        fwd_blocks(k, h, depth_of_sn(T), [&](int i0, int i1, int j0, int j1) {
           P.ffl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, j1, wait_idx, need, P.sn_parent[T], l, depth_of_level[l] == 16, 0});
         });
       }
@@ -1876,7 +1888,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         const int h   = (int)(P.Wptr[T + 1] - P.Wptr[T]);
         const int par = P.sn_parent[T];
         const int signal_idx = P.child_ptr[T + 1] > P.child_ptr[T] ? T : -1;
-        bwd_blocks(k, h, depth_of_level[l], [&](int i0, int i1, int j0, int j1) {
+        bwd_blocks(k, h, depth_of_sn(T), [&](int i0, int i1, int j0, int j1) {
           const bool tail = i1 > k && par >= 0; // touches x of the ancestors
           P.bfl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, j1, tail ? par : -1, tail ? nbk[par] : 0, signal_idx, l, depth_of_level[l] == 16, 0});
         });

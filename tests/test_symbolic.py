@@ -73,12 +73,45 @@ def test_plan_emulation_solves_kkt(name):
         assert np.linalg.norm(zs - z) <= 1e-10 * np.linalg.norm(z)
 
 
-@pytest.mark.parametrize("name", ["poisson2d_g48_wide_supernodes", "poisson3d_g6"])
+DEEP_CASES = {
+    "poisson2d_g48_wide_supernodes": CASES["poisson2d_g48_wide_supernodes"],
+    "poisson3d_g10": lambda: problems.poisson_control(10, 3, seed=4),
+}
+
+
+def _depths(plan):
+    f = np.asarray(plan["ffl_tasks"]).reshape(-1, 16)
+    b = np.asarray(plan["bfl_tasks"]).reshape(-1, 16)
+    return f[:, 9] - f[:, 8], b[:, 7] - b[:, 6]
+
+
+def test_gpu_deep_task_cases_have_deep_tasks(monkeypatch):
+    """The problems of tests/test_gpu_parity.py::test_deep_sweep_tasks really produce depth > 32 tasks in both sweeps
+    (only supernodes with at least 128 columns get them), and never without the lowered threshold at these sizes."""
+    for make in (lambda: problems.poisson_control(44, 2, seed=11), lambda: problems.poisson_control(12, 3, seed=12),
+                 lambda: problems.poisson_control(90, 2, seed=13)):
+        p = make()
+        cp, ri, v = p.kkt_lower()
+        monkeypatch.delenv("B200_FLOW_DEEP_TASKS", raising=False)
+        s = Symbolic(p.N, cp, ri, v)
+        df, db = _depths(s.plan())
+        assert df.max() <= 32 and db.max() <= 32
+        s.close()
+        monkeypatch.setenv("B200_FLOW_DEEP_TASKS", "1")
+        s = Symbolic(p.N, cp, ri, v)
+        df, db = _depths(s.plan())
+        assert 64 <= df.max() <= 128 and 64 <= db.max() <= 128, p.name
+        # a deep chunk is at least 64 deep; everything else keeps the shapes of the other levels
+        assert not np.any((df > 32) & (df < 64)) and not np.any((db > 32) & (db < 64))
+        s.close()
+
+
+@pytest.mark.parametrize("name", list(DEEP_CASES))
 def test_deep_sweep_tasks_emulate(name, monkeypatch):
     """The bandwidth-bound levels of large fronts get tasks of depth 128 (symbolic.cpp); the threshold is lowered so
     that small problems produce them too. Same counters, same result."""
     monkeypatch.setenv("B200_FLOW_DEEP_TASKS", "1")
-    p = CASES[name]()
+    p = DEEP_CASES[name]()
     cp, ri, v = p.kkt_lower()
     s = Symbolic(p.N, cp, ri, v)
     plan = s.plan()
