@@ -650,6 +650,9 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   }
   P.e_of_k.assign(n, -1);
   P.r_of_k.assign(n, -1);
+  P.k_of_e.reserve((size_t)n);
+  P.dE_src.reserve((size_t)n);
+  P.k_of_r.reserve((size_t)n);
   for (int j = 0; j < n; ++j)
   {
     if (diag_src[j] >= 0)
@@ -672,6 +675,8 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     int r, c, src;
   };
   std::vector<Ent> Aent, Gent;
+  Aent.reserve((size_t)P.nnzK);
+  Gent.reserve((size_t)P.nnzK / 4 + (size_t)n);
   for (int j = 0; j < n; ++j)
   {
     for (int p = colptr[j]; p < colptr[j + 1]; ++p)
@@ -934,13 +939,19 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   {
     int v        = P.perm[k];
     xadj2[k + 1] = xadj2[k] + (xadj[v + 1] - xadj[v]);
-    int o        = xadj2[k];
-    for (int p = xadj[v]; p < xadj[v + 1]; ++p)
-    {
-      adj2[o++] = P.pinv[adj[p]];
-    }
-    std::sort(adj2.begin() + xadj2[k], adj2.begin() + xadj2[k + 1]);
   }
+  parallel_ranges(m, host_threads((i64)adj.size(), 500000), [&](int, i64 klo, i64 khi) {
+    for (int k = (int)klo; k < (int)khi; ++k)
+    {
+      int v = P.perm[k];
+      int o = xadj2[k];
+      for (int p = xadj[v]; p < xadj[v + 1]; ++p)
+      {
+        adj2[o++] = P.pinv[adj[p]];
+      }
+      std::sort(adj2.begin() + xadj2[k], adj2.begin() + xadj2[k + 1]);
+    }
+  });
   std::vector<int>().swap(adj);
 
   tick("etree + postorder + relabel");
