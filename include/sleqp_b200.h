@@ -84,6 +84,7 @@ typedef struct b200_stats
   double ms_solve;         /* device time of the last solve (CUDA events) */
   int32_t n_scratch_slots; /* diagonal-block scratch slots of the numeric schedule */
   int32_t reserved;
+  uint64_t pattern_hash2;  /* second, independent hash of the pattern (the plan cache is keyed by both) */
 } b200_stats;
 
 /* ---- factorization plugin (SleqpFactCallbacks) --------------------------------------- */
@@ -157,6 +158,8 @@ B200_API int b200_fact_pivots(b200_fact* handle, double* d_out);
 
 /* CUDA stream the handle launches on (cudaStream_t as void*), for event timing by callers. */
 B200_API void* b200_fact_stream(b200_fact* handle);
+/* CUDA device ordinal the handle lives on (-1 for a null handle). */
+B200_API int b200_fact_device(b200_fact* handle);
 
 B200_API int b200_fact_free(b200_fact** handle);
 

@@ -40,6 +40,7 @@ class Stats(C.Structure):
         ("ms_solve", C.c_double),
         ("n_scratch_slots", C.c_int32),
         ("reserved", C.c_int32),
+        ("pattern_hash2", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -52,7 +53,7 @@ _lib = None
 SYMBOLS = [
     "b200_fact_create", "b200_fact_set_matrix", "b200_fact_solve", "b200_fact_solution",
     "b200_fact_solution_ptr", "b200_fact_solution_sparse", "b200_fact_solve_device", "b200_fact_refactor_device", "b200_fact_profile_solve", "b200_fact_profile_numeric", "b200_fact_rcond", "b200_fact_stats",
-    "b200_fact_structure", "b200_fact_pivots", "b200_fact_stream", "b200_fact_free", "b200_last_error",
+    "b200_fact_structure", "b200_fact_pivots", "b200_fact_stream", "b200_fact_device", "b200_fact_free", "b200_last_error",
     "b200_symbolic_analyze", "b200_symbolic_stats", "b200_symbolic_structure", "b200_symbolic_export",
     "b200_symbolic_free", "b200_mat_create", "b200_mat_set", "b200_mat_mult_vec", "b200_mat_mult_vec_trans",
     "b200_mat_mult_vec_device", "b200_mat_mult_vec_trans_device", "b200_mat_stream", "b200_mat_set_stream", "b200_mat_free",
@@ -88,6 +89,7 @@ def lib():
     L.b200_fact_pivots.argtypes = [vp, dp]
     L.b200_fact_stream.argtypes = [vp]
     L.b200_fact_stream.restype = vp
+    L.b200_fact_device.argtypes = [vp]
     L.b200_fact_free.argtypes = [C.POINTER(vp)]
     L.b200_symbolic_analyze.argtypes = [C.POINTER(vp), C.c_int, C.c_int, ip, ip, dp, C.c_int]
     L.b200_symbolic_stats.argtypes = [vp, C.POINTER(Stats)]

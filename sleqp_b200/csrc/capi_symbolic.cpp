@@ -30,16 +30,17 @@ constexpr size_t CACHE_CAPACITY = 16;
 int
 get_plan(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only, std::shared_ptr<const Plan>& out, bool& cached)
 {
-  if (n < 0 || nnz < 0 || !colptr || colptr[0] != 0 || colptr[n] != nnz)
+  if (!valid_csc_header(n, nnz, colptr, rowidx, val))
   {
-    return set_error(B200_ERR_ARG, "malformed CSC header");
+    return set_error(B200_ERR_ARG, "malformed CSC header (null arrays, colptr not monotone or out of range)");
   }
-  const uint64_t h = hash_pattern(n, nnz, colptr, rowidx, val, lower_only);
+  uint64_t h2      = 0;
+  const uint64_t h = hash_pattern(n, nnz, colptr, rowidx, val, lower_only, &h2);
   {
     std::lock_guard<std::mutex> lock(g_cache_mutex);
     for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
     {
-      if ((*it)->pattern_hash == h && (*it)->N == n)
+      if ((*it)->pattern_hash == h && (*it)->pattern_hash2 == h2 && (*it)->N == n && (*it)->nnzK_input == nnz)
       {
         out = *it;
         g_cache.splice(g_cache.begin(), g_cache, it);
@@ -88,6 +89,7 @@ fill_stats_from_plan(const Plan& P, b200_stats* s)
   s->flops_factor_stored = P.flops_stored;
   s->update_ws_doubles   = P.Utotal;
   s->pattern_hash        = P.pattern_hash;
+  s->pattern_hash2       = P.pattern_hash2;
   s->perm_hash           = P.perm_hash;
   s->ms_symbolic         = P.ms_symbolic;
   s->n_scratch_slots     = P.n_scratch_slots;

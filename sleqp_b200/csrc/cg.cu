@@ -164,9 +164,8 @@ b200_cg_create(b200_cg** handle, b200_fact* fact, b200_mat* hess)
     C->fact   = fact;
     C->hess   = hess;
     C->stream = (cudaStream_t)b200_fact_stream(fact);
-    int dev   = 0;
-    B200_CUDA(cudaGetDevice(&dev));
-    C->device = dev;
+    C->device = b200_fact_device(fact); // everything of the CG lives next to the factorization it projects with
+    B200_CUDA(cudaSetDevice(C->device));
     // Hessian products run on the factorization's stream: they alternate with its solves
     int rc = b200_mat_set_stream(hess, (void*)C->stream);
     if (rc != B200_OK)
@@ -208,6 +207,7 @@ b200_cg_solve(b200_cg* C,
     return set_error(B200_ERR_ARG, "number of variables exceeds the order of the factorized KKT matrix");
   }
   return guarded([&]() {
+    B200_CUDA(cudaSetDevice(C->device));
     const int N = st.n;
     C->n = n;
     C->N = N;

@@ -41,6 +41,7 @@ constexpr int MAX_REFINE = 3;
 struct b200_fact
 {
   int device          = 0;
+  int sms             = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_copy = nullptr;
   NumericOverlap overlap = {}; // side stream + events of the factorization graph (look-ahead)
@@ -103,6 +104,7 @@ struct b200_fact
     sb.yf  = yf.p;
     sb.x   = x.p;
     sb.flow = flow.p;
+    sb.sms  = sms;
     return sb;
   }
   void drop_graphs()
@@ -164,8 +166,12 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   const Plan& P  = *plan;
   DevPlan& dp    = F->dp;
   cudaStream_t s = F->stream;
+  // the captured graphs have the old buffers baked in; until every upload and reservation below has succeeded the
+  // handle has NO current plan (a failure midway must not leave a half-uploaded plan that the next set_matrix with
+  // the same pattern would take for current)
   F->drop_graphs();
-  dp.plan = plan;
+  dp.plan.reset();
+  F->factored = F->solved = false;
   std::vector<SnMeta> meta((size_t)P.nsuper);
   for (int T = 0; T < P.nsuper; ++T)
   {
@@ -259,6 +265,7 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   F->h_sol.reserve(N + 8);
   F->h_scal.reserve(8);
   F->h_nper.reserve(2);
+  dp.plan = plan;
 }
 
 template <typename Enqueue>
@@ -390,8 +397,9 @@ b200_fact_create(b200_fact** handle, int device)
     {
       B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    B200_CUDA(cudaDeviceGetAttribute(&F->sms, cudaDevAttrMultiProcessorCount, dev));
     configure_solve_kernels();
-    configure_numeric_kernels();
+    configure_numeric_kernels(dev);
     *handle = F.release();
     return (int)B200_OK;
   });
@@ -427,6 +435,13 @@ b200_fact_set_matrix(b200_fact* F, int n_rows, int n_cols, int nnz, const int* c
     {
       return set_error(B200_ERR_ARG, "malformed CSC values");
     }
+    if ((size_t)nnz + 8 > F->val.cap)
+    {
+      // DevBuf::reserve reallocates without keeping the contents and the captured graphs have val.p baked in: they
+      // must not survive the old buffer (also when get_plan fails below and the previous plan stays current)
+      B200_CUDA(cudaStreamSynchronize(F->stream));
+      F->drop_graphs();
+    }
     F->val.reserve((size_t)nnz + 8);
     B200_CUDA(cudaEventRecord(F->ev_a, F->stream));
     if (nnz > 0)
@@ -439,6 +454,8 @@ b200_fact_set_matrix(b200_fact* F, int n_rows, int n_cols, int nnz, const int* c
     lap("pattern hash + plan lookup");
     if (rc != B200_OK)
     {
+      // `val` is borrowed for the call only: the copy above must not be in flight when we return
+      cudaStreamSynchronize(F->stream);
       return rc;
     }
     F->symbolic_cached = cached;
@@ -1076,6 +1093,12 @@ void*
 b200_fact_stream(b200_fact* F)
 {
   return F ? (void*)F->stream : nullptr;
+}
+
+int
+b200_fact_device(b200_fact* F)
+{
+  return F ? F->device : -1;
 }
 
 int

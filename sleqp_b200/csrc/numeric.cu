@@ -14,6 +14,7 @@
 //   k_inv_gemm      64x64 DMMA tiles of the triangular products of the selective inversion
 #include "numeric.cuh"
 
+#include <algorithm>
 #include <mutex>
 
 namespace b200
@@ -725,25 +726,20 @@ k_transpose(const TrTask* __restrict__ tasks, const SnMeta* __restrict__ sn, con
 
 // ---------------------------------------------------------------------------------------------
 void
-configure_numeric_kernels()
+configure_numeric_kernels(int device)
 {
-  static std::once_flag once;
-  static std::string failure;
-  std::call_once(once, [] {
-    try
-    {
-      B200_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-      B200_CUDA(cudaFuncSetAttribute(k_inv_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
-    }
-    catch (const CudaError& e)
-    {
-      failure = e.what();
-    }
-  });
-  if (!failure.empty())
+  // cudaFuncSetAttribute is per device: every device a handle is created on is opted in once (the caller has made
+  // `device` current). Handles are created concurrently by independent solver threads.
+  static std::mutex mu;
+  static std::vector<int> done;
+  std::lock_guard<std::mutex> lock(mu);
+  if (std::find(done.begin(), done.end(), device) != done.end())
   {
-    throw CudaError(failure);
+    return;
   }
+  B200_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+  B200_CUDA(cudaFuncSetAttribute(k_inv_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM));
+  done.push_back(device);
 }
 
 void

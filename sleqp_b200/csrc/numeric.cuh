@@ -38,12 +38,14 @@ struct SolveBuffers
   double* x;    // m, solution of the reduced system (new labels)
   const void* trace_fwd = nullptr; // device FlowTrace records (profile entry point with B200_FLOW_TRACE=1 only)
   const void* trace_bwd = nullptr;
+  int sms = 148; // SM count of the handle's device (grid of the persistent sweep kernels)
   int* flow;    // dataflow sweeps: [0, ns) forward counters, [ns, 2 ns) backward counters, then the two ticket counters
 };
 
-// one-time process-wide configuration of the kernels (before any capture)
+// configuration of the kernels before any capture: the experiment knobs once per process, the opt-in to large dynamic
+// shared memory once per device (`device` is current)
 void configure_solve_kernels();
-void configure_numeric_kernels();
+void configure_numeric_kernels(int device);
 
 // Second stream + events of the look-ahead: the update tiles of a stage that do not touch the next panel's columns
 // run next to the next panel step (numeric.cu).

@@ -118,7 +118,7 @@ struct Plan
   int N = 0, nE = 0, m = 0;
   i64 nnzK = 0;
   i64 nnzK_input = 0; // entries of the caller's CSC (== nnzK for lower-triangular input)
-  uint64_t pattern_hash = 0, perm_hash = 0;
+  uint64_t pattern_hash = 0, pattern_hash2 = 0, perm_hash = 0; // the plan cache is keyed by (N, nnzK_input, both pattern hashes)
 
   // node classification / index maps
   std::vector<int> e_of_k, r_of_k, k_of_e, k_of_r;
@@ -189,7 +189,11 @@ struct Plan
 // Builds the plan. Returns 0 or a B200_ERR_* code with a message in err.
 int analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only, Plan& plan, std::string& err);
 
-uint64_t hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only);
+// cheap O(n) check of the column pointers; must hold before hash_pattern / analyze dereference through them
+bool valid_csc_header(int n, int nnz, const int* colptr, const int* rowidx, const double* val);
+
+// two independent 64-bit hashes of (n, pattern, which diagonals are non-zero): returns the first, *second gets the other
+uint64_t hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only, uint64_t* second = nullptr);
 
 // Expands (perm, parent, colcount, supernodes) of the reduced system to the full order of K.
 void full_structure(const Plan& p, int* perm, int* parent, int* colcount, int* n_super_total, int* super_first);

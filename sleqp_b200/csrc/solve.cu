@@ -942,7 +942,6 @@ nblocks(long long n, int threads)
 
 namespace
 {
-int g_sms        = 148;
 int g_flow_sleep = 512;              // B200_FLOW_SLEEP: poll interval of far-away consumers (ns)
 int g_flow_near = FLOW_NEAR, g_flow_per_signal = 4; // B200_FLOW_NEAR, B200_FLOW_PER_SIGNAL (experiments)
 int g_flow_ctas  = FLOW_CTAS_PER_SM; // B200_FLOW_CTAS: fewer resident CTAs per SM (experiments)
@@ -968,7 +967,7 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
                                                              sb.flow);
     lc.tick();
     mark(1);
-    const int max_ctas      = g_sms * g_flow_ctas;
+    const int max_ctas      = sb.sms * g_flow_ctas;
     auto grid = [&](size_t ntasks) {
       // at least ~4 tasks per warp: small systems (batched multistart, many handles on one GPU) leave room for the
       // sweeps of other handles instead of parking spinning warps on every SM
@@ -1018,41 +1017,27 @@ residual(const DevPlan& dp, const NumericBuffers& nb, const double* rhs, const d
 void
 configure_solve_kernels()
 {
-  // once per process, thread-safe (handles are created concurrently by independent solver threads)
+  // once per process, thread-safe (handles are created concurrently by independent solver threads): only the
+  // experiment knobs live here; everything that depends on the device (SM count) is per handle (SolveBuffers::sms)
   static std::once_flag once;
-  static std::string failure;
   std::call_once(once, [] {
-    try
+    if (const char* fc = std::getenv("B200_FLOW_CTAS"))
     {
-      if (const char* fc = std::getenv("B200_FLOW_CTAS"))
-      {
-        g_flow_ctas = std::min(FLOW_CTAS_PER_SM, std::max(1, std::atoi(fc)));
-      }
-      if (const char* fn = std::getenv("B200_FLOW_NEAR"))
-      {
-        g_flow_near = std::max(0, std::atoi(fn));
-      }
-      if (const char* fp = std::getenv("B200_FLOW_PER_SIGNAL"))
-      {
-        g_flow_per_signal = std::max(0, std::atoi(fp));
-      }
-      if (const char* fs = std::getenv("B200_FLOW_SLEEP"))
-      {
-        g_flow_sleep = std::max(32, std::atoi(fs));
-      }
-      int dev        = 0;
-      B200_CUDA(cudaGetDevice(&dev));
-      B200_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+      g_flow_ctas = std::min(FLOW_CTAS_PER_SM, std::max(1, std::atoi(fc)));
     }
-    catch (const CudaError& e)
+    if (const char* fn = std::getenv("B200_FLOW_NEAR"))
     {
-      failure = e.what();
+      g_flow_near = std::max(0, std::atoi(fn));
+    }
+    if (const char* fp = std::getenv("B200_FLOW_PER_SIGNAL"))
+    {
+      g_flow_per_signal = std::max(0, std::atoi(fp));
+    }
+    if (const char* fs = std::getenv("B200_FLOW_SLEEP"))
+    {
+      g_flow_sleep = std::max(32, std::atoi(fs));
     }
   });
-  if (!failure.empty())
-  {
-    throw CudaError(failure);
-  }
 }
 
 void

@@ -47,11 +47,28 @@ mix64(uint64_t h, uint64_t v)
   return h;
 }
 
-static uint64_t
-hash_words(uint64_t seed, const void* data, size_t bytes)
+// second, independent mixing function: the plan cache is keyed by both hashes (and n, nnz), so a collision of one
+// 64-bit hash alone cannot hand out another pattern's plan
+static inline uint64_t
+mix64b(uint64_t h, uint64_t v)
+{
+  h = ((h << 23) | (h >> 41)) + v;
+  h *= 0xC2B2AE3D27D4EB4Full;
+  h ^= h >> 31;
+  return h;
+}
+
+struct Hash2
+{
+  uint64_t a, b;
+};
+
+static Hash2
+hash_words(Hash2 seed, const void* data, size_t bytes)
 {
   const unsigned char* p = (const unsigned char*)data;
-  uint64_t h0 = seed ^ 0x243F6A8885A308D3ull, h1 = seed ^ 0x13198A2E03707344ull, h2 = seed ^ 0xA4093822299F31D0ull, h3 = seed ^ 0x082EFA98EC4E6C89ull;
+  uint64_t h0 = seed.a ^ 0x243F6A8885A308D3ull, h1 = seed.a ^ 0x13198A2E03707344ull, h2 = seed.a ^ 0xA4093822299F31D0ull, h3 = seed.a ^ 0x082EFA98EC4E6C89ull;
+  uint64_t g0 = seed.b ^ 0x452821E638D01377ull, g1 = seed.b ^ 0xBE5466CF34E90C6Cull;
   size_t i = 0;
   for (; i + 32 <= bytes; i += 32)
   {
@@ -61,6 +78,8 @@ hash_words(uint64_t seed, const void* data, size_t bytes)
     h1 = mix64(h1, w[1]);
     h2 = mix64(h2, w[2]);
     h3 = mix64(h3, w[3]);
+    g0 = mix64b(g0, w[0] ^ (w[2] << 1 | w[2] >> 63));
+    g1 = mix64b(g1, w[1] + (w[3] << 7 | w[3] >> 57));
   }
   uint64_t tail[4] = {0, 0, 0, 0};
   std::memcpy(tail, p + i, bytes - i);
@@ -68,21 +87,43 @@ hash_words(uint64_t seed, const void* data, size_t bytes)
   h1 = mix64(h1, tail[1]);
   h2 = mix64(h2, tail[2]);
   h3 = mix64(h3, tail[3] ^ (uint64_t)bytes);
-  return mix64(mix64(mix64(h0, h1), h2), h3);
+  g0 = mix64b(g0, tail[0] ^ (tail[2] << 1 | tail[2] >> 63));
+  g1 = mix64b(g1, tail[1] + (tail[3] << 7 | tail[3] >> 57) + (uint64_t)bytes);
+  return {mix64(mix64(mix64(h0, h1), h2), h3), mix64b(g0, g1)};
+}
+
+// O(n) sanity of the column pointers: everything the hash (and the analysis) dereferences through them is in range
+// afterwards. Row indices are validated by analyze(); the hash only reads them, it never indexes with them.
+bool
+valid_csc_header(int n, int nnz, const int* colptr, const int* rowidx, const double* val)
+{
+  if (n < 0 || nnz < 0 || !colptr || (nnz > 0 && (!rowidx || !val)) || colptr[0] != 0 || colptr[n] != nnz)
+  {
+    return false;
+  }
+  for (int j = 0; j < n; ++j)
+  {
+    if (colptr[j + 1] < colptr[j] || colptr[j + 1] > nnz)
+    {
+      return false;
+    }
+  }
+  return true;
 }
 
 uint64_t
-hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only)
+hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only, uint64_t* second)
 {
   // On the critical path of every set_matrix (the plan is looked up by this key before anything can be launched):
   // large patterns are hashed in four independent slices on host threads, the slice hashes are chained in order.
+  // The caller has checked the header (valid_csc_header).
   constexpr int SLICES = 4;
   const int nsl        = (long long)n + nnz >= 400000 ? SLICES : 1;
-  uint64_t part[SLICES] = {0, 0, 0, 0};
+  Hash2 part[SLICES]   = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
   auto slice = [&](int sl) {
     const int j0 = (int)((long long)n * sl / nsl), j1 = (int)((long long)n * (sl + 1) / nsl);
-    uint64_t h = hash_words(0x5EED + sl, colptr + j0, sizeof(int) * (size_t)(j1 - j0 + 1));
-    h          = hash_words(h, rowidx + colptr[j0], sizeof(int) * (size_t)(colptr[j1] - colptr[j0]));
+    Hash2 h = hash_words({(uint64_t)(0x5EED + sl), (uint64_t)(0xB200 + sl)}, colptr + j0, sizeof(int) * (size_t)(j1 - j0 + 1));
+    h       = hash_words(h, rowidx + colptr[j0], sizeof(int) * (size_t)(colptr[j1] - colptr[j0]));
     // the E/R classification depends on which diagonals are non-zero: part of the key
     uint64_t bits = 0;
     for (int j = j0; j < j1; ++j)
@@ -100,11 +141,12 @@ hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double*
       bits              = (bits << 1) | nz;
       if (((j - j0) & 63) == 63)
       {
-        h    = mix64(h, bits);
+        h.a  = mix64(h.a, bits);
+        h.b  = mix64b(h.b, bits);
         bits = 0;
       }
     }
-    part[sl] = mix64(h, bits ^ 0xD1A6);
+    part[sl] = {mix64(h.a, bits ^ 0xD1A6), mix64b(h.b, bits ^ 0x6A1D)};
   };
   if (nsl == 1)
   {
@@ -124,12 +166,17 @@ hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double*
     }
   }
   int hdr[4] = {n, nnz, lower_only ? 1 : 0, nsl};
-  uint64_t h = hash_words(0x5EED, hdr, sizeof(hdr));
+  Hash2 h    = hash_words({0x5EED, 0xB200}, hdr, sizeof(hdr));
   for (int sl = 0; sl < nsl; ++sl)
   {
-    h = mix64(h, part[sl]);
+    h.a = mix64(h.a, part[sl].a);
+    h.b = mix64b(h.b, part[sl].b);
   }
-  return h;
+  if (second)
+  {
+    *second = h.b;
+  }
+  return h.a;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -610,11 +657,15 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   {
     return fail(err, B200_ERR_ARG, "colptr[0] must be 0 and colptr[n] == nnz");
   }
+  if (!valid_csc_header(n, nnz, colptr, rowidx, val))
+  {
+    return fail(err, B200_ERR_ARG, "colptr not monotone or out of range");
+  }
   P       = Plan();
   P.N     = n;
   P.nnzK  = 0;
   P.nnzK_input = nnz;
-  P.pattern_hash = hash_pattern(n, nnz, colptr, rowidx, val, lower_only);
+  P.pattern_hash = hash_pattern(n, nnz, colptr, rowidx, val, lower_only, &P.pattern_hash2);
 
   // ---- classification ----------------------------------------------------------------
   std::vector<int> diag_src(n, -1);

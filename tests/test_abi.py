@@ -24,7 +24,7 @@ def test_header_symbols_exported():
 def test_stats_struct_layout_matches_header():
     hdr = open(os.path.join(ROOT, "include", "sleqp_b200.h")).read()
     body = hdr[hdr.index("typedef struct b200_stats"): hdr.index("} b200_stats;")]
-    fields = re.findall(r"^\s*(?:u?int32_t|u?int64_t|double)\s+([a-z_A-Z]+);", body, flags=re.M)
+    fields = re.findall(r"^\s*(?:u?int32_t|u?int64_t|double)\s+([a-z_A-Z0-9]+);", body, flags=re.M)
     assert fields == [f for f, _ in _lib.Stats._fields_]
 
 

@@ -191,6 +191,26 @@ def test_malformed_input_is_rejected():
     assert e.value.code == 4
 
 
+def test_malformed_colptr_is_an_error_not_a_crash():
+    """the pattern hash dereferenced colptr before anything validated it (segfault on a negative entry).
+    b200_symbolic_analyze and the plan lookup of set_matrix now check the header in an O(n) pass first."""
+    ri = np.array([0, 1, 2, 3], dtype=np.int32)
+    v = np.ones(4)
+    for cp in ([0, 2, -1000000000, 3, 4], [0, 3, 2, 3, 4], [0, 1, 2, 9, 4], [1, 1, 2, 3, 4]):
+        with pytest.raises(B200Error) as e:
+            Symbolic(4, np.array(cp, dtype=np.int32), ri, v)
+        assert e.value.code == 1
+
+
+def test_pattern_key_has_two_independent_hashes():
+    """The plan cache is keyed by (N, nnz, hash, second hash): both change with the pattern, neither with the values."""
+    a = problems.chain_rosenbrock(300, 0.2, seed=1)
+    c = problems.chain_rosenbrock(300, 0.2, seed=2)
+    sa, sc = Symbolic(a.N, *a.kkt_lower()).stats(), Symbolic(c.N, *c.kkt_lower()).stats()
+    assert sa["pattern_hash"] != sc["pattern_hash"] and sa["pattern_hash2"] != sc["pattern_hash2"]
+    assert sa["pattern_hash"] != sa["pattern_hash2"]
+
+
 def test_empty_matrix():
     s = Symbolic(0, np.zeros(1, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0))
     assert s.stats()["n"] == 0
