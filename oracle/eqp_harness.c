@@ -18,7 +18,11 @@
  * src/test/constrained_newton_test.c:196-201: every constraint, plus every 10th even variable at its
  * upper bound.
  *
- * usage: eqp_harness <n> <number_of_trust_radii>
+ * Second problem ("poisson", the configs 2/4/5 family): 2D Poisson control on a g x g grid, x = (y, u),
+ * f = 1/2 |y - y_d|^2 + alpha/2 |u|^2, c = A y - u = 0 with the h^2-scaled 5-point Laplacian, bounds on u only;
+ * working set: every constraint plus every 7th control at its upper bound.
+ *
+ * usage: eqp_harness <n> <number_of_trust_radii> [chain|poisson]     (poisson: <n> is the grid size g)
  * output: one "name count v0 v1 ..." line per quantity (%.17g).
  */
 #include <math.h>
@@ -52,7 +56,17 @@ typedef struct
 {
   int n, m;
   double* x;
+  int poisson; // 0: chained Rosenbrock, 1: 2D Poisson control
+  int g;
+  double alpha;
 } Data;
+
+static double
+poisson_target(const Data* d, int i)
+{
+  const int ix = i % d->g, iy = i / d->g;
+  return sin(M_PI * (ix + 1.) / (d->g + 1.)) * sin(M_PI * (iy + 1.) / (d->g + 1.));
+}
 
 static SLEQP_RETCODE
 f_set(SleqpFunc* func, SleqpVec* x, SLEQP_VALUE_REASON reason, bool* reject, void* fd)
@@ -67,6 +81,17 @@ f_obj_val(SleqpFunc* func, double* v, void* fd)
 {
   Data* d = (Data*)fd;
   double s = 0.;
+  if (d->poisson)
+  {
+    const int q = d->m;
+    for (int i = 0; i < q; ++i)
+    {
+      const double a = d->x[i] - poisson_target(d, i), u = d->x[q + i];
+      s += 0.5 * a * a + 0.5 * d->alpha * u * u;
+    }
+    *v = s;
+    return SLEQP_OKAY;
+  }
   for (int i = 0; i + 1 < d->n; ++i)
   {
     const double a = d->x[i + 1] - d->x[i] * d->x[i], b = 1. - d->x[i];
@@ -85,6 +110,12 @@ f_obj_grad(SleqpFunc* func, SleqpVec* g, void* fd)
   for (int i = 0; i < d->n; ++i)
   {
     double v = 0.;
+    if (d->poisson)
+    {
+      v = i < d->m ? d->x[i] - poisson_target(d, i) : d->alpha * d->x[i];
+      SLEQP_CALL(sleqp_vec_push(g, i, v));
+      continue;
+    }
     if (i + 1 < d->n)
     {
       v += -400. * d->x[i] * (d->x[i + 1] - d->x[i] * d->x[i]) - 2. * (1. - d->x[i]);
@@ -106,6 +137,17 @@ f_cons_val(SleqpFunc* func, SleqpVec* c, void* fd)
   SLEQP_CALL(sleqp_vec_reserve(c, d->m));
   for (int k = 0; k < d->m; ++k)
   {
+    if (d->poisson)
+    {
+      const int g = d->g, ix = k % g, iy = k / g;
+      double v = 4. * d->x[k] - d->x[d->m + k];
+      v -= ix > 0 ? d->x[k - 1] : 0.;
+      v -= ix + 1 < g ? d->x[k + 1] : 0.;
+      v -= iy > 0 ? d->x[k - g] : 0.;
+      v -= iy + 1 < g ? d->x[k + g] : 0.;
+      SLEQP_CALL(sleqp_vec_push(c, k, v));
+      continue;
+    }
     SLEQP_CALL(sleqp_vec_push(c, k, d->x[2 * k] * d->x[2 * k + 1] + d->x[2 * k + 2] - 1.));
   }
   return SLEQP_OKAY;
@@ -115,10 +157,38 @@ static SLEQP_RETCODE
 f_cons_jac(SleqpFunc* func, SleqpMat* J, void* fd)
 {
   Data* d = (Data*)fd;
-  SLEQP_CALL(sleqp_mat_reserve(J, 3 * d->m));
+  SLEQP_CALL(sleqp_mat_reserve(J, d->poisson ? 6 * d->m : 3 * d->m));
   for (int j = 0; j < d->n; ++j)
   {
     SLEQP_CALL(sleqp_mat_push_col(J, j));
+    if (d->poisson)
+    {
+      const int g = d->g, q = d->m;
+      if (j >= q)
+      {
+        SLEQP_CALL(sleqp_mat_push(J, j - q, j, -1.)); // -I block
+        continue;
+      }
+      const int ix = j % g, iy = j / g; // column j of the symmetric Laplacian, rows ascending
+      if (iy > 0)
+      {
+        SLEQP_CALL(sleqp_mat_push(J, j - g, j, -1.));
+      }
+      if (ix > 0)
+      {
+        SLEQP_CALL(sleqp_mat_push(J, j - 1, j, -1.));
+      }
+      SLEQP_CALL(sleqp_mat_push(J, j, j, 4.));
+      if (ix + 1 < g)
+      {
+        SLEQP_CALL(sleqp_mat_push(J, j + 1, j, -1.));
+      }
+      if (iy + 1 < g)
+      {
+        SLEQP_CALL(sleqp_mat_push(J, j + g, j, -1.));
+      }
+      continue;
+    }
     // column j: rows in ascending order
     if (j % 2 == 0)
     {
@@ -157,7 +227,11 @@ f_hess_prod(SleqpFunc* func, const SleqpVec* dir, const SleqpVec* duals, SleqpVe
   {
     SLEQP_CALL(sleqp_vec_to_raw(duals, lam));
   }
-  for (int i = 0; i < n; ++i)
+  for (int i = 0; i < n && d->poisson; ++i)
+  {
+    out[i] = (i < d->m ? 1. : d->alpha) * v[i]; // constraints are linear: the Hessian of the Lagrangian is diagonal
+  }
+  for (int i = 0; i < n && !d->poisson; ++i)
   {
     double diag = 0.;
     if (i + 1 < n)
@@ -172,7 +246,7 @@ f_hess_prod(SleqpFunc* func, const SleqpVec* dir, const SleqpVec* duals, SleqpVe
     }
     out[i] += diag * v[i];
   }
-  for (int k = 0; k < d->m; ++k)
+  for (int k = 0; k < d->m && !d->poisson; ++k)
   {
     out[2 * k] += lam[k] * v[2 * k + 1];
     out[2 * k + 1] += lam[k] * v[2 * k];
@@ -201,10 +275,12 @@ dump(const char* name, const SleqpVec* v)
 int
 main(int argc, char** argv)
 {
-  const int n      = argc > 1 ? atoi(argv[1]) : 100;
-  const int max_it = argc > 2 ? atoi(argv[2]) : 8;
-  const int m      = (n - 2) / 2;
-  Data data        = {n, m, (double*)calloc(n, sizeof(double))};
+  const int arg1    = argc > 1 ? atoi(argv[1]) : 100;
+  const int max_it  = argc > 2 ? atoi(argv[2]) : 8;
+  const int poisson = argc > 3 && argv[3][0] == 'p';
+  const int n       = poisson ? 2 * arg1 * arg1 : arg1;
+  const int m       = poisson ? arg1 * arg1 : (n - 2) / 2;
+  Data data         = {n, m, (double*)calloc(n, sizeof(double)), poisson, arg1, 1e-2};
 
   SleqpFuncCallbacks callbacks = {.set_value = f_set,
                                   .obj_val   = f_obj_val,
@@ -218,9 +294,13 @@ main(int argc, char** argv)
 
   SleqpVec *var_lb, *var_ub, *cons_lb, *cons_ub, *x0;
   CHECK(sleqp_vec_create_full(&var_lb, n));
-  CHECK(sleqp_vec_fill(var_lb, -2.));
   CHECK(sleqp_vec_create_full(&var_ub, n));
-  CHECK(sleqp_vec_fill(var_ub, 2.));
+  for (int i = 0; i < n; ++i) // poisson: the states y are free, the controls u are bounded
+  {
+    const double bound = (poisson && i < m) ? sleqp_infinity() : 2.;
+    CHECK(sleqp_vec_push(var_lb, i, -bound));
+    CHECK(sleqp_vec_push(var_ub, i, bound));
+  }
   CHECK(sleqp_vec_create_full(&cons_lb, m));
   CHECK(sleqp_vec_create_full(&cons_ub, m));
   CHECK(sleqp_vec_create_full(&x0, n));
@@ -244,7 +324,7 @@ main(int argc, char** argv)
   SleqpWorkingSet* ws = sleqp_iterate_working_set(iterate);
   CHECK(sleqp_working_set_reset(ws));
   int n_active_vars = 0;
-  for (int j = 0; j < n; j += 20) // every 10th even variable
+  for (int j = poisson ? m : 0; j < n; j += poisson ? 7 : 20) // chain: every 10th even variable; poisson: every 7th control
   {
     CHECK(sleqp_working_set_add_var(ws, j, SLEQP_ACTIVE_UPPER));
     ++n_active_vars;

@@ -190,3 +190,28 @@ def eqp_harness_problem(n: int = 400) -> tuple[KKTProblem, np.ndarray]:
     p = KKTProblem(name=f"eqp_harness_n{n}", n=n, m=m, J=J, H=_rosenbrock_hessian(x), active_vars=np.arange(0, n, 20, dtype=np.int64),
                    active_cons=np.arange(m, dtype=np.int64), meta=dict(x0=x))
     return p, grad
+
+
+def eqp_harness_poisson(g: int = 12, alpha: float = 1e-2) -> tuple[KKTProblem, np.ndarray]:
+    """The second problem of oracle/eqp_harness.c ("poisson"): 2D Poisson control on a g x g grid with the same x0
+    (xorshift64), target y_d and working set (every constraint + every 7th control at its upper bound)."""
+    q = g * g
+    n = 2 * q
+    mask = (1 << 64) - 1
+    state = 88172645463325252
+    x = np.empty(n)
+    for i in range(n):
+        state ^= (state << 13) & mask
+        state ^= state >> 7
+        state ^= (state << 17) & mask
+        x[i] = 0.5 + (state >> 11) / 9007199254740992.0
+    A = _laplacian(g, 2)
+    J = sp.hstack([A, -sp.identity(q, format="csr")], format="csc")
+    J.sort_indices()
+    i = np.arange(q)
+    yd = np.sin(np.pi * (i % g + 1.0) / (g + 1.0)) * np.sin(np.pi * (i // g + 1.0) / (g + 1.0))
+    grad = np.concatenate([x[:q] - yd, alpha * x[q:]])
+    H = sp.diags(np.concatenate([np.ones(q), alpha * np.ones(q)]), 0, format="csc")
+    p = KKTProblem(name=f"eqp_harness_poisson_g{g}", n=n, m=q, J=J, H=H, active_vars=np.arange(q, n, 7, dtype=np.int64),
+                   active_cons=np.arange(q, dtype=np.int64), meta=dict(x0=x, g=g, alpha=alpha))
+    return p, grad

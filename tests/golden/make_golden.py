@@ -105,19 +105,22 @@ if __name__ == "__main__":
     vec_cases(ref)
 
 
-def eqp_harness_case(n=400, radii=12):
-    """Output of the reference EQP harness (oracle/eqp_harness.c over the reference LAPACK backend)."""
+def eqp_harness_case(n=400, radii=12, problem="chain"):
+    """Output of the reference EQP harness (oracle/eqp_harness.c over the reference LAPACK backend). problem = "chain"
+    (n variables) or "poisson" (2D Poisson control, n = grid size)."""
     import subprocess
 
     exe = os.path.join(ROOT, "oracle", "_ref", "eqp_harness_lapack")
-    out = subprocess.run([exe, str(n), str(radii)], check=True, capture_output=True, text=True).stdout
+    out = subprocess.run([exe, str(n), str(radii), problem], check=True, capture_output=True, text=True).stdout
     data = {}
     for line in out.splitlines():
         parts = line.split()
         data[parts[0]] = np.array(parts[2:], dtype=np.float64)
-    np.savez_compressed(os.path.join(OUT, f"eqp_harness_lapack_n{n}.npz"), **data)
-    print("eqp harness:", list(data))
+    name = f"eqp_harness_lapack_n{n}.npz" if problem == "chain" else f"eqp_harness_lapack_{problem}_g{n}.npz"
+    np.savez_compressed(os.path.join(OUT, name), **data)
+    print("eqp harness:", name, list(data))
 
 
 if __name__ == "__main__":
     eqp_harness_case()
+    eqp_harness_case(12, 12, "poisson")

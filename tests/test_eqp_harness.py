@@ -11,10 +11,16 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref")
 N, RADII = 400, 12
+# (harness arguments, committed fixture of the reference LAPACK backend, problem builder in sleqp_b200.problems)
+CASES = {
+    "chain_n400": ((str(N), str(RADII), "chain"), f"eqp_harness_lapack_n{N}.npz", "eqp_harness_problem", N),
+    # second case: a Poisson-control problem, working set by hand like constrained_newton_test.c:196-201
+    "poisson_g12": (("12", str(RADII), "poisson"), "eqp_harness_lapack_poisson_g12.npz", "eqp_harness_poisson", 12),
+}
 
 
-def _run(exe):
-    out = subprocess.run([os.path.join(REF, exe), str(N), str(RADII)], check=True, capture_output=True, text=True, timeout=600)
+def _run(exe, case="chain_n400"):
+    out = subprocess.run([os.path.join(REF, exe), *CASES[case][0]], check=True, capture_output=True, text=True, timeout=600)
     data = {}
     for line in out.stdout.splitlines():
         parts = line.split()
@@ -30,10 +36,11 @@ def _compare(got, want, tol):
         assert np.abs(got[k] - want[k]).max() <= tol * scale, (k, float(np.abs(got[k] - want[k]).max()), scale)
 
 
+@pytest.mark.parametrize("case", list(CASES))
 @pytest.mark.skipif(not os.path.exists(os.path.join(REF, "eqp_harness_lapack")), reason="oracle/_ref not built")
-def test_reference_harness_matches_committed_fixture(golden):
-    want = golden(f"eqp_harness_lapack_n{N}.npz")
-    got, err = _run("eqp_harness_lapack")
+def test_reference_harness_matches_committed_fixture(golden, case):
+    want = golden(CASES[case][1])
+    got, err = _run("eqp_harness_lapack", case)
     assert "LAPACK" in err
     _compare(got, {k: want[k] for k in want.files}, 1e-9)
     # the samples really cover several CG segments (otherwise the comparison would be weak)
@@ -42,30 +49,32 @@ def test_reference_harness_matches_committed_fixture(golden):
 
 
 @pytest.mark.gpu
-def test_b200_backend_reproduces_reference_eqp_iterates(golden):
+@pytest.mark.parametrize("case", list(CASES))
+def test_b200_backend_reproduces_reference_eqp_iterates(golden, case):
     if not os.path.exists(os.path.join(REF, "eqp_harness_b200")):
         pytest.skip("oracle/_ref/eqp_harness_b200 not shipped")
-    want = golden(f"eqp_harness_lapack_n{N}.npz")
-    got, err = _run("eqp_harness_b200")
+    want = golden(CASES[case][1])
+    got, err = _run("eqp_harness_b200", case)
     assert "B200" in err
     _compare(got, {k: want[k] for k in want.files}, 1e-8)
     assert got["backend"][0] == 2  # SLEQP_FACT_FLAGS_LOWER
 
 
-def _harness_setup():
+def _harness_setup(case="chain_n400"):
     from sleqp_b200 import problems
 
-    p, grad = problems.eqp_harness_problem(N)
+    p, grad = getattr(problems, CASES[case][2])(CASES[case][3])
     return p, grad
 
 
-def test_oracle_cg_restatement_matches_reference_fixture(golden):
+@pytest.mark.parametrize("case", list(CASES))
+def test_oracle_cg_restatement_matches_reference_fixture(golden, case):
     """oracle.steihaug_projected_cg (numpy restatement of steihaug_solver.c) on the harness problem, with the
     projection done by a sparse LU of K, reproduces what the reference's own Steihaug solver printed."""
     from oracle import sleqp_oracle as orc
 
-    want = golden(f"eqp_harness_lapack_n{N}.npz")
-    p, grad = _harness_setup()
+    want = golden(CASES[case][1])
+    p, grad = _harness_setup(case)
     cp, ri, v = p.kkt_lower()
     lu = orc.SparseLU()
     lu.set_matrix(p.N, cp, ri, v)
@@ -88,13 +97,14 @@ def test_oracle_cg_restatement_matches_reference_fixture(golden):
 
 
 @pytest.mark.gpu
-def test_device_resident_projected_cg_matches_reference_iterates(golden):
+@pytest.mark.parametrize("case", list(CASES))
+def test_device_resident_projected_cg_matches_reference_iterates(golden, case):
     """the whole projected-CG loop on the device (b200_cg_solve) against the iterates
     of the reference's Steihaug solver (fixture from oracle/eqp_harness.c over the reference LAPACK backend)."""
     from sleqp_b200 import Fact, Mat, ProjectedCG
 
-    want = golden(f"eqp_harness_lapack_n{N}.npz")
-    p, grad = _harness_setup()
+    want = golden(CASES[case][1])
+    p, grad = _harness_setup(case)
     f = Fact()
     f.set_matrix(p.N, *p.kkt_lower())
     H = p.H.tocsc()

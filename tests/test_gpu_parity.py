@@ -239,30 +239,101 @@ def test_spmv_on_workloads():
             assert np.array_equal(m_.mult_vec(xi, 2.0 * xv), 2.0 * y)
 
 
-def test_large_configs_by_residual():
+LARGE = {
+    "config3_chain_n1e6": lambda: problems.config(2),
+    "config2_poisson2d_g354": lambda: problems.config(1),
+    "config4_poisson3d_g32": lambda: problems.poisson_control(32, 3, name="config4_poisson3d_g32"),
+    # the sizes config 4 is benchmarked at: fronts of 7-13 k rows, depth-128 sweep tasks
+    "config4_poisson3d_g48": lambda: problems.poisson_control(48, 3, name="config4_poisson3d_g48"),
+    "config4_poisson3d_g64": lambda: problems.poisson_control(64, 3, name="config4_poisson3d_g64"),
+}
+
+
+@pytest.mark.parametrize("name", list(LARGE))
+def test_large_configs_by_residual(name):
     """BASELINE.json sizes, checked through size-independent properties: residual of the
     unperturbed K, feasibility of the projection (A_W P r = 0), idempotence P(P r) = P r."""
-    for p in (problems.config(2), problems.config(1), problems.poisson_control(32, 3, name="config4_poisson3d_g32")):
-        cp, ri, v = p.kkt_lower()
-        f = Fact()
-        f.set_matrix(p.N, cp, ri, v)
-        K = p.kkt_full()
-        A = p.working_rows()
-        for kind in KINDS:
-            idx, val = p.rhs(kind, 4)
-            f.solve(idx, val, p.N)
-            x = f.solution_dense(0, p.N)
-            b = orc.vec_to_raw(idx, val, p.N)
-            assert np.linalg.norm(K @ x - b) <= RES_TOL * np.linalg.norm(b), (p.name, kind)
-        idx, val = p.rhs("project_nullspace", 5)
+    p = LARGE[name]()
+    cp, ri, v = p.kkt_lower()
+    f = Fact()
+    f.set_matrix(p.N, cp, ri, v)
+    K = p.kkt_full()
+    A = p.working_rows()
+    for kind in KINDS:
+        idx, val = p.rhs(kind, 4)
         f.solve(idx, val, p.N)
-        pr = f.solution_dense(0, p.n)
-        assert np.abs(A @ pr).max() <= 1e-10 * np.abs(val).max()
-        f.solve(idx, pr, p.N)
-        ppr = f.solution_dense(0, p.n)
-        assert np.abs(ppr - pr).max() <= 1e-10 * np.abs(pr).max()
-        st = f.stats()
-        print(p.name, {k: st[k] for k in ("n", "nnz_L", "n_supernodes", "n_levels", "n_stages", "ms_symbolic", "ms_numeric", "ms_solve", "refine_steps", "probe_residual")})
+        x = f.solution_dense(0, p.N)
+        b = orc.vec_to_raw(idx, val, p.N)
+        assert np.linalg.norm(K @ x - b) <= RES_TOL * np.linalg.norm(b), (p.name, kind)
+    idx, val = p.rhs("project_nullspace", 5)
+    f.solve(idx, val, p.N)
+    pr = f.solution_dense(0, p.n)
+    assert np.abs(A @ pr).max() <= 1e-10 * np.abs(val).max()
+    f.solve(idx, pr, p.N)
+    ppr = f.solution_dense(0, p.n)
+    assert np.abs(ppr - pr).max() <= 1e-10 * np.abs(pr).max()
+    st = f.stats()
+    if "g48" in name or "g64" in name:
+        assert st["max_front"] >= 7000 and st["refine_steps"] == 0
+        plan_depth = st["n_levels"]
+        assert plan_depth >= 8
+    print(p.name, {k: st[k] for k in ("n", "nnz_L", "nnz_L_stored", "n_supernodes", "n_levels", "n_stages", "max_front", "ms_symbolic", "ms_numeric", "ms_solve", "refine_steps", "probe_residual")})
+    f.release()
+
+
+def test_config5_batch_of_64_concurrent_handles():
+    """Config 5 as bench.py --batch 64 drives it: 64 independent g=128 instances on one device,
+    one handle and CUDA stream each, refactorizations and solves of all instances interleaved from one host thread so
+    that the sweeps of different handles overlap on the GPU. Every instance is checked by its own residual."""
+    import torch
+
+    from bench import make_workload, step_rhs
+
+    dev = torch.device("cuda", 0)
+    inst = []
+    for i in range(64):
+        w = make_workload(4, seed=i)
+        p = w["p"]
+        f = Fact(device=0)
+        f.set_matrix(p.N, w["cp"], w["ri"], w["v"])
+        rhs = []
+        for kind, idx, val, b, e in step_rhs(w, 2)[:4]:
+            rhs.append(torch.from_numpy(orc.vec_to_raw(idx, val, p.N)).to(dev))
+        inst.append(dict(f=f, p=p, d_val=torch.from_numpy(w["v"]).to(dev), rhs=rhs, sol=[torch.empty(p.N, dtype=torch.float64, device=dev) for _ in rhs]))
+    assert len({it["f"].stats()["pattern_hash"] for it in inst}) > 1  # the seeds move the active bounds: several patterns
+    torch.cuda.synchronize()
+    for rep in range(2):
+        for it in inst:
+            it["f"].refactor_device(it["d_val"].data_ptr())
+        for s_ in range(4):
+            for it in inst:
+                it["f"].solve_device(it["rhs"][s_].data_ptr(), it["sol"][s_].data_ptr())
+    torch.cuda.synchronize()
+    worst = 0.0
+    for it in inst:
+        K = it["p"].kkt_full()
+        for b, x in zip(it["rhs"], it["sol"]):
+            b, x = b.cpu().numpy(), x.cpu().numpy()
+            res = np.linalg.norm(K @ x - b) / np.linalg.norm(b)
+            worst = max(worst, res)
+            assert res <= RES_TOL, (it["p"].name, res)
+    print("config5 x64: worst relative residual", worst)
+    for it in inst:
+        it["f"].release()
+
+
+def test_two_handles_on_two_devices_in_one_process():
+    """the opt-in to > 48 KB of dynamic shared memory and the SM count were taken from the first device
+    only. Needs two visible GPUs (skipped on the single-GPU test box; the multi-GPU bench exercises one device per
+    process)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    p = problems.poisson_control(40, 2, seed=3)
+    for dev in (0, 1):
+        f = Fact(device=dev)
+        _check_problem(p, f)
         f.release()
 
 
