@@ -930,8 +930,8 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       }
     }
   }
-  // ---- postorder and relabel ------------------------------------------------------------------
-  std::vector<int> post(m);
+  // ---- postorder (labels L1) ------------------------------------------------------------------
+  std::vector<int> post1(m);
   {
     std::vector<int> head(m, -1), next(m, -1), stk;
     for (int j = m - 1; j >= 0; --j)
@@ -956,7 +956,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         int c = head[v];
         if (c == -1)
         {
-          post[k++] = v;
+          post1[k++] = v;
           stk.pop_back();
         }
         else
@@ -967,51 +967,24 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       }
     }
   }
-  P.perm.resize(m);
-  P.pinv.resize(m);
-  P.parent.assign(m, -1);
-  {
-    std::vector<int> postinv(m);
-    for (int k = 0; k < m; ++k)
-    {
-      postinv[post[k]] = k;
-    }
-    for (int k = 0; k < m; ++k)
-    {
-      P.perm[k]         = perm0[post[k]];
-      P.pinv[P.perm[k]] = k;
-      int p0            = parent0[post[k]];
-      P.parent[k]       = p0 == -1 ? -1 : postinv[p0];
-    }
-  }
-  // adjacency in new labels
-  std::vector<int> xadj2(m + 1, 0), adj2(adj.size());
+  std::vector<int> parent1(m, -1), postinv1(m);
   for (int k = 0; k < m; ++k)
   {
-    int v        = P.perm[k];
-    xadj2[k + 1] = xadj2[k] + (xadj[v + 1] - xadj[v]);
+    postinv1[post1[k]] = k;
   }
-  parallel_ranges(m, host_threads((i64)adj.size(), 500000), [&](int, i64 klo, i64 khi) {
-    for (int k = (int)klo; k < (int)khi; ++k)
-    {
-      int v = P.perm[k];
-      int o = xadj2[k];
-      for (int p = xadj[v]; p < xadj[v + 1]; ++p)
-      {
-        adj2[o++] = P.pinv[adj[p]];
-      }
-      std::sort(adj2.begin() + xadj2[k], adj2.begin() + xadj2[k + 1]);
-    }
-  });
-  std::vector<int>().swap(adj);
-
-  tick("etree + postorder + relabel");
-  // ---- column counts (Gilbert, Ng, Peyton 1994) ------------------------------------------------
-  const std::vector<int>& parent = P.parent;
-  P.colcount.assign(m, 0);
+  for (int k = 0; k < m; ++k)
   {
+    const int p0 = parent0[post1[k]];
+    parent1[k]   = p0 == -1 ? -1 : postinv1[p0];
+  }
+  tick("etree + postorder");
+  // ---- column counts (Gilbert, Ng, Peyton 1994) in the postorder labels; the neighbours are relabelled on the fly
+  // (the algorithm does not need them sorted) ----------------------------------------------------------------
+  std::vector<int> cc1(m, 0);
+  {
+    const std::vector<int>& parent = parent1;
     std::vector<int> first(m, -1), maxfirst(m, -1), prevleaf(m, -1), ancestor(m);
-    std::vector<int>& delta = P.colcount;
+    std::vector<int>& delta = cc1;
     for (int k = 0; k < m; ++k)
     {
       int j    = k;
@@ -1028,9 +1001,10 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       {
         --delta[parent[j]];
       }
-      for (int p = xadj2[j]; p < xadj2[j + 1]; ++p)
+      const int v = perm0[post1[j]];
+      for (int p = xadj[v]; p < xadj[v + 1]; ++p)
       {
-        int i = adj2[p];
+        int i = postinv1[pinv0[adj[p]]];
         if (i <= j || first[j] <= maxfirst[i])
         {
           continue;
@@ -1072,64 +1046,267 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       }
     }
   }
-  const std::vector<int>& cc = P.colcount;
-
   tick("column counts");
-  // ---- supernodes: dense leaf subtrees + fundamental + relaxed chains -----------------------------
-  std::vector<int> blk(m, -1);
-  {
-    std::vector<int> size(m, 1);
-    for (int j = 0; j < m; ++j)
-    {
-      if (parent[j] != -1)
-      {
-        size[parent[j]] += size[j];
-      }
-    }
-    for (int j = 0; j < m; ++j)
-    {
-      if (size[j] <= LEAF_MAX && size[j] > 1 && (parent[j] == -1 || size[parent[j]] > LEAF_MAX))
-      {
-        for (int c = j - size[j] + 1; c <= j; ++c)
-        {
-          blk[c] = j;
-        }
-      }
-    }
-  }
-  std::vector<char> join(std::max(m, 1), 0); // join[j]: j and j+1 share a supernode
+  // ---- supernodes, step 1: fundamental supernodes + relaxed chain amalgamation (in the postorder labels) ----------
+  // rn_last[j]: last column of the chain supernode ("R-node") column j belongs to. Chains only: column j joins the
+  // supernode of j + 1 when j + 1 is its parent and the merge is fundamental (identical structure) or the supernode
+  // is already at least NB wide and the merge adds at most 20 % explicit zeros.
+  std::vector<int> rn_last(m, 0);
   if (m > 0)
   {
-    int l         = m - 1;
-    i64 k         = 1;
-    i64 actual    = cc[l];
+    int l      = m - 1;
+    i64 k      = 1;
+    i64 actual = cc1[l];
+    rn_last[l] = l;
     for (int j = m - 2; j >= 0; --j)
     {
-      const bool forced = blk[j] != -1 && blk[j] == blk[j + 1];
-      const bool chain  = parent[j] == j + 1;
-      bool jn           = false;
-      if (forced || chain)
+      bool jn = false;
+      if (parent1[j] == j + 1)
       {
-        const i64 r       = cc[l] - 1;
+        const i64 r       = cc1[l] - 1;
         const i64 kn      = k + 1;
         const i64 stored  = kn * (kn + r) - kn * (kn - 1) / 2;
-        const i64 act     = actual + cc[j];
-        const bool fundam = chain && cc[j] == cc[j + 1] + 1;
-        jn                = forced || fundam || (chain && (kn <= 4 || (double)(stored - act) <= 0.2 * (double)stored));
+        const i64 act     = actual + cc1[j];
+        const bool fundam = cc1[j] == cc1[j + 1] + 1;
+        // the relaxed rule is for chains that are already wider than one panel step (big separators absorbing what
+        // is nearly identical below them); everything smaller is left to the latency-driven grouping of step 2
+        jn = fundam || (k >= NB && (double)(stored - act) <= 0.2 * (double)stored);
       }
       if (jn)
       {
-        join[j] = 1;
         ++k;
-        actual += cc[j];
+        actual += cc1[j];
       }
       else
       {
         l      = j;
         k      = 1;
-        actual = cc[j];
+        actual = cc1[j];
+      }
+      rn_last[j] = l;
+    }
+  }
+  // ---- supernodes, step 2: latency-driven amalgamation into groups of at most `cap` columns ------------------------
+  // A supernode of up to NB columns costs ONE panel step of the factorization and ONE dependency level of the sweeps
+  // whatever it holds, and every level of the supernodal tree costs a hand-off of several microseconds (profiles/):
+  // so the tree of chain supernodes is collapsed bottom-up. Every node keeps an "open set" of columns below it that
+  // are not yet part of a finished group; when node + open sets of its children exceed the cap, the largest open sets
+  // are closed -- each becomes one dense supernode, its columns made contiguous by the final relabelling -- until the
+  // rest fits. On a path graph (config 3) this turns log2(m) levels of one-column separators into log32(m) levels;
+  // chain supernodes wider than the cap (the separators of 2D/3D problems) stay what they were.
+  std::vector<int> grp1(m, -1); // group root (L1 label of its last column) of every column
+  std::vector<int> post(m);     // final order (ND labels), groups contiguous, child groups before parent groups
+  {
+    int cap = NB;
+    if (const char* gc = std::getenv("B200_GROUP_CAP"))
+    {
+      cap = std::max(1, std::atoi(gc));
+    }
+    // tree of R-nodes, identified by their last column; children lists in ascending order
+    std::vector<int> rpar(m, -1), nchild(m, 0), width(m, 0);
+    for (int j = 0; j < m; ++j)
+    {
+      ++width[rn_last[j]];
+    }
+    for (int l = 0; l < m; ++l)
+    {
+      if (rn_last[l] == l && parent1[l] != -1)
+      {
+        rpar[l] = rn_last[parent1[l]];
+        ++nchild[rpar[l]];
       }
     }
+    std::vector<int> cptr(m + 1, 0), cidx(std::max(m, 1));
+    for (int j = 0; j < m; ++j)
+    {
+      cptr[j + 1] = cptr[j] + nchild[j];
+    }
+    {
+      std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+      for (int l = 0; l < m; ++l)
+      {
+        if (rn_last[l] == l && rpar[l] != -1)
+        {
+          cidx[fill[rpar[l]]++] = l;
+        }
+      }
+    }
+    std::vector<int> open(m, 0);
+    std::vector<char> closed(m, 0);
+    std::vector<std::pair<int, int>> kids;
+    for (int l = 0; l < m; ++l) // children before parents (postorder)
+    {
+      if (rn_last[l] != l)
+      {
+        continue;
+      }
+      kids.clear();
+      int total = width[l];
+      for (int q = cptr[l]; q < cptr[l + 1]; ++q)
+      {
+        const int c = cidx[q];
+        if (open[c] > 0)
+        {
+          kids.push_back({open[c], c});
+          total += open[c];
+        }
+      }
+      std::sort(kids.begin(), kids.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+      for (size_t q = 0; q < kids.size() && total > cap; ++q)
+      {
+        closed[kids[q].second] = 1;
+        total -= kids[q].first;
+        open[kids[q].second] = 0;
+      }
+      open[l] = total;
+      if (rpar[l] == -1)
+      {
+        closed[l] = 1;
+      }
+    }
+    // group of an R-node: itself when closed, else its parent's; then of every column
+    std::vector<int> rgrp(m, -1);
+    for (int l = m - 1; l >= 0; --l) // parents before children
+    {
+      if (rn_last[l] == l)
+      {
+        rgrp[l] = closed[l] ? l : rgrp[rpar[l]];
+      }
+    }
+    for (int j = 0; j < m; ++j)
+    {
+      grp1[j] = rgrp[rn_last[j]];
+    }
+    // order: postorder over the tree of groups (children by ascending root), the columns of a group ascending
+    std::vector<int> gcount(m + 1, 0), gnodes(std::max(m, 1));
+    for (int j = 0; j < m; ++j)
+    {
+      ++gcount[grp1[j] + 1];
+    }
+    for (int g = 0; g < m; ++g)
+    {
+      gcount[g + 1] += gcount[g];
+    }
+    {
+      std::vector<int> fill(gcount.begin(), gcount.end() - 1);
+      for (int j = 0; j < m; ++j)
+      {
+        gnodes[fill[grp1[j]]++] = j;
+      }
+    }
+    // child groups of a group: the closed children of its columns, i.e. every group root r != tree root hangs below
+    // the group of its parent
+    std::vector<int> ghead(m, -1), gnext(m, -1);
+    for (int r = m - 1; r >= 0; --r)
+    {
+      if (closed[r] && parent1[r] != -1)
+      {
+        const int pg = grp1[parent1[r]];
+        gnext[r]     = ghead[pg];
+        ghead[pg]    = r;
+      }
+    }
+    std::vector<int> stk;
+    int k = 0;
+    for (int root = 0; root < m; ++root)
+    {
+      if (parent1[root] != -1)
+      {
+        continue;
+      }
+      stk.push_back(root);
+      while (!stk.empty())
+      {
+        const int g = stk.back();
+        const int c = ghead[g];
+        if (c == -1)
+        {
+          for (int q = gcount[g]; q < gcount[g + 1]; ++q)
+          {
+            post[k++] = gnodes[q]; // L1 label for now
+          }
+          stk.pop_back();
+        }
+        else
+        {
+          ghead[g] = gnext[c];
+          stk.push_back(c);
+        }
+      }
+    }
+  }
+  // final labels: position k holds L1 label post[k]; compose with the postorder to ND labels
+  std::vector<int> cc_final(m), grp_final(m);
+  {
+    std::vector<int> l1_to_final(m);
+    for (int k = 0; k < m; ++k)
+    {
+      l1_to_final[post[k]] = k;
+    }
+    for (int k = 0; k < m; ++k)
+    {
+      cc_final[k]  = cc1[post[k]];
+      grp_final[k] = l1_to_final[grp1[post[k]]];
+    }
+    for (int k = 0; k < m; ++k)
+    {
+      post[k] = post1[post[k]];
+    }
+  }
+  std::vector<int>().swap(post1);
+  std::vector<int>().swap(parent1);
+  std::vector<int>().swap(postinv1);
+  std::vector<int>().swap(cc1);
+  std::vector<int>().swap(grp1);
+  tick("amalgamation groups + order");
+  P.perm.resize(m);
+  P.pinv.resize(m);
+  P.parent.assign(m, -1);
+  {
+    std::vector<int> postinv(m);
+    for (int k = 0; k < m; ++k)
+    {
+      postinv[post[k]] = k;
+    }
+    for (int k = 0; k < m; ++k)
+    {
+      P.perm[k]         = perm0[post[k]];
+      P.pinv[P.perm[k]] = k;
+      int p0            = parent0[post[k]];
+      P.parent[k]       = p0 == -1 ? -1 : postinv[p0];
+    }
+  }
+  // adjacency in new labels
+  std::vector<int> xadj2(m + 1, 0), adj2(adj.size());
+  for (int k = 0; k < m; ++k)
+  {
+    int v        = P.perm[k];
+    xadj2[k + 1] = xadj2[k] + (xadj[v + 1] - xadj[v]);
+  }
+  parallel_ranges(m, host_threads((i64)adj.size(), 500000), [&](int, i64 klo, i64 khi) {
+    for (int k = (int)klo; k < (int)khi; ++k)
+    {
+      int v = P.perm[k];
+      int o = xadj2[k];
+      for (int p = xadj[v]; p < xadj[v + 1]; ++p)
+      {
+        adj2[o++] = P.pinv[adj[p]];
+      }
+      std::sort(adj2.begin() + xadj2[k], adj2.begin() + xadj2[k + 1]);
+    }
+  });
+  std::vector<int>().swap(adj);
+
+  tick("relabel");
+  const std::vector<int>& parent = P.parent;
+  P.colcount = cc_final;
+  const std::vector<int>& cc = P.colcount;
+
+  // ---- supernodes = the amalgamation groups (contiguous in the final labels, root column last) ---------------------
+  std::vector<char> join(std::max(m, 1), 0); // join[j]: j and j+1 share a supernode
+  for (int j = 0; j + 1 < m; ++j)
+  {
+    join[j] = grp_final[j] == grp_final[j + 1];
   }
   P.sn_of_col.assign(m, 0);
   P.sn_first.clear();
