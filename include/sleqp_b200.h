@@ -85,6 +85,9 @@ typedef struct b200_stats
   int32_t n_scratch_slots; /* diagonal-block scratch slots of the numeric schedule */
   int32_t reserved;
   uint64_t pattern_hash2;  /* second, independent hash of the pattern (the plan cache is keyed by both) */
+  double flops_update;     /* useful flops of the DMMA update tiles (in-panel + Schur): roofline numerator of k_update */
+  double flops_inv;        /* useful flops of the selective-inversion tiles: roofline numerator of k_inv_gemm */
+  int64_t panel_doubles;   /* doubles of one copy of the supernodal panels as laid out in HBM (L; Mt and Mr are as large) */
 } b200_stats;
 
 /* ---- factorization plugin (SleqpFactCallbacks) --------------------------------------- */

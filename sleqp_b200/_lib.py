@@ -41,6 +41,9 @@ class Stats(C.Structure):
         ("n_scratch_slots", C.c_int32),
         ("reserved", C.c_int32),
         ("pattern_hash2", C.c_uint64),
+        ("flops_update", C.c_double),
+        ("flops_inv", C.c_double),
+        ("panel_doubles", C.c_int64),
     ]
 
     def as_dict(self):

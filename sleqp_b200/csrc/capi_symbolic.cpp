@@ -90,6 +90,9 @@ fill_stats_from_plan(const Plan& P, b200_stats* s)
   s->update_ws_doubles   = P.Utotal;
   s->pattern_hash        = P.pattern_hash;
   s->pattern_hash2       = P.pattern_hash2;
+  s->flops_update        = P.flops_update;
+  s->flops_inv           = P.flops_inv;
+  s->panel_doubles       = P.Lptr.empty() ? 0 : P.Lptr[P.nsuper];
   s->perm_hash           = P.perm_hash;
   s->ms_symbolic         = P.ms_symbolic;
   s->n_scratch_slots     = P.n_scratch_slots;

@@ -182,6 +182,7 @@ struct Plan
   // statistics
   i64 nnzL = 0, nnzL_stored = 0;
   double flops = 0, flops_stored = 0;
+  double flops_update = 0, flops_inv = 0; // useful flops of the k_update / k_inv_gemm tile tasks
   int max_front = 0;
   double ms_symbolic = 0;
 };

@@ -2023,6 +2023,33 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
 
+  // useful flops of the tile classes (roofline numerators of the DMMA kernels): 2 na nb K per tile, half of it on the
+  // diagonal tiles of a symmetric update (only the lower triangle is kept)
+  for (const Task5& t : P.upd_tasks)
+  {
+    const i64 k = P.sn_first[t.sn + 1] - P.sn_first[t.sn], r = P.Rptr[t.sn + 1] - P.Rptr[t.sn];
+    const bool schur = t.kind == UPD_SCHUR;
+    const double na = (double)std::min<i64>(TILE, (schur ? r : k + r) - t.i0), nb = (double)std::min<i64>(TILE, (schur ? r : (i64)t.jend) - t.j0);
+    P.flops_update += (t.i0 == t.j0 ? 1.0 : 2.0) * na * nb * (double)(t.ke - t.kb);
+  }
+  for (const InvTask& t : P.inv_tasks)
+  {
+    const i64 k = P.sn_first[t.sn + 1] - P.sn_first[t.sn], r = P.Rptr[t.sn + 1] - P.Rptr[t.sn];
+    double na, nb;
+    if (t.kind == INV_T1)
+    {
+      na = (double)std::min<i64>(TILE, k - t.i0), nb = (double)std::min<i64>(TILE, t.ke - t.j0);
+    }
+    else if (t.kind == INV_T2)
+    {
+      na = (double)std::min<i64>(TILE, t.ke - t.i0), nb = (double)std::min<i64>(TILE, t.kb - t.j0);
+    }
+    else
+    {
+      na = (double)std::min<i64>(TILE, r - t.i0), nb = (double)std::min<i64>(TILE, k - t.j0);
+    }
+    P.flops_inv += 2.0 * na * nb * (double)(t.ke - t.kb);
+  }
   tick("inversion + transpose tasks");
   // ---- dataflow sweeps: warp tasks in ticket order, dependency counters per supernode -------------------------
   {
