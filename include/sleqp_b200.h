@@ -219,13 +219,27 @@ enum
 };
 
 /* Borrows a factorization handle (K = [I A_W^T; A_W 0] already factorized) and a matrix handle holding the
- * Hessian of the Lagrangian (n x n, full symmetric CSC); both must outlive the CG handle and live on one device. */
+ * Hessian of the Lagrangian (n x n, full symmetric CSC); both must outlive the CG handle and live on one device.
+ * hess may be NULL when the Hessian is matrix-free: set a host callback instead (below). */
 B200_API int b200_cg_create(b200_cg** handle, b200_fact* fact, b200_mat* hess);
+/* Matrix-free Hessian (the reference's user callback SLEQP_FUNC_HESS_PROD, pub_func.h:168, reached through
+ * sleqp_problem_hess_prod, problem.c:632): out[n] = H * dir[n], dense host vectors, non-zero return = failure. Used when
+ * the handle was created without a device matrix; costs one D2H + H2D of n doubles per CG iteration, everything else
+ * (projection, recurrences, exit tests) stays on the device. */
+typedef int (*b200_hess_prod_fn)(void* ctx, int n, const double* dir, double* out);
+B200_API int b200_cg_set_hess_callback(b200_cg* handle, b200_hess_prod_fn fn, void* ctx);
 /* min g^T p + 1/2 p^T H p  s.t.  A_W p = 0, |p| <= trust_radius. gradient: sparse host vector of dimension n;
  * rel_tol = stat_tol * 1e-2 in the reference (steihaug_solver.c:21,241); max_iter < 0: unlimited.
  * step_out: n doubles (host). */
 B200_API int b200_cg_solve(b200_cg* handle, int n, int nnz_g, const int* g_idx, const double* g_val, double trust_radius, double rel_tol,
                            int max_iter, double* step_out, int* iterations, int* termination);
+/* Same solve with the other outputs of SleqpTRCallbacks (tr/tr_types.h:9-30), each optional (NULL = skip):
+ * tr_dual: dual of the trust-region constraint, computed on the boundary exit only like steihaug_tr_dual
+ * (steihaug_solver.c:187-221, 432-437), NaN otherwise (the reference leaves SLEQP_NONE); min/max_rayleigh: bounds of
+ * d^T H d / d^T d over the directions of this solve, both starting at 1 (steihaug_solver.c:150-183, 234-235). */
+B200_API int b200_cg_solve_ex(b200_cg* handle, int n, int nnz_g, const int* g_idx, const double* g_val, double trust_radius, double rel_tol,
+                              int max_iter, double* step_out, int* iterations, int* termination, double* tr_dual, double* min_rayleigh,
+                              double* max_rayleigh);
 B200_API int b200_cg_free(b200_cg** handle);
 
 /* ---- misc ------------------------------------------------------------------------------ */

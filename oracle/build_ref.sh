@@ -8,7 +8,10 @@
 #   3. gcc -std=gnu11 on the file list, 4. LAPACK shim onto SciPy's bundled OpenBLAS.
 # Produces:
 #   oracle/_ref/libsleqp_ref_lapack.so   reference core + reference fact_lapack.c  (dense oracle)
-#   oracle/_ref/libsleqp_ref_b200.so     reference core + sleqp_b200/host/fact_b200.c (drop-in test)
+#   oracle/_ref/libsleqp_ref_b200.so     reference core + sleqp_b200/host/{fact/fact_b200.c, tr/tr_b200.c, sparse/mat_b200.c} (drop-in test)
+#   oracle/_ref/eqp_harness_{lapack,b200,b200tr}   the EQP harness over the reference LAPACK backend, over our factorization
+#                                        with the reference's Steihaug solver, and over our factorization + our TR solver
+#   oracle/_ref/eqp_step_b200            the timing mode of the same harness (bench.py's reference-driven e2e leg)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REPO="$(dirname "$HERE")"
@@ -97,11 +100,20 @@ gcc $CFLAGS -I"$SRC/fact" -I"$SRC/aug_jac" -I"$SRC/tr" "$HERE/eqp_harness.c" -o 
     -L"$OUT" -lsleqp_ref_lapack -Wl,-rpath,'$ORIGIN' -lm
 
 # drop-in: same reference core, our host glue instead of fact_lapack.c
-if [ -f "$REPO/sleqp_b200/host/fact_b200.c" ] && [ -f "$REPO/sleqp_b200/libsleqp_b200.so" ]; then
-  gcc $CFLAGS -I"$REPO/include" -I"$REPO/sleqp_b200/host" -I"$SRC/fact" -c "$REPO/sleqp_b200/host/fact_b200.c" -o "$OUT/obj/fact_b200.o"
-  gcc -shared -o "$OUT/libsleqp_ref_b200.so" $OBJS "$OUT/obj/fact_b200.o" \
+HOST="$REPO/sleqp_b200/host"
+if [ -f "$HOST/fact/fact_b200.c" ] && [ -f "$REPO/sleqp_b200/libsleqp_b200.so" ]; then
+  GLUE=""
+  for f in fact/fact_b200.c tr/tr_b200.c sparse/mat_b200.c; do
+    o="$OUT/obj/$(basename "$f" .c).o"
+    gcc $CFLAGS -I"$REPO/include" -I"$HOST" -I"$HOST/$(dirname "$f")" -I"$SRC/fact" -I"$SRC/tr" -I"$SRC/sparse" -c "$HOST/$f" -o "$o"
+    GLUE="$GLUE $o"
+  done
+  gcc -shared -o "$OUT/libsleqp_ref_b200.so" $OBJS $GLUE \
       -L"$REPO/sleqp_b200" -lsleqp_b200 -Wl,-rpath,'$ORIGIN/../../sleqp_b200' -lm
   echo "built $OUT/libsleqp_ref_b200.so"
-  gcc $CFLAGS -I"$SRC/fact" -I"$SRC/aug_jac" -I"$SRC/tr" "$HERE/eqp_harness.c" -o "$OUT/eqp_harness_b200" \
-      -L"$OUT" -lsleqp_ref_b200 -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../sleqp_b200' -L"$REPO/sleqp_b200" -lsleqp_b200 -lm
+  HFLAGS="$CFLAGS -I$SRC/fact -I$SRC/aug_jac -I$SRC/tr -I$SRC/sparse -I$HOST -I$REPO/include"
+  LINK="-L$OUT -lsleqp_ref_b200 -Wl,-rpath,\$ORIGIN -Wl,-rpath,\$ORIGIN/../../sleqp_b200 -L$REPO/sleqp_b200 -lsleqp_b200 -lm"
+  gcc $HFLAGS "$HERE/eqp_harness.c" -o "$OUT/eqp_harness_b200" $LINK
+  gcc $HFLAGS -DHARNESS_B200_TR "$HERE/eqp_harness.c" -o "$OUT/eqp_harness_b200tr" $LINK
+  gcc $HFLAGS -DHARNESS_B200_TR -DHARNESS_TIMING "$HERE/eqp_harness.c" -o "$OUT/eqp_step_b200" $LINK
 fi

@@ -56,7 +56,7 @@ typedef struct
 {
   int n, m;
   double* x;
-  int poisson; // 0: chained Rosenbrock, 1: 2D Poisson control
+  int poisson; // 0: chained Rosenbrock, 2 / 3: Poisson control on a g^2 / g^3 grid
   int g;
   double alpha;
 } Data;
@@ -64,8 +64,40 @@ typedef struct
 static double
 poisson_target(const Data* d, int i)
 {
-  const int ix = i % d->g, iy = i / d->g;
-  return sin(M_PI * (ix + 1.) / (d->g + 1.)) * sin(M_PI * (iy + 1.) / (d->g + 1.));
+  double v = 1.;
+  for (int a = 0; a < d->poisson; ++a, i /= d->g)
+  {
+    v *= sin(M_PI * (i % d->g + 1.) / (d->g + 1.));
+  }
+  return v;
+}
+
+// grid neighbours of node k in ascending order (Dirichlet boundary: outside nodes are dropped); returns their number
+static int
+poisson_neighbours(const Data* d, int k, int* out)
+{
+  const int g = d->g, dim = d->poisson;
+  int coord[3], stride[3], cnt = 0;
+  for (int a = 0, q = k, st = 1; a < dim; ++a, q /= g, st *= g)
+  {
+    coord[a]  = q % g;
+    stride[a] = st;
+  }
+  for (int a = dim - 1; a >= 0; --a)
+  {
+    if (coord[a] > 0)
+    {
+      out[cnt++] = k - stride[a];
+    }
+  }
+  for (int a = 0; a < dim; ++a)
+  {
+    if (coord[a] + 1 < g)
+    {
+      out[cnt++] = k + stride[a];
+    }
+  }
+  return cnt;
 }
 
 static SLEQP_RETCODE
@@ -139,12 +171,13 @@ f_cons_val(SleqpFunc* func, SleqpVec* c, void* fd)
   {
     if (d->poisson)
     {
-      const int g = d->g, ix = k % g, iy = k / g;
-      double v = 4. * d->x[k] - d->x[d->m + k];
-      v -= ix > 0 ? d->x[k - 1] : 0.;
-      v -= ix + 1 < g ? d->x[k + 1] : 0.;
-      v -= iy > 0 ? d->x[k - g] : 0.;
-      v -= iy + 1 < g ? d->x[k + g] : 0.;
+      int nb[6];
+      const int cnt = poisson_neighbours(d, k, nb);
+      double v      = 2. * d->poisson * d->x[k] - d->x[d->m + k];
+      for (int q = 0; q < cnt; ++q)
+      {
+        v -= d->x[nb[q]];
+      }
       SLEQP_CALL(sleqp_vec_push(c, k, v));
       continue;
     }
@@ -157,7 +190,7 @@ static SLEQP_RETCODE
 f_cons_jac(SleqpFunc* func, SleqpMat* J, void* fd)
 {
   Data* d = (Data*)fd;
-  SLEQP_CALL(sleqp_mat_reserve(J, d->poisson ? 6 * d->m : 3 * d->m));
+  SLEQP_CALL(sleqp_mat_reserve(J, d->poisson ? (2 * d->poisson + 2) * d->m : 3 * d->m));
   for (int j = 0; j < d->n; ++j)
   {
     SLEQP_CALL(sleqp_mat_push_col(J, j));
@@ -169,23 +202,22 @@ f_cons_jac(SleqpFunc* func, SleqpMat* J, void* fd)
         SLEQP_CALL(sleqp_mat_push(J, j - q, j, -1.)); // -I block
         continue;
       }
-      const int ix = j % g, iy = j / g; // column j of the symmetric Laplacian, rows ascending
-      if (iy > 0)
+      int nb[6]; // column j of the symmetric Laplacian, rows ascending
+      const int cnt = poisson_neighbours(d, j, nb);
+      (void)g;
+      bool diag_done = false;
+      for (int t = 0; t < cnt; ++t)
       {
-        SLEQP_CALL(sleqp_mat_push(J, j - g, j, -1.));
+        if (!diag_done && nb[t] > j)
+        {
+          SLEQP_CALL(sleqp_mat_push(J, j, j, 2. * d->poisson));
+          diag_done = true;
+        }
+        SLEQP_CALL(sleqp_mat_push(J, nb[t], j, -1.));
       }
-      if (ix > 0)
+      if (!diag_done)
       {
-        SLEQP_CALL(sleqp_mat_push(J, j - 1, j, -1.));
-      }
-      SLEQP_CALL(sleqp_mat_push(J, j, j, 4.));
-      if (ix + 1 < g)
-      {
-        SLEQP_CALL(sleqp_mat_push(J, j + 1, j, -1.));
-      }
-      if (iy + 1 < g)
-      {
-        SLEQP_CALL(sleqp_mat_push(J, j + g, j, -1.));
+        SLEQP_CALL(sleqp_mat_push(J, j, j, 2. * d->poisson));
       }
       continue;
     }
@@ -272,15 +304,35 @@ dump(const char* name, const SleqpVec* v)
   free(raw);
 }
 
-int
-main(int argc, char** argv)
+// ---- problem set-up shared by the parity and the timing mode ----------------------------------------------
+typedef struct
 {
-  const int arg1    = argc > 1 ? atoi(argv[1]) : 100;
-  const int max_it  = argc > 2 ? atoi(argv[2]) : 8;
-  const int poisson = argc > 3 && argv[3][0] == 'p';
-  const int n       = poisson ? 2 * arg1 * arg1 : arg1;
-  const int m       = poisson ? arg1 * arg1 : (n - 2) / 2;
-  Data data         = {n, m, (double*)calloc(n, sizeof(double)), poisson, arg1, 1e-2};
+  Data data;
+  SleqpFunc* func;
+  SleqpSettings* settings;
+  SleqpProblem* problem;
+  SleqpIterate* iterate;
+  SleqpFact* fact;
+  SleqpAugJac* jac;
+  int n, m, ws_size;
+} Setup;
+
+// kind: "chain" (size = number of variables), "poisson" / "poisson3" (size = grid edge g). active_every: every how
+// many-th candidate variable sits at its upper bound (chain: even variables, poisson: controls); 0 = none.
+static void
+setup_problem(Setup* s, const char* kind, int size, int active_every)
+{
+  const int poisson = kind[0] == 'p' ? (kind[7] == '3' ? 3 : 2) : 0;
+  int q             = 1;
+  for (int a = 0; a < poisson; ++a)
+  {
+    q *= size;
+  }
+  const int n = poisson ? 2 * q : size;
+  const int m = poisson ? q : (n - 2) / 2;
+  s->n        = n;
+  s->m        = m;
+  s->data     = (Data){n, m, (double*)calloc(n, sizeof(double)), poisson, size, 1e-2};
 
   SleqpFuncCallbacks callbacks = {.set_value = f_set,
                                   .obj_val   = f_obj_val,
@@ -289,8 +341,7 @@ main(int argc, char** argv)
                                   .cons_jac  = f_cons_jac,
                                   .hess_prod = f_hess_prod,
                                   .func_free = NULL};
-  SleqpFunc* func;
-  CHECK(sleqp_func_create(&func, &callbacks, n, m, &data));
+  CHECK(sleqp_func_create(&s->func, &callbacks, n, m, &s->data));
 
   SleqpVec *var_lb, *var_ub, *cons_lb, *cons_ub, *x0;
   CHECK(sleqp_vec_create_full(&var_lb, n));
@@ -313,34 +364,108 @@ main(int argc, char** argv)
     CHECK(sleqp_vec_push(x0, i, 0.5 + (double)(state >> 11) / 9007199254740992.0));
   }
 
-  SleqpSettings* settings;
-  CHECK(sleqp_settings_create(&settings));
-  SleqpProblem* problem;
-  CHECK(sleqp_problem_create_simple(&problem, func, var_lb, var_ub, cons_lb, cons_ub, settings));
-  SleqpIterate* iterate;
-  CHECK(sleqp_iterate_create(&iterate, problem, x0));
-  CHECK(sleqp_set_and_evaluate(problem, iterate, SLEQP_VALUE_REASON_NONE, NULL));
+  CHECK(sleqp_settings_create(&s->settings));
+  CHECK(sleqp_problem_create_simple(&s->problem, s->func, var_lb, var_ub, cons_lb, cons_ub, s->settings));
+  CHECK(sleqp_iterate_create(&s->iterate, s->problem, x0));
+  CHECK(sleqp_set_and_evaluate(s->problem, s->iterate, SLEQP_VALUE_REASON_NONE, NULL));
 
-  SleqpWorkingSet* ws = sleqp_iterate_working_set(iterate);
+  SleqpWorkingSet* ws = sleqp_iterate_working_set(s->iterate);
   CHECK(sleqp_working_set_reset(ws));
   int n_active_vars = 0;
-  for (int j = poisson ? m : 0; j < n; j += poisson ? 7 : 20) // chain: every 10th even variable; poisson: every 7th control
+  if (active_every > 0)
   {
-    CHECK(sleqp_working_set_add_var(ws, j, SLEQP_ACTIVE_UPPER));
-    ++n_active_vars;
+    const int step = poisson ? active_every : 2 * active_every;
+    for (int j = poisson ? m : 0; j < n; j += step)
+    {
+      CHECK(sleqp_working_set_add_var(ws, j, SLEQP_ACTIVE_UPPER));
+      ++n_active_vars;
+    }
   }
   for (int k = 0; k < m; ++k)
   {
     CHECK(sleqp_working_set_add_cons(ws, k, SLEQP_ACTIVE_BOTH));
   }
-  const int ws_size = n_active_vars + m;
+  s->ws_size = n_active_vars + m;
 
-  SleqpFact* fact;
-  CHECK(sleqp_fact_create_default(&fact, settings));
+  CHECK(sleqp_fact_create_default(&s->fact, s->settings));
+  CHECK(sleqp_standard_aug_jac_create(&s->jac, s->problem, s->settings, s->fact));
+}
+
+// Hessian of the Lagrangian at the start iterate as a full symmetric CSC matrix (the constraint duals are zero there)
+static SleqpMat*
+hessian_matrix(const Data* d)
+{
+  const int n = d->n;
+  SleqpMat* H;
+  CHECK(sleqp_mat_create(&H, n, n, d->poisson ? n : 3 * n));
+  for (int j = 0; j < n; ++j)
+  {
+    CHECK(sleqp_mat_push_col(H, j));
+    if (d->poisson)
+    {
+      CHECK(sleqp_mat_push(H, j, j, j < d->m ? 1. : d->alpha));
+      continue;
+    }
+    double diag = 0.;
+    if (j + 1 < n)
+    {
+      diag += 1200. * d->x[j] * d->x[j] - 400. * d->x[j + 1] + 2.;
+    }
+    if (j > 0)
+    {
+      diag += 200.;
+      CHECK(sleqp_mat_push(H, j - 1, j, -400. * d->x[j - 1]));
+    }
+    CHECK(sleqp_mat_push(H, j, j, diag));
+    if (j + 1 < n)
+    {
+      CHECK(sleqp_mat_push(H, j + 1, j, -400. * d->x[j]));
+    }
+  }
+  return H;
+}
+
+#ifdef HARNESS_B200_TR
+#include "tr/tr_b200.h"
+#endif
+
+// the trust-region solver under test: the reference's Steihaug solver, or (-DHARNESS_B200_TR) the B200 one
+static void
+create_tr_solver(SleqpTRSolver** tr, Setup* s, SleqpMat* hessian)
+{
+#ifdef HARNESS_B200_TR
+  CHECK(sleqp_b200_tr_solver_create(tr, s->problem, s->settings));
+  if (hessian)
+  {
+    CHECK(sleqp_tr_b200_set_hessian(*tr, hessian));
+  }
+#else
+  (void)hessian;
+  CHECK(sleqp_steihaug_solver_create(tr, s->problem, s->settings));
+#endif
+}
+
+#ifndef HARNESS_TIMING
+
+int
+main(int argc, char** argv)
+{
+  const int arg1    = argc > 1 ? atoi(argv[1]) : 100;
+  const int max_it  = argc > 2 ? atoi(argv[2]) : 8;
+  const char* kind  = argc > 3 ? argv[3] : "chain";
+  const bool matrix = argc > 4 && argv[4][0] == 'm'; // B200 TR solver: Hessian as a device matrix instead of the callback
+  Setup S;
+  setup_problem(&S, kind, arg1, kind[0] == 'p' ? 7 : 10);
+  const int n = S.n, ws_size = S.ws_size;
+  SleqpSettings* settings = S.settings;
+  SleqpProblem* problem   = S.problem;
+  SleqpIterate* iterate   = S.iterate;
+  SleqpFact* fact         = S.fact;
+  SleqpAugJac* jac        = S.jac;
+  (void)problem;
+
   printf("backend 1 %d\n", (int)sleqp_fact_flags(fact));
   fprintf(stderr, "backend: %s\n", sleqp_fact_name(fact));
-  SleqpAugJac* jac;
-  CHECK(sleqp_standard_aug_jac_create(&jac, problem, settings, fact));
   CHECK(sleqp_aug_jac_set_iterate(jac, iterate));
 
   SleqpVec* grad = sleqp_iterate_obj_grad(iterate);
@@ -371,26 +496,32 @@ main(int argc, char** argv)
   // zero step on this problem (steihaug_solver.c:302-305)
   CHECK(sleqp_settings_set_int_value(settings, SLEQP_SETTINGS_INT_MAX_NEWTON_ITERATIONS, 4 * n));
   CHECK(sleqp_settings_set_real_value(settings, SLEQP_SETTINGS_REAL_STAT_TOL, 1e-2));
-  double full_norm = 0.;
+  SleqpMat* hessian = matrix ? hessian_matrix(&S.data) : NULL;
+  double full_norm  = 0.;
   for (int it = -1; it < max_it; ++it)
   {
     // it = -1: unconstrained by the radius (the converged Newton step); then radii inside its norm
     const double radius = it < 0 ? 1e8 : full_norm * (0.6 + 0.4 * (it + 0.5) / max_it);
     SleqpTRSolver* tr;
-    CHECK(sleqp_steihaug_solver_create(&tr, problem, settings));
+    create_tr_solver(&tr, &S, hessian);
     SleqpVec* step;
     CHECK(sleqp_vec_create_empty(&step, n));
     double tr_dual = 0.;
     CHECK(sleqp_tr_solver_solve(tr, jac, cons_dual, grad, step, radius, &tr_dual));
+    double ray_min = 0., ray_max = 0.;
+    CHECK(sleqp_tr_solver_current_rayleigh(tr, &ray_min, &ray_max));
     char name[64];
     if (it < 0)
     {
       full_norm = sleqp_vec_norm(step);
       snprintf(name, sizeof(name), "cg_converged_step");
+      printf("tr_info_converged 3 %.17g %.17g %.17g\n", tr_dual, ray_min, ray_max);
     }
     else
     {
       snprintf(name, sizeof(name), "cg_path_sample_%d", it);
+      // dual of the trust region (boundary exit) and the Rayleigh bounds of the directions so far
+      printf("tr_info_%d 3 %.17g %.17g %.17g\n", it, tr_dual, ray_min, ray_max);
     }
     dump(name, step);
     CHECK(sleqp_vec_free(&step));
@@ -400,7 +531,145 @@ main(int argc, char** argv)
   CHECK(sleqp_aug_jac_release(&jac));
   CHECK(sleqp_fact_release(&fact));
   CHECK(sleqp_iterate_release(&iterate));
-  CHECK(sleqp_problem_release(&problem));
+  CHECK(sleqp_problem_release(&S.problem));
   CHECK(sleqp_settings_release(&settings));
   return 0;
 }
+
+#else // HARNESS_TIMING: the EQP part of one SQP iteration, timed end to end through reference code
+
+#include <time.h>
+
+#include "sparse/mat.h"
+
+static double
+now_ms(void)
+{
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return 1e3 * t.tv_sec + 1e-6 * t.tv_nsec;
+}
+
+/*
+ * usage: eqp_step_b200 <chain|poisson|poisson3> <size> <cg_iters> <steps> [steihaug]
+ *
+ * One step = what SLEQP does between the Cauchy step and the trial point, every call a reference
+ * function on host data:
+ *   sleqp_aug_jac_set_iterate    host fill_aug_jac (standard_aug_jac.c:135-237) + SleqpFact.set_matrix + condition
+ *   sleqp_aug_jac_solve_min_norm, sleqp_aug_jac_solve_lsq
+ *   sleqp_mat_mult_vec_trans (sparse multipliers, newton.c:377), sleqp_mat_mult_vec (direction.c:66)
+ *   sleqp_tr_solver_solve capped at <cg_iters> iterations: the B200 TR solver (device CG, Hessian as a matrix), or with
+ *   the 5th argument the reference's own Steihaug solver over the B200 factorization (one boundary crossing per iteration)
+ * Prints one JSON line.
+ */
+int
+main(int argc, char** argv)
+{
+  const char* kind   = argc > 1 ? argv[1] : "chain";
+  const int size     = argc > 2 ? atoi(argv[2]) : 100000;
+  const int cg_iters = argc > 3 ? atoi(argv[3]) : 30;
+  const int steps    = argc > 4 ? atoi(argv[4]) : 5;
+  const bool steihaug = argc > 5 && argv[5][0] == 's';
+  Setup S;
+  // working sets like sleqp_b200/problems.py: chain = every constraint, poisson = every constraint + 10 % of the controls
+  setup_problem(&S, kind, size, kind[0] == 'p' ? 10 : 0);
+  const int n = S.n, m = S.m, ws_size = S.ws_size;
+  CHECK(sleqp_settings_set_int_value(S.settings, SLEQP_SETTINGS_INT_MAX_NEWTON_ITERATIONS, cg_iters));
+  CHECK(sleqp_settings_set_real_value(S.settings, SLEQP_SETTINGS_REAL_STAT_TOL, 1e-12)); // run to the cap
+
+  SleqpVec* grad      = sleqp_iterate_obj_grad(S.iterate);
+  SleqpVec* cons_dual = sleqp_iterate_cons_dual(S.iterate);
+  SleqpMat* J         = sleqp_iterate_cons_jac(S.iterate);
+  SleqpVec *minnorm_rhs, *minnorm, *duals, *step, *viol, *jtv, *xfull;
+  CHECK(sleqp_vec_create_full(&minnorm_rhs, ws_size));
+  CHECK(sleqp_vec_create_empty(&minnorm, n));
+  CHECK(sleqp_vec_create_empty(&duals, ws_size));
+  CHECK(sleqp_vec_create_empty(&step, n));
+  CHECK(sleqp_vec_create_empty(&viol, m));
+  CHECK(sleqp_vec_create_empty(&jtv, n));
+  CHECK(sleqp_vec_create_full(&xfull, n));
+  for (int i = 0; i < ws_size; ++i)
+  {
+    CHECK(sleqp_vec_push(minnorm_rhs, i, sin(0.37 * i) + 0.1));
+  }
+  CHECK(sleqp_vec_reserve(viol, m / 100 + 1));
+  for (int k = 0; k < m; k += 100)
+  {
+    CHECK(sleqp_vec_push(viol, k, cos(0.11 * k)));
+  }
+  for (int i = 0; i < n; ++i)
+  {
+    CHECK(sleqp_vec_push(xfull, i, sin(0.05 * i) + 0.2));
+  }
+  double* jx = (double*)calloc(m > 0 ? m : 1, sizeof(double));
+
+  SleqpMat* hessian = steihaug ? NULL : hessian_matrix(&S.data);
+  SleqpTRSolver* tr;
+#ifdef HARNESS_B200_TR
+  if (steihaug)
+  {
+    CHECK(sleqp_steihaug_solver_create(&tr, S.problem, S.settings));
+  }
+  else
+  {
+    create_tr_solver(&tr, &S, hessian);
+  }
+#else
+  create_tr_solver(&tr, &S, hessian);
+#endif
+
+  double t_set = 0., t_solves = 0., t_spmv = 0., t_tr = 0., t_total = 0.;
+  double tr_dual = 0.;
+  const int warm = 2;
+  for (int it = -warm; it < steps; ++it)
+  {
+    const double t0 = now_ms();
+    CHECK(sleqp_aug_jac_set_iterate(S.jac, S.iterate));
+    const double t1 = now_ms();
+    CHECK(sleqp_aug_jac_solve_min_norm(S.jac, minnorm_rhs, minnorm));
+    CHECK(sleqp_aug_jac_solve_lsq(S.jac, grad, duals));
+    const double t2 = now_ms();
+    CHECK(sleqp_mat_mult_vec_trans(J, viol, 0., jtv));
+    CHECK(sleqp_mat_mult_vec(J, xfull, jx));
+    const double t3 = now_ms();
+    CHECK(sleqp_tr_solver_solve(tr, S.jac, cons_dual, grad, step, 1e8, &tr_dual));
+    const double t4 = now_ms();
+    if (it >= 0)
+    {
+      t_set += t1 - t0;
+      t_solves += t2 - t1;
+      t_spmv += t3 - t2;
+      t_tr += t4 - t3;
+      t_total += t4 - t0;
+    }
+  }
+  int cg_done = cg_iters, cg_exit = -1;
+#ifdef HARNESS_B200_TR
+  if (!steihaug)
+  {
+    CHECK(sleqp_tr_b200_last_solve(tr, &cg_done, &cg_exit));
+  }
+#endif
+  const SleqpMat* K = NULL;
+  (void)K;
+  const double ms = t_total / steps;
+  // bytes over PCIe per step (counted from the vectors that cross): K values in; per aug_jac solve a sparse right-hand
+  // side in (8 B values, 4 B indices unless contiguous) and a sparsified slice out (12 B per entry, copied at full
+  // length); the TR solve: gradient in (12 B), step out (8 B) -- or, with the reference's Steihaug loop, one
+  // projection (12 n in, 12 n out) per iteration
+  const double nnzK = (double)n + 3. * m; // order of magnitude only for chain; exact value is printed by bench.py's C-ABI leg
+  (void)nnzK;
+  const long long h2d = 8LL * sleqp_mat_nnz(J) + 8LL * n /* diag */ + 8LL * ws_size + 12LL * n
+                        + (steihaug ? 12LL * n * (cg_iters + 1) : 12LL * n + (hessian ? 0 : 8LL * n * cg_iters));
+  const long long d2h = 12LL * n + 12LL * ws_size + (steihaug ? 12LL * n * (cg_iters + 1) : 8LL * n + (hessian ? 0 : 8LL * n * cg_iters));
+  printf("{\"driver\": \"eqp_step (reference aug_jac/TR code over the B200 glue)\", \"problem\": \"%s\", \"size\": %d, \"n\": %d, \"m\": %d, "
+         "\"ws_size\": %d, \"N\": %d, \"backend\": \"%s\", \"tr_solver\": \"%s\", \"cg_iters_cap\": %d, \"cg_iterations\": %d, \"cg_exit\": %d, "
+         "\"steps\": %d, \"warmup\": %d, \"ms_per_step\": %.6f, \"iters_per_s\": %.6f, \"set_iterate_ms\": %.6f, \"two_solves_ms\": %.6f, "
+         "\"solve_ms\": %.6f, \"host_spmv_ms\": %.6f, \"tr_solve_ms\": %.6f, \"h2d_bytes_per_step\": %lld, \"d2h_bytes_per_step\": %lld}\n",
+         kind, size, n, m, ws_size, n + ws_size, sleqp_fact_name(S.fact),
+         steihaug ? "reference steihaug_solver.c over SleqpFact B200" : "tr_b200.c (device CG, Hessian as a device matrix)", cg_iters, cg_done, cg_exit,
+         steps, warm, ms, 1e3 / ms, t_set / steps, t_solves / steps, t_solves / steps / 2., t_spmv / steps, t_tr / steps, h2d, d2h);
+  return 0;
+}
+
+#endif

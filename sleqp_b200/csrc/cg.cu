@@ -88,7 +88,10 @@ k_cg_beta(double* S)
 struct b200_cg
 {
   b200_fact* fact = nullptr;
-  b200_mat* hess  = nullptr;
+  b200_mat* hess  = nullptr; // Hessian of the Lagrangian resident on the device, or
+  b200_hess_prod_fn hess_cb = nullptr; // ... a host callback (the reference's matrix-free SLEQP_FUNC_HESS_PROD, pub_func.h:168)
+  void* hess_ctx            = nullptr;
+  PinnedBuf<double> h_d, h_Bd; // staging of the callback mode
   int device      = 0;
   cudaStream_t stream = nullptr;
   int n = 0, N = 0;
@@ -154,7 +157,7 @@ extern "C" {
 int
 b200_cg_create(b200_cg** handle, b200_fact* fact, b200_mat* hess)
 {
-  if (!handle || !fact || !hess)
+  if (!handle || !fact)
   {
     return set_error(B200_ERR_ARG, "null argument");
   }
@@ -167,16 +170,31 @@ b200_cg_create(b200_cg** handle, b200_fact* fact, b200_mat* hess)
     C->device = b200_fact_device(fact); // everything of the CG lives next to the factorization it projects with
     B200_CUDA(cudaSetDevice(C->device));
     // Hessian products run on the factorization's stream: they alternate with its solves
-    int rc = b200_mat_set_stream(hess, (void*)C->stream);
-    if (rc != B200_OK)
+    if (hess)
     {
-      return rc;
+      int rc = b200_mat_set_stream(hess, (void*)C->stream);
+      if (rc != B200_OK)
+      {
+        return rc;
+      }
     }
     C->scal.reserve(16);
     C->h_scal.reserve(16);
     *handle = C.release();
     return (int)B200_OK;
   });
+}
+
+int
+b200_cg_set_hess_callback(b200_cg* C, b200_hess_prod_fn fn, void* ctx)
+{
+  if (!C)
+  {
+    return set_error(B200_ERR_ARG, "null handle");
+  }
+  C->hess_cb  = fn;
+  C->hess_ctx = ctx;
+  return B200_OK;
 }
 
 int
@@ -192,9 +210,39 @@ b200_cg_solve(b200_cg* C,
               int* iterations,
               int* termination)
 {
+  return b200_cg_solve_ex(C, n, nnz_g, g_idx, g_val, trust_radius, rel_tol, max_iter, step_out, iterations, termination, nullptr, nullptr, nullptr);
+}
+
+int
+b200_cg_solve_ex(b200_cg* C,
+                 int n,
+                 int nnz_g,
+                 const int* g_idx,
+                 const double* g_val,
+                 double trust_radius,
+                 double rel_tol,
+                 int max_iter,
+                 double* step_out,
+                 int* iterations,
+                 int* termination,
+                 double* tr_dual,
+                 double* min_rayleigh,
+                 double* max_rayleigh)
+{
   if (!C || !step_out || n <= 0 || nnz_g < 0 || nnz_g > n || (nnz_g > 0 && (!g_idx || !g_val)))
   {
     return set_error(B200_ERR_ARG, "bad argument");
+  }
+  if (!C->hess && !C->hess_cb)
+  {
+    return set_error(B200_ERR_STATE, "no Hessian: neither a device matrix nor a host callback is set");
+  }
+  // steihaug_solver.c:234-235, 246: both Rayleigh bounds start at 1, the dual of the trust region is only set on the
+  // boundary exit
+  double ray_min = 1.0, ray_max = 1.0;
+  if (tr_dual)
+  {
+    *tr_dual = NAN; // "not computed" (the reference: SLEQP_NONE); the glue translates
   }
   b200_stats st;
   int rc = b200_fact_stats(C->fact, &st);
@@ -240,6 +288,33 @@ b200_cg_solve(b200_cg* C,
     double* r = C->rfull.p;
     double* g = C->gfull.p;
     auto project = [&]() -> int { return b200_fact_solve_device(C->fact, C->rfull.p, C->gfull.p); };
+    // out = H v: a device SpMV, or -- matrix-free Hessians -- one round trip through the host callback
+    auto hess_prod = [&](const double* v_dev, double* out_dev) -> int {
+      if (C->hess)
+      {
+        return b200_mat_mult_vec_device(C->hess, v_dev, out_dev);
+      }
+      C->h_d.reserve((size_t)n);
+      C->h_Bd.reserve((size_t)n);
+      B200_CUDA(cudaMemcpyAsync(C->h_d.p, v_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+      B200_CUDA(cudaStreamSynchronize(s));
+      if (C->hess_cb(C->hess_ctx, n, C->h_d.p, C->h_Bd.p) != 0)
+      {
+        return set_error(B200_ERR_ARG, "Hessian callback failed");
+      }
+      B200_CUDA(cudaMemcpyAsync(out_dev, C->h_Bd.p, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+      return (int)B200_OK;
+    };
+    auto report_rayleigh = [&]() {
+      if (min_rayleigh)
+      {
+        *min_rayleigh = ray_min;
+      }
+      if (max_rayleigh)
+      {
+        *max_rayleigh = ray_max;
+      }
+    };
     auto finish  = [&](const double* p_dev, int iters, int term) {
       if (p_dev)
       {
@@ -259,6 +334,32 @@ b200_cg_solve(b200_cg* C,
       {
         *termination = term;
       }
+      report_rayleigh();
+      return (int)B200_OK;
+    };
+    // dual of the trust-region constraint on the boundary exit (steihaug_tr_dual, steihaug_solver.c:187-221):
+    // max(0, -(p^T H p + p^T grad)) / radius^2 with one more Hessian product
+    auto boundary_dual = [&](const double* p_dev, double* scratch_grad, double* scratch_Hp) -> int {
+      if (!tr_dual)
+      {
+        return (int)B200_OK;
+      }
+      int hrc = hess_prod(p_dev, scratch_Hp);
+      if (hrc != B200_OK)
+      {
+        return hrc;
+      }
+      B200_CUDA(cudaMemsetAsync(scratch_grad, 0, sizeof(double) * (size_t)n, s));
+      if (nnz_g > 0)
+      {
+        LaunchCounter lc;
+        enqueue_scatter_rhs(scratch_grad, n, nnz_g, C->g_idx.p, 0, C->g_val.p, s, lc);
+      }
+      double a[3], b[3];
+      dot3(C, p_dev, scratch_Hp, a);
+      dot3(C, p_dev, scratch_grad, b);
+      const double comb = a[0] + b[0];
+      *tr_dual          = comb < 0 ? -comb / (trust_radius * trust_radius) : 0.0;
       return (int)B200_OK;
     };
 
@@ -311,7 +412,7 @@ b200_cg_solve(b200_cg* C,
         return finish(z_cur, it, B200_CG_INTERIOR);
       }
       B200_CUDA(cudaMemsetAsync(S, 0, 9 * sizeof(double), s));
-      int hrc = b200_mat_mult_vec_device(C->hess, d_cur, C->Bd.p); //          (:339)
+      int hrc = hess_prod(d_cur, C->Bd.p); //                                   (:339)
       if (hrc != B200_OK)
       {
         return hrc;
@@ -334,6 +435,11 @@ b200_cg_solve(b200_cg* C,
       B200_CUDA(cudaStreamSynchronize(s));
       const double dBd = C->h_scal.p[0], d_nrm_sq = C->h_scal.p[1];
       const double z_next_nrm_sq = C->h_scal.p[4], r_dot_g_new = C->h_scal.p[6];
+      if (d_nrm_sq != 0.) // steihaug_collect_rayleigh (:150-173), right after the Hessian product (:345)
+      {
+        ray_min = std::min(ray_min, dBd / d_nrm_sq);
+        ray_max = std::max(ray_max, dBd / d_nrm_sq);
+      }
       if (dBd <= 0.0) // negative curvature                                  (:349-402)
       {
         double zs[3];
@@ -368,6 +474,11 @@ b200_cg_solve(b200_cg* C,
         const double inner  = prev_dot_d * prev_dot_d - d_norm * d_norm * (p_norm * p_norm - trust_radius * trust_radius);
         const double factor = 1. / (d_norm * d_norm) * (-prev_dot_d + std::sqrt(inner));
         axpby(C, 1.0, z_cur, factor, d_cur, z_new);
+        int drc = boundary_dual(z_new, d_new, C->Bd.p); // d_new / Bd: scratch from here on
+        if (drc != B200_OK)
+        {
+          return drc;
+        }
         return finish(z_new, it, B200_CG_BOUNDARY);
       }
       std::swap(z_cur, z_new);
@@ -390,7 +501,10 @@ b200_cg_free(b200_cg** handle)
   {
     cudaStreamSynchronize(C->stream);
   }
-  b200_mat_set_stream(C->hess, nullptr);
+  if (C->hess)
+  {
+    b200_mat_set_stream(C->hess, nullptr);
+  }
   delete C;
   *handle = nullptr;
   return B200_OK;

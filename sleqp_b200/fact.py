@@ -276,10 +276,36 @@ class ProjectedCG:
 
     INTERIOR, BOUNDARY, NEG_CURVATURE, MAX_ITER = range(4)
 
-    def __init__(self, fact: Fact, hess: Mat):
+    HESS_PROD = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, _dp, _dp)
+
+    def __init__(self, fact: Fact, hess: Mat | None = None, hess_prod=None):
+        """hess: the Hessian of the Lagrangian as a device matrix, or hess_prod: a host function d -> H d (the
+        reference's matrix-free SLEQP_FUNC_HESS_PROD callback)."""
         self._h = C.c_void_p()
         self._fact, self._hess = fact, hess  # keep the borrowed handles alive
-        check(lib().b200_cg_create(C.byref(self._h), fact._h, hess._h))
+        check(lib().b200_cg_create(C.byref(self._h), fact._h, hess._h if hess is not None else None))
+        self._cb = None
+        if hess is None:
+            def _cb(_ctx, n, d, out):
+                try:
+                    np.ctypeslib.as_array(out, shape=(n,))[:] = hess_prod(np.ctypeslib.as_array(d, shape=(n,)))
+                    return 0
+                except Exception:  # noqa: BLE001
+                    return 1
+
+            self._cb = self.HESS_PROD(_cb)
+            check(lib().b200_cg_set_hess_callback(self._h, C.cast(self._cb, C.c_void_p), None))
+
+    def solve_ex(self, n, g_idx, g_val, trust_radius, rel_tol=1e-8, max_iter=100):
+        """Returns (step[n], iterations, termination, tr_dual, min_rayleigh, max_rayleigh): everything
+        SleqpTRCallbacks.solve / .rayleigh hand back (tr/tr_types.h:9-30)."""
+        g_idx, g_val = _i32(g_idx), _f64(g_val)
+        step = np.empty(int(n), dtype=np.float64)
+        it, term = C.c_int(), C.c_int()
+        dual, rmin, rmax = C.c_double(), C.c_double(), C.c_double()
+        check(lib().b200_cg_solve_ex(self._h, int(n), int(len(g_idx)), _pi(g_idx), _pd(g_val), float(trust_radius), float(rel_tol),
+                                     int(max_iter), _pd(step), C.byref(it), C.byref(term), C.byref(dual), C.byref(rmin), C.byref(rmax)))
+        return step, it.value, term.value, dual.value, rmin.value, rmax.value
 
     def solve(self, n, g_idx, g_val, trust_radius, rel_tol=1e-8, max_iter=100):
         """Returns (step[n], iterations, termination)."""

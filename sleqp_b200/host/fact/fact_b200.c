@@ -22,11 +22,85 @@
 #include "error.h"
 #include "mem.h"
 
+// Page-locked caller buffers. The aug_jac reuses a handful of SleqpVec objects for its right-hand sides and
+// solutions (standard_aug_jac.c:306-435): their data / indices arrays are registered with the CUDA driver once, so
+// that the device library DMAs straight from / into them (b200_host_pin; a pageable buffer costs a staging copy and,
+// for solutions, a host pass over the slice). A vector that has been reallocated since (sleqp_vec_reserve) shows up
+// as a new pointer: whatever overlapped the new range is released first.
+#define B200_MAX_PINNED 16
+
+typedef struct
+{
+  char* ptr;
+  size_t bytes;
+} B200Pinned;
+
 typedef struct
 {
   b200_fact* handle;
   int num_rows;
+  B200Pinned pinned[B200_MAX_PINNED];
+  int num_pinned;
+  int next_evict;
 } B200Data;
+
+// handle of the factorization that last ran set_matrix on this thread (one SleqpFact per solver thread,
+// src/test/thread_test.c:92-110): what a B200 trust-region solver created without an explicit handle projects with
+static _Thread_local b200_fact* last_handle = NULL;
+
+b200_fact*
+sleqp_fact_b200_last_handle(void)
+{
+  return last_handle;
+}
+
+static void
+pin_buffer(B200Data* data, const void* buffer, size_t bytes)
+{
+  char* ptr = (char*)buffer;
+
+  if (!ptr || bytes < (1 << 16)) // small vectors: the staging copy is cheaper than a registration
+  {
+    return;
+  }
+
+  for (int i = 0; i < data->num_pinned; ++i)
+  {
+    if (data->pinned[i].ptr == ptr && data->pinned[i].bytes >= bytes)
+    {
+      return;
+    }
+  }
+
+  // release whatever overlaps the new range (stale registrations of reallocated vectors)
+  for (int i = 0; i < data->num_pinned;)
+  {
+    B200Pinned* reg = data->pinned + i;
+
+    if (reg->ptr < ptr + bytes && ptr < reg->ptr + reg->bytes)
+    {
+      b200_host_unpin(reg->ptr);
+      *reg = data->pinned[--data->num_pinned];
+    }
+    else
+    {
+      ++i;
+    }
+  }
+
+  if (data->num_pinned == B200_MAX_PINNED)
+  {
+    B200Pinned* reg = data->pinned + (data->next_evict++ % B200_MAX_PINNED);
+    b200_host_unpin(reg->ptr);
+    *reg = data->pinned[--data->num_pinned];
+  }
+
+  // failure is not an error: the library falls back to its own staging buffer for pageable memory
+  if (b200_host_pin(ptr, bytes) == B200_OK)
+  {
+    data->pinned[data->num_pinned++] = (B200Pinned){ptr, bytes};
+  }
+}
 
 #define B200_CALL(x)                                                           \
   do                                                                           \
@@ -64,6 +138,8 @@ b200_set_matrix(void* fact_data, SleqpMat* matrix)
 
   data->num_rows = num_rows;
 
+  last_handle = data->handle;
+
   return SLEQP_OKAY;
 }
 
@@ -76,6 +152,8 @@ b200_solve(void* fact_data, const SleqpVec* rhs)
 
   // sparse right-hand side goes over as-is; the scatter into the zeroed dense vector
   // (set_cache / reset_cache, fact_umfpack.c:185-205) happens on the device
+  pin_buffer(data, rhs->data, sizeof(double) * (size_t)rhs->nnz_max);
+
   B200_CALL(
     b200_fact_solve(data->handle, rhs->nnz, rhs->indices, rhs->data, rhs->dim));
 
@@ -93,11 +171,30 @@ b200_solution(void* fact_data,
 
   assert(begin <= end);
 
-  const double* values = NULL;
+  // What sleqp_vec_set_from_raw (vec.c:72-104) would build from the dense slice, built on the device instead:
+  // the entries with |v| > zero_eps in ascending order are written straight into the (page-locked) arrays of `sol`.
+  // The arrays are reserved at full length because the device copies them at full length (one synchronisation
+  // serves the count and the data).
+  const int dim = end - begin;
 
-  B200_CALL(b200_fact_solution_ptr(data->handle, begin, end, &values));
+  SLEQP_CALL(sleqp_vec_clear(sol));
+  SLEQP_CALL(sleqp_vec_resize(sol, dim));
+  SLEQP_CALL(sleqp_vec_reserve(sol, dim));
 
-  SLEQP_CALL(sleqp_vec_set_from_raw(sol, values, end - begin, zero_eps));
+  pin_buffer(data, sol->data, sizeof(double) * (size_t)sol->nnz_max);
+  pin_buffer(data, sol->indices, sizeof(int) * (size_t)sol->nnz_max);
+
+  int nnz = 0;
+
+  B200_CALL(b200_fact_solution_sparse(data->handle,
+                                      begin,
+                                      end,
+                                      zero_eps,
+                                      sol->indices,
+                                      sol->data,
+                                      &nnz));
+
+  sol->nnz = nnz;
 
   return SLEQP_OKAY;
 }
@@ -125,6 +222,16 @@ b200_free(void** star)
   if (!data)
   {
     return SLEQP_OKAY;
+  }
+
+  for (int i = 0; i < data->num_pinned; ++i)
+  {
+    b200_host_unpin(data->pinned[i].ptr);
+  }
+
+  if (last_handle == data->handle)
+  {
+    last_handle = NULL;
   }
 
   B200_CALL(b200_fact_free(&data->handle));

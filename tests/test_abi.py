@@ -39,6 +39,6 @@ def test_no_cpu_fallback():
 
 
 def test_host_glue_is_c11_and_names_the_reference_interface():
-    src = open(os.path.join(ROOT, "sleqp_b200", "host", "fact_b200.c")).read()
+    src = open(os.path.join(ROOT, "sleqp_b200", "host", "fact", "fact_b200.c")).read()
     for needle in ("sleqp_fact_create_default", "SLEQP_FACT_FLAGS_LOWER", ".set_matrix", ".solve", ".solution", ".condition", ".free", "sleqp_vec_set_from_raw"):
         assert needle in src

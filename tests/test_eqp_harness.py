@@ -60,6 +60,33 @@ def test_b200_backend_reproduces_reference_eqp_iterates(golden, case):
     assert got["backend"][0] == 2  # SLEQP_FACT_FLAGS_LOWER
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("hess", ["callback", "matrix"])
+@pytest.mark.parametrize("case", list(CASES))
+def test_b200_tr_solver_plugin_reproduces_reference_steihaug(golden, case, hess):
+    """host/tr/tr_b200.c registered through the reference's own tr_solver.c (sleqp_tr_solver_create /
+    _solve / _current_rayleigh) over fact_b200.c, against what the reference's Steihaug solver computed over the
+    reference LAPACK backend: steps, the dual of the trust region and the Rayleigh bounds, to 1e-8. Both Hessian modes:
+    the reference's matrix-free callback (sleqp_problem_hess_prod on the host) and a device matrix."""
+    if not os.path.exists(os.path.join(REF, "eqp_harness_b200tr")):
+        pytest.skip("oracle/_ref/eqp_harness_b200tr not shipped")
+    want = golden(CASES[case][1])
+    out = subprocess.run([os.path.join(REF, "eqp_harness_b200tr"), *CASES[case][0], hess], check=True, capture_output=True, text=True, timeout=600)
+    got = {}
+    for line in out.stdout.splitlines():
+        parts = line.split()
+        got[parts[0]] = np.array(parts[2:], dtype=np.float64)
+    assert "B200" in out.stderr
+    _compare(got, {k: want[k] for k in want.files}, 1e-8)
+    assert any(k.startswith("tr_info_") for k in want.files)
+
+
+def _check_tr_info(info, want, tol=1e-8):
+    """(tr_dual, min_rayleigh, max_rayleigh) as sleqp_tr_solver_solve / _current_rayleigh returned them."""
+    got = np.array([info["tr_dual"], info["min_rayleigh"], info["max_rayleigh"]])
+    assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max()), (got, want)
+
+
 def _harness_setup(case="chain_n400"):
     from sleqp_b200 import problems
 
@@ -85,15 +112,20 @@ def test_oracle_cg_restatement_matches_reference_fixture(golden, case):
 
     # the projection and the objective gradient themselves
     assert np.abs(project(grad) - want["project_nullspace"]).max() <= 1e-9 * np.abs(want["project_nullspace"]).max()
-    step, it, how = orc.steihaug_projected_cg(project, lambda d: H @ d, grad, 1e8, 1e-4, 4 * N)
+    info = {}
+    step, it, how = orc.steihaug_projected_cg(project, lambda d: H @ d, grad, 1e8, 1e-4, 4 * N, info)
     assert how == "interior" and it > 10
     assert np.abs(step - want["cg_converged_step"]).max() <= 1e-8 * max(1.0, np.abs(want["cg_converged_step"]).max())
+    _check_tr_info(info, want["tr_info_converged"])
+    assert want["tr_info_converged"][0] == -1.0  # SLEQP_NONE: no dual of the trust region on an interior exit
     full = np.linalg.norm(want["cg_converged_step"])
     for i in range(RADII):
         radius = full * (0.6 + 0.4 * (i + 0.5) / RADII)
-        s, _, how = orc.steihaug_projected_cg(project, lambda d: H @ d, grad, radius, 1e-4, 4 * N)
+        s, _, how = orc.steihaug_projected_cg(project, lambda d: H @ d, grad, radius, 1e-4, 4 * N, info)
         assert how == "boundary"
         assert np.abs(s - want[f"cg_path_sample_{i}"]).max() <= 1e-8 * max(1.0, np.abs(want[f"cg_path_sample_{i}"]).max())
+        _check_tr_info(info, want[f"tr_info_{i}"])
+        assert want[f"tr_info_{i}"][0] >= 0.0
 
 
 @pytest.mark.gpu
@@ -113,17 +145,27 @@ def test_device_resident_projected_cg_matches_reference_iterates(golden, case):
     mh.set(p.n, p.n, H.indptr, H.indices, H.data)
     cg = ProjectedCG(f, mh)
     gi = np.arange(p.n, dtype=np.int32)
-    step, it, how = cg.solve(p.n, gi, grad, 1e8, 1e-4, 4 * N)
+    step, it, how, dual, rmin, rmax = cg.solve_ex(p.n, gi, grad, 1e8, 1e-4, 4 * N)
     assert how == ProjectedCG.INTERIOR and it > 10
     ref = want["cg_converged_step"]
     assert np.abs(step - ref).max() <= 1e-8 * max(1.0, np.abs(ref).max())
+    assert np.isnan(dual)  # not computed on an interior exit (the glue leaves SLEQP_NONE)
+    _check_tr_info(dict(tr_dual=-1.0, min_rayleigh=rmin, max_rayleigh=rmax), want["tr_info_converged"])
     full = np.linalg.norm(ref)
     for i in range(RADII):
         radius = full * (0.6 + 0.4 * (i + 0.5) / RADII)
-        s, _, how = cg.solve(p.n, gi, grad, radius, 1e-4, 4 * N)
+        s, _, how, dual, rmin, rmax = cg.solve_ex(p.n, gi, grad, radius, 1e-4, 4 * N)
         assert how == ProjectedCG.BOUNDARY
         ref = want[f"cg_path_sample_{i}"]
         assert np.abs(s - ref).max() <= 1e-8 * max(1.0, np.abs(ref).max()), i
+        _check_tr_info(dict(tr_dual=dual, min_rayleigh=rmin, max_rayleigh=rmax), want[f"tr_info_{i}"])
+    # matrix-free Hessian (the reference's callback): same iterates with the products done on the host
+    Hs = p.H.tocsr()
+    cgf = ProjectedCG(f, None, hess_prod=lambda d: Hs @ d)
+    s2, it2, how2, _, rmin2, rmax2 = cgf.solve_ex(p.n, gi, grad, 1e8, 1e-4, 4 * N)
+    assert how2 == ProjectedCG.INTERIOR and it2 == it
+    assert np.abs(s2 - step).max() <= 1e-8 * max(1.0, np.abs(step).max())
+    cgf.release()
     # iteration cap: zero step, like the reference
     s, it, how = cg.solve(p.n, gi, grad, 1e8, 1e-4, 3)
     assert how == ProjectedCG.MAX_ITER and it == 3 and not s.any()
