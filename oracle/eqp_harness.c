@@ -542,6 +542,10 @@ main(int argc, char** argv)
 
 #include "sparse/mat.h"
 
+#ifdef HARNESS_B200_TR
+#include "sparse/mat_b200.h"
+#endif
+
 static double
 now_ms(void)
 {
@@ -551,13 +555,15 @@ now_ms(void)
 }
 
 /*
- * usage: eqp_step_b200 <chain|poisson|poisson3> <size> <cg_iters> <steps> [steihaug]
+ * usage: eqp_step_b200 <chain|poisson|poisson3> <size> <cg_iters> <steps> [steihaug] [hostspmv]
  *
  * One step = what SLEQP does between the Cauchy step and the trial point, every call a reference
  * function on host data:
  *   sleqp_aug_jac_set_iterate    host fill_aug_jac (standard_aug_jac.c:135-237) + SleqpFact.set_matrix + condition
  *   sleqp_aug_jac_solve_min_norm, sleqp_aug_jac_solve_lsq
- *   sleqp_mat_mult_vec_trans (sparse multipliers, newton.c:377), sleqp_mat_mult_vec (direction.c:66)
+ *   J^T v (sparse multipliers, newton.c:377) and J x (direction.c:66) through the shipped SpMV glue sparse/mat_b200.c
+ *   (mirror refreshed once per step, like the Jacobian of a new iterate), or with "hostspmv" the reference's own
+ *   sleqp_mat_mult_vec_trans / sleqp_mat_mult_vec -- whose transposed product is quadratic (mat.c:329-331)
  *   sleqp_tr_solver_solve capped at <cg_iters> iterations: the B200 TR solver (device CG, Hessian as a matrix), or with
  *   the 5th argument the reference's own Steihaug solver over the B200 factorization (one boundary crossing per iteration)
  * Prints one JSON line.
@@ -570,6 +576,7 @@ main(int argc, char** argv)
   const int cg_iters = argc > 3 ? atoi(argv[3]) : 30;
   const int steps    = argc > 4 ? atoi(argv[4]) : 5;
   const bool steihaug = argc > 5 && argv[5][0] == 's';
+  const bool hostspmv = (argc > 5 && argv[5][0] == 'h') || (argc > 6 && argv[6][0] == 'h');
   Setup S;
   // working sets like sleqp_b200/problems.py: chain = every constraint, poisson = every constraint + 10 % of the controls
   setup_problem(&S, kind, size, kind[0] == 'p' ? 10 : 0);
@@ -618,6 +625,14 @@ main(int argc, char** argv)
   create_tr_solver(&tr, &S, hessian);
 #endif
 
+#ifdef HARNESS_B200_TR
+  SleqpMatB200* mirror = NULL;
+  if (!hostspmv)
+  {
+    CHECK(sleqp_mat_b200_create(&mirror));
+  }
+#endif
+
   double t_set = 0., t_solves = 0., t_spmv = 0., t_tr = 0., t_total = 0.;
   double tr_dual = 0.;
   const int warm = 2;
@@ -629,8 +644,19 @@ main(int argc, char** argv)
     CHECK(sleqp_aug_jac_solve_min_norm(S.jac, minnorm_rhs, minnorm));
     CHECK(sleqp_aug_jac_solve_lsq(S.jac, grad, duals));
     const double t2 = now_ms();
-    CHECK(sleqp_mat_mult_vec_trans(J, viol, 0., jtv));
-    CHECK(sleqp_mat_mult_vec(J, xfull, jx));
+#ifdef HARNESS_B200_TR
+    if (mirror)
+    {
+      CHECK(sleqp_mat_b200_update(mirror, J)); // the Jacobian of this iterate goes to the device once
+      CHECK(sleqp_mat_b200_mult_vec_trans(mirror, viol, 0., jtv));
+      CHECK(sleqp_mat_b200_mult_vec(mirror, xfull, jx));
+    }
+    else
+#endif
+    {
+      CHECK(sleqp_mat_mult_vec_trans(J, viol, 0., jtv));
+      CHECK(sleqp_mat_mult_vec(J, xfull, jx));
+    }
     const double t3 = now_ms();
     CHECK(sleqp_tr_solver_solve(tr, S.jac, cons_dual, grad, step, 1e8, &tr_dual));
     const double t4 = now_ms();
@@ -665,10 +691,12 @@ main(int argc, char** argv)
   printf("{\"driver\": \"eqp_step (reference aug_jac/TR code over the B200 glue)\", \"problem\": \"%s\", \"size\": %d, \"n\": %d, \"m\": %d, "
          "\"ws_size\": %d, \"N\": %d, \"backend\": \"%s\", \"tr_solver\": \"%s\", \"cg_iters_cap\": %d, \"cg_iterations\": %d, \"cg_exit\": %d, "
          "\"steps\": %d, \"warmup\": %d, \"ms_per_step\": %.6f, \"iters_per_s\": %.6f, \"set_iterate_ms\": %.6f, \"two_solves_ms\": %.6f, "
-         "\"solve_ms\": %.6f, \"host_spmv_ms\": %.6f, \"tr_solve_ms\": %.6f, \"h2d_bytes_per_step\": %lld, \"d2h_bytes_per_step\": %lld}\n",
+         "\"solve_ms\": %.6f, \"spmv\": \"%s\", \"jac_products_ms\": %.6f, \"tr_solve_ms\": %.6f, \"h2d_bytes_per_step\": %lld, \"d2h_bytes_per_step\": %lld}\n",
          kind, size, n, m, ws_size, n + ws_size, sleqp_fact_name(S.fact),
          steihaug ? "reference steihaug_solver.c over SleqpFact B200" : "tr_b200.c (device CG, Hessian as a device matrix)", cg_iters, cg_done, cg_exit,
-         steps, warm, ms, 1e3 / ms, t_set / steps, t_solves / steps, t_solves / steps / 2., t_spmv / steps, t_tr / steps, h2d, d2h);
+         steps, warm, ms, 1e3 / ms, t_set / steps, t_solves / steps, t_solves / steps / 2.,
+         hostspmv ? "reference sleqp_mat_mult_vec(_trans) on the host" : "sparse/mat_b200.c (device mirror, refreshed every step)", t_spmv / steps, t_tr / steps,
+         h2d + (hostspmv ? 0 : 12LL * sleqp_mat_nnz(J) + 12LL * n + 12LL * (m / 100 + 1)), d2h + (hostspmv ? 0 : 8LL * n + 8LL * m));
   return 0;
 }
 

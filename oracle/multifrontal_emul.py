@@ -15,6 +15,11 @@ from __future__ import annotations
 import numpy as np
 
 NB, RB, TILE, EA_COLS = 32, 128, 64, 4
+
+
+def _ld(h):
+    """Leading dimension of a column-major panel: the front height rounded up to even (plan.hpp panel_ld)."""
+    return (h + 1) & ~1
 UPD_INPANEL, UPD_SCHUR, UPD_DIAGCOPY = 0, 1, 2
 
 
@@ -41,8 +46,8 @@ class Emulated:
     def panel(self, T):
         """h x k column-major view of supernode T's panel."""
         f, k, r, h = self._geom(T)
-        o = int(self.p["Lptr"][T])
-        return self.L[o : o + h * k].reshape((k, h)).T
+        o, ld = int(self.p["Lptr"][T]), _ld(h)
+        return self.L[o : o + ld * k].reshape((k, ld)).T[:h]
 
     def umat(self, T):
         f, k, r, h = self._geom(T)
@@ -108,8 +113,8 @@ class Emulated:
     # ---------------------------------------------------------------- selective inversion
     def mpanel(self, T):
         f, k, r, h = self._geom(T)
-        o = int(self.p["Lptr"][T])
-        return self.Mt[o : o + h * k].reshape((k, h)).T
+        o, ld = int(self.p["Lptr"][T]), _ld(h)
+        return self.Mt[o : o + ld * k].reshape((k, ld)).T[:h]
 
     def _invert(self):
         """Minv = [L11^-1; -L21 L11^-1] per supernode, executed tile task by tile task."""
@@ -150,7 +155,7 @@ class Emulated:
             T, i0, j0 = int(T), int(i0), int(j0)
             f, k, r, h = self._geom(T)
             o = int(p["Lptr"][T])
-            src = self.Mt[o : o + h * k].reshape((k, h)).T  # h x k view of the column-major panel
+            src = self.Mt[o : o + _ld(h) * k].reshape((k, _ld(h))).T[:h]  # h x k view of the column-major panel
             dst = Mr[o : o + h * k].reshape((h, k))
             i1, j1 = min(h, i0 + 32), min(k, j0 + 32)
             dst[i0:i1, j0:j1] = src[i0:i1, j0:j1]

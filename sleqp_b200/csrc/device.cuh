@@ -152,7 +152,16 @@ struct SnMeta
   int parent;
   int child_begin;
   int child_end;
-  int pad0, pad1, pad2, pad3, pad4, pad5;
+  int ld;   // leading dimension of the column-major panels L / Mt (panel_ld(k + r))
+  int tmap; // index of the panel's TMA tensor map, -1: none (small fronts use the cp.async path)
+  int pad2, pad3, pad4, pad5;
+};
+
+// A TMA tensor map (CUtensorMap: 128 opaque bytes, 64-byte aligned) of one supernode's panel, encoded on the host
+// (fact.cu) and read by the copy engine through a generic address in global memory.
+struct alignas(64) PanelTensorMap
+{
+  unsigned long long opaque[16];
 };
 
 // Device copy of a Plan (per handle).
@@ -160,6 +169,7 @@ struct DevPlan
 {
   std::shared_ptr<const Plan> plan;
   DevBuf<SnMeta> sn;
+  DevBuf<PanelTensorMap> tmaps; // one per supernode with a front of at least TMA_MIN_FRONT rows (SnMeta::tmap)
   DevBuf<int> Ridx, rel, child_idx;
   // assembly
   DevBuf<long long> Sdest, Sterm_ptr, Sdiag;

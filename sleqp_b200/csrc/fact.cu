@@ -2,6 +2,8 @@
 // copy of the cached plan, the factor, and the solve workspaces. Host glue: ../host/fact_b200.c.
 #include "numeric.cuh"
 
+#include <cuda.h> // CUtensorMap and the cuTensorMapEncodeTiled prototype (resolved at run time, no link against libcuda)
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -160,6 +162,40 @@ guarded(F&& f)
   }
 }
 
+// 2-D tensor map of a column-major panel (h rows x k columns of doubles, leading dimension ld, even): boxes of
+// 16 x 16 elements in the 128-byte swizzle, rows / columns outside the panel read as zero.
+void
+encode_panel_map(PanelTensorMap* out, double* panel, int h, int k, int ld)
+{
+  typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiled encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    {
+      cudaGetLastError();
+      fn = nullptr;
+    }
+    return (EncodeTiled)fn;
+  }();
+  if (!encode)
+  {
+    throw CudaError("cuTensorMapEncodeTiled is not available from this driver");
+  }
+  static_assert(sizeof(PanelTensorMap) == sizeof(CUtensorMap), "CUtensorMap is 128 bytes");
+  const cuuint64_t dims[2]    = {(cuuint64_t)h, (cuuint64_t)k};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  const cuuint32_t box[2]     = {16, 16};
+  const cuuint32_t estr[2]    = {1, 1};
+  const CUresult rc = encode((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)panel, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS)
+  {
+    throw CudaError("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)rc) + " (h = " + std::to_string(h) + ", k = " + std::to_string(k) + ")");
+  }
+}
+
 void
 upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
 {
@@ -172,23 +208,6 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   F->drop_graphs();
   dp.plan.reset();
   F->factored = F->solved = false;
-  std::vector<SnMeta> meta((size_t)P.nsuper);
-  for (int T = 0; T < P.nsuper; ++T)
-  {
-    SnMeta& m     = meta[T];
-    m.Lptr        = P.Lptr[T];
-    m.Uoff        = P.Uoff[T];
-    m.Rptr        = P.Rptr[T];
-    m.Tptr        = P.Tptr[T];
-    m.first       = P.sn_first[T];
-    m.k           = P.sn_first[T + 1] - P.sn_first[T];
-    m.r           = (int)(P.Rptr[T + 1] - P.Rptr[T]);
-    m.parent      = P.sn_parent[T];
-    m.child_begin = P.child_ptr[T];
-    m.child_end   = P.child_ptr[T + 1];
-    m.pad0 = m.pad1 = m.pad2 = 0;
-  }
-  dp.sn.upload(meta, s);
   dp.Ridx.upload(P.Ridx, s);
   dp.rel.upload(P.rel, s);
   dp.child_idx.upload(P.child_idx, s);
@@ -265,6 +284,45 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   F->h_sol.reserve(N + 8);
   F->h_scal.reserve(8);
   F->h_nper.reserve(2);
+  std::vector<SnMeta> meta((size_t)P.nsuper);
+  for (int T = 0; T < P.nsuper; ++T)
+  {
+    SnMeta& m     = meta[T];
+    m.Lptr        = P.Lptr[T];
+    m.Uoff        = P.Uoff[T];
+    m.Rptr        = P.Rptr[T];
+    m.Tptr        = P.Tptr[T];
+    m.first       = P.sn_first[T];
+    m.k           = P.sn_first[T + 1] - P.sn_first[T];
+    m.r           = (int)(P.Rptr[T + 1] - P.Rptr[T]);
+    m.parent      = P.sn_parent[T];
+    m.child_begin = P.child_ptr[T];
+    m.child_end   = P.child_ptr[T + 1];
+    m.ld          = (int)panel_ld(m.k + m.r);
+    m.tmap        = -1;
+    m.pad2 = m.pad3 = m.pad4 = m.pad5 = 0;
+  }
+  // TMA tensor maps of the panels of large fronts (numeric.cu: tile_update_tma): L is allocated by now
+  {
+    const char* e       = std::getenv("B200_TMA_MIN_FRONT"); // tests lower it so that small fronts take the TMA path too
+    const int min_front = e ? std::max(1, std::atoi(e)) : TMA_MIN_FRONT;
+    std::vector<PanelTensorMap> maps;
+    for (int T = 0; T < P.nsuper; ++T)
+    {
+      SnMeta& m = meta[T];
+      if (m.k + m.r < min_front)
+      {
+        continue;
+      }
+      PanelTensorMap tm;
+      encode_panel_map(&tm, F->L.p + m.Lptr, m.k + m.r, m.k, m.ld);
+      m.tmap = (int)maps.size();
+      maps.push_back(tm);
+    }
+    dp.tmaps.upload(maps, s);
+    dp.sn.upload(meta, s);
+    B200_CUDA(cudaStreamSynchronize(s)); // `maps` and `meta` are locals
+  }
   dp.plan = plan;
 }
 

@@ -121,7 +121,7 @@ k_extend_add(const EaTask* __restrict__ tasks,
   const SnMeta p   = sn[c.parent];
   const int* rl    = rel + c.Rptr;
   const double* Uc = U + c.Uoff;
-  const int hp     = p.k + p.r;
+  const int hp     = p.ld;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = t.jb * EA_COLS + warp;
   if (j >= c.r)
@@ -206,6 +206,7 @@ k_panel(const PanelTask* __restrict__ tasks,
   const PanelTask t = tasks[blockIdx.x];
   const SnMeta s    = sn[t.sn];
   const int h       = s.k + s.r;
+  const int ld      = s.ld;
   const int c0      = t.t * NB;
   const int w       = min(NB, s.k - c0);
   double* P         = L + s.Lptr;
@@ -225,14 +226,14 @@ k_panel(const PanelTask* __restrict__ tasks,
       for (int k4 = 0; k4 < 8; ++k4)
       {
         const int row = r0 + mi * 8 + (lane >> 2), col = k4 * 4 + (lane & 3);
-        af[mi][k4]    = (row < h && col < w) ? P[(long long)(c0 + col) * h + row] : 0.0;
+        af[mi][k4]    = (row < h && col < w) ? P[(long long)(c0 + col) * ld + row] : 0.0;
       }
   }
 #pragma unroll
   for (int u = 0; u < EPT; ++u)
   {
     const int c   = warp + NWD * u;
-    A[lane][c]    = (lane < w && c <= lane) ? P[(long long)(c0 + c) * h + c0 + lane] : 0.0;
+    A[lane][c]    = (lane < w && c <= lane) ? P[(long long)(c0 + c) * ld + c0 + lane] : 0.0;
     Ainv[lane][c] = lane == c ? 1.0 : 0.0;
   }
   const double tau = scal[1];
@@ -300,7 +301,7 @@ k_panel(const PanelTask* __restrict__ tasks,
       const int c = warp + NWD * u;
       if (lane < w && c <= lane)
       {
-        M[(long long)(c0 + c) * h + c0 + lane] = Ainv[lane][c];
+        M[(long long)(c0 + c) * ld + c0 + lane] = Ainv[lane][c];
       }
     }
   }
@@ -351,7 +352,7 @@ k_panel(const PanelTask* __restrict__ tasks,
         const int row = r0 + mi * 8 + (lane >> 2), col = nj * 8 + 2 * (lane & 3) + e;
         if (row < h && col < w)
         {
-          P[(long long)(c0 + col) * h + row] = acc[mi][nj][e];
+          P[(long long)(c0 + col) * ld + row] = acc[mi][nj][e];
         }
       }
 }
@@ -545,24 +546,261 @@ tile_update(const double* __restrict__ P,
       }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA variant of the tile update for large fronts: the operand tiles are fetched by the copy engine
+// (cp.async.bulk.tensor, SASS UTMALDG) straight from the column-major panel through a per-supernode tensor map --
+// one elected thread issues eight 16 x 16 boxes per k-chunk and arms an mbarrier with the byte count; nobody computes
+// addresses or predicates per element, rows beyond the front are zero-filled by the hardware. The boxes land in shared
+// memory in the 128-byte swizzle (dense, no padding: 16 KB per stage instead of 17.4 KB): element (kk, r) of a box
+// sits at kk * 128 B + ((r / 2) ^ (kk % 8)) * 16 B + (r % 2) * 8 B. A DMMA fragment takes 8 rows x 4 consecutive kk; with
+// the rows of a fragment chosen as {0,1,8,9,2,3,10,11} (+4 for the second fragment of a box) the 16 lanes of a half
+// warp hit 16 different 8-byte slots of the 128-byte bank window: conflict-free without padding.
+constexpr int TMA_BOX         = 16;                              // rows and columns of one box
+constexpr int TMA_BOX_DOUBLES = TMA_BOX * KC;                    // 2 KB
+constexpr int TMA_STAGE_DOUBLES = 2 * (TILE / TMA_BOX) * TMA_BOX_DOUBLES; // A and B boxes of one stage: 16 KB
+static_assert(KC == 16 && TMA_BOX * sizeof(double) == 128, "one box row is one 128-byte swizzle span");
+static_assert(sizeof(double) * (STAGES * (TMA_STAGE_DOUBLES + KC)) + 8 * STAGES + 1024 <= TILE_SMEM, "the TMA layout fits the same allocation");
+
+__device__ __forceinline__ unsigned
+smem_u32(const void* p)
+{
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void
+mbar_init(unsigned bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_wait(unsigned bar, unsigned parity)
+{
+  asm volatile("{\n"
+               ".reg .pred P1;\n"
+               "LAB_WAIT:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+               "@P1 bra DONE;\n"
+               "bra LAB_WAIT;\n"
+               "DONE:\n"
+               "}\n" ::"r"(bar),
+               "r"(parity)
+               : "memory");
+}
+
+// one 16 x 16 box of the panel: rows [row, row + 16) x columns [col, col + 16) -> dst (1 KB aligned), completion on bar
+__device__ __forceinline__ void
+tma_load_box(unsigned dst, const void* tmap, int row, int col, unsigned bar)
+{
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst), "l"(tmap), "r"(row), "r"(col),
+               "r"(bar)
+               : "memory");
+}
+
+// row inside a 16-row box of lane group g (0..7) for fragment f (0..1): {0,1,8,9,2,3,10,11} + 4 f
+__device__ __forceinline__ int
+frag_row(int f, int g)
+{
+  return (g & 1) + 8 * ((g >> 1) & 1) + 2 * (g >> 2) + 4 * f;
+}
+
+// offset (doubles) of element (kk, r) inside a swizzled box
+__device__ __forceinline__ int
+swz(int kk, int r)
+{
+  return kk * TMA_BOX + ((((r >> 1) ^ (kk & 7)) << 1) | (r & 1));
+}
+
+__device__ __forceinline__ void
+tile_update_tma(const void* __restrict__ tmap,
+                int kb,
+                int ke,
+                const double* __restrict__ d,
+                int ra0,
+                int na,
+                int rb0,
+                int nb,
+                double* __restrict__ C,
+                long long ldc,
+                int gi0,
+                int gj0,
+                bool accumulate,
+                double* smem_raw)
+{
+  // 1 KB alignment of the swizzle atoms
+  double* base          = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  double* dsm           = base + STAGES * TMA_STAGE_DOUBLES;                       // [STAGES][KC]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(dsm + STAGES * KC); // [STAGES]
+  const int tid  = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wy = warp >> 1, wx = warp & 1;
+  const bool active = (gi0 + wy * 32 + 31) >= (gj0 + wx * 32);
+  if (tid == 0)
+  {
+#pragma unroll
+    for (int st = 0; st < STAGES; ++st)
+    {
+      mbar_init(smem_u32(bars + st), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+    {
+      acc[a][b][0] = 0.0;
+      acc[a][b][1] = 0.0;
+    }
+  const int nchunks = (ke - kb + KC - 1) / KC;
+  auto issue = [&](int c, int st) {
+    const int kc = kb + c * KC;
+    if (tid == 0)
+    {
+      // the stage was read through the generic proxy before the barrier the caller just passed
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      const unsigned bar = smem_u32(bars + st);
+      mbar_expect_tx(bar, (unsigned)(TMA_STAGE_DOUBLES * sizeof(double)));
+      const unsigned dst = smem_u32(base + st * TMA_STAGE_DOUBLES);
+#pragma unroll
+      for (int q = 0; q < TILE / TMA_BOX; ++q)
+      {
+        tma_load_box(dst + q * TMA_BOX_DOUBLES * 8, tmap, ra0 + q * TMA_BOX, kc, bar);
+        tma_load_box(dst + (TILE / TMA_BOX + q) * TMA_BOX_DOUBLES * 8, tmap, rb0 + q * TMA_BOX, kc, bar);
+      }
+    }
+    if (tid < KC)
+    {
+      const int col = kc + tid;
+      cp_async8(dsm + st * KC + tid, d + (col < ke ? col : kb), col < ke); // zero beyond ke: those columns do not count
+    }
+  };
+#pragma unroll
+  for (int c = 0; c < STAGES - 1; ++c)
+  {
+    if (c < nchunks)
+    {
+      issue(c, c);
+    }
+    cp_async_commit();
+  }
+  for (int c = 0; c < nchunks; ++c)
+  {
+    const int st = c % STAGES;
+    cp_async_wait<STAGES - 2>();
+    mbar_wait(smem_u32(bars + st), (unsigned)((c / STAGES) & 1));
+    __syncthreads(); // the pivots of everybody's copies; and stage (c - 1) % STAGES is free again
+    if (c + STAGES - 1 < nchunks)
+    {
+      issue(c + STAGES - 1, (c + STAGES - 1) % STAGES);
+    }
+    cp_async_commit();
+    if (active)
+    {
+      const double* As = base + st * TMA_STAGE_DOUBLES;
+      const double* Bs = As + (TILE / TMA_BOX) * TMA_BOX_DOUBLES;
+      const double* dsc = dsm + st * KC;
+#pragma unroll
+      for (int k4 = 0; k4 < KC / 4; ++k4)
+      {
+        const int kr   = k4 * 4 + (lane & 3);
+        const double dk = dsc[kr];
+        double af[4], bf[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+        {
+          const int r = frag_row(a & 1, lane >> 2);
+          af[a]       = As[(wy * 2 + (a >> 1)) * TMA_BOX_DOUBLES + swz(kr, r)];
+          bf[a]       = Bs[(wx * 2 + (a >> 1)) * TMA_BOX_DOUBLES + swz(kr, r)] * dk;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+          {
+            dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+          }
+      }
+    }
+  }
+  if (!active)
+  {
+    return;
+  }
+  // epilogue (two phases, like tile_update); rows and columns follow the fragment permutation
+  double cv[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+      {
+        const int i = wy * 32 + (a >> 1) * 16 + frag_row(a & 1, lane >> 2);
+        const int j = wx * 32 + (b >> 1) * 16 + frag_row(b & 1, 2 * (lane & 3) + e);
+        const bool ok = i < na && j < nb && gi0 + i >= gj0 + j;
+        cv[a][b][e]   = (ok && accumulate) ? C[i + (long long)j * ldc] : 0.0;
+      }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+      {
+        const int i = wy * 32 + (a >> 1) * 16 + frag_row(a & 1, lane >> 2);
+        const int j = wx * 32 + (b >> 1) * 16 + frag_row(b & 1, 2 * (lane & 3) + e);
+        if (i < na && j < nb && gi0 + i >= gj0 + j)
+        {
+          C[i + (long long)j * ldc] = cv[a][b][e] - acc[a][b][e];
+        }
+      }
+}
+
 __global__ void __launch_bounds__(128)
 k_update(const Task5* __restrict__ tasks,
          const SnMeta* __restrict__ sn,
          double* __restrict__ L,
          double* __restrict__ U,
-         const double* __restrict__ D)
+         const double* __restrict__ D,
+         const PanelTensorMap* __restrict__ tmaps)
 {
   extern __shared__ double tile_smem[];
   TileSmem sm(tile_smem);
   const Task5 t  = tasks[blockIdx.x];
   const SnMeta s = sn[t.sn];
   const int h    = s.k + s.r;
+  const int ld   = s.ld;
   double* P      = L + s.Lptr;
+  if (s.tmap >= 0) // large front: operands through the copy engine (uniform per CTA)
+  {
+    const void* tmap = tmaps + s.tmap;
+    if (t.kind == UPD_INPANEL)
+    {
+      const int na = min(TILE, h - t.i0), nb = min(TILE, t.jend - t.j0);
+      tile_update_tma(tmap, t.kb, t.ke, D + s.first, t.i0, na, t.j0, nb, P + t.i0 + (long long)t.j0 * ld, ld, t.i0, t.j0, true, tile_smem);
+    }
+    else
+    {
+      const int na = min(TILE, s.r - t.i0), nb = min(TILE, s.r - t.j0);
+      tile_update_tma(tmap, 0, s.k, D + s.first, s.k + t.i0, na, s.k + t.j0, nb, U + s.Uoff + t.i0 + (long long)t.j0 * s.r, s.r, t.i0, t.j0,
+                      s.child_end > s.child_begin, tile_smem);
+    }
+    return;
+  }
   if (t.kind == UPD_INPANEL)
   {
     // front rows [i0, i0+64) x front columns [j0, j0+64), columns < k, rows < h
     const int na = min(TILE, h - t.i0), nb = min(TILE, t.jend - t.j0);
-    tile_update(P, h, t.kb, t.ke, D + s.first, t.i0, na, t.j0, nb, P + t.i0 + (long long)t.j0 * h, h, t.i0, t.j0, true, sm);
+    tile_update(P, ld, t.kb, t.ke, D + s.first, t.i0, na, t.j0, nb, P + t.i0 + (long long)t.j0 * ld, ld, t.i0, t.j0, true, sm);
     return;
   }
   // UPD_SCHUR: update rows/cols [i0, i0+64) x [j0, j0+64) of U (r x r), operands are panel rows k + ...
@@ -570,7 +808,7 @@ k_update(const Task5* __restrict__ tasks,
     const int na = min(TILE, s.r - t.i0), nb = min(TILE, s.r - t.j0);
     double* Um   = U + s.Uoff;
     const bool accumulate = s.child_end > s.child_begin;
-    tile_update(P, h, 0, s.k, D + s.first, s.k + t.i0, na, s.k + t.j0, nb, Um + t.i0 + (long long)t.j0 * s.r, s.r, t.i0, t.j0, accumulate, sm);
+    tile_update(P, ld, 0, s.k, D + s.first, s.k + t.i0, na, s.k + t.j0, nb, Um + t.i0 + (long long)t.j0 * s.r, s.r, t.i0, t.j0, accumulate, sm);
   }
 }
 
@@ -588,7 +826,7 @@ k_inv_gemm(const InvTask* __restrict__ tasks,
   TileSmem sm(tile_smem);
   const InvTask t = tasks[blockIdx.x];
   const SnMeta s  = sn[t.sn];
-  const int k = s.k, h = s.k + s.r;
+  const int k = s.k, h = s.ld; // h: leading dimension of the panels
   const double* P = L + s.Lptr;
   double* M       = Mt + s.Lptr;
   double* Tm      = tmp + s.Tptr;
@@ -704,14 +942,14 @@ k_transpose(const TrTask* __restrict__ tasks, const SnMeta* __restrict__ sn, con
   __shared__ double tile[32][33];
   const TrTask t = tasks[blockIdx.x];
   const SnMeta s = sn[t.sn];
-  const int k = s.k, h = s.k + s.r;
+  const int k = s.k, h = s.k + s.r, ld = s.ld;
   const double* src = Mt + s.Lptr;
   double* dst       = Mr + s.Lptr;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int jj = ty; jj < 32; jj += 8)
   {
     const int i = t.i0 + tx, j = t.j0 + jj;
-    tile[jj][tx] = (i < h && j < k) ? src[(long long)j * h + i] : 0.0;
+    tile[jj][tx] = (i < h && j < k) ? src[(long long)j * ld + i] : 0.0;
   }
   __syncthreads();
   for (int ii = ty; ii < 32; ii += 8)
@@ -804,12 +1042,12 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
     }
     if (st.upd_mid > st.upd_begin)
     {
-      k_update<<<(unsigned)(st.upd_mid - st.upd_begin), 128, TILE_SMEM, stream>>>(dp.upd_tasks.p + st.upd_begin, dp.sn.p, nb.L, nb.U, nb.D);
+      k_update<<<(unsigned)(st.upd_mid - st.upd_begin), 128, TILE_SMEM, stream>>>(dp.upd_tasks.p + st.upd_begin, dp.sn.p, nb.L, nb.U, nb.D, dp.tmaps.p);
       lc.tick("update");
     }
     if (st.upd_end > st.upd_mid)
     {
-      k_update<<<(unsigned)(st.upd_end - st.upd_mid), 128, TILE_SMEM, rest_stream>>>(dp.upd_tasks.p + st.upd_mid, dp.sn.p, nb.L, nb.U, nb.D);
+      k_update<<<(unsigned)(st.upd_end - st.upd_mid), 128, TILE_SMEM, rest_stream>>>(dp.upd_tasks.p + st.upd_mid, dp.sn.p, nb.L, nb.U, nb.D, dp.tmaps.p);
       lc.tick("update");
     }
     if (ov)

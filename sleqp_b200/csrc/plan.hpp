@@ -26,7 +26,17 @@ constexpr int EA_COLS  = 4;   // update-matrix columns per extend-add task (one 
 constexpr int FLOW_THREADS     = 256; // dataflow sweep kernels: persistent CTAs of 8 warps,
 constexpr int FLOW_CTAS_PER_SM = 4;   // four per SM (64 registers per thread)
 constexpr int FLOW_DEEP        = 128; // depth of a sweep task in the levels that are bandwidth-bound (symbolic.cpp, solve.cu)
+constexpr int TMA_MIN_FRONT = 128; // fronts of at least this many rows fetch their update-tile operands through TMA (numeric.cu)
 constexpr int LEAF_MAX = 32;  // etree subtrees up to this many columns become one dense supernode
+
+// Leading dimension of a supernode's column-major panel (L and Mt): the front height rounded up to an even number of
+// rows, so that every column starts on a 16-byte boundary -- what a TMA tensor map needs of its strides (numeric.cu).
+// The row-major copy Mr of the same panel is dense h x k inside the same slot.
+constexpr inline i64
+panel_ld(i64 h)
+{
+  return (h + 1) & ~(i64)1;
+}
 
 // kinds of update tasks
 enum
@@ -92,7 +102,7 @@ struct alignas(16) SweepTask
   long long Lptr; // panel offset (doubles)
   int Rptr;       // offset of the supernode's update rows in Ridx
   int first;      // first column (new labels)
-  int k, h;
+  int k, h; // h: leading dimension of the column-major panel (panel_ld of the front height)
   int i0, i1;
   int j0, j1;
   int wait_idx, need;

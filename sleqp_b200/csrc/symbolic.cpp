@@ -1457,7 +1457,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     const i64 k = P.sn_first[T + 1] - P.sn_first[T];
     const i64 r = P.Rptr[T + 1] - P.Rptr[T];
     const i64 h = k + r;
-    i64 sz      = h * k;
+    i64 sz      = panel_ld(h) * k; // leading dimension padded to an even number of rows (plan.hpp)
     sz          = (sz + 3) & ~(i64)3;
     P.Lptr[T + 1] = P.Lptr[T] + sz;
     P.Wptr[T + 1] = P.Wptr[T] + h;
@@ -1557,7 +1557,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
           }
           rowpos = k + (it - rows);
         }
-        P.Sdest[q] = P.Lptr[T] + (i64)(j - f) * h + rowpos;
+        P.Sdest[q] = P.Lptr[T] + (i64)(j - f) * panel_ld(h) + rowpos;
       }
       P.Sdiag[j] = P.Sdest[Sptr[j]];
     }
@@ -2140,7 +2140,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         }
         const int wait_idx = need > 0 ? T : -1;
         fwd_blocks(k, h, depth_of_sn(T), [&](int i0, int i1, int j0, int j1) {
-          P.ffl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, j1, wait_idx, need, P.sn_parent[T], l, depth_of_level[l] == 16, 0});
+          P.ffl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, (int)panel_ld(h), i0, i1, j0, j1, wait_idx, need, P.sn_parent[T], l, depth_of_level[l] == 16, 0});
         });
       }
     }
@@ -2156,7 +2156,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
         const int signal_idx = P.child_ptr[T + 1] > P.child_ptr[T] ? T : -1;
         bwd_blocks(k, h, depth_of_sn(T), [&](int i0, int i1, int j0, int j1) {
           const bool tail = i1 > k && par >= 0; // touches x of the ancestors
-          P.bfl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, h, i0, i1, j0, j1, tail ? par : -1, tail ? nbk[par] : 0, signal_idx, l, depth_of_level[l] == 16, 0});
+          P.bfl_tasks.push_back({P.Lptr[T], (int)P.Rptr[T], P.sn_first[T], k, (int)panel_ld(h), i0, i1, j0, j1, tail ? par : -1, tail ? nbk[par] : 0, signal_idx, l, depth_of_level[l] == 16, 0});
         });
       }
     }

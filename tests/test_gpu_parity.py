@@ -109,6 +109,28 @@ def test_deep_sweep_tasks(make, monkeypatch):
     assert f.stats()["refine_steps"] == 0
 
 
+@pytest.mark.parametrize("make", [
+    lambda: problems.poisson_control(40, 2, seed=3),
+    lambda: problems.poisson_control(10, 3, seed=4),
+    lambda: problems.poisson_control(100, 2, seed=1),
+    lambda: problems.chain_rosenbrock(5000, 0.15, seed=5),
+], ids=["p2d_g40", "p3d_g10", "p2d_g100", "chain_5000"])
+def test_update_tiles_through_tma(make, monkeypatch):
+    """The DMMA update tiles of large fronts fetch their operands with cp.async.bulk.tensor through per-supernode
+    tensor maps (numeric.cu tile_update_tma: 128-byte swizzle, permuted fragment rows). The threshold is lowered so
+    that every front of these small problems takes that path: same pivots as the cp.async path, same solutions."""
+    p = make()
+    f_ref = Fact()
+    f_ref.set_matrix(p.N, *p.kkt_lower())
+    d_ref = f_ref.pivots()
+    f_ref.release()
+    monkeypatch.setenv("B200_TMA_MIN_FRONT", "1")
+    f = _check_problem(p, seeds=(1, 2))
+    d = f.pivots()
+    assert np.abs(d - d_ref).max() <= 1e-11 * np.abs(d_ref).max()
+    f.release()
+
+
 def test_structure_and_pivots_match_host_analysis_and_emulation():
     p = problems.poisson_control(20, 2, seed=7)
     cp, ri, v = p.kkt_lower()
