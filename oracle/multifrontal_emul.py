@@ -296,7 +296,9 @@ class Emulated:
         if kind == UPD_SCHUR:
             d = self.D[f : f + k]
             Um = self.umat(T)
-            i1, j1 = min(r, i0 + TILE), min(r, j0 + TILE)
+            sh = k & 1  # shifted tile grid: Schur tiles start at even front rows (symbolic.cpp)
+            i1, j1 = min(r, i0 - sh + TILE), min(r, j0 - sh + TILE)
+            i0, j0 = max(0, i0 - sh), max(0, j0 - sh)
             Li = P[k + i0 : k + i1, :k]
             Lj = P[k + j0 : k + j1, :k]
             upd = (Li * d) @ Lj.T

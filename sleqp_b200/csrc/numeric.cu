@@ -449,7 +449,9 @@ tile_update(const double* __restrict__ P,
             int gi0,
             int gj0,
             bool accumulate,
-            TileSmem sm)
+            TileSmem sm,
+            int loa = 0, // first valid tile row / column (1 for the first tiles of a shifted Schur grid, else 0)
+            int lob = 0)
 {
   const int tid  = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -478,8 +480,9 @@ tile_update(const double* __restrict__ P,
       const int col    = kc + kk;
       const bool okc   = col < ke;
       const double* pc = P + (long long)(okc ? col : kb) * h;
-      cp_async8(&sm.As[st][kk][ii], pc + ra0 + (ii < na ? ii : 0), okc && ii < na);
-      cp_async8(&sm.Bs[st][kk][ii], pc + rb0 + (ii < nb ? ii : 0), okc && ii < nb);
+      const bool va = ii < na && ii >= loa, vb = ii < nb && ii >= lob;
+      cp_async8(&sm.As[st][kk][ii], pc + ra0 + (va ? ii : loa), okc && va);
+      cp_async8(&sm.Bs[st][kk][ii], pc + rb0 + (vb ? ii : lob), okc && vb);
     }
     if (tid < KC)
     {
@@ -527,7 +530,7 @@ tile_update(const double* __restrict__ P,
       {
         const int i = wy * 32 + a * 8 + (lane >> 2);
         const int j = wx * 32 + b * 8 + 2 * (lane & 3) + e;
-        const bool ok = i < na && j < nb && gi0 + i >= gj0 + j;
+        const bool ok = i < na && j < nb && i >= loa && j >= lob && gi0 + i >= gj0 + j;
         cv[a][b][e]   = (ok && accumulate) ? C[i + (long long)j * ldc] : 0.0;
       }
 #pragma unroll
@@ -539,7 +542,7 @@ tile_update(const double* __restrict__ P,
       {
         const int i = wy * 32 + a * 8 + (lane >> 2);
         const int j = wx * 32 + b * 8 + 2 * (lane & 3) + e;
-        if (i < na && j < nb && gi0 + i >= gj0 + j)
+        if (i < na && j < nb && i >= loa && j >= lob && gi0 + i >= gj0 + j)
         {
           C[i + (long long)j * ldc] = cv[a][b][e] - acc[a][b][e];
         }
@@ -631,7 +634,9 @@ tile_update_tma(const void* __restrict__ tmap,
                 int gi0,
                 int gj0,
                 bool accumulate,
-                double* smem_raw)
+                double* smem_raw,
+                int loa = 0,
+                int lob = 0)
 {
   // 1 KB alignment of the swizzle atoms
   double* base          = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -649,6 +654,9 @@ tile_update_tma(const void* __restrict__ tmap,
       mbar_init(smem_u32(bars + st), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    // the tensor map lives in global memory and was written by a host copy: the thread that hands it to the copy
+    // engine acquires it through the tensormap proxy first (system scope)
+    asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;\n" ::"l"(tmap) : "memory");
   }
   __syncthreads();
   double acc[4][4][2];
@@ -746,7 +754,7 @@ tile_update_tma(const void* __restrict__ tmap,
       {
         const int i = wy * 32 + (a >> 1) * 16 + frag_row(a & 1, lane >> 2);
         const int j = wx * 32 + (b >> 1) * 16 + frag_row(b & 1, 2 * (lane & 3) + e);
-        const bool ok = i < na && j < nb && gi0 + i >= gj0 + j;
+        const bool ok = i < na && j < nb && i >= loa && j >= lob && gi0 + i >= gj0 + j;
         cv[a][b][e]   = (ok && accumulate) ? C[i + (long long)j * ldc] : 0.0;
       }
 #pragma unroll
@@ -758,7 +766,7 @@ tile_update_tma(const void* __restrict__ tmap,
       {
         const int i = wy * 32 + (a >> 1) * 16 + frag_row(a & 1, lane >> 2);
         const int j = wx * 32 + (b >> 1) * 16 + frag_row(b & 1, 2 * (lane & 3) + e);
-        if (i < na && j < nb && gi0 + i >= gj0 + j)
+        if (i < na && j < nb && i >= loa && j >= lob && gi0 + i >= gj0 + j)
         {
           C[i + (long long)j * ldc] = cv[a][b][e] - acc[a][b][e];
         }
@@ -790,9 +798,11 @@ k_update(const Task5* __restrict__ tasks,
     }
     else
     {
-      const int na = min(TILE, s.r - t.i0), nb = min(TILE, s.r - t.j0);
-      tile_update_tma(tmap, 0, s.k, D + s.first, s.k + t.i0, na, s.k + t.j0, nb, U + s.Uoff + t.i0 + (long long)t.j0 * s.r, s.r, t.i0, t.j0,
-                      s.child_end > s.child_begin, tile_smem);
+      // shifted tile grid (even front rows): tile row ii is row u0 + ii of the update matrix, row -1 is masked
+      const int sh = s.k & 1, u0 = t.i0 - sh, v0 = t.j0 - sh;
+      const int na = min(TILE, s.r - u0), nb = min(TILE, s.r - v0);
+      tile_update_tma(tmap, 0, s.k, D + s.first, s.k + u0, na, s.k + v0, nb, U + s.Uoff + u0 + (long long)v0 * s.r, s.r, u0, v0,
+                      s.child_end > s.child_begin, tile_smem, u0 < 0, v0 < 0);
     }
     return;
   }
@@ -805,10 +815,11 @@ k_update(const Task5* __restrict__ tasks,
   }
   // UPD_SCHUR: update rows/cols [i0, i0+64) x [j0, j0+64) of U (r x r), operands are panel rows k + ...
   {
-    const int na = min(TILE, s.r - t.i0), nb = min(TILE, s.r - t.j0);
+    const int sh = s.k & 1, u0 = t.i0 - sh, v0 = t.j0 - sh; // shifted tile grid, see above
+    const int na = min(TILE, s.r - u0), nb = min(TILE, s.r - v0);
     double* Um   = U + s.Uoff;
     const bool accumulate = s.child_end > s.child_begin;
-    tile_update(P, ld, 0, s.k, D + s.first, s.k + t.i0, na, s.k + t.j0, nb, Um + t.i0 + (long long)t.j0 * s.r, s.r, t.i0, t.j0, accumulate, sm);
+    tile_update(P, ld, 0, s.k, D + s.first, s.k + u0, na, s.k + v0, nb, Um + u0 + (long long)v0 * s.r, s.r, u0, v0, accumulate, sm, u0 < 0, v0 < 0);
   }
 }
 

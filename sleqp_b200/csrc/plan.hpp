@@ -26,7 +26,7 @@ constexpr int EA_COLS  = 4;   // update-matrix columns per extend-add task (one 
 constexpr int FLOW_THREADS     = 256; // dataflow sweep kernels: persistent CTAs of 8 warps,
 constexpr int FLOW_CTAS_PER_SM = 4;   // four per SM (64 registers per thread)
 constexpr int FLOW_DEEP        = 128; // depth of a sweep task in the levels that are bandwidth-bound (symbolic.cpp, solve.cu)
-constexpr int TMA_MIN_FRONT = 128; // fronts of at least this many rows fetch their update-tile operands through TMA (numeric.cu)
+constexpr int TMA_MIN_FRONT = 512; // fronts of at least this many rows fetch their update-tile operands through TMA (numeric.cu); measured: below ~500 rows the per-CTA barrier set-up costs more than the address arithmetic it saves (profiles/r02_tma_vs_cpasync.txt)
 constexpr int LEAF_MAX = 32;  // etree subtrees up to this many columns become one dense supernode
 
 // Leading dimension of a supernode's column-major panel (L and Mt): the front height rounded up to an even number of

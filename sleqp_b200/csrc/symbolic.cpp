@@ -1898,9 +1898,13 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
             }
             if (t == P.sn_nt[T] - 1 && r > 0)
             {
-              for (int j0 = 0; j0 < r; j0 += TILE)
+              // Schur tiles start at EVEN front rows (a TMA box must start on a 16-byte boundary of the panel column):
+              // for an odd k the tile grid is shifted up by one row, tile (i0, j0) covers the rows i0 - 1 .. i0 + 62 of
+              // the update matrix (row -1 does not exist and is masked), so the grid spans r + 1 rows
+              const int span = r + (k & 1);
+              for (int j0 = 0; j0 < span; j0 += TILE)
               {
-                for (int i0 = j0; i0 < r; i0 += TILE)
+                for (int i0 = j0; i0 < span; i0 += TILE)
                 {
                   P.upd_tasks.push_back({T, r, UPD_SCHUR, i0, j0, 0, k});
                 }
@@ -2029,7 +2033,10 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   {
     const i64 k = P.sn_first[t.sn + 1] - P.sn_first[t.sn], r = P.Rptr[t.sn + 1] - P.Rptr[t.sn];
     const bool schur = t.kind == UPD_SCHUR;
-    const double na = (double)std::min<i64>(TILE, (schur ? r : k + r) - t.i0), nb = (double)std::min<i64>(TILE, (schur ? r : (i64)t.jend) - t.j0);
+    const i64 sh     = schur ? (k & 1) : 0; // shifted tile grid of the Schur tiles (see the task generation)
+    const i64 u0 = t.i0 - sh, v0 = t.j0 - sh;
+    const double na = (double)(std::min<i64>(u0 + TILE, schur ? r : k + r) - std::max<i64>(u0, 0));
+    const double nb = (double)(std::min<i64>(v0 + TILE, schur ? r : (i64)t.jend) - std::max<i64>(v0, 0));
     P.flops_update += (t.i0 == t.j0 ? 1.0 : 2.0) * na * nb * (double)(t.ke - t.kb);
   }
   for (const InvTask& t : P.inv_tasks)
