@@ -109,9 +109,30 @@ B200_API int b200_fact_set_matrix(b200_fact* handle,
                          const double* val,
                          int lower_only);
 
+/* The same factorization from what the augmented Jacobian is built of (standard_aug_jac.c:135-237, aug_jac_set_iterate
+ * :239-293): the constraint Jacobian of the iterate (CSC, num_cons x num_vars, as sleqp_iterate_cons_jac returns it) and
+ * the working set as index maps (var_index[j] / cons_index[i] = position in the working set or -1, exactly
+ * sleqp_working_set_var_index / _cons_index, working_set.c:117-180). tril([I A_W^T; A_W 0]) is laid out like
+ * fill_aug_jac does, but only when (Jacobian pattern, working set) is new; for a known key the host does nothing but
+ * hash the arrays: the Jacobian values are copied to the device and the KKT values are gathered there. Arrays are
+ * borrowed for the call. */
+B200_API int b200_fact_set_kkt(b200_fact* handle,
+                               int num_vars,
+                               int num_cons,
+                               int nnz_jac,
+                               const int* jac_cols,
+                               const int* jac_rows,
+                               const double* jac_data,
+                               const int* var_index,
+                               const int* cons_index,
+                               int working_set_size);
+
 /* Solve K x = b for a sparse right-hand side (idx ascending, dim == n). The result stays in
  * device memory inside the handle (like `umfpack->solution`). */
 B200_API int b200_fact_solve(b200_fact* handle, int nnz_rhs, const int* idx, const double* val, int dim);
+/* Same with every index shifted by `offset`: the right-hand side [0; rhs] of the min-norm solve without touching the
+ * caller's vector (the reference adds num_vars to rhs->indices and takes it off again, standard_aug_jac.c:328-345). */
+B200_API int b200_fact_solve_offset(b200_fact* handle, int nnz_rhs, const int* idx, const double* val, int offset, int dim);
 
 /* Copy x[begin:end) of the last solve into out_dense (host memory, end-begin doubles). */
 B200_API int b200_fact_solution(b200_fact* handle, int begin, int end, double* out_dense);
@@ -179,6 +200,10 @@ B200_API int b200_symbolic_analyze(b200_symbolic** out,
                           const int* rowidx,
                           const double* val,
                           int lower_only);
+/* Analysis of the KKT system b200_fact_set_kkt would build from (Jacobian, working set); the plan field "Ksrc" tells
+ * where every value of tril(K) comes from (-1: the constant 1, else an index into jac_data). */
+B200_API int b200_symbolic_analyze_kkt(b200_symbolic** out, int num_vars, int num_cons, int nnz_jac, const int* jac_cols, const int* jac_rows,
+                                       const double* jac_data, const int* var_index, const int* cons_index, int working_set_size);
 B200_API int b200_symbolic_stats(const b200_symbolic* s, b200_stats* stats);
 B200_API int b200_symbolic_structure(const b200_symbolic* s, int* perm, int* parent, int* colcount, int* n_super_total, int* super_first);
 /* Export of the numeric plan (reduced system) for the CPU emulation used in tests:

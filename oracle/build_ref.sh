@@ -11,6 +11,7 @@
 #   oracle/_ref/libsleqp_ref_b200.so     reference core + sleqp_b200/host/{fact/fact_b200.c, tr/tr_b200.c, sparse/mat_b200.c} (drop-in test)
 #   oracle/_ref/eqp_harness_{lapack,b200,b200tr}   the EQP harness over the reference LAPACK backend, over our factorization
 #                                        with the reference's Steihaug solver, and over our factorization + our TR solver
+#   oracle/_ref/eqp_harness_b200aj       ... and with our augmented Jacobian (device KKT assembly) instead of standard_aug_jac.c
 #   oracle/_ref/eqp_step_b200            the timing mode of the same harness (bench.py's reference-driven e2e leg)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -103,9 +104,9 @@ gcc $CFLAGS -I"$SRC/fact" -I"$SRC/aug_jac" -I"$SRC/tr" "$HERE/eqp_harness.c" -o 
 HOST="$REPO/sleqp_b200/host"
 if [ -f "$HOST/fact/fact_b200.c" ] && [ -f "$REPO/sleqp_b200/libsleqp_b200.so" ]; then
   GLUE=""
-  for f in fact/fact_b200.c tr/tr_b200.c sparse/mat_b200.c; do
+  for f in fact/fact_b200.c tr/tr_b200.c sparse/mat_b200.c aug_jac/b200_aug_jac.c; do
     o="$OUT/obj/$(basename "$f" .c).o"
-    gcc $CFLAGS -I"$REPO/include" -I"$HOST" -I"$HOST/$(dirname "$f")" -I"$SRC/fact" -I"$SRC/tr" -I"$SRC/sparse" -c "$HOST/$f" -o "$o"
+    gcc $CFLAGS -I"$REPO/include" -I"$HOST" -I"$HOST/$(dirname "$f")" -I"$SRC/fact" -I"$SRC/tr" -I"$SRC/sparse" -I"$SRC/aug_jac" -c "$HOST/$f" -o "$o"
     GLUE="$GLUE $o"
   done
   gcc -shared -o "$OUT/libsleqp_ref_b200.so" $OBJS $GLUE \
@@ -115,5 +116,6 @@ if [ -f "$HOST/fact/fact_b200.c" ] && [ -f "$REPO/sleqp_b200/libsleqp_b200.so" ]
   LINK="-L$OUT -lsleqp_ref_b200 -Wl,-rpath,\$ORIGIN -Wl,-rpath,\$ORIGIN/../../sleqp_b200 -L$REPO/sleqp_b200 -lsleqp_b200 -lm"
   gcc $HFLAGS "$HERE/eqp_harness.c" -o "$OUT/eqp_harness_b200" $LINK
   gcc $HFLAGS -DHARNESS_B200_TR "$HERE/eqp_harness.c" -o "$OUT/eqp_harness_b200tr" $LINK
-  gcc $HFLAGS -DHARNESS_B200_TR -DHARNESS_TIMING "$HERE/eqp_harness.c" -o "$OUT/eqp_step_b200" $LINK
+  gcc $HFLAGS -DHARNESS_B200_TR -DHARNESS_B200_AUG_JAC "$HERE/eqp_harness.c" -o "$OUT/eqp_harness_b200aj" $LINK
+  gcc $HFLAGS -DHARNESS_B200_TR -DHARNESS_B200_AUG_JAC -DHARNESS_TIMING "$HERE/eqp_harness.c" -o "$OUT/eqp_step_b200" $LINK
 fi

@@ -38,6 +38,9 @@
 #include "working_set.h"
 
 #include "aug_jac/standard_aug_jac.h"
+#ifdef HARNESS_B200_AUG_JAC
+#include "aug_jac/b200_aug_jac.h"
+#endif
 #include "fact/fact.h"
 #include "tr/steihaug_solver.h"
 #include "tr/tr_solver.h"
@@ -388,6 +391,14 @@ setup_problem(Setup* s, const char* kind, int size, int active_every)
   s->ws_size = n_active_vars + m;
 
   CHECK(sleqp_fact_create_default(&s->fact, s->settings));
+#ifdef HARNESS_B200_AUG_JAC
+  // the augmented Jacobian of the B200 backend: KKT assembly on the device (the SleqpFact above is only asked its name)
+  if (!getenv("HARNESS_STANDARD_AUG_JAC"))
+  {
+    CHECK(sleqp_b200_aug_jac_create(&s->jac, s->problem, s->settings));
+    return;
+  }
+#endif
   CHECK(sleqp_standard_aug_jac_create(&s->jac, s->problem, s->settings, s->fact));
 }
 
@@ -689,10 +700,15 @@ main(int argc, char** argv)
                         + (steihaug ? 12LL * n * (cg_iters + 1) : 12LL * n + (hessian ? 0 : 8LL * n * cg_iters));
   const long long d2h = 12LL * n + 12LL * ws_size + (steihaug ? 12LL * n * (cg_iters + 1) : 8LL * n + (hessian ? 0 : 8LL * n * cg_iters));
   printf("{\"driver\": \"eqp_step (reference aug_jac/TR code over the B200 glue)\", \"problem\": \"%s\", \"size\": %d, \"n\": %d, \"m\": %d, "
-         "\"ws_size\": %d, \"N\": %d, \"backend\": \"%s\", \"tr_solver\": \"%s\", \"cg_iters_cap\": %d, \"cg_iterations\": %d, \"cg_exit\": %d, "
+         "\"ws_size\": %d, \"N\": %d, \"backend\": \"%s\", \"aug_jac\": \"%s\", \"tr_solver\": \"%s\", \"cg_iters_cap\": %d, \"cg_iterations\": %d, \"cg_exit\": %d, "
          "\"steps\": %d, \"warmup\": %d, \"ms_per_step\": %.6f, \"iters_per_s\": %.6f, \"set_iterate_ms\": %.6f, \"two_solves_ms\": %.6f, "
          "\"solve_ms\": %.6f, \"spmv\": \"%s\", \"jac_products_ms\": %.6f, \"tr_solve_ms\": %.6f, \"h2d_bytes_per_step\": %lld, \"d2h_bytes_per_step\": %lld}\n",
          kind, size, n, m, ws_size, n + ws_size, sleqp_fact_name(S.fact),
+#ifdef HARNESS_B200_AUG_JAC
+         getenv("HARNESS_STANDARD_AUG_JAC") ? "reference standard_aug_jac.c (host fill_aug_jac)" : "aug_jac/b200_aug_jac.c (KKT assembled on the device)",
+#else
+         "reference standard_aug_jac.c (host fill_aug_jac)",
+#endif
          steihaug ? "reference steihaug_solver.c over SleqpFact B200" : "tr_b200.c (device CG, Hessian as a device matrix)", cg_iters, cg_done, cg_exit,
          steps, warm, ms, 1e3 / ms, t_set / steps, t_solves / steps, t_solves / steps / 2.,
          hostspmv ? "reference sleqp_mat_mult_vec(_trans) on the host" : "sparse/mat_b200.c (device mirror, refreshed every step)", t_spmv / steps, t_tr / steps,

@@ -54,10 +54,10 @@ _lib = None
 
 # every symbol include/sleqp_b200.h declares (tests check they are all exported)
 SYMBOLS = [
-    "b200_fact_create", "b200_fact_set_matrix", "b200_fact_solve", "b200_fact_solution",
+    "b200_fact_create", "b200_fact_set_matrix", "b200_fact_set_kkt", "b200_fact_solve", "b200_fact_solve_offset", "b200_fact_solution",
     "b200_fact_solution_ptr", "b200_fact_solution_sparse", "b200_fact_solve_device", "b200_fact_refactor_device", "b200_fact_profile_solve", "b200_fact_profile_numeric", "b200_fact_rcond", "b200_fact_stats",
     "b200_fact_structure", "b200_fact_pivots", "b200_fact_stream", "b200_fact_device", "b200_fact_free", "b200_last_error",
-    "b200_symbolic_analyze", "b200_symbolic_stats", "b200_symbolic_structure", "b200_symbolic_export",
+    "b200_symbolic_analyze", "b200_symbolic_analyze_kkt", "b200_symbolic_stats", "b200_symbolic_structure", "b200_symbolic_export",
     "b200_symbolic_free", "b200_mat_create", "b200_mat_set", "b200_mat_mult_vec", "b200_mat_mult_vec_trans",
     "b200_mat_mult_vec_device", "b200_mat_mult_vec_trans_device", "b200_mat_stream", "b200_mat_set_stream", "b200_mat_free",
     "b200_cg_create", "b200_cg_set_hess_callback", "b200_cg_solve", "b200_cg_solve_ex", "b200_cg_free", "b200_device_count", "b200_launch_count", "b200_host_pin", "b200_host_unpin",
@@ -78,7 +78,9 @@ def lib():
     L.b200_last_error.restype = C.c_char_p
     L.b200_fact_create.argtypes = [C.POINTER(vp), C.c_int]
     L.b200_fact_set_matrix.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, ip, dp, C.c_int]
+    L.b200_fact_set_kkt.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, ip, dp, ip, ip, C.c_int]
     L.b200_fact_solve.argtypes = [vp, C.c_int, ip, dp, C.c_int]
+    L.b200_fact_solve_offset.argtypes = [vp, C.c_int, ip, dp, C.c_int, C.c_int]
     L.b200_fact_solution.argtypes = [vp, C.c_int, C.c_int, dp]
     L.b200_fact_solution_ptr.argtypes = [vp, C.c_int, C.c_int, C.POINTER(dp)]
     L.b200_fact_solution_sparse.argtypes = [vp, C.c_int, C.c_int, C.c_double, ip, dp, ip]
@@ -95,6 +97,7 @@ def lib():
     L.b200_fact_device.argtypes = [vp]
     L.b200_fact_free.argtypes = [C.POINTER(vp)]
     L.b200_symbolic_analyze.argtypes = [C.POINTER(vp), C.c_int, C.c_int, ip, ip, dp, C.c_int]
+    L.b200_symbolic_analyze_kkt.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, ip, ip, dp, ip, ip, C.c_int]
     L.b200_symbolic_stats.argtypes = [vp, C.POINTER(Stats)]
     L.b200_symbolic_structure.argtypes = [vp, ip, ip, ip, ip, ip]
     L.b200_symbolic_export.argtypes = [vp, C.c_char_p, vp, C.POINTER(C.c_int64)]

@@ -40,7 +40,7 @@ get_plan(int n, int nnz, const int* colptr, const int* rowidx, const double* val
     std::lock_guard<std::mutex> lock(g_cache_mutex);
     for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
     {
-      if ((*it)->pattern_hash == h && (*it)->pattern_hash2 == h2 && (*it)->N == n && (*it)->nnzK_input == nnz)
+      if (!(*it)->kkt_keyed && (*it)->pattern_hash == h && (*it)->pattern_hash2 == h2 && (*it)->N == n && (*it)->nnzK_input == nnz)
       {
         out = *it;
         g_cache.splice(g_cache.begin(), g_cache, it);
@@ -56,6 +56,66 @@ get_plan(int n, int nnz, const int* colptr, const int* rowidx, const double* val
   {
     return set_error(rc, err);
   }
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    g_cache.push_front(plan);
+    while (g_cache.size() > CACHE_CAPACITY)
+    {
+      g_cache.pop_back();
+    }
+  }
+  out    = plan;
+  cached = false;
+  return B200_OK;
+}
+
+int
+get_plan_kkt(int num_vars, int num_cons, int nnz_jac, const int* jac_cols, const int* jac_rows, const double* jac_data, const int* var_index, const int* cons_index,
+             int ws_size, std::shared_ptr<const Plan>& out, bool& cached)
+{
+  if (num_vars < 0 || num_cons < 0 || nnz_jac < 0 || ws_size < 0 || !jac_cols || !var_index || (num_cons > 0 && !cons_index) || (nnz_jac > 0 && (!jac_rows || !jac_data))
+      || jac_cols[0] != 0 || jac_cols[num_vars] != nnz_jac)
+  {
+    return set_error(B200_ERR_ARG, "malformed Jacobian / working-set arrays");
+  }
+  uint64_t h2      = 0;
+  const uint64_t h = hash_kkt(num_vars, num_cons, nnz_jac, jac_cols, jac_rows, var_index, cons_index, ws_size, &h2);
+  const int N      = num_vars + ws_size;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
+    {
+      if ((*it)->kkt_keyed && (*it)->pattern_hash == h && (*it)->pattern_hash2 == h2 && (*it)->N == N && (*it)->key_aux == nnz_jac)
+      {
+        out = *it;
+        g_cache.splice(g_cache.begin(), g_cache, it);
+        cached = true;
+        return B200_OK;
+      }
+    }
+  }
+  std::vector<int> colptr, rowidx, src;
+  if (!build_kkt_lower(num_vars, num_cons, jac_cols, jac_rows, var_index, cons_index, ws_size, colptr, rowidx, src))
+  {
+    return set_error(B200_ERR_ARG, "malformed Jacobian / working-set arrays (indices out of range or rows not increasing)");
+  }
+  std::vector<double> val(src.size());
+  for (size_t q = 0; q < src.size(); ++q)
+  {
+    val[q] = src[q] < 0 ? 1.0 : jac_data[src[q]];
+  }
+  auto plan = std::make_shared<Plan>();
+  std::string err;
+  int rc = analyze(N, (int)rowidx.size(), colptr.data(), rowidx.data(), val.data(), /*lower_only=*/1, *plan, err);
+  if (rc != B200_OK)
+  {
+    return set_error(rc, err);
+  }
+  plan->kkt_keyed     = true;
+  plan->key_aux       = nnz_jac;
+  plan->pattern_hash  = h;
+  plan->pattern_hash2 = h2;
+  plan->Ksrc          = std::move(src);
   {
     std::lock_guard<std::mutex> lock(g_cache_mutex);
     g_cache.push_front(plan);
@@ -156,6 +216,52 @@ b200_symbolic_analyze(b200_symbolic** out, int n, int nnz, const int* colptr, co
 }
 
 int
+b200_symbolic_analyze_kkt(b200_symbolic** out,
+                          int num_vars,
+                          int num_cons,
+                          int nnz_jac,
+                          const int* jac_cols,
+                          const int* jac_rows,
+                          const double* jac_data,
+                          const int* var_index,
+                          const int* cons_index,
+                          int working_set_size)
+{
+  if (!out)
+  {
+    return set_error(B200_ERR_ARG, "null output handle");
+  }
+  *out = nullptr;
+  if (num_vars < 0 || num_cons < 0 || nnz_jac < 0 || working_set_size < 0 || !jac_cols || !var_index || (num_cons > 0 && !cons_index)
+      || (nnz_jac > 0 && (!jac_rows || !jac_data)) || jac_cols[0] != 0 || jac_cols[num_vars] != nnz_jac)
+  {
+    return set_error(B200_ERR_ARG, "malformed Jacobian / working-set arrays");
+  }
+  std::vector<int> colptr, rowidx, src;
+  if (!build_kkt_lower(num_vars, num_cons, jac_cols, jac_rows, var_index, cons_index, working_set_size, colptr, rowidx, src))
+  {
+    return set_error(B200_ERR_ARG, "malformed Jacobian / working-set arrays (indices out of range or rows not increasing)");
+  }
+  std::vector<double> val(src.size());
+  for (size_t q = 0; q < src.size(); ++q)
+  {
+    val[q] = src[q] < 0 ? 1.0 : jac_data[src[q]];
+  }
+  auto plan = std::make_shared<Plan>();
+  std::string err;
+  int rc = analyze(num_vars + working_set_size, (int)rowidx.size(), colptr.data(), rowidx.data(), val.data(), 1, *plan, err);
+  if (rc != B200_OK)
+  {
+    return set_error(rc, err);
+  }
+  plan->kkt_keyed = true;
+  plan->key_aux   = nnz_jac;
+  plan->Ksrc      = std::move(src);
+  *out            = new b200_symbolic{plan, false};
+  return B200_OK;
+}
+
+int
 b200_symbolic_stats(const b200_symbolic* s, b200_stats* stats)
 {
   if (!s || !stats)
@@ -236,6 +342,7 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
   FIELD(lvl_sn)
   FIELD(inv_phase_ptr)
   FIELD(Tptr)
+  FIELD(Ksrc)
 #undef FIELD
   if (f == "stages")
   {

@@ -187,6 +187,7 @@ struct DevPlan
   DevBuf<int> k_of_e, k_of_r, pinv, perm, dE_src;
   DevBuf<int> Acsc_ptr, Acsc_row, Acsc_src, Acsr_ptr, Acsr_col, Acsr_src, Gsym_ptr, Gsym_col, Gsym_src;
   DevBuf<int> Acsr_k, Acsr_dsrc, Acsc_p;
+  DevBuf<int> Ksrc; // set_kkt plans: source of every value of tril(K) in the Jacobian's value array (-1: the constant 1)
 };
 
 } // namespace b200

@@ -52,6 +52,7 @@ struct b200_fact
   // factor
   DevBuf<double> val, L, Mt, Mr, tmp, U, D, Dinv, scratch, scal, dE, Acsc_val, Acsr_val, Acsr_sval, Gsym_val;
   DevBuf<int> nper;
+  DevBuf<double> jval; // values of the constraint Jacobian (set_kkt: the KKT values are gathered from them on the device)
   // solve
   DevBuf<double> rhs, z, res, dz, bR, y, yf, x;
   DevBuf<int> rhs_idx, flow, cp_idx, cp_cnt; // cp_*: device-side sparsification of a solution slice
@@ -252,6 +253,7 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   dp.Gsym_ptr.upload(P.Gsym_ptr, s);
   dp.Gsym_col.upload(P.Gsym_col, s);
   dp.Gsym_src.upload(P.Gsym_src, s);
+  dp.Ksrc.upload(P.Ksrc, s);
   // the uploads read pageable host vectors owned by the (shared, immutable) plan: safe, but
   // finish them before anything else touches the stream
   B200_CUDA(cudaStreamSynchronize(s));
@@ -366,6 +368,80 @@ launch_solve(b200_fact* F, int refine)
   const NumericBuffers nb = F->nbuf();
   const SolveBuffers sb   = F->sbuf();
   run_graph(F, F->g_solve[refine], [&](LaunchCounter& lc) { enqueue_solve(F->dp, nb, sb, refine, F->stream, lc); });
+}
+
+// The part of a factorization that follows the plan lookup and the upload of the values (F->val): numeric graph,
+// pivot range, probe solve that fixes the number of refinement steps (shared by set_matrix and set_kkt).
+template <typename Lap>
+int
+factor_and_probe(b200_fact* F, Lap&& lap)
+{
+  {
+    const Plan& P = *F->dp.plan;
+    if (P.N == 0)
+    {
+      F->factored = true;
+      F->refine   = 0;
+      F->rcond    = 1.0;
+      return (int)B200_OK;
+    }
+    {
+      const NumericBuffers nb = F->nbuf();
+      run_graph(F, F->g_numeric, [&](LaunchCounter& lc) {
+        enqueue_numeric(F->dp, nb, F->stream, lc, &F->overlap);
+        enqueue_pivot_range(F->dp, nb, F->stream, lc);
+      });
+    }
+    B200_CUDA(cudaEventRecord(F->ev_b, F->stream));
+    F->timed_numeric = true;
+    lap("enqueue copy + numeric graph");
+    // pivot range and perturbation count
+    B200_CUDA(cudaMemcpyAsync(F->h_scal.p, F->scal.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, F->stream));
+    B200_CUDA(cudaMemcpyAsync(F->h_nper.p, F->nper.p, sizeof(int), cudaMemcpyDeviceToHost, F->stream));
+    B200_CUDA(cudaStreamSynchronize(F->stream));
+    const double dmin = F->h_scal.p[2], dmax = F->h_scal.p[3];
+    F->rcond       = (dmax > 0.0 && std::isfinite(dmax) && std::isfinite(dmin)) ? dmin / dmax : 0.0;
+    F->n_perturbed = P.m > 0 ? F->h_nper.p[0] : 0;
+    lap("numeric factorization (wait)");
+
+    // probe solve: choose the number of refinement steps every solve of this factor performs
+    const NumericBuffers nb = F->nbuf();
+    const SolveBuffers sb   = F->sbuf();
+    LaunchCounter eager;
+    double best = INFINITY, prev = INFINITY;
+    int refine  = 0;
+    for (int r = 0; r <= MAX_REFINE; ++r)
+    {
+      enqueue_probe_rhs(sb.rhs, P.N, F->stream, eager);
+      launch_solve(F, r);
+      enqueue_residual_norms(F->dp, nb, sb, F->stream, eager);
+      B200_CUDA(cudaMemcpyAsync(F->h_scal.p, F->scal.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, F->stream));
+      B200_CUDA(cudaStreamSynchronize(F->stream));
+      const double rr = std::sqrt(F->h_scal.p[2]) / std::sqrt(F->h_scal.p[3]);
+      if (std::isfinite(rr) && rr < best)
+      {
+        best   = rr;
+        refine = r;
+      }
+      // good enough, broken, or refinement stopped paying
+      if (!std::isfinite(rr) || rr <= 1e-13 || (r > 0 && rr > 0.25 * prev))
+      {
+        break;
+      }
+      prev = rr;
+    }
+    F->refine    = refine;
+    F->probe_res = best;
+    lap("probe solve(s) + residual");
+    if (!(best <= 1e-6))
+    {
+      return set_error(B200_ERR_SINGULAR,
+                       "KKT matrix is numerically singular (probe residual " + std::to_string(best) + ", " + std::to_string(F->n_perturbed) +
+                         " perturbed pivots): the working set rows are not linearly independent");
+    }
+    F->factored = true;
+    return (int)B200_OK;
+  }
 }
 
 } // namespace
@@ -522,70 +598,79 @@ b200_fact_set_matrix(b200_fact* F, int n_rows, int n_cols, int nnz, const int* c
     {
       upload_plan(F, plan);
     }
-    const Plan& P = *plan;
-    if (P.N == 0)
-    {
-      F->factored = true;
-      F->refine   = 0;
-      F->rcond    = 1.0;
-      return (int)B200_OK;
-    }
-    {
-      const NumericBuffers nb = F->nbuf();
-      run_graph(F, F->g_numeric, [&](LaunchCounter& lc) {
-        enqueue_numeric(F->dp, nb, F->stream, lc, &F->overlap);
-        enqueue_pivot_range(F->dp, nb, F->stream, lc);
-      });
-    }
-    B200_CUDA(cudaEventRecord(F->ev_b, F->stream));
-    F->timed_numeric = true;
-    lap("enqueue copy + numeric graph");
-    // pivot range and perturbation count
-    B200_CUDA(cudaMemcpyAsync(F->h_scal.p, F->scal.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, F->stream));
-    B200_CUDA(cudaMemcpyAsync(F->h_nper.p, F->nper.p, sizeof(int), cudaMemcpyDeviceToHost, F->stream));
-    B200_CUDA(cudaStreamSynchronize(F->stream));
-    const double dmin = F->h_scal.p[2], dmax = F->h_scal.p[3];
-    F->rcond       = (dmax > 0.0 && std::isfinite(dmax) && std::isfinite(dmin)) ? dmin / dmax : 0.0;
-    F->n_perturbed = P.m > 0 ? F->h_nper.p[0] : 0;
-    lap("numeric factorization (wait)");
+    return factor_and_probe(F, lap);
+  });
+}
 
-    // probe solve: choose the number of refinement steps every solve of this factor performs
-    const NumericBuffers nb = F->nbuf();
-    const SolveBuffers sb   = F->sbuf();
-    LaunchCounter eager;
-    double best = INFINITY, prev = INFINITY;
-    int refine  = 0;
-    for (int r = 0; r <= MAX_REFINE; ++r)
-    {
-      enqueue_probe_rhs(sb.rhs, P.N, F->stream, eager);
-      launch_solve(F, r);
-      enqueue_residual_norms(F->dp, nb, sb, F->stream, eager);
-      B200_CUDA(cudaMemcpyAsync(F->h_scal.p, F->scal.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, F->stream));
-      B200_CUDA(cudaStreamSynchronize(F->stream));
-      const double rr = std::sqrt(F->h_scal.p[2]) / std::sqrt(F->h_scal.p[3]);
-      if (std::isfinite(rr) && rr < best)
+int
+b200_fact_set_kkt(b200_fact* F,
+                  int num_vars,
+                  int num_cons,
+                  int nnz_jac,
+                  const int* jac_cols,
+                  const int* jac_rows,
+                  const double* jac_data,
+                  const int* var_index,
+                  const int* cons_index,
+                  int working_set_size)
+{
+  if (!F)
+  {
+    return set_error(B200_ERR_ARG, "null handle");
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaSetDevice(F->device));
+    F->factored = F->solved = false;
+    static const bool timing = std::getenv("B200_TIMING") != nullptr;
+    auto t_last              = std::chrono::steady_clock::now();
+    auto lap                 = [&](const char* what) {
+      if (timing)
       {
-        best   = rr;
-        refine = r;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[b200 set_kkt] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
       }
-      // good enough, broken, or refinement stopped paying
-      if (!std::isfinite(rr) || rr <= 1e-13 || (r > 0 && rr > 0.25 * prev))
-      {
-        break;
-      }
-      prev = rr;
-    }
-    F->refine    = refine;
-    F->probe_res = best;
-    lap("probe solve(s) + residual");
-    if (!(best <= 1e-6))
+    };
+    if (nnz_jac < 0 || (nnz_jac > 0 && !jac_data))
     {
-      return set_error(B200_ERR_SINGULAR,
-                       "KKT matrix is numerically singular (probe residual " + std::to_string(best) + ", " + std::to_string(F->n_perturbed) +
-                         " perturbed pivots): the working set rows are not linearly independent");
+      return set_error(B200_ERR_ARG, "malformed Jacobian values");
     }
-    F->factored = true;
-    return (int)B200_OK;
+    // the Jacobian values go to the device while the host hashes the pattern + working set and looks the plan up;
+    // jval is not part of any captured graph (the gather below is launched eagerly)
+    F->jval.reserve((size_t)nnz_jac + 8);
+    B200_CUDA(cudaEventRecord(F->ev_a, F->stream));
+    if (nnz_jac > 0)
+    {
+      B200_CUDA(cudaMemcpyAsync(F->jval.p, jac_data, sizeof(double) * (size_t)nnz_jac, cudaMemcpyHostToDevice, F->stream));
+    }
+    std::shared_ptr<const Plan> plan;
+    bool cached = false;
+    int rc      = get_plan_kkt(num_vars, num_cons, nnz_jac, jac_cols, jac_rows, jac_data, var_index, cons_index, working_set_size, plan, cached);
+    lap("key hash + plan lookup");
+    if (rc != B200_OK)
+    {
+      cudaStreamSynchronize(F->stream); // `jac_data` is borrowed for the call only
+      return rc;
+    }
+    F->symbolic_cached = cached;
+    F->ms_symbolic     = cached ? 0.0 : plan->ms_symbolic;
+    const Plan& P      = *plan;
+    if ((size_t)P.nnzK_input + 8 > F->val.cap)
+    {
+      B200_CUDA(cudaStreamSynchronize(F->stream)); // the captured graphs have val.p baked in
+      F->drop_graphs();
+      F->dp.plan.reset();
+      F->val.reserve((size_t)P.nnzK_input + 8);
+    }
+    if (F->dp.plan != plan)
+    {
+      upload_plan(F, plan);
+    }
+    if (P.nnzK_input > 0)
+    {
+      enqueue_gather_kkt((int)P.nnzK_input, F->dp.Ksrc.p, F->jval.p, F->val.p, F->stream);
+    }
+    return factor_and_probe(F, lap);
   });
 }
 
@@ -820,6 +905,12 @@ b200_fact_profile_solve(b200_fact* F, int reps, double* ms_out)
 int
 b200_fact_solve(b200_fact* F, int nnz_rhs, const int* idx, const double* val, int dim)
 {
+  return b200_fact_solve_offset(F, nnz_rhs, idx, val, 0, dim);
+}
+
+int
+b200_fact_solve_offset(b200_fact* F, int nnz_rhs, const int* idx, const double* val, int offset, int dim)
+{
   if (!F)
   {
     return set_error(B200_ERR_ARG, "null handle");
@@ -851,7 +942,7 @@ b200_fact_solve(b200_fact* F, int nnz_rhs, const int* idx, const double* val, in
     B200_CUDA(cudaEventRecord(F->ev_c, F->stream));
     if (nnz_rhs > 0)
     {
-      if (idx[0] < 0 || idx[nnz_rhs - 1] >= dim)
+      if (offset < 0 || idx[0] < 0 || (long long)idx[nnz_rhs - 1] + offset >= dim)
       {
         return set_error(B200_ERR_ARG, "rhs index out of range");
       }
@@ -884,7 +975,7 @@ b200_fact_solve(b200_fact* F, int nnz_rhs, const int* idx, const double* val, in
         B200_CUDA(cudaEventRecord(F->ev_copy, F->stream));
       }
       copy_pending = direct;
-      enqueue_scatter_rhs(F->rhs.p, P.N, nnz_rhs, d_idx, idx[0], F->rhs_val.p, F->stream, eager);
+      enqueue_scatter_rhs(F->rhs.p, P.N, nnz_rhs, d_idx, idx[0], F->rhs_val.p, F->stream, eager, offset);
     }
     else
     {

@@ -71,7 +71,10 @@ void enqueue_residual_norms(const DevPlan& dp, const NumericBuffers& nb, const S
 
 // rhs[i] = 0 for all i, then rhs[idx[q]] = val[q]; idx == nullptr means the contiguous range
 // [first, first + nnz).
-void enqueue_scatter_rhs(double* rhs, int n, int nnz, const int* d_idx, int first, const double* d_val, cudaStream_t stream, LaunchCounter& lc);
+void enqueue_scatter_rhs(double* rhs, int n, int nnz, const int* d_idx, int first, const double* d_val, cudaStream_t stream, LaunchCounter& lc, int offset = 0);
+
+// val[q] = src[q] < 0 ? 1 : jval[src[q]]: the values of tril(K) gathered from the constraint Jacobian's (Plan::Ksrc)
+void enqueue_gather_kkt(int nnz, const int* d_src, const double* d_jval, double* d_val, cudaStream_t stream);
 
 // deterministic pseudo-random probe right-hand side
 void enqueue_probe_rhs(double* rhs, int n, cudaStream_t stream, LaunchCounter& lc);

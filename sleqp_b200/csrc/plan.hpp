@@ -130,6 +130,14 @@ struct Plan
   i64 nnzK_input = 0; // entries of the caller's CSC (== nnzK for lower-triangular input)
   uint64_t pattern_hash = 0, pattern_hash2 = 0, perm_hash = 0; // the plan cache is keyed by (N, nnzK_input, both pattern hashes)
 
+  // Plans built from (constraint Jacobian, working set) by b200_fact_set_kkt: the cache key is a hash of THOSE arrays
+  // (pattern_hash / pattern_hash2 / key_aux = nnz of the Jacobian), and Ksrc tells where every value of tril(K)
+  // comes from: -1 = the constant 1 (identity diagonal, row of an active bound), else an index into the Jacobian's
+  // values (standard_aug_jac.c:135-237)
+  bool kkt_keyed = false;
+  i64 key_aux    = 0;
+  std::vector<int> Ksrc;
+
   // node classification / index maps
   std::vector<int> e_of_k, r_of_k, k_of_e, k_of_r;
   std::vector<int> dE_src;                       // K-value index of d_e
@@ -205,6 +213,16 @@ bool valid_csc_header(int n, int nnz, const int* colptr, const int* rowidx, cons
 
 // two independent 64-bit hashes of (n, pattern, which diagonals are non-zero): returns the first, *second gets the other
 uint64_t hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only, uint64_t* second = nullptr);
+
+// Key of a KKT system given as (Jacobian pattern, working-set index maps): two independent hashes like hash_pattern.
+uint64_t hash_kkt(int num_vars, int num_cons, int nnz_jac, const int* jac_cols, const int* jac_rows, const int* var_index, const int* cons_index, int ws_size,
+                  uint64_t* second);
+
+// tril([I A_W^T; A_W 0]) exactly as the reference's fill_aug_jac lays it out (standard_aug_jac.c:135-237, lower_only):
+// per variable column the unit diagonal, the row of its active bound (if any), then its Jacobian entries in the rows of
+// the active constraints; empty columns for the working set. src: see Plan::Ksrc. Returns false on malformed input.
+bool build_kkt_lower(int num_vars, int num_cons, const int* jac_cols, const int* jac_rows, const int* var_index, const int* cons_index, int ws_size,
+                     std::vector<int>& colptr, std::vector<int>& rowidx, std::vector<int>& src);
 
 // Expands (perm, parent, colcount, supernodes) of the reduced system to the full order of K.
 void full_structure(const Plan& p, int* perm, int* parent, int* colcount, int* n_super_total, int* super_first);

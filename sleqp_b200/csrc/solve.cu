@@ -720,12 +720,24 @@ k_flow(const SweepTask* __restrict__ tasks,
 
 // ---- small utilities -----------------------------------------------------------------------------------
 __global__ void
-k_scatter(int nnz, const int* __restrict__ idx, int first, const double* __restrict__ val, double* __restrict__ out)
+k_scatter(int nnz, const int* __restrict__ idx, int first, const double* __restrict__ val, double* __restrict__ out, int offset)
 {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < nnz)
   {
-    out[idx ? idx[q] : first + q] = val[q];
+    out[(idx ? idx[q] : first + q) + offset] = val[q];
+  }
+}
+
+// values of tril(K) from the values of the constraint Jacobian (b200_fact_set_kkt): src < 0 = the constant 1
+__global__ void
+k_gather_kkt(int nnz, const int* __restrict__ src, const double* __restrict__ jval, double* __restrict__ val)
+{
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nnz)
+  {
+    const int sidx = src[q];
+    val[q]         = sidx < 0 ? 1.0 : jval[sidx];
   }
 }
 
@@ -1077,14 +1089,22 @@ enqueue_residual_norms(const DevPlan& dp, const NumericBuffers& nb, const SolveB
 }
 
 void
-enqueue_scatter_rhs(double* rhs, int n, int nnz, const int* d_idx, int first, const double* d_val, cudaStream_t stream, LaunchCounter& lc)
+enqueue_scatter_rhs(double* rhs, int n, int nnz, const int* d_idx, int first, const double* d_val, cudaStream_t stream, LaunchCounter& lc, int offset)
 {
   B200_CUDA(cudaMemsetAsync(rhs, 0, sizeof(double) * (size_t)n, stream));
   if (nnz > 0)
   {
-    k_scatter<<<nblocks(nnz, 256), 256, 0, stream>>>(nnz, d_idx, first, d_val, rhs);
+    k_scatter<<<nblocks(nnz, 256), 256, 0, stream>>>(nnz, d_idx, first, d_val, rhs, offset);
     lc.tick();
   }
+  B200_CUDA(cudaGetLastError());
+}
+
+void
+enqueue_gather_kkt(int nnz, const int* d_src, const double* d_jval, double* d_val, cudaStream_t stream)
+{
+  k_gather_kkt<<<nblocks(nnz, 256), 256, 0, stream>>>(nnz, d_src, d_jval, d_val);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   B200_CUDA(cudaGetLastError());
 }
 

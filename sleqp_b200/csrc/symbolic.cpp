@@ -179,6 +179,124 @@ hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double*
   return h.a;
 }
 
+uint64_t
+hash_kkt(int num_vars, int num_cons, int nnz_jac, const int* jac_cols, const int* jac_rows, const int* var_index, const int* cons_index, int ws_size, uint64_t* second)
+{
+  // four arrays, four threads when they are large (this is on the critical path of every set_iterate)
+  int hdr[4]    = {num_vars, num_cons, nnz_jac, ws_size};
+  Hash2 part[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+  auto run = [&](int q) {
+    const Hash2 seed = {(uint64_t)(0x4B4B54 + q), (uint64_t)(0xB2004B + q)};
+    switch (q)
+    {
+    case 0:
+      part[0] = hash_words(seed, jac_cols, sizeof(int) * (size_t)(num_vars + 1));
+      break;
+    case 1:
+      part[1] = hash_words(seed, jac_rows, sizeof(int) * (size_t)nnz_jac);
+      break;
+    case 2:
+      part[2] = hash_words(seed, var_index, sizeof(int) * (size_t)num_vars);
+      break;
+    default:
+      part[3] = hash_words(seed, cons_index, sizeof(int) * (size_t)num_cons);
+    }
+  };
+  if ((long long)num_vars + nnz_jac >= 400000)
+  {
+    std::thread pool[3];
+    for (int q = 1; q < 4; ++q)
+    {
+      pool[q - 1] = std::thread(run, q);
+    }
+    run(0);
+    for (auto& th : pool)
+    {
+      th.join();
+    }
+  }
+  else
+  {
+    for (int q = 0; q < 4; ++q)
+    {
+      run(q);
+    }
+  }
+  Hash2 h = hash_words({0x4B4B54, 0xB2004B}, hdr, sizeof(hdr));
+  for (int q = 0; q < 4; ++q)
+  {
+    h.a = mix64(h.a, part[q].a);
+    h.b = mix64b(h.b, part[q].b);
+  }
+  if (second)
+  {
+    *second = h.b;
+  }
+  return h.a;
+}
+
+bool
+build_kkt_lower(int num_vars, int num_cons, const int* jac_cols, const int* jac_rows, const int* var_index, const int* cons_index, int ws_size, std::vector<int>& colptr,
+                std::vector<int>& rowidx, std::vector<int>& src)
+{
+  const int n = num_vars, N = num_vars + ws_size;
+  colptr.assign((size_t)N + 1, 0);
+  rowidx.clear();
+  src.clear();
+  rowidx.reserve((size_t)n + (size_t)jac_cols[n] + 16);
+  src.reserve((size_t)n + (size_t)jac_cols[n] + 16);
+  for (int j = 0; j < n; ++j)
+  {
+    rowidx.push_back(j); // identity part first (standard_aug_jac.c:160)
+    src.push_back(-1);
+    int last = -1;
+    if (var_index[j] != -1)
+    {
+      if (var_index[j] < 0 || var_index[j] >= ws_size)
+      {
+        return false;
+      }
+      last = n + var_index[j];
+      rowidx.push_back(last); // unit row of the active bound (:171-176)
+      src.push_back(-1);
+    }
+    if (jac_cols[j + 1] < jac_cols[j])
+    {
+      return false;
+    }
+    for (int q = jac_cols[j]; q < jac_cols[j + 1]; ++q)
+    {
+      const int row = jac_rows[q];
+      if (row < 0 || row >= num_cons)
+      {
+        return false;
+      }
+      const int ci = cons_index[row];
+      if (ci == -1)
+      {
+        continue;
+      }
+      if (ci < 0 || ci >= ws_size || n + ci <= last) // rows must come out strictly increasing (mat.c:797-804)
+      {
+        return false;
+      }
+      last = n + ci;
+      rowidx.push_back(last);
+      src.push_back(q);
+    }
+    colptr[(size_t)j + 1] = (int)rowidx.size();
+    if (rowidx.size() > (size_t)0x7ffffff0)
+    {
+      return false;
+    }
+  }
+  for (int j = n; j < N; ++j)
+  {
+    colptr[(size_t)j + 1] = colptr[(size_t)n]; // empty columns of the working set (:221-226)
+  }
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------
 // Nested dissection on rooted level structures (George 1973; George & Liu 1978).
 // Subproblems are independent once split, so they are processed by a small pool of host threads

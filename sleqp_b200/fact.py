@@ -48,7 +48,7 @@ PLAN_FIELDS = {
         "e_of_k r_of_k k_of_e k_of_r dE_src Acsc_ptr Acsc_row Acsc_src Acsr_ptr Acsr_col Acsr_src "
         "Gsym_ptr Gsym_col Gsym_src perm pinv parent colcount sn_first sn_of_col sn_parent sn_level "
         "Ridx rel child_ptr child_idx Sgsrc Sterm_a Sterm_b Sterm_d sn_base sn_nt zero_sn lvl_ptr lvl_sn "
-        "inv_phase_ptr"
+        "inv_phase_ptr Ksrc"
     ).split()},
     **{k: np.int64 for k in "Rptr Lptr Wptr Sdest Sterm_ptr Uoff Tptr".split()},
 }
@@ -64,6 +64,18 @@ class Symbolic:
         colptr, rowidx, val = _i32(colptr), _i32(rowidx), _f64(val)
         check(lib().b200_symbolic_analyze(C.byref(self._h), int(n), int(len(rowidx)), _pi(colptr), _pi(rowidx), _pd(val), int(bool(lower_only))))
         self.n = int(n)
+
+    @classmethod
+    def from_kkt(cls, num_vars, num_cons, jac_cols, jac_rows, jac_data, var_index, cons_index, working_set_size):
+        """Analysis of the KKT system b200_fact_set_kkt builds from (constraint Jacobian, working-set index maps)."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        jac_cols, jac_rows, jac_data = _i32(jac_cols), _i32(jac_rows), _f64(jac_data)
+        var_index, cons_index = _i32(var_index), _i32(cons_index)
+        check(lib().b200_symbolic_analyze_kkt(C.byref(self._h), int(num_vars), int(num_cons), int(len(jac_rows)), _pi(jac_cols), _pi(jac_rows), _pd(jac_data),
+                                              _pi(var_index), _pi(cons_index), int(working_set_size)))
+        self.n = int(num_vars + working_set_size)
+        return self
 
     def stats(self) -> dict:
         s = Stats()
@@ -126,10 +138,19 @@ class Fact:
         check(lib().b200_fact_set_matrix(self._h, int(n), int(n), int(len(rowidx)), _pi(colptr), _pi(rowidx), _pd(val), int(bool(lower_only))))
         self._n = int(n)
 
-    def solve(self, idx, val, dim=None):
+    def set_kkt(self, num_vars, num_cons, jac_cols, jac_rows, jac_data, var_index, cons_index, working_set_size):
+        """sleqp_aug_jac_set_iterate with the KKT assembly on the device (b200_fact_set_kkt): the constraint Jacobian
+        (CSC) and the working set as index maps (-1 = not in the working set)."""
+        jac_cols, jac_rows, jac_data = _i32(jac_cols), _i32(jac_rows), _f64(jac_data)
+        var_index, cons_index = _i32(var_index), _i32(cons_index)
+        check(lib().b200_fact_set_kkt(self._h, int(num_vars), int(num_cons), int(len(jac_rows)), _pi(jac_cols), _pi(jac_rows), _pd(jac_data),
+                                      _pi(var_index), _pi(cons_index), int(working_set_size)))
+        self._n = int(num_vars + working_set_size)
+
+    def solve(self, idx, val, dim=None, offset=0):
         """sleqp_fact_solve (fact.c:83-89) with a sparse right-hand side of dimension `dim`."""
         idx, val = _i32(idx), _f64(val)
-        check(lib().b200_fact_solve(self._h, int(len(idx)), _pi(idx), _pd(val), int(self._n if dim is None else dim)))
+        check(lib().b200_fact_solve_offset(self._h, int(len(idx)), _pi(idx), _pd(val), int(offset), int(self._n if dim is None else dim)))
 
     def solution_dense(self, begin, end) -> np.ndarray:
         out = np.empty(int(end - begin), dtype=np.float64)

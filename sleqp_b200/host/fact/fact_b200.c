@@ -27,21 +27,11 @@
 // that the device library DMAs straight from / into them (b200_host_pin; a pageable buffer costs a staging copy and,
 // for solutions, a host pass over the slice). A vector that has been reallocated since (sleqp_vec_reserve) shows up
 // as a new pointer: whatever overlapped the new range is released first.
-#define B200_MAX_PINNED 16
-
-typedef struct
-{
-  char* ptr;
-  size_t bytes;
-} B200Pinned;
-
 typedef struct
 {
   b200_fact* handle;
   int num_rows;
-  B200Pinned pinned[B200_MAX_PINNED];
-  int num_pinned;
-  int next_evict;
+  SleqpB200Pins pins;
 } B200Data;
 
 // handle of the factorization that last ran set_matrix on this thread (one SleqpFact per solver thread,
@@ -54,8 +44,14 @@ sleqp_fact_b200_last_handle(void)
   return last_handle;
 }
 
-static void
-pin_buffer(B200Data* data, const void* buffer, size_t bytes)
+void
+sleqp_fact_b200_set_last_handle(b200_fact* handle)
+{
+  last_handle = handle;
+}
+
+void
+sleqp_b200_pin_buffer(SleqpB200Pins* data, const void* buffer, size_t bytes)
 {
   char* ptr = (char*)buffer;
 
@@ -75,7 +71,7 @@ pin_buffer(B200Data* data, const void* buffer, size_t bytes)
   // release whatever overlaps the new range (stale registrations of reallocated vectors)
   for (int i = 0; i < data->num_pinned;)
   {
-    B200Pinned* reg = data->pinned + i;
+    SleqpB200Pinned* reg = data->pinned + i;
 
     if (reg->ptr < ptr + bytes && ptr < reg->ptr + reg->bytes)
     {
@@ -88,9 +84,9 @@ pin_buffer(B200Data* data, const void* buffer, size_t bytes)
     }
   }
 
-  if (data->num_pinned == B200_MAX_PINNED)
+  if (data->num_pinned == SLEQP_B200_MAX_PINNED)
   {
-    B200Pinned* reg = data->pinned + (data->next_evict++ % B200_MAX_PINNED);
+    SleqpB200Pinned* reg = data->pinned + (data->next_evict++ % SLEQP_B200_MAX_PINNED);
     b200_host_unpin(reg->ptr);
     *reg = data->pinned[--data->num_pinned];
   }
@@ -98,8 +94,19 @@ pin_buffer(B200Data* data, const void* buffer, size_t bytes)
   // failure is not an error: the library falls back to its own staging buffer for pageable memory
   if (b200_host_pin(ptr, bytes) == B200_OK)
   {
-    data->pinned[data->num_pinned++] = (B200Pinned){ptr, bytes};
+    data->pinned[data->num_pinned++] = (SleqpB200Pinned){ptr, bytes};
   }
+}
+
+void
+sleqp_b200_unpin_all(SleqpB200Pins* data)
+{
+  for (int i = 0; i < data->num_pinned; ++i)
+  {
+    b200_host_unpin(data->pinned[i].ptr);
+  }
+
+  data->num_pinned = 0;
 }
 
 #define B200_CALL(x)                                                           \
@@ -152,7 +159,7 @@ b200_solve(void* fact_data, const SleqpVec* rhs)
 
   // sparse right-hand side goes over as-is; the scatter into the zeroed dense vector
   // (set_cache / reset_cache, fact_umfpack.c:185-205) happens on the device
-  pin_buffer(data, rhs->data, sizeof(double) * (size_t)rhs->nnz_max);
+  sleqp_b200_pin_buffer(&data->pins, rhs->data, sizeof(double) * (size_t)rhs->nnz_max);
 
   B200_CALL(
     b200_fact_solve(data->handle, rhs->nnz, rhs->indices, rhs->data, rhs->dim));
@@ -181,8 +188,8 @@ b200_solution(void* fact_data,
   SLEQP_CALL(sleqp_vec_resize(sol, dim));
   SLEQP_CALL(sleqp_vec_reserve(sol, dim));
 
-  pin_buffer(data, sol->data, sizeof(double) * (size_t)sol->nnz_max);
-  pin_buffer(data, sol->indices, sizeof(int) * (size_t)sol->nnz_max);
+  sleqp_b200_pin_buffer(&data->pins, sol->data, sizeof(double) * (size_t)sol->nnz_max);
+  sleqp_b200_pin_buffer(&data->pins, sol->indices, sizeof(int) * (size_t)sol->nnz_max);
 
   int nnz = 0;
 
@@ -224,10 +231,7 @@ b200_free(void** star)
     return SLEQP_OKAY;
   }
 
-  for (int i = 0; i < data->num_pinned; ++i)
-  {
-    b200_host_unpin(data->pinned[i].ptr);
-  }
+  sleqp_b200_unpin_all(&data->pins);
 
   if (last_handle == data->handle)
   {

@@ -61,17 +61,20 @@ def test_b200_backend_reproduces_reference_eqp_iterates(golden, case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("exe", ["eqp_harness_b200tr", "eqp_harness_b200aj"])
 @pytest.mark.parametrize("hess", ["callback", "matrix"])
 @pytest.mark.parametrize("case", list(CASES))
-def test_b200_tr_solver_plugin_reproduces_reference_steihaug(golden, case, hess):
+def test_b200_tr_solver_plugin_reproduces_reference_steihaug(golden, case, hess, exe):
     """host/tr/tr_b200.c registered through the reference's own tr_solver.c (sleqp_tr_solver_create /
     _solve / _current_rayleigh) over fact_b200.c, against what the reference's Steihaug solver computed over the
     reference LAPACK backend: steps, the dual of the trust region and the Rayleigh bounds, to 1e-8. Both Hessian modes:
-    the reference's matrix-free callback (sleqp_problem_hess_prod on the host) and a device matrix."""
-    if not os.path.exists(os.path.join(REF, "eqp_harness_b200tr")):
-        pytest.skip("oracle/_ref/eqp_harness_b200tr not shipped")
+    the reference's matrix-free callback (sleqp_problem_hess_prod on the host) and a device matrix. Second executable:
+    the same with host/aug_jac/b200_aug_jac.c (KKT assembled on the device from the Jacobian and the working set, SURVEY
+    section 8f rank 2) in place of the reference's standard_aug_jac.c."""
+    if not os.path.exists(os.path.join(REF, exe)):
+        pytest.skip(f"oracle/_ref/{exe} not shipped")
     want = golden(CASES[case][1])
-    out = subprocess.run([os.path.join(REF, "eqp_harness_b200tr"), *CASES[case][0], hess], check=True, capture_output=True, text=True, timeout=600)
+    out = subprocess.run([os.path.join(REF, exe), *CASES[case][0], hess], check=True, capture_output=True, text=True, timeout=600)
     got = {}
     for line in out.stdout.splitlines():
         parts = line.split()
