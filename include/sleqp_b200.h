@@ -221,9 +221,18 @@ B200_API int b200_mat_set(b200_mat* handle, int num_rows, int num_cols, int nnz,
 B200_API int b200_mat_mult_vec(b200_mat* handle, int nnz_x, const int* idx, const double* val, double* result_dense);
 /* result[num_cols] = A^T * v, v sparse; dense result, the glue drops |s| <= eps (mat.c:312-363). */
 B200_API int b200_mat_mult_vec_trans(b200_mat* handle, int nnz_v, const int* idx, const double* val, double* result_dense);
+/* The same product as a sparse vector, exactly what sleqp_mat_mult_vec_trans returns (mat.c:312-363: ascending column
+ * indices, entries with |s| <= eps dropped): sparsified on the device, only the kept entries are copied back.
+ * idx_out / val_out must hold num_cols entries. */
+B200_API int b200_mat_mult_vec_trans_sparse(b200_mat* handle, int nnz_v, const int* idx, const double* val, double eps, int* idx_out, double* val_out,
+                                            int* nnz_out);
 /* Device-resident forms: d_x/d_y dense device vectors. */
 B200_API int b200_mat_mult_vec_device(b200_mat* handle, const double* d_x, double* d_y);
 B200_API int b200_mat_mult_vec_trans_device(b200_mat* handle, const double* d_v, double* d_y);
+/* y = A x unless the device flag *d_skip is non-zero (then y is left alone): lets a device-resident loop that has
+ * already met its exit condition run out without touching its state (the projected CG enqueues several iterations
+ * ahead of the host). d_skip may be NULL. */
+B200_API int b200_mat_mult_vec_device_if(b200_mat* handle, const double* d_x, double* d_y, const int* d_skip);
 B200_API void* b200_mat_stream(b200_mat* handle);
 /* Launch this matrix's products on another CUDA stream (e.g. b200_fact_stream of the factorization the
  * products alternate with in the projected-CG loop); the handle does not own that stream. */

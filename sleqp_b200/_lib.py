@@ -58,8 +58,8 @@ SYMBOLS = [
     "b200_fact_solution_ptr", "b200_fact_solution_sparse", "b200_fact_solve_device", "b200_fact_refactor_device", "b200_fact_profile_solve", "b200_fact_profile_numeric", "b200_fact_rcond", "b200_fact_stats",
     "b200_fact_structure", "b200_fact_pivots", "b200_fact_stream", "b200_fact_device", "b200_fact_free", "b200_last_error",
     "b200_symbolic_analyze", "b200_symbolic_analyze_kkt", "b200_symbolic_stats", "b200_symbolic_structure", "b200_symbolic_export",
-    "b200_symbolic_free", "b200_mat_create", "b200_mat_set", "b200_mat_mult_vec", "b200_mat_mult_vec_trans",
-    "b200_mat_mult_vec_device", "b200_mat_mult_vec_trans_device", "b200_mat_stream", "b200_mat_set_stream", "b200_mat_free",
+    "b200_symbolic_free", "b200_mat_create", "b200_mat_set", "b200_mat_mult_vec", "b200_mat_mult_vec_trans", "b200_mat_mult_vec_trans_sparse",
+    "b200_mat_mult_vec_device", "b200_mat_mult_vec_device_if", "b200_mat_mult_vec_trans_device", "b200_mat_stream", "b200_mat_set_stream", "b200_mat_free",
     "b200_cg_create", "b200_cg_set_hess_callback", "b200_cg_solve", "b200_cg_solve_ex", "b200_cg_free", "b200_device_count", "b200_launch_count", "b200_host_pin", "b200_host_unpin",
 ]
 
@@ -106,8 +106,10 @@ def lib():
     L.b200_mat_set.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, ip, dp]
     L.b200_mat_mult_vec.argtypes = [vp, C.c_int, ip, dp, dp]
     L.b200_mat_mult_vec_trans.argtypes = [vp, C.c_int, ip, dp, dp]
+    L.b200_mat_mult_vec_trans_sparse.argtypes = [vp, C.c_int, ip, dp, C.c_double, ip, dp, ip]
     L.b200_mat_mult_vec_device.argtypes = [vp, vp, vp]
     L.b200_mat_mult_vec_trans_device.argtypes = [vp, vp, vp]
+    L.b200_mat_mult_vec_device_if.argtypes = [vp, vp, vp, vp]
     L.b200_mat_stream.argtypes = [vp]
     L.b200_mat_stream.restype = vp
     L.b200_mat_set_stream.argtypes = [vp, vp]

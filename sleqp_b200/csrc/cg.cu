@@ -83,6 +83,134 @@ k_cg_beta(double* S)
   S[9]  = S[6];
 }
 
+// ---- device-controlled loop (Hessian on the device): the host enqueues iterations ahead, the exit tests run in
+// one-thread kernels and every kernel of the CG checks the exit flag first, so that the state of the exit iteration
+// (z, d, B d) survives whatever has been enqueued behind it.
+// Scalars S: [0..2] d.Bd, d.d, Bd.Bd   [3..5] z+.d, z+.z+, d.d   [6..8] r.g, r.r, g.g   [9] current r.g   [10] alpha
+// [11] beta   [12] |z|^2   [13] min Rayleigh   [14] max Rayleigh   [15] iterations completed
+// Exit record E (ints): [0] flag (0 running, 1 + B200_CG_* otherwise)   [1] iteration of the exit
+// Exit scalars X: [0] d.Bd   [1] d.d   [2] |z|^2 at the exit
+__global__ void
+k_cgd_dot3(int n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out, const int* __restrict__ flag)
+{
+  if (*flag)
+  {
+    return;
+  }
+  double xy = 0.0, xx = 0.0, yy = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  {
+    const double a = x[i], b = y[i];
+    xy += a * b;
+    xx += a * a;
+    yy += b * b;
+  }
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    xy += __shfl_xor_sync(0xffffffffu, xy, o);
+    xx += __shfl_xor_sync(0xffffffffu, xx, o);
+    yy += __shfl_xor_sync(0xffffffffu, yy, o);
+  }
+  if ((threadIdx.x & 31) == 0)
+  {
+    atomicAdd(out + 0, xy);
+    atomicAdd(out + 1, xx);
+    atomicAdd(out + 2, yy);
+  }
+}
+
+__global__ void
+k_cgd_axpby(int n, double a, const double* x, const double* __restrict__ b, const double* y, double* out, const int* __restrict__ flag)
+{
+  if (*flag)
+  {
+    return;
+  }
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+  {
+    out[i] = a * x[i] + (*b) * y[i];
+  }
+}
+
+// loop top (steihaug_solver.c:318-327): interior exit when |r.g| < tol^2; otherwise the dot-product slots are cleared
+__global__ void
+k_cgd_top(double* S, int* E, double tol_sq, int iteration)
+{
+  if (E[0])
+  {
+    return;
+  }
+  if (fabs(S[9]) < tol_sq)
+  {
+    E[0] = 1 + B200_CG_INTERIOR;
+    E[1] = iteration;
+    return;
+  }
+  for (int q = 0; q < 9; ++q)
+  {
+    S[q] = 0.0;
+  }
+}
+
+// after d.Bd: Rayleigh bounds (:150-173), negative curvature exit (:349), alpha (:405)
+__global__ void
+k_cgd_curvature(double* S, int* E, double* X, int iteration)
+{
+  if (E[0])
+  {
+    return;
+  }
+  const double dBd = S[0], dd = S[1];
+  if (dd != 0.0)
+  {
+    S[13] = fmin(S[13], dBd / dd);
+    S[14] = fmax(S[14], dBd / dd);
+  }
+  if (dBd <= 0.0)
+  {
+    E[0] = 1 + B200_CG_NEG_CURVATURE;
+    E[1] = iteration;
+    X[0] = dBd;
+    X[1] = dd;
+    X[2] = S[12];
+    return;
+  }
+  S[10] = S[9] / dBd;
+}
+
+// after |z + alpha d|^2: boundary exit (:419)
+__global__ void
+k_cgd_radius(double* S, int* E, double* X, double radius_sq, int iteration)
+{
+  if (E[0])
+  {
+    return;
+  }
+  if (S[4] >= radius_sq)
+  {
+    E[0] = 1 + B200_CG_BOUNDARY;
+    E[1] = iteration;
+    X[0] = S[0];
+    X[1] = S[1];
+    X[2] = S[12];
+  }
+}
+
+// after the new r.g: beta (:467-469), |z|^2 of the accepted iterate, iteration count
+__global__ void
+k_cgd_tail(double* S, const int* E)
+{
+  if (E[0])
+  {
+    return;
+  }
+  S[11] = S[6] / S[9];
+  S[9]  = S[6];
+  S[12] = S[4];
+  S[15] += 1.0;
+}
+
 } // namespace b200
 
 struct b200_cg
@@ -96,7 +224,8 @@ struct b200_cg
   cudaStream_t stream = nullptr;
   int n = 0, N = 0;
   DevBuf<double> z, znext, rfull, gfull, d, dnext, Bd, scal;
-  DevBuf<int> g_idx;
+  DevBuf<int> g_idx, exit_rec;
+  PinnedBuf<int> h_exit;
   DevBuf<double> g_val;
   PinnedBuf<double> h_scal, h_step, h_val;
   PinnedBuf<int> h_idx;
@@ -178,8 +307,8 @@ b200_cg_create(b200_cg** handle, b200_fact* fact, b200_mat* hess)
         return rc;
       }
     }
-    C->scal.reserve(16);
-    C->h_scal.reserve(16);
+    C->scal.reserve(32);
+    C->h_scal.reserve(32);
     *handle = C.release();
     return (int)B200_OK;
   });
@@ -379,7 +508,141 @@ b200_cg_solve_ex(b200_cg* C,
     {
       return finish(C->z.p, 0, B200_CG_INTERIOR);
     }
-    // One host synchronisation per iteration. The scalars of the recurrences stay on the device:
+    if (C->hess)
+    {
+      // ---- Hessian on the device: the whole loop runs ahead of the host, CHUNK iterations per synchronisation ----
+      constexpr int CHUNK = 8;
+      double* S = C->scal.p;
+      C->exit_rec.reserve(4);
+      C->h_exit.reserve(4);
+      int* E    = C->exit_rec.p;
+      double* X = S + 16;
+      {
+        double init[20] = {0};
+        init[9]  = r_dot_g;
+        init[13] = 1.0;
+        init[14] = 1.0;
+        std::memcpy(C->h_scal.p, init, sizeof(init));
+        B200_CUDA(cudaMemcpyAsync(S, C->h_scal.p, sizeof(init), cudaMemcpyHostToDevice, s));
+        B200_CUDA(cudaMemsetAsync(E, 0, 4 * sizeof(int), s));
+      }
+      double* zb[2] = {C->z.p, C->znext.p};
+      double* db[2] = {C->d.p, C->dnext.p};
+      const unsigned gb = nb(n), gd = std::min(nb(n), 592u);
+      auto enqueue_iteration = [&](int it) -> int {
+        double* z_cur = zb[it & 1];
+        double* z_new = zb[(it + 1) & 1];
+        double* d_cur = db[it & 1];
+        double* d_new = db[(it + 1) & 1];
+        k_cgd_top<<<1, 1, 0, s>>>(S, E, tol_sq, it);
+        int hrc = b200_mat_mult_vec_device_if(C->hess, d_cur, C->Bd.p, E); //       (:339)
+        if (hrc != B200_OK)
+        {
+          return hrc;
+        }
+        k_cgd_dot3<<<gd, 256, 0, s>>>(n, d_cur, C->Bd.p, S, E);
+        k_cgd_curvature<<<1, 1, 0, s>>>(S, E, X, it);
+        k_cgd_axpby<<<gb, 256, 0, s>>>(n, 1.0, z_cur, S + 10, d_cur, z_new, E); // z+ = z + alpha d
+        k_cgd_dot3<<<gd, 256, 0, s>>>(n, z_new, d_cur, S + 3, E);
+        k_cgd_radius<<<1, 1, 0, s>>>(S, E, X, trust_radius * trust_radius, it);
+        k_cgd_axpby<<<gb, 256, 0, s>>>(n, 1.0, r, S + 10, C->Bd.p, r, E); // r += alpha B d  (:449-456)
+        int prc2 = project();                                              // g = P[r]        (:459)
+        if (prc2 != B200_OK)
+        {
+          return prc2;
+        }
+        k_cgd_dot3<<<gd, 256, 0, s>>>(n, r, g, S + 6, E);
+        k_cgd_tail<<<1, 1, 0, s>>>(S, E);
+        k_cgd_axpby<<<gb, 256, 0, s>>>(n, -1.0, g, S + 11, d_cur, d_new, E); // d+ = -g + beta d (:472-479)
+        g_launches.fetch_add(11, std::memory_order_relaxed);
+        return (int)B200_OK;
+      };
+      int enq = 0;
+      for (;;)
+      {
+        const int upto = max_iter >= 0 ? std::min(max_iter, enq + CHUNK) : enq + CHUNK;
+        for (; enq < upto; ++enq)
+        {
+          int erc = enqueue_iteration(enq);
+          if (erc != B200_OK)
+          {
+            return erc;
+          }
+        }
+        if (max_iter >= 0 && enq == max_iter)
+        {
+          // the loop-top test of the iteration behind the cap (an interior exit there still counts, :318 precedes :302
+          // only for the NEXT pass: the reference tests the cap first, so nothing more is enqueued)
+        }
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaMemcpyAsync(C->h_exit.p, E, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaMemcpyAsync(C->h_scal.p, S, 20 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaStreamSynchronize(s));
+        const int flag = C->h_exit.p[0];
+        ray_min = C->h_scal.p[13];
+        ray_max = C->h_scal.p[14];
+        if (flag)
+        {
+          const int it   = C->h_exit.p[1];
+          const int kind = flag - 1;
+          double* z_cur  = zb[it & 1];
+          double* z_new  = zb[(it + 1) & 1];
+          double* d_cur  = db[it & 1];
+          double* d_new  = db[(it + 1) & 1];
+          if (kind == B200_CG_INTERIOR)
+          {
+            return finish(z_cur, it, B200_CG_INTERIOR);
+          }
+          const double dBd = C->h_scal.p[16], d_nrm_sq = C->h_scal.p[17], z_nrm_sq_x = C->h_scal.p[18];
+          if (kind == B200_CG_NEG_CURVATURE) //                                 (:349-402)
+          {
+            double zs[3];
+            dot3(C, z_cur, d_cur, zs);
+            const double z_dot_d = zs[0];
+            const double inner   = z_dot_d * z_dot_d - d_nrm_sq * (z_nrm_sq_x - trust_radius * trust_radius);
+            const double tau_min = 1. / d_nrm_sq * (-z_dot_d - std::sqrt(inner));
+            const double tau_max = 1. / d_nrm_sq * (-z_dot_d + std::sqrt(inner));
+            double gs[3], zbd[3];
+            B200_CUDA(cudaMemsetAsync(z_new, 0, sizeof(double) * (size_t)n, s));
+            if (nnz_g > 0)
+            {
+              LaunchCounter lc;
+              enqueue_scatter_rhs(z_new, n, nnz_g, C->g_idx.p, 0, C->g_val.p, s, lc);
+            }
+            dot3(C, z_new, d_cur, gs);
+            dot3(C, z_cur, C->Bd.p, zbd);
+            const double gd_ = gs[0], zBd = zbd[0];
+            const double tau_min_obj = tau_min * ((gd_ + zBd) + 0.5 * tau_min * dBd);
+            const double tau_max_obj = tau_max * ((gd_ + zBd) + 0.5 * tau_max * dBd);
+            const double tau         = (tau_min_obj < tau_max_obj) ? tau_min : tau_max;
+            axpby(C, 1.0, z_cur, tau, d_cur, z_new);
+            return finish(z_new, it, B200_CG_NEG_CURVATURE);
+          }
+          // boundary (:419-441, tr_util.c:9-50)
+          double zs[3];
+          dot3(C, z_cur, d_cur, zs);
+          const double prev_dot_d = zs[0];
+          const double p_norm = std::sqrt(zs[1]), d_norm = std::sqrt(zs[2]);
+          const double inner  = prev_dot_d * prev_dot_d - d_norm * d_norm * (p_norm * p_norm - trust_radius * trust_radius);
+          const double factor = 1. / (d_norm * d_norm) * (-prev_dot_d + std::sqrt(inner));
+          axpby(C, 1.0, z_cur, factor, d_cur, z_new);
+          int drc = boundary_dual(z_new, d_new, C->Bd.p);
+          if (drc != B200_OK)
+          {
+            return drc;
+          }
+          return finish(z_new, it, B200_CG_BOUNDARY);
+        }
+        if (max_iter >= 0 && enq >= max_iter)
+        {
+          // cap reached without an exit: the reference tests the cap before the convergence test of the next pass
+          // and returns the zero step (:302-305)
+          return finish(nullptr, max_iter, B200_CG_MAX_ITER);
+        }
+      }
+    }
+    // ---- matrix-free Hessian (host callback): one host synchronisation per iteration ------------------------------
+    // The scalars of the recurrences stay on the device:
     //   S[0..2] = (d.Bd, d.d, Bd.Bd)   S[3..5] = (z+.d, z+.z+, d.d)   S[6..8] = (r.g, r.r, g.g) after the update
     //   S[9] = current r.g   S[10] = alpha   S[11] = beta
     // so the whole iteration -- SpMV, step, residual update, projection, new direction -- is enqueued without

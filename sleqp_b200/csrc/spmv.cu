@@ -11,7 +11,7 @@
 // contribute nothing there and exact zeros here).
 // Both are bandwidth-bound: one pass over (ptr, idx, val) plus the dense vectors; a sub-warp of
 // G lanes works on one row/column, G chosen from the average segment length.
-#include "device.cuh"
+#include "numeric.cuh"
 
 #include <cstring>
 
@@ -27,8 +27,13 @@ k_spmv_gather(int nseg,
               const int* __restrict__ idx,
               const double* __restrict__ val,
               const double* __restrict__ x,
-              double* __restrict__ y)
+              double* __restrict__ y,
+              const int* __restrict__ skip) // optional device flag: non-zero = leave y alone (device-side control flow of the CG)
 {
+  if (skip && *skip)
+  {
+    return;
+  }
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long seg  = gtid / G;
   const int gl         = threadIdx.x % G;
@@ -73,7 +78,7 @@ k_scatter_sparse(int nnz, const int* __restrict__ idx, int first, const double* 
 }
 
 static void
-launch_spmv(int nseg, long long nnz, const int* ptr, const int* idx, const double* val, const double* x, double* y, cudaStream_t s)
+launch_spmv(int nseg, long long nnz, const int* ptr, const int* idx, const double* val, const double* x, double* y, cudaStream_t s, const int* skip = nullptr)
 {
   if (nseg <= 0)
   {
@@ -82,7 +87,7 @@ launch_spmv(int nseg, long long nnz, const int* ptr, const int* idx, const doubl
   const double avg = (double)nnz / (double)nseg;
   const int T      = 256;
 #define B200_SPMV(G)                                                                                                    \
-  k_spmv_gather<G><<<(unsigned)(((long long)nseg * G + T - 1) / T), T, 0, s>>>(nseg, ptr, idx, val, x, y)
+  k_spmv_gather<G><<<(unsigned)(((long long)nseg * G + T - 1) / T), T, 0, s>>>(nseg, ptr, idx, val, x, y, skip)
   if (avg <= 4.0)
   {
     B200_SPMV(1);
@@ -123,8 +128,9 @@ struct b200_mat
   bool have = false;
   std::vector<int> h_cols, h_rows; // cached pattern
   DevBuf<int> cols, rows, csr_ptr, csr_col, csr_src;
-  DevBuf<double> data, csr_val, x, y, sp_val;
-  DevBuf<int> sp_idx;
+  DevBuf<double> data, csr_val, x, y, sp_val, cp_val;
+  DevBuf<int> sp_idx, cp_idx, cp_cnt;
+  PinnedBuf<int> h_cnt;
   PinnedBuf<double> h_val, h_out;
   PinnedBuf<int> h_idx;
 };
@@ -345,6 +351,20 @@ b200_mat_mult_vec_device(b200_mat* M, const double* d_x, double* d_y)
 }
 
 int
+b200_mat_mult_vec_device_if(b200_mat* M, const double* d_x, double* d_y, const int* d_skip)
+{
+  if (!M || !M->have || !d_x || !d_y)
+  {
+    return set_error(B200_ERR_STATE, "matrix not set or null vector");
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaSetDevice(M->device));
+    launch_spmv(M->num_rows, M->nnz, M->csr_ptr.p, M->csr_col.p, M->csr_val.p, d_x, d_y, M->stream, d_skip);
+    return (int)B200_OK;
+  });
+}
+
+int
 b200_mat_mult_vec_trans_device(b200_mat* M, const double* d_v, double* d_y)
 {
   if (!M || !M->have || !d_v || !d_y)
@@ -414,6 +434,55 @@ b200_mat_mult_vec_trans(b200_mat* M, int nnz_v, const int* idx, const double* va
     {
       std::memcpy(result_dense, M->h_out.p, sizeof(double) * (size_t)M->num_cols);
     }
+    return (int)B200_OK;
+  });
+}
+
+int
+b200_mat_mult_vec_trans_sparse(b200_mat* M, int nnz_v, const int* idx, const double* val, double eps, int* idx_out, double* val_out, int* nnz_out)
+{
+  if (!M || !M->have)
+  {
+    return set_error(B200_ERR_STATE, "matrix not set");
+  }
+  if (!nnz_out || (M->num_cols > 0 && (!idx_out || !val_out)))
+  {
+    return set_error(B200_ERR_ARG, "null output");
+  }
+  int rc = check_sparse(nnz_v, idx, val, M->num_rows);
+  if (rc != B200_OK)
+  {
+    return rc;
+  }
+  return guarded([&]() {
+    B200_CUDA(cudaSetDevice(M->device));
+    const int n = M->num_cols;
+    if (n == 0)
+    {
+      *nnz_out = 0;
+      return (int)B200_OK;
+    }
+    stage_sparse(M, M->num_rows, nnz_v, idx, val, M->x.p);
+    launch_spmv(n, M->nnz, M->cols.p, M->rows.p, M->data.p, M->x.p, M->y.p, M->stream);
+    // the result is sparsified on the device (mat.c:355-358: entries with |s| <= eps are dropped) and only the kept
+    // entries cross the bus: a product with a few violated-constraint multipliers touches a few columns
+    const int nchunks = compact_chunks(n);
+    M->cp_idx.reserve((size_t)n);
+    M->cp_val.reserve((size_t)n);
+    M->cp_cnt.reserve((size_t)nchunks + 1);
+    M->h_cnt.reserve(2);
+    LaunchCounter eager;
+    enqueue_compact(M->y.p, n, eps, M->cp_cnt.p, M->cp_idx.p, M->cp_val.p, M->stream, eager);
+    B200_CUDA(cudaMemcpyAsync(M->h_cnt.p, M->cp_cnt.p + nchunks, sizeof(int), cudaMemcpyDeviceToHost, M->stream));
+    B200_CUDA(cudaStreamSynchronize(M->stream));
+    const int kept = M->h_cnt.p[0];
+    if (kept > 0)
+    {
+      B200_CUDA(cudaMemcpyAsync(val_out, M->cp_val.p, sizeof(double) * (size_t)kept, cudaMemcpyDeviceToHost, M->stream));
+      B200_CUDA(cudaMemcpyAsync(idx_out, M->cp_idx.p, sizeof(int) * (size_t)kept, cudaMemcpyDeviceToHost, M->stream));
+      B200_CUDA(cudaStreamSynchronize(M->stream));
+    }
+    *nnz_out = kept;
     return (int)B200_OK;
   });
 }

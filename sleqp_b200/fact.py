@@ -267,6 +267,15 @@ class Mat:
         keep = np.nonzero(np.abs(out) > eps)[0].astype(np.int32)
         return keep, out[keep]
 
+    def mult_vec_trans_sparse(self, idx, val, eps=0.0):
+        """Same product, sparsified on the device: only the kept entries come back (b200_mat_mult_vec_trans_sparse)."""
+        idx, val = _i32(idx), _f64(val)
+        oi = np.empty(max(self.num_cols, 1), dtype=np.int32)
+        ov = np.empty(max(self.num_cols, 1), dtype=np.float64)
+        nnz = C.c_int()
+        check(lib().b200_mat_mult_vec_trans_sparse(self._h, int(len(idx)), _pi(idx), _pd(val), float(eps), _pi(oi), _pd(ov), C.byref(nnz)))
+        return oi[: nnz.value].copy(), ov[: nnz.value].copy()
+
     def set_stream(self, stream_ptr: int):
         check(lib().b200_mat_set_stream(self._h, C.c_void_p(stream_ptr)))
 

@@ -17,13 +17,14 @@
 #include "error.h"
 #include "mem.h"
 
+#include "fact/fact_b200.h"
+
 struct SleqpMatB200
 {
   b200_mat* handle;
   int num_rows;
   int num_cols;
-  double* dense; // result of the transposed product before it is sparsified
-  int dense_size;
+  SleqpB200Pins pins; // page-locked caller arrays (matrix values, vectors, results): DMA without staging copies
 };
 
 #define B200_CALL(x)                                                           \
@@ -68,6 +69,10 @@ sleqp_mat_b200_update(SleqpMatB200* mirror, const SleqpMat* matrix)
   mirror->num_rows = sleqp_mat_num_rows(matrix);
   mirror->num_cols = sleqp_mat_num_cols(matrix);
 
+  sleqp_b200_pin_buffer(&mirror->pins,
+                        sleqp_mat_data(matrix),
+                        sizeof(double) * (size_t)sleqp_mat_nnz(matrix));
+
   B200_CALL(b200_mat_set(mirror->handle,
                          mirror->num_rows,
                          mirror->num_cols,
@@ -85,6 +90,13 @@ sleqp_mat_b200_mult_vec(SleqpMatB200* mirror,
                         double* result)
 {
   assert(mirror->num_cols == vector->dim);
+
+  sleqp_b200_pin_buffer(&mirror->pins,
+                        vector->data,
+                        sizeof(double) * (size_t)vector->nnz_max);
+  sleqp_b200_pin_buffer(&mirror->pins,
+                        result,
+                        sizeof(double) * (size_t)mirror->num_rows);
 
   B200_CALL(b200_mat_mult_vec(mirror->handle,
                               vector->nnz,
@@ -104,21 +116,22 @@ sleqp_mat_b200_mult_vec_trans(SleqpMatB200* mirror,
   assert(mirror->num_rows == vector->dim);
   assert(mirror->num_cols == result->dim);
 
-  if (mirror->dense_size < mirror->num_cols)
-  {
-    SLEQP_CALL(sleqp_realloc(&mirror->dense, mirror->num_cols));
-    mirror->dense_size = mirror->num_cols;
-  }
+  // sparsified on the device like mat.c:355-358 (|s| <= eps dropped): only the kept entries come back
+  SLEQP_CALL(sleqp_vec_clear(result));
+  SLEQP_CALL(sleqp_vec_reserve(result, mirror->num_cols));
 
-  B200_CALL(b200_mat_mult_vec_trans(mirror->handle,
-                                    vector->nnz,
-                                    vector->indices,
-                                    vector->data,
-                                    mirror->dense));
+  int nnz = 0;
 
-  // entries with |s| <= eps are dropped like mat.c:355-358 does
-  SLEQP_CALL(
-    sleqp_vec_set_from_raw(result, mirror->dense, mirror->num_cols, eps));
+  B200_CALL(b200_mat_mult_vec_trans_sparse(mirror->handle,
+                                           vector->nnz,
+                                           vector->indices,
+                                           vector->data,
+                                           eps,
+                                           result->indices,
+                                           result->data,
+                                           &nnz));
+
+  result->nnz = nnz;
 
   return SLEQP_OKAY;
 }
@@ -133,9 +146,9 @@ sleqp_mat_b200_free(SleqpMatB200** star)
     return SLEQP_OKAY;
   }
 
-  B200_CALL(b200_mat_free(&mirror->handle));
+  sleqp_b200_unpin_all(&mirror->pins);
 
-  sleqp_free(&mirror->dense);
+  B200_CALL(b200_mat_free(&mirror->handle));
 
   sleqp_free(star);
 

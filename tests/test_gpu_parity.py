@@ -257,6 +257,10 @@ def test_spmv_on_workloads():
             ti, tv = m_.mult_vec_trans(vi, vv, eps=0.0)
             oi, ov = orc.mat_mult_vec_trans(A.shape[1], A.indptr, A.indices, A.data, vi, vv, A.shape[0], 0.0)
             assert np.abs(orc.vec_to_raw(ti, tv, A.shape[1]) - orc.vec_to_raw(oi, ov, A.shape[1])).max() <= 1e-12 * max(1.0, np.abs(ov).max())
+            # the same product sparsified on the device (what the SpMV glue hands back as a SleqpVec)
+            si, sv = m_.mult_vec_trans_sparse(vi[::50], vv[::50], eps=1e-14)
+            oi2, ov2 = orc.mat_mult_vec_trans(A.shape[1], A.indptr, A.indices, A.data, vi[::50], vv[::50], A.shape[0], 1e-14)
+            assert np.array_equal(si, oi2) and np.abs(sv - ov2).max() <= 1e-12 * max(1.0, np.abs(ov2).max())
             # linearity: A(2x) = 2 A x exactly in binary floating point
             assert np.array_equal(m_.mult_vec(xi, 2.0 * xv), 2.0 * y)
 
