@@ -656,7 +656,8 @@ def run_ours(args, rank, world, local_rank):
             # headline e2e: the shipped drop-in as SLEQP would drive it (reference code on top, host vectors)
             e2e = {"value": ref_e2e["iters_per_s"], "unit": UNIT, "h2d_bytes_per_step": ref_e2e["h2d_bytes_per_step"], "d2h_bytes_per_step": ref_e2e["d2h_bytes_per_step"],
                    "ms_per_step": ref_e2e["ms_per_step"], "factor_ms": ref_e2e["set_iterate_ms"], "solve_ms": ref_e2e["solve_ms"],
-                   "via": "reference-driven: unmodified sleqp aug_jac / working-step / TR-solver code (oracle/_ref/eqp_step_b200) over host/fact_b200.c + host/tr_b200.c",
+                   "via": "reference-driven: the reference's own problem / iterate / working-set / aug_jac.c / tr_solver.c / SleqpVec code (oracle/_ref/eqp_step_b200, "
+                          "unmodified sources) calling the shipped plugins host/aug_jac/b200_aug_jac.c, host/tr/tr_b200.c, host/sparse/mat_b200.c with host vectors",
                    "detail": ref_e2e, "c_abi": main["e2e"]}
         elif ref_e2e:
             e2e["reference_driver_error"] = ref_e2e["error"]
