@@ -130,11 +130,11 @@ def ncu_traffic_per_launch(kernel, workload):
 
 def pick_3d_grid(free_bytes):
     """Config 4: the nominal g = 159 needs ~0.8 TB of factor, so the grid is the largest one whose
-    three panel copies (L, Mt, Mr) + update workspace + vectors fit the free HBM. Panel entries grow like
-    1.76e9 (g/96)^4.1 (measured g = 48..96, profiles/r01_run_3d_g48_to_g96.txt); 4 copies' worth, 30 % headroom."""
-    for g in (112, 104, 96, 88, 80, 64, 48):
-        need = 4.0 * 8 * 1.76e9 * (g / 96.0) ** 4.1
-        if need <= 0.7 * free_bytes:
+    three panel copies (L, Mt, Mr), update workspace, inversion scratch and vectors fit the free HBM with headroom.
+    Panel entries measured: 1.76e9 at g = 96, 2.59e9 at g = 104 (profiles/r01_run_3d_g48_to_g96.txt, r02_run_3d_g104.txt),
+    growing like g^4.1..4.8; about 3.6 panel copies' worth of memory in total."""
+    for g, entries in ((104, 2.59e9), (96, 1.76e9), (88, 1.25e9), (80, 0.84e9), (64, 0.352e9), (48, 0.104e9)):
+        if 1.05 * 8 * 3.6 * entries <= 0.55 * free_bytes:
             return g
     return 32
 

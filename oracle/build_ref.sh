@@ -119,3 +119,49 @@ if [ -f "$HOST/fact/fact_b200.c" ] && [ -f "$REPO/sleqp_b200/libsleqp_b200.so" ]
   gcc $HFLAGS -DHARNESS_B200_TR -DHARNESS_B200_AUG_JAC "$HERE/eqp_harness.c" -o "$OUT/eqp_harness_b200aj" $LINK
   gcc $HFLAGS -DHARNESS_B200_TR -DHARNESS_B200_AUG_JAC -DHARNESS_TIMING "$HERE/eqp_harness.c" -o "$OUT/eqp_step_b200" $LINK
 fi
+
+# ---- the whole reference solver (sleqp_solver_solve) over an LP backend that exists here ---------------------------
+# Every source of src/main except the backends whose libraries are absent (SuiteSparse, MUMPS, HSL, HiGHS, Gurobi,
+# trlib); the LP backend is sleqp_b200/host/lp/lpi_simplex.c, the factorization either the
+# reference's LAPACK backend or ours. sleqp_trlib_solver_create is a stub that raises (SLEQP_TR_SOLVER_CG is selected).
+FULL=""
+mkdir -p "$OUT/objfull"
+for f in $(cd "$SRC" && find . -name '*.c' | grep -v -E 'fact_(cholmod|ma27|ma57|ma86|ma97|mumps|spqr|umfpack|lapack)|cholmod_helpers|hsl_matrix|lpi_gurobi|lpi_highs|trlib_solver|mpi_utils' | sort); do
+  o="$OUT/objfull/$(echo "$f" | sed 's|^\./||' | tr '/' '_' | sed 's/\.c$/.o/')"
+  if [ ! -f "$o" ] || [ "$SRC/$f" -nt "$o" ]; then gcc $CFLAGS -c "$SRC/$f" -o "$o"; fi
+  FULL="$FULL $o"
+done
+cat > "$OUT/obj/trlib_stub.c" <<'EOC'
+#include "tr/trlib_solver.h"
+#include "error.h"
+SLEQP_RETCODE
+sleqp_trlib_solver_create(SleqpTRSolver** star, SleqpProblem* problem, SleqpSettings* settings)
+{
+  (void)star; (void)problem; (void)settings;
+  sleqp_raise(SLEQP_INTERNAL_ERROR, "trlib is absent in this environment: select SLEQP_TR_SOLVER_CG");
+}
+EOC
+gcc $CFLAGS -I"$SRC/tr" -c "$OUT/obj/trlib_stub.c" -o "$OUT/obj/trlib_stub.o"
+gcc $CFLAGS -I"$HOST" -I"$SRC/lp" -c "$HOST/lp/lpi_simplex.c" -o "$OUT/obj/lpi_simplex.o"
+gcc -shared -o "$OUT/libsleqp_full_lapack.so" $FULL "$OUT/obj/fact_lapack.o" "$OUT/obj/lapack_shim.o" "$OUT/obj/lpi_simplex.o" "$OUT/obj/trlib_stub.o" \
+    "$OPENBLAS" -Wl,-rpath,"$(dirname "$OPENBLAS")" -lm
+echo "built $OUT/libsleqp_full_lapack.so"
+gcc $CFLAGS -I"$SRC/fact" -I"$SRC/aug_jac" -I"$SRC/tr" "$HERE/full_solve.c" -o "$OUT/full_solve_lapack" -L"$OUT" -lsleqp_full_lapack -Wl,-rpath,'$ORIGIN' -lm
+if [ -f "$OUT/obj/fact_b200.o" ]; then
+  # the reference tree as the integration patch leaves it: newton.c / trial_point.c select the B200 TR solver and augmented Jacobian
+  mkdir -p "$OUT/patched/src/main" "$OUT/patched/cmake"
+  cp "$SRC/newton.c" "$SRC/trial_point.c" "$OUT/patched/src/main/"
+  cp "$REF/cmake/SearchFact.cmake" "$OUT/patched/cmake/"
+  (cd "$OUT/patched" && patch -p1 -s < "$REPO/cmake/sleqp_b200_backend.patch")
+  FULLB=""
+  for o in $FULL; do case "$o" in *objfull/newton.o|*objfull/trial_point.o) ;; *) FULLB="$FULLB $o";; esac; done
+  for f in newton trial_point; do
+    gcc $CFLAGS -I"$HOST" -I"$REPO/include" -c "$OUT/patched/src/main/$f.c" -o "$OUT/obj/${f}_b200.o"
+    FULLB="$FULLB $OUT/obj/${f}_b200.o"
+  done
+  gcc -shared -o "$OUT/libsleqp_full_b200.so" $FULLB $GLUE "$OUT/obj/lpi_simplex.o" "$OUT/obj/trlib_stub.o" \
+      -L"$REPO/sleqp_b200" -lsleqp_b200 -Wl,-rpath,'$ORIGIN/../../sleqp_b200' -lm
+  echo "built $OUT/libsleqp_full_b200.so"
+  gcc $CFLAGS -I"$SRC/fact" -I"$SRC/aug_jac" -I"$SRC/tr" "$HERE/full_solve.c" -o "$OUT/full_solve_b200" -L"$OUT" -lsleqp_full_b200 -Wl,-rpath,'$ORIGIN' \
+      -Wl,-rpath,'$ORIGIN/../../sleqp_b200' -L"$REPO/sleqp_b200" -lsleqp_b200 -lm
+fi

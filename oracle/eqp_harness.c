@@ -456,7 +456,9 @@ create_tr_solver(SleqpTRSolver** tr, Setup* s, SleqpMat* hessian)
 #endif
 }
 
-#ifndef HARNESS_TIMING
+#if defined(HARNESS_NO_MAIN)
+// included by full_solve.c for the problem definitions only
+#elif !defined(HARNESS_TIMING)
 
 int
 main(int argc, char** argv)

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <stdexcept>
@@ -79,7 +80,7 @@ struct DevBuf
     if (n > cap)
     {
       release();
-      size_t want = n + n / 8 + 16;
+      size_t want = n + std::min<size_t>(n / 8, (size_t)1 << 22) + 16; // slack for slowly growing patterns, bounded for the big panel buffers
       B200_CUDA(cudaMalloc((void**)&p, want * sizeof(T)));
       cap = want;
     }

@@ -1,0 +1,235 @@
+"""The LP backend of SURVEY.md section 8f rank 3 (sleqp_b200/host/lp/lpi_simplex.c: the sixteen SleqpLPiCallbacks over
+a dense bounded-variable primal simplex) through the reference's own lp/lpi.c wrapper, against SciPy's HiGHS on the
+same LPs; and a complete sleqp_solver_solve through unmodified reference code over it (oracle/full_solve.c)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.optimize as so
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+LIB = os.path.join(REF, "libsleqp_full_lapack.so")
+INF = 1e100
+
+pytestmark = pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libsleqp_full_lapack.so not built")
+
+LOWER, BASIC, UPPER, ZERO = 0, 1, 2, 3
+OPTIMAL, INFEASIBLE, UNBOUNDED = 1, 2, 4
+
+
+class LP:
+    def __init__(self, A, c, rl, ru, xl, xu):
+        from oracle.ref_lib import RefLib
+
+        self.ref = RefLib.__new__(RefLib)
+        RefLib.__init__(self.ref, "lapack")  # containers (SleqpMat) from the small library ...
+        self.L = L = C.CDLL(LIB, mode=C.RTLD_GLOBAL)  # ... the LP interface from the full one
+        vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
+        L.sleqp_settings_create.argtypes = [C.POINTER(vp)]
+        L.sleqp_lpi_create_default.argtypes = [C.POINTER(vp), C.c_int, C.c_int, vp]
+        L.sleqp_lpi_set_bounds.argtypes = [vp, dp, dp, dp, dp]
+        L.sleqp_lpi_set_coeffs.argtypes = [vp, vp]
+        L.sleqp_lpi_set_objective.argtypes = [vp, dp]
+        L.sleqp_lpi_solve.argtypes = [vp]
+        L.sleqp_lpi_status.argtypes = [vp]
+        L.sleqp_lpi_primal_sol.argtypes = [vp, dp, dp]
+        L.sleqp_lpi_dual_sol.argtypes = [vp, dp, dp]
+        L.sleqp_lpi_vars_stats.argtypes = [vp, ip]
+        L.sleqp_lpi_cons_stats.argtypes = [vp, ip]
+        L.sleqp_lpi_set_basis.argtypes = [vp, C.c_int, ip, ip]
+        L.sleqp_lpi_save_basis.argtypes = [vp, C.c_int]
+        L.sleqp_lpi_restore_basis.argtypes = [vp, C.c_int]
+        L.sleqp_lpi_name.argtypes = [vp]
+        L.sleqp_lpi_name.restype = C.c_char_p
+        L.sleqp_lpi_release.argtypes = [C.POINTER(vp)]
+        L.sleqp_mat_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int]
+        L.sleqp_mat_push.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+        L.sleqp_mat_push_col.argtypes = [vp, C.c_int]
+        A = sp.csc_matrix(A)
+        A.sort_indices()
+        self.m, self.n = A.shape
+        self.settings, self.h, self.mat = vp(), vp(), vp()
+        assert L.sleqp_settings_create(C.byref(self.settings)) == 0
+        assert L.sleqp_lpi_create_default(C.byref(self.h), self.n, self.m, self.settings) == 0
+        assert L.sleqp_mat_create(C.byref(self.mat), self.m, self.n, max(A.nnz, 1)) == 0
+        for j in range(self.n):
+            assert L.sleqp_mat_push_col(self.mat, j) == 0
+            for q in range(A.indptr[j], A.indptr[j + 1]):
+                assert L.sleqp_mat_push(self.mat, int(A.indices[q]), j, float(A.data[q])) == 0
+        self._d = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(dp)
+        self._keep = [np.ascontiguousarray(v, dtype=np.float64) for v in (rl, ru, xl, xu, c)]
+        assert L.sleqp_lpi_set_coeffs(self.h, self.mat) == 0
+        self.set(c, rl, ru, xl, xu)
+
+    def set(self, c, rl, ru, xl, xu):
+        self._keep = [np.ascontiguousarray(v, dtype=np.float64) for v in (rl, ru, xl, xu, c)]
+        k = self._keep
+        assert self.L.sleqp_lpi_set_bounds(self.h, self._d(k[0]), self._d(k[1]), self._d(k[2]), self._d(k[3])) == 0
+        assert self.L.sleqp_lpi_set_objective(self.h, self._d(k[4])) == 0
+
+    def solve(self):
+        L = self.L
+        assert L.sleqp_lpi_solve(self.h) == 0
+        status = L.sleqp_lpi_status(self.h)
+        if status != OPTIMAL:
+            return status, None
+        x, obj = np.empty(self.n), C.c_double()
+        vd, cd = np.empty(self.n), np.empty(self.m)
+        vs, cs = np.empty(self.n, dtype=np.int32), np.empty(self.m, dtype=np.int32)
+        ip = C.POINTER(C.c_int)
+        assert L.sleqp_lpi_primal_sol(self.h, C.byref(obj), self._d(x)) == 0
+        assert L.sleqp_lpi_dual_sol(self.h, vd.ctypes.data_as(C.POINTER(C.c_double)), cd.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        assert L.sleqp_lpi_vars_stats(self.h, vs.ctypes.data_as(ip)) == 0
+        assert L.sleqp_lpi_cons_stats(self.h, cs.ctypes.data_as(ip)) == 0
+        return status, dict(x=x, obj=obj.value, vars_dual=vd, cons_dual=cd, vars_stats=vs, cons_stats=cs)
+
+
+def _highs(A, c, rl, ru, xl, xu):
+    A = sp.csr_matrix(A)
+    fin = lambda v: np.where(np.abs(v) >= INF / 2, np.sign(v) * np.inf, v)  # noqa: E731
+    rl, ru, xl, xu = fin(np.asarray(rl, float)), fin(np.asarray(ru, float)), fin(np.asarray(xl, float)), fin(np.asarray(xu, float))
+    cons = so.LinearConstraint(A, rl, ru)
+    return so.linprog(c, A_ub=sp.vstack([A[np.isfinite(ru)], -A[np.isfinite(rl)]]), b_ub=np.concatenate([ru[np.isfinite(ru)], -rl[np.isfinite(rl)]]),
+                      bounds=list(zip(np.where(np.isfinite(xl), xl, None), np.where(np.isfinite(xu), xu, None))), method="highs"), cons
+
+
+def _check_optimality(A, c, rl, ru, xl, xu, r, tol=1e-7):
+    """KKT conditions of the LP with the dual convention of lpi_highs.c: reduced costs = c - A^T y."""
+    A = sp.csr_matrix(A)
+    x, y, d = r["x"], r["cons_dual"], r["vars_dual"]
+    act = A @ x
+    assert np.all(x >= np.asarray(xl) - tol) and np.all(x <= np.asarray(xu) + tol)
+    assert np.all(act >= np.asarray(rl) - tol) and np.all(act <= np.asarray(ru) + tol)
+    assert np.abs(c - A.T @ y - d).max() <= tol * max(1.0, np.abs(c).max())
+    for j in range(len(x)):  # sign of a reduced cost follows the bound the variable sits at
+        if r["vars_stats"][j] == BASIC:
+            assert abs(d[j]) <= tol
+        elif r["vars_stats"][j] == LOWER and xl[j] < xu[j]:
+            assert d[j] >= -tol and abs(x[j] - xl[j]) <= tol
+        elif r["vars_stats"][j] == UPPER and xl[j] < xu[j]:
+            assert d[j] <= tol and abs(x[j] - xu[j]) <= tol
+    for i in range(len(y)):
+        if r["cons_stats"][i] == BASIC:
+            assert abs(y[i]) <= tol
+        elif r["cons_stats"][i] == LOWER and rl[i] < ru[i]:
+            assert y[i] >= -tol and abs(act[i] - rl[i]) <= tol * max(1.0, abs(rl[i]))
+        elif r["cons_stats"][i] == UPPER and rl[i] < ru[i]:
+            assert y[i] <= tol and abs(act[i] - ru[i]) <= tol * max(1.0, abs(ru[i]))
+    assert (r["vars_stats"] == BASIC).sum() + (r["cons_stats"] == BASIC).sum() == len(y)  # a basis
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_lps_against_highs(seed):
+    rng = np.random.default_rng(seed)
+    m, n = int(rng.integers(2, 14)), int(rng.integers(3, 25))
+    A = sp.random(m, n, density=0.5, random_state=np.random.RandomState(seed), format="csc") + sp.csc_matrix((m, n))
+    c = rng.standard_normal(n)
+    xl, xu = -rng.uniform(0.5, 2, n), rng.uniform(0.5, 2, n)
+    x0 = rng.uniform(xl, xu)
+    act = A @ x0
+    rl, ru = act - rng.uniform(0, 1, m), act + rng.uniform(0, 1, m)
+    eq = rng.random(m) < 0.3  # some equality rows, some one-sided ones
+    rl[eq] = ru[eq] = act[eq]
+    one = rng.random(m) < 0.2
+    ru[one & ~eq] = INF
+    lp = LP(A, c, rl, ru, xl, xu)
+    status, r = lp.solve()
+    ref, _ = _highs(A, c, rl, ru, xl, xu)
+    assert status == OPTIMAL and ref.status == 0
+    assert abs(r["obj"] - ref.fun) <= 1e-7 * max(1.0, abs(ref.fun))
+    _check_optimality(A, c, rl, ru, xl, xu, r)
+
+
+def test_cauchy_shaped_lp_with_slack_basis_and_warm_start():
+    """The LP of standard_cauchy.c:155-190: [J, I, -I] (d, s+, s-) with |d| <= radius, s >= 0, penalised slacks; first from
+    the slack basis SLEQP hands over, then re-solved from the saved basis after the trust radius and the objective moved."""
+    rng = np.random.default_rng(3)
+    n, m = 12, 5
+    J = rng.standard_normal((m, n))
+    A = sp.hstack([sp.csc_matrix(J), sp.identity(m), -sp.identity(m)], format="csc")
+    g = rng.standard_normal(n)
+    resid = rng.standard_normal(m)
+    penalty = 10.0
+
+    def data(radius, grad):
+        c = np.concatenate([grad, penalty * np.ones(2 * m)])
+        xl = np.concatenate([-radius * np.ones(n), np.zeros(2 * m)])
+        xu = np.concatenate([radius * np.ones(n), INF * np.ones(2 * m)])
+        return c, -resid, -resid, xl, xu
+
+    c, rl, ru, xl, xu = data(0.5, g)
+    lp = LP(A, c, rl, ru, xl, xu)
+    ip = C.POINTER(C.c_int)
+    vs = np.full(n + 2 * m, LOWER, dtype=np.int32)
+    cs = np.full(m, LOWER, dtype=np.int32)
+    vs[n:n + m][rl > 0] = BASIC           # create_and_set_slack_basis, standard_cauchy.c:95-121
+    vs[n + m:][ru < 0] = BASIC
+    cs[ru < 0] = UPPER
+    assert lp.L.sleqp_lpi_set_basis(lp.h, 0, vs.ctypes.data_as(ip), cs.ctypes.data_as(ip)) == 0
+    assert lp.L.sleqp_lpi_restore_basis(lp.h, 0) == 0
+    status, r = lp.solve()
+    ref, _ = _highs(A, c, rl, ru, xl, xu)
+    assert status == OPTIMAL and abs(r["obj"] - ref.fun) <= 1e-8 * max(1.0, abs(ref.fun))
+    _check_optimality(A, c, rl, ru, xl, xu, r)
+    assert lp.L.sleqp_lpi_save_basis(lp.h, 1) == 0
+    for radius, scale in ((0.05, 1.0), (2.0, -1.0), (0.3, 0.5)):
+        c, rl, ru, xl, xu = data(radius, scale * g)
+        lp.set(c, rl, ru, xl, xu)
+        assert lp.L.sleqp_lpi_restore_basis(lp.h, 1) == 0
+        status, r = lp.solve()
+        ref, _ = _highs(A, c, rl, ru, xl, xu)
+        assert status == OPTIMAL and abs(r["obj"] - ref.fun) <= 1e-8 * max(1.0, abs(ref.fun)), radius
+        _check_optimality(A, c, rl, ru, xl, xu, r)
+    assert lp.L.sleqp_lpi_name(lp.h) == b"Simplex"
+
+
+def test_infeasible_and_unbounded_are_reported():
+    A = sp.csc_matrix(np.array([[1.0, 1.0]]))
+    lp = LP(A, [1.0, 1.0], [3.0], [INF], [0.0, 0.0], [1.0, 1.0])  # x + y >= 3 with x, y <= 1
+    assert lp.solve()[0] == INFEASIBLE
+    lp2 = LP(A, [-1.0, 0.0], [-INF], [INF], [0.0, 0.0], [INF, 1.0])  # min -x, x unbounded above
+    assert lp2.solve()[0] == UNBOUNDED
+
+
+def _run(exe, *args):
+    out = subprocess.run([os.path.join(REF, exe), *args], check=True, capture_output=True, text=True, timeout=900)
+    data = {}
+    for line in out.stdout.splitlines():
+        parts = line.split()
+        data[parts[0]] = np.array(parts[2:], dtype=np.float64)
+    return data
+
+
+def test_full_solver_reaches_the_reference_known_optimum_of_hs71():
+    """sleqp_solver_solve through unmodified reference code (Cauchy LP over our backend, EQP over the reference LAPACK
+    factorization): the optimum the reference's own test demands (src/test/constrained_fixture.c:268-273, 1e-6)."""
+    d = _run("full_solve_lapack", "hs71")
+    assert d["status"][0] == 2  # SLEQP_STATUS_OPTIMAL
+    assert np.abs(d["solution"] - np.array([1.0, 4.742999, 3.821151, 1.379408])).max() <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args,compare", [(("hs71",), 200), (("chain", "100", "60"), 60)], ids=["hs71", "config1_chain_n100"])
+def test_full_solver_over_the_b200_backend_walks_the_same_iterates(args, compare):
+    """north_star: "identical SLEQP convergence". The whole solver -- Cauchy LP, working set, device-assembled augmented
+    Jacobian (b200_aug_jac.c), device projected CG (tr_b200.c), line search, trust-region updates -- over the B200
+    backend accepts the same iterates as over the reference LAPACK backend with the reference's Steihaug solver."""
+    if not os.path.exists(os.path.join(REF, "full_solve_b200")):
+        pytest.skip("oracle/_ref/full_solve_b200 not shipped")
+    want = _run("full_solve_lapack", *args)
+    got = _run("full_solve_b200", *args)
+    assert got["status"][0] == want["status"][0]
+    k = 0
+    while f"iterate_{k}" in want and k < compare:
+        assert f"iterate_{k}" in got, k
+        a, b = got[f"iterate_{k}"], want[f"iterate_{k}"]
+        assert np.abs(a - b).max() <= 1e-8 * max(1.0, np.abs(b).max()), (k, float(np.abs(a - b).max()))
+        k += 1
+    assert k >= min(compare, 10)
+    if args[0] == "hs71":
+        assert got["iterations"][0] == want["iterations"][0]
+        assert np.abs(got["solution"] - np.array([1.0, 4.742999, 3.821151, 1.379408])).max() <= 1e-5
