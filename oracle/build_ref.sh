@@ -151,7 +151,7 @@ if [ -f "$OUT/obj/fact_b200.o" ]; then
   # the reference tree as the integration patch leaves it: newton.c / trial_point.c select the B200 TR solver and augmented Jacobian
   mkdir -p "$OUT/patched/src/main" "$OUT/patched/cmake"
   cp "$SRC/newton.c" "$SRC/trial_point.c" "$OUT/patched/src/main/"
-  cp "$REF/cmake/SearchFact.cmake" "$OUT/patched/cmake/"
+  cp "$REF/cmake/SearchFact.cmake" "$REF/cmake/SearchLPS.cmake" "$OUT/patched/cmake/"
   (cd "$OUT/patched" && patch -p1 -s < "$REPO/cmake/sleqp_b200_backend.patch")
   FULLB=""
   for o in $FULL; do case "$o" in *objfull/newton.o|*objfull/trial_point.o) ;; *) FULLB="$FULLB $o";; esac; done
