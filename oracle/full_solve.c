@@ -20,6 +20,7 @@
 #include <string.h>
 #include <time.h>
 
+#include "pub_log.h"
 #include "pub_solver.h"
 
 // ---- HS71 (constrained_fixture.c, restated) ------------------------------------------------------------------------
@@ -157,6 +158,11 @@ main(int argc, char** argv)
   const int m         = hs ? 2 : (n - 2) / 2;
   const double inf    = sleqp_infinity();
 
+  if (getenv("FULL_SOLVE_DEBUG"))
+  {
+    sleqp_log_set_level(SLEQP_LOG_DEBUG);
+  }
+
   HS71 hsdata;
   Data data = {n, m, (double*)calloc(n, sizeof(double)), 0, 0, 1e-2};
 
@@ -199,6 +205,15 @@ main(int argc, char** argv)
       CHECK(sleqp_vec_push(var_lb, i, -2.));
       CHECK(sleqp_vec_push(var_ub, i, 2.));
       CHECK(sleqp_vec_push(x0, i, 0.5 + (double)(state >> 11) / 9007199254740992.0));
+    }
+  }
+
+  if (getenv("FULL_SOLVE_PERTURB"))
+  {
+    // sensitivity probe: the start point moved by a relative 1e-15 (one or two units in the last place)
+    for (int k = 0; k < x0->nnz; ++k)
+    {
+      x0->data[k] *= 1. + atof(getenv("FULL_SOLVE_PERTURB")) * ((k % 3) - 1);
     }
   }
 
