@@ -32,8 +32,87 @@ class Emulated:
         self.N = int(plan["n"])
         self.n_perturbed = 0
         self.L11 = {}  # unit lower factors of the diagonal blocks, keyed by (supernode, panel step)
+        self._read_sst()
         self._factor()
         self._invert()
+
+    # ---------------------------------------------------------------- sparse subtrees (sst.cu)
+    def _read_sst(self):
+        """SstMeta records of the plan (plan.hpp): supernodes kept with their exact sparse structure."""
+        p = self.p
+        ns = int(p["n_supernodes"])
+        self.is_sst = np.zeros(ns, dtype=bool)
+        self.sst = []
+        raw = np.asarray(p.get("sst", np.zeros((0, 16), dtype=np.int32))).reshape(-1, 16)
+        for rec in raw:
+            lptr = int(np.array(rec[0:2], dtype=np.int32).view(np.int64)[0])
+            uoff = int(np.array(rec[2:4], dtype=np.int32).view(np.int64)[0])
+            sn, first, k, r, rptr, parent, col_ptr, row_ptr, lvl_ptr, lvl_col, nlev, nnz = (int(v) for v in rec[4:16])
+            colptr = np.asarray(p["sst_colptr"][col_ptr : col_ptr + k + 1], dtype=np.int64)
+            rows = np.asarray(p["sst_rows"][row_ptr : row_ptr + nnz], dtype=np.int64)
+            lptrs = np.asarray(p["sst_lvl_ptr"][lvl_ptr : lvl_ptr + nlev + 1], dtype=np.int64)
+            lcols = np.asarray(p["sst_lvl_col"][lvl_col : lvl_col + k], dtype=np.int64)
+            assert colptr[0] == 0 and colptr[-1] == nnz and lptrs[-1] == k
+            self.sst.append(dict(Lptr=lptr, Uoff=uoff, sn=sn, first=first, k=k, r=r, Rptr=rptr, parent=parent, colptr=colptr, rows=rows,
+                                 lvl_ptr=lptrs, lvl_col=lcols, nlev=nlev, nnz=nnz))
+            self.is_sst[sn] = True
+            assert p["sn_sparse"][sn] == 1
+
+    def _sst_factor(self, M):
+        """k_sst_factor: right-looking sparse LDL^T, level by level; the levels must respect the dependencies."""
+        vals = self.L[M["Lptr"] : M["Lptr"] + M["nnz"]]
+        k, r, colptr, rows = M["k"], M["r"], M["colptr"], M["rows"]
+        Us = np.zeros((r, r))
+        done = np.zeros(k, dtype=bool)
+        for lev in range(M["nlev"]):
+            cols = M["lvl_col"][M["lvl_ptr"][lev] : M["lvl_ptr"][lev + 1]]
+            upd = []
+            for j in cols:
+                p0, p1 = colptr[j], colptr[j + 1]
+                assert rows[p0] == j
+                d = vals[p0]
+                if not (abs(d) >= self.tau) or not np.isfinite(d):
+                    d = -self.tau if self.tau > 0 else -1e-300
+                    self.n_perturbed += 1
+                self.D[M["first"] + j] = d
+                vals[p0] = d
+                for a in range(p0 + 1, p1):
+                    la = vals[a] / d
+                    for b in range(p0 + 1, a + 1):
+                        upd.append((rows[a], rows[b], -la * vals[b]))
+                vals[p0 + 1 : p1] /= d
+            for ia, ib, u in upd:  # targets belong to later levels (or to the update block)
+                if ib >= k:
+                    Us[ia - k, ib - k] += u
+                else:
+                    assert not done[ib] and ib not in cols
+                    t = colptr[ib] + int(np.nonzero(rows[colptr[ib] : colptr[ib + 1]] == ia)[0][0])
+                    vals[t] += u
+            done[cols] = True
+        if r:
+            self.U[M["Uoff"] : M["Uoff"] + r * r] = Us.T.reshape(-1)  # column-major r x r like umat()
+
+    def _sst_forward(self, M, yacc, yf):
+        k, r, colptr, rows = M["k"], M["r"], M["colptr"], M["rows"]
+        vals = self.L[M["Lptr"] : M["Lptr"] + M["nnz"]]
+        x = np.concatenate([yacc[M["first"] : M["first"] + k], np.zeros(r)])
+        for lev in range(M["nlev"]):
+            for j in M["lvl_col"][M["lvl_ptr"][lev] : M["lvl_ptr"][lev + 1]]:
+                for a in range(colptr[j] + 1, colptr[j + 1]):
+                    x[rows[a]] -= vals[a] * x[j]
+        yf[M["first"] : M["first"] + k] = x[:k] / self.D[M["first"] : M["first"] + k]
+        tail = self.p["Ridx"][M["Rptr"] : M["Rptr"] + r]
+        np.add.at(yacc, tail, x[k:])
+
+    def _sst_backward(self, M, yf, xg):
+        k, r, colptr, rows = M["k"], M["r"], M["colptr"], M["rows"]
+        vals = self.L[M["Lptr"] : M["Lptr"] + M["nnz"]]
+        tail = self.p["Ridx"][M["Rptr"] : M["Rptr"] + r]
+        x = np.concatenate([yf[M["first"] : M["first"] + k], xg[tail]])
+        for lev in range(M["nlev"] - 1, -1, -1):
+            for j in M["lvl_col"][M["lvl_ptr"][lev] : M["lvl_ptr"][lev + 1]]:
+                x[j] -= sum(vals[a] * x[rows[a]] for a in range(colptr[j] + 1, colptr[j + 1]))
+        xg[M["first"] : M["first"] + k] = x[:k]
 
     # ---------------------------------------------------------------- geometry helpers
     def _geom(self, T):
@@ -76,9 +155,16 @@ class Emulated:
         # diagonal entry is the first entry of every column of S; recover via Sdest of (j,j)
         smax = 0.0
         for T in range(int(p["n_supernodes"])):
+            if self.is_sst[T]:
+                continue
             f, k, r, h = self._geom(T)
             smax = max(smax, np.abs(np.diag(self.panel(T)[:k, :k])).max(initial=0.0))
+        for M in self.sst:
+            smax = max(smax, np.abs(self.L[M["Lptr"] + M["colptr"][:-1]]).max(initial=0.0))
         self.tau = 64 * np.finfo(float).eps * smax
+        self.n_perturbed = getattr(self, "n_perturbed", 0)
+        for M in self.sst:  # leaves of the supernodal tree: before the first stage
+            self._sst_factor(M)
         scratch = np.full(max(1, int(p["n_scratch_slots"]) if "n_scratch_slots" in p else 1) * NB * NB, np.nan)
         has_children = np.diff(p["child_ptr"]) > 0
         # Look-ahead on the device (two streams): per stage the panel step and the update tiles of the NEXT panel's
@@ -123,6 +209,8 @@ class Emulated:
         tmp = np.full(max(1, int(p["Tptr"][-1])), np.nan)
         ns = int(p["n_supernodes"])
         for T in range(ns):  # what k_panel publishes: inverse of every NB x NB diagonal block
+            if self.is_sst[T]:
+                continue  # sparse subtrees keep their factor (substitution instead of inverse panels)
             f, k, r, h = self._geom(T)
             P, M = self.panel(T), self.mpanel(T)
             for c0 in range(0, k, NB):
@@ -181,6 +269,10 @@ class Emulated:
         yf = np.zeros(self.m)
         x = np.zeros(self.m)
         cnt = np.zeros(ns, dtype=np.int64)
+        for M in self.sst:  # k_sst_forward runs before the dataflow kernel and signals the parents
+            self._sst_forward(M, yacc, yf)
+            if M["parent"] >= 0:
+                cnt[M["parent"]] += 1
         tasks = p["ffl_tasks"]
         for t in range(len(tasks)):
             lptr, rptr, first, k, h, i0, i1, j0, j1, wait_idx, need, signal_idx = fields(tasks[t])
@@ -211,6 +303,8 @@ class Emulated:
                 x[first + j] += Mr[lptr + ii * k + j] @ v
             if signal_idx >= 0:
                 cnt[signal_idx] += 1
+        for M in self.sst:  # k_sst_backward: after the dataflow kernel
+            self._sst_backward(M, yf, x)
         assert np.all(np.isfinite(x))
         return x
 
@@ -335,6 +429,14 @@ class Emulated:
                 w = W[int(p["Wptr"][T]) : int(p["Wptr"][T]) + h]
                 w[:k] = b_new[f : f + k]
                 w[k:] = 0.0
+                if self.is_sst[T]:
+                    M = next(q for q in self.sst if q["sn"] == T)
+                    vals = self.L[M["Lptr"] : M["Lptr"] + M["nnz"]]
+                    for j in range(k):  # column order = a topological order of the subtree
+                        for a in range(M["colptr"][j] + 1, M["colptr"][j + 1]):
+                            w[M["rows"][a]] -= vals[a] * w[j]
+                    x[f : f + k] = w[:k]
+                    continue
                 for c in p["child_idx"][int(p["child_ptr"][T]) : int(p["child_ptr"][T + 1])]:
                     c = int(c)
                     fc, kc, rc, hc = self._geom(c)
@@ -353,6 +455,14 @@ class Emulated:
                 T = int(T)
                 f, k, r, h = self._geom(T)
                 rows = p["Ridx"][int(p["Rptr"][T]) : int(p["Rptr"][T + 1])]
+                if self.is_sst[T]:
+                    M = next(q for q in self.sst if q["sn"] == T)
+                    vals = self.L[M["Lptr"] : M["Lptr"] + M["nnz"]]
+                    loc = np.concatenate([x[f : f + k], x[rows]])
+                    for j in range(k - 1, -1, -1):
+                        loc[j] -= sum(vals[a] * loc[M["rows"][a]] for a in range(M["colptr"][j] + 1, M["colptr"][j + 1]))
+                    x[f : f + k] = loc[:k]
+                    continue
                 P = self.panel(T)
                 L11 = self._L11_full(T)
                 t = x[f : f + k] - P[k:, :k].T @ x[rows]

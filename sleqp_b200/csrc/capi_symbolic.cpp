@@ -1,6 +1,7 @@
 // capi_symbolic.cpp -- host-only C-ABI entry points (symbolic analysis, plan cache, errors).
 #include "common.hpp"
 
+#include <cstdlib>
 #include <cstring>
 #include <list>
 #include <mutex>
@@ -27,6 +28,24 @@ std::list<std::shared_ptr<const Plan>> g_cache; // most recently used first
 constexpr size_t CACHE_CAPACITY = 16;
 } // namespace
 
+// The analysis depends on a few environment knobs (measurements and tests: B200_SST, B200_GROUP_CAP,
+// B200_FLOW_DEEP_TASKS): they are part of the cache key, so a plan built under other settings is never handed out.
+static uint64_t
+plan_variant_bits()
+{
+  uint64_t v = 0;
+  for (const char* name : {"B200_SST", "B200_GROUP_CAP", "B200_FLOW_DEEP_TASKS"})
+  {
+    const char* e = std::getenv(name);
+    v             = v * 0x100000001B3ull + 0x9E37;
+    for (; e && *e; ++e)
+    {
+      v = (v ^ (unsigned char)*e) * 0x100000001B3ull;
+    }
+  }
+  return v;
+}
+
 int
 get_plan(int n, int nnz, const int* colptr, const int* rowidx, const double* val, int lower_only, std::shared_ptr<const Plan>& out, bool& cached)
 {
@@ -36,6 +55,7 @@ get_plan(int n, int nnz, const int* colptr, const int* rowidx, const double* val
   }
   uint64_t h2      = 0;
   const uint64_t h = hash_pattern(n, nnz, colptr, rowidx, val, lower_only, &h2);
+  h2 ^= plan_variant_bits();
   {
     std::lock_guard<std::mutex> lock(g_cache_mutex);
     for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
@@ -56,6 +76,7 @@ get_plan(int n, int nnz, const int* colptr, const int* rowidx, const double* val
   {
     return set_error(rc, err);
   }
+  plan->pattern_hash2 = h2; // incl. the variant bits
   {
     std::lock_guard<std::mutex> lock(g_cache_mutex);
     g_cache.push_front(plan);
@@ -80,6 +101,7 @@ get_plan_kkt(int num_vars, int num_cons, int nnz_jac, const int* jac_cols, const
   }
   uint64_t h2      = 0;
   const uint64_t h = hash_kkt(num_vars, num_cons, nnz_jac, jac_cols, jac_rows, var_index, cons_index, ws_size, &h2);
+  h2 ^= plan_variant_bits();
   const int N      = num_vars + ws_size;
   {
     std::lock_guard<std::mutex> lock(g_cache_mutex);
@@ -343,7 +365,21 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
   FIELD(inv_phase_ptr)
   FIELD(Tptr)
   FIELD(Ksrc)
+  FIELD(sst_colptr)
+  FIELD(sst_rows)
+  FIELD(sst_lvl_ptr)
+  FIELD(sst_lvl_col)
 #undef FIELD
+  if (f == "sn_sparse")
+  {
+    std::vector<int> v(P.sn_sparse.begin(), P.sn_sparse.end());
+    return export_vec(v, out, count);
+  }
+  if (f == "sst")
+  {
+    static_assert(sizeof(SstMeta) == 16 * sizeof(int), "SstMeta layout");
+    return export_vec(P.sst, out, count);
+  }
   if (f == "stages")
   {
     static_assert(sizeof(Stage) == 10 * sizeof(int), "Stage layout");

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <mutex>
 #include <stdexcept>
 #include <vector>
 
@@ -188,6 +189,8 @@ struct DevPlan
   DevBuf<int> k_of_e, k_of_r, pinv, perm, dE_src;
   DevBuf<int> Acsc_ptr, Acsc_row, Acsc_src, Acsr_ptr, Acsr_col, Acsr_src, Gsym_ptr, Gsym_col, Gsym_src;
   DevBuf<int> Acsr_k, Acsr_dsrc, Acsc_p;
+  DevBuf<SstMeta> sst; // sparse subtrees (sst.cu)
+  DevBuf<int> sst_colptr, sst_rows, sst_lvl_ptr, sst_lvl_col;
   DevBuf<int> Ksrc; // set_kkt plans: source of every value of tril(K) in the Jacobian's value array (-1: the constant 1)
 };
 

@@ -254,6 +254,11 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   dp.Gsym_col.upload(P.Gsym_col, s);
   dp.Gsym_src.upload(P.Gsym_src, s);
   dp.Ksrc.upload(P.Ksrc, s);
+  dp.sst.upload(P.sst, s);
+  dp.sst_colptr.upload(P.sst_colptr, s);
+  dp.sst_rows.upload(P.sst_rows, s);
+  dp.sst_lvl_ptr.upload(P.sst_lvl_ptr, s);
+  dp.sst_lvl_col.upload(P.sst_lvl_col, s);
   // the uploads read pageable host vectors owned by the (shared, immutable) plan: safe, but
   // finish them before anything else touches the stream
   B200_CUDA(cudaStreamSynchronize(s));
@@ -534,6 +539,7 @@ b200_fact_create(b200_fact** handle, int device)
     B200_CUDA(cudaDeviceGetAttribute(&F->sms, cudaDevAttrMultiProcessorCount, dev));
     configure_solve_kernels();
     configure_numeric_kernels(dev);
+    configure_sst_kernels(dev);
     *handle = F.release();
     return (int)B200_OK;
   });

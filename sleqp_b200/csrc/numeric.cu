@@ -1010,6 +1010,7 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
     lc.tick();
     k_set_tau<<<1, 1, 0, stream>>>(nb.scal);
     lc.tick();
+    enqueue_sst_factor(dp, nb, stream, lc); // the sparse subtrees are leaves: their update blocks are ready before stage 0
   }
   // Look-ahead over two streams. Main: zero-fill / extend-add of the supernodes that start, the panel step, then the
   // update tiles of the NEXT panel's columns. Side: the rest of the stage's update tiles (and the Schur complements),

@@ -56,6 +56,13 @@ struct NumericOverlap
   cudaEvent_t rest_done[3];
 };
 
+// sparse subtrees (sst.cu): factorization before the first stage of the dense schedule, forward sweep before the
+// forward dataflow kernel (signals the parents' counters), backward sweep after the backward dataflow kernel
+void configure_sst_kernels(int device);
+void enqueue_sst_factor(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc);
+void enqueue_sst_forward(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc);
+void enqueue_sst_backward(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc);
+
 // ov == nullptr: everything on `stream` in stage order (profiling entry point: per-class timings)
 void enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc, const NumericOverlap* ov = nullptr);
 

@@ -38,6 +38,33 @@ panel_ld(i64 h)
   return (h + 1) & ~(i64)1;
 }
 
+// Sparse subtrees (SST). A complete subtree of the elimination tree whose columns hold only a few entries each (chains,
+// banded systems: config 3) is kept as ONE supernode with its exact sparse structure instead of a dense panel: a dense
+// 32-column block stores (and streams, in every sweep) ten times what a bidiagonal factor holds, and a tree of
+// 32-column blocks is log32(m) hand-offs deep. One CTA factors / sweeps a whole subtree of up to SST_MAX_COLS columns in
+// shared memory, level by level of its own elimination tree (columns of one level are independent).
+constexpr int SST_MAX_COLS  = 1024; // columns of one sparse subtree
+constexpr int SST_MIN_COLS  = 16;
+constexpr int SST_MAX_TAIL  = 32;   // update rows (the subtree's contribution to its ancestors is a dense r x r block)
+constexpr int SST_MAX_NNZ   = 6144; // entries of L in the subtree (values live in shared memory during the factorization)
+constexpr int SST_MAX_AVG   = 8;    // mean entries per column: beyond that the dense supernodal path is the better one
+constexpr int SST_THREADS   = 256;
+
+struct SstMeta
+{
+  long long Lptr;  // values of the subtree in the panel buffer (compact, column by column, diagonal first)
+  long long Uoff;  // its r x r update matrix
+  int sn;          // supernode index
+  int first, k, r;
+  int Rptr;        // update rows in Ridx
+  int parent;      // parent supernode (-1: root)
+  int col_ptr;     // offset of its k + 1 column pointers in sst_colptr (entries relative to Lptr)
+  int row_ptr;     // offset of its row indices in sst_rows (front-local: < k a column of the subtree, else k + update row)
+  int lvl_ptr;     // offset of its nlev + 1 level pointers in sst_lvl_ptr
+  int lvl_col;     // offset of its k columns sorted by level in sst_lvl_col
+  int nlev, nnz;
+};
+
 // kinds of update tasks
 enum
 {
@@ -163,6 +190,11 @@ struct Plan
   std::vector<i64> Lptr; // nsuper+1, panel offsets (doubles); panel is h x k column-major
   std::vector<i64> Wptr; // nsuper+1, prefix sum of front heights
   std::vector<int> child_ptr, child_idx;
+
+  // sparse subtrees
+  std::vector<char> sn_sparse; // nsuper: 1 if the supernode is a sparse subtree
+  std::vector<SstMeta> sst;
+  std::vector<int> sst_colptr, sst_rows, sst_lvl_ptr, sst_lvl_col;
 
   // assembly of S straight into the panels: S_e = val[gsrc] - sum_t val[a]*val[b]/val[d]
   i64 nnzS = 0;

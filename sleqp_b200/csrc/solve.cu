@@ -979,6 +979,7 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
                                                              sb.flow);
     lc.tick();
     mark(1);
+    enqueue_sst_forward(dp, nb, sb, stream, lc); // sparse subtrees first (leaves of the supernodal tree)
     const int max_ctas      = sb.sms * g_flow_ctas;
     auto grid = [&](size_t ntasks) {
       // at least ~4 tasks per warp: small systems (batched multistart, many handles on one GPU) leave room for the
@@ -999,6 +1000,7 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
     kb<<<sb.trace_bwd ? max_ctas : grid(P.bfl_tasks.size()), FLOW_THREADS, 0, stream>>>(dp.bfl_tasks.p, bs, dp.Ridx.p, nb.Mr, nb.Dinv, sb.y, sb.yf, sb.x, sb.flow + ns, tickets_b,
                                                                  (const FlowTrace*)sb.trace_bwd);
     lc.tick();
+    enqueue_sst_backward(dp, nb, sb, stream, lc);
     mark(3);
   }
   if (P.m + P.nE > 0)

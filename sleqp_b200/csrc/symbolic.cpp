@@ -1165,6 +1165,38 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
   tick("column counts");
+  // ---- sparse subtrees: maximal complete subtrees with few entries per column (plan.hpp) ---------------------------
+  std::vector<int> sst_root(m, -1); // root (L1 label) of the sparse subtree a column belongs to
+  {
+    const char* e   = std::getenv("B200_SST"); // 0: everything through the dense supernodal path (measurements, tests)
+    const bool on   = !(e && e[0] == '0');
+    std::vector<int> size(m, 1);
+    std::vector<i64> nnz(m, 0);
+    std::vector<char> ok(m, 1);
+    for (int j = 0; j < m && on; ++j) // children before parents
+    {
+      nnz[j] += cc1[j];
+      ok[j] = ok[j] && size[j] <= SST_MAX_COLS && nnz[j] <= SST_MAX_NNZ && nnz[j] <= (i64)SST_MAX_AVG * size[j] && cc1[j] - 1 <= SST_MAX_TAIL;
+      const int p = parent1[j];
+      if (p != -1)
+      {
+        size[p] += size[j];
+        nnz[p] += nnz[j];
+        ok[p] = ok[p] && ok[j];
+      }
+    }
+    for (int j = 0; j < m && on; ++j)
+    {
+      const int p = parent1[j];
+      if (ok[j] && (p == -1 || !ok[p]) && size[j] >= SST_MIN_COLS)
+      {
+        for (int c = j - size[j] + 1; c <= j; ++c) // a subtree is contiguous in the postorder
+        {
+          sst_root[c] = j;
+        }
+      }
+    }
+  }
   // ---- supernodes, step 1: fundamental supernodes + relaxed chain amalgamation (in the postorder labels) ----------
   // rn_last[j]: last column of the chain supernode ("R-node") column j belongs to. Chains only: column j joins the
   // supernode of j + 1 when j + 1 is its parent and the merge is fundamental (identical structure) or the supernode
@@ -1179,7 +1211,11 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     for (int j = m - 2; j >= 0; --j)
     {
       bool jn = false;
-      if (parent1[j] == j + 1)
+      if (sst_root[j] != -1 || sst_root[j + 1] != -1)
+      {
+        jn = sst_root[j] == sst_root[j + 1]; // a sparse subtree is one supernode, nothing else joins it
+      }
+      else if (parent1[j] == j + 1)
       {
         const i64 r       = cc1[l] - 1;
         const i64 kn      = k + 1;
@@ -1281,6 +1317,11 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       {
         closed[l] = 1;
       }
+      if (sst_root[l] != -1) // a sparse subtree stays on its own
+      {
+        closed[l] = 1;
+        open[l]   = 0;
+      }
     }
     // group of an R-node: itself when closed, else its parent's; then of every column
     std::vector<int> rgrp(m, -1);
@@ -1355,6 +1396,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   }
   // final labels: position k holds L1 label post[k]; compose with the postorder to ND labels
   std::vector<int> cc_final(m), grp_final(m);
+  std::vector<char> sst_final(m, 0);
   {
     std::vector<int> l1_to_final(m);
     for (int k = 0; k < m; ++k)
@@ -1365,6 +1407,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     {
       cc_final[k]  = cc1[post[k]];
       grp_final[k] = l1_to_final[grp1[post[k]]];
+      sst_final[k] = sst_root[post[k]] != -1;
     }
     for (int k = 0; k < m; ++k)
     {
@@ -1565,6 +1608,129 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   }
 
   tick("row structures + rel");
+  // ---- sparse subtrees: exact column structures, levels of their own elimination trees ----------------------------
+  P.sn_sparse.assign(ns, 0);
+  std::vector<i64> sst_nnz(ns, 0);       // entries of a sparse subtree (its share of the panel buffer)
+  std::vector<int> sst_index(ns, -1);    // position in P.sst
+  std::vector<int> sst_col_of(m, -1);    // for the columns of sparse subtrees: offset of their column pointer in sst_colptr
+  for (int T = 0; T < ns; ++T)
+  {
+    const int f = P.sn_first[T], l = P.sn_first[T + 1] - 1, k = l - f + 1;
+    if (!sst_final[f])
+    {
+      continue;
+    }
+    if (P.child_ptr[T] != P.child_ptr[T + 1])
+    {
+      return fail(err, B200_ERR_ARG, "internal: a sparse subtree has a child supernode");
+    }
+    P.sn_sparse[T] = 1;
+    const int* rows_T = P.Ridx.data() + P.Rptr[T];
+    const int r       = (int)(P.Rptr[T + 1] - P.Rptr[T]);
+    SstMeta M;
+    M.sn      = T;
+    M.first   = f;
+    M.k       = k;
+    M.r       = r;
+    M.Rptr    = (int)P.Rptr[T];
+    M.parent  = P.sn_parent[T];
+    M.col_ptr = (int)P.sst_colptr.size();
+    M.row_ptr = (int)P.sst_rows.size();
+    M.lvl_ptr = (int)P.sst_lvl_ptr.size();
+    M.lvl_col = (int)P.sst_lvl_col.size();
+    M.Lptr = M.Uoff = 0; // set with the storage offsets / the update workspace
+    // struct(j) = {j} + lower adjacency of j + the structures of its children without j (all inside the subtree)
+    std::vector<std::vector<int>> st((size_t)k);
+    std::vector<int> lev((size_t)k, 0);
+    int nlev = 0;
+    for (int j = f; j <= l; ++j)
+    {
+      std::vector<int>& cur = st[(size_t)(j - f)];
+      for (int p = xadj2[j]; p < xadj2[j + 1]; ++p)
+      {
+        if (adj2[p] > j)
+        {
+          cur.push_back(adj2[p]);
+        }
+      }
+      std::sort(cur.begin(), cur.end());
+      cur.erase(std::unique(cur.begin(), cur.end()), cur.end());
+      if ((int)cur.size() != cc[j] - 1)
+      {
+        return fail(err, B200_ERR_ARG, "internal: column structure of a sparse subtree disagrees with the column count");
+      }
+      // hand the structure (without the parent itself) on to the parent
+      const int par = parent[j];
+      if (par != -1 && par <= l)
+      {
+        std::vector<int>& up = st[(size_t)(par - f)];
+        for (int i : cur)
+        {
+          if (i != par)
+          {
+            up.push_back(i);
+          }
+        }
+        lev[(size_t)(par - f)] = std::max(lev[(size_t)(par - f)], lev[(size_t)(j - f)] + 1);
+      }
+      nlev = std::max(nlev, lev[(size_t)(j - f)] + 1);
+    }
+    // column pointers (relative to the subtree's values), rows as front-local indices, the diagonal first
+    int nnz = 0;
+    for (int j = f; j <= l; ++j)
+    {
+      sst_col_of[j] = (int)P.sst_colptr.size();
+      P.sst_colptr.push_back(nnz);
+      P.sst_rows.push_back(j - f);
+      for (int i : st[(size_t)(j - f)])
+      {
+        int loc;
+        if (i <= l)
+        {
+          loc = i - f;
+        }
+        else
+        {
+          const int* it = std::lower_bound(rows_T, rows_T + r, i);
+          if (it == rows_T + r || *it != i)
+          {
+            return fail(err, B200_ERR_ARG, "internal: row of a sparse subtree missing from its update rows");
+          }
+          loc = k + (int)(it - rows_T);
+        }
+        P.sst_rows.push_back(loc);
+      }
+      nnz += 1 + (int)st[(size_t)(j - f)].size();
+    }
+    P.sst_colptr.push_back(nnz);
+    M.nnz  = nnz;
+    M.nlev = nlev;
+    // columns by level (counting sort)
+    std::vector<int> cnt((size_t)nlev + 1, 0);
+    for (int c = 0; c < k; ++c)
+    {
+      ++cnt[(size_t)lev[(size_t)c] + 1];
+    }
+    for (int q = 0; q < nlev; ++q)
+    {
+      cnt[(size_t)q + 1] += cnt[(size_t)q];
+    }
+    for (int q = 0; q <= nlev; ++q)
+    {
+      P.sst_lvl_ptr.push_back(cnt[(size_t)q]);
+    }
+    std::vector<int> fillp(cnt.begin(), cnt.end() - 1);
+    const size_t base = P.sst_lvl_col.size();
+    P.sst_lvl_col.resize(base + (size_t)k);
+    for (int c = 0; c < k; ++c)
+    {
+      P.sst_lvl_col[base + (size_t)fillp[(size_t)lev[(size_t)c]]++] = c;
+    }
+    sst_nnz[T]   = nnz;
+    sst_index[T] = (int)P.sst.size();
+    P.sst.push_back(M);
+  }
+  tick("sparse subtrees");
   // ---- storage offsets, levels, statistics ---------------------------------------------------------
   P.Lptr.assign(ns + 1, 0);
   P.Wptr.assign(ns + 1, 0);
@@ -1575,10 +1741,20 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     const i64 k = P.sn_first[T + 1] - P.sn_first[T];
     const i64 r = P.Rptr[T + 1] - P.Rptr[T];
     const i64 h = k + r;
-    i64 sz      = panel_ld(h) * k; // leading dimension padded to an even number of rows (plan.hpp)
+    i64 sz      = P.sn_sparse[T] ? sst_nnz[T] : panel_ld(h) * k; // leading dimension padded to an even number of rows (plan.hpp)
     sz          = (sz + 3) & ~(i64)3;
     P.Lptr[T + 1] = P.Lptr[T] + sz;
     P.Wptr[T + 1] = P.Wptr[T] + h;
+    if (P.sn_sparse[T])
+    {
+      P.sst[(size_t)sst_index[T]].Lptr = P.Lptr[T];
+      P.nnzL_stored += sst_nnz[T];
+      for (int j = P.sn_first[T]; j < P.sn_first[T + 1]; ++j)
+      {
+        P.flops_stored += (double)cc[j] * (double)cc[j];
+      }
+      continue;
+    }
     P.max_front   = std::max<i64>(P.max_front, h);
     P.nnzL_stored += k * h - k * (k - 1) / 2;
     for (i64 c = 0; c < k; ++c)
@@ -1657,6 +1833,37 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       const i64 h      = k + (P.Rptr[T + 1] - P.Rptr[T]);
       const int* rows  = P.Ridx.data() + P.Rptr[T];
       const int nrows  = (int)(P.Rptr[T + 1] - P.Rptr[T]);
+      if (P.sn_sparse[T])
+      {
+        // sparse subtree: the entry goes to its slot in the compact column (rows there are front-local indices)
+        const int cp        = sst_col_of[j];
+        const SstMeta& M    = P.sst[(size_t)sst_index[T]];
+        const int c0        = P.sst_colptr[(size_t)cp], c1 = P.sst_colptr[(size_t)cp + 1];
+        const int* crow     = P.sst_rows.data() + M.row_ptr + c0;
+        for (i64 q = Sptr[j]; q < Sptr[j + 1]; ++q)
+        {
+          const int i = Srow[q];
+          int loc;
+          if (i <= l)
+          {
+            loc = i - f;
+          }
+          else
+          {
+            const int* it = std::lower_bound(rows, rows + nrows, i);
+            loc           = (it != rows + nrows && *it == i) ? k + (int)(it - rows) : -1;
+          }
+          const int* it = std::lower_bound(crow, crow + (c1 - c0), loc);
+          if (loc < 0 || it == crow + (c1 - c0) || *it != loc)
+          {
+            outside = true;
+            it      = crow;
+          }
+          P.Sdest[q] = P.Lptr[T] + c0 + (it - crow);
+        }
+        P.Sdiag[j] = P.Sdest[Sptr[j]];
+        continue;
+      }
       for (i64 q = Sptr[j]; q < Sptr[j + 1]; ++q)
       {
         int i = Srow[q];
@@ -1817,7 +2024,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   for (int T = 0; T < ns; ++T)
   {
     const int k = P.sn_first[T + 1] - P.sn_first[T];
-    P.sn_nt[T]  = (k + NB - 1) / NB;
+    P.sn_nt[T]  = P.sn_sparse[T] ? 0 : (k + NB - 1) / NB; // sparse subtrees are factored before the first stage (k_sst_factor)
   }
   for (int T = 0; T < ns; ++T) // children precede parents
   {
@@ -1909,11 +2116,19 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       }
     }
   }
+  for (SstMeta& M : P.sst)
+  {
+    M.Uoff = M.r > 0 ? P.Uoff[M.sn] : 0;
+  }
   // tasks
   {
     std::vector<std::vector<int>> starts(nstages), active(nstages);
     for (int T = 0; T < ns; ++T)
     {
+      if (P.sn_sparse[T])
+      {
+        continue; // no children to assemble, no panel steps (and possibly no stage at all)
+      }
       starts[P.sn_base[T]].push_back(T);
       for (int t = 0; t < P.sn_nt[T]; ++t)
       {
@@ -2076,7 +2291,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     for (int T = 0; T < ns; ++T)
     {
       const i64 k  = P.sn_first[T + 1] - P.sn_first[T];
-      const int nb = (int)((k + NB - 1) / NB);
+      const int nb = P.sn_sparse[T] ? 0 : (int)((k + NB - 1) / NB); // sparse subtrees keep their factor as it is (substitution)
       P.Tptr[T + 1] = P.Tptr[T] + (nb > 1 ? ((k * k + 3) & ~(i64)3) : 0);
       if (nb > 1)
       {
@@ -2118,7 +2333,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
     for (int T = 0; T < ns; ++T)
     {
-      const int k = P.sn_first[T + 1] - P.sn_first[T];
+      const int k = P.sn_sparse[T] ? 0 : P.sn_first[T + 1] - P.sn_first[T];
       const int r = (int)(P.Rptr[T + 1] - P.Rptr[T]);
       for (int j0 = 0; j0 < k; j0 += TILE)
       {
@@ -2132,7 +2347,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     // row-major copy of every inverse panel for the forward sweep
     for (int T = 0; T < ns; ++T)
     {
-      const int k = P.sn_first[T + 1] - P.sn_first[T];
+      const int k = P.sn_sparse[T] ? 0 : P.sn_first[T + 1] - P.sn_first[T];
       const int h = k + (int)(P.Rptr[T + 1] - P.Rptr[T]);
       for (int j0 = 0; j0 < k; j0 += 32)
       {
@@ -2200,7 +2415,10 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       for (int q = P.lvl_ptr[l]; q < P.lvl_ptr[l + 1]; ++q)
       {
         const int T = P.lvl_sn[q];
-        entries += (P.Wptr[T + 1] - P.Wptr[T]) * (i64)(P.sn_first[T + 1] - P.sn_first[T]);
+        if (!P.sn_sparse[T])
+        {
+          entries += (P.Wptr[T + 1] - P.Wptr[T]) * (i64)(P.sn_first[T + 1] - P.sn_first[T]);
+        }
       }
       // (measured on B200: a lower threshold for the second batch is slower on every configuration.) Levels that
       // still give every warp a task at a depth of FLOW_DEEP are bandwidth-bound: there the panel is streamed with a
@@ -2247,6 +2465,11 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     {
       const int k = P.sn_first[T + 1] - P.sn_first[T];
       const int h = (int)(P.Wptr[T + 1] - P.Wptr[T]);
+      if (P.sn_sparse[T])
+      {
+        nf[T] = 1; // a sparse subtree is swept by one CTA before the dataflow kernel starts: one signal to its parent
+        continue;
+      }
       fwd_blocks(k, h, depth_of_sn(T), [&](int, int, int, int) { ++nf[T]; });
       bwd_blocks(k, h, depth_of_sn(T), [&](int, int, int, int) { ++nbk[T]; });
     }
@@ -2256,6 +2479,10 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return (P.Wptr[x + 1] - P.Wptr[x]) > (P.Wptr[y + 1] - P.Wptr[y]); });
       for (int T : order)
       {
+        if (P.sn_sparse[T])
+        {
+          continue;
+        }
         const int k = P.sn_first[T + 1] - P.sn_first[T];
         const int h = (int)(P.Wptr[T + 1] - P.Wptr[T]);
         int need    = 0;
@@ -2275,6 +2502,10 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return (P.Wptr[x + 1] - P.Wptr[x]) > (P.Wptr[y + 1] - P.Wptr[y]); });
       for (int T : order)
       {
+        if (P.sn_sparse[T])
+        {
+          continue;
+        }
         const int k   = P.sn_first[T + 1] - P.sn_first[T];
         const int h   = (int)(P.Wptr[T + 1] - P.Wptr[T]);
         const int par = P.sn_parent[T];

@@ -131,6 +131,34 @@ def test_update_tiles_through_tma(make, monkeypatch):
     f.release()
 
 
+@pytest.mark.parametrize("make", [
+    lambda: problems.chain_rosenbrock(50_000, 0.1, seed=6),
+    lambda: problems.config(0),
+    lambda: problems.chain_rosenbrock(2500, 0.3, seed=7),
+], ids=["chain_5e4", "config1", "chain_2500"])
+def test_sparse_subtrees_equal_the_dense_path(make, monkeypatch):
+    """sst.cu (sparse LDL^T and level-scheduled substitution of the chain-like bottom of the tree, one CTA per subtree)
+    against the all-dense supernodal path on the same matrices: same pivots, same solutions, all parity gates."""
+    p = make()
+    f = _check_problem(p, seeds=(1, 2))
+    st = f.stats()
+    assert st["nnz_L_stored"] <= 1.05 * st["nnz_L"] + 2048  # the sparse path really is in use
+    d = f.pivots()
+    monkeypatch.setenv("B200_SST", "0")
+    g = _check_problem(p, seeds=(1,))
+    assert g.stats()["nnz_L_stored"] > 2 * st["nnz_L_stored"]
+    dg = g.pivots()
+    # same elimination order up to the labelling inside the subtrees: compare the pivots as multisets per magnitude
+    assert np.abs(np.sort(d) - np.sort(dg)).max() <= 1e-10 * np.abs(dg).max()
+    idx, val = p.rhs("solve_lsq", 9)
+    f.solve(idx, val, p.N)
+    g.solve(idx, val, p.N)
+    xa, xb = f.solution_dense(0, p.N), g.solution_dense(0, p.N)
+    assert np.abs(xa - xb).max() <= 1e-9 * max(1.0, np.abs(xb).max())
+    f.release()
+    g.release()
+
+
 def test_structure_and_pivots_match_host_analysis_and_emulation():
     p = problems.poisson_control(20, 2, seed=7)
     cp, ri, v = p.kkt_lower()

@@ -127,6 +127,44 @@ def test_deep_sweep_tasks_emulate(name, monkeypatch):
     assert np.linalg.norm(K @ z - rhs) <= 1e-12 * np.linalg.norm(rhs)
 
 
+@pytest.mark.parametrize("make", [lambda: problems.chain_rosenbrock(6000, 0.1, seed=3), lambda: problems.config(0), lambda: problems.chain_rosenbrock(300, 0.3, seed=8)],
+                         ids=["chain_n6000", "config1", "chain_n300"])
+def test_sparse_subtrees_on_chains(make, monkeypatch):
+    """Chains / banded systems (configs 1 and 3) keep their bottom subtrees as sparse supernodes (plan.hpp SST, sst.cu):
+    the stored factor is the exact one (dense 32-column blocks stored ~6 x as much), the tree above is a few levels, and
+    the emulated sparse factorization + level-scheduled substitution solves K like the all-dense plan."""
+    p = make()
+    cp, ri, v = p.kkt_lower()
+    s = Symbolic(p.N, cp, ri, v)
+    st, plan = s.stats(), s.plan()
+    assert len(plan["sst"]) >= 1 and plan["sn_sparse"].sum() == len(plan["sst"])
+    assert st["nnz_L_stored"] <= 1.05 * st["nnz_L"] + 2048
+    monkeypatch.setenv("B200_SST", "0")
+    sd = Symbolic(p.N, cp, ri, v)
+    std_, pland = sd.stats(), sd.plan()
+    assert len(pland["sst"]) == 0 and std_["nnz_L_stored"] > 2 * st["nnz_L_stored"] and std_["n_levels"] >= st["n_levels"]
+    assert std_["nnz_L"] == st["nnz_L"]  # same fill: only the representation differs
+    K = p.kkt_full()
+    sols = []
+    for pl in (plan, pland):
+        em = Emulated(pl, v)
+        assert em.n_perturbed == 0
+        idx, val = p.rhs("solve_lsq", 5)
+        b = orc.vec_to_raw(idx, val, p.N)
+        z = em.solve(b, refine=0)
+        assert np.linalg.norm(K @ z - b) <= 1e-12 * np.linalg.norm(b)
+        assert np.linalg.norm(em.solve(b, refine=0, flow=False) - z) <= 1e-10 * np.linalg.norm(z)
+        sols.append(z)
+    assert np.abs(sols[0] - sols[1]).max() <= 1e-10 * np.abs(sols[1]).max()
+    # every level of a subtree only depends on the levels before it (checked inside Emulated._sst_factor)
+
+
+def test_two_dimensional_problems_have_no_sparse_subtrees():
+    p = problems.poisson_control(24, 2, seed=2)
+    s = Symbolic(p.N, *p.kkt_lower())
+    assert len(s.plan()["sst"]) == 0
+
+
 def test_plan_does_not_depend_on_the_number_of_host_threads(monkeypatch):
     """Nested dissection, product-term search and assembly map run on several host threads; ordering, task lists and
     the order of the product terms inside every entry of S (the summation order on the device) must not depend on how many."""
