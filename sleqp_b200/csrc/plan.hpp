@@ -195,6 +195,7 @@ struct Plan
   std::vector<char> sn_sparse; // nsuper: 1 if the supernode is a sparse subtree
   std::vector<SstMeta> sst;
   std::vector<int> sst_colptr, sst_rows, sst_lvl_ptr, sst_lvl_col;
+  size_t sst_smem_bytes = 0; // dynamic shared memory of the sst kernels: what the largest subtree of this plan needs
 
   // assembly of S straight into the panels: S_e = val[gsrc] - sum_t val[a]*val[b]/val[d]
   i64 nnzS = 0;

@@ -1634,6 +1634,12 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     M.r       = r;
     M.Rptr    = (int)P.Rptr[T];
     M.parent  = P.sn_parent[T];
+    // every segment starts on a 16-byte boundary of its (16-bit / 32-bit) device array: sst.cu stages them with
+    // 16-byte loads
+    for (std::vector<int>* v : {&P.sst_colptr, &P.sst_rows, &P.sst_lvl_ptr, &P.sst_lvl_col})
+    {
+      v->resize((v->size() + 7) & ~(size_t)7, 0);
+    }
     M.col_ptr = (int)P.sst_colptr.size();
     M.row_ptr = (int)P.sst_rows.size();
     M.lvl_ptr = (int)P.sst_lvl_ptr.size();
@@ -1729,6 +1735,17 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     sst_nnz[T]   = nnz;
     sst_index[T] = (int)P.sst.size();
     P.sst.push_back(M);
+    {
+      // dynamic shared memory of the subtree's CTA (sst.cu: sst_stage): values, front vector / update block, indices
+      const size_t vec = (size_t)std::max(k + r, r * r);
+      const size_t b   = sizeof(double) * ((((size_t)nnz + 1) & ~(size_t)1) + ((vec + 1) & ~(size_t)1)) + sizeof(int) * (((size_t)nlev + 4) & ~(size_t)3)
+                       + sizeof(unsigned short) * ((((size_t)k + 8) & ~(size_t)7) + (((size_t)nnz + 7) & ~(size_t)7) + (((size_t)k + 7) & ~(size_t)7));
+      P.sst_smem_bytes = std::max(P.sst_smem_bytes, b + 64);
+    }
+  }
+  for (std::vector<int>* v : {&P.sst_colptr, &P.sst_rows, &P.sst_lvl_ptr, &P.sst_lvl_col})
+  {
+    v->resize(((v->size() + 7) & ~(size_t)7) + 8, 0); // the staging reads whole 16-byte pieces
   }
   tick("sparse subtrees");
   // ---- storage offsets, levels, statistics ---------------------------------------------------------
