@@ -38,68 +38,99 @@ class Emulated:
 
     # ---------------------------------------------------------------- sparse subtrees (sst.cu)
     def _read_sst(self):
-        """SstMeta records of the plan (plan.hpp): supernodes kept with their exact sparse structure."""
+        """SstMeta records of the plan (plan.hpp): supernodes kept with their exact sparse structure, sorted by
+        generation; the index structure is read from the 16-bit blob the device stages (sst.cu: sst_stage)."""
         p = self.p
         ns = int(p["n_supernodes"])
         self.is_sst = np.zeros(ns, dtype=bool)
         self.sst = []
-        raw = np.asarray(p.get("sst", np.zeros((0, 16), dtype=np.int32))).reshape(-1, 16)
+        raw = np.asarray(p.get("sst", np.zeros((0, 24), dtype=np.int32))).reshape(-1, 24)
+        blob_all = np.asarray(p.get("sst_blob", np.zeros(0, dtype=np.int32)), dtype=np.int64)
+        last_gen = 0
         for rec in raw:
             lptr = int(np.array(rec[0:2], dtype=np.int32).view(np.int64)[0])
             uoff = int(np.array(rec[2:4], dtype=np.int32).view(np.int64)[0])
-            sn, first, k, r, rptr, parent, col_ptr, row_ptr, lvl_ptr, lvl_col, nlev, nnz = (int(v) for v in rec[4:16])
-            colptr = np.asarray(p["sst_colptr"][col_ptr : col_ptr + k + 1], dtype=np.int64)
-            rows = np.asarray(p["sst_rows"][row_ptr : row_ptr + nnz], dtype=np.int64)
-            lptrs = np.asarray(p["sst_lvl_ptr"][lvl_ptr : lvl_ptr + nlev + 1], dtype=np.int64)
-            lcols = np.asarray(p["sst_lvl_col"][lvl_col : lvl_col + k], dtype=np.int64)
-            assert colptr[0] == 0 and colptr[-1] == nnz and lptrs[-1] == k
-            self.sst.append(dict(Lptr=lptr, Uoff=uoff, sn=sn, first=first, k=k, r=r, Rptr=rptr, parent=parent, colptr=colptr, rows=rows,
-                                 lvl_ptr=lptrs, lvl_col=lcols, nlev=nlev, nnz=nnz))
+            (sn, first, k, r, rptr, signal, blob, blob_len16, nslev, nseg, nnz, gen, o_segstart, o_seglen, o_colptr, o_rows, ea_begin, ea_end,
+             col_ptr, row_ptr) = (int(v) for v in rec[4:24])
+            assert blob % 8 == 0 and gen >= last_gen
+            last_gen = gen
+            b = blob_all[blob : blob + 8 * blob_len16]
+            slvl = b[: nslev + 1]
+            segstart = b[o_segstart : o_segstart + nseg]
+            seglen = b[o_seglen : o_seglen + nseg]
+            colptr = b[o_colptr : o_colptr + k + 1]
+            rows = b[o_rows : o_rows + nnz]
+            assert slvl[0] == 0 and slvl[-1] == nseg and colptr[0] == 0 and colptr[-1] == nnz
+            assert np.array_equal(colptr, p["sst_colptr"][col_ptr : col_ptr + k + 1])
+            assert np.array_equal(rows, p["sst_rows"][row_ptr : row_ptr + nnz])
+            assert sorted(np.concatenate([np.arange(s0, s0 + n) for s0, n in zip(segstart, seglen)]).tolist()) == list(range(k))
+            seg_lev = np.zeros(k, dtype=np.int64)  # segment level of every column
+            seg_end = np.zeros(k, dtype=np.int64)
+            for lev in range(nslev):
+                for q in range(slvl[lev], slvl[lev + 1]):
+                    seg_lev[segstart[q] : segstart[q] + seglen[q]] = lev
+                    seg_end[segstart[q] : segstart[q] + seglen[q]] = segstart[q] + seglen[q]
+            if signal >= 0:
+                assert p["sn_parent"][sn] == signal and p["sn_sparse"][signal] == 0
+            self.sst.append(dict(Lptr=lptr, Uoff=uoff, sn=sn, first=first, k=k, r=r, Rptr=rptr, signal=signal, colptr=colptr, rows=rows,
+                                 slvl=slvl, segstart=segstart, seglen=seglen, nslev=nslev, nnz=nnz, gen=gen, seg_lev=seg_lev, seg_end=seg_end,
+                                 ea=(ea_begin, ea_end)))
             self.is_sst[sn] = True
             assert p["sn_sparse"][sn] == 1
 
+    def _sst_segments(self, M, lev):
+        return [(int(M["segstart"][q]), int(M["segstart"][q] + M["seglen"][q])) for q in range(M["slvl"][lev], M["slvl"][lev + 1])]
+
     def _sst_factor(self, M):
-        """k_sst_factor: right-looking sparse LDL^T, level by level; the levels must respect the dependencies."""
+        """k_sst_factor: extend-add of the child subtrees, then right-looking sparse LDL^T; one thread per segment,
+        segments of one level at a time: a target outside the thread's own segment must belong to a later level."""
         vals = self.L[M["Lptr"] : M["Lptr"] + M["nnz"]]
         k, r, colptr, rows = M["k"], M["r"], M["colptr"], M["rows"]
-        Us = np.zeros((r, r))
-        done = np.zeros(k, dtype=bool)
-        for lev in range(M["nlev"]):
-            cols = M["lvl_col"][M["lvl_ptr"][lev] : M["lvl_ptr"][lev + 1]]
-            upd = []
-            for j in cols:
-                p0, p1 = colptr[j], colptr[j + 1]
-                assert rows[p0] == j
-                d = vals[p0]
-                if not (abs(d) >= self.tau) or not np.isfinite(d):
-                    d = -self.tau if self.tau > 0 else -1e-300
-                    self.n_perturbed += 1
-                self.D[M["first"] + j] = d
-                vals[p0] = d
-                for a in range(p0 + 1, p1):
-                    la = vals[a] / d
-                    for b in range(p0 + 1, a + 1):
-                        upd.append((rows[a], rows[b], -la * vals[b]))
-                vals[p0 + 1 : p1] /= d
-            for ia, ib, u in upd:  # targets belong to later levels (or to the update block)
-                if ib >= k:
-                    Us[ia - k, ib - k] += u
-                else:
-                    assert not done[ib] and ib not in cols
-                    t = colptr[ib] + int(np.nonzero(rows[colptr[ib] : colptr[ib + 1]] == ia)[0][0])
-                    vals[t] += u
-            done[cols] = True
+        Us = np.zeros(r * r)  # column-major like the device block
+        for e in range(*M["ea"]):
+            dst, v = int(self.p["sst_ea_dst"][e]), self.U[int(self.p["sst_ea_src"][e])]
+            if dst >= 0:
+                assert dst < M["nnz"]
+                vals[dst] += v
+            else:
+                Us[-1 - dst] += v
+        for lev in range(M["nslev"]):
+            for j0, j1 in self._sst_segments(M, lev):
+                for j in range(j0, j1):
+                    p0, p1 = colptr[j], colptr[j + 1]
+                    assert rows[p0] == j
+                    d = vals[p0]
+                    if not (abs(d) >= self.tau) or not np.isfinite(d):
+                        d = -self.tau if self.tau > 0 else -1e-300
+                        self.n_perturbed += 1
+                    self.D[M["first"] + j] = d
+                    vals[p0] = d
+                    for a in range(p0 + 1, p1):
+                        la = vals[a] / d
+                        ia = rows[a]
+                        for b in range(p0 + 1, a + 1):
+                            ib, u = rows[b], -la * vals[b]
+                            if ib >= k:
+                                Us[(ia - k) + (ib - k) * r] += u
+                            else:
+                                assert (j < ib < j1) or M["seg_lev"][ib] > lev
+                                t = colptr[ib] + int(np.nonzero(rows[colptr[ib] : colptr[ib + 1]] == ia)[0][0])
+                                vals[t] += u
+                    vals[p0 + 1 : p1] /= d
         if r:
-            self.U[M["Uoff"] : M["Uoff"] + r * r] = Us.T.reshape(-1)  # column-major r x r like umat()
+            self.U[M["Uoff"] : M["Uoff"] + r * r] = Us
 
     def _sst_forward(self, M, yacc, yf):
         k, r, colptr, rows = M["k"], M["r"], M["colptr"], M["rows"]
         vals = self.L[M["Lptr"] : M["Lptr"] + M["nnz"]]
         x = np.concatenate([yacc[M["first"] : M["first"] + k], np.zeros(r)])
-        for lev in range(M["nlev"]):
-            for j in M["lvl_col"][M["lvl_ptr"][lev] : M["lvl_ptr"][lev + 1]]:
-                for a in range(colptr[j] + 1, colptr[j + 1]):
-                    x[rows[a]] -= vals[a] * x[j]
+        for lev in range(M["nslev"]):
+            for j0, j1 in self._sst_segments(M, lev):
+                for j in range(j0, j1):
+                    for a in range(colptr[j] + 1, colptr[j + 1]):
+                        i = rows[a]
+                        assert (j < i < j1) or i >= k or M["seg_lev"][i] > lev  # plain store / atomic on a later level
+                        x[i] -= vals[a] * x[j]
         yf[M["first"] : M["first"] + k] = x[:k] / self.D[M["first"] : M["first"] + k]
         tail = self.p["Ridx"][M["Rptr"] : M["Rptr"] + r]
         np.add.at(yacc, tail, x[k:])
@@ -109,9 +140,13 @@ class Emulated:
         vals = self.L[M["Lptr"] : M["Lptr"] + M["nnz"]]
         tail = self.p["Ridx"][M["Rptr"] : M["Rptr"] + r]
         x = np.concatenate([yf[M["first"] : M["first"] + k], xg[tail]])
-        for lev in range(M["nlev"] - 1, -1, -1):
-            for j in M["lvl_col"][M["lvl_ptr"][lev] : M["lvl_ptr"][lev + 1]]:
-                x[j] -= sum(vals[a] * x[rows[a]] for a in range(colptr[j] + 1, colptr[j + 1]))
+        for lev in range(M["nslev"] - 1, -1, -1):
+            for j0, j1 in self._sst_segments(M, lev):
+                for j in range(j1 - 1, j0 - 1, -1):
+                    for a in range(colptr[j] + 1, colptr[j + 1]):
+                        i = rows[a]
+                        assert (j < i < j1) or i >= k or M["seg_lev"][i] > lev
+                    x[j] -= sum(vals[a] * x[rows[a]] for a in range(colptr[j] + 1, colptr[j + 1]))
         xg[M["first"] : M["first"] + k] = x[:k]
 
     # ---------------------------------------------------------------- geometry helpers
@@ -271,8 +306,8 @@ class Emulated:
         cnt = np.zeros(ns, dtype=np.int64)
         for M in self.sst:  # k_sst_forward runs before the dataflow kernel and signals the parents
             self._sst_forward(M, yacc, yf)
-            if M["parent"] >= 0:
-                cnt[M["parent"]] += 1
+            if M["signal"] >= 0:
+                cnt[M["signal"]] += 1
         tasks = p["ffl_tasks"]
         for t in range(len(tasks)):
             lptr, rptr, first, k, h, i0, i1, j0, j1, wait_idx, need, signal_idx = fields(tasks[t])
@@ -303,7 +338,7 @@ class Emulated:
                 x[first + j] += Mr[lptr + ii * k + j] @ v
             if signal_idx >= 0:
                 cnt[signal_idx] += 1
-        for M in self.sst:  # k_sst_backward: after the dataflow kernel
+        for M in reversed(self.sst):  # k_sst_backward: after the dataflow kernel, generations from the top down
             self._sst_backward(M, yf, x)
         assert np.all(np.isfinite(x))
         return x
@@ -429,6 +464,12 @@ class Emulated:
                 w = W[int(p["Wptr"][T]) : int(p["Wptr"][T]) + h]
                 w[:k] = b_new[f : f + k]
                 w[k:] = 0.0
+                for c in p["child_idx"][int(p["child_ptr"][T]) : int(p["child_ptr"][T + 1])]:
+                    c = int(c)
+                    fc, kc, rc, hc = self._geom(c)
+                    rel = p["rel"][int(p["Rptr"][c]) : int(p["Rptr"][c + 1])]
+                    wc = W[int(p["Wptr"][c]) + kc : int(p["Wptr"][c]) + hc]
+                    np.add.at(w, rel, wc)
                 if self.is_sst[T]:
                     M = next(q for q in self.sst if q["sn"] == T)
                     vals = self.L[M["Lptr"] : M["Lptr"] + M["nnz"]]
@@ -437,12 +478,6 @@ class Emulated:
                             w[M["rows"][a]] -= vals[a] * w[j]
                     x[f : f + k] = w[:k]
                     continue
-                for c in p["child_idx"][int(p["child_ptr"][T]) : int(p["child_ptr"][T + 1])]:
-                    c = int(c)
-                    fc, kc, rc, hc = self._geom(c)
-                    rel = p["rel"][int(p["Rptr"][c]) : int(p["Rptr"][c + 1])]
-                    wc = W[int(p["Wptr"][c]) + kc : int(p["Wptr"][c]) + hc]
-                    np.add.at(w, rel, wc)
                 P = self.panel(T)
                 L11 = self._L11_full(T)
                 y = np.linalg.solve(L11, w[:k])

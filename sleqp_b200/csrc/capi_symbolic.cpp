@@ -367,9 +367,15 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
   FIELD(Ksrc)
   FIELD(sst_colptr)
   FIELD(sst_rows)
-  FIELD(sst_lvl_ptr)
-  FIELD(sst_lvl_col)
+  FIELD(sst_ea_src)
+  FIELD(sst_ea_dst)
+  FIELD(sst_gen_ptr)
 #undef FIELD
+  if (f == "sst_blob")
+  {
+    std::vector<int> v(P.sst_blob.begin(), P.sst_blob.end());
+    return export_vec(v, out, count);
+  }
   if (f == "sn_sparse")
   {
     std::vector<int> v(P.sn_sparse.begin(), P.sn_sparse.end());
@@ -377,7 +383,7 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
   }
   if (f == "sst")
   {
-    static_assert(sizeof(SstMeta) == 16 * sizeof(int), "SstMeta layout");
+    static_assert(sizeof(SstMeta) == 24 * sizeof(int), "SstMeta layout");
     return export_vec(P.sst, out, count);
   }
   if (f == "stages")

@@ -190,8 +190,9 @@ struct DevPlan
   DevBuf<int> Acsc_ptr, Acsc_row, Acsc_src, Acsr_ptr, Acsr_col, Acsr_src, Gsym_ptr, Gsym_col, Gsym_src;
   DevBuf<int> Acsr_k, Acsr_dsrc, Acsc_p;
   DevBuf<SstMeta> sst; // sparse subtrees (sst.cu)
-  DevBuf<int> sst_lvl_ptr;
-  DevBuf<unsigned short> sst_colptr16, sst_rows16, sst_lvl_col16; // 16-bit copies (a subtree has < 2^16 entries and rows)
+  DevBuf<unsigned short> sst_blob; // their index structure, 16-bit (a subtree has < 2^16 entries and rows)
+  DevBuf<long long> sst_ea_src;    // assembly of child subtrees into their parents
+  DevBuf<int> sst_ea_dst;
   DevBuf<int> Ksrc; // set_kkt plans: source of every value of tril(K) in the Jacobian's value array (-1: the constant 1)
 };
 

@@ -255,14 +255,9 @@ upload_plan(b200_fact* F, std::shared_ptr<const Plan> plan)
   dp.Gsym_src.upload(P.Gsym_src, s);
   dp.Ksrc.upload(P.Ksrc, s);
   dp.sst.upload(P.sst, s);
-  dp.sst_lvl_ptr.upload(P.sst_lvl_ptr, s);
-  {
-    std::vector<unsigned short> c16(P.sst_colptr.begin(), P.sst_colptr.end()), r16(P.sst_rows.begin(), P.sst_rows.end()), l16(P.sst_lvl_col.begin(), P.sst_lvl_col.end());
-    dp.sst_colptr16.upload(c16, s);
-    dp.sst_rows16.upload(r16, s);
-    dp.sst_lvl_col16.upload(l16, s);
-    B200_CUDA(cudaStreamSynchronize(s)); // locals
-  }
+  dp.sst_blob.upload(P.sst_blob, s);
+  dp.sst_ea_src.upload(P.sst_ea_src, s);
+  dp.sst_ea_dst.upload(P.sst_ea_dst, s);
   // the uploads read pageable host vectors owned by the (shared, immutable) plan: safe, but
   // finish them before anything else touches the stream
   B200_CUDA(cudaStreamSynchronize(s));

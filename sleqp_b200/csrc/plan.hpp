@@ -50,6 +50,8 @@ constexpr int SST_MAX_NNZ   = 6144; // entries of L in the subtree (values live 
 constexpr int SST_MAX_AVG   = 8;    // mean entries per column: beyond that the dense supernodal path is the better one
 constexpr int SST_THREADS   = 256;
 
+constexpr size_t SST_SMEM_LIMIT = 200 * 1024; // what sst.cu opts its kernels into
+
 struct SstMeta
 {
   long long Lptr;  // values of the subtree in the panel buffer (compact, column by column, diagonal first)
@@ -57,13 +59,18 @@ struct SstMeta
   int sn;          // supernode index
   int first, k, r;
   int Rptr;        // update rows in Ridx
-  int parent;      // parent supernode (-1: root)
-  int col_ptr;     // offset of its k + 1 column pointers in sst_colptr (entries relative to Lptr)
-  int row_ptr;     // offset of its row indices in sst_rows (front-local: < k a column of the subtree, else k + update row)
-  int lvl_ptr;     // offset of its nlev + 1 level pointers in sst_lvl_ptr
-  int lvl_col;     // offset of its k columns sorted by level in sst_lvl_col
-  int nlev, nnz;
+  int signal;      // dense parent supernode whose forward counter gets one signal when the subtree is swept, -1: none
+  int blob;        // offset of the index blob in sst_blob (16-bit units, multiple of 8)
+  int blob_len16;  // its length in 16-byte pieces
+  int nslev;       // levels of segments
+  int nseg;        // segments (single-child chains of the subtree's elimination tree)
+  int nnz;         // entries
+  int gen;         // generation: 0 = leaves of the supernodal tree, g = all children are subtrees of generations < g
+  int o_segstart, o_seglen, o_colptr, o_rows; // parts of the blob after the level pointers (16-bit units from blob)
+  int ea_begin, ea_end;                        // assembly of the children's update blocks: entries of sst_ea_src / _dst
+  int col_ptr, row_ptr;                        // host copies: offsets into Plan::sst_colptr / sst_rows (32-bit)
 };
+static_assert(sizeof(SstMeta) == 96, "SstMeta layout");
 
 // kinds of update tasks
 enum
@@ -194,7 +201,11 @@ struct Plan
   // sparse subtrees
   std::vector<char> sn_sparse; // nsuper: 1 if the supernode is a sparse subtree
   std::vector<SstMeta> sst;
-  std::vector<int> sst_colptr, sst_rows, sst_lvl_ptr, sst_lvl_col;
+  std::vector<int> sst_colptr, sst_rows; // 32-bit host copies (assembly map, emulation)
+  std::vector<unsigned short> sst_blob;  // what the device reads
+  std::vector<long long> sst_ea_src;     // assembly of child subtrees: offset of the entry in the update workspace ...
+  std::vector<int> sst_ea_dst;           // ... and where it goes: >= 0 slot of the subtree's values, < 0: -1 - index in its update block
+  std::vector<int> sst_gen_ptr;          // P.sst is sorted by generation: [gen_ptr[g], gen_ptr[g + 1])
   size_t sst_smem_bytes = 0; // dynamic shared memory of the sst kernels: what the largest subtree of this plan needs
 
   // assembly of S straight into the panels: S_e = val[gsrc] - sum_t val[a]*val[b]/val[d]

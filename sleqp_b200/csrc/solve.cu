@@ -993,13 +993,19 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
     int* const tickets_b = tickets_f + FLOW_SHARDS * FLOW_TICKET_PITCH;
     auto kf = sb.trace_fwd ? k_flow<true, true> : k_flow<true, false>;
     auto kb = sb.trace_bwd ? k_flow<false, true> : k_flow<false, false>;
-    kf<<<sb.trace_fwd ? max_ctas : grid(P.ffl_tasks.size()), FLOW_THREADS, 0, stream>>>(dp.ffl_tasks.p, fs, dp.Ridx.p, nb.Mt, nb.Dinv, sb.y, sb.yf, sb.x, sb.flow, tickets_f,
-                                                                (const FlowTrace*)sb.trace_fwd);
-    lc.tick();
+    if (!P.ffl_tasks.empty()) // nothing dense left when sparse subtrees cover the whole tree
+    {
+      kf<<<sb.trace_fwd ? max_ctas : grid(P.ffl_tasks.size()), FLOW_THREADS, 0, stream>>>(dp.ffl_tasks.p, fs, dp.Ridx.p, nb.Mt, nb.Dinv, sb.y, sb.yf, sb.x, sb.flow, tickets_f,
+                                                                  (const FlowTrace*)sb.trace_fwd);
+      lc.tick();
+    }
     mark(2);
-    kb<<<sb.trace_bwd ? max_ctas : grid(P.bfl_tasks.size()), FLOW_THREADS, 0, stream>>>(dp.bfl_tasks.p, bs, dp.Ridx.p, nb.Mr, nb.Dinv, sb.y, sb.yf, sb.x, sb.flow + ns, tickets_b,
-                                                                 (const FlowTrace*)sb.trace_bwd);
-    lc.tick();
+    if (!P.bfl_tasks.empty())
+    {
+      kb<<<sb.trace_bwd ? max_ctas : grid(P.bfl_tasks.size()), FLOW_THREADS, 0, stream>>>(dp.bfl_tasks.p, bs, dp.Ridx.p, nb.Mr, nb.Dinv, sb.y, sb.yf, sb.x, sb.flow + ns, tickets_b,
+                                                                   (const FlowTrace*)sb.trace_bwd);
+      lc.tick();
+    }
     enqueue_sst_backward(dp, nb, sb, stream, lc);
     mark(3);
   }

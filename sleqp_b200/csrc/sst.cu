@@ -1,15 +1,21 @@
 // sst.cu -- sparse subtrees (plan.hpp): complete subtrees of the elimination tree whose columns hold a few entries each
-// (chains, banded systems) are factored and swept with their exact sparse structure, one CTA per subtree, level by
-// level of the subtree's own elimination tree; everything of a subtree lives in shared memory while its CTA works.
+// (chains, banded systems) are factored and swept with their exact sparse structure, one CTA per subtree; everything
+// of a subtree lives in shared memory while its CTA works.
 //
 // Why: as dense 32-column supernodes the chain of config 3 (n = 1e6) stored 8.8 M entries for an exact nnz(L) of
 // 1.5 M, streamed 129 MB per sweep for 20 MB of factor, and paid one dataflow hand-off per 32-column level (7 levels
-// after amalgamation, 15 before). As 512 sparse subtrees of ~1000 columns it stores 1.005 x nnz(L) and the tree above
-// them is three small dense levels.
+// after amalgamation, 15 before). As sparse subtrees it stores 1.005 x nnz(L).
 //
-//   k_sst_factor    sparse LDL^T of every subtree (right-looking, columns of one level in parallel, shared-memory
-//                   atomics for the updates) + its r x r contribution block for the parent front
-//   k_sst_forward   y = D^-1 L^-1 b inside the subtree, contribution of the subtree to the right-hand side of its ancestors
+// Subtrees nest: generation 0 are the leaves of the supernodal tree, a subtree of generation g sits on top of
+// subtrees of earlier generations only (symbolic.cpp) -- for config 3 the whole top of the tree is ONE subtree of
+// generation 1, and no dense supernode (hence no dataflow kernel) is left. One launch per generation.
+//
+// Inside a subtree the unit of work is a SEGMENT: a maximal single-child path of the subtree's own elimination tree
+// (consecutive columns). One thread walks a segment column by column, segments of one level run in parallel; the
+// number of block-wide synchronisations is the number of segment levels, not the height of the elimination tree.
+//
+//   k_sst_factor    assembly of the children's update blocks, sparse LDL^T (right-looking), r x r update block
+//   k_sst_forward   y = D^-1 L^-1 b inside the subtree, contribution to the right-hand side of the ancestors
 //   k_sst_backward  x = L^-T (y - L21^T x_ancestors)
 #include "numeric.cuh"
 
@@ -21,29 +27,23 @@ namespace
 
 typedef unsigned short u16;
 
-// Shared memory of one CTA: the values of the subtree, the front vector (sweeps) or the update block (factorization),
-// and the WHOLE index structure of the subtree (column pointers, front-local rows, columns by level as 16-bit
-// integers, level pointers): a level of a subtree is a few dozen columns with two or three entries each, so anything
-// fetched from global memory inside the level loop costs a full memory latency per level (measured: 60 us for the
-// forward sweep of config 3 with the indices in global memory, against 13 us for the three dense levels above).
-constexpr int SST_VEC      = SST_MAX_COLS + SST_MAX_TAIL > SST_MAX_TAIL * SST_MAX_TAIL ? SST_MAX_COLS + SST_MAX_TAIL : SST_MAX_TAIL * SST_MAX_TAIL;
-constexpr size_t SST_SMEM = sizeof(double) * (size_t)(SST_MAX_NNZ + SST_VEC + 8) + sizeof(int) * (size_t)(SST_MAX_COLS + 8)
-                            + sizeof(u16) * (size_t)(SST_MAX_NNZ + 2 * SST_MAX_COLS + 16);
+constexpr size_t SST_SMEM = SST_SMEM_LIMIT; // upper bound of Plan::sst_smem_bytes (enforced by the analysis)
 
 struct SstShared
 {
-  double* vals; // nnz
-  double* vec;  // k + r (sweeps) / r * r (factorization)
-  int* lptr;    // nlev + 1
-  u16* colptr;  // k + 1
-  u16* rows;    // nnz
-  u16* lcol;    // k
+  double* vals;        // nnz
+  double* vec;         // k + r (sweeps) / r * r (factorization)
+  const u16* slvl;     // nslev + 1: segments by level
+  const u16* segstart; // first column of the segments, ordered by level
+  const u16* seglen;
+  const u16* colptr;   // k + 1
+  const u16* rows;     // nnz, front-local, diagonal first
 };
 
 // Bulk copy global -> shared in 16-byte pieces with eight loads per thread in flight before the first store: the
 // staging of a subtree is a few dozen KB per CTA, and with one load per thread and loop trip it is nothing but memory
 // latency (measured: 39 us of a 52 us forward sweep). Both pointers 16-byte aligned, n16 = number of 16-byte pieces
-// (the plan pads every segment so that reading up to the next multiple of 16 bytes is safe).
+// (the plan pads every part so that reading up to the next multiple of 16 bytes is safe).
 __device__ __forceinline__ void
 stage16(void* dst, const void* __restrict__ src, int n16)
 {
@@ -73,25 +73,22 @@ stage16(void* dst, const void* __restrict__ src, int n16)
   }
 }
 
-// carves the dynamic shared memory and loads the index structure and the values (segments padded to 16 bytes, see
-// symbolic.cpp); the caller fills vec and synchronises
+// carves the dynamic shared memory and loads the index blob and the values; the caller fills vec and synchronises
 __device__ __forceinline__ SstShared
-sst_stage(double* smem, const SstMeta& M, const u16* __restrict__ colptr_all, const u16* __restrict__ rows_all, const int* __restrict__ lvl_ptr_all,
-          const u16* __restrict__ lvl_col_all, const double* __restrict__ Lg, int vec_len)
+sst_stage(double* smem, const SstMeta& M, const u16* __restrict__ blob_all, const double* __restrict__ Lg, int vec_len)
 {
   SstShared S;
-  const int nv = (M.nnz + 1) & ~1, nx = (vec_len + 1) & ~1, nl = (M.nlev + 1 + 3) & ~3, nc = (M.k + 1 + 7) & ~7, nr = (M.nnz + 7) & ~7, nk = (M.k + 7) & ~7;
-  S.vals   = smem;
-  S.vec    = S.vals + nv;
-  S.lptr   = reinterpret_cast<int*>(S.vec + nx);
-  S.colptr = reinterpret_cast<u16*>(S.lptr + nl);
-  S.rows   = S.colptr + nc;
-  S.lcol   = S.rows + nr;
+  const int nv = (M.nnz + 1) & ~1, nx = (vec_len + 1) & ~1;
+  S.vals      = smem;
+  S.vec       = S.vals + nv;
+  u16* blob   = reinterpret_cast<u16*>(S.vec + nx);
+  S.slvl      = blob;
+  S.segstart  = blob + M.o_segstart;
+  S.seglen    = blob + M.o_seglen;
+  S.colptr    = blob + M.o_colptr;
+  S.rows      = blob + M.o_rows;
   stage16(S.vals, Lg, nv / 2);
-  stage16(S.lptr, lvl_ptr_all + M.lvl_ptr, nl / 4);
-  stage16(S.colptr, colptr_all + M.col_ptr, nc / 8);
-  stage16(S.rows, rows_all + M.row_ptr, nr / 8);
-  stage16(S.lcol, lvl_col_all + M.lvl_col, nk / 8);
+  stage16(blob, blob_all + M.blob, M.blob_len16);
   return S;
 }
 
@@ -105,10 +102,9 @@ smem_add(double* p, double v)
 
 __global__ void __launch_bounds__(SST_THREADS)
 k_sst_factor(const SstMeta* __restrict__ metas,
-             const u16* __restrict__ colptr_all,
-             const u16* __restrict__ rows_all,
-             const int* __restrict__ lvl_ptr_all,
-             const u16* __restrict__ lvl_col_all,
+             const u16* __restrict__ blob_all,
+             const long long* __restrict__ ea_src,
+             const int* __restrict__ ea_dst,
              double* __restrict__ L,
              double* __restrict__ U,
              double* __restrict__ D,
@@ -120,7 +116,7 @@ k_sst_factor(const SstMeta* __restrict__ metas,
   const SstMeta M = metas[blockIdx.x];
   const int k = M.k, r = M.r;
   double* Lg        = L + M.Lptr;
-  const SstShared S = sst_stage(sst_smem, M, colptr_all, rows_all, lvl_ptr_all, lvl_col_all, Lg, r * r); // vals = assembled entries of S, zeros in the fill
+  const SstShared S = sst_stage(sst_smem, M, blob_all, Lg, r * r); // vals = assembled entries of S, zeros in the fill
   double* vals      = S.vals;
   double* Us        = S.vec;
   for (int q = threadIdx.x; q < r * r; q += blockDim.x)
@@ -130,50 +126,83 @@ k_sst_factor(const SstMeta* __restrict__ metas,
   const double tau = scal[1];
   int nper         = 0;
   __syncthreads();
-  for (int lev = 0; lev < M.nlev; ++lev)
+  // extend-add of the children (subtrees of earlier generations, factored by earlier launches)
+  for (int base = M.ea_begin; base < M.ea_end; base += 4 * SST_THREADS)
   {
-    for (int q = S.lptr[lev] + threadIdx.x; q < S.lptr[lev + 1]; q += blockDim.x)
+    double v[4];
+    int dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
     {
-      const int j  = S.lcol[q];
-      const int p0 = S.colptr[j], p1 = S.colptr[j + 1];
-      double d     = vals[p0];
-      if (!(fabs(d) >= tau) || !isfinite(d))
+      const int e = base + u * SST_THREADS + threadIdx.x;
+      if (e < M.ea_end)
       {
-        d = tau > 0.0 ? -tau : -1e-300; // static pivoting, same rule as k_panel
-        ++nper;
+        dst[u] = ea_dst[e];
+        v[u]   = U[ea_src[e]];
       }
-      const double dinv = 1.0 / d;
-      D[M.first + j]    = d;
-      Dinv[M.first + j] = dinv;
-      vals[p0]          = d;
-      // right-looking update: A[ia, ib] -= f_a f_b / d for the entries a >= b of the column (all targets belong to
-      // ancestors of j, i.e. to later levels or to the update block; columns of one level may share a target: atomics)
-      for (int a = p0 + 1; a < p1; ++a)
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      const int e = base + u * SST_THREADS + threadIdx.x;
+      if (e < M.ea_end)
       {
-        const double la = vals[a] * dinv;
-        const int ia    = S.rows[a];
-        for (int b = p0 + 1; b <= a; ++b)
+        smem_add(dst[u] >= 0 ? vals + dst[u] : Us + (-1 - dst[u]), v[u]);
+      }
+    }
+  }
+  if (M.ea_end > M.ea_begin)
+  {
+    __syncthreads();
+  }
+  for (int lev = 0; lev < M.nslev; ++lev)
+  {
+    for (int q = S.slvl[lev] + threadIdx.x; q < S.slvl[lev + 1]; q += blockDim.x)
+    {
+      const int j0 = S.segstart[q], j1 = j0 + S.seglen[q];
+      for (int j = j0; j < j1; ++j)
+      {
+        const int p0 = S.colptr[j], p1 = S.colptr[j + 1];
+        double d     = vals[p0];
+        if (!(fabs(d) >= tau) || !isfinite(d))
         {
-          const int ib   = S.rows[b];
-          const double u = -la * vals[b];
-          if (ib >= k)
+          d = tau > 0.0 ? -tau : -1e-300; // static pivoting, same rule as k_panel
+          ++nper;
+        }
+        const double dinv = 1.0 / d;
+        D[M.first + j]    = d;
+        Dinv[M.first + j] = dinv;
+        vals[p0]          = d;
+        // right-looking update: A[ia, ib] -= f_a f_b / d for the entries a >= b of the column. All targets belong to
+        // ancestors of j: later columns of this segment (only this thread touches them before the next barrier, but
+        // other segments of the level may share targets further up: atomics throughout)
+        for (int a = p0 + 1; a < p1; ++a)
+        {
+          const double la = vals[a] * dinv;
+          const int ia    = S.rows[a];
+          for (int b = p0 + 1; b <= a; ++b)
           {
-            smem_add(Us + (ia - k) + (ib - k) * r, u);
-          }
-          else
-          {
-            int t = S.colptr[ib]; // position of row ia in column ib: the structure of an ancestor contains it
-            while (S.rows[t] != ia)
+            const int ib   = S.rows[b];
+            const double u = -la * vals[b];
+            if (ib >= k)
             {
-              ++t;
+              smem_add(Us + (ia - k) + (ib - k) * r, u);
             }
-            smem_add(vals + t, u);
+            else
+            {
+              int t = S.colptr[ib]; // position of row ia in column ib: the structure of an ancestor contains it
+              while (S.rows[t] != ia)
+              {
+                ++t;
+              }
+              smem_add(vals + t, u);
+            }
           }
         }
-      }
-      for (int a = p0 + 1; a < p1; ++a)
-      {
-        vals[a] *= dinv; // l_ij
+        for (int a = p0 + 1; a < p1; ++a)
+        {
+          vals[a] *= dinv; // l_ij
+        }
       }
     }
     __syncthreads();
@@ -185,7 +214,7 @@ k_sst_factor(const SstMeta* __restrict__ metas,
   double* Ug = U + M.Uoff;
   for (int q = threadIdx.x; q < r * r; q += blockDim.x)
   {
-    Ug[q] = Us[q]; // the whole block: nobody zeroes the update matrix of a leaf
+    Ug[q] = Us[q]; // the whole block: nobody zeroes the update matrix of a sparse subtree
   }
   if (nper)
   {
@@ -193,15 +222,13 @@ k_sst_factor(const SstMeta* __restrict__ metas,
   }
 }
 
-// forward: inside the subtree y = L^-1 b level by level (a column that is done pushes its multiples down its entries),
-// yf = D^-1 y; the rows of the ancestors receive their share through atomics on the global accumulator, then the
-// parent's dependency counter is signalled (the dataflow kernel that follows waits on it like on any child)
+// forward: inside the subtree y = L^-1 b segment level by segment level (a column that is done pushes its multiples
+// down its entries: plain stores inside the thread's own segment, atomics above it), yf = D^-1 y; the rows of the
+// ancestors receive their share through atomics on the global accumulator, then the dense parent's dependency counter
+// is signalled (the dataflow kernel that follows waits on it like on any child)
 __global__ void __launch_bounds__(SST_THREADS)
 k_sst_forward(const SstMeta* __restrict__ metas,
-              const u16* __restrict__ colptr_all,
-              const u16* __restrict__ rows_all,
-              const int* __restrict__ lvl_ptr_all,
-              const u16* __restrict__ lvl_col_all,
+              const u16* __restrict__ blob_all,
               const int* __restrict__ Ridx,
               const double* __restrict__ L,
               const double* __restrict__ Dinv,
@@ -212,7 +239,7 @@ k_sst_forward(const SstMeta* __restrict__ metas,
   extern __shared__ double sst_smem[];
   const SstMeta M = metas[blockIdx.x];
   const int k = M.k, r = M.r;
-  const SstShared S = sst_stage(sst_smem, M, colptr_all, rows_all, lvl_ptr_all, lvl_col_all, L + M.Lptr, k + r);
+  const SstShared S = sst_stage(sst_smem, M, blob_all, L + M.Lptr, k + r);
   double* x         = S.vec;
   {
     double t[(SST_MAX_COLS + SST_MAX_TAIL + SST_THREADS - 1) / SST_THREADS]; // all loads of the right-hand side first
@@ -233,15 +260,27 @@ k_sst_forward(const SstMeta* __restrict__ metas,
     }
   }
   __syncthreads();
-  for (int lev = 0; lev < M.nlev; ++lev)
+  for (int lev = 0; lev < M.nslev; ++lev)
   {
-    for (int q = S.lptr[lev] + threadIdx.x; q < S.lptr[lev + 1]; q += blockDim.x)
+    for (int q = S.slvl[lev] + threadIdx.x; q < S.slvl[lev + 1]; q += blockDim.x)
     {
-      const int j    = S.lcol[q];
-      const double y = x[j];
-      for (int a = S.colptr[j] + 1; a < S.colptr[j + 1]; ++a)
+      const int j0 = S.segstart[q], j1 = j0 + S.seglen[q];
+      for (int j = j0; j < j1; ++j)
       {
-        smem_add(x + S.rows[a], -S.vals[a] * y);
+        const double y = x[j];
+        for (int a = S.colptr[j] + 1; a < S.colptr[j + 1]; ++a)
+        {
+          const int i    = S.rows[a];
+          const double u = -S.vals[a] * y;
+          if (i < j1)
+          {
+            x[i] += u; // a later column of this thread's own segment
+          }
+          else
+          {
+            smem_add(x + i, u);
+          }
+        }
       }
     }
     __syncthreads();
@@ -254,24 +293,22 @@ k_sst_forward(const SstMeta* __restrict__ metas,
   {
     atomicAdd(yacc + Ridx[M.Rptr + q], x[k + q]);
   }
-  if (M.parent >= 0)
+  if (M.signal >= 0)
   {
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0)
     {
-      atomicAdd(cnt + M.parent, 1);
+      atomicAdd(cnt + M.signal, 1);
     }
   }
 }
 
-// backward: x_j = yf_j - sum_i l_ij x_i over the entries of column j, levels from the root of the subtree down
+// backward: x_j = yf_j - sum_i l_ij x_i over the entries of column j; segment levels from the root of the subtree
+// down, the columns of a segment from its top to its bottom (no atomics: a column only reads its ancestors)
 __global__ void __launch_bounds__(SST_THREADS)
 k_sst_backward(const SstMeta* __restrict__ metas,
-               const u16* __restrict__ colptr_all,
-               const u16* __restrict__ rows_all,
-               const int* __restrict__ lvl_ptr_all,
-               const u16* __restrict__ lvl_col_all,
+               const u16* __restrict__ blob_all,
                const int* __restrict__ Ridx,
                const double* __restrict__ L,
                const double* __restrict__ yf,
@@ -280,7 +317,7 @@ k_sst_backward(const SstMeta* __restrict__ metas,
   extern __shared__ double sst_smem[];
   const SstMeta M = metas[blockIdx.x];
   const int k = M.k, r = M.r;
-  const SstShared S = sst_stage(sst_smem, M, colptr_all, rows_all, lvl_ptr_all, lvl_col_all, L + M.Lptr, k + r);
+  const SstShared S = sst_stage(sst_smem, M, blob_all, L + M.Lptr, k + r);
   double* x         = S.vec;
   {
     double t[(SST_MAX_COLS + SST_MAX_TAIL + SST_THREADS - 1) / SST_THREADS];
@@ -301,17 +338,20 @@ k_sst_backward(const SstMeta* __restrict__ metas,
     }
   }
   __syncthreads();
-  for (int lev = M.nlev - 1; lev >= 0; --lev)
+  for (int lev = M.nslev - 1; lev >= 0; --lev)
   {
-    for (int q = S.lptr[lev] + threadIdx.x; q < S.lptr[lev + 1]; q += blockDim.x)
+    for (int q = S.slvl[lev] + threadIdx.x; q < S.slvl[lev + 1]; q += blockDim.x)
     {
-      const int j = S.lcol[q];
-      double s    = x[j];
-      for (int a = S.colptr[j] + 1; a < S.colptr[j + 1]; ++a)
+      const int j0 = S.segstart[q];
+      for (int j = j0 + S.seglen[q] - 1; j >= j0; --j)
       {
-        s -= S.vals[a] * x[S.rows[a]];
+        double s = x[j];
+        for (int a = S.colptr[j] + 1; a < S.colptr[j + 1]; ++a)
+        {
+          s -= S.vals[a] * x[S.rows[a]];
+        }
+        x[j] = s;
       }
-      x[j] = s;
     }
     __syncthreads();
   }
@@ -340,42 +380,50 @@ configure_sst_kernels(int device)
 void
 enqueue_sst_factor(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc)
 {
-  const int n = (int)dp.plan->sst.size();
-  if (n == 0)
+  const std::vector<int>& gp = dp.plan->sst_gen_ptr;
+  for (size_t g = 0; g + 1 < gp.size(); ++g) // children first
   {
-    return;
+    if (gp[g + 1] == gp[g])
+    {
+      continue;
+    }
+    k_sst_factor<<<gp[g + 1] - gp[g], SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p + gp[g], dp.sst_blob.p, dp.sst_ea_src.p, dp.sst_ea_dst.p, nb.L, nb.U, nb.D, nb.Dinv, nb.scal,
+                                                                                      nb.n_perturbed);
+    lc.tick("sst");
+    B200_CUDA(cudaGetLastError());
   }
-  k_sst_factor<<<n, SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p, dp.sst_colptr16.p, dp.sst_rows16.p, dp.sst_lvl_ptr.p, dp.sst_lvl_col16.p, nb.L, nb.U, nb.D, nb.Dinv, nb.scal,
-                                                     nb.n_perturbed);
-  lc.tick("sst");
-  B200_CUDA(cudaGetLastError());
 }
 
 void
 enqueue_sst_forward(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc)
 {
-  const int n = (int)dp.plan->sst.size();
-  if (n == 0)
+  const std::vector<int>& gp = dp.plan->sst_gen_ptr;
+  for (size_t g = 0; g + 1 < gp.size(); ++g)
   {
-    return;
+    if (gp[g + 1] == gp[g])
+    {
+      continue;
+    }
+    k_sst_forward<<<gp[g + 1] - gp[g], SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p + gp[g], dp.sst_blob.p, dp.Ridx.p, nb.L, nb.Dinv, sb.y, sb.yf, sb.flow);
+    lc.tick();
+    B200_CUDA(cudaGetLastError());
   }
-  k_sst_forward<<<n, SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p, dp.sst_colptr16.p, dp.sst_rows16.p, dp.sst_lvl_ptr.p, dp.sst_lvl_col16.p, dp.Ridx.p, nb.L, nb.Dinv, sb.y, sb.yf,
-                                                  sb.flow);
-  lc.tick();
-  B200_CUDA(cudaGetLastError());
 }
 
 void
 enqueue_sst_backward(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc)
 {
-  const int n = (int)dp.plan->sst.size();
-  if (n == 0)
+  const std::vector<int>& gp = dp.plan->sst_gen_ptr;
+  for (size_t g = gp.size() - 1; g-- > 0;) // parents first
   {
-    return;
+    if (gp[g + 1] == gp[g])
+    {
+      continue;
+    }
+    k_sst_backward<<<gp[g + 1] - gp[g], SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p + gp[g], dp.sst_blob.p, dp.Ridx.p, nb.L, sb.yf, sb.x);
+    lc.tick();
+    B200_CUDA(cudaGetLastError());
   }
-  k_sst_backward<<<n, SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p, dp.sst_colptr16.p, dp.sst_rows16.p, dp.sst_lvl_ptr.p, dp.sst_lvl_col16.p, dp.Ridx.p, nb.L, sb.yf, sb.x);
-  lc.tick();
-  B200_CUDA(cudaGetLastError());
 }
 
 } // namespace b200

@@ -1165,35 +1165,69 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
   }
   tick("column counts");
-  // ---- sparse subtrees: maximal complete subtrees with few entries per column (plan.hpp) ---------------------------
+  // ---- sparse subtrees: maximal complete subtrees with few entries per column (plan.hpp), in generations: what is
+  // left of the tree once the subtrees of one generation are cut off may again end in sparse subtrees (the separators
+  // above the chains of config 3), whose children are the subtrees of the generations before ---------------------
   std::vector<int> sst_root(m, -1); // root (L1 label) of the sparse subtree a column belongs to
+  std::vector<int> sst_gen(m, -1);  // generation of the subtree rooted at a column
   {
     const char* e   = std::getenv("B200_SST"); // 0: everything through the dense supernodal path (measurements, tests)
     const bool on   = !(e && e[0] == '0');
-    std::vector<int> size(m, 1);
-    std::vector<i64> nnz(m, 0);
-    std::vector<char> ok(m, 1);
-    for (int j = 0; j < m && on; ++j) // children before parents
+    std::vector<int> full(m, 1); // size of the whole subtree (a contiguous range of postorder labels)
+    for (int j = 0; j < m; ++j)
     {
-      nnz[j] += cc1[j];
-      ok[j] = ok[j] && size[j] <= SST_MAX_COLS && nnz[j] <= SST_MAX_NNZ && nnz[j] <= (i64)SST_MAX_AVG * size[j] && cc1[j] - 1 <= SST_MAX_TAIL;
-      const int p = parent1[j];
-      if (p != -1)
+      if (parent1[j] != -1)
       {
-        size[p] += size[j];
-        nnz[p] += nnz[j];
-        ok[p] = ok[p] && ok[j];
+        full[parent1[j]] += full[j];
       }
     }
-    for (int j = 0; j < m && on; ++j)
+    std::vector<int> size(m);
+    std::vector<i64> nnz(m);
+    std::vector<char> ok(m);
+    for (int gen = 0; on && gen < 16; ++gen)
     {
-      const int p = parent1[j];
-      if (ok[j] && (p == -1 || !ok[p]) && size[j] >= SST_MIN_COLS)
+      // over the columns not yet in a subtree: own columns / entries below every node, limits
+      std::fill(size.begin(), size.end(), 0);
+      std::fill(nnz.begin(), nnz.end(), 0);
+      std::fill(ok.begin(), ok.end(), 1);
+      for (int j = 0; j < m; ++j) // children before parents
       {
-        for (int c = j - size[j] + 1; c <= j; ++c) // a subtree is contiguous in the postorder
+        if (sst_root[j] == -1)
         {
-          sst_root[c] = j;
+          size[j] += 1;
+          nnz[j] += cc1[j];
+          ok[j] = ok[j] && size[j] <= SST_MAX_COLS && nnz[j] <= SST_MAX_NNZ && nnz[j] <= (i64)SST_MAX_AVG * size[j];
         }
+        const int p = parent1[j];
+        if (p != -1)
+        {
+          size[p] += size[j];
+          nnz[p] += nnz[j];
+          ok[p] = ok[p] && ok[j];
+        }
+      }
+      // the highest eligible nodes, parents first
+      const int min_cols = gen == 0 ? SST_MIN_COLS : 1;
+      bool any           = false;
+      for (int j = m - 1; j >= 0; --j)
+      {
+        if (sst_root[j] != -1 || !ok[j] || cc1[j] - 1 > SST_MAX_TAIL || size[j] < min_cols)
+        {
+          continue;
+        }
+        for (int c = j - full[j] + 1; c <= j; ++c)
+        {
+          if (sst_root[c] == -1)
+          {
+            sst_root[c] = j;
+          }
+        }
+        sst_gen[j] = gen;
+        any        = true;
+      }
+      if (!any)
+      {
+        break;
       }
     }
   }
@@ -1213,7 +1247,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       bool jn = false;
       if (sst_root[j] != -1 || sst_root[j + 1] != -1)
       {
-        jn = sst_root[j] == sst_root[j + 1]; // a sparse subtree is one supernode, nothing else joins it
+        jn = false; // the columns of a sparse subtree are grouped below (they need not be consecutive here)
       }
       else if (parent1[j] == j + 1)
       {
@@ -1317,7 +1351,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       {
         closed[l] = 1;
       }
-      if (sst_root[l] != -1) // a sparse subtree stays on its own
+      if (sst_root[l] != -1) // the columns of a sparse subtree form their own group, nothing else merges with them
       {
         closed[l] = 1;
         open[l]   = 0;
@@ -1334,7 +1368,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     }
     for (int j = 0; j < m; ++j)
     {
-      grp1[j] = rgrp[rn_last[j]];
+      grp1[j] = sst_root[j] != -1 ? sst_root[j] : rgrp[rn_last[j]];
     }
     // order: postorder over the tree of groups (children by ascending root), the columns of a group ascending
     std::vector<int> gcount(m + 1, 0), gnodes(std::max(m, 1));
@@ -1358,7 +1392,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     std::vector<int> ghead(m, -1), gnext(m, -1);
     for (int r = m - 1; r >= 0; --r)
     {
-      if (closed[r] && parent1[r] != -1)
+      if (grp1[r] == r && parent1[r] != -1) // r is the root (last column) of its group
       {
         const int pg = grp1[parent1[r]];
         gnext[r]     = ghead[pg];
@@ -1396,7 +1430,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   }
   // final labels: position k holds L1 label post[k]; compose with the postorder to ND labels
   std::vector<int> cc_final(m), grp_final(m);
-  std::vector<char> sst_final(m, 0);
+  std::vector<int> sst_final(m, -1); // generation of the sparse subtree a column belongs to (-1: none)
   {
     std::vector<int> l1_to_final(m);
     for (int k = 0; k < m; ++k)
@@ -1407,7 +1441,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     {
       cc_final[k]  = cc1[post[k]];
       grp_final[k] = l1_to_final[grp1[post[k]]];
-      sst_final[k] = sst_root[post[k]] != -1;
+      sst_final[k] = sst_root[post[k]] != -1 ? sst_gen[sst_root[post[k]]] : -1;
     }
     for (int k = 0; k < m; ++k)
     {
@@ -1608,47 +1642,67 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   }
 
   tick("row structures + rel");
-  // ---- sparse subtrees: exact column structures, levels of their own elimination trees ----------------------------
+  // ---- sparse subtrees: exact column structures, chains ("segments") and their levels, child assembly maps ---------
+  // Device layout per subtree (sst.cu): values in the panel buffer (compact, column by column, diagonal first) and
+  // ONE blob of 16-bit indices [level pointers over segments | segment starts | segment lengths | column pointers |
+  // front-local rows], every part padded to 16 bytes. A segment is a maximal single-child path of the subtree's own
+  // elimination tree (consecutive columns): one thread walks it sequentially, segments of one level run in parallel.
   P.sn_sparse.assign(ns, 0);
   std::vector<i64> sst_nnz(ns, 0);       // entries of a sparse subtree (its share of the panel buffer)
   std::vector<int> sst_index(ns, -1);    // position in P.sst
   std::vector<int> sst_col_of(m, -1);    // for the columns of sparse subtrees: offset of their column pointer in sst_colptr
+  std::vector<int> sst_ea_child;         // per assembly entry: the child supernode (until its workspace offset is known)
+  for (int T = 0; T < ns; ++T)
+  {
+    P.sn_sparse[T] = sst_final[P.sn_first[T]] >= 0;
+  }
+  auto pad8 = [](std::vector<unsigned short>& v) { v.resize((v.size() + 7) & ~(size_t)7, 0); };
   for (int T = 0; T < ns; ++T)
   {
     const int f = P.sn_first[T], l = P.sn_first[T + 1] - 1, k = l - f + 1;
-    if (!sst_final[f])
+    if (!P.sn_sparse[T])
     {
       continue;
     }
-    if (P.child_ptr[T] != P.child_ptr[T + 1])
-    {
-      return fail(err, B200_ERR_ARG, "internal: a sparse subtree has a child supernode");
-    }
-    P.sn_sparse[T] = 1;
     const int* rows_T = P.Ridx.data() + P.Rptr[T];
     const int r       = (int)(P.Rptr[T + 1] - P.Rptr[T]);
-    SstMeta M;
+    SstMeta M         = SstMeta();
     M.sn      = T;
     M.first   = f;
     M.k       = k;
     M.r       = r;
     M.Rptr    = (int)P.Rptr[T];
-    M.parent  = P.sn_parent[T];
-    // every segment starts on a 16-byte boundary of its (16-bit / 32-bit) device array: sst.cu stages them with
-    // 16-byte loads
-    for (std::vector<int>* v : {&P.sst_colptr, &P.sst_rows, &P.sst_lvl_ptr, &P.sst_lvl_col})
-    {
-      v->resize((v->size() + 7) & ~(size_t)7, 0);
-    }
-    M.col_ptr = (int)P.sst_colptr.size();
-    M.row_ptr = (int)P.sst_rows.size();
-    M.lvl_ptr = (int)P.sst_lvl_ptr.size();
-    M.lvl_col = (int)P.sst_lvl_col.size();
-    M.Lptr = M.Uoff = 0; // set with the storage offsets / the update workspace
-    // struct(j) = {j} + lower adjacency of j + the structures of its children without j (all inside the subtree)
+    M.gen     = sst_final[f];
+    M.signal  = (P.sn_parent[T] >= 0 && !P.sn_sparse[P.sn_parent[T]]) ? P.sn_parent[T] : -1;
+    // front-local index of a row (new labels): a column of the subtree or one of its update rows
+    auto local = [&](int i) -> int {
+      if (i <= l)
+      {
+        return i >= f ? i - f : -1;
+      }
+      const int* it = std::lower_bound(rows_T, rows_T + r, i);
+      return (it != rows_T + r && *it == i) ? k + (int)(it - rows_T) : -1;
+    };
+    // struct(j) = lower adjacency of j + the structures of its children without j; a child is a column of the subtree
+    // or the root of a child subtree (whose structure is its update rows)
     std::vector<std::vector<int>> st((size_t)k);
-    std::vector<int> lev((size_t)k, 0);
-    int nlev = 0;
+    std::vector<int> nchild((size_t)k, 0); // children inside the subtree
+    for (int q = P.child_ptr[T]; q < P.child_ptr[T + 1]; ++q)
+    {
+      const int c = P.child_idx[q];
+      if (!P.sn_sparse[c])
+      {
+        return fail(err, B200_ERR_ARG, "internal: a sparse subtree has a dense child supernode");
+      }
+      const int pc = parent[P.sn_first[c + 1] - 1]; // the column of T the child hangs below
+      for (i64 t = P.Rptr[c]; t < P.Rptr[c + 1]; ++t)
+      {
+        if (P.Ridx[t] != pc)
+        {
+          st[(size_t)(pc - f)].push_back(P.Ridx[t]);
+        }
+      }
+    }
     for (int j = f; j <= l; ++j)
     {
       std::vector<int>& cur = st[(size_t)(j - f)];
@@ -1665,7 +1719,6 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       {
         return fail(err, B200_ERR_ARG, "internal: column structure of a sparse subtree disagrees with the column count");
       }
-      // hand the structure (without the parent itself) on to the parent
       const int par = parent[j];
       if (par != -1 && par <= l)
       {
@@ -1677,75 +1730,197 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
             up.push_back(i);
           }
         }
-        lev[(size_t)(par - f)] = std::max(lev[(size_t)(par - f)], lev[(size_t)(j - f)] + 1);
+        ++nchild[(size_t)(par - f)];
       }
-      nlev = std::max(nlev, lev[(size_t)(j - f)] + 1);
     }
-    // column pointers (relative to the subtree's values), rows as front-local indices, the diagonal first
-    int nnz = 0;
+    // column pointers and front-local rows (diagonal first)
+    std::vector<int> colptr((size_t)k + 1, 0), rowloc;
     for (int j = f; j <= l; ++j)
     {
-      sst_col_of[j] = (int)P.sst_colptr.size();
-      P.sst_colptr.push_back(nnz);
-      P.sst_rows.push_back(j - f);
+      colptr[(size_t)(j - f)] = (int)rowloc.size();
+      rowloc.push_back(j - f);
       for (int i : st[(size_t)(j - f)])
       {
-        int loc;
-        if (i <= l)
+        const int loc = local(i);
+        if (loc < 0)
         {
-          loc = i - f;
+          return fail(err, B200_ERR_ARG, "internal: row of a sparse subtree missing from its update rows");
         }
-        else
-        {
-          const int* it = std::lower_bound(rows_T, rows_T + r, i);
-          if (it == rows_T + r || *it != i)
-          {
-            return fail(err, B200_ERR_ARG, "internal: row of a sparse subtree missing from its update rows");
-          }
-          loc = k + (int)(it - rows_T);
-        }
-        P.sst_rows.push_back(loc);
+        rowloc.push_back(loc);
       }
-      nnz += 1 + (int)st[(size_t)(j - f)].size();
     }
-    P.sst_colptr.push_back(nnz);
-    M.nnz  = nnz;
-    M.nlev = nlev;
-    // columns by level (counting sort)
-    std::vector<int> cnt((size_t)nlev + 1, 0);
+    const int nnz     = (int)rowloc.size();
+    colptr[(size_t)k] = nnz;
+    // segments: column c continues the segment of c - 1 iff c - 1 is its only child inside the subtree
+    std::vector<int> seg_start, seg_len, seg_of((size_t)k, 0), seg_lev;
     for (int c = 0; c < k; ++c)
     {
-      ++cnt[(size_t)lev[(size_t)c] + 1];
+      const bool cont = c > 0 && parent[f + c - 1] == f + c && nchild[(size_t)c] == 1;
+      if (!cont)
+      {
+        seg_start.push_back(c);
+        seg_len.push_back(0);
+        seg_lev.push_back(0);
+      }
+      seg_of[(size_t)c] = (int)seg_start.size() - 1;
+      ++seg_len.back();
     }
-    for (int q = 0; q < nlev; ++q)
+    const int nseg = (int)seg_start.size();
+    int nslev      = 0;
+    for (int q = 0; q < nseg; ++q) // children before parents: levels of the child segments are final
+    {
+      const int top = f + seg_start[(size_t)q] + seg_len[(size_t)q] - 1;
+      const int par = parent[top];
+      nslev         = std::max(nslev, seg_lev[(size_t)q] + 1);
+      if (par != -1 && par <= l)
+      {
+        int& pl = seg_lev[(size_t)seg_of[(size_t)(par - f)]];
+        pl      = std::max(pl, seg_lev[(size_t)q] + 1);
+      }
+    }
+    std::vector<int> cnt((size_t)nslev + 1, 0);
+    for (int q = 0; q < nseg; ++q)
+    {
+      ++cnt[(size_t)seg_lev[(size_t)q] + 1];
+    }
+    for (int q = 0; q < nslev; ++q)
     {
       cnt[(size_t)q + 1] += cnt[(size_t)q];
     }
-    for (int q = 0; q <= nlev; ++q)
+    std::vector<int> order((size_t)nseg);
     {
-      P.sst_lvl_ptr.push_back(cnt[(size_t)q]);
+      std::vector<int> fillp(cnt.begin(), cnt.end() - 1);
+      for (int q = 0; q < nseg; ++q)
+      {
+        order[(size_t)fillp[(size_t)seg_lev[(size_t)q]]++] = q;
+      }
     }
-    std::vector<int> fillp(cnt.begin(), cnt.end() - 1);
-    const size_t base = P.sst_lvl_col.size();
-    P.sst_lvl_col.resize(base + (size_t)k);
+    // the blob
+    pad8(P.sst_blob);
+    M.blob = (int)P.sst_blob.size();
+    for (int q = 0; q <= nslev; ++q)
+    {
+      P.sst_blob.push_back((unsigned short)cnt[(size_t)q]);
+    }
+    pad8(P.sst_blob);
+    M.o_segstart = (int)P.sst_blob.size() - M.blob;
+    for (int q : order)
+    {
+      P.sst_blob.push_back((unsigned short)seg_start[(size_t)q]);
+    }
+    pad8(P.sst_blob);
+    M.o_seglen = (int)P.sst_blob.size() - M.blob;
+    for (int q : order)
+    {
+      P.sst_blob.push_back((unsigned short)seg_len[(size_t)q]);
+    }
+    pad8(P.sst_blob);
+    M.o_colptr = (int)P.sst_blob.size() - M.blob;
+    for (int c = 0; c <= k; ++c)
+    {
+      P.sst_blob.push_back((unsigned short)colptr[(size_t)c]);
+    }
+    pad8(P.sst_blob);
+    M.o_rows = (int)P.sst_blob.size() - M.blob;
+    for (int v : rowloc)
+    {
+      P.sst_blob.push_back((unsigned short)v);
+    }
+    pad8(P.sst_blob);
+    M.blob_len16 = ((int)P.sst_blob.size() - M.blob) / 8;
+    M.nslev      = nslev;
+    M.nseg       = nseg;
+    M.nnz        = nnz;
+    // int copies for the host side (assembly destinations below, emulation in the tests)
     for (int c = 0; c < k; ++c)
     {
-      P.sst_lvl_col[base + (size_t)fillp[(size_t)lev[(size_t)c]]++] = c;
+      sst_col_of[f + c] = (int)P.sst_colptr.size() + c;
     }
+    M.col_ptr = (int)P.sst_colptr.size();
+    M.row_ptr = (int)P.sst_rows.size();
+    P.sst_colptr.insert(P.sst_colptr.end(), colptr.begin(), colptr.end());
+    P.sst_rows.insert(P.sst_rows.end(), rowloc.begin(), rowloc.end());
+    // assembly of the children: where every entry (a >= b) of a child's update block goes -- a slot of the compact
+    // values (>= 0) or an entry of this subtree's own update block (-1 - index)
+    M.ea_begin = (int)P.sst_ea_dst.size();
+    for (int q = P.child_ptr[T]; q < P.child_ptr[T + 1]; ++q)
+    {
+      const int c  = P.child_idx[q];
+      const int rc = (int)(P.Rptr[c + 1] - P.Rptr[c]);
+      for (int bcol = 0; bcol < rc; ++bcol)
+      {
+        const int ib = local(P.Ridx[P.Rptr[c] + bcol]);
+        for (int arow = bcol; arow < rc; ++arow)
+        {
+          const int ia = local(P.Ridx[P.Rptr[c] + arow]);
+          if (ia < 0 || ib < 0)
+          {
+            return fail(err, B200_ERR_ARG, "internal: update row of a child missing from the sparse subtree");
+          }
+          sst_ea_child.push_back(c);
+          P.sst_ea_src.push_back(arow + (i64)bcol * rc); // + the child's workspace offset once that is allocated
+          if (ib >= k)
+          {
+            P.sst_ea_dst.push_back(-1 - ((ia - k) + (ib - k) * r));
+          }
+          else
+          {
+            const int* b0 = rowloc.data() + colptr[(size_t)ib];
+            const int* b1 = rowloc.data() + colptr[(size_t)ib + 1];
+            const int* it = std::lower_bound(b0, b1, ia);
+            if (it == b1 || *it != ia)
+            {
+              return fail(err, B200_ERR_ARG, "internal: fill of a child missing from the structure of the sparse subtree");
+            }
+            P.sst_ea_dst.push_back((int)(it - rowloc.data()));
+          }
+        }
+      }
+    }
+    M.ea_end = (int)P.sst_ea_dst.size();
     sst_nnz[T]   = nnz;
     sst_index[T] = (int)P.sst.size();
     P.sst.push_back(M);
     {
-      // dynamic shared memory of the subtree's CTA (sst.cu: sst_stage): values, front vector / update block, indices
+      // dynamic shared memory of the subtree's CTA (sst.cu): values, front vector / update block, index blob
       const size_t vec = (size_t)std::max(k + r, r * r);
-      const size_t b   = sizeof(double) * ((((size_t)nnz + 1) & ~(size_t)1) + ((vec + 1) & ~(size_t)1)) + sizeof(int) * (((size_t)nlev + 4) & ~(size_t)3)
-                       + sizeof(unsigned short) * ((((size_t)k + 8) & ~(size_t)7) + (((size_t)nnz + 7) & ~(size_t)7) + (((size_t)k + 7) & ~(size_t)7));
+      const size_t b   = sizeof(double) * ((((size_t)nnz + 1) & ~(size_t)1) + ((vec + 1) & ~(size_t)1)) + 16 * (size_t)M.blob_len16;
       P.sst_smem_bytes = std::max(P.sst_smem_bytes, b + 64);
+      if (P.sst_smem_bytes > SST_SMEM_LIMIT)
+      {
+        return fail(err, B200_ERR_ARG, "internal: a sparse subtree exceeds the shared memory of one CTA");
+      }
     }
   }
-  for (std::vector<int>* v : {&P.sst_colptr, &P.sst_rows, &P.sst_lvl_ptr, &P.sst_lvl_col})
+  pad8(P.sst_blob);
+  P.sst_blob.resize(P.sst_blob.size() + 8, 0);
+  // launch order: generation by generation (a subtree after its children); P.sst is in supernode order, which already
+  // puts children first, but one launch covers one generation
   {
-    v->resize(((v->size() + 7) & ~(size_t)7) + 8, 0); // the staging reads whole 16-byte pieces
+    std::vector<int> ord(P.sst.size());
+    std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return P.sst[(size_t)x].gen < P.sst[(size_t)y].gen; });
+    std::vector<SstMeta> sorted;
+    sorted.reserve(P.sst.size());
+    for (int q : ord)
+    {
+      sst_index[P.sst[(size_t)q].sn] = (int)sorted.size();
+      sorted.push_back(P.sst[(size_t)q]);
+    }
+    P.sst.swap(sorted);
+    P.sst_gen_ptr.assign(1, 0);
+    for (size_t q = 0; q < P.sst.size(); ++q)
+    {
+      while ((int)P.sst_gen_ptr.size() - 1 < P.sst[q].gen)
+      {
+        P.sst_gen_ptr.push_back((int)q);
+      }
+    }
+    P.sst_gen_ptr.push_back((int)P.sst.size());
+    if (P.sst.empty())
+    {
+      P.sst_gen_ptr.assign(1, 0);
+    }
   }
   tick("sparse subtrees");
   // ---- storage offsets, levels, statistics ---------------------------------------------------------
@@ -2055,7 +2230,8 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   // update-matrix workspace: U_T lives from stage base[T] to stage base[parent] (inclusive)
   P.Uoff.assign(ns, -1);
   {
-    std::vector<std::vector<int>> alloc_at(nstages + 1), free_at(nstages + 2);
+    const int alloc_stages = std::max(nstages, 1); // update blocks of sparse subtrees exist even without a single dense stage
+    std::vector<std::vector<int>> alloc_at(alloc_stages + 1), free_at(alloc_stages + 2);
     for (int T = 0; T < ns; ++T)
     {
       i64 r = P.Rptr[T + 1] - P.Rptr[T];
@@ -2065,7 +2241,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       }
       alloc_at[P.sn_base[T]].push_back(T);
       int p = P.sn_parent[T];
-      free_at[(p >= 0 ? P.sn_base[p] : nstages - 1) + 1].push_back(T);
+      free_at[(p >= 0 ? P.sn_base[p] : alloc_stages - 1) + 1].push_back(T);
     }
     std::map<i64, i64> freelist; // offset -> size
     i64 top = 0;
@@ -2094,7 +2270,7 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       }
     };
     std::vector<i64> usz(ns, 0);
-    for (int s = 0; s < nstages; ++s)
+    for (int s = 0; s < alloc_stages; ++s)
     {
       for (int T : free_at[s])
       {
@@ -2136,6 +2312,10 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   for (SstMeta& M : P.sst)
   {
     M.Uoff = M.r > 0 ? P.Uoff[M.sn] : 0;
+  }
+  for (size_t e = 0; e < P.sst_ea_src.size(); ++e)
+  {
+    P.sst_ea_src[e] += P.Uoff[(size_t)sst_ea_child[e]];
   }
   // tasks
   {

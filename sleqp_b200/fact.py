@@ -48,12 +48,12 @@ PLAN_FIELDS = {
         "e_of_k r_of_k k_of_e k_of_r dE_src Acsc_ptr Acsc_row Acsc_src Acsr_ptr Acsr_col Acsr_src "
         "Gsym_ptr Gsym_col Gsym_src perm pinv parent colcount sn_first sn_of_col sn_parent sn_level "
         "Ridx rel child_ptr child_idx Sgsrc Sterm_a Sterm_b Sterm_d sn_base sn_nt zero_sn lvl_ptr lvl_sn "
-        "inv_phase_ptr Ksrc sst_colptr sst_rows sst_lvl_ptr sst_lvl_col sn_sparse"
+        "inv_phase_ptr Ksrc sst_colptr sst_rows sst_blob sst_ea_dst sst_gen_ptr sn_sparse"
     ).split()},
-    **{k: np.int64 for k in "Rptr Lptr Wptr Sdest Sterm_ptr Uoff Tptr".split()},
+    **{k: np.int64 for k in "Rptr Lptr Wptr Sdest Sterm_ptr Uoff Tptr sst_ea_src".split()},
 }
 PLAN_STRUCTS = {"stages": 10, "ea_tasks": 2, "pan_tasks": 4, "upd_tasks": 7, "inv_tasks": 6,
-                "ffl_tasks": 16, "bfl_tasks": 16, "tr_tasks": 3, "sst": 16}  # int32 columns
+                "ffl_tasks": 16, "bfl_tasks": 16, "tr_tasks": 3, "sst": 24}  # int32 columns
 
 
 class Symbolic:
