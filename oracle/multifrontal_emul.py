@@ -44,14 +44,14 @@ class Emulated:
         ns = int(p["n_supernodes"])
         self.is_sst = np.zeros(ns, dtype=bool)
         self.sst = []
-        raw = np.asarray(p.get("sst", np.zeros((0, 24), dtype=np.int32))).reshape(-1, 24)
+        raw = np.asarray(p.get("sst", np.zeros((0, 26), dtype=np.int32))).reshape(-1, 26)
         blob_all = np.asarray(p.get("sst_blob", np.zeros(0, dtype=np.int32)), dtype=np.int64)
         last_gen = 0
         for rec in raw:
             lptr = int(np.array(rec[0:2], dtype=np.int32).view(np.int64)[0])
             uoff = int(np.array(rec[2:4], dtype=np.int32).view(np.int64)[0])
             (sn, first, k, r, rptr, signal, blob, blob_len16, nslev, nseg, nnz, gen, o_segstart, o_seglen, o_colptr, o_rows, ea_begin, ea_end,
-             col_ptr, row_ptr) = (int(v) for v in rec[4:24])
+             col_ptr, row_ptr, nchild, parent_sst) = (int(v) for v in rec[4:26])
             assert blob % 8 == 0 and gen >= last_gen
             last_gen = gen
             b = blob_all[blob : blob + 8 * blob_len16]
@@ -70,11 +70,11 @@ class Emulated:
                 for q in range(slvl[lev], slvl[lev + 1]):
                     seg_lev[segstart[q] : segstart[q] + seglen[q]] = lev
                     seg_end[segstart[q] : segstart[q] + seglen[q]] = segstart[q] + seglen[q]
-            if signal >= 0:
-                assert p["sn_parent"][sn] == signal and p["sn_sparse"][signal] == 0
+            assert p["sn_parent"][sn] == signal and nchild == p["child_ptr"][sn + 1] - p["child_ptr"][sn]
+            assert parent_sst == (signal if signal >= 0 and p["sn_sparse"][signal] else -1)
             self.sst.append(dict(Lptr=lptr, Uoff=uoff, sn=sn, first=first, k=k, r=r, Rptr=rptr, signal=signal, colptr=colptr, rows=rows,
                                  slvl=slvl, segstart=segstart, seglen=seglen, nslev=nslev, nnz=nnz, gen=gen, seg_lev=seg_lev, seg_end=seg_end,
-                                 ea=(ea_begin, ea_end)))
+                                 ea=(ea_begin, ea_end), nchild=nchild, parent_sst=parent_sst))
             self.is_sst[sn] = True
             assert p["sn_sparse"][sn] == 1
 
@@ -305,6 +305,7 @@ class Emulated:
         x = np.zeros(self.m)
         cnt = np.zeros(ns, dtype=np.int64)
         for M in self.sst:  # k_sst_forward runs before the dataflow kernel and signals the parents
+            assert cnt[M["sn"]] == M["nchild"], "sparse subtree swept before its children"
             self._sst_forward(M, yacc, yf)
             if M["signal"] >= 0:
                 cnt[M["signal"]] += 1
@@ -338,8 +339,11 @@ class Emulated:
                 x[first + j] += Mr[lptr + ii * k + j] @ v
             if signal_idx >= 0:
                 cnt[signal_idx] += 1
+        swept = set()
         for M in reversed(self.sst):  # k_sst_backward: after the dataflow kernel, generations from the top down
+            assert M["parent_sst"] < 0 or M["parent_sst"] in swept, "sparse subtree swept before its parent"
             self._sst_backward(M, yf, x)
+            swept.add(M["sn"])
         assert np.all(np.isfinite(x))
         return x
 

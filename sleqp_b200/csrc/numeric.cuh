@@ -59,6 +59,13 @@ struct NumericOverlap
 // sparse subtrees (sst.cu): factorization before the first stage of the dense schedule, forward sweep before the
 // forward dataflow kernel (signals the parents' counters), backward sweep after the backward dataflow kernel
 void configure_sst_kernels(int device);
+// the two ticket counters of the sparse-subtree sweeps inside SolveBuffers::flow (after the counters and tickets of
+// the dataflow sweeps; zeroed by k_pre with the rest)
+inline int
+sst_ticket_offset(int nsuper)
+{
+  return 2 * nsuper + 2 * (FLOW_THREADS / 32) * 32;
+}
 void enqueue_sst_factor(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream, LaunchCounter& lc);
 void enqueue_sst_forward(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc);
 void enqueue_sst_backward(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc);

@@ -59,7 +59,7 @@ struct SstMeta
   int sn;          // supernode index
   int first, k, r;
   int Rptr;        // update rows in Ridx
-  int signal;      // dense parent supernode whose forward counter gets one signal when the subtree is swept, -1: none
+  int signal;      // parent supernode (dense or sparse): its forward counter gets one signal when the subtree is swept, -1: root
   int blob;        // offset of the index blob in sst_blob (16-bit units, multiple of 8)
   int blob_len16;  // its length in 16-byte pieces
   int nslev;       // levels of segments
@@ -69,8 +69,10 @@ struct SstMeta
   int o_segstart, o_seglen, o_colptr, o_rows; // parts of the blob after the level pointers (16-bit units from blob)
   int ea_begin, ea_end;                        // assembly of the children's update blocks: entries of sst_ea_src / _dst
   int col_ptr, row_ptr;                        // host copies: offsets into Plan::sst_colptr / sst_rows (32-bit)
+  int nchild;                                  // child subtrees: signals the forward sweep waits for
+  int parent_sst;                              // parent supernode if that is a sparse subtree (the backward sweep waits for its flag), else -1
 };
-static_assert(sizeof(SstMeta) == 96, "SstMeta layout");
+static_assert(sizeof(SstMeta) == 104, "SstMeta layout");
 
 // kinds of update tasks
 enum

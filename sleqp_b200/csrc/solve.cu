@@ -319,6 +319,7 @@ wait_counter(const int* cnt, int need, unsigned far_sleep, int near, unsigned pe
 // exhausted helps with the others.
 constexpr int FLOW_SHARDS       = FLOW_THREADS / 32;
 constexpr int FLOW_TICKET_PITCH = 32; // ints between two counters
+static_assert(FLOW_SHARDS * FLOW_TICKET_PITCH == (FLOW_THREADS / 32) * 32, "sst_ticket_offset (numeric.cuh) assumes this layout");
 
 struct FlowSched
 {
@@ -974,7 +975,7 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
   if (P.m > 0)
   {
     const int ns    = P.nsuper;
-    const int nflow = 2 * ns + 2 * FLOW_SHARDS * FLOW_TICKET_PITCH;
+    const int nflow = sst_ticket_offset(ns) + 8; // counters, tickets of the dataflow sweeps, tickets of the sparse subtrees
     k_pre<<<nblocks(std::max(P.m, nflow), T), T, 0, stream>>>(P.m, dp.k_of_r.p, dp.pinv.p, dp.Acsr_ptr.p, dp.Acsr_k.p, nb.Acsr_sval, in, sb.y, nflow, sb.yf, sb.x,
                                                              sb.flow);
     lc.tick();

@@ -92,6 +92,48 @@ sst_stage(double* smem, const SstMeta& M, const u16* __restrict__ blob_all, cons
   return S;
 }
 
+__device__ __forceinline__ int
+ld_acquire(const int* p)
+{
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// thread 0 polls a counter until it reaches `need`; the barrier hands the acquired view to the whole CTA (the data
+// behind the counter is then read with L2 loads, __ldcg)
+__device__ __forceinline__ void
+wait_counter(const int* c, int need)
+{
+  if (threadIdx.x == 0)
+  {
+    while (ld_acquire(c) < need)
+    {
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+}
+
+// Order of work inside a launch that holds several generations: a CTA that has to wait only ever waits for CTAs with
+// lower tickets, which are running already -- no assumption on the order the hardware dispatches blocks in, no bound
+// on the grid. With one generation (ticket == nullptr) nobody waits and the block index will do.
+__device__ __forceinline__ int
+take_ticket(int* ticket)
+{
+  if (ticket == nullptr)
+  {
+    return blockIdx.x;
+  }
+  __shared__ int t;
+  if (threadIdx.x == 0)
+  {
+    t = atomicAdd(ticket, 1);
+  }
+  __syncthreads();
+  return t;
+}
+
 __device__ __forceinline__ void
 smem_add(double* p, double v)
 {
@@ -234,20 +276,27 @@ k_sst_forward(const SstMeta* __restrict__ metas,
               const double* __restrict__ Dinv,
               double* __restrict__ yacc,
               double* __restrict__ yf,
-              int* __restrict__ cnt)
+              int* __restrict__ cnt,
+              int* __restrict__ ticket)
 {
   extern __shared__ double sst_smem[];
-  const SstMeta M = metas[blockIdx.x];
+  const SstMeta M = metas[take_ticket(ticket)]; // children (earlier generations) get the lower tickets
   const int k = M.k, r = M.r;
   const SstShared S = sst_stage(sst_smem, M, blob_all, L + M.Lptr, k + r);
   double* x         = S.vec;
+  if (M.nchild > 0)
+  {
+    // child subtrees of earlier generations run in this very launch under lower tickets, i.e. they are already
+    // running: the structure is staged, now wait for their shares of the right-hand side
+    wait_counter(cnt + M.sn, M.nchild);
+  }
   {
     double t[(SST_MAX_COLS + SST_MAX_TAIL + SST_THREADS - 1) / SST_THREADS]; // all loads of the right-hand side first
 #pragma unroll
     for (int u = 0; u < (int)(sizeof(t) / sizeof(double)); ++u)
     {
       const int q = u * SST_THREADS + threadIdx.x;
-      t[u]        = q < k ? yacc[M.first + q] : 0.0;
+      t[u]        = q < k ? __ldcg(yacc + M.first + q) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < (int)(sizeof(t) / sizeof(double)); ++u)
@@ -312,30 +361,40 @@ k_sst_backward(const SstMeta* __restrict__ metas,
                const int* __restrict__ Ridx,
                const double* __restrict__ L,
                const double* __restrict__ yf,
-               double* __restrict__ xg)
+               double* __restrict__ xg,
+               int* __restrict__ done,
+               int* __restrict__ ticket)
 {
   extern __shared__ double sst_smem[];
-  const SstMeta M = metas[blockIdx.x];
+  const SstMeta M = metas[gridDim.x - 1 - take_ticket(ticket)]; // parents (later generations) get the lower tickets
   const int k = M.k, r = M.r;
   const SstShared S = sst_stage(sst_smem, M, blob_all, L + M.Lptr, k + r);
   double* x         = S.vec;
   {
-    double t[(SST_MAX_COLS + SST_MAX_TAIL + SST_THREADS - 1) / SST_THREADS];
+    double t[(SST_MAX_COLS + SST_THREADS - 1) / SST_THREADS];
 #pragma unroll
     for (int u = 0; u < (int)(sizeof(t) / sizeof(double)); ++u)
     {
       const int q = u * SST_THREADS + threadIdx.x;
-      t[u]        = q < k ? yf[M.first + q] : (q < k + r ? xg[Ridx[M.Rptr + q - k]] : 0.0);
+      t[u]        = q < k ? yf[M.first + q] : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < (int)(sizeof(t) / sizeof(double)); ++u)
     {
       const int q = u * SST_THREADS + threadIdx.x;
-      if (q < k + r)
+      if (q < k)
       {
         x[q] = t[u];
       }
     }
+  }
+  if (M.parent_sst >= 0)
+  {
+    wait_counter(done + M.parent_sst, 1); // the parent subtree runs in this very launch (lower ticket: already running)
+  }
+  for (int q = threadIdx.x; q < r; q += blockDim.x)
+  {
+    x[k + q] = __ldcg(xg + Ridx[M.Rptr + q]);
   }
   __syncthreads();
   for (int lev = M.nslev - 1; lev >= 0; --lev)
@@ -358,6 +417,15 @@ k_sst_backward(const SstMeta* __restrict__ metas,
   for (int q = threadIdx.x; q < k; q += blockDim.x)
   {
     xg[M.first + q] = x[q];
+  }
+  if (M.nchild > 0)
+  {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      atomicAdd(done + M.sn, 1);
+    }
   }
 }
 
@@ -394,36 +462,34 @@ enqueue_sst_factor(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t str
   }
 }
 
+// One launch per sweep for all generations: the waits inside the kernels order parents and children
 void
 enqueue_sst_forward(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc)
 {
-  const std::vector<int>& gp = dp.plan->sst_gen_ptr;
-  for (size_t g = 0; g + 1 < gp.size(); ++g)
+  const int n = (int)dp.plan->sst.size();
+  if (n == 0)
   {
-    if (gp[g + 1] == gp[g])
-    {
-      continue;
-    }
-    k_sst_forward<<<gp[g + 1] - gp[g], SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p + gp[g], dp.sst_blob.p, dp.Ridx.p, nb.L, nb.Dinv, sb.y, sb.yf, sb.flow);
-    lc.tick();
-    B200_CUDA(cudaGetLastError());
+    return;
   }
+  int* const ticket = dp.plan->sst_gen_ptr.size() > 2 ? sb.flow + sst_ticket_offset(dp.plan->nsuper) : nullptr;
+  k_sst_forward<<<n, SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p, dp.sst_blob.p, dp.Ridx.p, nb.L, nb.Dinv, sb.y, sb.yf, sb.flow, ticket);
+  lc.tick();
+  B200_CUDA(cudaGetLastError());
 }
 
 void
 enqueue_sst_backward(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, cudaStream_t stream, LaunchCounter& lc)
 {
-  const std::vector<int>& gp = dp.plan->sst_gen_ptr;
-  for (size_t g = gp.size() - 1; g-- > 0;) // parents first
+  const int n = (int)dp.plan->sst.size();
+  if (n == 0)
   {
-    if (gp[g + 1] == gp[g])
-    {
-      continue;
-    }
-    k_sst_backward<<<gp[g + 1] - gp[g], SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p + gp[g], dp.sst_blob.p, dp.Ridx.p, nb.L, sb.yf, sb.x);
-    lc.tick();
-    B200_CUDA(cudaGetLastError());
+    return;
   }
+  int* const ticket = dp.plan->sst_gen_ptr.size() > 2 ? sb.flow + sst_ticket_offset(dp.plan->nsuper) + 4 : nullptr;
+  int* const done   = sb.flow + dp.plan->nsuper; // the backward counters of the sweeps; those of sparse subtrees are free
+  k_sst_backward<<<n, SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p, dp.sst_blob.p, dp.Ridx.p, nb.L, sb.yf, sb.x, done, ticket);
+  lc.tick();
+  B200_CUDA(cudaGetLastError());
 }
 
 } // namespace b200

@@ -1673,7 +1673,9 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
     M.r       = r;
     M.Rptr    = (int)P.Rptr[T];
     M.gen     = sst_final[f];
-    M.signal  = (P.sn_parent[T] >= 0 && !P.sn_sparse[P.sn_parent[T]]) ? P.sn_parent[T] : -1;
+    M.signal     = P.sn_parent[T];
+    M.parent_sst = (P.sn_parent[T] >= 0 && P.sn_sparse[P.sn_parent[T]]) ? P.sn_parent[T] : -1;
+    M.nchild     = P.child_ptr[T + 1] - P.child_ptr[T];
     // front-local index of a row (new labels): a column of the subtree or one of its update rows
     auto local = [&](int i) -> int {
       if (i <= l)
