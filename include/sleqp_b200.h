@@ -184,6 +184,10 @@ B200_API int b200_fact_pivots(b200_fact* handle, double* d_out);
 B200_API void* b200_fact_stream(b200_fact* handle);
 /* CUDA device ordinal the handle lives on (-1 for a null handle). */
 B200_API int b200_fact_device(b200_fact* handle);
+/* Device buffers the solve graph of the handle reads its right-hand side from and leaves its solution in (N doubles
+ * each, valid after a successful set_matrix / set_kkt until the next one). b200_fact_solve_device called with exactly
+ * these pointers skips its two device copies: a device-resident caller (the projected CG) keeps its residual there. */
+B200_API int b200_fact_device_buffers(b200_fact* handle, double** rhs, double** solution);
 
 B200_API int b200_fact_free(b200_fact** handle);
 

@@ -56,7 +56,7 @@ _lib = None
 SYMBOLS = [
     "b200_fact_create", "b200_fact_set_matrix", "b200_fact_set_kkt", "b200_fact_solve", "b200_fact_solve_offset", "b200_fact_solution",
     "b200_fact_solution_ptr", "b200_fact_solution_sparse", "b200_fact_solve_device", "b200_fact_refactor_device", "b200_fact_profile_solve", "b200_fact_profile_numeric", "b200_fact_rcond", "b200_fact_stats",
-    "b200_fact_structure", "b200_fact_pivots", "b200_fact_stream", "b200_fact_device", "b200_fact_free", "b200_last_error",
+    "b200_fact_structure", "b200_fact_pivots", "b200_fact_stream", "b200_fact_device", "b200_fact_device_buffers", "b200_fact_free", "b200_last_error",
     "b200_symbolic_analyze", "b200_symbolic_analyze_kkt", "b200_symbolic_stats", "b200_symbolic_structure", "b200_symbolic_export",
     "b200_symbolic_free", "b200_mat_create", "b200_mat_set", "b200_mat_mult_vec", "b200_mat_mult_vec_trans", "b200_mat_mult_vec_trans_sparse",
     "b200_mat_mult_vec_device", "b200_mat_mult_vec_device_if", "b200_mat_mult_vec_trans_device", "b200_mat_stream", "b200_mat_set_stream", "b200_mat_free",
@@ -95,6 +95,7 @@ def lib():
     L.b200_fact_stream.argtypes = [vp]
     L.b200_fact_stream.restype = vp
     L.b200_fact_device.argtypes = [vp]
+    L.b200_fact_device_buffers.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]
     L.b200_fact_free.argtypes = [C.POINTER(vp)]
     L.b200_symbolic_analyze.argtypes = [C.POINTER(vp), C.c_int, C.c_int, ip, ip, dp, C.c_int]
     L.b200_symbolic_analyze_kkt.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, ip, ip, dp, ip, ip, C.c_int]

@@ -83,39 +83,159 @@ k_cg_beta(double* S)
   S[9]  = S[6];
 }
 
-// ---- device-controlled loop (Hessian on the device): the host enqueues iterations ahead, the exit tests run in
-// one-thread kernels and every kernel of the CG checks the exit flag first, so that the state of the exit iteration
-// (z, d, B d) survives whatever has been enqueued behind it.
+// ---- device-controlled loop (Hessian on the device): the host enqueues iterations ahead, the exit tests run in the
+// last block of the reductions and every kernel of the CG checks the exit flag first, so that the state of the exit
+// iteration (z, d, B d) survives whatever has been enqueued behind it.
 // Scalars S: [0..2] d.Bd, d.d, Bd.Bd   [3..5] z+.d, z+.z+, d.d   [6..8] r.g, r.r, g.g   [9] current r.g   [10] alpha
 // [11] beta   [12] |z|^2   [13] min Rayleigh   [14] max Rayleigh   [15] iterations completed
 // Exit record E (ints): [0] flag (0 running, 1 + B200_CG_* otherwise)   [1] iteration of the exit
 // Exit scalars X: [0] d.Bd   [1] d.d   [2] |z|^2 at the exit
-__global__ void
-k_cgd_dot3(int n, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out, const int* __restrict__ flag)
+constexpr int CGD_BLOCKS = 592; // 4 per SM
+enum
 {
-  if (*flag)
+  CGD_CURVATURE, // (x, y) = (d, B d): Rayleigh bounds (:150-173), negative-curvature exit (:349), alpha (:405)
+  CGD_RADIUS,    // z+ = z + alpha d written, (x, y) = (z+, d): boundary exit (:419)
+  CGD_TAIL       // (x, y) = (r, g): beta (:467-469), |z|^2 of the accepted iterate, iteration count, and the
+                 // convergence test the reference makes at the top of the next pass (:318-327)
+};
+
+// (x.y, x.x, y.y) -> S[3 * MODE ...] and the scalar logic that follows, in one launch: every block leaves its partial
+// sums in `part`, the block that arrives last adds them up in a fixed order (the result does not depend on which block
+// that is, nor on the order of arrival: bit-reproducible, unlike atomics on the three sums) and runs the exit test.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_cgd_reduce(int n,
+             const double* __restrict__ x,
+             const double* __restrict__ y,
+             double* __restrict__ xout,
+             double* __restrict__ S,
+             int* __restrict__ E,
+             double* __restrict__ X,
+             double* __restrict__ part,
+             unsigned* __restrict__ arrived,
+             double param, // CGD_RADIUS: radius^2   CGD_TAIL: tol^2, negative = no convergence test (iteration cap behind)
+             const int nblocks)
+{
+  if (*E)
   {
     return;
   }
+  __shared__ double red[8][3];
+  __shared__ bool last;
   double xy = 0.0, xx = 0.0, yy = 0.0;
+  const double alpha = MODE == CGD_RADIUS ? S[10] : 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
   {
-    const double a = x[i], b = y[i];
+    double a       = x[i];
+    const double b = y[i];
+    if (MODE == CGD_RADIUS)
+    {
+      a += alpha * b;
+      xout[i] = a;
+    }
     xy += a * b;
     xx += a * a;
     yy += b * b;
   }
-  for (int o = 16; o > 0; o >>= 1)
+  auto block_sum = [&]() { // fixed shape: butterfly inside the warp, the eight warps in order
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      xy += __shfl_xor_sync(0xffffffffu, xy, o);
+      xx += __shfl_xor_sync(0xffffffffu, xx, o);
+      yy += __shfl_xor_sync(0xffffffffu, yy, o);
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+      red[threadIdx.x >> 5][0] = xy;
+      red[threadIdx.x >> 5][1] = xx;
+      red[threadIdx.x >> 5][2] = yy;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      xy = xx = yy = 0.0;
+      for (int w = 0; w < 8; ++w)
+      {
+        xy += red[w][0];
+        xx += red[w][1];
+        yy += red[w][2];
+      }
+    }
+  };
+  block_sum();
+  if (threadIdx.x == 0)
   {
-    xy += __shfl_xor_sync(0xffffffffu, xy, o);
-    xx += __shfl_xor_sync(0xffffffffu, xx, o);
-    yy += __shfl_xor_sync(0xffffffffu, yy, o);
+    part[3 * blockIdx.x + 0] = xy;
+    part[3 * blockIdx.x + 1] = xx;
+    part[3 * blockIdx.x + 2] = yy;
+    __threadfence();
+    last = atomicAdd(arrived, 1u) == (unsigned)nblocks - 1;
   }
-  if ((threadIdx.x & 31) == 0)
+  __syncthreads();
+  if (!last)
   {
-    atomicAdd(out + 0, xy);
-    atomicAdd(out + 1, xx);
-    atomicAdd(out + 2, yy);
+    return;
+  }
+  __threadfence();
+  xy = xx = yy = 0.0;
+  for (int q = threadIdx.x; q < nblocks; q += blockDim.x)
+  {
+    xy += __ldcg(part + 3 * q + 0);
+    xx += __ldcg(part + 3 * q + 1);
+    yy += __ldcg(part + 3 * q + 2);
+  }
+  __syncthreads(); // red is reused
+  block_sum();
+  if (threadIdx.x != 0)
+  {
+    return;
+  }
+  *arrived        = 0;
+  S[3 * MODE + 0] = xy;
+  S[3 * MODE + 1] = xx;
+  S[3 * MODE + 2] = yy;
+  const int iteration = (int)S[15];
+  if (MODE == CGD_CURVATURE)
+  {
+    const double dBd = xy, dd = xx;
+    if (dd != 0.0)
+    {
+      S[13] = fmin(S[13], dBd / dd);
+      S[14] = fmax(S[14], dBd / dd);
+    }
+    if (dBd <= 0.0)
+    {
+      E[0] = 1 + B200_CG_NEG_CURVATURE;
+      E[1] = iteration;
+      X[0] = dBd;
+      X[1] = dd;
+      X[2] = S[12];
+      return;
+    }
+    S[10] = S[9] / dBd;
+  }
+  if (MODE == CGD_RADIUS)
+  {
+    if (xx >= param)
+    {
+      E[0] = 1 + B200_CG_BOUNDARY;
+      E[1] = iteration;
+      X[0] = S[0];
+      X[1] = S[1];
+      X[2] = S[12];
+    }
+  }
+  if (MODE == CGD_TAIL)
+  {
+    S[11] = xy / S[9];
+    S[9]  = xy;
+    S[12] = S[4];
+    S[15] += 1.0;
+    if (param >= 0.0 && fabs(xy) < param) // what the reference tests at the top of the next pass
+    {
+      E[0] = 1 + B200_CG_INTERIOR;
+      E[1] = iteration + 1;
+    }
   }
 }
 
@@ -133,84 +253,6 @@ k_cgd_axpby(int n, double a, const double* x, const double* __restrict__ b, cons
   }
 }
 
-// loop top (steihaug_solver.c:318-327): interior exit when |r.g| < tol^2; otherwise the dot-product slots are cleared
-__global__ void
-k_cgd_top(double* S, int* E, double tol_sq, int iteration)
-{
-  if (E[0])
-  {
-    return;
-  }
-  if (fabs(S[9]) < tol_sq)
-  {
-    E[0] = 1 + B200_CG_INTERIOR;
-    E[1] = iteration;
-    return;
-  }
-  for (int q = 0; q < 9; ++q)
-  {
-    S[q] = 0.0;
-  }
-}
-
-// after d.Bd: Rayleigh bounds (:150-173), negative curvature exit (:349), alpha (:405)
-__global__ void
-k_cgd_curvature(double* S, int* E, double* X, int iteration)
-{
-  if (E[0])
-  {
-    return;
-  }
-  const double dBd = S[0], dd = S[1];
-  if (dd != 0.0)
-  {
-    S[13] = fmin(S[13], dBd / dd);
-    S[14] = fmax(S[14], dBd / dd);
-  }
-  if (dBd <= 0.0)
-  {
-    E[0] = 1 + B200_CG_NEG_CURVATURE;
-    E[1] = iteration;
-    X[0] = dBd;
-    X[1] = dd;
-    X[2] = S[12];
-    return;
-  }
-  S[10] = S[9] / dBd;
-}
-
-// after |z + alpha d|^2: boundary exit (:419)
-__global__ void
-k_cgd_radius(double* S, int* E, double* X, double radius_sq, int iteration)
-{
-  if (E[0])
-  {
-    return;
-  }
-  if (S[4] >= radius_sq)
-  {
-    E[0] = 1 + B200_CG_BOUNDARY;
-    E[1] = iteration;
-    X[0] = S[0];
-    X[1] = S[1];
-    X[2] = S[12];
-  }
-}
-
-// after the new r.g: beta (:467-469), |z|^2 of the accepted iterate, iteration count
-__global__ void
-k_cgd_tail(double* S, const int* E)
-{
-  if (E[0])
-  {
-    return;
-  }
-  S[11] = S[6] / S[9];
-  S[9]  = S[6];
-  S[12] = S[4];
-  S[15] += 1.0;
-}
-
 } // namespace b200
 
 struct b200_cg
@@ -223,8 +265,10 @@ struct b200_cg
   int device      = 0;
   cudaStream_t stream = nullptr;
   int n = 0, N = 0;
-  DevBuf<double> z, znext, rfull, gfull, d, dnext, Bd, scal;
+  DevBuf<double> z, znext, d, dnext, Bd, scal;
   DevBuf<int> g_idx, exit_rec;
+  DevBuf<double> part;       // partial sums of the reductions of the device-controlled loop
+  DevBuf<unsigned> arrived;  // ... and their arrival counter (zero between launches)
   PinnedBuf<int> h_exit;
   DevBuf<double> g_val;
   PinnedBuf<double> h_scal, h_step, h_val;
@@ -394,12 +438,20 @@ b200_cg_solve_ex(b200_cg* C,
     C->d.reserve((size_t)n);
     C->dnext.reserve((size_t)n);
     C->Bd.reserve((size_t)n);
-    C->rfull.reserve((size_t)N); // [r; 0]: the right-hand side of the projection, tail stays zero
-    C->gfull.reserve((size_t)N); // K^-1 [r; 0]: its first n entries are g = P r
+    // [r; 0], the right-hand side of the projection (tail stays zero), and K^-1 [r; 0], whose first n entries are
+    // g = P r, live in the buffers the solve graph of the factorization works on: no copies around the projection
+    double *rfull = nullptr, *gfull = nullptr;
+    {
+      int brc = b200_fact_device_buffers(C->fact, &rfull, &gfull);
+      if (brc != B200_OK)
+      {
+        return brc;
+      }
+    }
     C->h_step.reserve((size_t)n);
     B200_CUDA(cudaStreamSynchronize(s));
     B200_CUDA(cudaMemsetAsync(C->z.p, 0, sizeof(double) * (size_t)n, s));
-    B200_CUDA(cudaMemsetAsync(C->rfull.p, 0, sizeof(double) * (size_t)N, s));
+    B200_CUDA(cudaMemsetAsync(rfull, 0, sizeof(double) * (size_t)N, s));
     // r0 = gradient (sparse host vector -> dense device vector)
     if (nnz_g > 0)
     {
@@ -412,11 +464,11 @@ b200_cg_solve_ex(b200_cg* C,
       B200_CUDA(cudaMemcpyAsync(C->g_val.p, C->h_val.p, sizeof(double) * (size_t)nnz_g, cudaMemcpyHostToDevice, s));
       B200_CUDA(cudaMemcpyAsync(C->g_idx.p, C->h_idx.p, sizeof(int) * (size_t)nnz_g, cudaMemcpyHostToDevice, s));
       LaunchCounter lc;
-      enqueue_scatter_rhs(C->rfull.p, N, nnz_g, C->g_idx.p, 0, C->g_val.p, s, lc);
+      enqueue_scatter_rhs(rfull, N, nnz_g, C->g_idx.p, 0, C->g_val.p, s, lc);
     }
-    double* r = C->rfull.p;
-    double* g = C->gfull.p;
-    auto project = [&]() -> int { return b200_fact_solve_device(C->fact, C->rfull.p, C->gfull.p); };
+    double* r = rfull;
+    double* g = gfull;
+    auto project = [&]() -> int { return b200_fact_solve_device(C->fact, rfull, gfull); };
     // out = H v: a device SpMV, or -- matrix-free Hessians -- one round trip through the host callback
     auto hess_prod = [&](const double* v_dev, double* out_dev) -> int {
       if (C->hess)
@@ -526,35 +578,45 @@ b200_cg_solve_ex(b200_cg* C,
         B200_CUDA(cudaMemcpyAsync(S, C->h_scal.p, sizeof(init), cudaMemcpyHostToDevice, s));
         B200_CUDA(cudaMemsetAsync(E, 0, 4 * sizeof(int), s));
       }
+      if (max_iter != 0 && std::fabs(r_dot_g) < tol_sq)
+      {
+        return finish(C->z.p, 0, B200_CG_INTERIOR); // the test at the top of the first pass (:318-327), known on the host
+      }
       double* zb[2] = {C->z.p, C->znext.p};
       double* db[2] = {C->d.p, C->dnext.p};
-      const unsigned gb = nb(n), gd = std::min(nb(n), 592u);
+      const unsigned gb = nb(n);
+      if (C->part.cap < (size_t)(3 * CGD_BLOCKS))
+      {
+        C->part.reserve(3 * CGD_BLOCKS);
+        C->arrived.reserve(2);
+        B200_CUDA(cudaMemsetAsync(C->arrived.p, 0, 2 * sizeof(unsigned), s));
+      }
+      double* const part      = C->part.p;
+      unsigned* const arrived = C->arrived.p;
+      const int gr            = (int)std::min(nb(n), (unsigned)CGD_BLOCKS);
       auto enqueue_iteration = [&](int it) -> int {
         double* z_cur = zb[it & 1];
         double* z_new = zb[(it + 1) & 1];
         double* d_cur = db[it & 1];
         double* d_new = db[(it + 1) & 1];
-        k_cgd_top<<<1, 1, 0, s>>>(S, E, tol_sq, it);
         int hrc = b200_mat_mult_vec_device_if(C->hess, d_cur, C->Bd.p, E); //       (:339)
         if (hrc != B200_OK)
         {
           return hrc;
         }
-        k_cgd_dot3<<<gd, 256, 0, s>>>(n, d_cur, C->Bd.p, S, E);
-        k_cgd_curvature<<<1, 1, 0, s>>>(S, E, X, it);
-        k_cgd_axpby<<<gb, 256, 0, s>>>(n, 1.0, z_cur, S + 10, d_cur, z_new, E); // z+ = z + alpha d
-        k_cgd_dot3<<<gd, 256, 0, s>>>(n, z_new, d_cur, S + 3, E);
-        k_cgd_radius<<<1, 1, 0, s>>>(S, E, X, trust_radius * trust_radius, it);
+        k_cgd_reduce<CGD_CURVATURE><<<gr, 256, 0, s>>>(n, d_cur, C->Bd.p, nullptr, S, E, X, part, arrived, 0.0, gr);
+        k_cgd_reduce<CGD_RADIUS><<<gr, 256, 0, s>>>(n, z_cur, d_cur, z_new, S, E, X, part, arrived, trust_radius * trust_radius, gr); // z+ = z + alpha d
         k_cgd_axpby<<<gb, 256, 0, s>>>(n, 1.0, r, S + 10, C->Bd.p, r, E); // r += alpha B d  (:449-456)
         int prc2 = project();                                              // g = P[r]        (:459)
         if (prc2 != B200_OK)
         {
           return prc2;
         }
-        k_cgd_dot3<<<gd, 256, 0, s>>>(n, r, g, S + 6, E);
-        k_cgd_tail<<<1, 1, 0, s>>>(S, E);
+        // the convergence test of the next pass rides on this reduction, unless the iteration cap comes first (:302)
+        const bool cap_next = max_iter >= 0 && it + 1 >= max_iter;
+        k_cgd_reduce<CGD_TAIL><<<gr, 256, 0, s>>>(n, r, g, nullptr, S, E, X, part, arrived, cap_next ? -1.0 : tol_sq, gr);
         k_cgd_axpby<<<gb, 256, 0, s>>>(n, -1.0, g, S + 11, d_cur, d_new, E); // d+ = -g + beta d (:472-479)
-        g_launches.fetch_add(11, std::memory_order_relaxed);
+        g_launches.fetch_add(5, std::memory_order_relaxed);
         return (int)B200_OK;
       };
       int enq = 0;

@@ -1145,14 +1145,36 @@ b200_fact_solve_device(b200_fact* F, const double* d_rhs, double* d_sol)
       return (int)B200_OK;
     }
     B200_CUDA(cudaEventRecord(F->ev_c, F->stream));
-    B200_CUDA(cudaMemcpyAsync(F->rhs.p, d_rhs, sizeof(double) * (size_t)P.N, cudaMemcpyDeviceToDevice, F->stream));
+    if (d_rhs != F->rhs.p)
+    {
+      B200_CUDA(cudaMemcpyAsync(F->rhs.p, d_rhs, sizeof(double) * (size_t)P.N, cudaMemcpyDeviceToDevice, F->stream));
+    }
     launch_solve(F, F->refine);
-    B200_CUDA(cudaMemcpyAsync(d_sol, F->z.p, sizeof(double) * (size_t)P.N, cudaMemcpyDeviceToDevice, F->stream));
+    if (d_sol != F->z.p)
+    {
+      B200_CUDA(cudaMemcpyAsync(d_sol, F->z.p, sizeof(double) * (size_t)P.N, cudaMemcpyDeviceToDevice, F->stream));
+    }
     B200_CUDA(cudaEventRecord(F->ev_d, F->stream));
     F->timed_solve = true;
     F->solved      = true;
     return (int)B200_OK;
   });
+}
+
+int
+b200_fact_device_buffers(b200_fact* F, double** rhs, double** solution)
+{
+  if (!F || !rhs || !solution)
+  {
+    return set_error(B200_ERR_ARG, "null argument");
+  }
+  if (!F->factored)
+  {
+    return set_error(B200_ERR_STATE, "device buffers requested before a successful set_matrix");
+  }
+  *rhs      = F->rhs.p;
+  *solution = F->z.p;
+  return B200_OK;
 }
 
 int
