@@ -95,7 +95,7 @@ def lib():
     L.b200_fact_stream.argtypes = [vp]
     L.b200_fact_stream.restype = vp
     L.b200_fact_device.argtypes = [vp]
-    L.b200_fact_device_buffers.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]
+    L.b200_fact_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.b200_fact_free.argtypes = [C.POINTER(vp)]
     L.b200_symbolic_analyze.argtypes = [C.POINTER(vp), C.c_int, C.c_int, ip, ip, dp, C.c_int]
     L.b200_symbolic_analyze_kkt.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, ip, ip, dp, ip, ip, C.c_int]
