@@ -278,6 +278,13 @@ B200_API int b200_cg_solve(b200_cg* handle, int n, int nnz_g, const int* g_idx, 
 B200_API int b200_cg_solve_ex(b200_cg* handle, int n, int nnz_g, const int* g_idx, const double* g_val, double trust_radius, double rel_tol,
                               int max_iter, double* step_out, int* iterations, int* termination, double* tr_dual, double* min_rayleigh,
                               double* max_rayleigh);
+/* Same solve with the step returned as a sparse vector with the contract of sleqp_vec_set_from_raw (vec.c:72-104):
+ * entries with |v| <= zero_eps dropped, ascending indices; step_idx / step_val hold n entries. When both arrays (and
+ * the gradient's) are page-locked (b200_host_pin) the step is sparsified on the device and DMA'd straight into them,
+ * with no host pass over the n values -- what tr/tr_b200.c does with the arrays of the caller's SleqpVec. */
+B200_API int b200_cg_solve_sparse(b200_cg* handle, int n, int nnz_g, const int* g_idx, const double* g_val, double trust_radius, double rel_tol,
+                                  int max_iter, double zero_eps, int* step_idx, double* step_val, int* step_nnz, int* iterations,
+                                  int* termination, double* tr_dual, double* min_rayleigh, double* max_rayleigh);
 B200_API int b200_cg_free(b200_cg** handle);
 
 /* ---- misc ------------------------------------------------------------------------------ */

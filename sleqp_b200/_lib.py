@@ -60,7 +60,7 @@ SYMBOLS = [
     "b200_symbolic_analyze", "b200_symbolic_analyze_kkt", "b200_symbolic_stats", "b200_symbolic_structure", "b200_symbolic_export",
     "b200_symbolic_free", "b200_mat_create", "b200_mat_set", "b200_mat_mult_vec", "b200_mat_mult_vec_trans", "b200_mat_mult_vec_trans_sparse",
     "b200_mat_mult_vec_device", "b200_mat_mult_vec_device_if", "b200_mat_mult_vec_trans_device", "b200_mat_stream", "b200_mat_set_stream", "b200_mat_free",
-    "b200_cg_create", "b200_cg_set_hess_callback", "b200_cg_solve", "b200_cg_solve_ex", "b200_cg_free", "b200_device_count", "b200_launch_count", "b200_host_pin", "b200_host_unpin",
+    "b200_cg_create", "b200_cg_set_hess_callback", "b200_cg_solve", "b200_cg_solve_ex", "b200_cg_solve_sparse", "b200_cg_free", "b200_device_count", "b200_launch_count", "b200_host_pin", "b200_host_unpin",
 ]
 
 
@@ -118,6 +118,7 @@ def lib():
     L.b200_cg_create.argtypes = [C.POINTER(vp), vp, vp]
     L.b200_cg_solve.argtypes = [vp, C.c_int, C.c_int, ip, dp, C.c_double, C.c_double, C.c_int, dp, ip, ip]
     L.b200_cg_solve_ex.argtypes = [vp, C.c_int, C.c_int, ip, dp, C.c_double, C.c_double, C.c_int, dp, ip, ip, dp, dp, dp]
+    L.b200_cg_solve_sparse.argtypes = [vp, C.c_int, C.c_int, ip, dp, C.c_double, C.c_double, C.c_int, C.c_double, ip, dp, ip, ip, ip, dp, dp, dp]
     L.b200_cg_set_hess_callback.argtypes = [vp, vp, vp]
     L.b200_cg_free.argtypes = [C.POINTER(vp)]
     L.b200_host_pin.argtypes = [vp, C.c_size_t]

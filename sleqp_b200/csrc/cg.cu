@@ -266,7 +266,8 @@ struct b200_cg
   cudaStream_t stream = nullptr;
   int n = 0, N = 0;
   DevBuf<double> z, znext, d, dnext, Bd, scal;
-  DevBuf<int> g_idx, exit_rec;
+  DevBuf<int> g_idx, exit_rec, cp_idx, cp_cnt; // cp_*: compaction of the sparse result
+  DevBuf<double> cp_val;
   DevBuf<double> part;       // partial sums of the reductions of the device-controlled loop
   DevBuf<unsigned> arrived;  // ... and their arrival counter (zero between launches)
   PinnedBuf<int> h_exit;
@@ -386,23 +387,35 @@ b200_cg_solve(b200_cg* C,
   return b200_cg_solve_ex(C, n, nnz_g, g_idx, g_val, trust_radius, rel_tol, max_iter, step_out, iterations, termination, nullptr, nullptr, nullptr);
 }
 
-int
-b200_cg_solve_ex(b200_cg* C,
-                 int n,
-                 int nnz_g,
-                 const int* g_idx,
-                 const double* g_val,
-                 double trust_radius,
-                 double rel_tol,
-                 int max_iter,
-                 double* step_out,
-                 int* iterations,
-                 int* termination,
-                 double* tr_dual,
-                 double* min_rayleigh,
-                 double* max_rayleigh)
+namespace
 {
-  if (!C || !step_out || n <= 0 || nnz_g < 0 || nnz_g > n || (nnz_g > 0 && (!g_idx || !g_val)))
+// sparse result (b200_cg_solve_sparse): entries with |v| > zero_eps, ascending, compacted on the device
+struct SparseStep
+{
+  double zero_eps;
+  int* idx;
+  double* val;
+  int* nnz;
+};
+
+int
+cg_solve_impl(b200_cg* C,
+              int n,
+              int nnz_g,
+              const int* g_idx,
+              const double* g_val,
+              double trust_radius,
+              double rel_tol,
+              int max_iter,
+              double* step_out,
+              const SparseStep* sparse,
+              int* iterations,
+              int* termination,
+              double* tr_dual,
+              double* min_rayleigh,
+              double* max_rayleigh)
+{
+  if (!C || (!step_out && !sparse) || (sparse && (!sparse->idx || !sparse->val || !sparse->nnz)) || n <= 0 || nnz_g < 0 || nnz_g > n || (nnz_g > 0 && (!g_idx || !g_val)))
   {
     return set_error(B200_ERR_ARG, "bad argument");
   }
@@ -449,6 +462,7 @@ b200_cg_solve_ex(b200_cg* C,
       }
     }
     C->h_step.reserve((size_t)n);
+    C->h_exit.reserve(4);
     B200_CUDA(cudaStreamSynchronize(s));
     B200_CUDA(cudaMemsetAsync(C->z.p, 0, sizeof(double) * (size_t)n, s));
     B200_CUDA(cudaMemsetAsync(rfull, 0, sizeof(double) * (size_t)N, s));
@@ -459,10 +473,17 @@ b200_cg_solve_ex(b200_cg* C,
       C->h_idx.reserve((size_t)nnz_g);
       C->g_val.reserve((size_t)nnz_g);
       C->g_idx.reserve((size_t)nnz_g);
-      std::memcpy(C->h_val.p, g_val, sizeof(double) * (size_t)nnz_g);
-      std::memcpy(C->h_idx.p, g_idx, sizeof(int) * (size_t)nnz_g);
-      B200_CUDA(cudaMemcpyAsync(C->g_val.p, C->h_val.p, sizeof(double) * (size_t)nnz_g, cudaMemcpyHostToDevice, s));
-      B200_CUDA(cudaMemcpyAsync(C->g_idx.p, C->h_idx.p, sizeof(int) * (size_t)nnz_g, cudaMemcpyHostToDevice, s));
+      const double* src_val = g_val;
+      const int* src_idx    = g_idx;
+      if (!is_pinned_host(g_val, sizeof(double) * (size_t)nnz_g) || !is_pinned_host(g_idx, sizeof(int) * (size_t)nnz_g)) // page-locked caller arrays are DMA'd as they are
+      {
+        std::memcpy(C->h_val.p, g_val, sizeof(double) * (size_t)nnz_g);
+        std::memcpy(C->h_idx.p, g_idx, sizeof(int) * (size_t)nnz_g);
+        src_val = C->h_val.p;
+        src_idx = C->h_idx.p;
+      }
+      B200_CUDA(cudaMemcpyAsync(C->g_val.p, src_val, sizeof(double) * (size_t)nnz_g, cudaMemcpyHostToDevice, s));
+      B200_CUDA(cudaMemcpyAsync(C->g_idx.p, src_idx, sizeof(int) * (size_t)nnz_g, cudaMemcpyHostToDevice, s));
       LaunchCounter lc;
       enqueue_scatter_rhs(rfull, N, nnz_g, C->g_idx.p, 0, C->g_val.p, s, lc);
     }
@@ -497,13 +518,50 @@ b200_cg_solve_ex(b200_cg* C,
       }
     };
     auto finish  = [&](const double* p_dev, int iters, int term) {
-      if (p_dev)
+      if (sparse)
+      {
+        *sparse->nnz = 0;
+      }
+      if (p_dev && sparse && is_pinned_host(sparse->idx, sizeof(int) * (size_t)n) && is_pinned_host(sparse->val, sizeof(double) * (size_t)n))
+      {
+        // sparsified on the device (sleqp_vec_set_from_raw, vec.c:72-104), both arrays DMA'd into the caller's buffers
+        const int nchunks = compact_chunks(n);
+        C->cp_idx.reserve((size_t)n);
+        C->cp_val.reserve((size_t)n);
+        C->cp_cnt.reserve((size_t)nchunks + 1);
+        LaunchCounter eager;
+        enqueue_compact(p_dev, n, sparse->zero_eps, C->cp_cnt.p, C->cp_idx.p, C->cp_val.p, s, eager);
+        B200_CUDA(cudaMemcpyAsync(C->h_exit.p + 2, C->cp_cnt.p + nchunks, sizeof(int), cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaMemcpyAsync(sparse->val, C->cp_val.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaMemcpyAsync(sparse->idx, C->cp_idx.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaStreamSynchronize(s));
+        *sparse->nnz = C->h_exit.p[2];
+      }
+      else if (p_dev)
       {
         B200_CUDA(cudaMemcpyAsync(C->h_step.p, p_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
         B200_CUDA(cudaStreamSynchronize(s));
-        std::memcpy(step_out, C->h_step.p, sizeof(double) * (size_t)n);
+        if (sparse)
+        {
+          int nnz = 0;
+          for (int i = 0; i < n; ++i)
+          {
+            const double v = C->h_step.p[i];
+            if (std::fabs(v) > sparse->zero_eps)
+            {
+              sparse->idx[nnz] = i;
+              sparse->val[nnz] = v;
+              ++nnz;
+            }
+          }
+          *sparse->nnz = nnz;
+        }
+        else
+        {
+          std::memcpy(step_out, C->h_step.p, sizeof(double) * (size_t)n);
+        }
       }
-      else
+      else if (step_out)
       {
         std::memset(step_out, 0, sizeof(double) * (size_t)n);
       }
@@ -812,6 +870,53 @@ b200_cg_solve_ex(b200_cg* C,
       r_dot_g  = r_dot_g_new;
     }
   });
+}
+} // namespace
+
+int
+b200_cg_solve_ex(b200_cg* C,
+                 int n,
+                 int nnz_g,
+                 const int* g_idx,
+                 const double* g_val,
+                 double trust_radius,
+                 double rel_tol,
+                 int max_iter,
+                 double* step_out,
+                 int* iterations,
+                 int* termination,
+                 double* tr_dual,
+                 double* min_rayleigh,
+                 double* max_rayleigh)
+{
+  if (!step_out)
+  {
+    return set_error(B200_ERR_ARG, "bad argument");
+  }
+  return cg_solve_impl(C, n, nnz_g, g_idx, g_val, trust_radius, rel_tol, max_iter, step_out, nullptr, iterations, termination, tr_dual, min_rayleigh, max_rayleigh);
+}
+
+int
+b200_cg_solve_sparse(b200_cg* C,
+                     int n,
+                     int nnz_g,
+                     const int* g_idx,
+                     const double* g_val,
+                     double trust_radius,
+                     double rel_tol,
+                     int max_iter,
+                     double zero_eps,
+                     int* step_idx,
+                     double* step_val,
+                     int* step_nnz,
+                     int* iterations,
+                     int* termination,
+                     double* tr_dual,
+                     double* min_rayleigh,
+                     double* max_rayleigh)
+{
+  const SparseStep sp{zero_eps, step_idx, step_val, step_nnz};
+  return cg_solve_impl(C, n, nnz_g, g_idx, g_val, trust_radius, rel_tol, max_iter, nullptr, &sp, iterations, termination, tr_dual, min_rayleigh, max_rayleigh);
 }
 
 int

@@ -141,6 +141,14 @@ is_pinned_host(const void* p)
   return attr.type == cudaMemoryTypeHost;
 }
 
+// ... over its whole extent: a registration that another owner made for an array that has since moved may cover only
+// the head of `p`
+inline bool
+is_pinned_host(const void* p, size_t bytes)
+{
+  return is_pinned_host(p) && (bytes == 0 || is_pinned_host(static_cast<const char*>(p) + bytes - 1));
+}
+
 // Per-supernode geometry on the device.
 struct SnMeta
 {

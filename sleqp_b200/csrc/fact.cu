@@ -471,10 +471,17 @@ b200_host_pin(void* ptr, size_t bytes)
   {
     return set_error(B200_ERR_ARG, "null buffer");
   }
-  return guarded([&]() {
-    B200_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
-    return (int)B200_OK;
-  });
+  const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess)
+  {
+    cudaGetLastError(); // not sticky, but the next cudaGetLastError() of an unrelated call would report it
+    if (e == cudaErrorHostMemoryAlreadyRegistered && is_pinned_host(ptr, bytes))
+    {
+      return B200_OK; // another owner page-locked the same array: nothing to do
+    }
+    return set_error(B200_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+  }
+  return B200_OK;
 }
 
 int
@@ -484,10 +491,13 @@ b200_host_unpin(void* ptr)
   {
     return set_error(B200_ERR_ARG, "null buffer");
   }
-  return guarded([&]() {
-    B200_CUDA(cudaHostUnregister(ptr));
-    return (int)B200_OK;
-  });
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess)
+  {
+    cudaGetLastError();
+    return set_error(B200_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+  }
+  return B200_OK;
 }
 
 int64_t
@@ -955,7 +965,7 @@ b200_fact_solve_offset(b200_fact* F, int nnz_rhs, const int* idx, const double* 
       F->rhs_val.reserve((size_t)nnz_rhs);
       // the right-hand side is borrowed for the duration of the call: pageable memory is staged through the
       // handle's pinned buffer, page-locked memory is read by the copy engine directly (and waited for below)
-      bool direct = is_pinned_host(val);
+      bool direct = is_pinned_host(val, sizeof(double) * (size_t)nnz_rhs);
       if (direct)
       {
         B200_CUDA(cudaMemcpyAsync(F->rhs_val.p, val, sizeof(double) * (size_t)nnz_rhs, cudaMemcpyHostToDevice, F->stream));
@@ -1029,7 +1039,7 @@ b200_fact_solution_ptr(b200_fact* F, int begin, int end, const double** out)
 int
 b200_fact_solution(b200_fact* F, int begin, int end, double* out_dense)
 {
-  if (F && F->solved && out_dense && end > begin && begin >= 0 && F->dp.plan && end <= F->dp.plan->N && is_pinned_host(out_dense))
+  if (F && F->solved && out_dense && end > begin && begin >= 0 && F->dp.plan && end <= F->dp.plan->N && is_pinned_host(out_dense, sizeof(double) * (size_t)(end - begin)))
   {
     return guarded([&]() {
       B200_CUDA(cudaSetDevice(F->device));
@@ -1061,7 +1071,7 @@ b200_fact_solution_sparse(b200_fact* F, int begin, int end, double zero_eps, int
   // Page-locked outputs: the slice is sparsified on the device (sleqp_vec_set_from_raw, vec.c:72-104) and both
   // arrays are DMA'd straight into the caller's buffers -- no host pass over the values. (The arrays are copied at
   // full length so that one synchronisation serves the count and the data.)
-  if (F && F->solved && nnz_out && idx_out && val_out && end > begin && begin >= 0 && F->dp.plan && end <= F->dp.plan->N && is_pinned_host(val_out) && is_pinned_host(idx_out))
+  if (F && F->solved && nnz_out && idx_out && val_out && end > begin && begin >= 0 && F->dp.plan && end <= F->dp.plan->N && is_pinned_host(val_out, sizeof(double) * (size_t)(end - begin)) && is_pinned_host(idx_out, sizeof(int) * (size_t)(end - begin)))
   {
     return guarded([&]() {
       B200_CUDA(cudaSetDevice(F->device));

@@ -167,7 +167,7 @@ stage_sparse(b200_mat* M, int dim, int nnz, const int* idx, const double* val, d
     return;
   }
   M->sp_val.reserve((size_t)nnz);
-  if (is_pinned_host(val)) // borrowed buffer, but every caller synchronises the stream before returning
+  if (is_pinned_host(val, sizeof(double) * (size_t)nnz)) // borrowed buffer, but every caller synchronises the stream before returning
   {
     B200_CUDA(cudaMemcpyAsync(M->sp_val.p, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, M->stream));
   }
@@ -394,7 +394,7 @@ b200_mat_mult_vec(b200_mat* M, int nnz_x, const int* idx, const double* val, dou
     B200_CUDA(cudaSetDevice(M->device));
     stage_sparse(M, M->num_cols, nnz_x, idx, val, M->x.p);
     launch_spmv(M->num_rows, M->nnz, M->csr_ptr.p, M->csr_col.p, M->csr_val.p, M->x.p, M->y.p, M->stream);
-    const bool direct = is_pinned_host(result_dense);
+    const bool direct = is_pinned_host(result_dense, sizeof(double) * (size_t)M->num_rows);
     if (M->num_rows > 0)
     {
       B200_CUDA(cudaMemcpyAsync(direct ? result_dense : M->h_out.p, M->y.p, sizeof(double) * (size_t)M->num_rows, cudaMemcpyDeviceToHost, M->stream));
@@ -424,7 +424,7 @@ b200_mat_mult_vec_trans(b200_mat* M, int nnz_v, const int* idx, const double* va
     B200_CUDA(cudaSetDevice(M->device));
     stage_sparse(M, M->num_rows, nnz_v, idx, val, M->x.p);
     launch_spmv(M->num_cols, M->nnz, M->cols.p, M->rows.p, M->data.p, M->x.p, M->y.p, M->stream);
-    const bool direct = is_pinned_host(result_dense);
+    const bool direct = is_pinned_host(result_dense, sizeof(double) * (size_t)M->num_cols);
     if (M->num_cols > 0)
     {
       B200_CUDA(cudaMemcpyAsync(direct ? result_dense : M->h_out.p, M->y.p, sizeof(double) * (size_t)M->num_cols, cudaMemcpyDeviceToHost, M->stream));

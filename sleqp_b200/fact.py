@@ -337,6 +337,27 @@ class ProjectedCG:
                                      int(max_iter), _pd(step), C.byref(it), C.byref(term), C.byref(dual), C.byref(rmin), C.byref(rmax)))
         return step, it.value, term.value, dual.value, rmin.value, rmax.value
 
+    def solve_sparse(self, n, g_idx, g_val, trust_radius, rel_tol=1e-8, max_iter=100, zero_eps=0.0, pinned=False):
+        """The step as (indices, values) with the contract of sleqp_vec_set_from_raw (|v| > zero_eps, ascending), plus
+        (iterations, termination, tr_dual, min_rayleigh, max_rayleigh). pinned=True page-locks the arrays first: the
+        step is then sparsified on the device and DMA'd into them (what host/tr/tr_b200.c does)."""
+        g_idx, g_val = _i32(g_idx), _f64(g_val)
+        idx = np.empty(int(n), dtype=np.int32)
+        val = np.empty(int(n), dtype=np.float64)
+        bufs = (g_idx, g_val, idx, val) if pinned else ()
+        for b in bufs:
+            check(lib().b200_host_pin(b.ctypes.data_as(C.c_void_p), b.nbytes))
+        try:
+            it, term, nnz = C.c_int(), C.c_int(), C.c_int()
+            dual, rmin, rmax = C.c_double(), C.c_double(), C.c_double()
+            check(lib().b200_cg_solve_sparse(self._h, int(n), int(len(g_idx)), _pi(g_idx), _pd(g_val), float(trust_radius), float(rel_tol),
+                                             int(max_iter), float(zero_eps), _pi(idx), _pd(val), C.byref(nnz), C.byref(it), C.byref(term),
+                                             C.byref(dual), C.byref(rmin), C.byref(rmax)))
+        finally:
+            for b in bufs:
+                lib().b200_host_unpin(b.ctypes.data_as(C.c_void_p))
+        return idx[: nnz.value].copy(), val[: nnz.value].copy(), it.value, term.value, dual.value, rmin.value, rmax.value
+
     def solve(self, n, g_idx, g_val, trust_radius, rel_tol=1e-8, max_iter=100):
         """Returns (step[n], iterations, termination)."""
         g_idx, g_val = _i32(g_idx), _f64(g_val)

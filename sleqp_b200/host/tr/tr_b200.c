@@ -49,10 +49,10 @@ typedef struct
   SleqpVec* product;
   bool callback_failed;
 
-  double* step;
 
   int last_iterations;
   int last_exit;
+  SleqpB200Pins pins; // page-locked arrays of the caller's gradient / step vectors
 } TRData;
 
 #define B200_CALL(x)                                                           \
@@ -179,20 +179,37 @@ b200_tr_solve(SleqpAugJac* jacobian,
 
   double dual = 0.;
 
-  const int status = b200_cg_solve_ex(data->cg,
-                                      num_vars,
-                                      gradient->nnz,
-                                      gradient->indices,
-                                      gradient->data,
-                                      trust_radius,
-                                      rel_tol,
-                                      data->max_iter, // SLEQP_NONE == -1: no cap
-                                      data->step,
-                                      &data->last_iterations,
-                                      &data->last_exit,
-                                      &dual,
-                                      &data->min_rayleigh,
-                                      &data->max_rayleigh);
+  // The gradient is read from, and the step is written to, the arrays of the caller's
+  // SleqpVec objects by the copy engine: registered once (SLEQP reuses these vectors across
+  // iterations), re-registered if sleqp_vec_reserve moved them. The step comes back
+  // sparsified on the device (contract of sleqp_vec_set_from_raw).
+  SLEQP_CALL(sleqp_vec_clear(newton_step));
+  SLEQP_CALL(sleqp_vec_reserve(newton_step, num_vars));
+
+  sleqp_b200_pin_buffer(&data->pins, gradient->data, sizeof(double) * (size_t)gradient->nnz_max);
+  sleqp_b200_pin_buffer(&data->pins, gradient->indices, sizeof(int) * (size_t)gradient->nnz_max);
+  sleqp_b200_pin_buffer(&data->pins, newton_step->data, sizeof(double) * (size_t)newton_step->nnz_max);
+  sleqp_b200_pin_buffer(&data->pins, newton_step->indices, sizeof(int) * (size_t)newton_step->nnz_max);
+
+  int step_nnz = 0;
+
+  const int status = b200_cg_solve_sparse(data->cg,
+                                          num_vars,
+                                          gradient->nnz,
+                                          gradient->indices,
+                                          gradient->data,
+                                          trust_radius,
+                                          rel_tol,
+                                          data->max_iter, // SLEQP_NONE == -1: no cap
+                                          zero_eps,
+                                          newton_step->indices,
+                                          newton_step->data,
+                                          &step_nnz,
+                                          &data->last_iterations,
+                                          &data->last_exit,
+                                          &dual,
+                                          &data->min_rayleigh,
+                                          &data->max_rayleigh);
 
   data->multipliers = NULL;
 
@@ -204,7 +221,7 @@ b200_tr_solve(SleqpAugJac* jacobian,
 
   B200_CALL(status);
 
-  SLEQP_CALL(sleqp_vec_set_from_raw(newton_step, data->step, num_vars, zero_eps));
+  newton_step->nnz = step_nnz;
 
   if (!isnan(dual))
   {
@@ -247,7 +264,7 @@ b200_tr_free(void** star)
   B200_CALL(b200_cg_free(&data->cg));
   B200_CALL(b200_mat_free(&data->hessian));
 
-  sleqp_free(&data->step);
+  sleqp_b200_unpin_all(&data->pins);
 
   SLEQP_CALL(sleqp_vec_free(&data->product));
   SLEQP_CALL(sleqp_vec_free(&data->direction));
@@ -290,8 +307,6 @@ sleqp_b200_tr_solver_create(SleqpTRSolver** solver_star,
 
   SLEQP_CALL(sleqp_vec_create_empty(&data->direction, num_vars));
   SLEQP_CALL(sleqp_vec_create_empty(&data->product, num_vars));
-
-  SLEQP_CALL(sleqp_alloc_array(&data->step, num_vars));
 
   SleqpTRCallbacks callbacks = {.solve    = b200_tr_solve,
                                 .rayleigh = b200_tr_rayleigh,

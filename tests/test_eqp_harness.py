@@ -162,6 +162,14 @@ def test_device_resident_projected_cg_matches_reference_iterates(golden, case):
         ref = want[f"cg_path_sample_{i}"]
         assert np.abs(s - ref).max() <= 1e-8 * max(1.0, np.abs(ref).max()), i
         _check_tr_info(dict(tr_dual=dual, min_rayleigh=rmin, max_rayleigh=rmax), want[f"tr_info_{i}"])
+    # sparse result (what tr_b200.c hands to the caller's SleqpVec): same step, sparsified with the rule of
+    # sleqp_vec_set_from_raw, through pageable arrays (host pass) and through page-locked ones (device compaction)
+    eps = float(np.median(np.abs(step)))
+    for pinned in (False, True):
+        si, sv, it_s, how_s, _, _, _ = cg.solve_sparse(p.n, gi, grad, 1e8, 1e-4, 4 * N, zero_eps=eps, pinned=pinned)
+        keep = np.nonzero(np.abs(step) > eps)[0]
+        assert it_s == it and how_s == ProjectedCG.INTERIOR and 0 < len(keep) < p.n
+        assert np.array_equal(si, keep) and np.abs(sv - step[keep]).max() <= 1e-8 * np.abs(step).max()
     # matrix-free Hessian (the reference's callback): same iterates with the products done on the host
     Hs = p.H.tocsr()
     cgf = ProjectedCG(f, None, hess_prod=lambda d: Hs @ d)
