@@ -426,7 +426,9 @@ def measure_config(cfg_idx, args, torch, dev, local_rank, rank, world, dist, ste
 
     def hbm_roof(kernel, nbytes, ms, launches_, extra=None):
         a = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        r = {"kernel": kernel, "bound": "hbm", "achieved": a, "peak": hbm, "unit": "GB/s", "frac": a / hbm, "traffic": ncu_traffic_per_launch(kernel, p.name),
+        extra = dict(extra or {})
+        r = {"kernel": kernel, "bound": "hbm", "achieved": a, "peak": hbm, "unit": "GB/s", "frac": a / hbm,
+             "traffic": ncu_traffic_per_launch(extra.pop("traffic_key", kernel), p.name),
              "peak_source": peak_src, "bytes_per_launch": int(nbytes), "ms_per_launch": ms, "launches_per_step": launches_}
         r.update(extra or {})
         return r
@@ -458,9 +460,23 @@ def measure_config(cfg_idx, args, torch, dev, local_rank, rank, world, dist, ste
     spmvj_ms = time_spmv(lambda: mJ.mult_vec_device(d_x.data_ptr(), d_jx.data_ptr()))
     spmvt_ms = time_spmv(lambda: mJ.mult_vec_trans_device(d_v.data_ptr(), d_jtv.data_ptr()))
     spmv_bytes = lambda A: 12 * A.nnz + 4 * (A.shape[1] + 1) + 8 * A.shape[1] + 8 * A.shape[0]  # noqa: E731
+    # which kernels a sweep consists of: sparse subtrees (sst.cu, one ticketed launch for all generations), the dataflow
+    # kernel over the dense supernodes (solve.cu), or the first followed by the second
+    from sleqp_b200.fact import Symbolic
+
+    sym = Symbolic(p.N, w["cp"], w["ri"], w["v"])  # plan cache hit: the handle analysed the same pattern
+    n_sst, n_dense_tasks = len(sym.export("sst")), len(sym.export("ffl_tasks"))
+    sym.close()
+    names = {d: " + ".join(([f"k_sst_{'forward' if d == 'fwd' else 'backward'}"] if n_sst else []) + ([f"k_flow<{d}>"] if n_dense_tasks else []))
+             for d in ("fwd", "bwd")}
+    if n_sst and n_dense_tasks:
+        names["bwd"] = "k_flow<bwd> + k_sst_backward"
+    sweep_extra = {"tree_levels": st["n_levels"], "stored_bytes": 8 * st["panel_doubles"], "sparse_subtrees": n_sst, "dense_sweep_tasks": n_dense_tasks}
     rooflines = {
-        "k_flow_fwd": hbm_roof("k_flow_fwd", sweep_bytes, float(phases[1]), n_solves, {"tree_levels": st["n_levels"], "stored_bytes": 8 * st["panel_doubles"]}),
-        "k_flow_bwd": hbm_roof("k_flow_bwd", sweep_bytes + 8 * st["n_reduced"], float(phases[2]), n_solves, {"tree_levels": st["n_levels"], "stored_bytes": 8 * st["panel_doubles"]}),
+        "k_flow_fwd": hbm_roof(names["fwd"], sweep_bytes, float(phases[1]), n_solves,
+                               dict(sweep_extra, traffic_key="k_flow_fwd" if n_dense_tasks else "k_sst_forward")),
+        "k_flow_bwd": hbm_roof(names["bwd"], sweep_bytes + 8 * st["n_reduced"], float(phases[2]), n_solves,
+                               dict(sweep_extra, traffic_key="k_flow_bwd" if n_dense_tasks else "k_sst_backward")),
         "k_pre+k_post": hbm_roof("k_pre+k_post", 2 * (12 * len(w["ri"]) + 16 * p.N), float(phases[0] + phases[3]), n_solves),
         "k_update": fp64_roof("k_update", st["flops_update"], classes["update"], "all in-panel + Schur DMMA tiles of one factorization, eager launch-by-launch timing"),
         "k_inv_gemm": fp64_roof("k_inv_gemm", st["flops_inv"], classes["inv_gemm"], "selective inversion tiles"),

@@ -37,8 +37,11 @@ typedef struct
   int working_set_size;
   bool has_factorization;
 
-  // working set of the last factorization (linear problems: nothing to do while it stays the same)
+  // working set of the last factorization (linear problems: nothing to do while it stays the
+  // same; all problems: the index maps below stay valid while it stays the same)
   SleqpWorkingSet* working_set;
+  bool fixed_jacobian;
+  bool maps_valid;
 
   // the working set as index maps (-1: not in the working set)
   int* var_index;
@@ -70,35 +73,44 @@ aug_jac_set_iterate(SleqpIterate* iterate, void* data)
   SleqpProblem* problem        = jacobian->problem;
   SleqpWorkingSet* working_set = sleqp_iterate_working_set(iterate);
 
-  // Do not recompute for linear problems & unchanged working set (standard_aug_jac.c:247-259)
-  if (jacobian->working_set)
+  // Do not recompute for linear problems & unchanged working set (standard_aug_jac.c:247-259).
+  // The copy of the working set is kept for nonlinear problems too: while the working set stays
+  // the same (the usual case once the active set has settled) the index maps handed to the
+  // device library are still valid and the two passes over all variables and constraints that
+  // rebuild them are skipped; the Jacobian values are of course sent every time.
+  const bool same_working_set
+    = jacobian->maps_valid
+      && sleqp_working_set_eq(working_set, jacobian->working_set);
+
+  if (same_working_set && jacobian->fixed_jacobian
+      && jacobian->has_factorization)
   {
-    if (sleqp_working_set_eq(working_set, jacobian->working_set)
-        && jacobian->has_factorization)
-    {
-      sleqp_fact_b200_set_last_handle(jacobian->handle);
-      return SLEQP_OKAY;
-    }
-    else
-    {
-      SLEQP_CALL(sleqp_working_set_copy(working_set, jacobian->working_set));
-    }
+    sleqp_fact_b200_set_last_handle(jacobian->handle);
+    return SLEQP_OKAY;
   }
 
   const int num_variables   = sleqp_problem_num_vars(problem);
   const int num_constraints = sleqp_problem_num_cons(problem);
 
-  jacobian->working_set_size = sleqp_working_set_size(working_set);
-  jacobian->condition        = SLEQP_NONE;
+  jacobian->condition = SLEQP_NONE;
 
-  for (int j = 0; j < num_variables; ++j)
+  if (!same_working_set)
   {
-    jacobian->var_index[j] = sleqp_working_set_var_index(working_set, j);
-  }
+    SLEQP_CALL(sleqp_working_set_copy(working_set, jacobian->working_set));
 
-  for (int i = 0; i < num_constraints; ++i)
-  {
-    jacobian->cons_index[i] = sleqp_working_set_cons_index(working_set, i);
+    jacobian->working_set_size = sleqp_working_set_size(working_set);
+
+    for (int j = 0; j < num_variables; ++j)
+    {
+      jacobian->var_index[j] = sleqp_working_set_var_index(working_set, j);
+    }
+
+    for (int i = 0; i < num_constraints; ++i)
+    {
+      jacobian->cons_index[i] = sleqp_working_set_cons_index(working_set, i);
+    }
+
+    jacobian->maps_valid = true;
   }
 
   SleqpMat* cons_jac = sleqp_iterate_cons_jac(iterate);
@@ -311,12 +323,9 @@ sleqp_b200_aug_jac_create(SleqpAugJac** star,
   SLEQP_CALL(sleqp_alloc_array(&jacobian->var_index, num_variables));
   SLEQP_CALL(sleqp_alloc_array(&jacobian->cons_index, num_constraints));
 
-  const bool fixed_jacobian = !(sleqp_problem_has_nonlinear_cons(problem));
+  jacobian->fixed_jacobian = !(sleqp_problem_has_nonlinear_cons(problem));
 
-  if (fixed_jacobian)
-  {
-    SLEQP_CALL(sleqp_working_set_create(&jacobian->working_set, problem));
-  }
+  SLEQP_CALL(sleqp_working_set_create(&jacobian->working_set, problem));
 
   const int status = b200_fact_create(&jacobian->handle, -1);
 
