@@ -88,6 +88,8 @@ typedef struct b200_stats
   double flops_update;     /* useful flops of the DMMA update tiles (in-panel + Schur): roofline numerator of k_update */
   double flops_inv;        /* useful flops of the selective-inversion tiles: roofline numerator of k_inv_gemm */
   int64_t panel_doubles;   /* doubles of one copy of the supernodal panels as laid out in HBM (L; Mt and Mr are as large) */
+  int64_t n_demoted;       /* indices with a non-zero diagonal kept in the reduced system instead of being eliminated in
+                              closed form: coupled to an eliminated index (non-diagonal (1,1) block) or a dense column */
 } b200_stats;
 
 /* ---- factorization plugin (SleqpFactCallbacks) --------------------------------------- */

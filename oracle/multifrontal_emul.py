@@ -196,7 +196,7 @@ class Emulated:
             smax = max(smax, np.abs(np.diag(self.panel(T)[:k, :k])).max(initial=0.0))
         for M in self.sst:
             smax = max(smax, np.abs(self.L[M["Lptr"] + M["colptr"][:-1]]).max(initial=0.0))
-        self.tau = 64 * np.finfo(float).eps * smax
+        self.tau = (2.0 ** -26 if int(p.get("n_demoted", 0)) > 0 else 64 * np.finfo(float).eps) * smax  # plan.hpp STATIC_PIVOT_*
         self.n_perturbed = getattr(self, "n_perturbed", 0)
         for M in self.sst:  # leaves of the supernodal tree: before the first stage
             self._sst_factor(M)

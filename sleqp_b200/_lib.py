@@ -44,6 +44,7 @@ class Stats(C.Structure):
         ("flops_update", C.c_double),
         ("flops_inv", C.c_double),
         ("panel_doubles", C.c_int64),
+        ("n_demoted", C.c_int64),
     ]
 
     def as_dict(self):

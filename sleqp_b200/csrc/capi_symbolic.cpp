@@ -175,6 +175,7 @@ fill_stats_from_plan(const Plan& P, b200_stats* s)
   s->flops_update        = P.flops_update;
   s->flops_inv           = P.flops_inv;
   s->panel_doubles       = P.Lptr.empty() ? 0 : P.Lptr[P.nsuper];
+  s->n_demoted           = P.n_demoted;
   s->perm_hash           = P.perm_hash;
   s->ms_symbolic         = P.ms_symbolic;
   s->n_scratch_slots     = P.n_scratch_slots;

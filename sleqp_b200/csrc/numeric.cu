@@ -86,10 +86,15 @@ k_diagmax(int m, const long long* __restrict__ Sdiag, const double* __restrict__
   }
 }
 
+// Static pivot threshold relative to the largest |S_jj|. Negative definite S (everything SLEQP builds): 64 ulps -- a
+// pivot below that is rounding noise, i.e. dependent working-set rows. Quasi-definite S (candidates kept in the
+// reduced system, plan.hpp n_demoted): a working-set row without an eliminated neighbour has an exactly zero pivot
+// when the ordering places it before its variables; it is replaced by -sqrt(eps) |S|_max (the usual static-pivoting
+// size) and iterative refinement against the unperturbed K removes the perturbation.
 __global__ void
-k_set_tau(double* scal)
+k_set_tau(double* scal, double rel)
 {
-  scal[1] = 64.0 * 2.220446049250313e-16 * scal[0];
+  scal[1] = rel * scal[0];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1008,7 +1013,7 @@ enqueue_numeric(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t stream
     const unsigned rb = (unsigned)std::min<long long>((P.m + threads - 1) / threads, 1184);
     k_diagmax<<<rb, threads, 0, stream>>>(P.m, dp.Sdiag.p, nb.L, (unsigned long long*)nb.scal);
     lc.tick();
-    k_set_tau<<<1, 1, 0, stream>>>(nb.scal);
+    k_set_tau<<<1, 1, 0, stream>>>(nb.scal, P.n_demoted > 0 ? STATIC_PIVOT_QUASI : STATIC_PIVOT_DEFINITE);
     lc.tick();
     enqueue_sst_factor(dp, nb, stream, lc); // the sparse subtrees are leaves: their update blocks are ready before stage 0
   }

@@ -50,6 +50,10 @@ constexpr int SST_MAX_NNZ   = 6144; // entries of L in the subtree (values live 
 constexpr int SST_MAX_AVG   = 8;    // mean entries per column: beyond that the dense supernodal path is the better one
 constexpr int SST_THREADS   = 256;
 
+// static pivot threshold relative to max |S_jj| (numeric.cu: k_set_tau)
+constexpr double STATIC_PIVOT_DEFINITE = 64.0 * 2.220446049250313e-16;
+constexpr double STATIC_PIVOT_QUASI    = 1.4901161193847656e-08;
+
 constexpr size_t SST_SMEM_LIMIT = 200 * 1024; // what sst.cu opts its kernels into
 
 struct SstMeta
@@ -208,6 +212,7 @@ struct Plan
   std::vector<long long> sst_ea_src;     // assembly of child subtrees: offset of the entry in the update workspace ...
   std::vector<int> sst_ea_dst;           // ... and where it goes: >= 0 slot of the subtree's values, < 0: -1 - index in its update block
   std::vector<int> sst_gen_ptr;          // P.sst is sorted by generation: [gen_ptr[g], gen_ptr[g + 1])
+  int n_demoted = 0; // indices with a non-zero diagonal kept in the reduced system (coupled to an E node, or a dense column)
   size_t sst_smem_bytes = 0; // dynamic shared memory of the sst kernels: what the largest subtree of this plan needs
 
   // assembly of S straight into the panels: S_e = val[gsrc] - sum_t val[a]*val[b]/val[d]

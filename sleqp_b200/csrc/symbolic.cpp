@@ -822,9 +822,52 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
   P.k_of_e.reserve((size_t)n);
   P.dE_src.reserve((size_t)n);
   P.k_of_r.reserve((size_t)n);
+  // Which indices are eliminated in closed form (E): those with a non-zero diagonal entry, as long as they form an
+  // independent set of K's graph and their elimination does not densify the Schur complement. What SLEQP builds
+  // (standard_aug_jac.c:135-237: identity (1,1) block) makes every variable an E node. Two kinds of candidates stay in
+  // the reduced system instead (R nodes with a non-zero diagonal; S is then symmetric quasi-definite instead of
+  // negative definite, which the LDL^T below factors just the same):
+  //   * a candidate coupled to an E node chosen before it (an off-diagonal entry inside the (1,1) block), and
+  //   * a candidate whose column is so long that its clique in S alone would hold more than 8 x nnz(K) entries (a dense
+  //     column of J).
+  std::vector<char> elim(n, 0);
+  {
+    std::vector<int> deg(n, 0);
+    for (int j = 0; j < n; ++j)
+    {
+      for (int p = colptr[j]; p < colptr[j + 1]; ++p)
+      {
+        const int i = rowidx[p];
+        if (i > j)
+        {
+          ++deg[i];
+          ++deg[j];
+        }
+      }
+    }
+    const double clique_cap = 8.0 * (double)std::max<long long>(P.nnzK, 1);
+    std::vector<char> blocked(n, 0);
+    for (int j = 0; j < n; ++j)
+    {
+      const bool dense = deg[j] > 128 && (double)deg[j] * deg[j] > clique_cap;
+      if (diag_src[j] < 0 || blocked[j] || dense)
+      {
+        P.n_demoted += diag_src[j] >= 0;
+        continue;
+      }
+      elim[j] = 1;
+      for (int p = colptr[j]; p < colptr[j + 1]; ++p)
+      {
+        if (rowidx[p] > j)
+        {
+          blocked[rowidx[p]] = 1; // a neighbour of an E node cannot be one itself
+        }
+      }
+    }
+  }
   for (int j = 0; j < n; ++j)
   {
-    if (diag_src[j] >= 0)
+    if (elim[j])
     {
       P.e_of_k[j] = P.nE++;
       P.k_of_e.push_back(j);
