@@ -412,20 +412,24 @@ factor_and_probe(b200_fact* F, Lap&& lap)
     const NumericBuffers nb = F->nbuf();
     const SolveBuffers sb   = F->sbuf();
     LaunchCounter eager;
-    double best = INFINITY, prev = INFINITY;
+    double best = INFINITY, prev = INFINITY, best_eta = INFINITY;
     int refine  = 0;
+    enqueue_abs_range(F->val.p, P.nnzK_input, F->scal.p, F->stream, eager); // max |K_ij| <= ||K||_2
     for (int r = 0; r <= MAX_REFINE; ++r)
     {
       enqueue_probe_rhs(sb.rhs, P.N, F->stream, eager);
       launch_solve(F, r);
       enqueue_residual_norms(F->dp, nb, sb, F->stream, eager);
-      B200_CUDA(cudaMemcpyAsync(F->h_scal.p, F->scal.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, F->stream));
+      B200_CUDA(cudaMemcpyAsync(F->h_scal.p, F->scal.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, F->stream));
       B200_CUDA(cudaStreamSynchronize(F->stream));
-      const double rr = std::sqrt(F->h_scal.p[2]) / std::sqrt(F->h_scal.p[3]);
+      const double rnorm = std::sqrt(F->h_scal.p[2]), bnorm = std::sqrt(F->h_scal.p[3]), xnorm = std::sqrt(F->h_scal.p[4]);
+      const double rr = rnorm / bnorm;
       if (std::isfinite(rr) && rr < best)
       {
         best   = rr;
         refine = r;
+        // normwise backward error with ||K||_2 bounded from below by its largest entry (i.e. from above)
+        best_eta = rnorm / (F->h_scal.p[6] * xnorm + bnorm);
       }
       // good enough, broken, or refinement stopped paying
       if (!std::isfinite(rr) || rr <= 1e-13 || (r > 0 && rr > 0.25 * prev))
@@ -437,7 +441,17 @@ factor_and_probe(b200_fact* F, Lap&& lap)
     F->refine    = refine;
     F->probe_res = best;
     lap("probe solve(s) + residual");
-    if (!(best <= 1e-6))
+    // Verdict. A residual of 1e-6 |b| or better (refinement is then chosen so that every solve meets 1e-10): fine.
+    // Otherwise the system is accepted only if no pivot fell below the noise threshold (so the rows of the working set
+    // are independent at working precision) and the computed solution is the exact solution of a system within 1e-13
+    // of K relative to |K| -- nearly dependent rows, where |x| >> |b| and no backward-stable solver (Umfpack's LU
+    // included) gets a small residual relative to |b|.
+    static const bool timing = std::getenv("B200_TIMING") != nullptr;
+    if (timing)
+    {
+      std::fprintf(stderr, "[b200 probe] residual %.3e backward error %.3e perturbed %d refine %d\n", best, best_eta, F->n_perturbed, refine);
+    }
+    if (!(best <= 1e-6) && !(F->n_perturbed == 0 && best_eta <= 1e-13))
     {
       return set_error(B200_ERR_SINGULAR,
                        "KKT matrix is numerically singular (probe residual " + std::to_string(best) + ", " + std::to_string(F->n_perturbed) +

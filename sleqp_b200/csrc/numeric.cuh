@@ -98,6 +98,7 @@ void enqueue_pivot_range(const DevPlan& dp, const NumericBuffers& nb, cudaStream
 
 // Sparsification of x[0, n) on the device (sleqp_vec_set_from_raw, vec.c:72-104): the entries with |x_i| > eps in
 // ascending order -> (idx_out, val_out), their number -> chunk_cnt[compact_chunks(n)]. chunk_cnt: compact_chunks(n) + 1 ints.
+void enqueue_abs_range(const double* v, long long n, double* scal, cudaStream_t stream, LaunchCounter& lc);
 void enqueue_compact(const double* x, int n, double eps, int* chunk_cnt, int* idx_out, double* val_out, cudaStream_t stream, LaunchCounter& lc);
 int compact_chunks(int n);
 

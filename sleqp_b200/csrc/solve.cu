@@ -1088,12 +1088,28 @@ enqueue_residual_norms(const DevPlan& dp, const NumericBuffers& nb, const SolveB
 {
   const Plan& P = *dp.plan;
   residual(dp, nb, sb.rhs, sb.z, sb.res, stream, lc);
-  B200_CUDA(cudaMemsetAsync(nb.scal + 2, 0, 2 * sizeof(double), stream));
+  B200_CUDA(cudaMemsetAsync(nb.scal + 2, 0, 3 * sizeof(double), stream));
   const unsigned blocks = std::min<unsigned>(nblocks(P.N, 256), 1184);
   k_sumsq<<<blocks, 256, 0, stream>>>(P.N, sb.res, nb.scal + 2);
   lc.tick();
   k_sumsq<<<blocks, 256, 0, stream>>>(P.N, sb.rhs, nb.scal + 3);
   lc.tick();
+  k_sumsq<<<blocks, 256, 0, stream>>>(P.N, sb.z, nb.scal + 4); // |x|^2: normwise backward error of the probe solve
+  lc.tick();
+  B200_CUDA(cudaGetLastError());
+}
+
+// scal[5], scal[6] = smallest and largest |v_i| (bit patterns of non-negative doubles)
+void
+enqueue_abs_range(const double* v, long long n, double* scal, cudaStream_t stream, LaunchCounter& lc)
+{
+  const unsigned long long init[2] = {0x7ff0000000000000ull, 0ull};
+  B200_CUDA(cudaMemcpyAsync(scal + 5, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+  if (n > 0)
+  {
+    k_absrange<<<std::min<unsigned>(nblocks(n, 256), 1184), 256, 0, stream>>>((int)n, v, (unsigned long long*)(scal + 5), (unsigned long long*)(scal + 6));
+    lc.tick();
+  }
   B200_CUDA(cudaGetLastError());
 }
 
