@@ -61,47 +61,68 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md clocks line), read through NVML every
+    5 ms by a thread (what `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints; the CLI
+    block-buffers its output into a pipe and takes longer to start than a short timed region lasts). mark() opens /
+    closes the window of the timed region; only samples inside it count."""
 
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, device):
         self.device = device
-        self.rows = []
-        self.proc = None
+        self.rows = []  # (time, sm_mhz, reasons bitmask)
+        self.window = [None, None]
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.device)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it is a plain list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.device
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.device])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def run():
+                while not self.stop_flag:
+                    try:
+                        try:
+                            mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.rows.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(mask)))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.thread = threading.Thread(target=run, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def mark(self, which):
+        self.window[which] = time.perf_counter()
+
+    def samples_in_window(self):
+        t0, t1 = self.window[0], self.window[1] or time.perf_counter()
+        return sum(1 for t, _, _ in self.rows if t0 is None or t0 <= t <= t1)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.thread:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        t0, t1 = self.window
+        rows = [r for r in self.rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)]
+        reasons = sorted(name for name, bit in self.REASONS.items() if any(r[2] & bit for r in rows))
+        sm = [r[1] for r in rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
 def ncu_traffic_per_launch(kernel, workload):
@@ -389,16 +410,17 @@ def measure_config(cfg_idx, args, torch, dev, local_rank, rank, world, dist, ste
         torch.cuda.synchronize()
 
     warm = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(warm):
         device_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = lib.b200_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
     if args.profile_step and main:
         torch.cuda.profiler.start()  # ncu --profile-from-start off: capture exactly the timed steps
+    sampler.mark(0)
     for s in range(steps):
         with torch.cuda.stream(stream):
             flush.fill_(1.0)  # L2 flush between timed steps, outside the step's event pair
@@ -406,11 +428,23 @@ def measure_config(cfg_idx, args, torch, dev, local_rank, rank, world, dist, ste
         device_step()
         ev[s][1].record(stream)
     barrier()
+    sampler.mark(1)
     if args.profile_step and main:
         torch.cuda.profiler.stop()
     launches = lib.b200_launch_count() - launches0
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    extended = 0
+    if sampler.thread and sampler.samples_in_window() < 3:
+        # the timed region is shorter than three sampling periods: keep the same load running (untimed) until the
+        # window holds three samples, and say so
+        while sampler.samples_in_window() < 3 and extended < 2000:
+            device_step()
+            torch.cuda.synchronize()
+            extended += 1
+            sampler.mark(1)
     clocks = sampler.stop()
+    if extended:
+        clocks["window"] = f"timed region + {extended} untimed identical steps (the region is shorter than three sampling periods)"
     ms_dev = shard.max_over_ranks(float(step_ms.mean()), dist, dev)
     value = world * 1e3 / ms_dev
 

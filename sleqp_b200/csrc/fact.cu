@@ -412,15 +412,14 @@ factor_and_probe(b200_fact* F, Lap&& lap)
     const NumericBuffers nb = F->nbuf();
     const SolveBuffers sb   = F->sbuf();
     LaunchCounter eager;
-    double best = INFINITY, prev = INFINITY, best_eta = INFINITY;
+    double best = INFINITY, prev = INFINITY, best_r = 0.0, best_x = 0.0, best_b = 0.0;
     int refine  = 0;
-    enqueue_abs_range(F->val.p, P.nnzK_input, F->scal.p, F->stream, eager); // max |K_ij| <= ||K||_2
     for (int r = 0; r <= MAX_REFINE; ++r)
     {
       enqueue_probe_rhs(sb.rhs, P.N, F->stream, eager);
       launch_solve(F, r);
       enqueue_residual_norms(F->dp, nb, sb, F->stream, eager);
-      B200_CUDA(cudaMemcpyAsync(F->h_scal.p, F->scal.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, F->stream));
+      B200_CUDA(cudaMemcpyAsync(F->h_scal.p, F->scal.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, F->stream));
       B200_CUDA(cudaStreamSynchronize(F->stream));
       const double rnorm = std::sqrt(F->h_scal.p[2]), bnorm = std::sqrt(F->h_scal.p[3]), xnorm = std::sqrt(F->h_scal.p[4]);
       const double rr = rnorm / bnorm;
@@ -428,8 +427,9 @@ factor_and_probe(b200_fact* F, Lap&& lap)
       {
         best   = rr;
         refine = r;
-        // normwise backward error with ||K||_2 bounded from below by its largest entry (i.e. from above)
-        best_eta = rnorm / (F->h_scal.p[6] * xnorm + bnorm);
+        best_r = rnorm;
+        best_x = xnorm;
+        best_b = bnorm;
       }
       // good enough, broken, or refinement stopped paying
       if (!std::isfinite(rr) || rr <= 1e-13 || (r > 0 && rr > 0.25 * prev))
@@ -446,12 +446,21 @@ factor_and_probe(b200_fact* F, Lap&& lap)
     // are independent at working precision) and the computed solution is the exact solution of a system within 1e-13
     // of K relative to |K| -- nearly dependent rows, where |x| >> |b| and no backward-stable solver (Umfpack's LU
     // included) gets a small residual relative to |b|.
+    double best_eta = INFINITY;
+    if (!(best <= 1e-6) && F->n_perturbed == 0 && std::isfinite(best))
+    {
+      // normwise backward error with ||K||_2 bounded from below by its largest entry (i.e. the error from above)
+      enqueue_abs_range(F->val.p, P.nnzK_input, F->scal.p, F->stream, eager);
+      B200_CUDA(cudaMemcpyAsync(F->h_scal.p, F->scal.p, 7 * sizeof(double), cudaMemcpyDeviceToHost, F->stream));
+      B200_CUDA(cudaStreamSynchronize(F->stream));
+      best_eta = best_r / (F->h_scal.p[6] * best_x + best_b);
+    }
     static const bool timing = std::getenv("B200_TIMING") != nullptr;
     if (timing)
     {
       std::fprintf(stderr, "[b200 probe] residual %.3e backward error %.3e perturbed %d refine %d\n", best, best_eta, F->n_perturbed, refine);
     }
-    if (!(best <= 1e-6) && !(F->n_perturbed == 0 && best_eta <= 1e-13))
+    if (!(best <= 1e-6) && !(best_eta <= 1e-13))
     {
       return set_error(B200_ERR_SINGULAR,
                        "KKT matrix is numerically singular (probe residual " + std::to_string(best) + ", " + std::to_string(F->n_perturbed) +

@@ -18,8 +18,9 @@ REQUIRED = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
 
 def test_committed_bench_lines_follow_the_contract():
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_final_bench_config[234]*.json")))
-    assert files
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_final_bench_config[234]*.json"))
+                   + glob.glob(os.path.join(ROOT, "profiles", "r02_bench_default_config3*.json")))
+    assert len(files) >= 4
     for path in files:
         d = json.loads(open(path).read().strip().splitlines()[-1])
         for k in REQUIRED:
@@ -44,6 +45,10 @@ def test_traffic_comes_from_the_committed_ncu_capture():
     for kernel in ("k_flow_fwd", "k_flow_bwd"):
         t = bench.ncu_traffic_per_launch(kernel, "config2_poisson2d_g354")
         assert t is not None and 1.2e8 < t < 2.5e8  # padded panels (136 MB) + records and indices
+    # config 3 is swept by the sparse-subtree kernels: traffic ~ the exact factor (12 MB) + indices + vectors
+    for kernel in ("k_sst_forward", "k_sst_backward"):
+        t = bench.ncu_traffic_per_launch(kernel, "config3_chain_n1e6")
+        assert t is not None and 1.5e7 < t < 3.5e7
     assert bench.ncu_traffic_per_launch("k_flow_fwd", "config3_chain_n1e6") is None  # no capture for that workload
     assert bench.ncu_traffic_per_launch("no_such_kernel", "config2_poisson2d_g354") is None
 
