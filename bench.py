@@ -698,6 +698,12 @@ def run_ours(args, rank, world, local_rank):
                 r = measure_config(idx, args, torch, dev, local_rank, rank, world, dist, 3, False, kw)
                 r.pop("w"), r.pop("rhs")
                 r["steps"] = 3
+                if name == "config2":  # the same reference-driven end-to-end leg as the headline (config 4: too long here)
+                    rd = reference_driver_e2e("poisson", 354, k, 3, local_rank)
+                    if rd and "ms_per_step" in rd:
+                        r["e2e"] = {"value": rd["iters_per_s"], "unit": UNIT, "ms_per_step": rd["ms_per_step"], "h2d_bytes_per_step": rd["h2d_bytes_per_step"],
+                                    "d2h_bytes_per_step": rd["d2h_bytes_per_step"], "via": "reference-driven (oracle/_ref/eqp_step_b200), like the headline",
+                                    "detail": rd, "c_abi": r["e2e"]}
                 subs[name] = r
             except Exception as e:  # noqa: BLE001  (a sub-line must not take the headline down)
                 subs[name] = {"error": repr(e)[:300]}
