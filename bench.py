@@ -680,12 +680,26 @@ def run_ours(args, rank, world, local_rank):
     main = measure_config(args.config, args, torch, dev, local_rank, rank, world, dist, args.steps, True)
     w, rhs, k = main.pop("w"), main.pop("rhs"), args.cg_iters
 
-    # reference-driven end-to-end leg (rank 0, N = 1): the reference's own EQP code over fact_b200.c / tr_b200.c
+    # reference-driven end-to-end leg: the reference's own EQP code over the shipped glue. Every rank runs its own instance
+    # on its own GPU at the same time (replicas, like `value`); whole-job rate = ranks / slowest rank's time per step
     ref_e2e = None
-    if rank == 0 and world == 1 and not args.no_sub:
+    if not args.no_sub:
         kind, size = {0: ("chain", 100), 1: ("poisson", 354), 2: ("chain", 1_000_000), 3: ("poisson3", 48), 4: ("poisson", 128)}[args.config]
+        if dist is not None:
+            dist.barrier()
         ref_e2e = reference_driver_e2e(kind, size, k, max(3, min(args.steps, 5)), local_rank)
+        if world > 1:
+            from sleqp_b200 import shard
 
+            ok = bool(ref_e2e) and "ms_per_step" in ref_e2e
+            ms = shard.max_over_ranks(float(ref_e2e["ms_per_step"]) if ok else 1e30, dist, dev)
+            if ms >= 1e29:
+                ref_e2e = {"error": "the reference-driven leg failed on at least one rank: " + str((ref_e2e or {}).get("error", "no output"))[:200]}
+            else:
+                ref_e2e = dict(ref_e2e, ms_per_step=ms, iters_per_s=world * 1e3 / ms, ranks=world,
+                               h2d_bytes_per_step=world * ref_e2e["h2d_bytes_per_step"], d2h_bytes_per_step=world * ref_e2e["d2h_bytes_per_step"],
+                               timing="every rank runs oracle/_ref/eqp_step_b200 on its own GPU concurrently (started after a barrier); max over ranks of "
+                                      "the per-step time each process measures")
     subs = {}
     if world == 1 and not args.no_sub and args.config == DEFAULT_CONFIG:
         free, _ = torch.cuda.mem_get_info(dev)
