@@ -108,6 +108,8 @@ k_cgd_reduce(int n,
              const double* __restrict__ x,
              const double* __restrict__ y,
              double* __restrict__ xout,
+             double* __restrict__ res,       // CGD_RADIUS: r += alpha * Bd rides along (same alpha, same pass) ...
+             const double* __restrict__ Bd,  // ... (:449-456); the reference updates r after the boundary test, but r is dead on that exit
              double* __restrict__ S,
              int* __restrict__ E,
              double* __restrict__ X,
@@ -132,6 +134,7 @@ k_cgd_reduce(int n,
     {
       a += alpha * b;
       xout[i] = a;
+      res[i] += alpha * Bd[i];
     }
     xy += a * b;
     xx += a * a;
@@ -662,9 +665,9 @@ cg_solve_impl(b200_cg* C,
         {
           return hrc;
         }
-        k_cgd_reduce<CGD_CURVATURE><<<gr, 256, 0, s>>>(n, d_cur, C->Bd.p, nullptr, S, E, X, part, arrived, 0.0, gr);
-        k_cgd_reduce<CGD_RADIUS><<<gr, 256, 0, s>>>(n, z_cur, d_cur, z_new, S, E, X, part, arrived, trust_radius * trust_radius, gr); // z+ = z + alpha d
-        k_cgd_axpby<<<gb, 256, 0, s>>>(n, 1.0, r, S + 10, C->Bd.p, r, E); // r += alpha B d  (:449-456)
+        k_cgd_reduce<CGD_CURVATURE><<<gr, 256, 0, s>>>(n, d_cur, C->Bd.p, nullptr, nullptr, nullptr, S, E, X, part, arrived, 0.0, gr);
+        // z+ = z + alpha d, r += alpha B d
+        k_cgd_reduce<CGD_RADIUS><<<gr, 256, 0, s>>>(n, z_cur, d_cur, z_new, r, C->Bd.p, S, E, X, part, arrived, trust_radius * trust_radius, gr);
         int prc2 = project();                                              // g = P[r]        (:459)
         if (prc2 != B200_OK)
         {
@@ -672,9 +675,9 @@ cg_solve_impl(b200_cg* C,
         }
         // the convergence test of the next pass rides on this reduction, unless the iteration cap comes first (:302)
         const bool cap_next = max_iter >= 0 && it + 1 >= max_iter;
-        k_cgd_reduce<CGD_TAIL><<<gr, 256, 0, s>>>(n, r, g, nullptr, S, E, X, part, arrived, cap_next ? -1.0 : tol_sq, gr);
+        k_cgd_reduce<CGD_TAIL><<<gr, 256, 0, s>>>(n, r, g, nullptr, nullptr, nullptr, S, E, X, part, arrived, cap_next ? -1.0 : tol_sq, gr);
         k_cgd_axpby<<<gb, 256, 0, s>>>(n, -1.0, g, S + 11, d_cur, d_new, E); // d+ = -g + beta d (:472-479)
-        g_launches.fetch_add(5, std::memory_order_relaxed);
+        g_launches.fetch_add(4, std::memory_order_relaxed);
         return (int)B200_OK;
       };
       int enq = 0;
