@@ -44,14 +44,14 @@ class Emulated:
         ns = int(p["n_supernodes"])
         self.is_sst = np.zeros(ns, dtype=bool)
         self.sst = []
-        raw = np.asarray(p.get("sst", np.zeros((0, 26), dtype=np.int32))).reshape(-1, 26)
+        raw = np.asarray(p.get("sst", np.zeros((0, 30), dtype=np.int32))).reshape(-1, 30)
         blob_all = np.asarray(p.get("sst_blob", np.zeros(0, dtype=np.int32)), dtype=np.int64)
         last_gen = 0
         for rec in raw:
             lptr = int(np.array(rec[0:2], dtype=np.int32).view(np.int64)[0])
             uoff = int(np.array(rec[2:4], dtype=np.int32).view(np.int64)[0])
             (sn, first, k, r, rptr, signal, blob, blob_len16, nslev, nseg, nnz, gen, o_segstart, o_seglen, o_colptr, o_rows, ea_begin, ea_end,
-             col_ptr, row_ptr, nchild, parent_sst) = (int(v) for v in rec[4:26])
+             col_ptr, row_ptr, nchild, parent_sst, o_rowptr, o_rcol, o_rpos, _pad) = (int(v) for v in rec[4:30])
             assert blob % 8 == 0 and gen >= last_gen
             last_gen = gen
             b = blob_all[blob : blob + 8 * blob_len16]
@@ -61,6 +61,18 @@ class Emulated:
             colptr = b[o_colptr : o_colptr + k + 1]
             rows = b[o_rows : o_rows + nnz]
             assert slvl[0] == 0 and slvl[-1] == nseg and colptr[0] == 0 and colptr[-1] == nnz
+            rowptr = b[o_rowptr : o_rowptr + k + r + 1]
+            rcol = b[o_rcol : o_rcol + nnz - k]
+            rpos = b[o_rpos : o_rpos + nnz - k]
+            assert rowptr[0] == 0 and rowptr[-1] == nnz - k
+            # the row view holds exactly the off-diagonal entries, every row with ascending columns
+            seen = np.zeros(nnz, dtype=bool)
+            for i in range(k + r):
+                cs = rcol[rowptr[i] : rowptr[i + 1]]
+                assert np.all(np.diff(cs) > 0) and np.all(rows[rpos[rowptr[i] : rowptr[i + 1]]] == i)
+                assert np.all((colptr[cs] < rpos[rowptr[i] : rowptr[i + 1]]) & (rpos[rowptr[i] : rowptr[i + 1]] < colptr[cs + 1]))
+                seen[rpos[rowptr[i] : rowptr[i + 1]]] = True
+            assert seen.sum() == nnz - k and not seen[colptr[:-1]].any()
             assert np.array_equal(colptr, p["sst_colptr"][col_ptr : col_ptr + k + 1])
             assert np.array_equal(rows, p["sst_rows"][row_ptr : row_ptr + nnz])
             assert sorted(np.concatenate([np.arange(s0, s0 + n) for s0, n in zip(segstart, seglen)]).tolist()) == list(range(k))
@@ -74,7 +86,7 @@ class Emulated:
             assert parent_sst == (signal if signal >= 0 and p["sn_sparse"][signal] else -1)
             self.sst.append(dict(Lptr=lptr, Uoff=uoff, sn=sn, first=first, k=k, r=r, Rptr=rptr, signal=signal, colptr=colptr, rows=rows,
                                  slvl=slvl, segstart=segstart, seglen=seglen, nslev=nslev, nnz=nnz, gen=gen, seg_lev=seg_lev, seg_end=seg_end,
-                                 ea=(ea_begin, ea_end), nchild=nchild, parent_sst=parent_sst))
+                                 ea=(ea_begin, ea_end), nchild=nchild, parent_sst=parent_sst, rowptr=rowptr, rcol=rcol, rpos=rpos))
             self.is_sst[sn] = True
             assert p["sn_sparse"][sn] == 1
 
@@ -121,16 +133,22 @@ class Emulated:
             self.U[M["Uoff"] : M["Uoff"] + r * r] = Us
 
     def _sst_forward(self, M, yacc, yf):
-        k, r, colptr, rows = M["k"], M["r"], M["colptr"], M["rows"]
+        """k_sst_forward: every column GATHERS along its row (no atomics inside a subtree): x_j = b_j - sum_c l_jc x_c over
+        the entries of row j, which belong to earlier columns of the thread's own segment or to segments of lower levels;
+        the tail rows gather after the last level."""
+        k, r = M["k"], M["r"]
+        rowptr, rcol, rpos = M["rowptr"], M["rcol"], M["rpos"]
         vals = self.L[M["Lptr"] : M["Lptr"] + M["nnz"]]
         x = np.concatenate([yacc[M["first"] : M["first"] + k], np.zeros(r)])
         for lev in range(M["nslev"]):
             for j0, j1 in self._sst_segments(M, lev):
                 for j in range(j0, j1):
-                    for a in range(colptr[j] + 1, colptr[j + 1]):
-                        i = rows[a]
-                        assert (j < i < j1) or i >= k or M["seg_lev"][i] > lev  # plain store / atomic on a later level
-                        x[i] -= vals[a] * x[j]
+                    for e in range(rowptr[j], rowptr[j + 1]):
+                        c = rcol[e]
+                        assert (j0 <= c < j) or M["seg_lev"][c] < lev  # written by this thread or before the last barrier
+                        x[j] -= vals[rpos[e]] * x[c]
+        for i in range(k, k + r):
+            x[i] = -sum(vals[rpos[e]] * x[rcol[e]] for e in range(rowptr[i], rowptr[i + 1]))
         yf[M["first"] : M["first"] + k] = x[:k] / self.D[M["first"] : M["first"] + k]
         tail = self.p["Ridx"][M["Rptr"] : M["Rptr"] + r]
         np.add.at(yacc, tail, x[k:])

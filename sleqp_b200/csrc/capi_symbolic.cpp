@@ -384,7 +384,7 @@ b200_symbolic_export(const b200_symbolic* s, const char* field, void* out, int64
   }
   if (f == "sst")
   {
-    static_assert(sizeof(SstMeta) == 26 * sizeof(int), "SstMeta layout");
+    static_assert(sizeof(SstMeta) == 30 * sizeof(int), "SstMeta layout");
     return export_vec(P.sst, out, count);
   }
   if (f == "stages")

@@ -75,8 +75,11 @@ struct SstMeta
   int col_ptr, row_ptr;                        // host copies: offsets into Plan::sst_colptr / sst_rows (32-bit)
   int nchild;                                  // child subtrees: signals the forward sweep waits for
   int parent_sst;                              // parent supernode if that is a sparse subtree (the backward sweep waits for its flag), else -1
+  int o_rowptr, o_rcol, o_rpos;                // the off-diagonal entries by ROW (forward sweep: a column gathers): row pointers over
+                                               // the k + r front rows, per entry its column and its position in the values
+  int pad_;
 };
-static_assert(sizeof(SstMeta) == 104, "SstMeta layout");
+static_assert(sizeof(SstMeta) == 120, "SstMeta layout");
 
 // kinds of update tasks
 enum

@@ -38,6 +38,9 @@ struct SstShared
   const u16* seglen;
   const u16* colptr;   // k + 1
   const u16* rows;     // nnz, front-local, diagonal first
+  const u16* rowptr;   // k + r + 1: the off-diagonal entries by row ...
+  const u16* rcol;     // ... their columns (ascending inside a row)
+  const u16* rpos;     // ... their positions in vals
 };
 
 // Bulk copy global -> shared in 16-byte pieces with eight loads per thread in flight before the first store: the
@@ -87,6 +90,9 @@ sst_stage(double* smem, const SstMeta& M, const u16* __restrict__ blob_all, cons
   S.seglen    = blob + M.o_seglen;
   S.colptr    = blob + M.o_colptr;
   S.rows      = blob + M.o_rows;
+  S.rowptr    = blob + M.o_rowptr;
+  S.rcol      = blob + M.o_rcol;
+  S.rpos      = blob + M.o_rpos;
   stage16(S.vals, Lg, nv / 2);
   stage16(blob, blob_all + M.blob, M.blob_len16);
   return S;
@@ -264,10 +270,13 @@ k_sst_factor(const SstMeta* __restrict__ metas,
   }
 }
 
-// forward: inside the subtree y = L^-1 b segment level by segment level (a column that is done pushes its multiples
-// down its entries: plain stores inside the thread's own segment, atomics above it), yf = D^-1 y; the rows of the
-// ancestors receive their share through atomics on the global accumulator, then the dense parent's dependency counter
-// is signalled (the dataflow kernel that follows waits on it like on any child)
+// forward: inside the subtree y = L^-1 b segment level by segment level. A column GATHERS along its row,
+// x_j = b_j - sum_c l_jc x_c: the entries of row j belong to earlier columns of the thread's own segment or to segments
+// of lower levels, so nothing inside a subtree needs an atomic (shared-memory FP64 atomics are compare-and-swap loops,
+// ATOMS.CAST.SPIN: the scatter form of this loop spent 7.8 us in the seven levels of a 976-column subtree, measured
+// with %globaltimer) and the sums of a subtree come out in a fixed order. yf = D^-1 y; the tail rows gather after the
+// last level and go to the global accumulator (atomics: several subtrees share an ancestor row), then the parent's
+// dependency counter is signalled (a dense parent's dataflow tasks and a parent subtree wait on the same counters)
 __global__ void __launch_bounds__(SST_THREADS)
 k_sst_forward(const SstMeta* __restrict__ metas,
               const u16* __restrict__ blob_all,
@@ -314,25 +323,28 @@ k_sst_forward(const SstMeta* __restrict__ metas,
     for (int q = S.slvl[lev] + threadIdx.x; q < S.slvl[lev + 1]; q += blockDim.x)
     {
       const int j0 = S.segstart[q], j1 = j0 + S.seglen[q];
+      int e        = S.rowptr[j0];
       for (int j = j0; j < j1; ++j)
       {
-        const double y = x[j];
-        for (int a = S.colptr[j] + 1; a < S.colptr[j + 1]; ++a)
+        const int e1 = S.rowptr[j + 1];
+        double acc   = x[j];
+        for (; e < e1; ++e)
         {
-          const int i    = S.rows[a];
-          const double u = -S.vals[a] * y;
-          if (i < j1)
-          {
-            x[i] += u; // a later column of this thread's own segment
-          }
-          else
-          {
-            smem_add(x + i, u);
-          }
+          acc -= S.vals[S.rpos[e]] * x[S.rcol[e]];
         }
+        x[j] = acc;
       }
     }
     __syncthreads();
+  }
+  for (int q = threadIdx.x; q < r; q += blockDim.x)
+  {
+    double acc = 0.0;
+    for (int e = S.rowptr[k + q]; e < S.rowptr[k + q + 1]; ++e)
+    {
+      acc -= S.vals[S.rpos[e]] * x[S.rcol[e]];
+    }
+    x[k + q] = acc; // only this thread reads it again (below)
   }
   for (int q = threadIdx.x; q < k; q += blockDim.x)
   {
@@ -344,10 +356,11 @@ k_sst_forward(const SstMeta* __restrict__ metas,
   }
   if (M.signal >= 0)
   {
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0)
     {
+      // cumulativity: the barrier ordered the CTA's stores and atomics before this thread's release fence
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
       atomicAdd(cnt + M.signal, 1);
     }
   }
@@ -420,10 +433,10 @@ k_sst_backward(const SstMeta* __restrict__ metas,
   }
   if (M.nchild > 0)
   {
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0)
     {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
       atomicAdd(done + M.sn, 1);
     }
   }

@@ -1872,6 +1872,49 @@ analyze(int n, int nnz, const int* colptr, const int* rowidx, const double* val,
       P.sst_blob.push_back((unsigned short)v);
     }
     pad8(P.sst_blob);
+    {
+      // the same entries by row (diagonal left out), columns ascending: what a column gathers in the forward sweep
+      std::vector<int> rptr((size_t)(k + r) + 1, 0);
+      for (int c = 0; c < k; ++c)
+      {
+        for (int q = colptr[(size_t)c] + 1; q < colptr[(size_t)c + 1]; ++q)
+        {
+          ++rptr[(size_t)rowloc[(size_t)q] + 1];
+        }
+      }
+      for (int i = 0; i < k + r; ++i)
+      {
+        rptr[(size_t)i + 1] += rptr[(size_t)i];
+      }
+      std::vector<int> rcol((size_t)rptr[(size_t)(k + r)]), rpos(rcol.size()), fillp(rptr.begin(), rptr.end() - 1);
+      for (int c = 0; c < k; ++c) // columns ascending => ascending inside every row
+      {
+        for (int q = colptr[(size_t)c] + 1; q < colptr[(size_t)c + 1]; ++q)
+        {
+          const int o      = fillp[(size_t)rowloc[(size_t)q]]++;
+          rcol[(size_t)o] = c;
+          rpos[(size_t)o] = q;
+        }
+      }
+      M.o_rowptr = (int)P.sst_blob.size() - M.blob;
+      for (int v : rptr)
+      {
+        P.sst_blob.push_back((unsigned short)v);
+      }
+      pad8(P.sst_blob);
+      M.o_rcol = (int)P.sst_blob.size() - M.blob;
+      for (int v : rcol)
+      {
+        P.sst_blob.push_back((unsigned short)v);
+      }
+      pad8(P.sst_blob);
+      M.o_rpos = (int)P.sst_blob.size() - M.blob;
+      for (int v : rpos)
+      {
+        P.sst_blob.push_back((unsigned short)v);
+      }
+      pad8(P.sst_blob);
+    }
     M.blob_len16 = ((int)P.sst_blob.size() - M.blob) / 8;
     M.nslev      = nslev;
     M.nseg       = nseg;

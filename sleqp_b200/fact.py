@@ -53,7 +53,7 @@ PLAN_FIELDS = {
     **{k: np.int64 for k in "Rptr Lptr Wptr Sdest Sterm_ptr Uoff Tptr sst_ea_src".split()},
 }
 PLAN_STRUCTS = {"stages": 10, "ea_tasks": 2, "pan_tasks": 4, "upd_tasks": 7, "inv_tasks": 6,
-                "ffl_tasks": 16, "bfl_tasks": 16, "tr_tasks": 3, "sst": 26}  # int32 columns
+                "ffl_tasks": 16, "bfl_tasks": 16, "tr_tasks": 3, "sst": 30}  # int32 columns
 
 
 class Symbolic:
