@@ -59,6 +59,7 @@ struct NumericOverlap
 // sparse subtrees (sst.cu): factorization before the first stage of the dense schedule, forward sweep before the
 // forward dataflow kernel (signals the parents' counters), backward sweep after the backward dataflow kernel
 void configure_sst_kernels(int device);
+void dump_sst_trace(); // -DB200_SST_TRACE_BUILD only
 // the two ticket counters of the sparse-subtree sweeps inside SolveBuffers::flow (after the counters and tickets of
 // the dataflow sweeps; zeroed by k_pre with the rest)
 inline int

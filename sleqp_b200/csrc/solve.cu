@@ -1016,6 +1016,13 @@ solve_once(const DevPlan& dp, const NumericBuffers& nb, const SolveBuffers& sb, 
     lc.tick();
   }
   mark(4);
+#ifdef B200_SST_TRACE_BUILD
+  if (ev && std::getenv("B200_SST_TRACE"))
+  {
+    cudaStreamSynchronize(stream);
+    dump_sst_trace();
+  }
+#endif
 }
 
 static void

@@ -76,9 +76,13 @@ stage16(void* dst, const void* __restrict__ src, int n16)
   }
 }
 
-// carves the dynamic shared memory and loads the index blob and the values; the caller fills vec and synchronises
+// carves the dynamic shared memory and loads the values and the parts of the index blob a kernel needs; the caller
+// fills vec and synchronises. WHAT: 0 = everything, values by column (factorization); 1 = segments + row view, values by
+// row (forward sweep: Mt holds the off-diagonal values in row order); 2 = segments + column view, values by column
+// (backward sweep). The blob keeps its layout in shared memory, parts that are not needed are simply not copied.
+template <int WHAT>
 __device__ __forceinline__ SstShared
-sst_stage(double* smem, const SstMeta& M, const u16* __restrict__ blob_all, const double* __restrict__ Lg, int vec_len)
+sst_stage(double* smem, const SstMeta& M, const u16* __restrict__ blob_all, const double* __restrict__ values, int vec_len)
 {
   SstShared S;
   const int nv = (M.nnz + 1) & ~1, nx = (vec_len + 1) & ~1;
@@ -93,8 +97,23 @@ sst_stage(double* smem, const SstMeta& M, const u16* __restrict__ blob_all, cons
   S.rowptr    = blob + M.o_rowptr;
   S.rcol      = blob + M.o_rcol;
   S.rpos      = blob + M.o_rpos;
-  stage16(S.vals, Lg, nv / 2);
-  stage16(blob, blob_all + M.blob, M.blob_len16);
+  const u16* src = blob_all + M.blob;
+  if (WHAT == 0)
+  {
+    stage16(S.vals, values, nv / 2);
+    stage16(blob, src, M.blob_len16);
+  }
+  else if (WHAT == 1)
+  {
+    stage16(S.vals, values, ((M.nnz - M.k + 1) & ~1) / 2);
+    stage16(blob, src, M.o_colptr / 8);
+    stage16(blob + M.o_rowptr, src + M.o_rowptr, (M.o_rpos - M.o_rowptr) / 8);
+  }
+  else
+  {
+    stage16(S.vals, values, nv / 2);
+    stage16(blob, src, M.o_rowptr / 8);
+  }
   return S;
 }
 
@@ -140,6 +159,26 @@ take_ticket(int* ticket)
   return t;
 }
 
+// Phase stamps of the forward sweep (build with -DB200_SST_TRACE_BUILD, run profiles/prof_driver.py with B200_SST_TRACE=1):
+// %globaltimer at the phase boundaries of the CTAs with tickets 0 and 300 and of the first subtree that has children
+#ifdef B200_SST_TRACE_BUILD
+__device__ unsigned long long g_sst_trace[4 * 8];
+__device__ __forceinline__ unsigned long long
+gtime()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define SST_TR(which, ph)                          \
+  if (threadIdx.x == 0 && (which) >= 0)            \
+  {                                                \
+    g_sst_trace[(which) * 8 + (ph)] = gtime();     \
+  }
+#else
+#define SST_TR(which, ph)
+#endif
+
 __device__ __forceinline__ void
 smem_add(double* p, double v)
 {
@@ -154,6 +193,7 @@ k_sst_factor(const SstMeta* __restrict__ metas,
              const long long* __restrict__ ea_src,
              const int* __restrict__ ea_dst,
              double* __restrict__ L,
+             double* __restrict__ Mt,
              double* __restrict__ U,
              double* __restrict__ D,
              double* __restrict__ Dinv,
@@ -164,7 +204,7 @@ k_sst_factor(const SstMeta* __restrict__ metas,
   const SstMeta M = metas[blockIdx.x];
   const int k = M.k, r = M.r;
   double* Lg        = L + M.Lptr;
-  const SstShared S = sst_stage(sst_smem, M, blob_all, Lg, r * r); // vals = assembled entries of S, zeros in the fill
+  const SstShared S = sst_stage<0>(sst_smem, M, blob_all, Lg, r * r); // vals = assembled entries of S, zeros in the fill
   double* vals      = S.vals;
   double* Us        = S.vec;
   for (int q = threadIdx.x; q < r * r; q += blockDim.x)
@@ -259,6 +299,13 @@ k_sst_factor(const SstMeta* __restrict__ metas,
   {
     Lg[q] = vals[q];
   }
+  // the off-diagonal entries once more in row order, where the inverse panels of a dense supernode would be: what the
+  // forward sweep streams (a column gathers along its row; no indirection through value positions there)
+  double* Rg = Mt + M.Lptr;
+  for (int q = threadIdx.x; q < M.nnz - k; q += blockDim.x)
+  {
+    Rg[q] = vals[S.rpos[q]];
+  }
   double* Ug = U + M.Uoff;
   for (int q = threadIdx.x; q < r * r; q += blockDim.x)
   {
@@ -289,10 +336,23 @@ k_sst_forward(const SstMeta* __restrict__ metas,
               int* __restrict__ ticket)
 {
   extern __shared__ double sst_smem[];
-  const SstMeta M = metas[take_ticket(ticket)]; // children (earlier generations) get the lower tickets
+#ifdef B200_SST_TRACE_BUILD
+  const unsigned long long T0 = gtime();
+#endif
+  const int tk    = take_ticket(ticket);
+  const SstMeta M = metas[tk]; // children (earlier generations) get the lower tickets
   const int k = M.k, r = M.r;
-  const SstShared S = sst_stage(sst_smem, M, blob_all, L + M.Lptr, k + r);
+#ifdef B200_SST_TRACE_BUILD
+  const int W = tk == 0 ? 0 : (tk == 300 ? 1 : (M.nchild > 0 ? 2 : -1));
+  if (threadIdx.x == 0 && W >= 0)
+  {
+    g_sst_trace[W * 8 + 0] = T0;
+  }
+#endif
+  SST_TR(W, 1) // ticket + record
+  const SstShared S = sst_stage<1>(sst_smem, M, blob_all, L + M.Lptr, k + r); // L: here the row-ordered copy (Mt)
   double* x         = S.vec;
+  SST_TR(W, 2) // structure and values staged
   if (M.nchild > 0)
   {
     // child subtrees of earlier generations run in this very launch under lower tickets, i.e. they are already
@@ -318,6 +378,7 @@ k_sst_forward(const SstMeta* __restrict__ metas,
     }
   }
   __syncthreads();
+  SST_TR(W, 3) // (children waited for,) right-hand side in shared memory
   for (int lev = 0; lev < M.nslev; ++lev)
   {
     for (int q = S.slvl[lev] + threadIdx.x; q < S.slvl[lev + 1]; q += blockDim.x)
@@ -328,21 +389,43 @@ k_sst_forward(const SstMeta* __restrict__ metas,
       {
         const int e1 = S.rowptr[j + 1];
         double acc   = x[j];
-        for (; e < e1; ++e)
+        // four entries at a time: columns and values first (independent of x), then the gathers, then the products --
+        // two shared-memory round trips per chunk instead of two per entry
+        while (e < e1)
         {
-          acc -= S.vals[S.rpos[e]] * x[S.rcol[e]];
+          int c[4];
+          double v[4], xv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+          {
+            c[u] = e + u < e1 ? (int)S.rcol[e + u] : j;
+            v[u] = e + u < e1 ? S.vals[e + u] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+          {
+            xv[u] = x[c[u]];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+          {
+            acc -= v[u] * xv[u];
+          }
+          e += 4;
         }
+        e    = e1;
         x[j] = acc;
       }
     }
     __syncthreads();
   }
+  SST_TR(W, 4) // levels
   for (int q = threadIdx.x; q < r; q += blockDim.x)
   {
     double acc = 0.0;
     for (int e = S.rowptr[k + q]; e < S.rowptr[k + q + 1]; ++e)
     {
-      acc -= S.vals[S.rpos[e]] * x[S.rcol[e]];
+      acc -= S.vals[e] * x[S.rcol[e]];
     }
     x[k + q] = acc; // only this thread reads it again (below)
   }
@@ -364,6 +447,7 @@ k_sst_forward(const SstMeta* __restrict__ metas,
       atomicAdd(cnt + M.signal, 1);
     }
   }
+  SST_TR(W, 5) // tails, stores, signal
 }
 
 // backward: x_j = yf_j - sum_i l_ij x_i over the entries of column j; segment levels from the root of the subtree
@@ -381,7 +465,7 @@ k_sst_backward(const SstMeta* __restrict__ metas,
   extern __shared__ double sst_smem[];
   const SstMeta M = metas[gridDim.x - 1 - take_ticket(ticket)]; // parents (later generations) get the lower tickets
   const int k = M.k, r = M.r;
-  const SstShared S = sst_stage(sst_smem, M, blob_all, L + M.Lptr, k + r);
+  const SstShared S = sst_stage<2>(sst_smem, M, blob_all, L + M.Lptr, k + r);
   double* x         = S.vec;
   {
     double t[(SST_MAX_COLS + SST_THREADS - 1) / SST_THREADS];
@@ -417,12 +501,30 @@ k_sst_backward(const SstMeta* __restrict__ metas,
       const int j0 = S.segstart[q];
       for (int j = j0 + S.seglen[q] - 1; j >= j0; --j)
       {
-        double s = x[j];
-        for (int a = S.colptr[j] + 1; a < S.colptr[j + 1]; ++a)
+        const int a1 = S.colptr[j + 1];
+        double acc   = x[j];
+        for (int a = S.colptr[j] + 1; a < a1; a += 4) // chunks of four like the forward sweep
         {
-          s -= S.vals[a] * x[S.rows[a]];
+          int i[4];
+          double v[4], xv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+          {
+            i[u] = a + u < a1 ? (int)S.rows[a + u] : j;
+            v[u] = a + u < a1 ? S.vals[a + u] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+          {
+            xv[u] = x[i[u]];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+          {
+            acc -= v[u] * xv[u];
+          }
         }
-        x[j] = s;
+        x[j] = acc;
       }
     }
     __syncthreads();
@@ -440,6 +542,25 @@ k_sst_backward(const SstMeta* __restrict__ metas,
       atomicAdd(done + M.sn, 1);
     }
   }
+}
+
+void
+dump_sst_trace()
+{
+#ifdef B200_SST_TRACE_BUILD
+  unsigned long long h[32];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_sst_trace, sizeof(h));
+  for (int w = 0; w < 3; ++w)
+  {
+    std::fprintf(stderr, "[sst trace %d] start %+lld ns:", w, (long long)(h[w * 8] - h[0]));
+    for (int ph = 1; ph < 6; ++ph)
+    {
+      std::fprintf(stderr, " +%lld", (long long)(h[w * 8 + ph] - h[w * 8]));
+    }
+    std::fprintf(stderr, "  (ticket+record, staged, rhs, levels, end)\n");
+  }
+#endif
 }
 
 void
@@ -468,7 +589,7 @@ enqueue_sst_factor(const DevPlan& dp, const NumericBuffers& nb, cudaStream_t str
     {
       continue;
     }
-    k_sst_factor<<<gp[g + 1] - gp[g], SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p + gp[g], dp.sst_blob.p, dp.sst_ea_src.p, dp.sst_ea_dst.p, nb.L, nb.U, nb.D, nb.Dinv, nb.scal,
+    k_sst_factor<<<gp[g + 1] - gp[g], SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p + gp[g], dp.sst_blob.p, dp.sst_ea_src.p, dp.sst_ea_dst.p, nb.L, nb.Mt, nb.U, nb.D, nb.Dinv, nb.scal,
                                                                                       nb.n_perturbed);
     lc.tick("sst");
     B200_CUDA(cudaGetLastError());
@@ -485,7 +606,7 @@ enqueue_sst_forward(const DevPlan& dp, const NumericBuffers& nb, const SolveBuff
     return;
   }
   int* const ticket = dp.plan->sst_gen_ptr.size() > 2 ? sb.flow + sst_ticket_offset(dp.plan->nsuper) : nullptr;
-  k_sst_forward<<<n, SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p, dp.sst_blob.p, dp.Ridx.p, nb.L, nb.Dinv, sb.y, sb.yf, sb.flow, ticket);
+  k_sst_forward<<<n, SST_THREADS, dp.plan->sst_smem_bytes, stream>>>(dp.sst.p, dp.sst_blob.p, dp.Ridx.p, nb.Mt, nb.Dinv, sb.y, sb.yf, sb.flow, ticket);
   lc.tick();
   B200_CUDA(cudaGetLastError());
 }
