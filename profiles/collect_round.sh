@@ -22,6 +22,10 @@ full ncu_full_k_pre_config3 '^k_pre' 2 2 2
 full ncu_full_k_post_config3 '^k_post' 2 2 2
 full ncu_full_k_sst_factor_config3 '^k_sst_factor' 0 2 2
 full ncu_full_k_flow_config2 'k_flow' 4 2 1   # one forward, one backward launch (split by profiles/split_ncu_csv.py)
+for tool in memcheck racecheck; do
+  timeout 900 compute-sanitizer --tool $tool python profiles/sanitize.py > $O/sanitizer_$tool.txt 2>&1
+  tail -3 $O/sanitizer_$tool.txt
+done
 python - <<'PY' > $O/summary.txt 2>&1
 import json, glob, sys
 for f in sorted(glob.glob(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/r02/bench_*.json")):
