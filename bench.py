@@ -650,8 +650,33 @@ def pin_rank_to_cores(rank, world):
         return None
     try:
         cores = sorted(os.sched_getaffinity(0))
-        per = max(1, len(cores) // world)
-        mine = cores[rank * per:(rank + 1) * per] or cores
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        mine = None
+        try:
+            # the cores next to this rank's GPU (same NUMA node / PCIe root): page-locked host buffers are first touched
+            # there, so the copy engines do not cross the socket interconnect. Ranks whose GPUs share a node split its cores.
+            import pynvml
+
+            pynvml.nvmlInit()
+            words = (max(cores) // 64) + 1
+
+            def near(gpu):
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+                mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+                return tuple(c for c in cores if (mask[c // 64] >> (c % 64)) & 1)
+
+            sets = [near(g) for g in range(world)]
+            peers = [g for g in range(world) if sets[g] == sets[local]]
+            node = list(sets[local])
+            if node:
+                per = max(1, len(node) // len(peers))
+                i = peers.index(local)
+                mine = node[i * per:(i + 1) * per] or node
+        except Exception:
+            mine = None
+        if not mine:
+            per = max(1, len(cores) // world)
+            mine = cores[rank * per:(rank + 1) * per] or cores
         os.sched_setaffinity(0, mine)
         os.environ["B200_HOST_THREADS"] = str(len(mine))
         os.environ["B200_ND_THREADS"] = str(len(mine))
