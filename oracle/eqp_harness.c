@@ -692,15 +692,16 @@ main(int argc, char** argv)
   const SleqpMat* K = NULL;
   (void)K;
   const double ms = t_total / steps;
-  // bytes over PCIe per step (counted from the vectors that cross): K values in; per aug_jac solve a sparse right-hand
-  // side in (8 B values, 4 B indices unless contiguous) and a sparsified slice out (12 B per entry, copied at full
-  // length); the TR solve: gradient in (12 B), step out (8 B) -- or, with the reference's Steihaug loop, one
-  // projection (12 n in, 12 n out) per iteration
+  // bytes over PCIe per step (counted from the vectors that cross): K / Jacobian values in; per aug_jac solve a sparse
+  // right-hand side in (8 B values; the indices of a contiguous run stay on the host) and a sparsified slice out (12 B
+  // per entry, copied at full length); the TR solve: gradient in (8 B, contiguous), sparse step out (12 B) -- or, with
+  // the reference's Steihaug loop, one projection (12 n in, 12 n out) per iteration; the device mirror of the Jacobian:
+  // its values in, x in (8 B), the multipliers in (12 B, sparse), J^T v out (12 B, sparsified), J x out (8 B)
   const double nnzK = (double)n + 3. * m; // order of magnitude only for chain; exact value is printed by bench.py's C-ABI leg
   (void)nnzK;
-  const long long h2d = 8LL * sleqp_mat_nnz(J) + 8LL * n /* diag */ + 8LL * ws_size + 12LL * n
-                        + (steihaug ? 12LL * n * (cg_iters + 1) : 12LL * n + (hessian ? 0 : 8LL * n * cg_iters));
-  const long long d2h = 12LL * n + 12LL * ws_size + (steihaug ? 12LL * n * (cg_iters + 1) : 8LL * n + (hessian ? 0 : 8LL * n * cg_iters));
+  const long long h2d = 8LL * sleqp_mat_nnz(J) + 8LL * n /* diag */ + 8LL * ws_size + 8LL * n
+                        + (steihaug ? 12LL * n * (cg_iters + 1) : 8LL * n + (hessian ? 0 : 8LL * n * cg_iters));
+  const long long d2h = 12LL * n + 12LL * ws_size + (steihaug ? 12LL * n * (cg_iters + 1) : 12LL * n + (hessian ? 0 : 8LL * n * cg_iters));
   printf("{\"driver\": \"eqp_step (reference aug_jac/TR code over the B200 glue)\", \"problem\": \"%s\", \"size\": %d, \"n\": %d, \"m\": %d, "
          "\"ws_size\": %d, \"N\": %d, \"backend\": \"%s\", \"aug_jac\": \"%s\", \"tr_solver\": \"%s\", \"cg_iters_cap\": %d, \"cg_iterations\": %d, \"cg_exit\": %d, "
          "\"steps\": %d, \"warmup\": %d, \"ms_per_step\": %.6f, \"iters_per_s\": %.6f, \"set_iterate_ms\": %.6f, \"two_solves_ms\": %.6f, "
@@ -714,7 +715,7 @@ main(int argc, char** argv)
          steihaug ? "reference steihaug_solver.c over SleqpFact B200" : "tr_b200.c (device CG, Hessian as a device matrix)", cg_iters, cg_done, cg_exit,
          steps, warm, ms, 1e3 / ms, t_set / steps, t_solves / steps, t_solves / steps / 2.,
          hostspmv ? "reference sleqp_mat_mult_vec(_trans) on the host" : "sparse/mat_b200.c (device mirror, refreshed every step)", t_spmv / steps, t_tr / steps,
-         h2d + (hostspmv ? 0 : 12LL * sleqp_mat_nnz(J) + 12LL * n + 12LL * (m / 100 + 1)), d2h + (hostspmv ? 0 : 8LL * n + 8LL * m));
+         h2d + (hostspmv ? 0 : 8LL * sleqp_mat_nnz(J) + 8LL * n + 12LL * (m / 100 + 1)), d2h + (hostspmv ? 0 : 12LL * n + 8LL * m));
   return 0;
 }
 

@@ -470,6 +470,8 @@ cg_solve_impl(b200_cg* C,
     B200_CUDA(cudaMemsetAsync(C->z.p, 0, sizeof(double) * (size_t)n, s));
     B200_CUDA(cudaMemsetAsync(rfull, 0, sizeof(double) * (size_t)N, s));
     // r0 = gradient (sparse host vector -> dense device vector)
+    bool g_contig = false;
+    int g_first   = 0;
     if (nnz_g > 0)
     {
       C->h_val.reserve((size_t)nnz_g);
@@ -478,17 +480,27 @@ cg_solve_impl(b200_cg* C,
       C->g_idx.reserve((size_t)nnz_g);
       const double* src_val = g_val;
       const int* src_idx    = g_idx;
-      if (!is_pinned_host(g_val, sizeof(double) * (size_t)nnz_g) || !is_pinned_host(g_idx, sizeof(int) * (size_t)nnz_g)) // page-locked caller arrays are DMA'd as they are
+      // ascending indices (pub_vec.h:13-14): a dense gradient is a contiguous run and its indices stay on the host
+      g_contig = (g_idx[nnz_g - 1] - g_idx[0]) == nnz_g - 1;
+      g_first  = g_idx[0];
+      const bool pinned_in = is_pinned_host(g_val, sizeof(double) * (size_t)nnz_g) && (g_contig || is_pinned_host(g_idx, sizeof(int) * (size_t)nnz_g));
+      if (!pinned_in) // page-locked caller arrays are DMA'd as they are
       {
         std::memcpy(C->h_val.p, g_val, sizeof(double) * (size_t)nnz_g);
-        std::memcpy(C->h_idx.p, g_idx, sizeof(int) * (size_t)nnz_g);
         src_val = C->h_val.p;
-        src_idx = C->h_idx.p;
+        if (!g_contig)
+        {
+          std::memcpy(C->h_idx.p, g_idx, sizeof(int) * (size_t)nnz_g);
+          src_idx = C->h_idx.p;
+        }
       }
       B200_CUDA(cudaMemcpyAsync(C->g_val.p, src_val, sizeof(double) * (size_t)nnz_g, cudaMemcpyHostToDevice, s));
-      B200_CUDA(cudaMemcpyAsync(C->g_idx.p, src_idx, sizeof(int) * (size_t)nnz_g, cudaMemcpyHostToDevice, s));
+      if (!g_contig)
+      {
+        B200_CUDA(cudaMemcpyAsync(C->g_idx.p, src_idx, sizeof(int) * (size_t)nnz_g, cudaMemcpyHostToDevice, s));
+      }
       LaunchCounter lc;
-      enqueue_scatter_rhs(rfull, N, nnz_g, C->g_idx.p, 0, C->g_val.p, s, lc);
+      enqueue_scatter_rhs(rfull, N, nnz_g, g_contig ? nullptr : C->g_idx.p, g_first, C->g_val.p, s, lc);
     }
     double* r = rfull;
     double* g = gfull;
@@ -595,7 +607,7 @@ cg_solve_impl(b200_cg* C,
       if (nnz_g > 0)
       {
         LaunchCounter lc;
-        enqueue_scatter_rhs(scratch_grad, n, nnz_g, C->g_idx.p, 0, C->g_val.p, s, lc);
+        enqueue_scatter_rhs(scratch_grad, n, nnz_g, g_contig ? nullptr : C->g_idx.p, g_first, C->g_val.p, s, lc);
       }
       double a[3], b[3];
       dot3(C, p_dev, scratch_Hp, a);
@@ -730,7 +742,7 @@ cg_solve_impl(b200_cg* C,
             if (nnz_g > 0)
             {
               LaunchCounter lc;
-              enqueue_scatter_rhs(z_new, n, nnz_g, C->g_idx.p, 0, C->g_val.p, s, lc);
+              enqueue_scatter_rhs(z_new, n, nnz_g, g_contig ? nullptr : C->g_idx.p, g_first, C->g_val.p, s, lc);
             }
             dot3(C, z_new, d_cur, gs);
             dot3(C, z_cur, C->Bd.p, zbd);
@@ -840,7 +852,7 @@ cg_solve_impl(b200_cg* C,
         if (nnz_g > 0)
         {
           LaunchCounter lc;
-          enqueue_scatter_rhs(z_new, n, nnz_g, C->g_idx.p, 0, C->g_val.p, s, lc);
+          enqueue_scatter_rhs(z_new, n, nnz_g, g_contig ? nullptr : C->g_idx.p, g_first, C->g_val.p, s, lc);
         }
         dot3(C, z_new, d_cur, gs);
         dot3(C, z_cur, C->Bd.p, zb);
