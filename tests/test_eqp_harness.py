@@ -170,6 +170,14 @@ def test_device_resident_projected_cg_matches_reference_iterates(golden, case):
         keep = np.nonzero(np.abs(step) > eps)[0]
         assert it_s == it and how_s == ProjectedCG.INTERIOR and 0 < len(keep) < p.n
         assert np.array_equal(si, keep) and np.abs(sv - step[keep]).max() <= 1e-8 * np.abs(step).max()
+    # a sparse gradient (indices not contiguous: they are uploaded; a contiguous run keeps them on the host) equals the same
+    # vector passed densely with explicit zeros
+    g2 = grad.copy()
+    g2[::3] = 0.0
+    nz = np.nonzero(g2)[0].astype(np.int32)
+    sa, ita, howa = cg.solve(p.n, nz, g2[nz], 1e8, 1e-4, 4 * N)
+    sb, itb, howb = cg.solve(p.n, gi, g2, 1e8, 1e-4, 4 * N)
+    assert ita == itb and howa == howb and np.abs(sa - sb).max() <= 1e-8 * max(1.0, np.abs(sb).max())
     # matrix-free Hessian (the reference's callback): same iterates with the products done on the host
     Hs = p.H.tocsr()
     cgf = ProjectedCG(f, None, hess_prod=lambda d: Hs @ d)
