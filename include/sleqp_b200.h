@@ -1,8 +1,9 @@
 /*
  * sleqp_b200.h -- C-ABI of libsleqp_b200.so, the B200-native sparse KKT backend for SLEQP.
  *
- * Plain C types only (no C++/torch types): this header is what the C11 host glue
- * `sleqp_b200/host/fact_b200.c` includes, exactly like fact_umfpack.c includes <umfpack.h>.
+ * Plain C types only (no C++/torch types): this header is what the C11 host glue under
+ * `sleqp_b200/host/` (fact/fact_b200.c, aug_jac/b200_aug_jac.c, tr/tr_b200.c, sparse/mat_b200.c)
+ * includes, exactly like fact_umfpack.c includes <umfpack.h>.
  *
  * Each entry point names the reference interface it stands behind (paths relative to the
  * reference tree, chrhansk/sleqp v1.0.2):
@@ -15,6 +16,11 @@
  *   SleqpFactCallbacks.free         fact_types.h:23,  fact.c:128-141, fact_umfpack.c:264-284
  *   sleqp_mat_mult_vec              src/main/sparse/mat.c:282-310
  *   sleqp_mat_mult_vec_trans        src/main/sparse/mat.c:312-363
+ *   SleqpAugJacCallbacks            src/main/aug_jac/aug_jac.h; set_iterate = fill_aug_jac + set_matrix
+ *     (b200_fact_set_kkt,           (aug_jac/standard_aug_jac.c:135-293), the three solves :306-435
+ *      b200_fact_solve_offset)
+ *   SleqpTRCallbacks                src/main/tr/tr_types.h:9-30; the loop restated: tr/steihaug_solver.c:223-496,
+ *     (b200_cg_*)                   tr_dual :187-221, Rayleigh bounds :150-183, boundary step tr/tr_util.c:9-50
  *
  * There is NO CPU fallback: every function that computes returns B200_ERR_CUDA when no
  * device is usable. Only the b200_symbolic_* entry points (host-side analysis, which the
@@ -48,7 +54,7 @@ enum
   B200_ERR_ARG         = 1, /* malformed input (dims, unsorted rows, ...) */
   B200_ERR_CUDA        = 2, /* no device / CUDA runtime failure */
   B200_ERR_SINGULAR    = 3, /* numerically singular KKT (Umfpack convention: error, fact_umfpack.c:66-82) */
-  B200_ERR_UNSUPPORTED = 4, /* structure outside the supported class (off-diagonal (1,1) block) */
+  B200_ERR_UNSUPPORTED = 4, /* structure outside the supported class (the Schur pattern would exceed 4e9 entries) */
   B200_ERR_STATE       = 5  /* call protocol violated (solve before set_matrix, ...) */
 };
 
