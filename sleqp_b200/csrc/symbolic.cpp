@@ -182,34 +182,65 @@ hash_pattern(int n, int nnz, const int* colptr, const int* rowidx, const double*
 uint64_t
 hash_kkt(int num_vars, int num_cons, int nnz_jac, const int* jac_cols, const int* jac_rows, const int* var_index, const int* cons_index, int ws_size, uint64_t* second)
 {
-  // four arrays, four threads when they are large (this is on the critical path of every set_iterate)
-  int hdr[4]    = {num_vars, num_cons, nnz_jac, ws_size};
-  Hash2 part[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-  auto run = [&](int q) {
-    const Hash2 seed = {(uint64_t)(0x4B4B54 + q), (uint64_t)(0xB2004B + q)};
-    switch (q)
-    {
-    case 0:
-      part[0] = hash_words(seed, jac_cols, sizeof(int) * (size_t)(num_vars + 1));
-      break;
-    case 1:
-      part[1] = hash_words(seed, jac_rows, sizeof(int) * (size_t)nnz_jac);
-      break;
-    case 2:
-      part[2] = hash_words(seed, var_index, sizeof(int) * (size_t)num_vars);
-      break;
-    default:
-      part[3] = hash_words(seed, cons_index, sizeof(int) * (size_t)num_cons);
-    }
+  // This is on the critical path of every set_iterate (16 MB at config 3). The four arrays are cut into pieces of at most
+  // 2 MB, every piece is hashed on its own (seeded with its number) and the piece hashes are combined in order: the
+  // value does not depend on how many threads share the pieces out.
+  int hdr[4] = {num_vars, num_cons, nnz_jac, ws_size};
+  struct Piece
+  {
+    const unsigned char* p;
+    size_t bytes;
   };
+  std::vector<Piece> pieces;
+  constexpr size_t PIECE = (size_t)2 << 20;
+  auto cut = [&](const int* a, size_t count) {
+    const unsigned char* p = (const unsigned char*)a;
+    size_t bytes           = sizeof(int) * count;
+    if (bytes == 0)
+    {
+      pieces.push_back({(const unsigned char*)"", 0}); // an empty array still takes its place in the sequence
+      return;
+    }
+    do
+    {
+      const size_t len = std::min(bytes, PIECE);
+      pieces.push_back({p, len});
+      p += len;
+      bytes -= len;
+    } while (bytes > 0);
+  };
+  cut(jac_cols, (size_t)num_vars + 1);
+  cut(jac_rows, (size_t)nnz_jac);
+  cut(var_index, (size_t)num_vars);
+  cut(cons_index, (size_t)num_cons);
+  std::vector<Hash2> part(pieces.size());
+  auto run = [&](size_t q) {
+    const Hash2 seed = {(uint64_t)(0x4B4B54 + q), (uint64_t)(0xB2004B + q)};
+    part[q]          = hash_words(seed, pieces[q].p, pieces[q].bytes);
+  };
+  int nthreads = 1;
   if ((long long)num_vars + nnz_jac >= 400000)
   {
-    std::thread pool[3];
-    for (int q = 1; q < 4; ++q)
+    nthreads = (int)std::min<size_t>(pieces.size(), (size_t)std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency())));
+    if (const char* ht = std::getenv("B200_HOST_THREADS"))
     {
-      pool[q - 1] = std::thread(run, q);
+      nthreads = std::max(1, std::min(nthreads, std::atoi(ht)));
     }
-    run(0);
+  }
+  if (nthreads > 1)
+  {
+    std::vector<std::thread> pool;
+    auto worker = [&](int w) {
+      for (size_t q = (size_t)w; q < pieces.size(); q += (size_t)nthreads)
+      {
+        run(q);
+      }
+    };
+    for (int w = 1; w < nthreads; ++w)
+    {
+      pool.emplace_back(worker, w);
+    }
+    worker(0);
     for (auto& th : pool)
     {
       th.join();
@@ -217,13 +248,13 @@ hash_kkt(int num_vars, int num_cons, int nnz_jac, const int* jac_cols, const int
   }
   else
   {
-    for (int q = 0; q < 4; ++q)
+    for (size_t q = 0; q < pieces.size(); ++q)
     {
       run(q);
     }
   }
   Hash2 h = hash_words({0x4B4B54, 0xB2004B}, hdr, sizeof(hdr));
-  for (int q = 0; q < 4; ++q)
+  for (size_t q = 0; q < pieces.size(); ++q)
   {
     h.a = mix64(h.a, part[q].a);
     h.b = mix64b(h.b, part[q].b);
