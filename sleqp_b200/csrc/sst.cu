@@ -185,6 +185,121 @@ smem_add(double* p, double v)
   atomicAdd(p, v); // shared-memory FP64 atomic
 }
 
+// Shared memory through 32-bit shared-window addresses and explicit ld.shared / st.shared: with pointers derived from the
+// dynamic shared array the compiler rebuilt the window base (S2R SR_CgaCtaId, the window of a CTA inside a cluster)
+// inside the loops. shared_addr is opaque to the optimiser on purpose (a volatile asm runs once, its result stays in a
+// register).
+__device__ __forceinline__ unsigned
+shared_addr(const void* p)
+{
+  unsigned a;
+  asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(p));
+  return a;
+}
+
+__device__ __forceinline__ double
+lds64(unsigned a)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+
+__device__ __forceinline__ int
+lds16(unsigned a)
+{
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return (int)v;
+}
+
+__device__ __forceinline__ void
+sts64(unsigned a, double v)
+{
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
+// One thread walks the columns of a segment: x_j -= sum over the entries of column j (backward: rows below the diagonal
+// through the column view) or of row j (forward: columns left of the diagonal through the row view) of val * x[idx].
+// Measured (clock64 around the walk of thread 0, config 3): 340 cycles per column of a 14-column leaf segment and
+// ~1,000 cycles for a single column with 15-26 entries, where the isolated latencies (profiles/micro/chain_latency.cu:
+// DFMA 8.7, ld.shared 28.8, st -> ld 39.5 cycles) predict 100-150; hand-pipelined variants (operands one or two columns
+// ahead) changed little or lost to register pressure, so the shared-memory round trips evidently take far longer than
+// in isolation while the other CTAs of the SM stage their subtrees. What is kept is what needs the fewest round trips
+// and instructions: short rows / columns (one or two entries: chains) take a lean scalar path -- address registers
+// stepped, the column just finished taken from a register, the next entry range loaded a column ahead; longer ones go
+// four entries at a time (indices and values first, then the gathers, then the products).
+// ptr / idx / vals / x: shared-window byte addresses of the arrays.
+template <bool FWD>
+__device__ __forceinline__ void
+sst_walk(unsigned ptr, unsigned idx, unsigned vals, unsigned x, int j0, int j1)
+{
+  int j          = FWD ? j0 : j1 - 1;
+  unsigned pj    = ptr + 2u * (unsigned)j; // &ptr[j]
+  unsigned xj    = x + 8u * (unsigned)j;   // &x[j]
+  int e          = lds16(pj) + (FWD ? 0 : 1);
+  int e1         = lds16(pj + 2u);
+  double prev    = 0.0;
+  int prevc      = -2;
+  for (int n = j1 - j0; n > 0; --n)
+  {
+    // entry range of the next column (forward: it begins where this one ends)
+    const unsigned pn = FWD ? pj + 2u : pj - 2u;
+    const int en      = n > 1 ? lds16(pn) + (FWD ? 0 : 1) : 0;
+    const int en1     = n > 1 ? lds16(pn + 2u) : 0;
+    double acc        = lds64(xj);
+    const int cnt     = e1 - e;
+    unsigned ai = idx + 2u * (unsigned)e, av = vals + 8u * (unsigned)e;
+    if (cnt <= 2)
+    {
+      if (cnt >= 1)
+      {
+        const int c    = lds16(ai);
+        const double v = lds64(av);
+        acc -= v * (c == prevc ? prev : lds64(x + 8u * (unsigned)c));
+      }
+      if (cnt == 2)
+      {
+        const int c    = lds16(ai + 2u);
+        const double v = lds64(av + 8u);
+        acc -= v * (c == prevc ? prev : lds64(x + 8u * (unsigned)c));
+      }
+    }
+    else
+    {
+      for (int left = cnt; left > 0; left -= 4, ai += 8u, av += 32u)
+      {
+        int c[4];
+        double v[4], xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+          c[u] = u < left ? lds16(ai + 2u * u) : -1;
+          v[u] = u < left ? lds64(av + 8u * u) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+          xv[u] = c[u] >= 0 ? lds64(x + 8u * (unsigned)c[u]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+          acc -= v[u] * xv[u];
+        }
+      }
+    }
+    sts64(xj, acc);
+    prev  = acc;
+    prevc = j;
+    j += FWD ? 1 : -1;
+    pj = pn;
+    xj = FWD ? xj + 8u : xj - 8u;
+    e  = en;
+    e1 = en1;
+  }
+}
+
 } // namespace
 
 __global__ void __launch_bounds__(SST_THREADS)
@@ -379,45 +494,23 @@ k_sst_forward(const SstMeta* __restrict__ metas,
   }
   __syncthreads();
   SST_TR(W, 3) // (children waited for,) right-hand side in shared memory
-  for (int lev = 0; lev < M.nslev; ++lev)
   {
-    for (int q = S.slvl[lev] + threadIdx.x; q < S.slvl[lev + 1]; q += blockDim.x)
+    const unsigned sv = shared_addr(S.vals);
+    const unsigned sx = sv + (unsigned)((const char*)x - (const char*)S.vals), sb = sv + (unsigned)((const char*)S.slvl - (const char*)S.vals);
+    const unsigned s_start = sb + 2u * (unsigned)M.o_segstart, s_len = sb + 2u * (unsigned)M.o_seglen, s_ptr = sb + 2u * (unsigned)M.o_rowptr,
+                   s_idx = sb + 2u * (unsigned)M.o_rcol;
+    int q0 = lds16(sb);
+    for (int lev = 0; lev < M.nslev; ++lev)
     {
-      const int j0 = S.segstart[q], j1 = j0 + S.seglen[q];
-      int e        = S.rowptr[j0];
-      for (int j = j0; j < j1; ++j)
+      const int q1 = lds16(sb + 2u * (unsigned)(lev + 1));
+      for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x)
       {
-        const int e1 = S.rowptr[j + 1];
-        double acc   = x[j];
-        // four entries at a time: columns and values first (independent of x), then the gathers, then the products --
-        // two shared-memory round trips per chunk instead of two per entry
-        while (e < e1)
-        {
-          int c[4];
-          double v[4], xv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-          {
-            c[u] = e + u < e1 ? (int)S.rcol[e + u] : j;
-            v[u] = e + u < e1 ? S.vals[e + u] : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-          {
-            xv[u] = x[c[u]];
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-          {
-            acc -= v[u] * xv[u];
-          }
-          e += 4;
-        }
-        e    = e1;
-        x[j] = acc;
+        const int j0 = lds16(s_start + 2u * (unsigned)q);
+        sst_walk<true>(s_ptr, s_idx, sv, sx, j0, j0 + lds16(s_len + 2u * (unsigned)q));
       }
+      q0 = q1;
+      __syncthreads();
     }
-    __syncthreads();
   }
   SST_TR(W, 4) // levels
   for (int q = threadIdx.x; q < r; q += blockDim.x)
@@ -494,40 +587,23 @@ k_sst_backward(const SstMeta* __restrict__ metas,
     x[k + q] = __ldcg(xg + Ridx[M.Rptr + q]);
   }
   __syncthreads();
-  for (int lev = M.nslev - 1; lev >= 0; --lev)
   {
-    for (int q = S.slvl[lev] + threadIdx.x; q < S.slvl[lev + 1]; q += blockDim.x)
+    const unsigned sv = shared_addr(S.vals);
+    const unsigned sx = sv + (unsigned)((const char*)x - (const char*)S.vals), sb = sv + (unsigned)((const char*)S.slvl - (const char*)S.vals);
+    const unsigned s_start = sb + 2u * (unsigned)M.o_segstart, s_len = sb + 2u * (unsigned)M.o_seglen, s_ptr = sb + 2u * (unsigned)M.o_colptr,
+                   s_idx = sb + 2u * (unsigned)M.o_rows;
+    int q1 = lds16(sb + 2u * (unsigned)M.nslev);
+    for (int lev = M.nslev - 1; lev >= 0; --lev)
     {
-      const int j0 = S.segstart[q];
-      for (int j = j0 + S.seglen[q] - 1; j >= j0; --j)
+      const int q0 = lds16(sb + 2u * (unsigned)lev);
+      for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x)
       {
-        const int a1 = S.colptr[j + 1];
-        double acc   = x[j];
-        for (int a = S.colptr[j] + 1; a < a1; a += 4) // chunks of four like the forward sweep
-        {
-          int i[4];
-          double v[4], xv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-          {
-            i[u] = a + u < a1 ? (int)S.rows[a + u] : j;
-            v[u] = a + u < a1 ? S.vals[a + u] : 0.0;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-          {
-            xv[u] = x[i[u]];
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-          {
-            acc -= v[u] * xv[u];
-          }
-        }
-        x[j] = acc;
+        const int j0 = lds16(s_start + 2u * (unsigned)q);
+        sst_walk<false>(s_ptr, s_idx, sv, sx, j0, j0 + lds16(s_len + 2u * (unsigned)q));
       }
+      q1 = q0;
+      __syncthreads();
     }
-    __syncthreads();
   }
   for (int q = threadIdx.x; q < k; q += blockDim.x)
   {
